@@ -1,0 +1,143 @@
+// Core plumbing of the rav1d_b200 library: error reporting, per-thread staging
+// arenas for the host-pointer entry points, and small device-memory helpers so
+// that a non-CUDA host (Rust FFI, Python ctypes) can drive the batch API.
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace rb200 {
+
+static thread_local char g_err[512];
+static rb200_error_cb g_cb = nullptr;
+static void *g_cb_cookie = nullptr;
+static thread_local int g_last_code = 0;
+
+int set_error(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    g_last_code = code;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    const char *base = strrchr(file, '/');
+    return set_error(e == cudaErrorMemoryAllocation ? -12 : -5, "CUDA error %d (%s) at %s:%d: %s", (int)e,
+                     cudaGetErrorString(e), base ? base + 1 : file, line, what);
+}
+
+// ------------------------------------------------------------ Staging
+Staging::~Staging() {
+    // Process teardown order vs. the CUDA runtime is undefined; leak on exit.
+}
+
+int Staging::begin(size_t dev_bytes, size_t host_bytes) {
+    if (!stream) {
+        RB_CUDA(cudaGetDevice(&device));
+        RB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    }
+    if (dev_bytes > dev_cap) {
+        if (dev) RB_CUDA(cudaFree(dev));
+        dev = nullptr;
+        size_t cap = dev_bytes < (1u << 20) ? (1u << 20) : dev_bytes * 2;
+        RB_CUDA(cudaMalloc((void **)&dev, cap));
+        dev_cap = cap;
+    }
+    if (host_bytes > host_cap) {
+        if (host) RB_CUDA(cudaFreeHost(host));
+        host = nullptr;
+        size_t cap = host_bytes < (1u << 20) ? (1u << 20) : host_bytes * 2;
+        RB_CUDA(cudaMallocHost((void **)&host, cap));
+        host_cap = cap;
+    }
+    dev_used = host_used = 0;
+    return 0;
+}
+
+void *Staging::dalloc(size_t bytes) {
+    size_t off = (dev_used + 255) & ~size_t(255);
+    if (off + bytes > dev_cap) return nullptr;
+    dev_used = off + bytes;
+    return dev + off;
+}
+void *Staging::halloc(size_t bytes) {
+    size_t off = (host_used + 63) & ~size_t(63);
+    if (off + bytes > host_cap) return nullptr;
+    host_used = off + bytes;
+    return host + off;
+}
+
+Staging &staging() {
+    static thread_local Staging s;
+    return s;
+}
+
+// ------------------------------------------------------------ DevRect
+int DevRect::upload(Staging &st, const void *host_row0, int64_t stride, size_t rb, int nrows) {
+    row_bytes = rb; rows = nrows; hstride = stride; hsrc = (const uint8_t *)host_row0;
+    dpitch = (int64_t)pitch_for(rb);
+    const size_t total = (size_t)dpitch * rows;
+    dptr = (uint8_t *)st.dalloc(total);
+    hstage = (uint8_t *)st.halloc(total);
+    if (!dptr || !hstage) return set_error(-12, "staging arena too small (%zu bytes)", total);
+    for (int y = 0; y < rows; y++) memcpy(hstage + (size_t)y * dpitch, hsrc + (int64_t)y * stride, rb);
+    RB_CUDA(cudaMemcpyAsync(dptr, hstage, total, cudaMemcpyHostToDevice, st.stream));
+    return 0;
+}
+int DevRect::download(Staging &st) {
+    RB_CUDA(cudaMemcpyAsync(hstage, dptr, (size_t)dpitch * rows, cudaMemcpyDeviceToHost, st.stream));
+    return 0;
+}
+void DevRect::finish(void *host_row0) {
+    uint8_t *d = (uint8_t *)host_row0;
+    for (int y = 0; y < rows; y++) memcpy(d + (int64_t)y * hstride, hstage + (size_t)y * dpitch, row_bytes);
+}
+
+}  // namespace rb200
+
+using namespace rb200;
+
+extern "C" int rb200_abi_version(void) { return RB200_ABI_VERSION; }
+
+extern "C" int rb200_init(int device) {
+    int n = 0;
+    RB_CUDA(cudaGetDeviceCount(&n));
+    if (n <= 0) return set_error(-19, "no CUDA device visible: rav1d_b200 has no CPU fallback");
+    if (device < 0) RB_CUDA(cudaGetDevice(&device));
+    if (device >= n) return set_error(-22, "device %d out of range (%d visible)", device, n);
+    RB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp p;
+    RB_CUDA(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10) return set_error(-19, "device %d is sm_%d%d; this library is built for sm_100a only", device, p.major, p.minor);
+    RB_CUDA(cudaFree(0));
+    return 0;
+}
+
+extern "C" const char *rb200_last_error(void) { return g_err; }
+
+extern "C" void rb200_set_error_callback(rb200_error_cb cb, void *cookie) { g_cb = cb; g_cb_cookie = cookie; }
+
+extern "C" void rb200_report_fatal(const char *where) {
+    if (g_cb) { g_cb(g_cb_cookie, g_last_code, g_err); return; }
+    fprintf(stderr, "rav1d_b200: fatal GPU error in %s: %s\n", where, g_err);
+    abort();
+}
+
+extern "C" int rb200_malloc(void **dptr, size_t bytes) { RB_CUDA(cudaMalloc(dptr, bytes)); return 0; }
+extern "C" int rb200_free(void *dptr) { RB_CUDA(cudaFree(dptr)); return 0; }
+extern "C" int rb200_malloc_host(void **hptr, size_t bytes) { RB_CUDA(cudaMallocHost(hptr, bytes)); return 0; }
+extern "C" int rb200_free_host(void *hptr) { RB_CUDA(cudaFreeHost(hptr)); return 0; }
+extern "C" int rb200_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream) {
+    RB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream)); return 0;
+}
+extern "C" int rb200_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream) {
+    RB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream)); return 0;
+}
+extern "C" int rb200_memset(void *dst, int value, size_t bytes, void *stream) {
+    RB_CUDA(cudaMemsetAsync(dst, value, bytes, (cudaStream_t)stream)); return 0;
+}
+extern "C" int rb200_stream_sync(void *stream) { RB_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); return 0; }

@@ -1,0 +1,273 @@
+// Inverse transform + add-to-destination ("itxfm_add") for sm_100a.
+//
+// Replaces Rav1dInvTxfmDSPContext.itxfm_add[19][17] (src/itx.rs:190-196; body
+// inv_txfm_add_rust src/itx.rs:64-188 == inv_txfm_add_c src/itx_tmpl.c:40-113,
+// WHT src/itx.rs:475-526 == src/itx_tmpl.c:173-193).
+//
+// Mapping: one GPU thread owns one row (first pass) and then one column (second
+// pass) of a transform block, with the whole 1-D transform unrolled into
+// registers (itx1d.cuh); the two passes meet in a padded shared-memory tile.
+// A block of W x H uses T = max(W, min(H,32)) threads; a 128-thread CTA holds
+// 128/T transform blocks.  Kernels are specialised per transform size; the
+// 1-D kind (DCT/ADST/flipADST/identity/WHT) is a warp-uniform runtime switch,
+// so the host buckets items by (size, type).  No tensor cores: this is an
+// integer butterfly network, not a contraction.
+#include "common.cuh"
+#include "itx1d.cuh"
+#include <string.h>
+#include <utility>
+
+namespace rb200 {
+
+// (w, h, shift) per RectTxfmSize, index = enum order of src/levels.rs:31-59.
+// shift values: src/itx.rs:439-457 == src/itx_tmpl.c:153-171.
+__host__ __device__ constexpr int tx_w(int tx) {
+    constexpr int W[19] = {4, 8, 16, 32, 64, 4, 8, 8, 16, 16, 32, 32, 64, 4, 16, 8, 32, 16, 64};
+    return W[tx];
+}
+__host__ __device__ constexpr int tx_h(int tx) {
+    constexpr int H[19] = {4, 8, 16, 32, 64, 8, 4, 16, 8, 32, 16, 64, 32, 16, 4, 32, 8, 64, 16};
+    return H[tx];
+}
+__host__ __device__ constexpr int tx_shift(int tx) {
+    constexpr int S[19] = {0, 1, 2, 2, 2, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2};
+    return S[tx];
+}
+
+// txtp -> 1-D kinds.  "A_B" = A vertical (columns, second pass), B horizontal
+// (rows, first pass): src/levels.rs:63-82, assignment src/itx.rs:978-1068.
+// packed 3-bit kinds per txtp (index order of RB200_* txtp enum):
+//   rows: DCT DCT ADST ADST DCT FLIPADST FLIPADST FLIPADST ADST IDENTITY IDENTITY DCT IDENTITY ADST IDENTITY FLIPADST WHT
+//   cols: DCT ADST DCT ADST FLIPADST DCT FLIPADST ADST FLIPADST IDENTITY DCT IDENTITY ADST IDENTITY FLIPADST IDENTITY WHT
+__host__ __device__ inline int txtp_row_kind(int txtp) { return (int)((0x44cb0d9490240ULL >> (3 * txtp)) & 7); }
+__host__ __device__ inline int txtp_col_kind(int txtp) { return (int)((0x469961a282208ULL >> (3 * txtp)) & 7); }
+
+static bool itx_valid(int tx, int txtp) {
+    if (tx < 0 || tx >= 19 || txtp < 0 || txtp >= 17) return false;
+    const int w = tx_w(tx), h = tx_h(tx), m = w > h ? w : h;
+    if (txtp == RB200_WHT_WHT) return tx == RB200_TX_4X4;
+    if (m == 64) return txtp == RB200_DCT_DCT;
+    if (m == 32) return txtp == RB200_DCT_DCT || txtp == RB200_IDTX;
+    if (w == 16 && h == 16) return txtp <= RB200_H_DCT;  // 12 types: no V/H (flip)ADST
+    return true;
+}
+
+template <int N>
+__device__ __forceinline__ void run_kind(int kind, int *x, int lo, int hi) {
+    if constexpr (N == 64) {
+        itx1d<64, T1_DCT>(x, lo, hi);
+    } else if constexpr (N == 32) {
+        if (kind == T1_DCT) itx1d<32, T1_DCT>(x, lo, hi);
+        else itx1d<32, T1_IDENTITY>(x, lo, hi);
+    } else {
+        switch (kind) {
+        case T1_DCT: itx1d<N, T1_DCT>(x, lo, hi); break;
+        case T1_ADST: itx1d<N, T1_ADST>(x, lo, hi); break;
+        case T1_FLIPADST: itx1d<N, T1_FLIPADST>(x, lo, hi); break;
+        case T1_IDENTITY: itx1d<N, T1_IDENTITY>(x, lo, hi); break;
+        default: if constexpr (N == 4) wht4(x); break;
+        }
+    }
+}
+
+template <int TX>
+struct ItxGeom {
+    static constexpr int W = tx_w(TX), H = tx_h(TX);
+    static constexpr int SW = W < 32 ? W : 32, SH = H < 32 ? H : 32;
+    static constexpr int T = W > SH ? W : SH;   // threads per transform block
+    static constexpr int CTA = 128;
+    static constexpr int PER_CTA = CTA / T;
+    static constexpr int PITCH = W + 1;         // padded row pitch (ints) -> conflict-free both passes
+    static constexpr int TILE = PITCH * SH;
+};
+
+template <typename BD, int TX>
+__global__ void __launch_bounds__(128)
+itx_add_kernel(Rb200Planes planes, const typename BD::coef *__restrict__ cf,
+               const Rb200ItxItem *__restrict__ items, int n_items, int bdmax) {
+    using G = ItxGeom<TX>;
+    using pixel = typename BD::pixel;
+    constexpr int W = G::W, H = G::H, SW = G::SW, SH = G::SH;
+    constexpr int shift = tx_shift(TX);
+    constexpr bool rect2 = (W * 2 == H) || (H * 2 == W);
+    __shared__ int tile[G::PER_CTA * G::TILE];
+
+    const int slot = threadIdx.x / G::T, lane = threadIdx.x % G::T;
+    const int idx = blockIdx.x * G::PER_CTA + slot;
+    const bool live = idx < n_items;
+    int *tl = tile + slot * G::TILE;
+
+    Rb200ItxItem it;
+    if (live) it = items[idx];
+    else { it.cf_off = 0; it.x = it.y = 0; it.plane = 0; it.tx = TX; it.txtp = 0; it.eob = 0; it.flags = 0; }
+
+    const int row_lo = BD::hbd ? (int)((unsigned)~bdmax << 7) : -32768;
+    const int col_lo = BD::hbd ? (int)((unsigned)~bdmax << 5) : -32768;
+    const int row_hi = ~row_lo, col_hi = ~col_lo;
+    const typename BD::coef *c = cf + it.cf_off;
+    const bool dconly = live && it.txtp == RB200_DCT_DCT && it.eob < 1;
+    const bool wht = it.txtp == RB200_WHT_WHT;
+
+    // ---- first pass: rows ----
+    if (live && !dconly && lane < SH) {
+        int x[W];
+        if (wht) {
+#pragma unroll
+            for (int i = 0; i < SW; i++) x[i] = (int)c[lane + i * SH] >> 2;
+        } else {
+#pragma unroll
+            for (int i = 0; i < SW; i++) {
+                const int v = c[lane + i * SH];
+                x[i] = rect2 ? (v * 181 + 128) >> 8 : v;
+            }
+        }
+        run_kind<W>(txtp_row_kind(it.txtp), x, row_lo, row_hi);
+        constexpr int rnd = (1 << shift) >> 1;
+        if (wht) {
+#pragma unroll
+            for (int i = 0; i < W; i++) tl[lane * G::PITCH + i] = x[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < W; i++) tl[lane * G::PITCH + i] = iclip((x[i] + rnd) >> shift, col_lo, col_hi);
+        }
+    }
+    __syncthreads();
+    if (!live || lane >= W) return;
+
+    // ---- second pass: columns, add to destination ----
+    const int64_t bstride = plane_stride(planes, it.plane);
+    pixel *dst = (pixel *)(plane_ptr(planes, it.plane) + (int64_t)it.y * bstride) + it.x + lane;
+    const int64_t pstride = bstride / (int64_t)sizeof(pixel);
+    if (dconly) {
+        // src/itx.rs:90-111
+        int dc = c[0];
+        if (rect2) dc = (dc * 181 + 128) >> 8;
+        dc = (dc * 181 + 128) >> 8;
+        dc = (dc + ((1 << shift) >> 1)) >> shift;
+        dc = (dc * 181 + 128 + 2048) >> 12;
+#pragma unroll 8
+        for (int i = 0; i < H; i++) dst[i * pstride] = (pixel)iclip((int)dst[i * pstride] + dc, 0, bdmax);
+        return;
+    }
+    int v[H];
+#pragma unroll
+    for (int i = 0; i < SH; i++) v[i] = tl[i * G::PITCH + lane];
+    run_kind<H>(txtp_col_kind(it.txtp), v, col_lo, col_hi);
+    if (wht) {
+#pragma unroll
+        for (int i = 0; i < H; i++) dst[i * pstride] = (pixel)iclip((int)dst[i * pstride] + v[i], 0, bdmax);
+    } else {
+#pragma unroll
+        for (int i = 0; i < H; i++) dst[i * pstride] = (pixel)iclip((int)dst[i * pstride] + ((v[i] + 8) >> 4), 0, bdmax);
+    }
+}
+
+template <typename BD, int TX>
+static int launch_one(const Rb200Planes &planes, const void *cf, const Rb200ItxItem *items, int n, int bdmax,
+                      cudaStream_t st) {
+    using G = ItxGeom<TX>;
+    if (n <= 0) return 0;
+    const int grid = (n + G::PER_CTA - 1) / G::PER_CTA;
+    itx_add_kernel<BD, TX><<<grid, G::CTA, 0, st>>>(planes, (const typename BD::coef *)cf, items, n, bdmax);
+    RB_LAUNCH_CHECK();
+    return 0;
+}
+
+template <typename BD>
+static int launch_tx(int tx, const Rb200Planes &planes, const void *cf, const Rb200ItxItem *items, int n, int bdmax,
+                     cudaStream_t st) {
+    switch (tx) {
+#define CASE(TX) case TX: return launch_one<BD, TX>(planes, cf, items, n, bdmax, st);
+        CASE(0) CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9)
+        CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16) CASE(17) CASE(18)
+#undef CASE
+    }
+    return set_error(-22, "itx: bad transform size %d", tx);
+}
+
+int itx_launch(int tx, const Rb200Planes &planes, const void *cf, const Rb200ItxItem *items, int n, int bdmax,
+               cudaStream_t st) {
+    return bdmax > 255 ? launch_tx<BD16>(tx, planes, cf, items, n, bdmax, st)
+                       : launch_tx<BD8>(tx, planes, cf, items, n, bdmax, st);
+}
+
+}  // namespace rb200
+
+using namespace rb200;
+
+// ---------------------------------------------------------------- C ABI
+extern "C" int rb200_itx_valid(int tx, int txtp) { return itx_valid(tx, txtp) ? 1 : 0; }
+
+extern "C" int rb200_itx_add_batch(const Rb200Planes *planes, const void *d_coef, const Rb200ItxItem *d_items,
+                                   const int32_t counts[19], int bitdepth_max, void *stream) {
+    if (!planes || !counts) return set_error(-22, "itx_add_batch: null argument");
+    int off = 0;
+    for (int tx = 0; tx < 19; tx++) {
+        const int n = counts[tx];
+        if (n < 0) return set_error(-22, "itx_add_batch: negative count");
+        if (n) {
+            int r = itx_launch(tx, *planes, d_coef, d_items + off, n, bitdepth_max, (cudaStream_t)stream);
+            if (r) return r;
+        }
+        off += n;
+    }
+    return 0;
+}
+
+// Host-pointer, synchronous, one transform block: exact semantics of one
+// itxfm_add[tx][txtp] call including zeroing of the consumed coefficients
+// (src/itx.rs:94 dc-only zeroes coeff[0]; :152-158 full path zeroes sw*sh).
+extern "C" int rb200_itxfm_add(int tx, int txtp, void *dst, ptrdiff_t stride, void *coeff, int eob,
+                               int bitdepth_max) {
+    if (!itx_valid(tx, txtp)) return set_error(-22, "itxfm_add: no such transform tx=%d txtp=%d", tx, txtp);
+    if (eob < 0 || !dst || !coeff) return set_error(-22, "itxfm_add: bad argument");
+    const bool hbd = bitdepth_max > 255;
+    const int w = tx_w(tx), h = tx_h(tx), sw = w < 32 ? w : 32, sh = h < 32 ? h : 32;
+    const size_t px = hbd ? 2 : 1, cs = hbd ? 4 : 2;
+    const size_t ncoef = (size_t)sw * sh;
+    Staging &st = staging();
+    int r = st.begin(DevRect::bytes_for(w * px, h) + ncoef * cs + sizeof(Rb200ItxItem) + 1024,
+                     DevRect::bytes_for(w * px, h) + ncoef * cs + sizeof(Rb200ItxItem) + 1024);
+    if (r) return r;
+    DevRect rect;
+    if ((r = rect.upload(st, dst, stride, w * px, h))) return r;
+    void *d_cf = st.dalloc(ncoef * cs);
+    void *h_cf = st.halloc(ncoef * cs);
+    memcpy(h_cf, coeff, ncoef * cs);
+    RB_CUDA(cudaMemcpyAsync(d_cf, h_cf, ncoef * cs, cudaMemcpyHostToDevice, st.stream));
+    Rb200ItxItem *h_it = (Rb200ItxItem *)st.halloc(sizeof(Rb200ItxItem));
+    Rb200ItxItem *d_it = (Rb200ItxItem *)st.dalloc(sizeof(Rb200ItxItem));
+    memset(h_it, 0, sizeof(*h_it));
+    h_it->tx = (uint8_t)tx; h_it->txtp = (uint8_t)txtp; h_it->eob = (int16_t)(eob > 32767 ? 32767 : eob);
+    RB_CUDA(cudaMemcpyAsync(d_it, h_it, sizeof(*h_it), cudaMemcpyHostToDevice, st.stream));
+    Rb200Planes pl = {};
+    pl.data[0] = rect.dptr; pl.stride[0] = rect.dpitch;
+    if ((r = itx_launch(tx, pl, d_cf, d_it, 1, bitdepth_max, st.stream))) return r;
+    if ((r = rect.download(st))) return r;
+    RB_CUDA(cudaStreamSynchronize(st.stream));
+    rect.finish(dst);
+    if (txtp == RB200_DCT_DCT && eob < 1) memset(coeff, 0, cs);
+    else memset(coeff, 0, ncoef * cs);
+    return 0;
+}
+
+// ---- function-pointer table (drop-in for rav1d_itx_dsp_init, src/itx.rs:1072-1105) ----
+namespace {
+template <int TX, int TXTP>
+void itx_slot(void *dst, ptrdiff_t stride, void *coeff, int eob, int bitdepth_max) {
+    if (rb200_itxfm_add(TX, TXTP, dst, stride, coeff, eob, bitdepth_max)) rb200_report_fatal("itxfm_add");
+}
+template <int TX, int... TP>
+void fill_row(Rb200InvTxfmDSPContext *c, std::integer_sequence<int, TP...>) {
+    ((c->itxfm_add[TX][TP] = itx_valid(TX, TP) ? &itx_slot<TX, TP> : nullptr), ...);
+}
+template <int... TX>
+void fill_all(Rb200InvTxfmDSPContext *c, std::integer_sequence<int, TX...>) {
+    (fill_row<TX>(c, std::make_integer_sequence<int, 17>{}), ...);
+}
+}  // namespace
+
+extern "C" void rb200_itx_dsp_init(Rb200InvTxfmDSPContext *c, int bpc) {
+    (void)bpc;  // the bit depth travels in each call's bitdepth_max, as in the Rust fn-pointer ABI
+    fill_all(c, std::make_integer_sequence<int, 19>{});
+}
