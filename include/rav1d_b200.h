@@ -112,6 +112,257 @@ typedef struct Rb200ItxItem {
 int rb200_itx_add_batch(const Rb200Planes *planes, const void *d_coef, const Rb200ItxItem *d_items,
                         const int32_t counts[RB200_N_RECT_TX_SIZES], int bitdepth_max, void *stream);
 
+/* -------------------------------------------------------------------- mc */
+/* enum Filter2d, src/levels.rs:172-183 */
+enum {
+    RB200_FILTER_2D_8TAP_REGULAR, RB200_FILTER_2D_8TAP_REGULAR_SMOOTH, RB200_FILTER_2D_8TAP_REGULAR_SHARP,
+    RB200_FILTER_2D_8TAP_SHARP_REGULAR, RB200_FILTER_2D_8TAP_SHARP_SMOOTH, RB200_FILTER_2D_8TAP_SHARP,
+    RB200_FILTER_2D_8TAP_SMOOTH_REGULAR, RB200_FILTER_2D_8TAP_SMOOTH, RB200_FILTER_2D_8TAP_SMOOTH_SHARP,
+    RB200_FILTER_2D_BILINEAR, RB200_N_2D_FILTERS
+};
+/* fn-pointer types of Rav1dMCDSPContext, src/mc.rs:1174-1320 (trailing bitdepth_max in every
+ * pixel function, as in the Rust ABI; blend* and emu_edge take none, as in the reference). */
+typedef void (*rb200_mc_fn)(void *dst, ptrdiff_t dst_stride, const void *src, ptrdiff_t src_stride,
+                            int w, int h, int mx, int my, int bitdepth_max);
+typedef void (*rb200_mc_scaled_fn)(void *dst, ptrdiff_t dst_stride, const void *src, ptrdiff_t src_stride,
+                                   int w, int h, int mx, int my, int dx, int dy, int bitdepth_max);
+typedef void (*rb200_mct_fn)(int16_t *tmp, const void *src, ptrdiff_t src_stride,
+                             int w, int h, int mx, int my, int bitdepth_max);
+typedef void (*rb200_mct_scaled_fn)(int16_t *tmp, const void *src, ptrdiff_t src_stride,
+                                    int w, int h, int mx, int my, int dx, int dy, int bitdepth_max);
+typedef void (*rb200_avg_fn)(void *dst, ptrdiff_t dst_stride, const int16_t *tmp1, const int16_t *tmp2,
+                             int w, int h, int bitdepth_max);
+typedef void (*rb200_w_avg_fn)(void *dst, ptrdiff_t dst_stride, const int16_t *tmp1, const int16_t *tmp2,
+                               int w, int h, int weight, int bitdepth_max);
+typedef void (*rb200_mask_fn)(void *dst, ptrdiff_t dst_stride, const int16_t *tmp1, const int16_t *tmp2,
+                              int w, int h, const uint8_t *mask, int bitdepth_max);
+typedef void (*rb200_w_mask_fn)(void *dst, ptrdiff_t dst_stride, const int16_t *tmp1, const int16_t *tmp2,
+                                int w, int h, uint8_t *mask, int sign, int bitdepth_max);
+typedef void (*rb200_blend_fn)(void *dst, ptrdiff_t dst_stride, const void *tmp, int w, int h,
+                               const uint8_t *mask);
+typedef void (*rb200_blend_dir_fn)(void *dst, ptrdiff_t dst_stride, const void *tmp, int w, int h);
+typedef void (*rb200_warp8x8_fn)(void *dst, ptrdiff_t dst_stride, const void *src, ptrdiff_t src_stride,
+                                 const int16_t *abcd, int mx, int my, int bitdepth_max);
+typedef void (*rb200_warp8x8t_fn)(int16_t *tmp, ptrdiff_t tmp_stride, const void *src, ptrdiff_t src_stride,
+                                  const int16_t *abcd, int mx, int my, int bitdepth_max);
+typedef void (*rb200_emu_edge_fn)(intptr_t bw, intptr_t bh, intptr_t iw, intptr_t ih, intptr_t x, intptr_t y,
+                                  void *dst, ptrdiff_t dst_stride, const void *ref, ptrdiff_t ref_stride);
+typedef void (*rb200_resize_fn)(void *dst, ptrdiff_t dst_stride, const void *src, ptrdiff_t src_stride,
+                                int dst_w, int h, int src_w, int dx, int mx, int bitdepth_max);
+/* Rav1dMCDSPContext, src/mc.rs:1321-1338 (same member order) */
+typedef struct Rb200MCDSPContext {
+    rb200_mc_fn mc[RB200_N_2D_FILTERS];
+    rb200_mc_scaled_fn mc_scaled[RB200_N_2D_FILTERS];
+    rb200_mct_fn mct[RB200_N_2D_FILTERS];
+    rb200_mct_scaled_fn mct_scaled[RB200_N_2D_FILTERS];
+    rb200_avg_fn avg;
+    rb200_w_avg_fn w_avg;
+    rb200_mask_fn mask;
+    rb200_w_mask_fn w_mask[3]; /* 444, 422, 420 */
+    rb200_blend_fn blend;
+    rb200_blend_dir_fn blend_v;
+    rb200_blend_dir_fn blend_h;
+    rb200_warp8x8_fn warp8x8;
+    rb200_warp8x8t_fn warp8x8t;
+    rb200_emu_edge_fn emu_edge;
+    rb200_resize_fn resize;
+} Rb200MCDSPContext;
+/* rav1d_mc_dsp_init, src/mc.rs:2495-2566.  `bpc` selects pixel size for the functions
+ * that take no bitdepth_max (blend, blend_v, blend_h, emu_edge): 8 -> u8, 10/12 -> u16. */
+void rb200_mc_dsp_init(Rb200MCDSPContext *c, int bpc);
+/* Index-based entry points (error code instead of the table's void). */
+int rb200_mc(int filter2d, void *dst, ptrdiff_t dst_stride, const void *src, ptrdiff_t src_stride,
+             int w, int h, int mx, int my, int bitdepth_max);
+int rb200_mct(int filter2d, int16_t *tmp, const void *src, ptrdiff_t src_stride,
+              int w, int h, int mx, int my, int bitdepth_max);
+int rb200_mc_scaled(int filter2d, void *dst, ptrdiff_t dst_stride, const void *src, ptrdiff_t src_stride,
+                    int w, int h, int mx, int my, int dx, int dy, int bitdepth_max);
+int rb200_mct_scaled(int filter2d, int16_t *tmp, const void *src, ptrdiff_t src_stride,
+                     int w, int h, int mx, int my, int dx, int dy, int bitdepth_max);
+int rb200_avg(void *dst, ptrdiff_t dst_stride, const int16_t *tmp1, const int16_t *tmp2, int w, int h,
+              int bitdepth_max);
+int rb200_w_avg(void *dst, ptrdiff_t dst_stride, const int16_t *tmp1, const int16_t *tmp2, int w, int h,
+                int weight, int bitdepth_max);
+int rb200_mask(void *dst, ptrdiff_t dst_stride, const int16_t *tmp1, const int16_t *tmp2, int w, int h,
+               const uint8_t *mask, int bitdepth_max);
+int rb200_w_mask(int ss /* 0:444 1:422 2:420 */, void *dst, ptrdiff_t dst_stride, const int16_t *tmp1,
+                 const int16_t *tmp2, int w, int h, uint8_t *mask, int sign, int bitdepth_max);
+int rb200_blend(int dir /* 0:mask 1:v 2:h */, void *dst, ptrdiff_t dst_stride, const void *tmp, int w, int h,
+                const uint8_t *mask, int bitdepth_max);
+int rb200_warp8x8(void *dst, ptrdiff_t dst_stride, const void *src, ptrdiff_t src_stride,
+                  const int16_t *abcd, int mx, int my, int bitdepth_max);
+int rb200_warp8x8t(int16_t *tmp, ptrdiff_t tmp_stride, const void *src, ptrdiff_t src_stride,
+                   const int16_t *abcd, int mx, int my, int bitdepth_max);
+int rb200_emu_edge(intptr_t bw, intptr_t bh, intptr_t iw, intptr_t ih, intptr_t x, intptr_t y,
+                   void *dst, ptrdiff_t dst_stride, const void *ref, ptrdiff_t ref_stride, int bitdepth_max);
+int rb200_resize(void *dst, ptrdiff_t dst_stride, const void *src, ptrdiff_t src_stride,
+                 int dst_w, int h, int src_w, int dx, int mx, int bitdepth_max);
+
+/* Batch form: one record per prediction block and plane, what recon.rs `mc()`
+ * (src/recon.rs:2025-2203) appends instead of calling emu_edge + mc/mct.  Source
+ * coordinates may leave the reference picture: the kernel clamps them, which is
+ * what emu_edge materialises (src/mc.rs:1032-1112). */
+typedef struct Rb200McItem {
+    int16_t dst_x, dst_y; /* top-left in the destination plane, pixels */
+    int16_t src_x, src_y; /* integer source position `dx`, `dy` (src/recon.rs:2052-2055), pixels */
+    uint8_t w, h;         /* block size in pixels, 2..128 */
+    uint8_t plane;        /* 0..2 */
+    uint8_t ref;          /* reference slot, 0..7 */
+    uint8_t mx, my;       /* sub-pel phase 0..15 (already << !ss, src/recon.rs:2100-2101) */
+    uint8_t filter2d;     /* RB200_FILTER_2D_* */
+    uint8_t flags;        /* RB200_MC_* */
+} Rb200McItem;            /* 16 bytes */
+enum { RB200_MC_PUT = 0 };
+/* refs[slot]: device planes of reference pictures; ref_w/ref_h: picture size of plane 0 in pixels;
+ * ss_hor/ss_ver: chroma subsampling.  dst: device planes of the current picture. */
+int rb200_mc_batch(const Rb200Planes *dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h,
+                   int ss_hor, int ss_ver, const Rb200McItem *d_items, int n_items, int bitdepth_max,
+                   void *stream);
+
+/* ------------------------------------------------------------ loop filter */
+/* Av1FilterLUT, src/lf_mask.rs:24-28 */
+typedef struct Rb200Av1FilterLUT {
+    uint8_t e[64];
+    uint8_t i[64];
+    uint64_t sharp[2];
+} Rb200Av1FilterLUT;
+/* Av1Filter, src/lf_mask.rs:43-52: one per 128x128 luma area */
+typedef struct Rb200Av1Filter {
+    uint16_t filter_y[2 /* 0=col, 1=row */][32][3][2];
+    uint16_t filter_uv[2][32][2][2];
+    int8_t cdef_idx[4]; /* -1 = unset */
+    uint16_t noskip_mask[16][2];
+} Rb200Av1Filter;
+/* Av1RestorationUnit / Av1Restoration, src/lf_mask.rs:32-41,56-58 */
+typedef struct Rb200Av1RestorationUnit {
+    uint8_t type; /* RB200_RESTORATION_*; SGR: RB200_RESTORATION_SGRPROJ + sgr_idx */
+    int8_t filter_h[3];
+    int8_t filter_v[3];
+    int8_t sgr_weights[2];
+} Rb200Av1RestorationUnit;
+typedef struct Rb200Av1Restoration {
+    Rb200Av1RestorationUnit lr[3][4];
+} Rb200Av1Restoration;
+enum { RB200_RESTORATION_NONE, RB200_RESTORATION_SWITCHABLE, RB200_RESTORATION_WIENER, RB200_RESTORATION_SGRPROJ };
+
+/* loopfilter_sb_fn, src/loopfilter.rs:20-29 */
+typedef void (*rb200_loopfilter_sb_fn)(void *dst, ptrdiff_t stride, const uint32_t *mask,
+                                       const uint8_t (*lvl)[4], ptrdiff_t lvl_stride,
+                                       const Rb200Av1FilterLUT *lut, int w_or_h, int bitdepth_max);
+/* Rav1dLoopFilterDSPContext, src/loopfilter.rs:31-34: [0=y,1=uv][0=h (column edges),1=v (row edges)] */
+typedef struct Rb200LoopFilterDSPContext {
+    rb200_loopfilter_sb_fn loop_filter_sb[2][2];
+} Rb200LoopFilterDSPContext;
+void rb200_loop_filter_dsp_init(Rb200LoopFilterDSPContext *c, int bpc);
+int rb200_loop_filter_sb(int uv, int dir, void *dst, ptrdiff_t stride, const uint32_t *mask,
+                         const uint8_t (*lvl)[4], ptrdiff_t lvl_stride, const Rb200Av1FilterLUT *lut,
+                         int w_or_h, int bitdepth_max);
+
+/* ------------------------------------------------------------------- cdef */
+enum { RB200_CDEF_HAVE_LEFT = 1, RB200_CDEF_HAVE_RIGHT = 2, RB200_CDEF_HAVE_TOP = 4, RB200_CDEF_HAVE_BOTTOM = 8 };
+/* cdef_fn / cdef_dir_fn, src/cdef.rs:35-50 */
+typedef void (*rb200_cdef_fn)(void *dst, ptrdiff_t stride, const void *left /* [8][2] px */, const void *top,
+                              const void *bottom, int pri_strength, int sec_strength, int dir, int damping,
+                              uint32_t edges, int bitdepth_max);
+typedef int (*rb200_cdef_dir_fn)(const void *src, ptrdiff_t stride, unsigned *var, int bitdepth_max);
+/* Rav1dCdefDSPContext, src/cdef.rs:52-56 */
+typedef struct Rb200CdefDSPContext {
+    rb200_cdef_dir_fn dir;
+    rb200_cdef_fn fb[3]; /* 8x8, 4x8, 4x4 */
+} Rb200CdefDSPContext;
+void rb200_cdef_dsp_init(Rb200CdefDSPContext *c, int bpc);
+int rb200_cdef_dir(const void *src, ptrdiff_t stride, unsigned *var, int bitdepth_max, int *dir_out);
+int rb200_cdef_fb(int idx /* 0:8x8 1:4x8 2:4x4 */, void *dst, ptrdiff_t stride, const void *left,
+                  const void *top, const void *bottom, int pri_strength, int sec_strength, int dir,
+                  int damping, uint32_t edges, int bitdepth_max);
+
+/* ------------------------------------------------------- loop restoration */
+enum { RB200_LR_HAVE_LEFT = 1, RB200_LR_HAVE_RIGHT = 2, RB200_LR_HAVE_TOP = 4, RB200_LR_HAVE_BOTTOM = 8 };
+/* LooprestorationParams, src/looprestoration.rs:76-89 */
+typedef union Rb200LooprestorationParams {
+    int16_t filter[2][8] __attribute__((aligned(16)));
+    struct { uint32_t s0, s1; int16_t w0, w1; } sgr;
+} Rb200LooprestorationParams;
+/* looprestorationfilter_fn, src/looprestoration.rs:91-101 */
+typedef void (*rb200_lr_fn)(void *dst, ptrdiff_t stride, const void *left /* [h][4] px */, const void *lpf,
+                            int w, int h, const Rb200LooprestorationParams *params, uint32_t edges,
+                            int bitdepth_max);
+/* Rav1dLoopRestorationDSPContext, src/looprestoration.rs:103-107 */
+typedef struct Rb200LoopRestorationDSPContext {
+    rb200_lr_fn wiener[2]; /* 7-tap, 5-tap */
+    rb200_lr_fn sgr[3];    /* 5x5, 3x3, mix */
+} Rb200LoopRestorationDSPContext;
+void rb200_loop_restoration_dsp_init(Rb200LoopRestorationDSPContext *c, int bpc);
+int rb200_lr(int kind /* 0 wiener7, 1 wiener5, 2 sgr5x5, 3 sgr3x3, 4 sgr mix */, void *dst, ptrdiff_t stride,
+             const void *left, const void *lpf, int w, int h, const Rb200LooprestorationParams *params,
+             uint32_t edges, int bitdepth_max);
+
+/* ------------------------------------------------------------ frame level */
+/* The coarser drop-in: Rav1dFrameContext_bd_fn.filter_sbrow_{deblock_cols,deblock_rows,
+ * cdef,lr} (src/internal.rs:368-395, bodies src/recon.rs:4047-4338 driving
+ * src/lf_apply.rs:597,763, src/cdef_apply.rs:159, src/lr_apply.rs:261) and the
+ * pass-2 reconstruction calls of recon.rs become frame-level launches over
+ * device-resident planes.  The host hands over the arrays the reference's
+ * pass 1 already produces, in the reference's own layouts. */
+enum { RB200_LAYOUT_I400, RB200_LAYOUT_I420, RB200_LAYOUT_I422, RB200_LAYOUT_I444 };
+enum { RB200_STAGE_RECON = 1, RB200_STAGE_DEBLOCK = 2, RB200_STAGE_CDEF = 4, RB200_STAGE_LR = 8 };
+typedef struct Rb200FrameHeader {
+    int32_t width, height;       /* picture size in pixels (plane 0) */
+    int32_t bpc;                 /* 8, 10 or 12 */
+    int32_t layout;              /* RB200_LAYOUT_* */
+    int32_t sb128;               /* Dav1dSequenceHeader.sb128 */
+    int32_t lf_level_y[2];       /* frame_hdr.loopfilter.level_y: deblock runs if either is non-zero */
+    int32_t lf_level_u, lf_level_v; /* chroma deblock runs if either is non-zero (src/lf_apply.rs:731) */
+    int32_t cdef_damping;        /* frame_hdr.cdef.damping (3..6) */
+    int32_t cdef_y_strength[8];
+    int32_t cdef_uv_strength[8];
+    int32_t lr_type[3];          /* frame_hdr.restoration.type[plane]; NONE = plane not restored */
+    int32_t lr_unit_size_log2[2];/* frame_hdr.restoration.unit_size[y, uv] */
+} Rb200FrameHeader;
+typedef struct Rb200Frame Rb200Frame;
+
+/* Geometry derived from the header exactly as src/decode.rs:4880-4905 does. */
+typedef struct Rb200FrameGeometry {
+    int32_t bw, bh;         /* 4-pixel units, rounded up to 8 pixels */
+    int32_t w4, h4;
+    int32_t sb128w, sb128h, sbh;
+    int32_t b4_stride;
+    int32_t ss_hor, ss_ver;
+    int64_t stride[2];      /* device plane strides in bytes (y, uv) */
+    int32_t plane_h[2];     /* allocated rows (y, uv) */
+    int32_t n_planes;
+} Rb200FrameGeometry;
+
+int rb200_frame_create(Rb200Frame **out, const Rb200FrameHeader *hdr, size_t max_coefs, int max_itx_items,
+                       int max_mc_items);
+int rb200_frame_destroy(Rb200Frame *f);
+int rb200_frame_geometry(const Rb200Frame *f, Rb200FrameGeometry *g);
+/* Pinned host staging the front end writes into (the batch the north star describes). */
+void *rb200_frame_coef_buffer(Rb200Frame *f);                 /* coef[max_coefs] (i16 / i32) */
+Rb200ItxItem *rb200_frame_itx_items(Rb200Frame *f);           /* [max_itx_items], sorted by tx size */
+Rb200McItem *rb200_frame_mc_items(Rb200Frame *f);             /* [max_mc_items] */
+Rb200Av1Filter *rb200_frame_lf_masks(Rb200Frame *f);          /* [sb128h * sb128w] */
+uint8_t (*rb200_frame_lf_levels(Rb200Frame *f))[4];           /* [b4_stride * 32 * sb128h] */
+Rb200Av1FilterLUT *rb200_frame_lf_lut(Rb200Frame *f);
+Rb200Av1Restoration *rb200_frame_lr_masks(Rb200Frame *f);     /* [sb128h * sb128w] */
+/* Reference pictures: device planes (layout of rb200_frame_geometry) that stay resident. */
+int rb200_frame_set_ref(Rb200Frame *f, int slot, const Rb200Planes *planes);
+/* Upload a host picture into one of the frame's own plane sets (0 = current/recon). */
+int rb200_frame_upload_planes(Rb200Frame *f, int which, const void *const data[3], const ptrdiff_t stride[2]);
+/* The device planes holding the result of the last submit (valid after rb200_frame_wait). */
+int rb200_frame_output_planes(Rb200Frame *f, Rb200Planes *out);
+int rb200_frame_stage_planes(Rb200Frame *f, int which, Rb200Planes *out);
+/* Launch: H2D of `n_coefs` coefficients, the item lists and the filter metadata, then one
+ * kernel sequence per stage on the frame's stream.  Asynchronous. */
+int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t itx_counts[RB200_N_RECT_TX_SIZES],
+                       int n_mc_items, int stages, int upload);
+int rb200_frame_wait(Rb200Frame *f);
+/* D2H of the output picture into host planes (stride in bytes, may be negative). */
+int rb200_frame_readback(Rb200Frame *f, void *const data[3], const ptrdiff_t stride[2]);
+void *rb200_frame_stream(Rb200Frame *f);
+/* Number of kernels launched by the last submit (bench bookkeeping). */
+int rb200_frame_last_launches(const Rb200Frame *f);
+
 #ifdef __cplusplus
 }
 #endif

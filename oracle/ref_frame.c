@@ -1,0 +1,324 @@
+/*
+ * oracle/ref_frame.c -- TEST INFRASTRUCTURE ONLY (linked into oracle/_ref/libdav1d_ref.so).
+ *
+ * Drives the REFERENCE'S OWN frame-level drivers over a synthetic frame:
+ *   dav1d_filter_sbrow_{deblock_cols,deblock_rows,cdef,lr}_{8,16}bpc  (src/recon_tmpl.c:2053-2176)
+ *     -> dav1d_loopfilter_sbrow_cols/rows, dav1d_copy_lpf        (src/lf_apply_tmpl.c)
+ *     -> dav1d_cdef_brow                                        (src/cdef_apply_tmpl.c:98)
+ *     -> dav1d_lr_sbrow                                         (src/lr_apply_tmpl.c:162)
+ * by building the minimal Dav1dContext / Dav1dFrameContext those functions read
+ * (buffer set-up restated from dav1d_decode_frame_init, src/decode.c:2911-3004).
+ * Reconstruction (prediction + residual) is replayed item by item through the
+ * reference's DSP tables with the addressing rules of recon_tmpl.c `mc()`
+ * (src/recon_tmpl.c:1036-1106: emu_edge when the block window leaves the picture).
+ *
+ * Two schedules:
+ *   n_threads == 1: the reference's single-thread order, dav1d_filter_sbrow(f, sby) per sbrow
+ *                   (n_tc == 1: rolling 12-line lpf buffer, src/decode.c:2972);
+ *   n_threads  > 1: the reference's tile-thread buffers (n_tc > 1: per-sbrow lpf / cdef
+ *                   lines) with every stage run as a parallel-for over superblock rows and
+ *                   a join between stages -- the dependency structure of
+ *                   src/thread_task.c:761-830 with the wavefront flattened.  This is the CPU
+ *                   baseline bench.py times.
+ */
+#include "config.h"
+
+#include <pthread.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "src/internal.h"
+#include "src/lf_mask.h"
+#include "src/levels.h"
+#include "src/tables.h"
+#include "src/recon.h"
+
+#include "../include/rav1d_b200.h"
+
+typedef struct RefFrame {
+    Dav1dContext *c;
+    Dav1dFrameContext *f;
+    Dav1dSequenceHeader seq;
+    Dav1dFrameHeader hdr;
+    Dav1dTaskContext *tc;   /* n_tc entries */
+    int n_tc, hbd, bdmax;
+    uint8_t *plane_mem;
+    size_t plane_bytes;
+    uint8_t *lvl_mem;
+    uint8_t start_of_tile_row[1024];
+} RefFrame;
+
+void ref_init(void);
+void dav1d_filter_sbrow_8bpc(Dav1dFrameContext *f, int sby);
+void dav1d_filter_sbrow_16bpc(Dav1dFrameContext *f, int sby);
+void dav1d_filter_sbrow_deblock_cols_8bpc(Dav1dFrameContext *f, int sby);
+void dav1d_filter_sbrow_deblock_cols_16bpc(Dav1dFrameContext *f, int sby);
+void dav1d_filter_sbrow_deblock_rows_8bpc(Dav1dFrameContext *f, int sby);
+void dav1d_filter_sbrow_deblock_rows_16bpc(Dav1dFrameContext *f, int sby);
+void dav1d_filter_sbrow_cdef_8bpc(Dav1dTaskContext *tc, int sby);
+void dav1d_filter_sbrow_cdef_16bpc(Dav1dTaskContext *tc, int sby);
+void dav1d_filter_sbrow_lr_8bpc(Dav1dFrameContext *f, int sby);
+void dav1d_filter_sbrow_lr_16bpc(Dav1dFrameContext *f, int sby);
+void dav1d_itx_dsp_init_8bpc(Dav1dInvTxfmDSPContext *c, int bpc);
+void dav1d_itx_dsp_init_16bpc(Dav1dInvTxfmDSPContext *c, int bpc);
+void dav1d_mc_dsp_init_8bpc(Dav1dMCDSPContext *c);
+void dav1d_mc_dsp_init_16bpc(Dav1dMCDSPContext *c);
+void dav1d_loop_filter_dsp_init_8bpc(Dav1dLoopFilterDSPContext *c);
+void dav1d_loop_filter_dsp_init_16bpc(Dav1dLoopFilterDSPContext *c);
+void dav1d_cdef_dsp_init_8bpc(Dav1dCdefDSPContext *c);
+void dav1d_cdef_dsp_init_16bpc(Dav1dCdefDSPContext *c);
+void dav1d_loop_restoration_dsp_init_8bpc(Dav1dLoopRestorationDSPContext *c, int bpc);
+void dav1d_loop_restoration_dsp_init_16bpc(Dav1dLoopRestorationDSPContext *c, int bpc);
+
+static void *zalloc(size_t n) { void *p = NULL; if (posix_memalign(&p, 64, n ? n : 64)) return NULL; memset(p, 0, n); return p; }
+
+void ref_frame_free(RefFrame *r) {
+    if (!r) return;
+    if (r->f) {
+        free(r->f->lf.cdef_line_buf); free(r->f->lf.lr_line_buf); free(r->f->lf.mask); free(r->f->lf.lr_mask);
+        free(r->f->lf.tx_lpf_right_edge[0]);
+    }
+    free(r->lvl_mem); free(r->plane_mem); free(r->tc); free(r->f); free(r->c); free(r);
+}
+
+/* layout: 0 I400, 1 I420, 2 I422, 3 I444 (same values as Dav1dPixelLayout) */
+RefFrame *ref_frame_new(const Rb200FrameHeader *h, int n_tc) {
+    ref_init();
+    RefFrame *r = zalloc(sizeof(*r));
+    Dav1dContext *c = r->c = zalloc(sizeof(Dav1dContext));
+    Dav1dFrameContext *f = r->f = zalloc(sizeof(Dav1dFrameContext));
+    if (n_tc < 1) n_tc = 1;
+    r->n_tc = n_tc;
+    r->tc = zalloc(sizeof(Dav1dTaskContext) * n_tc);
+    r->hbd = h->bpc > 8;
+    r->bdmax = (1 << h->bpc) - 1;
+    for (int i = 0; i < n_tc; i++) { r->tc[i].c = c; r->tc[i].f = f; }
+    c->tc = r->tc; c->n_tc = n_tc; c->fc = f; c->n_fc = 1;
+    c->inloop_filters = DAV1D_INLOOPFILTER_ALL;
+    Dav1dDSPContext *dsp = &c->dsp[(h->bpc >> 1) - 4];
+    if (r->hbd) {
+        dav1d_itx_dsp_init_16bpc(&dsp->itx, h->bpc); dav1d_mc_dsp_init_16bpc(&dsp->mc);
+        dav1d_loop_filter_dsp_init_16bpc(&dsp->lf); dav1d_cdef_dsp_init_16bpc(&dsp->cdef);
+        dav1d_loop_restoration_dsp_init_16bpc(&dsp->lr, h->bpc);
+    } else {
+        dav1d_itx_dsp_init_8bpc(&dsp->itx, 8); dav1d_mc_dsp_init_8bpc(&dsp->mc);
+        dav1d_loop_filter_dsp_init_8bpc(&dsp->lf); dav1d_cdef_dsp_init_8bpc(&dsp->cdef);
+        dav1d_loop_restoration_dsp_init_8bpc(&dsp->lr, 8);
+    }
+    f->c = c; f->dsp = dsp; f->seq_hdr = &r->seq; f->frame_hdr = &r->hdr;
+    f->bitdepth_max = r->bdmax;
+    r->seq.sb128 = h->sb128; r->seq.cdef = 1; r->seq.restoration = 1;
+    r->seq.layout = h->layout; r->seq.hbd = h->bpc == 8 ? 0 : h->bpc == 10 ? 1 : 2;
+    r->hdr.width[0] = r->hdr.width[1] = h->width; r->hdr.height = h->height;
+    r->hdr.tiling.cols = r->hdr.tiling.rows = 1;
+    r->hdr.tiling.col_start_sb[0] = 0; r->hdr.tiling.col_start_sb[1] = 1 << 20;
+    r->hdr.tiling.row_start_sb[0] = 0; r->hdr.tiling.row_start_sb[1] = 1 << 20;
+    r->hdr.loopfilter.level_y[0] = h->lf_level_y[0]; r->hdr.loopfilter.level_y[1] = h->lf_level_y[1];
+    r->hdr.loopfilter.level_u = h->lf_level_u; r->hdr.loopfilter.level_v = h->lf_level_v;
+    r->hdr.cdef.damping = h->cdef_damping;
+    for (int i = 0; i < 8; i++) { r->hdr.cdef.y_strength[i] = h->cdef_y_strength[i]; r->hdr.cdef.uv_strength[i] = h->cdef_uv_strength[i]; }
+    for (int i = 0; i < 3; i++) r->hdr.restoration.type[i] = h->lr_type[i];
+    r->hdr.restoration.unit_size[0] = h->lr_unit_size_log2[0]; r->hdr.restoration.unit_size[1] = h->lr_unit_size_log2[1];
+
+    /* geometry: dav1d_submit_frame, src/decode.c:3560-3580 */
+    f->bw = ((h->width + 7) >> 3) << 1; f->bh = ((h->height + 7) >> 3) << 1;
+    f->w4 = (h->width + 3) >> 2; f->h4 = (h->height + 3) >> 2;
+    f->sb128w = (f->bw + 31) >> 5; f->sb128h = (f->bh + 31) >> 5; f->sr_sb128w = f->sb128w;
+    f->sb_shift = 4 + h->sb128; f->sb_step = 16 << h->sb128;
+    f->sbh = (f->bh + f->sb_step - 1) >> f->sb_shift;
+    f->b4_stride = (f->bw + 31) & ~31;
+
+    /* picture: dav1d_default_picture_alloc, src/picture.c:47-90 */
+    const int px = r->hbd ? 2 : 1;
+    const int aw = (h->width + 127) & ~127, ah = (h->height + 127) & ~127;
+    const int has_chroma = h->layout != 0, ss_ver = h->layout == 1, ss_hor = h->layout != 3;
+    ptrdiff_t y_stride = (ptrdiff_t)aw * px, uv_stride = has_chroma ? y_stride >> ss_hor : 0;
+    if (!(y_stride & 1023)) y_stride += 64;
+    if (has_chroma && !(uv_stride & 1023)) uv_stride += 64;
+    const size_t ysz = (size_t)y_stride * ah, uvsz = (size_t)uv_stride * (ah >> ss_ver);
+    r->plane_bytes = ysz + 2 * uvsz + 64;
+    r->plane_mem = zalloc(r->plane_bytes);
+    f->cur.data[0] = r->plane_mem;
+    f->cur.data[1] = has_chroma ? r->plane_mem + ysz : NULL;
+    f->cur.data[2] = has_chroma ? r->plane_mem + ysz + uvsz : NULL;
+    f->cur.stride[0] = y_stride; f->cur.stride[1] = uv_stride;
+    f->cur.p.w = h->width; f->cur.p.h = h->height; f->cur.p.layout = h->layout; f->cur.p.bpc = h->bpc;
+    f->sr_cur.p = f->cur;
+    for (int i = 0; i < 3; i++) f->lf.p[i] = f->lf.sr_p[i] = f->cur.data[i];
+
+    /* filter metadata */
+    const int num_sb128 = f->sb128w * f->sb128h;
+    f->lf.mask = zalloc(sizeof(Av1Filter) * num_sb128);
+    f->lf.lr_mask = zalloc(sizeof(Av1Restoration) * num_sb128);
+    r->lvl_mem = zalloc(((size_t)f->b4_stride * 32 * f->sb128h + 32 + 3) * 4);
+    f->lf.level = (uint8_t(*)[4])r->lvl_mem + 32;
+    f->lf.tx_lpf_right_edge[0] = zalloc((size_t)f->sb128h * 32 * 2 + 64);
+    f->lf.tx_lpf_right_edge[1] = f->lf.tx_lpf_right_edge[0] + f->sb128h * 32;
+    f->lf.start_of_tile_row = r->start_of_tile_row;
+    f->lf.restore_planes = ((h->lr_type[0] != 0) << 0) | ((has_chroma && h->lr_type[1] != 0) << 1) |
+                           ((has_chroma && h->lr_type[2] != 0) << 2);
+
+    /* cdef / lr line buffers: src/decode.c:2911-3004 (positive strides, no super-res) */
+    {
+        size_t alloc_sz = 64 + (size_t)y_stride * 4 * f->sbh + (size_t)uv_stride * 8 * f->sbh;
+        uint8_t *ptr = f->lf.cdef_line_buf = zalloc(alloc_sz + 64);
+        ptr += 32;
+        f->lf.cdef_line[0][0] = ptr; f->lf.cdef_line[1][0] = ptr + y_stride * 2;
+        ptr += y_stride * f->sbh * 4;
+        f->lf.cdef_line[0][1] = ptr; f->lf.cdef_line[0][2] = ptr + uv_stride * 2;
+        f->lf.cdef_line[1][1] = ptr + uv_stride * 4; f->lf.cdef_line[1][2] = ptr + uv_stride * 6;
+        const int num_lines = n_tc > 1 ? f->sbh * 4 << h->sb128 : 12;
+        alloc_sz = 128 + (size_t)y_stride * num_lines + (size_t)uv_stride * num_lines * 2;
+        ptr = f->lf.lr_line_buf = zalloc(alloc_sz + 64);
+        ptr += 64;
+        f->lf.lr_lpf_line[0] = ptr; ptr += y_stride * num_lines;
+        f->lf.lr_lpf_line[1] = ptr; f->lf.lr_lpf_line[2] = ptr + uv_stride * num_lines;
+    }
+    return r;
+}
+
+void *ref_frame_plane(RefFrame *r, int pl) { return r->f->cur.data[pl]; }
+ptrdiff_t ref_frame_stride(RefFrame *r, int uv) { return r->f->cur.stride[uv]; }
+void *ref_frame_masks(RefFrame *r) { return r->f->lf.mask; }
+void *ref_frame_levels(RefFrame *r) { return r->f->lf.level; }
+void *ref_frame_lut(RefFrame *r) { return &r->f->lf.lim_lut; }
+void *ref_frame_lr_masks(RefFrame *r) { return r->f->lf.lr_mask; }
+int ref_frame_sbh(RefFrame *r) { return r->f->sbh; }
+void ref_calc_eih(void *lut, int sharpness) { dav1d_calc_eih((Av1FilterLUT *)lut, sharpness); }
+size_t ref_sizeof(int what) {
+    switch (what) {
+    case 0: return sizeof(Av1Filter);
+    case 1: return sizeof(Av1Restoration);
+    case 2: return sizeof(Av1FilterLUT);
+    case 3: return sizeof(Av1RestorationUnit);
+    }
+    return 0;
+}
+
+/* ---------------------------------------------------------------- threads */
+typedef struct Job { void (*fn)(RefFrame *, int tid, int idx, void *arg); RefFrame *r; void *arg; int n, tid; int *next; } Job;
+static void *job_main(void *p) {
+    Job *j = p;
+    /* dynamic schedule (one shared counter), like the reference's task queue */
+    for (;;) {
+        const int i = __atomic_fetch_add(j->next, 1, __ATOMIC_RELAXED);
+        if (i >= j->n) break;
+        j->fn(j->r, j->tid, i, j->arg);
+    }
+    return NULL;
+}
+static void parallel_for(RefFrame *r, int nthr, int n, void (*fn)(RefFrame *, int, int, void *), void *arg) {
+    if (nthr > n) nthr = n;
+    if (nthr <= 1) { for (int i = 0; i < n; i++) fn(r, 0, i, arg); return; }
+    pthread_t th[256]; Job jobs[256];
+    int next = 0;
+    if (nthr > 256) nthr = 256;
+    for (int t = 0; t < nthr; t++) {
+        jobs[t] = (Job){ fn, r, arg, n, t, &next };
+        pthread_create(&th[t], NULL, job_main, &jobs[t]);
+    }
+    for (int t = 0; t < nthr; t++) pthread_join(th[t], NULL);
+}
+
+static void st_cols(RefFrame *r, int tid, int sby, void *a) { (void)tid; (void)a; if (r->hbd) dav1d_filter_sbrow_deblock_cols_16bpc(r->f, sby); else dav1d_filter_sbrow_deblock_cols_8bpc(r->f, sby); }
+static void st_rows(RefFrame *r, int tid, int sby, void *a) { (void)tid; (void)a; if (r->hbd) dav1d_filter_sbrow_deblock_rows_16bpc(r->f, sby); else dav1d_filter_sbrow_deblock_rows_8bpc(r->f, sby); }
+static void st_cdef(RefFrame *r, int tid, int sby, void *a) { (void)a; if (r->hbd) dav1d_filter_sbrow_cdef_16bpc(&r->tc[tid], sby); else dav1d_filter_sbrow_cdef_8bpc(&r->tc[tid], sby); }
+static void st_lr(RefFrame *r, int tid, int sby, void *a) { (void)tid; (void)a; if (r->hbd) dav1d_filter_sbrow_lr_16bpc(r->f, sby); else dav1d_filter_sbrow_lr_8bpc(r->f, sby); }
+
+/* stages: RB200_STAGE_DEBLOCK | _CDEF | _LR */
+void ref_frame_filter(RefFrame *r, int stages, int n_threads) {
+    Dav1dFrameContext *f = r->f;
+    r->c->inloop_filters = ((stages & RB200_STAGE_DEBLOCK) ? DAV1D_INLOOPFILTER_DEBLOCK : 0) |
+                           ((stages & RB200_STAGE_CDEF) ? DAV1D_INLOOPFILTER_CDEF : 0) |
+                           ((stages & RB200_STAGE_LR) ? DAV1D_INLOOPFILTER_RESTORATION : 0);
+    r->seq.cdef = !!(stages & RB200_STAGE_CDEF);
+    const int restore_planes = f->lf.restore_planes;
+    if (!(stages & RB200_STAGE_LR)) f->lf.restore_planes = 0;
+    for (int i = 0; i < r->n_tc; i++) r->tc[i].top_pre_cdef_toggle = 0;
+    if (r->n_tc == 1) {
+        for (int sby = 0; sby < f->sbh; sby++) {
+            if (r->hbd) dav1d_filter_sbrow_16bpc(f, sby); else dav1d_filter_sbrow_8bpc(f, sby);
+        }
+    } else {
+        if (n_threads > r->n_tc) n_threads = r->n_tc;
+        parallel_for(r, n_threads, f->sbh, st_cols, NULL);
+        parallel_for(r, n_threads, f->sbh, st_rows, NULL);   /* + dav1d_copy_lpf */
+        if (r->seq.cdef) parallel_for(r, n_threads, f->sbh, st_cdef, NULL);
+        if (f->lf.restore_planes) parallel_for(r, n_threads, f->sbh, st_lr, NULL);
+    }
+    f->lf.restore_planes = restore_planes;
+}
+
+/* ------------------------------------------------------------------ recon */
+typedef struct ReconArgs {
+    const Rb200McItem *mc; const Rb200ItxItem *itx; const void *coef_src; void *coef_work;
+    RefFrame *refs[8]; int chunk;
+    int n_mc, n_itx;
+} ReconArgs;
+
+typedef void (*mc_fn8)(void *, ptrdiff_t, const void *, ptrdiff_t, int, int, int, int);
+typedef void (*mc_fn16)(void *, ptrdiff_t, const void *, ptrdiff_t, int, int, int, int, int);
+typedef void (*itx_fn8)(void *, ptrdiff_t, void *, int);
+typedef void (*itx_fn16)(void *, ptrdiff_t, void *, int, int);
+
+static void do_mc_chunk(RefFrame *r, int tid, int chunk, void *arg) {
+    (void)tid;
+    ReconArgs *a = arg;
+    Dav1dFrameContext *f = r->f;
+    const int px = r->hbd ? 2 : 1;
+    const int ss_ver_l = f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420, ss_hor_l = f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444;
+    uint8_t emu[320 * (256 + 7) * 2];
+    const int lo = chunk * a->chunk, hi = lo + a->chunk < a->n_mc ? lo + a->chunk : a->n_mc;
+    for (int i = lo; i < hi; i++) {
+        const Rb200McItem *it = &a->mc[i];
+        const int pl = it->plane, ss_hor = pl && ss_hor_l, ss_ver = pl && ss_ver_l;
+        const Dav1dFrameContext *rf = a->refs[it->ref]->f;
+        const int w = (f->cur.p.w + ss_hor) >> ss_hor, h = (f->cur.p.h + ss_ver) >> ss_ver;
+        const int mx = it->mx, my = it->my, dx = it->src_x, dy = it->src_y, bw = it->w, bh = it->h;
+        ptrdiff_t ref_stride = rf->cur.stride[!!pl];
+        const uint8_t *ref;
+        /* src/recon_tmpl.c:1065-1080 */
+        if (dx < !!mx * 3 || dy < !!my * 3 || dx + bw + !!mx * 4 > w || dy + bh + !!my * 4 > h) {
+            ((void (*)(intptr_t, intptr_t, intptr_t, intptr_t, intptr_t, intptr_t, void *, ptrdiff_t, const void *, ptrdiff_t))
+                 f->dsp->mc.emu_edge)(bw + !!mx * 7, bh + !!my * 7, w, h, dx - !!mx * 3, dy - !!my * 3, emu,
+                                      192 * px, rf->cur.data[pl], ref_stride);
+            ref = emu + (192 * !!my * 3 + !!mx * 3) * px;
+            ref_stride = 192 * px;
+        } else {
+            ref = (const uint8_t *)rf->cur.data[pl] + ref_stride * dy + (ptrdiff_t)dx * px;
+        }
+        uint8_t *dst = (uint8_t *)f->cur.data[pl] + f->cur.stride[!!pl] * it->dst_y + (ptrdiff_t)it->dst_x * px;
+        if (r->hbd) ((mc_fn16)f->dsp->mc.mc[it->filter2d])(dst, f->cur.stride[!!pl], ref, ref_stride, bw, bh, mx, my, r->bdmax);
+        else ((mc_fn8)f->dsp->mc.mc[it->filter2d])(dst, f->cur.stride[!!pl], ref, ref_stride, bw, bh, mx, my);
+    }
+}
+
+static void do_itx_chunk(RefFrame *r, int tid, int chunk, void *arg) {
+    (void)tid;
+    ReconArgs *a = arg;
+    Dav1dFrameContext *f = r->f;
+    const int px = r->hbd ? 2 : 1, cs = r->hbd ? 4 : 2;
+    const int lo = chunk * a->chunk, hi = lo + a->chunk < a->n_itx ? lo + a->chunk : a->n_itx;
+    for (int i = lo; i < hi; i++) {
+        const Rb200ItxItem *it = &a->itx[i];
+        uint8_t *dst = (uint8_t *)f->cur.data[it->plane] + f->cur.stride[!!it->plane] * it->y + (ptrdiff_t)it->x * px;
+        void *cf = (uint8_t *)a->coef_work + (size_t)it->cf_off * cs;
+        if (r->hbd) ((itx_fn16)f->dsp->itx.itxfm_add[it->tx][it->txtp])(dst, f->cur.stride[!!it->plane], cf, it->eob, r->bdmax);
+        else ((itx_fn8)f->dsp->itx.itxfm_add[it->tx][it->txtp])(dst, f->cur.stride[!!it->plane], cf, it->eob);
+    }
+}
+
+/* Prediction + residual for one frame.  `coef_work` is consumed (zeroed) like the
+ * reference's cf buffer; the caller restores it between timed iterations. */
+void ref_frame_recon(RefFrame *r, RefFrame *const refs[], int n_refs, const Rb200McItem *mc, int n_mc,
+                     const Rb200ItxItem *itx, int n_itx, void *coef_work, int n_threads) {
+    ReconArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mc = mc; a.itx = itx; a.coef_work = coef_work; a.n_mc = n_mc; a.n_itx = n_itx;
+    for (int i = 0; i < n_refs && i < 8; i++) a.refs[i] = refs[i];
+    a.chunk = 256;
+    parallel_for(r, n_threads, (n_mc + a.chunk - 1) / a.chunk, do_mc_chunk, &a);
+    parallel_for(r, n_threads, (n_itx + a.chunk - 1) / a.chunk, do_itx_chunk, &a);
+}

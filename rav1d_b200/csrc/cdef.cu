@@ -1,0 +1,402 @@
+// CDEF (constrained directional enhancement filter) for sm_100a.
+//
+// Replaces Rav1dCdefDSPContext {dir, fb[3]} (src/cdef.rs:35-56; cdef_find_dir_rust
+// src/cdef.rs:921, cdef_filter_block_c src/cdef.rs:668 == src/cdef_tmpl.c:104-300) and,
+// at frame level, the per-sbrow driver rav1d_cdef_brow (src/cdef_apply.rs:159-507 ==
+// src/cdef_apply_tmpl.c:98-309).
+//
+// Frame kernel: one CTA per 64x64 luma area (one cdef_idx unit).  The pre-CDEF
+// (deblocked) pixels of the area plus a 2-pixel halo are staged in shared memory as
+// int16 with the reference's INT16_MIN sentinel outside the frame; 64 threads
+// each run the direction search of one 8x8 block out of registers; then all 256
+// threads filter, out of place, so every tap reads pre-CDEF data without the
+// reference's line/column backups.  Blocks that are skipped are
+// copied through.  Chroma planes reuse the tile buffer and the luma directions.
+#include "common.cuh"
+#include "tables.cuh"
+
+namespace rb200 {
+
+constexpr int CDEF_T = 64;               // luma tile edge
+constexpr int CDEF_PITCH = CDEF_T + 4;   // 68
+constexpr int16_t CDEF_SENTINEL = -32768;
+
+__device__ __forceinline__ int cdef_constrain(int diff, int threshold, int shift) {
+    const int adiff = diff < 0 ? -diff : diff;
+    const int v = imin(adiff, imax(0, threshold - (adiff >> shift)));
+    return diff < 0 ? -v : v;
+}
+
+// One pixel of cdef_filter_block_c.  t points at the pixel inside an int16 tile of row pitch `pitch`.
+__device__ __forceinline__ int cdef_filter_px(const int16_t *t, int pitch, int pri, int sec, int dir, int damping,
+                                              int bdmin8) {
+    const int px = t[0];
+    int sum = 0;
+    if (pri) {
+        const int pri_tap = 4 - ((pri >> bdmin8) & 1);
+        const int pri_shift = imax(0, damping - ulog2(pri));
+        if (sec) {
+            const int sec_shift = damping - ulog2(sec);
+            int mx = px, mn = px;
+            int ptk = pri_tap;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                int dy, dx;
+                tab::cdef_dir_off(dir, k, dy, dx);
+                const int o1 = dy * pitch + dx;
+                const int p0 = t[o1], p1 = t[-o1];
+                sum += ptk * cdef_constrain(p0 - px, pri, pri_shift);
+                sum += ptk * cdef_constrain(p1 - px, pri, pri_shift);
+                ptk = (ptk & 3) | 2;
+                mn = (int)umin((unsigned)p0, (unsigned)mn); mx = imax(p0, mx);
+                mn = (int)umin((unsigned)p1, (unsigned)mn); mx = imax(p1, mx);
+                tab::cdef_dir_off((dir + 2) & 7, k, dy, dx);
+                const int o2 = dy * pitch + dx;
+                tab::cdef_dir_off((dir + 6) & 7, k, dy, dx);
+                const int o3 = dy * pitch + dx;
+                const int s0 = t[o2], s1 = t[-o2], s2 = t[o3], s3 = t[-o3];
+                const int sec_tap = 2 - k;
+                sum += sec_tap * cdef_constrain(s0 - px, sec, sec_shift);
+                sum += sec_tap * cdef_constrain(s1 - px, sec, sec_shift);
+                sum += sec_tap * cdef_constrain(s2 - px, sec, sec_shift);
+                sum += sec_tap * cdef_constrain(s3 - px, sec, sec_shift);
+                mn = (int)umin((unsigned)s0, (unsigned)mn); mx = imax(s0, mx);
+                mn = (int)umin((unsigned)s1, (unsigned)mn); mx = imax(s1, mx);
+                mn = (int)umin((unsigned)s2, (unsigned)mn); mx = imax(s2, mx);
+                mn = (int)umin((unsigned)s3, (unsigned)mn); mx = imax(s3, mx);
+            }
+            return iclip(px + ((sum - (sum < 0) + 8) >> 4), mn, mx);
+        }
+        int ptk = pri_tap;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            int dy, dx;
+            tab::cdef_dir_off(dir, k, dy, dx);
+            const int o = dy * pitch + dx;
+            sum += ptk * cdef_constrain(t[o] - px, pri, pri_shift);
+            sum += ptk * cdef_constrain(t[-o] - px, pri, pri_shift);
+            ptk = (ptk & 3) | 2;
+        }
+        return px + ((sum - (sum < 0) + 8) >> 4);
+    }
+    const int sec_shift = damping - ulog2(sec);
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        int dy, dx;
+        tab::cdef_dir_off((dir + 2) & 7, k, dy, dx);
+        const int o1 = dy * pitch + dx;
+        tab::cdef_dir_off((dir + 6) & 7, k, dy, dx);
+        const int o2 = dy * pitch + dx;
+        const int sec_tap = 2 - k;
+        sum += sec_tap * cdef_constrain(t[o1] - px, sec, sec_shift);
+        sum += sec_tap * cdef_constrain(t[-o1] - px, sec, sec_shift);
+        sum += sec_tap * cdef_constrain(t[o2] - px, sec, sec_shift);
+        sum += sec_tap * cdef_constrain(t[-o2] - px, sec, sec_shift);
+    }
+    return px + ((sum - (sum < 0) + 8) >> 4);
+}
+
+// cdef_find_dir for one 8x8 block held in an int16 tile; fully unrolled so that the 90
+// partial sums live in registers.  src/cdef_tmpl.c:223-300
+__device__ __forceinline__ int cdef_find_dir(const int16_t *t, int pitch, int bdmin8, unsigned *var) {
+    int hv0[8] = {0}, hv1[8] = {0}, dg0[15] = {0}, dg1[15] = {0}, al0[11] = {0}, al1[11] = {0}, al2[11] = {0},
+        al3[11] = {0};
+#pragma unroll
+    for (int y = 0; y < 8; y++) {
+#pragma unroll
+        for (int x = 0; x < 8; x++) {
+            const int px = ((int)t[y * pitch + x] >> bdmin8) - 128;
+            dg0[y + x] += px;
+            al0[y + (x >> 1)] += px;
+            hv0[y] += px;
+            al1[3 + y - (x >> 1)] += px;
+            dg1[7 + y - x] += px;
+            al2[3 - (y >> 1) + x] += px;
+            hv1[x] += px;
+            al3[(y >> 1) + x] += px;
+        }
+    }
+    unsigned cost[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int n = 0; n < 8; n++) {
+        cost[2] += hv0[n] * hv0[n];
+        cost[6] += hv1[n] * hv1[n];
+    }
+    cost[2] *= 105; cost[6] *= 105;
+    constexpr int div_table[7] = {840, 420, 280, 210, 168, 140, 120};
+#pragma unroll
+    for (int n = 0; n < 7; n++) {
+        const int d = div_table[n];
+        cost[0] += (dg0[n] * dg0[n] + dg0[14 - n] * dg0[14 - n]) * d;
+        cost[4] += (dg1[n] * dg1[n] + dg1[14 - n] * dg1[14 - n]) * d;
+    }
+    cost[0] += dg0[7] * dg0[7] * 105;
+    cost[4] += dg1[7] * dg1[7] * 105;
+    auto alt_cost = [&](const int *a) -> unsigned {
+        unsigned c = 0;
+#pragma unroll
+        for (int m = 0; m < 5; m++) c += a[3 + m] * a[3 + m];
+        c *= 105;
+#pragma unroll
+        for (int m = 0; m < 3; m++) c += (a[m] * a[m] + a[10 - m] * a[10 - m]) * div_table[2 * m + 1];
+        return c;
+    };
+    cost[1] = alt_cost(al0); cost[3] = alt_cost(al1); cost[5] = alt_cost(al2); cost[7] = alt_cost(al3);
+    int best = 0;
+    unsigned best_cost = cost[0];
+#pragma unroll
+    for (int n = 1; n < 8; n++)
+        if (cost[n] > best_cost) { best_cost = cost[n]; best = n; }
+    unsigned opp = 0;
+#pragma unroll
+    for (int n = 0; n < 8; n++) if (n == (best ^ 4)) opp = cost[n];
+    *var = (best_cost - opp) >> 10;
+    return best;
+}
+
+__device__ __forceinline__ int cdef_adjust_strength(int strength, unsigned var) {  // src/cdef_apply_tmpl.c:92-96
+    if (!var) return 0;
+    const int i = (var >> 6) ? imin(ulog2(var >> 6), 12) : 0;
+    return (strength * (4 + i) + 8) >> 4;
+}
+
+
+struct CdefBlk {  // per 8x8 luma block of the tile
+    int16_t y_pri, y_sec, uv_pri, uv_sec;
+    int8_t dir, uvdir, do_y, do_uv;
+};
+
+template <typename BD>
+__device__ void cdef_stage_tile(int16_t *tile, const uint8_t *plane, int64_t stride, int x0, int y0, int tw, int th,
+                                int fw, int fh) {
+    using pixel = typename BD::pixel;
+    const int cols = tw + 4, rows = th + 4;
+    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
+        const int r = i / cols, c = i - r * cols;
+        const int y = y0 + r - 2, x = x0 + c - 2;
+        int16_t v = CDEF_SENTINEL;
+        if (x >= 0 && y >= 0 && x < fw && y < fh) v = (int16_t)((const pixel *)(plane + (int64_t)y * stride))[x];
+        tile[r * CDEF_PITCH + c] = v;
+    }
+}
+
+template <typename BD>
+__global__ void __launch_bounds__(256)
+cdef_frame_kernel(Rb200Planes src, Rb200Planes dst, CdefFrameParams P, const Rb200Av1Filter *__restrict__ masks,
+                  int bdmax) {
+    using pixel = typename BD::pixel;
+    __shared__ int16_t tile[CDEF_PITCH * CDEF_PITCH];
+    __shared__ CdefBlk blk[64];
+    const int sbx = blockIdx.x, sby = blockIdx.y;  // 64x64 units
+    const int x0 = sbx * 64, y0 = sby * 64;
+    const int fw = P.bw * 4, fh = P.bh * 4;
+    const int tw = imin(64, fw - x0), th = imin(64, fh - y0);
+
+    const Rb200Av1Filter &m = masks[(sby >> 1) * P.sb128w + (sbx >> 1)];
+    const int cdef_idx = m.cdef_idx[((sby & 1) << 1) + (sbx & 1)];
+    const int y_lvl = cdef_idx >= 0 ? P.y_strength[cdef_idx] : 0;
+    const int uv_lvl = cdef_idx >= 0 ? P.uv_strength[cdef_idx] : 0;
+    const bool sb_on = cdef_idx >= 0 && (y_lvl || uv_lvl);
+
+    // ---- luma
+    cdef_stage_tile<BD>(tile, (const uint8_t *)src.data[0], src.stride[0], x0, y0, tw, th, fw, fh);
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        const int bx = threadIdx.x & 7, by = threadIdx.x >> 3;  // 8x8 block inside the tile
+        CdefBlk b = {};
+        if (sb_on && bx * 8 < tw && by * 8 < th) {
+            // noskip_mask row = 8-pixel row pair inside the sb128, bits = 4-pixel columns inside the sb128
+            const int by4 = (y0 >> 2) + by * 2, bx4 = (x0 >> 2) + bx * 2;
+            const uint16_t *row = m.noskip_mask[(by4 & 30) >> 1];
+            const unsigned nm = ((unsigned)row[1] << 16) | row[0];
+            if (nm & (3u << (bx4 & 30))) {
+                const int y_pri = (y_lvl >> 2) << P.bdmin8;
+                int y_sec = y_lvl & 3; y_sec += y_sec == 3; y_sec <<= P.bdmin8;
+                const int uv_pri = (uv_lvl >> 2) << P.bdmin8;
+                int uv_sec = uv_lvl & 3; uv_sec += uv_sec == 3; uv_sec <<= P.bdmin8;
+                int dir = 0; unsigned var = 0;
+                if (y_pri || uv_pri) dir = cdef_find_dir(tile + (2 + by * 8) * CDEF_PITCH + 2 + bx * 8, CDEF_PITCH, P.bdmin8, &var);
+                if (y_pri) {
+                    const int adj = cdef_adjust_strength(y_pri, var);
+                    if (adj || y_sec) { b.do_y = 1; b.y_pri = (int16_t)adj; b.y_sec = (int16_t)y_sec; b.dir = (int8_t)dir; }
+                } else if (y_sec) {
+                    b.do_y = 1; b.y_pri = 0; b.y_sec = (int16_t)y_sec; b.dir = 0;
+                }
+                if (uv_lvl) {
+                    b.do_uv = 1; b.uv_pri = (int16_t)uv_pri; b.uv_sec = (int16_t)uv_sec;
+                    // 4:2:2 remaps directions (src/cdef_apply_tmpl.c:113-115)
+                    const int d422 = (0x66654207 >> (4 * dir)) & 7;
+                    b.uvdir = (int8_t)(uv_pri ? (P.layout_422 ? d422 : dir) : 0);
+                }
+            }
+        }
+        blk[threadIdx.x] = b;
+    }
+    __syncthreads();
+    {
+        uint8_t *dbase = (uint8_t *)dst.data[0];
+        for (int i = threadIdx.x; i < th * tw; i += 256) {
+            const int r = i / tw, c = i - r * tw;
+            const CdefBlk b = blk[(r >> 3) * 8 + (c >> 3)];
+            const int16_t *t = tile + (2 + r) * CDEF_PITCH + 2 + c;
+            int v = t[0];
+            if (b.do_y) v = cdef_filter_px(t, CDEF_PITCH, b.y_pri, b.y_sec, b.dir, P.damping, P.bdmin8);
+            ((pixel *)(dbase + (int64_t)(y0 + r) * dst.stride[0]))[x0 + c] = (pixel)v;
+        }
+    }
+    // ---- chroma
+    for (int p = 1; p < P.n_planes; p++) {
+        __syncthreads();
+        const int cx0 = x0 >> P.ss_hor, cy0 = y0 >> P.ss_ver;
+        const int ctw = tw >> P.ss_hor, cth = th >> P.ss_ver, cfw = fw >> P.ss_hor, cfh = fh >> P.ss_ver;
+        cdef_stage_tile<BD>(tile, (const uint8_t *)src.data[p], src.stride[p], cx0, cy0, ctw, cth, cfw, cfh);
+        __syncthreads();
+        uint8_t *dbase = (uint8_t *)dst.data[p];
+        for (int i = threadIdx.x; i < cth * ctw; i += 256) {
+            const int r = i / ctw, c = i - r * ctw;
+            const CdefBlk b = blk[(r >> (3 - P.ss_ver)) * 8 + (c >> (3 - P.ss_hor))];
+            const int16_t *t = tile + (2 + r) * CDEF_PITCH + 2 + c;
+            int v = t[0];
+            if (b.do_uv) v = cdef_filter_px(t, CDEF_PITCH, b.uv_pri, b.uv_sec, b.uvdir, P.damping - 1, P.bdmin8);
+            ((pixel *)(dbase + (int64_t)(cy0 + r) * dst.stride[p]))[cx0 + c] = (pixel)v;
+        }
+    }
+}
+
+// ---- per-call kernels
+template <typename BD>
+__global__ void cdef_dir_kernel(const uint8_t *src, int64_t stride, int bdmax, int *out /* dir, var */) {
+    using pixel = typename BD::pixel;
+    __shared__ int16_t t[64];
+    if (threadIdx.x < 64) t[threadIdx.x] = (int16_t)((const pixel *)(src + (int64_t)(threadIdx.x >> 3) * stride))[threadIdx.x & 7];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned var;
+        out[0] = cdef_find_dir(t, 8, BD::hbd ? bpc_from_max(bdmax) - 8 : 0, &var);
+        out[1] = (int)var;
+    }
+}
+
+// padding() + filter of one w x h block.  src/cdef_tmpl.c:55-102
+template <typename BD>
+__global__ void cdef_fb_kernel(uint8_t *dst, int64_t stride, const uint8_t *left /* [h][2] */,
+                               const uint8_t *top /* 2 rows x (w+4), from x=-2 */, const uint8_t *bottom, int w, int h,
+                               int pri, int sec, int dir, int damping, unsigned edges, int bdmax) {
+    using pixel = typename BD::pixel;
+    __shared__ int16_t tile[12 * 12];
+    const int cols = w + 4, rows = h + 4;
+    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
+        const int r = i / cols, c = i - r * cols;
+        const int y = r - 2, x = c - 2;
+        bool avail = true;
+        if (y < 0 && !(edges & RB200_CDEF_HAVE_TOP)) avail = false;
+        if (y >= h && !(edges & RB200_CDEF_HAVE_BOTTOM)) avail = false;
+        if (x < 0 && !(edges & RB200_CDEF_HAVE_LEFT)) avail = false;
+        if (x >= w && !(edges & RB200_CDEF_HAVE_RIGHT)) avail = false;
+        int16_t v = CDEF_SENTINEL;
+        if (avail) {
+            if (y < 0) v = (int16_t)((const pixel *)top)[(y + 2) * cols + c];
+            else if (y >= h) v = (int16_t)((const pixel *)bottom)[(y - h) * cols + c];
+            else if (x < 0) v = (int16_t)((const pixel *)left)[y * 2 + 2 + x];
+            else v = (int16_t)((const pixel *)(dst + (int64_t)y * stride))[x];  // x >= w: right neighbour, in dst rect
+        }
+        tile[r * 12 + c] = v;
+    }
+    __syncthreads();
+    const int bdmin8 = BD::hbd ? bpc_from_max(bdmax) - 8 : 0;
+    for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
+        const int r = i / w, c = i - r * w;
+        const int v = cdef_filter_px(tile + (2 + r) * 12 + 2 + c, 12, pri, sec, dir, damping, bdmin8);
+        ((pixel *)(dst + (int64_t)r * stride))[c] = (pixel)v;
+    }
+}
+
+int cdef_frame_launch(const Rb200Planes &src, const Rb200Planes &dst, const CdefFrameParams &P,
+                      const Rb200Av1Filter *masks, int bdmax, cudaStream_t st) {
+    dim3 grid((P.bw * 4 + 63) / 64, (P.bh * 4 + 63) / 64);
+    if (bdmax > 255) cdef_frame_kernel<BD16><<<grid, 256, 0, st>>>(src, dst, P, masks, bdmax);
+    else cdef_frame_kernel<BD8><<<grid, 256, 0, st>>>(src, dst, P, masks, bdmax);
+    RB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace rb200
+
+using namespace rb200;
+
+extern "C" int rb200_cdef_dir(const void *src, ptrdiff_t stride, unsigned *var, int bdmax, int *dir_out) {
+    if (!src || !var || !dir_out) return set_error(-22, "cdef_dir: bad argument");
+    const size_t px = bdmax > 255 ? 2 : 1;
+    HostCall hc(4096);
+    DevRect rect;
+    if (hc.rect_up(rect, src, stride, 8 * px, 8)) return hc.err;
+    int *d_out = (int *)hc.dev(8);
+    if (hc.err) return hc.err;
+    if (bdmax > 255) cdef_dir_kernel<BD16><<<1, 64, 0, hc.stream()>>>(rect.dptr, rect.dpitch, bdmax, d_out);
+    else cdef_dir_kernel<BD8><<<1, 64, 0, hc.stream()>>>(rect.dptr, rect.dpitch, bdmax, d_out);
+    int *h_out = (int *)hc.down(d_out, 8);
+    if (hc.sync()) return hc.err;
+    *dir_out = h_out[0];
+    *var = (unsigned)h_out[1];
+    return 0;
+}
+
+extern "C" int rb200_cdef_fb(int idx, void *dst, ptrdiff_t stride, const void *left, const void *top,
+                             const void *bottom, int pri, int sec, int dir, int damping, uint32_t edges, int bdmax) {
+    if (idx < 0 || idx > 2 || !dst || (!pri && !sec) || dir < 0 || dir > 7) return set_error(-22, "cdef_fb: bad argument");
+    const int w = idx == 0 ? 8 : 4, h = idx == 2 ? 4 : 8;
+    const size_t px = bdmax > 255 ? 2 : 1;
+    HostCall hc(8192);
+    // destination rectangle incl. the 2 right-neighbour columns when they exist
+    const int cols = w + ((edges & RB200_CDEF_HAVE_RIGHT) ? 2 : 0);
+    DevRect rect;
+    if (hc.rect_up(rect, dst, stride, cols * px, h)) return hc.err;
+    // top / bottom: 2 rows of (w + 4) pixels starting at x = -2, gathered where the reference may read them
+    uint8_t rows2[2][2][12 * 2] = {};
+    const int xs = (edges & RB200_CDEF_HAVE_LEFT) ? -2 : 0, xe = w + ((edges & RB200_CDEF_HAVE_RIGHT) ? 2 : 0);
+    for (int tb = 0; tb < 2; tb++) {
+        const uint8_t *p = (const uint8_t *)(tb ? bottom : top);
+        if (!(edges & (tb ? RB200_CDEF_HAVE_BOTTOM : RB200_CDEF_HAVE_TOP)) || !p) continue;
+        for (int r = 0; r < 2; r++)
+            memcpy(&rows2[tb][r][(xs + 2) * px], p + (int64_t)r * stride + (int64_t)xs * (int64_t)px, (size_t)(xe - xs) * px);
+    }
+    uint8_t lbuf[8 * 2 * 2] = {};
+    if ((edges & RB200_CDEF_HAVE_LEFT) && left) memcpy(lbuf, left, (size_t)h * 2 * px);
+    // repack rows2 to pitch (w+4) pixels
+    uint8_t tbuf[2][2 * 12 * 2];
+    for (int tb = 0; tb < 2; tb++)
+        for (int r = 0; r < 2; r++) memcpy(&tbuf[tb][(size_t)r * (w + 4) * px], rows2[tb][r], (size_t)(w + 4) * px);
+    const uint8_t *d_left = (const uint8_t *)hc.up(lbuf, sizeof(lbuf));
+    const uint8_t *d_top = (const uint8_t *)hc.up(tbuf[0], sizeof(tbuf[0]));
+    const uint8_t *d_bot = (const uint8_t *)hc.up(tbuf[1], sizeof(tbuf[1]));
+    if (hc.err) return hc.err;
+    if (bdmax > 255) cdef_fb_kernel<BD16><<<1, 64, 0, hc.stream()>>>(rect.dptr, rect.dpitch, d_left, d_top, d_bot, w, h, pri, sec, dir, damping, edges, bdmax);
+    else cdef_fb_kernel<BD8><<<1, 64, 0, hc.stream()>>>(rect.dptr, rect.dpitch, d_left, d_top, d_bot, w, h, pri, sec, dir, damping, edges, bdmax);
+    // only the w x h block is written back
+    DevRect out = rect;
+    hc.rect_down(rect);
+    if (hc.sync()) return hc.err;
+    rect.row_bytes = w * px;
+    rect.finish(dst);
+    (void)out;
+    return 0;
+}
+
+namespace {
+int dir_slot(const void *src, ptrdiff_t stride, unsigned *var, int bd) {
+    int d = 0;
+    if (rb200_cdef_dir(src, stride, var, bd, &d)) rb200_report_fatal("cdef_dir");
+    return d;
+}
+template <int IDX>
+void fb_slot(void *dst, ptrdiff_t stride, const void *left, const void *top, const void *bottom, int pri, int sec,
+             int dir, int damping, uint32_t edges, int bd) {
+    if (rb200_cdef_fb(IDX, dst, stride, left, top, bottom, pri, sec, dir, damping, edges, bd)) rb200_report_fatal("cdef_fb");
+}
+}  // namespace
+
+extern "C" void rb200_cdef_dsp_init(Rb200CdefDSPContext *c, int bpc) {
+    (void)bpc;
+    c->dir = &dir_slot;
+    c->fb[0] = &fb_slot<0>; c->fb[1] = &fb_slot<1>; c->fb[2] = &fb_slot<2>;
+}

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/rav1d_b200.h"
 
@@ -48,6 +49,36 @@ __host__ __device__ __forceinline__ uint8_t *plane_ptr(const Rb200Planes &p, int
 __host__ __device__ __forceinline__ int64_t plane_stride(const Rb200Planes &p, int pl) {
     return pl == 0 ? p.stride[0] : (pl == 1 ? p.stride[1] : p.stride[2]);
 }
+
+// ---- stage launchers (defined in itx.cu, mc.cu, lf.cu, cdef.cu, lr.cu; used by frame.cu)
+struct CdefFrameParams {
+    int bw, bh;        // frame size in 4-pixel units (even)
+    int sb128w;
+    int ss_hor, ss_ver;
+    int n_planes;
+    int damping;       // frame_hdr.cdef.damping + bitdepth_min_8
+    int bdmin8;
+    int y_strength[8], uv_strength[8];
+    int layout_422;
+};
+struct LrFrameParams {
+    int w, h;             // plane size in pixels
+    int ss_hor, ss_ver;   // of this plane
+    int plane;
+    int unit_log2;
+    int sb128, sbh, sr_sb128w;
+};
+int itx_launch(int tx, const Rb200Planes &planes, const void *cf, const Rb200ItxItem *items, int n, int bdmax,
+               cudaStream_t st);
+int mc_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int ss_hor,
+                    int ss_ver, const Rb200McItem *d_items, int n, int bdmax, cudaStream_t st);
+int deblock_frame_launch(const Rb200Planes &pl, int n_planes, int w4, int h4, int sb128w, int b4_stride, int ss_hor,
+                         int ss_ver, bool do_uv, const Rb200Av1Filter *masks, const uint8_t (*lvl)[4],
+                         const Rb200Av1FilterLUT *lut, int bdmax, cudaStream_t st, int *launches);
+int cdef_frame_launch(const Rb200Planes &src, const Rb200Planes &dst, const CdefFrameParams &P,
+                      const Rb200Av1Filter *masks, int bdmax, cudaStream_t st);
+int lr_plane_launch(const uint8_t *cdef, const uint8_t *dbl, uint8_t *out, int64_t stride, const LrFrameParams &P,
+                    const Rb200Av1Restoration *lrm, int bdmax, cudaStream_t st);
 
 // ---- error plumbing --------------------------------------------------
 int set_error(int code, const char *fmt, ...);
@@ -95,6 +126,54 @@ struct DevRect {
     // queue the copy back to the same host rectangle (call st sync afterwards, then finish())
     int download(Staging &st);
     void finish(void *host_row0);  // scatter staged rows back
+};
+
+
+// Scope of one synchronous host-pointer DSP call: reserves the calling thread's
+// staging arenas, mirrors host buffers on the device and copies results back.
+struct HostCall {
+    Staging &st;
+    int err = 0;
+    explicit HostCall(size_t bytes) : st(staging()) { err = st.begin(bytes + 4096, bytes + 4096); }
+    cudaStream_t stream() const { return st.stream; }
+    // host array -> device (returns device pointer or nullptr on error)
+    void *up(const void *h, size_t n) {
+        if (err) return nullptr;
+        void *d = st.dalloc(n), *s = st.halloc(n);
+        if (!d || !s) { err = set_error(-12, "staging arena too small"); return nullptr; }
+        memcpy(s, h, n);
+        cudaError_t e = cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st.stream);
+        if (e != cudaSuccess) { err = cuda_fail(e, "cudaMemcpyAsync(H2D)", __FILE__, __LINE__); return nullptr; }
+        return d;
+    }
+    // device scratch whose content is fetched back with down()
+    void *dev(size_t n) {
+        if (err) return nullptr;
+        void *d = st.dalloc(n);
+        if (!d) err = set_error(-12, "staging arena too small");
+        return d;
+    }
+    // queue D2H of n bytes into a pinned stage; valid after sync()
+    void *down(const void *d, size_t n) {
+        if (err) return nullptr;
+        void *s = st.halloc(n);
+        if (!s) { err = set_error(-12, "staging arena too small"); return nullptr; }
+        cudaError_t e = cudaMemcpyAsync(s, d, n, cudaMemcpyDeviceToHost, st.stream);
+        if (e != cudaSuccess) { err = cuda_fail(e, "cudaMemcpyAsync(D2H)", __FILE__, __LINE__); return nullptr; }
+        return s;
+    }
+    int rect_up(DevRect &r, const void *row0, int64_t stride, size_t row_bytes, int rows) {
+        if (err) return err;
+        return err = r.upload(st, row0, stride, row_bytes, rows);
+    }
+    int rect_down(DevRect &r) { if (err) return err; return err = r.download(st); }
+    int sync() {
+        if (err) return err;
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st.stream);
+        if (e != cudaSuccess) err = cuda_fail(e, "kernel/stream sync", __FILE__, __LINE__);
+        return err;
+    }
 };
 
 }  // namespace rb200

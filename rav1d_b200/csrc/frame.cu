@@ -1,0 +1,345 @@
+// Frame-level pipeline: device-resident planes, per-frame batch staging and
+// stream-ordered stage launches.
+//
+// This is the B200 counterpart of the reference's pass-2 reconstruction plus the
+// filter tasks of its scheduler (TileReconstruction -> DeblockCols -> DeblockRows
+// -> Cdef -> LoopRestoration, src/thread_task.rs:1048-1241; single-thread form
+// rav1d_decode_frame_main src/decode.rs:4497-4570 calling filter_sbrow
+// src/recon.rs:4319-4338).  The per-sbrow wavefront of the CPU becomes
+// whole-frame launches ordered on one CUDA stream:
+//
+//   H2D(coef, items, masks)  ->  MC (prediction into `cur`)  ->  itx add (per tx size)
+//   -> deblock column edges -> deblock row edges (in place on `cur`)
+//   -> CDEF (cur -> p2, out of place) -> loop restoration (p2 + cur -> p3)
+//
+// and the in-place backups of the CPU (cdef_line_buf, lr_line_buf, left[][])
+// become three ping-pong plane sets.  The front end (entropy decode, mode
+// parsing, lf-mask generation) stays on the host and fills the pinned staging
+// arrays in the reference's own formats (Av1Filter, level[4], Av1Restoration,
+// packed cf).
+#include "common.cuh"
+#include <new>
+
+struct Rb200Frame {
+    Rb200FrameHeader hdr;
+    Rb200FrameGeometry g;
+    int bdmax;
+    size_t px, cs;
+    cudaStream_t stream;
+    // device plane sets: 0 = cur (recon, deblocked in place), 1 = CDEF output, 2 = LR output
+    uint8_t *plane_mem[3];
+    Rb200Planes planes[3];
+    Rb200Planes out;
+    Rb200Planes refs[8];
+    int n_refs;
+    // batch staging: pinned host + device mirror
+    size_t max_coefs; int max_itx, max_mc;
+    void *h_coef, *d_coef;
+    Rb200ItxItem *h_itx, *d_itx;
+    Rb200McItem *h_mc, *d_mc;
+    Rb200Av1Filter *h_masks, *d_masks;
+    uint8_t (*h_lvl)[4], (*d_lvl)[4];
+    Rb200Av1FilterLUT *h_lut, *d_lut;
+    Rb200Av1Restoration *h_lr, *d_lr;
+    size_t n_masks, n_lvl;
+    int launches;
+};
+
+using namespace rb200;
+
+namespace {
+
+int alloc_planes(Rb200Frame *f, int which) {
+    const size_t ysz = (size_t)f->g.stride[0] * f->g.plane_h[0];
+    const size_t uvsz = f->g.n_planes > 1 ? (size_t)f->g.stride[1] * f->g.plane_h[1] : 0;
+    RB_CUDA(cudaMalloc((void **)&f->plane_mem[which], ysz + 2 * uvsz + 256));
+    RB_CUDA(cudaMemsetAsync(f->plane_mem[which], 0, ysz + 2 * uvsz + 256, f->stream));
+    Rb200Planes &p = f->planes[which];
+    p.data[0] = f->plane_mem[which]; p.stride[0] = f->g.stride[0];
+    p.data[1] = uvsz ? f->plane_mem[which] + ysz : nullptr;
+    p.data[2] = uvsz ? f->plane_mem[which] + ysz + uvsz : nullptr;
+    p.stride[1] = p.stride[2] = uvsz ? f->g.stride[1] : 0;
+    return 0;
+}
+
+template <typename T>
+int alloc_pair(T **h, T **d, size_t n) {
+    const size_t bytes = (n ? n : 1) * sizeof(T);
+    RB_CUDA(cudaMallocHost((void **)h, bytes));
+    memset(*h, 0, bytes);
+    RB_CUDA(cudaMalloc((void **)d, bytes));
+    RB_CUDA(cudaMemset(*d, 0, bytes));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int rb200_frame_create(Rb200Frame **out, const Rb200FrameHeader *hdr, size_t max_coefs, int max_itx,
+                                  int max_mc) {
+    if (!out || !hdr) return set_error(-22, "frame_create: null argument");
+    if (hdr->width < 1 || hdr->height < 1 || hdr->width > 16384 || hdr->height > 16384 ||
+        (hdr->bpc != 8 && hdr->bpc != 10 && hdr->bpc != 12) || hdr->layout < 0 || hdr->layout > 3)
+        return set_error(-22, "frame_create: bad header");
+    Rb200Frame *f = new (std::nothrow) Rb200Frame();
+    if (!f) return set_error(-12, "frame_create: out of memory");
+    memset(f, 0, sizeof(*f));
+    f->hdr = *hdr;
+    f->bdmax = (1 << hdr->bpc) - 1;
+    f->px = hdr->bpc > 8 ? 2 : 1;
+    f->cs = hdr->bpc > 8 ? 4 : 2;
+    Rb200FrameGeometry &g = f->g;
+    // src/decode.rs:4880-4905 (dav1d_submit_frame): bw/bh in 4-px units rounded to 8 px
+    g.bw = ((hdr->width + 7) >> 3) << 1;
+    g.bh = ((hdr->height + 7) >> 3) << 1;
+    g.w4 = (hdr->width + 3) >> 2;
+    g.h4 = (hdr->height + 3) >> 2;
+    g.sb128w = (g.bw + 31) >> 5;
+    g.sb128h = (g.bh + 31) >> 5;
+    const int sb_shift = 4 + hdr->sb128;
+    g.sbh = (g.bh + (1 << sb_shift) - 1) >> sb_shift;
+    g.b4_stride = (g.bw + 31) & ~31;
+    g.ss_hor = hdr->layout != RB200_LAYOUT_I444 && hdr->layout != RB200_LAYOUT_I400;
+    g.ss_ver = hdr->layout == RB200_LAYOUT_I420;
+    g.n_planes = hdr->layout == RB200_LAYOUT_I400 ? 1 : 3;
+    // picture allocation: dimensions aligned up to 128 (src/picture.rs:91-137); the device
+    // planes are the library's own, so no extra 64-byte anti-aliasing pad is needed.
+    const int aw = (hdr->width + 127) & ~127, ah = (hdr->height + 127) & ~127;
+    g.stride[0] = (int64_t)aw * (int64_t)f->px;
+    g.stride[1] = g.n_planes > 1 ? (int64_t)(aw >> g.ss_hor) * (int64_t)f->px : 0;
+    g.plane_h[0] = ah;
+    g.plane_h[1] = g.n_planes > 1 ? ah >> g.ss_ver : 0;
+    f->max_coefs = max_coefs; f->max_itx = max_itx; f->max_mc = max_mc;
+    f->n_masks = (size_t)g.sb128w * g.sb128h;
+    f->n_lvl = (size_t)g.b4_stride * 32 * g.sb128h + 32;  // + guard for the level fallback of row/col 0
+    int r = 0;
+    cudaError_t e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { r = cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); delete f; return r; }
+    for (int i = 0; i < 3 && !r; i++) r = alloc_planes(f, i);
+    if (!r) {
+        RB_CUDA(cudaMallocHost(&f->h_coef, (max_coefs ? max_coefs : 1) * f->cs));
+        memset(f->h_coef, 0, (max_coefs ? max_coefs : 1) * f->cs);
+        RB_CUDA(cudaMalloc(&f->d_coef, (max_coefs ? max_coefs : 1) * f->cs));
+    }
+    if (!r) r = alloc_pair(&f->h_itx, &f->d_itx, (size_t)max_itx);
+    if (!r) r = alloc_pair(&f->h_mc, &f->d_mc, (size_t)max_mc);
+    if (!r) r = alloc_pair(&f->h_masks, &f->d_masks, f->n_masks);
+    if (!r) r = alloc_pair((uint8_t **)&f->h_lvl, (uint8_t **)&f->d_lvl, f->n_lvl * 4);
+    if (!r) r = alloc_pair(&f->h_lut, &f->d_lut, 1);
+    if (!r) r = alloc_pair(&f->h_lr, &f->d_lr, f->n_masks);
+    if (!r) { e = cudaStreamSynchronize(f->stream); if (e != cudaSuccess) r = cuda_fail(e, "sync", __FILE__, __LINE__); }
+    if (r) { rb200_frame_destroy(f); return r; }
+    f->out = f->planes[0];
+    *out = f;
+    return 0;
+}
+
+extern "C" int rb200_frame_destroy(Rb200Frame *f) {
+    if (!f) return 0;
+    if (f->stream) cudaStreamSynchronize(f->stream);
+    for (int i = 0; i < 3; i++) if (f->plane_mem[i]) cudaFree(f->plane_mem[i]);
+    if (f->h_coef) cudaFreeHost(f->h_coef);
+    if (f->d_coef) cudaFree(f->d_coef);
+    if (f->h_itx) cudaFreeHost(f->h_itx);
+    if (f->d_itx) cudaFree(f->d_itx);
+    if (f->h_mc) cudaFreeHost(f->h_mc);
+    if (f->d_mc) cudaFree(f->d_mc);
+    if (f->h_masks) cudaFreeHost(f->h_masks);
+    if (f->d_masks) cudaFree(f->d_masks);
+    if (f->h_lvl) cudaFreeHost(f->h_lvl);
+    if (f->d_lvl) cudaFree(f->d_lvl);
+    if (f->h_lut) cudaFreeHost(f->h_lut);
+    if (f->d_lut) cudaFree(f->d_lut);
+    if (f->h_lr) cudaFreeHost(f->h_lr);
+    if (f->d_lr) cudaFree(f->d_lr);
+    if (f->stream) cudaStreamDestroy(f->stream);
+    delete f;
+    return 0;
+}
+
+extern "C" int rb200_frame_geometry(const Rb200Frame *f, Rb200FrameGeometry *g) {
+    if (!f || !g) return set_error(-22, "frame_geometry: null argument");
+    *g = f->g;
+    return 0;
+}
+extern "C" void *rb200_frame_coef_buffer(Rb200Frame *f) { return f ? f->h_coef : nullptr; }
+extern "C" Rb200ItxItem *rb200_frame_itx_items(Rb200Frame *f) { return f ? f->h_itx : nullptr; }
+extern "C" Rb200McItem *rb200_frame_mc_items(Rb200Frame *f) { return f ? f->h_mc : nullptr; }
+extern "C" Rb200Av1Filter *rb200_frame_lf_masks(Rb200Frame *f) { return f ? f->h_masks : nullptr; }
+// The level array is handed out one 4x4 row (b4_stride entries) past its start so that the
+// reference's `l[-b4_stride]` fallback for the first row stays inside the allocation.
+extern "C" uint8_t (*rb200_frame_lf_levels(Rb200Frame *f))[4] { return f ? f->h_lvl + 32 : nullptr; }
+extern "C" Rb200Av1FilterLUT *rb200_frame_lf_lut(Rb200Frame *f) { return f ? f->h_lut : nullptr; }
+extern "C" Rb200Av1Restoration *rb200_frame_lr_masks(Rb200Frame *f) { return f ? f->h_lr : nullptr; }
+extern "C" void *rb200_frame_stream(Rb200Frame *f) { return f ? (void *)f->stream : nullptr; }
+extern "C" int rb200_frame_last_launches(const Rb200Frame *f) { return f ? f->launches : 0; }
+
+extern "C" int rb200_frame_set_ref(Rb200Frame *f, int slot, const Rb200Planes *planes) {
+    if (!f || slot < 0 || slot > 7 || !planes) return set_error(-22, "frame_set_ref: bad argument");
+    f->refs[slot] = *planes;
+    if (slot + 1 > f->n_refs) f->n_refs = slot + 1;
+    return 0;
+}
+
+extern "C" int rb200_frame_stage_planes(Rb200Frame *f, int which, Rb200Planes *out) {
+    if (!f || which < 0 || which > 2 || !out) return set_error(-22, "frame_stage_planes: bad argument");
+    *out = f->planes[which];
+    return 0;
+}
+extern "C" int rb200_frame_output_planes(Rb200Frame *f, Rb200Planes *out) {
+    if (!f || !out) return set_error(-22, "frame_output_planes: bad argument");
+    *out = f->out;
+    return 0;
+}
+
+static int plane_rows(const Rb200Frame *f, int p) {
+    return p ? (f->hdr.height + f->g.ss_ver) >> f->g.ss_ver : f->hdr.height;
+}
+static size_t plane_row_bytes(const Rb200Frame *f, int p) {
+    return (size_t)(p ? (f->hdr.width + f->g.ss_hor) >> f->g.ss_hor : f->hdr.width) * f->px;
+}
+
+extern "C" int rb200_frame_upload_planes(Rb200Frame *f, int which, const void *const data[3],
+                                         const ptrdiff_t stride[2]) {
+    if (!f || which < 0 || which > 2 || !data || !stride) return set_error(-22, "frame_upload_planes: bad argument");
+    for (int p = 0; p < f->g.n_planes; p++) {
+        const int rows = plane_rows(f, p);
+        const ptrdiff_t hs = stride[p ? 1 : 0];
+        const uint8_t *src = (const uint8_t *)data[p];
+        if (hs < 0) src += (int64_t)(rows - 1) * hs;  // lowest address; copy flipped below
+        if (hs >= 0) {
+            RB_CUDA(cudaMemcpy2DAsync(f->planes[which].data[p], (size_t)f->planes[which].stride[p], src, (size_t)hs,
+                                      plane_row_bytes(f, p), rows, cudaMemcpyHostToDevice, f->stream));
+        } else {
+            for (int y = 0; y < rows; y++)
+                RB_CUDA(cudaMemcpyAsync((uint8_t *)f->planes[which].data[p] + (int64_t)y * f->planes[which].stride[p],
+                                        (const uint8_t *)data[p] + (int64_t)y * hs, plane_row_bytes(f, p),
+                                        cudaMemcpyHostToDevice, f->stream));
+        }
+    }
+    RB_CUDA(cudaStreamSynchronize(f->stream));
+    return 0;
+}
+
+extern "C" int rb200_frame_readback(Rb200Frame *f, void *const data[3], const ptrdiff_t stride[2]) {
+    if (!f || !data || !stride) return set_error(-22, "frame_readback: bad argument");
+    for (int p = 0; p < f->g.n_planes; p++) {
+        const int rows = plane_rows(f, p);
+        const ptrdiff_t hs = stride[p ? 1 : 0];
+        if (hs >= 0) {
+            RB_CUDA(cudaMemcpy2DAsync(data[p], (size_t)hs, f->out.data[p], (size_t)f->out.stride[p],
+                                      plane_row_bytes(f, p), rows, cudaMemcpyDeviceToHost, f->stream));
+        } else {
+            for (int y = 0; y < rows; y++)
+                RB_CUDA(cudaMemcpyAsync((uint8_t *)data[p] + (int64_t)y * hs,
+                                        (const uint8_t *)f->out.data[p] + (int64_t)y * f->out.stride[p],
+                                        plane_row_bytes(f, p), cudaMemcpyDeviceToHost, f->stream));
+        }
+    }
+    RB_CUDA(cudaStreamSynchronize(f->stream));
+    return 0;
+}
+
+extern "C" int rb200_frame_wait(Rb200Frame *f) {
+    if (!f) return set_error(-22, "frame_wait: null frame");
+    RB_CUDA(cudaStreamSynchronize(f->stream));
+    RB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t itx_counts[RB200_N_RECT_TX_SIZES],
+                                  int n_mc, int stages, int upload) {
+    if (!f) return set_error(-22, "frame_submit: null frame");
+    const Rb200FrameHeader &h = f->hdr;
+    const Rb200FrameGeometry &g = f->g;
+    cudaStream_t st = f->stream;
+    int n_itx = 0;
+    if (stages & RB200_STAGE_RECON) {
+        if (!itx_counts) return set_error(-22, "frame_submit: itx_counts required for the recon stage");
+        for (int t = 0; t < RB200_N_RECT_TX_SIZES; t++) {
+            if (itx_counts[t] < 0) return set_error(-22, "frame_submit: negative itx count");
+            n_itx += itx_counts[t];
+        }
+        if (n_coefs > f->max_coefs || n_itx > f->max_itx || n_mc > f->max_mc || n_mc < 0)
+            return set_error(-22, "frame_submit: batch larger than the frame was created for");
+        if (n_mc && f->n_refs < 1) return set_error(-22, "frame_submit: no reference picture set");
+    }
+    f->launches = 0;
+    const bool do_lf = (stages & RB200_STAGE_DEBLOCK) && (h.lf_level_y[0] || h.lf_level_y[1]);
+    const bool do_cdef = (stages & RB200_STAGE_CDEF) != 0;
+    int restore_planes = 0;
+    if (stages & RB200_STAGE_LR)
+        for (int p = 0; p < g.n_planes; p++) if (h.lr_type[p] != RB200_RESTORATION_NONE) restore_planes |= 1 << p;
+
+    // ---- host -> device: the per-frame batch
+    if (upload) {
+        if (stages & RB200_STAGE_RECON) {
+            if (n_coefs) RB_CUDA(cudaMemcpyAsync(f->d_coef, f->h_coef, n_coefs * f->cs, cudaMemcpyHostToDevice, st));
+            if (n_itx) RB_CUDA(cudaMemcpyAsync(f->d_itx, f->h_itx, (size_t)n_itx * sizeof(Rb200ItxItem), cudaMemcpyHostToDevice, st));
+            if (n_mc) RB_CUDA(cudaMemcpyAsync(f->d_mc, f->h_mc, (size_t)n_mc * sizeof(Rb200McItem), cudaMemcpyHostToDevice, st));
+        }
+        if (do_lf || do_cdef)
+            RB_CUDA(cudaMemcpyAsync(f->d_masks, f->h_masks, f->n_masks * sizeof(Rb200Av1Filter), cudaMemcpyHostToDevice, st));
+        if (do_lf) {
+            RB_CUDA(cudaMemcpyAsync(f->d_lvl, f->h_lvl, f->n_lvl * 4, cudaMemcpyHostToDevice, st));
+            RB_CUDA(cudaMemcpyAsync(f->d_lut, f->h_lut, sizeof(Rb200Av1FilterLUT), cudaMemcpyHostToDevice, st));
+        }
+        if (restore_planes)
+            RB_CUDA(cudaMemcpyAsync(f->d_lr, f->h_lr, f->n_masks * sizeof(Rb200Av1Restoration), cudaMemcpyHostToDevice, st));
+    }
+
+    int r;
+    // ---- reconstruction: prediction, then residual add
+    if (stages & RB200_STAGE_RECON) {
+        if (n_mc) {
+            if ((r = mc_batch_launch(f->planes[0], f->refs, f->n_refs, h.width, h.height, g.ss_hor, g.ss_ver, f->d_mc,
+                                     n_mc, f->bdmax, st))) return r;
+            f->launches++;
+        }
+        int off = 0;
+        for (int t = 0; t < RB200_N_RECT_TX_SIZES; t++) {
+            if (itx_counts[t]) {
+                if ((r = itx_launch(t, f->planes[0], f->d_coef, f->d_itx + off, itx_counts[t], f->bdmax, st))) return r;
+                f->launches++;
+            }
+            off += itx_counts[t];
+        }
+    }
+    f->out = f->planes[0];
+    // ---- deblock (in place): all column edges, then all row edges (src/recon.rs:4047-4170)
+    if (do_lf) {
+        if ((r = deblock_frame_launch(f->planes[0], g.n_planes, g.w4, g.h4, g.sb128w, g.b4_stride, g.ss_hor, g.ss_ver,
+                                      h.lf_level_u || h.lf_level_v, f->d_masks, f->d_lvl + 32, f->d_lut, f->bdmax, st,
+                                      &f->launches))) return r;
+    }
+    // ---- CDEF: cur -> p2 (src/recon.rs:4172-4213)
+    if (do_cdef) {
+        CdefFrameParams P;
+        P.bw = g.bw; P.bh = g.bh; P.sb128w = g.sb128w; P.ss_hor = g.ss_hor; P.ss_ver = g.ss_ver;
+        P.n_planes = g.n_planes; P.bdmin8 = h.bpc - 8; P.damping = h.cdef_damping + P.bdmin8;
+        for (int i = 0; i < 8; i++) { P.y_strength[i] = h.cdef_y_strength[i]; P.uv_strength[i] = h.cdef_uv_strength[i]; }
+        P.layout_422 = h.layout == RB200_LAYOUT_I422;
+        if ((r = cdef_frame_launch(f->planes[0], f->planes[1], P, f->d_masks, f->bdmax, st))) return r;
+        f->launches++;
+        f->out = f->planes[1];
+    }
+    // ---- loop restoration: (p2 | cur) + cur -> p3 for the restored planes (src/recon.rs:4283-4317)
+    if (restore_planes) {
+        const Rb200Planes cdefp = f->out;
+        for (int p = 0; p < g.n_planes; p++) {
+            if (!(restore_planes & (1 << p))) continue;
+            LrFrameParams P;
+            P.plane = p;
+            P.ss_hor = p ? g.ss_hor : 0; P.ss_ver = p ? g.ss_ver : 0;
+            P.w = (h.width + P.ss_hor) >> P.ss_hor; P.h = (h.height + P.ss_ver) >> P.ss_ver;
+            P.unit_log2 = h.lr_unit_size_log2[p ? 1 : 0];
+            P.sb128 = h.sb128; P.sbh = g.sbh; P.sr_sb128w = g.sb128w;
+            if ((r = lr_plane_launch((const uint8_t *)cdefp.data[p], (const uint8_t *)f->planes[0].data[p],
+                                     (uint8_t *)f->planes[2].data[p], f->planes[2].stride[p], P, f->d_lr, f->bdmax, st)))
+                return r;
+            f->launches++;
+            f->out.data[p] = f->planes[2].data[p];
+            f->out.stride[p] = f->planes[2].stride[p];
+        }
+    }
+    return 0;
+}

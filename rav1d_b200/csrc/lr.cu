@@ -1,0 +1,384 @@
+// Loop restoration (Wiener and self-guided filters) for sm_100a.
+//
+// Replaces Rav1dLoopRestorationDSPContext {wiener[2], sgr[3]} (src/looprestoration.rs:91-107;
+// wiener_rust :299, selfguided_filter :566, sgr_5x5/3x3/mix :710,785,855 ==
+// src/looprestoration_tmpl.c:41-520) and, at frame level, the per-sbrow driver
+// rav1d_lr_sbrow / lr_sbrow / lr_stripe (src/lr_apply.rs:28-329 == src/lr_apply_tmpl.c:36-202)
+// together with the stripe-boundary row backup rav1d_copy_lpf (src/lf_apply.rs:24-226).
+//
+// Frame kernel: one CTA per (32-pixel column tile) x (64-row stripe, offset by 8
+// luma rows as in the reference).  The tile plus a 3-pixel halo is staged in shared
+// memory through one sampling rule that states which version of each neighbour
+// is read: CDEF output inside the stripe, *deblocked pre-CDEF* rows
+// (two real rows, the outer one duplicated) above / below it, replicated frame
+// edges, columns clamped to the picture.  The CPU needs lr_line_buf / left[]
+// backups for that because it filters in place; here the stage is out of place
+// and the deblocked plane is simply still alive.
+#include "common.cuh"
+#include "tables.cuh"
+
+namespace rb200 {
+
+constexpr int LR_TW = 32;             // tile width
+constexpr int LR_TH = 64;             // max stripe height
+constexpr int LR_WP = LR_TW + 6;      // window pitch (38)
+constexpr int LR_WROWS = LR_TH + 6;   // 70
+constexpr int LR_AP = LR_TW + 2;      // A/B pitch (34)
+constexpr int LR_AROWS = LR_TH + 2;   // 66
+
+struct LrSmem {
+    uint16_t win[LR_WROWS * LR_WP];   // padded source window
+    union {
+        uint16_t hor[LR_WROWS * LR_TW];                                 // Wiener intermediate
+        struct { int32_t A[LR_AROWS * LR_AP]; int32_t B[LR_AROWS * LR_AP]; } s;  // SGR
+    } u;
+};
+
+struct LrUnit {
+    int kind;          // 0 none, 1 wiener, 2 sgr 5x5, 3 sgr 3x3, 4 sgr mix
+    int16_t fh[8], fv[8];
+    uint32_t s0, s1;
+    int w0, w1;
+};
+
+// lr_stripe's parameter packing, src/lr_apply.rs:59-90 == src/lr_apply_tmpl.c:55-85
+__device__ __forceinline__ LrUnit lr_unpack(const Rb200Av1RestorationUnit &u) {
+    LrUnit r;
+    r.kind = 0; r.s0 = r.s1 = 0; r.w0 = r.w1 = 0;
+    if (u.type == RB200_RESTORATION_NONE) return r;
+    if (u.type == RB200_RESTORATION_WIENER) {
+        r.kind = 1;
+        r.fh[0] = r.fh[6] = u.filter_h[0]; r.fh[1] = r.fh[5] = u.filter_h[1]; r.fh[2] = r.fh[4] = u.filter_h[2];
+        r.fh[3] = (int16_t)(-(u.filter_h[0] + u.filter_h[1] + u.filter_h[2]) * 2 + 128);  // +128 folded in for every bpc
+        r.fv[0] = r.fv[6] = u.filter_v[0]; r.fv[1] = r.fv[5] = u.filter_v[1]; r.fv[2] = r.fv[4] = u.filter_v[2];
+        r.fv[3] = (int16_t)(128 - (u.filter_v[0] + u.filter_v[1] + u.filter_v[2]) * 2);
+        r.fh[7] = r.fv[7] = 0;
+        return r;
+    }
+    const int idx = u.type - RB200_RESTORATION_SGRPROJ;
+    r.s0 = tab::k_sgr_params[idx * 2]; r.s1 = tab::k_sgr_params[idx * 2 + 1];
+    r.w0 = u.sgr_weights[0];
+    r.w1 = 128 - (u.sgr_weights[0] + u.sgr_weights[1]);
+    r.kind = 1 + (!!r.s0 + !!r.s1 * 2);  // 2: 5x5 only, 3: 3x3 only, 4: mix
+    return r;
+}
+
+// ---- Wiener on a staged window.  out(r, c, v) stores pixel v.   src/looprestoration_tmpl.c:139-195
+template <typename BD, typename Out>
+__device__ void lr_wiener_tile(LrSmem &sm, int tw, int th, const int16_t *fh, const int16_t *fv, int bdmax, Out out) {
+    const int bitdepth = BD::hbd ? bpc_from_max(bdmax) : 8;
+    const int rbh = 3 + (bitdepth == 12) * 2, rbv = 11 - (bitdepth == 12) * 2;
+    const int clip_limit = 1 << (bitdepth + 1 + 7 - rbh);
+    int FH[7], FV[7];
+#pragma unroll
+    for (int k = 0; k < 7; k++) { FH[k] = fh[k]; FV[k] = fv[k]; }
+    for (int i = threadIdx.x; i < (th + 6) * tw; i += blockDim.x) {
+        const int r = i / tw, c = i - r * tw;
+        const uint16_t *s = sm.win + r * LR_WP + c;
+        int sum = 1 << (bitdepth + 6);
+#pragma unroll
+        for (int k = 0; k < 7; k++) sum += (int)s[k] * FH[k];
+        sm.u.hor[r * LR_TW + c] = (uint16_t)iclip((sum + (1 << (rbh - 1))) >> rbh, 0, clip_limit - 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < th * tw; i += blockDim.x) {
+        const int r = i / tw, c = i - r * tw;
+        int sum = -(1 << (bitdepth + (rbv - 1)));
+#pragma unroll
+        for (int k = 0; k < 7; k++) sum += (int)sm.u.hor[(r + k) * LR_TW + c] * FV[k];
+        out(r, c, iclip((sum + (1 << (rbv - 1))) >> rbv, 0, bdmax));
+    }
+}
+
+// ---- self-guided filter: fills A/B for box size n (25 or 9) with strength s.
+// A[j][i], B[j][i] for i in [-1, tw], j in [-1, th]  (stored at [(j+1)*LR_AP + i+1])
+template <typename BD>
+__device__ void sgr_ab(LrSmem &sm, int tw, int th, int n, unsigned s, int bdmin8) {
+    const unsigned one_by_x = n == 25 ? 164 : 455;
+    const int rad = n == 25 ? 2 : 1, step = n == 25 ? 2 : 1;
+    const int cols = tw + 2, rows = (th + 2 + step - 1) / step;
+    for (int t = threadIdx.x; t < rows * cols; t += blockDim.x) {
+        const int jr = t / cols, i = t - jr * cols - 1;
+        const int j = jr * step - 1;
+        // box centred on pixel (i, j): window coordinates (j + 3, i + 3)
+        int sum = 0, sumsq = 0;
+        for (int dy = -rad; dy <= rad; dy++) {
+            const uint16_t *row = sm.win + (j + 3 + dy) * LR_WP + (i + 3);
+            for (int dx = -rad; dx <= rad; dx++) { const int v = row[dx]; sum += v; sumsq += v * v; }
+        }
+        const int a = (sumsq + ((1 << (2 * bdmin8)) >> 1)) >> (2 * bdmin8);
+        const int b = (sum + ((1 << bdmin8) >> 1)) >> bdmin8;
+        const unsigned p = (unsigned)imax(a * n - b * b, 0);
+        const unsigned z = (p * s + (1u << 19)) >> 20;
+        const unsigned x = tab::k_sgr_x_by_x[z < 255 ? z : 255];
+        sm.u.s.A[(j + 1) * LR_AP + i + 1] = (int32_t)((x * (unsigned)sum * one_by_x + (1u << 11)) >> 12);
+        sm.u.s.B[(j + 1) * LR_AP + i + 1] = (int32_t)x;
+    }
+}
+
+// value of the filter output `dst[j][i]` (coef, truncated to int16 at 8 bpc)
+template <typename BD>
+__device__ __forceinline__ int sgr_out(const LrSmem &sm, int n, int j, int i) {
+    const int32_t *A = sm.u.s.A + (j + 1) * LR_AP + i + 1, *B = sm.u.s.B + (j + 1) * LR_AP + i + 1;
+    const int src = sm.win[(j + 3) * LR_WP + i + 3];
+    int v;
+    if (n == 25) {
+        if (!(j & 1)) {
+            const int a = (B[-LR_AP] + B[LR_AP]) * 6 + (B[-1 - LR_AP] + B[-1 + LR_AP] + B[1 - LR_AP] + B[1 + LR_AP]) * 5;
+            const int b = (A[-LR_AP] + A[LR_AP]) * 6 + (A[-1 - LR_AP] + A[-1 + LR_AP] + A[1 - LR_AP] + A[1 + LR_AP]) * 5;
+            v = (b - a * src + (1 << 8)) >> 9;
+        } else {
+            const int a = B[0] * 6 + (B[-1] + B[1]) * 5;
+            const int b = A[0] * 6 + (A[-1] + A[1]) * 5;
+            v = (b - a * src + (1 << 7)) >> 8;
+        }
+    } else {
+        const int a = (B[0] + B[-1] + B[1] + B[-LR_AP] + B[LR_AP]) * 4 +
+                      (B[-1 - LR_AP] + B[-1 + LR_AP] + B[1 - LR_AP] + B[1 + LR_AP]) * 3;
+        const int b = (A[0] + A[-1] + A[1] + A[-LR_AP] + A[LR_AP]) * 4 +
+                      (A[-1 - LR_AP] + A[-1 + LR_AP] + A[1 - LR_AP] + A[1 + LR_AP]) * 3;
+        v = (b - a * src + (1 << 8)) >> 9;
+    }
+    return BD::hbd ? v : (int)(int16_t)v;
+}
+
+constexpr int LR_PX_PER_THREAD = LR_TW * LR_TH / 256;  // 8
+
+// kind: 2 5x5, 3 3x3, 4 mix.  src/looprestoration_tmpl.c:446-520
+template <typename BD, typename Out>
+__device__ void lr_sgr_tile(LrSmem &sm, int tw, int th, int kind, unsigned s0, unsigned s1, int w0, int w1, int bdmax,
+                            Out out) {
+    const int bdmin8 = BD::hbd ? bpc_from_max(bdmax) - 8 : 0;
+    int acc[LR_PX_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < LR_PX_PER_THREAD; k++) acc[k] = 0;
+    if (kind != 3) {
+        sgr_ab<BD>(sm, tw, th, 25, s0, bdmin8);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < LR_PX_PER_THREAD; k++) {
+            const int i = threadIdx.x + k * 256;
+            const int r = i / LR_TW, c = i - r * LR_TW;
+            if (r < th && c < tw) acc[k] = w0 * sgr_out<BD>(sm, 25, r, c);
+        }
+        __syncthreads();
+    }
+    if (kind != 2) {
+        sgr_ab<BD>(sm, tw, th, 9, s1, bdmin8);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < LR_PX_PER_THREAD; k++) {
+            const int i = threadIdx.x + k * 256;
+            const int r = i / LR_TW, c = i - r * LR_TW;
+            if (r < th && c < tw) acc[k] += w1 * sgr_out<BD>(sm, 9, r, c);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < LR_PX_PER_THREAD; k++) {
+        const int i = threadIdx.x + k * 256;
+        const int r = i / LR_TW, c = i - r * LR_TW;
+        if (r < th && c < tw) {
+            const int px = sm.win[(r + 3) * LR_WP + c + 3];
+            out(r, c, iclip(px + ((acc[k] + (1 << 10)) >> 11), 0, bdmax));
+        }
+    }
+}
+
+
+// cdef: CDEF output (the picture being restored); dbl: deblocked pre-CDEF picture; out: restored picture
+template <typename BD>
+__global__ void __launch_bounds__(256)
+lr_frame_kernel(const uint8_t *__restrict__ cdef, const uint8_t *__restrict__ dbl, uint8_t *__restrict__ outp,
+                int64_t stride, LrFrameParams P, const Rb200Av1Restoration *__restrict__ lrm, int bdmax) {
+    using pixel = typename BD::pixel;
+    __shared__ LrSmem sm;
+    const int x0 = blockIdx.x * LR_TW, s = blockIdx.y;
+    const int sh = 64 >> P.ss_ver, off = 8 >> P.ss_ver;
+    const int top = imax(0, s * sh - off), bot = imin(P.h, (s + 1) * sh - off);
+    const int tw = imin(LR_TW, P.w - x0), th = bot - top;
+    if (th <= 0) return;
+
+    // ---- which restoration unit (lr_sbrow, src/lr_apply_tmpl.c:117-160)
+    const int unit = 1 << P.unit_log2, half = unit >> 1;
+    const int sby = imin(s >> P.sb128, P.sbh - 1);
+    const int row_y = sby << (6 - P.ss_ver + P.sb128);
+    int aligned = row_y & ~(unit - 1);
+    if (aligned && aligned + half > P.h) aligned -= unit;
+    aligned <<= P.ss_ver;
+    const int sb_idx = (aligned >> 7) * P.sr_sb128w;
+    const int unit_idx = ((aligned >> 6) & 1) << 1;
+    const int n_units = imax(1, (P.w + half) >> P.unit_log2);
+    const int ux = imin(x0 >> P.unit_log2, n_units - 1) << P.unit_log2;  // unit start x
+    const int shift_hor = 7 - P.ss_hor;
+    const Rb200Av1RestorationUnit ru =
+        lrm[sb_idx + (ux >> shift_hor)].lr[P.plane][unit_idx + ((ux >> (shift_hor - 1)) & 1)];
+    const LrUnit U = lr_unpack(ru);
+
+    const int64_t ps = stride / (int64_t)sizeof(pixel);
+    pixel *o = (pixel *)outp + (int64_t)top * ps + x0;
+    if (U.kind == 0) {  // unit not restored: copy through
+        const pixel *c = (const pixel *)cdef + (int64_t)top * ps + x0;
+        for (int i = threadIdx.x; i < th * tw; i += 256) {
+            const int r = i / tw, cc = i - r * tw;
+            o[(int64_t)r * ps + cc] = c[(int64_t)r * ps + cc];
+        }
+        return;
+    }
+    // ---- stage the padded window (padding(), src/looprestoration_tmpl.c:41-137, with
+    //      lpf rows = deblocked rows saved by backup_lpf, src/lf_apply_tmpl.c:41-106)
+    for (int i = threadIdx.x; i < (th + 6) * (tw + 6); i += 256) {
+        const int r = i / (tw + 6), c = i - r * (tw + 6);
+        const int xx = iclip(x0 + c - 3, 0, P.w - 1);
+        const int yy = top + r - 3;
+        pixel v;
+        if (yy < top) {
+            if (top == 0) v = ((const pixel *)cdef)[xx];                                   // no LR_HAVE_TOP
+            else v = ((const pixel *)dbl)[(int64_t)imax(yy, top - 2) * ps + xx];
+        } else if (yy >= bot) {
+            if (bot >= P.h) v = ((const pixel *)cdef)[(int64_t)(bot - 1) * ps + xx];      // no LR_HAVE_BOTTOM
+            else v = ((const pixel *)dbl)[(int64_t)imin(imin(yy, bot + 1), P.h - 1) * ps + xx];
+        } else {
+            v = ((const pixel *)cdef)[(int64_t)yy * ps + xx];
+        }
+        sm.win[r * LR_WP + c] = v;
+    }
+    __syncthreads();
+    auto out = [&](int r, int c, int v) { o[(int64_t)r * ps + c] = (pixel)v; };
+    if (U.kind == 1) lr_wiener_tile<BD>(sm, tw, th, U.fh, U.fv, bdmax, out);
+    else lr_sgr_tile<BD>(sm, tw, th, U.kind, U.s0, U.s1, U.w0, U.w1, bdmax, out);
+}
+
+// ---- per-call: window from an explicit padded buffer tmp[(h+6)][pitch], built by lr_pad_kernel
+template <typename BD>
+__global__ void lr_pad_kernel(uint8_t *tmp, int pitch, const uint8_t *p, int64_t stride, const uint8_t *left,
+                              const uint8_t *lpf, int64_t lpf_stride, int w, int h, unsigned edges) {
+    using pixel = typename BD::pixel;
+    // tmp(r, c), r in [0, h+6), c in [0, w+6) <-> picture (y = r-3, x = c-3); same cases as padding()
+    const int have_left = !!(edges & RB200_LR_HAVE_LEFT), have_right = !!(edges & RB200_LR_HAVE_RIGHT);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (h + 6) * (w + 6); i += gridDim.x * blockDim.x) {
+        const int r = i / (w + 6), c = i - r * (w + 6);
+        int x = c - 3, y = r - 3;
+        if (!have_left && x < 0) x = 0;
+        if (!have_right && x >= w) x = w - 1;
+        pixel v;
+        auto P = [&](int yy, int xx) -> pixel {  // picture rows: left[] supplies x < 0
+            if (xx < 0) return ((const pixel *)left)[yy * 4 + 4 + xx];
+            return ((const pixel *)(p + (int64_t)yy * stride))[xx];
+        };
+        // lpf is staged with its x = -3 column at offset 0 when have_left
+        auto Lp = [&](int row, int xx) -> pixel { return ((const pixel *)(lpf + (int64_t)row * lpf_stride))[xx + 3 * have_left]; };
+        if (y < 0) {
+            if (edges & RB200_LR_HAVE_TOP) v = Lp(y == -1 ? 1 : 0, x);
+            else v = P(0, x);
+        } else if (y >= h) {
+            if (edges & RB200_LR_HAVE_BOTTOM) v = Lp(y == h ? 2 : 3, x);
+            else v = P(h - 1, x);
+        } else {
+            v = P(y, x);
+        }
+        ((pixel *)tmp)[r * pitch + c] = v;
+    }
+}
+
+template <typename BD>
+__global__ void __launch_bounds__(256)
+lr_call_kernel(const uint8_t *tmp, int pitch, uint8_t *dst, int64_t stride, int w, int h, LrUnit U, int bdmax) {
+    using pixel = typename BD::pixel;
+    __shared__ LrSmem sm;
+    const int x0 = blockIdx.x * LR_TW;
+    const int tw = imin(LR_TW, w - x0), th = h;
+    for (int i = threadIdx.x; i < (th + 6) * (tw + 6); i += 256) {
+        const int r = i / (tw + 6), c = i - r * (tw + 6);
+        sm.win[r * LR_WP + c] = ((const pixel *)tmp)[r * pitch + x0 + c];
+    }
+    __syncthreads();
+    const int64_t ps = stride / (int64_t)sizeof(pixel);
+    pixel *o = (pixel *)dst + x0;
+    auto out = [&](int r, int c, int v) { o[(int64_t)r * ps + c] = (pixel)v; };
+    if (U.kind == 1) lr_wiener_tile<BD>(sm, tw, th, U.fh, U.fv, bdmax, out);
+    else lr_sgr_tile<BD>(sm, tw, th, U.kind, U.s0, U.s1, U.w0, U.w1, bdmax, out);
+}
+
+int lr_plane_launch(const uint8_t *cdef, const uint8_t *dbl, uint8_t *out, int64_t stride, const LrFrameParams &P,
+                    const Rb200Av1Restoration *lrm, int bdmax, cudaStream_t st) {
+    const int sh = 64 >> P.ss_ver, off = 8 >> P.ss_ver;
+    const int n_stripes = (P.h + off + sh - 1) / sh;
+    dim3 grid((P.w + LR_TW - 1) / LR_TW, n_stripes);
+    if (bdmax > 255) lr_frame_kernel<BD16><<<grid, 256, 0, st>>>(cdef, dbl, out, stride, P, lrm, bdmax);
+    else lr_frame_kernel<BD8><<<grid, 256, 0, st>>>(cdef, dbl, out, stride, P, lrm, bdmax);
+    RB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace rb200
+
+using namespace rb200;
+
+extern "C" int rb200_lr(int kind, void *dst, ptrdiff_t stride, const void *left, const void *lpf, int w, int h,
+                        const Rb200LooprestorationParams *params, uint32_t edges, int bdmax) {
+    if (kind < 0 || kind > 4 || !dst || !params || w < 1 || w > 384 || h < 1 || h > 64)
+        return set_error(-22, "lr: bad argument");
+    const size_t px = bdmax > 255 ? 2 : 1;
+    const int hl = !!(edges & RB200_LR_HAVE_LEFT), hr = !!(edges & RB200_LR_HAVE_RIGHT);
+    const int cols = w + 3 * hr;
+    const int lcols = w + 3 * hl + 3 * hr;
+    HostCall hc(2 * (DevRect::bytes_for(cols * px, h) + 4 * DevRect::pitch_for(lcols * px) + (size_t)h * 4 * px) +
+                (size_t)(h + 6) * (w + 6) * px + 8192);
+    DevRect rect;
+    if (hc.rect_up(rect, dst, stride, cols * px, h)) return hc.err;
+    // lpf rows the reference may read: 0, 1 (above, with LR_HAVE_TOP) and 6, 7 (below, with LR_HAVE_BOTTOM)
+    const size_t lp = DevRect::pitch_for(lcols * px);
+    uint8_t *hl_rows = (uint8_t *)hc.st.halloc(4 * lp);
+    uint8_t *dl_rows = (uint8_t *)hc.dev(4 * lp);
+    if (!hl_rows || hc.err) return hc.err ? hc.err : set_error(-12, "staging arena too small");
+    memset(hl_rows, 0, 4 * lp);
+    for (int k = 0; k < 4; k++) {
+        const bool need = k < 2 ? (edges & RB200_LR_HAVE_TOP) : (edges & RB200_LR_HAVE_BOTTOM);
+        if (!need || !lpf) continue;
+        const int row = k < 2 ? k : 4 + k;  // 0, 1, 6, 7
+        memcpy(hl_rows + k * lp, (const uint8_t *)lpf + (int64_t)row * stride - (int64_t)(3 * hl) * (int64_t)px, (size_t)lcols * px);
+    }
+    RB_CUDA(cudaMemcpyAsync(dl_rows, hl_rows, 4 * lp, cudaMemcpyHostToDevice, hc.stream()));
+    uint8_t lbuf[64 * 4 * 2] = {};
+    if (hl && left) memcpy(lbuf, left, (size_t)h * 4 * px);
+    const uint8_t *d_left = (const uint8_t *)hc.up(lbuf, sizeof(lbuf));
+    const int pitch = w + 6;
+    uint8_t *d_tmp = (uint8_t *)hc.dev((size_t)(h + 6) * pitch * px);
+    if (hc.err) return hc.err;
+    LrUnit U = {};
+    if (kind < 2) {
+        U.kind = 1;
+        for (int k = 0; k < 8; k++) { U.fh[k] = params->filter[0][k]; U.fv[k] = params->filter[1][k]; }
+        if (bdmax <= 255) U.fh[3] += 128;  // the 8 bpc convention keeps the +128 out of the table (src/lr_apply.rs:67-72)
+    } else {
+        U.kind = kind;  // 2: 5x5, 3: 3x3, 4: mix
+        U.s0 = params->sgr.s0; U.s1 = params->sgr.s1; U.w0 = params->sgr.w0; U.w1 = params->sgr.w1;
+    }
+    const int grid = (w + LR_TW - 1) / LR_TW;
+    if (bdmax > 255) {
+        lr_pad_kernel<BD16><<<8, 256, 0, hc.stream()>>>(d_tmp, pitch, rect.dptr, rect.dpitch, d_left, dl_rows, (int64_t)lp, w, h, edges);
+        lr_call_kernel<BD16><<<grid, 256, 0, hc.stream()>>>(d_tmp, pitch, rect.dptr, rect.dpitch, w, h, U, bdmax);
+    } else {
+        lr_pad_kernel<BD8><<<8, 256, 0, hc.stream()>>>(d_tmp, pitch, rect.dptr, rect.dpitch, d_left, dl_rows, (int64_t)lp, w, h, edges);
+        lr_call_kernel<BD8><<<grid, 256, 0, hc.stream()>>>(d_tmp, pitch, rect.dptr, rect.dpitch, w, h, U, bdmax);
+    }
+    hc.rect_down(rect);
+    if (hc.sync()) return hc.err;
+    rect.row_bytes = w * px;  // only the unit itself is written back
+    rect.finish(dst);
+    return 0;
+}
+
+namespace {
+template <int KIND>
+void lr_slot(void *dst, ptrdiff_t stride, const void *left, const void *lpf, int w, int h,
+             const Rb200LooprestorationParams *params, uint32_t edges, int bd) {
+    if (rb200_lr(KIND, dst, stride, left, lpf, w, h, params, edges, bd)) rb200_report_fatal("lr");
+}
+}  // namespace
+
+extern "C" void rb200_loop_restoration_dsp_init(Rb200LoopRestorationDSPContext *c, int bpc) {
+    (void)bpc;
+    c->wiener[0] = &lr_slot<0>; c->wiener[1] = &lr_slot<1>;
+    c->sgr[0] = &lr_slot<2>; c->sgr[1] = &lr_slot<3>; c->sgr[2] = &lr_slot<4>;
+}

@@ -1,0 +1,712 @@
+// Motion compensation for sm_100a: put / prep with 8-tap and bilinear filters,
+// scaled variants, compound combines (avg, w_avg, mask, w_mask), OBMC /
+// inter-intra blends, 8x8 affine warp, edge emulation and super-res resize.
+//
+// Replaces Rav1dMCDSPContext (src/mc.rs:1321-1338; kernels src/mc.rs:28-1172 ==
+// src/mc_tmpl.c) and the addressing half of recon.rs `mc()` (src/recon.rs:2025-2203).
+//
+// Mapping: one warp owns one prediction tile of at most 16x16 pixels.  The
+// source window (tile + 7 rows/columns of filter support) is staged into a
+// warp-private shared-memory tile with coordinates clamped to the reference
+// picture -- the clamp *is* emu_edge (src/mc.rs:1032-1112), so no edge buffer is
+// ever materialised -- then filtered horizontally into an int16 intermediate
+// (same truncating store as the reference's `mid`, src/mc.rs:161) and
+// vertically into the destination.  Larger blocks are split into 16x16 tiles;
+// the split is exact because filtering is separable per pixel and the 4-tap
+// selection rule (w <= 4 / h <= 4, src/mc.rs:119-127) can only apply to blocks
+// that are not split in that dimension.
+#include "common.cuh"
+#include "tables.cuh"
+#include <utility>
+
+namespace rb200 {
+
+template <typename BD>
+struct McBits {
+    // intermediate_bits: 4 for 8 and 10 bpc, 2 for 12 bpc (include/common/bitdepth.rs:315,395)
+    static __device__ __forceinline__ int ib(int bdmax) { return BD::hbd ? 14 - bpc_from_max(bdmax) : 4; }
+    static constexpr int prep_bias = BD::hbd ? 8192 : 0;  // bitdepth.rs:320,401
+};
+
+constexpr int MC_TILE = 16;
+constexpr int MC_WIN_ROWS = MC_TILE + 7;
+constexpr int MC_WIN_PITCH = MC_TILE + 8;  // 24 columns: 23 used
+constexpr int MC_WARPS = 4;
+
+struct McSmem {
+    uint16_t win[MC_WIN_ROWS * MC_WIN_PITCH];
+    int16_t mid[MC_WIN_ROWS * MC_TILE];
+};
+
+struct McRef {
+    const uint8_t *base;  // row 0 of the reference plane
+    int64_t stride;       // bytes
+    int w, h;             // clamp bounds in pixels
+};
+
+__device__ __forceinline__ void load_taps(int f[8], const int8_t *p) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) f[k] = p[k];
+}
+
+// One warp: w x h tile (<= 16x16) whose top-left source sample is (sx, sy) in `ref`.
+// bw/bh: size of the whole prediction block (selects 4-tap filters).
+// PREP: write int16 `(value) - PREP_BIAS` to out16 (row pitch out_pitch elements);
+// else write clipped pixels to out8/out16 as pixels (row pitch in bytes).
+template <typename BD, bool PREP>
+__device__ void mc_tile(McSmem &sm, const McRef ref, int sx, int sy, int w, int h, int bw, int bh,
+                        int mx, int my, int filter2d, void *out, int64_t out_pitch, int bdmax) {
+    using pixel = typename BD::pixel;
+    const int lane = threadIdx.x & 31;
+    const int ib = McBits<BD>::ib(bdmax);
+    const bool bilin = filter2d == RB200_FILTER_2D_BILINEAR;
+    const bool fh = mx != 0, fv = my != 0;
+    const int x0 = fh ? (bilin ? 0 : -3) : 0, y0 = fv ? (bilin ? 0 : -3) : 0;
+    const int ncols = w + (fh ? (bilin ? 1 : 7) : 0), nrows = h + (fv ? (bilin ? 1 : 7) : 0);
+
+    // ---- stage the clamped source window
+    for (int i = lane; i < nrows * ncols; i += 32) {
+        const int r = i / ncols, c = i - r * ncols;
+        const int yy = iclip(sy + y0 + r, 0, ref.h - 1), xx = iclip(sx + x0 + c, 0, ref.w - 1);
+        sm.win[r * MC_WIN_PITCH + c] = ((const pixel *)(ref.base + (int64_t)yy * ref.stride))[xx];
+    }
+    __syncwarp();
+
+    auto store = [&](int r, int c, int v) {  // v: final value (pixel or prep)
+        if (PREP) ((int16_t *)out)[(int64_t)r * out_pitch + c] = (int16_t)v;
+        else ((pixel *)((uint8_t *)out + (int64_t)r * out_pitch))[c] = (pixel)v;
+    };
+
+    if (bilin) {
+        // put_bilin / prep_bilin, src/mc.rs:431-652 == src/mc_tmpl.c:354-540
+        if (fh && fv) {
+            const int sh1 = 4 - ib, r1 = (1 << sh1) >> 1;
+            for (int i = lane; i < (h + 1) * w; i += 32) {
+                const int r = i / w, c = i - r * w;
+                const int a = sm.win[r * MC_WIN_PITCH + c], b = sm.win[r * MC_WIN_PITCH + c + 1];
+                sm.mid[r * MC_TILE + c] = (int16_t)((16 * a + mx * (b - a) + r1) >> sh1);
+            }
+            __syncwarp();
+            for (int i = lane; i < h * w; i += 32) {
+                const int r = i / w, c = i - r * w;
+                const int a = sm.mid[r * MC_TILE + c], b = sm.mid[(r + 1) * MC_TILE + c];
+                const int s = 16 * a + my * (b - a);
+                if (PREP) store(r, c, ((s + 8) >> 4) - McBits<BD>::prep_bias);
+                else store(r, c, iclip((s + ((1 << (4 + ib)) >> 1)) >> (4 + ib), 0, bdmax));
+            }
+        } else if (fh || fv) {
+            const int step = fh ? 1 : MC_WIN_PITCH, m = fh ? mx : my;
+            for (int i = lane; i < h * w; i += 32) {
+                const int r = i / w, c = i - r * w;
+                const int a = sm.win[r * MC_WIN_PITCH + c], b = sm.win[r * MC_WIN_PITCH + c + step];
+                const int s = 16 * a + m * (b - a);
+                if (PREP) {
+                    store(r, c, ((s + ((1 << (4 - ib)) >> 1)) >> (4 - ib)) - McBits<BD>::prep_bias);
+                } else if (fh) {
+                    const int px = (s + ((1 << (4 - ib)) >> 1)) >> (4 - ib);
+                    store(r, c, iclip((px + ((1 << ib) >> 1)) >> ib, 0, bdmax));
+                } else {
+                    store(r, c, iclip((s + 8) >> 4, 0, bdmax));
+                }
+            }
+        } else {
+            for (int i = lane; i < h * w; i += 32) {
+                const int r = i / w, c = i - r * w;
+                const int a = sm.win[r * MC_WIN_PITCH + c];
+                store(r, c, PREP ? (a << ib) - McBits<BD>::prep_bias : a);
+            }
+        }
+        __syncwarp();
+        return;
+    }
+
+    // 8-tap: filter_type = h | v << 2 with (0 regular, 1 smooth, 2 sharp)   (src/mc_tmpl.c:330-338)
+    //   Filter2d order: REG, REG_SMOOTH, REG_SHARP, SHARP_REG, SHARP_SMOOTH, SHARP, SMOOTH_REG, SMOOTH, SMOOTH_SHARP
+    //   name = <h>_<v>:  h type: 0,0,0,2,2,2,1,1,1   v type: 0,1,2,0,1,2,0,1,2
+    const int th_ = (0x111222000LL >> (4 * filter2d)) & 3, tv_ = (0x210210210LL >> (4 * filter2d)) & 3;
+    int FH[8], FV[8];
+    if (fh) load_taps(FH, tab::subpel(bw > 4 ? th_ : 3 + (th_ & 1), mx - 1));
+    if (fv) load_taps(FV, tab::subpel(bh > 4 ? tv_ : 3 + (tv_ & 1), my - 1));
+
+    if (fh && fv) {
+        const int sh1 = 6 - ib, r1 = (1 << sh1) >> 1;
+        for (int i = lane; i < (h + 7) * w; i += 32) {
+            const int r = i / w, c = i - r * w;
+            const uint16_t *s = sm.win + r * MC_WIN_PITCH + c;
+            int acc = r1;
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc += FH[k] * (int)s[k];
+            sm.mid[r * MC_TILE + c] = (int16_t)(acc >> sh1);
+        }
+        __syncwarp();
+        for (int i = lane; i < h * w; i += 32) {
+            const int r = i / w, c = i - r * w;
+            const int16_t *s = sm.mid + r * MC_TILE + c;
+            int acc = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc += FV[k] * (int)s[k * MC_TILE];
+            if (PREP) store(r, c, ((acc + 32) >> 6) - McBits<BD>::prep_bias);
+            else store(r, c, iclip((acc + ((1 << (6 + ib)) >> 1)) >> (6 + ib), 0, bdmax));
+        }
+    } else if (fh) {
+        for (int i = lane; i < h * w; i += 32) {
+            const int r = i / w, c = i - r * w;
+            const uint16_t *s = sm.win + r * MC_WIN_PITCH + c;
+            int acc = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc += FH[k] * (int)s[k];
+            if (PREP) store(r, c, ((acc + ((1 << (6 - ib)) >> 1)) >> (6 - ib)) - McBits<BD>::prep_bias);
+            else store(r, c, iclip((acc + 32 + ((1 << (6 - ib)) >> 1)) >> 6, 0, bdmax));
+        }
+    } else if (fv) {
+        for (int i = lane; i < h * w; i += 32) {
+            const int r = i / w, c = i - r * w;
+            const uint16_t *s = sm.win + r * MC_WIN_PITCH + c;
+            int acc = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc += FV[k] * (int)s[k * MC_WIN_PITCH];
+            if (PREP) store(r, c, ((acc + ((1 << (6 - ib)) >> 1)) >> (6 - ib)) - McBits<BD>::prep_bias);
+            else store(r, c, iclip((acc + 32) >> 6, 0, bdmax));
+        }
+    } else {
+        for (int i = lane; i < h * w; i += 32) {
+            const int r = i / w, c = i - r * w;
+            const int a = sm.win[r * MC_WIN_PITCH + c];
+            store(r, c, PREP ? (a << ib) - McBits<BD>::prep_bias : a);
+        }
+    }
+    __syncwarp();
+}
+
+struct McRefSet {
+    Rb200Planes p[8];
+};
+
+// Frame batch: one warp per item, items wider/taller than 16 are walked tile by tile.
+template <typename BD>
+__global__ void __launch_bounds__(MC_WARPS * 32)
+mc_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int ss_hor, int ss_ver,
+                const Rb200McItem *__restrict__ items, int n_items, int bdmax) {
+    __shared__ McSmem smem[MC_WARPS];
+    const int warp = threadIdx.x >> 5;
+    const int idx = blockIdx.x * MC_WARPS + warp;
+    if (idx >= n_items) return;
+    const Rb200McItem it = items[idx];
+    const Rb200Planes &rp = refs.p[it.ref & 7];
+    McRef ref;
+    ref.base = plane_ptr(rp, it.plane);
+    ref.stride = plane_stride(rp, it.plane);
+    ref.w = it.plane ? (ref_w + ss_hor) >> ss_hor : ref_w;
+    ref.h = it.plane ? (ref_h + ss_ver) >> ss_ver : ref_h;
+    uint8_t *dbase = plane_ptr(dst, it.plane);
+    const int64_t dstride = plane_stride(dst, it.plane);
+    for (int ty = 0; ty < it.h; ty += MC_TILE) {
+        for (int tx = 0; tx < it.w; tx += MC_TILE) {
+            uint8_t *o = dbase + (int64_t)(it.dst_y + ty) * dstride + (int64_t)(it.dst_x + tx) * sizeof(typename BD::pixel);
+            mc_tile<BD, false>(smem[warp], ref, it.src_x + tx, it.src_y + ty, imin(MC_TILE, it.w - tx),
+                               imin(MC_TILE, it.h - ty), it.w, it.h, it.mx, it.my, it.filter2d, o, dstride, bdmax);
+        }
+    }
+}
+
+// Per-call: a single prediction block over a staged source rectangle; one warp per 16x16 tile.
+template <typename BD, bool PREP>
+__global__ void __launch_bounds__(MC_WARPS * 32)
+mc_one_kernel(McRef ref, int ox, int oy, int w, int h, int mx, int my, int filter2d, void *out, int64_t out_pitch,
+              int bdmax) {
+    __shared__ McSmem smem[MC_WARPS];
+    const int warp = threadIdx.x >> 5;
+    const int tiles_x = (w + MC_TILE - 1) / MC_TILE, tiles_y = (h + MC_TILE - 1) / MC_TILE;
+    const int t = blockIdx.x * MC_WARPS + warp;
+    if (t >= tiles_x * tiles_y) return;
+    const int ty = (t / tiles_x) * MC_TILE, tx = (t % tiles_x) * MC_TILE;
+    void *o = PREP ? (void *)((int16_t *)out + (int64_t)ty * out_pitch + tx)
+                   : (void *)((uint8_t *)out + (int64_t)ty * out_pitch + (int64_t)tx * sizeof(typename BD::pixel));
+    mc_tile<BD, PREP>(smem[warp], ref, ox + tx, oy + ty, imin(MC_TILE, w - tx), imin(MC_TILE, h - ty), w, h, mx, my,
+                      filter2d, o, out_pitch, bdmax);
+}
+
+// ------------------------------------------------------------------ scaled
+// put_8tap_scaled / prep_8tap_scaled / bilin scaled: src/mc.rs:212-275,351-429,496-541,608-652.
+// One thread per output pixel; position (mx + x*dx) is the closed form of the
+// reference's running imx / ioff accumulation.
+template <typename BD, bool PREP>
+__global__ void mc_scaled_kernel(McRef ref, int ox, int oy, int w, int h, int mx, int my, int dx, int dy,
+                                 int filter2d, void *out, int64_t out_pitch, int bdmax) {
+    using pixel = typename BD::pixel;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w || y >= h) return;
+    const int ib = McBits<BD>::ib(bdmax);
+    const int px = mx + x * dx, py = my + y * dy;
+    const int ix = px >> 10, iy = py >> 10, fx = (px & 0x3ff) >> 6, fy = (py & 0x3ff) >> 6;
+    auto at = [&](int r, int c) -> int {
+        const int yy = iclip(oy + r, 0, ref.h - 1), xx = iclip(ox + c, 0, ref.w - 1);
+        return ((const pixel *)(ref.base + (int64_t)yy * ref.stride))[xx];
+    };
+    int v;
+    if (filter2d == RB200_FILTER_2D_BILINEAR) {
+        int m[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int a = at(iy + k, ix), b = at(iy + k, ix + 1);
+            m[k] = (int16_t)((16 * a + fx * (b - a) + ((1 << (4 - ib)) >> 1)) >> (4 - ib));
+        }
+        const int s = 16 * m[0] + fy * (m[1] - m[0]);
+        v = PREP ? ((s + 8) >> 4) - McBits<BD>::prep_bias : iclip((s + ((1 << (4 + ib)) >> 1)) >> (4 + ib), 0, bdmax);
+    } else {
+        const int th_ = (0x111222000LL >> (4 * filter2d)) & 3, tv_ = (0x210210210LL >> (4 * filter2d)) & 3;
+        const int8_t *FH = fx ? tab::subpel(w > 4 ? th_ : 3 + (th_ & 1), fx - 1) : nullptr;
+        const int8_t *FV = fy ? tab::subpel(h > 4 ? tv_ : 3 + (tv_ & 1), fy - 1) : nullptr;
+        int m[8];
+        // the source pointer of the reference is pre-advanced by -3 rows; row iy+k-3 <-> mid row (iy + k)
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (!FV && k != 3) { m[k] = 0; continue; }
+            const int r = iy + k - 3;
+            if (FH) {
+                int acc = (1 << (6 - ib)) >> 1;
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc += FH[j] * at(r, ix + j - 3);
+                m[k] = (int16_t)(acc >> (6 - ib));
+            } else {
+                m[k] = (int16_t)(at(r, ix) << ib);
+            }
+        }
+        if (FV) {
+            int acc = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc += FV[k] * m[k];
+            v = PREP ? ((acc + 32) >> 6) - McBits<BD>::prep_bias
+                     : iclip((acc + ((1 << (6 + ib)) >> 1)) >> (6 + ib), 0, bdmax);
+        } else {
+            v = PREP ? m[3] - McBits<BD>::prep_bias : iclip((m[3] + ((1 << ib) >> 1)) >> ib, 0, bdmax);
+        }
+    }
+    if (PREP) ((int16_t *)out)[(int64_t)y * out_pitch + x] = (int16_t)v;
+    else ((pixel *)((uint8_t *)out + (int64_t)y * out_pitch))[x] = (pixel)v;
+}
+
+// ---------------------------------------------------------------- compound
+// avg / w_avg / mask / w_mask: src/mc.rs:654-740,812-883 == src/mc_tmpl.c:542-604,643-699
+enum { CMP_AVG, CMP_WAVG, CMP_MASK };
+template <typename BD>
+__global__ void compound_kernel(int mode, void *dst, int64_t dstride, const int16_t *__restrict__ t1,
+                                const int16_t *__restrict__ t2, int w, int h, int weight,
+                                const uint8_t *__restrict__ mask, int bdmax) {
+    using pixel = typename BD::pixel;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w * h) return;
+    const int y = i / w, x = i - y * w;
+    const int ib = McBits<BD>::ib(bdmax), pb = McBits<BD>::prep_bias;
+    const int a = t1[i], b = t2[i];
+    int v;
+    if (mode == CMP_AVG) v = (a + b + (1 << ib) + pb * 2) >> (ib + 1);
+    else if (mode == CMP_WAVG) v = (a * weight + b * (16 - weight) + (8 << ib) + pb * 16) >> (ib + 4);
+    else { const int m = mask[i]; v = (a * m + b * (64 - m) + (32 << ib) + pb * 64) >> (ib + 6); }
+    ((pixel *)((uint8_t *)dst + (int64_t)y * dstride))[x] = (pixel)iclip(v, 0, bdmax);
+}
+
+// w_mask: one thread per (1 << ss_hor) x (1 << ss_ver) pixel group, so that the
+// sub-sampled mask value is produced without the reference's even/odd row carry.
+template <typename BD>
+__global__ void w_mask_kernel(void *dst, int64_t dstride, const int16_t *__restrict__ t1,
+                              const int16_t *__restrict__ t2, int w, int h, uint8_t *__restrict__ mask, int sign,
+                              int ss_hor, int ss_ver, int bdmax) {
+    using pixel = typename BD::pixel;
+    const int gw = w >> ss_hor, gh = h >> ss_ver;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= gw * gh) return;
+    const int gy = g / gw, gx = g - gy * gw;
+    const int ib = McBits<BD>::ib(bdmax), pb = McBits<BD>::prep_bias;
+    const int bitdepth = BD::hbd ? bpc_from_max(bdmax) : 8;
+    const int sh = ib + 6, rnd = (32 << ib) + pb * 64;
+    const int mask_sh = bitdepth + ib - 4, mask_rnd = 1 << (mask_sh - 5);
+    int msum = 0;
+    for (int j = 0; j <= ss_ver; j++) {
+        for (int k = 0; k <= ss_hor; k++) {
+            const int y = (gy << ss_ver) + j, x = (gx << ss_hor) + k;
+            const int a = t1[y * w + x], b = t2[y * w + x];
+            const int d = a - b;
+            const int m = imin(38 + (((d < 0 ? -d : d) + mask_rnd) >> mask_sh), 64);
+            ((pixel *)((uint8_t *)dst + (int64_t)y * dstride))[x] =
+                (pixel)iclip((a * m + b * (64 - m) + rnd) >> sh, 0, bdmax);
+            msum += m;
+        }
+    }
+    // 444: m ; 422: (m+n+1-sign)>>1 ; 420: (m+n+m'+n'+2-sign)>>2
+    const int n = (1 + ss_hor) * (1 + ss_ver);
+    mask[g] = (uint8_t)(n == 1 ? msum : n == 2 ? (msum + 1 - sign) >> 1 : (msum + 2 - sign) >> 2);
+}
+
+// blend / blend_v / blend_h: src/mc.rs:742-810 == src/mc_tmpl.c:606-641
+template <typename BD>
+__global__ void blend_kernel(int dir, void *dst, int64_t dstride, const void *__restrict__ tmp, int w, int h,
+                             const uint8_t *__restrict__ mask) {
+    using pixel = typename BD::pixel;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w * h) return;
+    const int y = i / w, x = i - y * w;
+    int m;
+    if (dir == 0) m = mask[i];
+    else if (dir == 1) { if (x >= (w * 3) >> 2) return; m = tab::k_obmc_masks[w + x]; }
+    else { if (y >= (h * 3) >> 2) return; m = tab::k_obmc_masks[h + y]; }
+    pixel *d = (pixel *)((uint8_t *)dst + (int64_t)y * dstride) + x;
+    const int a = *d, b = ((const pixel *)tmp)[i];
+    *d = (pixel)((a * (64 - m) + b * m + 32) >> 6);
+}
+
+// warp_affine_8x8 / 8x8t: src/mc.rs:885-1030 == src/mc_tmpl.c:701-772.  One block of 64 threads
+// per 8x8; 15x8 horizontal pass into shared int16, then vertical pass.
+template <typename BD, bool PREP>
+__global__ void __launch_bounds__(64)
+warp8x8_kernel(McRef ref, int ox, int oy, void *out, int64_t out_pitch, const int16_t *__restrict__ abcd_d,
+               int mx, int my, int bdmax) {
+    using pixel = typename BD::pixel;
+    __shared__ int16_t mid[15 * 8];
+    const int ib = McBits<BD>::ib(bdmax);
+    const int a0 = abcd_d[0], a1 = abcd_d[1], a2 = abcd_d[2], a3 = abcd_d[3];
+    for (int i = threadIdx.x; i < 15 * 8; i += 64) {
+        const int y = i >> 3, x = i & 7;
+        const int tmx = mx + y * a1 + x * a0;
+        const int8_t *f = tab::k_warp_filter + (64 + ((tmx + 512) >> 10)) * 8;
+        int acc = (1 << (7 - ib)) >> 1;
+        const int yy = iclip(oy + y - 3, 0, ref.h - 1);
+        const pixel *row = (const pixel *)(ref.base + (int64_t)yy * ref.stride);
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc += f[k] * (int)row[iclip(ox + x + k - 3, 0, ref.w - 1)];
+        mid[i] = (int16_t)(acc >> (7 - ib));
+    }
+    __syncthreads();
+    const int y = threadIdx.x >> 3, x = threadIdx.x & 7;
+    const int tmy = my + y * a3 + x * a2;
+    const int8_t *f = tab::k_warp_filter + (64 + ((tmy + 512) >> 10)) * 8;
+    int acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc += f[k] * (int)mid[(y + k) * 8 + x];
+    if (PREP) ((int16_t *)out)[(int64_t)y * out_pitch + x] = (int16_t)(((acc + 64) >> 7) - McBits<BD>::prep_bias);
+    else ((pixel *)((uint8_t *)out + (int64_t)y * out_pitch))[x] =
+             (pixel)iclip((acc + ((1 << (7 + ib)) >> 1)) >> (7 + ib), 0, bdmax);
+}
+
+// emu_edge: src/mc.rs:1032-1112 == src/mc_tmpl.c:774-826 (a clamped gather)
+template <typename BD>
+__global__ void emu_edge_kernel(McRef ref, int x0, int y0, int bw, int bh, void *dst, int64_t dstride) {
+    using pixel = typename BD::pixel;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= bw || y >= bh) return;
+    const int yy = iclip(y0 + y, 0, ref.h - 1), xx = iclip(x0 + x, 0, ref.w - 1);
+    ((pixel *)((uint8_t *)dst + (int64_t)y * dstride))[x] = ((const pixel *)(ref.base + (int64_t)yy * ref.stride))[xx];
+}
+
+// resize (super-resolution upscaling): src/mc.rs:1114-1172 == src/mc_tmpl.c:828-858
+template <typename BD>
+__global__ void resize_kernel(void *dst, int64_t dstride, const void *src, int64_t sstride, int dst_w, int h,
+                              int src_w, int dx, int mx0, int bdmax) {
+    using pixel = typename BD::pixel;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dst_w || y >= h) return;
+    const int64_t pos = (int64_t)mx0 + (int64_t)x * dx;  // running mx: src_x = -1 + (pos >> 14), phase pos & 0x3fff
+    const int src_x = -1 + (int)(pos >> 14), ph = (int)(pos & 0x3fff);
+    const int8_t *F = tab::k_resize_filter + (ph >> 8) * 8;
+    const pixel *s = (const pixel *)((const uint8_t *)src + (int64_t)y * sstride);
+    int acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc += F[k] * (int)s[iclip(src_x + k - 3, 0, src_w - 1)];
+    ((pixel *)((uint8_t *)dst + (int64_t)y * dstride))[x] = (pixel)iclip((-acc + 64) >> 7, 0, bdmax);
+}
+
+int mc_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int ss_hor,
+                    int ss_ver, const Rb200McItem *d_items, int n, int bdmax, cudaStream_t st) {
+    if (n <= 0) return 0;
+    McRefSet rs = {};
+    for (int i = 0; i < n_refs && i < 8; i++) rs.p[i] = refs[i];
+    const int grid = (n + MC_WARPS - 1) / MC_WARPS;
+    if (bdmax > 255)
+        mc_batch_kernel<BD16><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, ss_hor, ss_ver, d_items, n, bdmax);
+    else
+        mc_batch_kernel<BD8><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, ss_hor, ss_ver, d_items, n, bdmax);
+    RB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace rb200
+
+using namespace rb200;
+
+// ---------------------------------------------------------------- C ABI
+extern "C" int rb200_mc_batch(const Rb200Planes *dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h,
+                              int ss_hor, int ss_ver, const Rb200McItem *d_items, int n_items, int bitdepth_max,
+                              void *stream) {
+    if (!dst || !refs || n_refs < 1 || n_refs > 8) return set_error(-22, "mc_batch: bad argument");
+    return mc_batch_launch(*dst, refs, n_refs, ref_w, ref_h, ss_hor, ss_ver, d_items, n_items, bitdepth_max,
+                           (cudaStream_t)stream);
+}
+
+namespace {
+
+inline size_t pxsz(int bdmax) { return bdmax > 255 ? 2 : 1; }
+
+// Stage the source rectangle a (w x h) prediction at phase (mx, my) reads:
+// rows -3..h+3 / columns -3..w+3 for 8-tap, +1 for bilinear, nothing extra for phase 0.
+struct SrcStage {
+    DevRect rect;
+    McRef ref;
+    int ox, oy;
+    int setup(HostCall &hc, const void *src, ptrdiff_t ss, int w, int h, int before_x, int after_x, int before_y,
+              int after_y, int bdmax) {
+        const size_t px = pxsz(bdmax);
+        const uint8_t *row0 = (const uint8_t *)src - (int64_t)before_y * ss - (int64_t)before_x * (int64_t)px;
+        const int cols = w + before_x + after_x, rows = h + before_y + after_y;
+        if (hc.rect_up(rect, row0, ss, cols * px, rows)) return hc.err;
+        ref.base = rect.dptr; ref.stride = rect.dpitch; ref.w = cols; ref.h = rows;
+        ox = before_x; oy = before_y;
+        return 0;
+    }
+};
+
+int mc_common(bool prep, bool scaled, int filter2d, void *dst, ptrdiff_t ds, const void *src, ptrdiff_t ss, int w,
+              int h, int mx, int my, int dx, int dy, int bdmax) {
+    if (filter2d < 0 || filter2d >= RB200_N_2D_FILTERS || w < 1 || h < 1 || w > 128 || h > 256 || !dst || !src)
+        return set_error(-22, "mc: bad argument");
+    const bool bilin = filter2d == RB200_FILTER_2D_BILINEAR;
+    const size_t px = pxsz(bdmax);
+    int bx = 0, ax = 0, by = 0, ay = 0;
+    if (scaled) {
+        // reference reads rows -3 .. ((h-1)*dy+my >> 10) + 4 and columns -3 .. ((w-1)*dx+mx >> 10) + 4
+        const int lastx = ((w - 1) * dx + mx) >> 10, lasty = ((h - 1) * dy + my) >> 10;
+        if (bilin) { ax = lastx + 2 - w; ay = lasty + 2 - h; }
+        else { bx = by = 3; ax = lastx + 5 - w; ay = lasty + 5 - h; }
+    } else {
+        if (mx) { if (bilin) ax = 1; else { bx = 3; ax = 4; } }
+        if (my) { if (bilin) ay = 1; else { by = 3; ay = 4; } }
+    }
+    const size_t src_bytes = DevRect::bytes_for((size_t)(w + bx + ax) * px, h + by + ay);
+    const size_t dst_bytes = prep ? (size_t)w * h * 2 : DevRect::bytes_for(w * px, h);
+    HostCall hc(2 * (src_bytes + dst_bytes));
+    SrcStage s;
+    if (s.setup(hc, src, ss, w, h, bx, ax, by, ay, bdmax)) return hc.err;
+    DevRect drect;
+    void *out; int64_t pitch;
+    if (prep) { out = hc.dev((size_t)w * h * 2); pitch = w; }
+    else { if (hc.rect_up(drect, dst, ds, w * px, h)) return hc.err; out = drect.dptr; pitch = drect.dpitch; }
+    if (hc.err) return hc.err;
+    const bool hbd = bdmax > 255;
+    if (scaled) {
+        dim3 grid((w + 63) / 64, h), blk(64);
+#define L(BD, P) mc_scaled_kernel<BD, P><<<grid, blk, 0, hc.stream()>>>(s.ref, s.ox, s.oy, w, h, mx, my, dx, dy, filter2d, out, pitch, bdmax)
+        if (hbd) { if (prep) L(BD16, true); else L(BD16, false); } else { if (prep) L(BD8, true); else L(BD8, false); }
+#undef L
+    } else {
+        const int tiles = ((w + MC_TILE - 1) / MC_TILE) * ((h + MC_TILE - 1) / MC_TILE);
+        const int grid = (tiles + MC_WARPS - 1) / MC_WARPS;
+#define L(BD, P) mc_one_kernel<BD, P><<<grid, MC_WARPS * 32, 0, hc.stream()>>>(s.ref, s.ox, s.oy, w, h, mx, my, filter2d, out, pitch, bdmax)
+        if (hbd) { if (prep) L(BD16, true); else L(BD16, false); } else { if (prep) L(BD8, true); else L(BD8, false); }
+#undef L
+    }
+    void *stage = nullptr;
+    if (prep) stage = hc.down(out, (size_t)w * h * 2); else hc.rect_down(drect);
+    if (hc.sync()) return hc.err;
+    if (prep) memcpy(dst, stage, (size_t)w * h * 2); else drect.finish(dst);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int rb200_mc(int filter2d, void *dst, ptrdiff_t ds, const void *src, ptrdiff_t ss, int w, int h, int mx,
+                        int my, int bdmax) {
+    return mc_common(false, false, filter2d, dst, ds, src, ss, w, h, mx, my, 0, 0, bdmax);
+}
+extern "C" int rb200_mct(int filter2d, int16_t *tmp, const void *src, ptrdiff_t ss, int w, int h, int mx, int my,
+                         int bdmax) {
+    return mc_common(true, false, filter2d, tmp, 0, src, ss, w, h, mx, my, 0, 0, bdmax);
+}
+extern "C" int rb200_mc_scaled(int filter2d, void *dst, ptrdiff_t ds, const void *src, ptrdiff_t ss, int w, int h,
+                               int mx, int my, int dx, int dy, int bdmax) {
+    return mc_common(false, true, filter2d, dst, ds, src, ss, w, h, mx, my, dx, dy, bdmax);
+}
+extern "C" int rb200_mct_scaled(int filter2d, int16_t *tmp, const void *src, ptrdiff_t ss, int w, int h, int mx,
+                                int my, int dx, int dy, int bdmax) {
+    return mc_common(true, true, filter2d, tmp, 0, src, ss, w, h, mx, my, dx, dy, bdmax);
+}
+
+static int compound_common(int mode, void *dst, ptrdiff_t ds, const int16_t *t1, const int16_t *t2, int w, int h,
+                           int weight, const uint8_t *mask, int bdmax) {
+    if (!dst || !t1 || !t2 || w < 1 || h < 1 || w > 128 || h > 128) return set_error(-22, "compound: bad argument");
+    const size_t px = pxsz(bdmax), n = (size_t)w * h;
+    HostCall hc(2 * (DevRect::bytes_for(w * px, h) + n * 5));
+    DevRect drect;
+    if (hc.rect_up(drect, dst, ds, w * px, h)) return hc.err;
+    const int16_t *d1 = (const int16_t *)hc.up(t1, n * 2), *d2 = (const int16_t *)hc.up(t2, n * 2);
+    const uint8_t *dm = mask ? (const uint8_t *)hc.up(mask, n) : nullptr;
+    if (hc.err) return hc.err;
+    const int grid = (int)((n + 127) / 128);
+    if (bdmax > 255) compound_kernel<BD16><<<grid, 128, 0, hc.stream()>>>(mode, drect.dptr, drect.dpitch, d1, d2, w, h, weight, dm, bdmax);
+    else compound_kernel<BD8><<<grid, 128, 0, hc.stream()>>>(mode, drect.dptr, drect.dpitch, d1, d2, w, h, weight, dm, bdmax);
+    hc.rect_down(drect);
+    if (hc.sync()) return hc.err;
+    drect.finish(dst);
+    return 0;
+}
+extern "C" int rb200_avg(void *dst, ptrdiff_t ds, const int16_t *t1, const int16_t *t2, int w, int h, int bdmax) {
+    return compound_common(CMP_AVG, dst, ds, t1, t2, w, h, 0, nullptr, bdmax);
+}
+extern "C" int rb200_w_avg(void *dst, ptrdiff_t ds, const int16_t *t1, const int16_t *t2, int w, int h, int weight,
+                           int bdmax) {
+    return compound_common(CMP_WAVG, dst, ds, t1, t2, w, h, weight, nullptr, bdmax);
+}
+extern "C" int rb200_mask(void *dst, ptrdiff_t ds, const int16_t *t1, const int16_t *t2, int w, int h,
+                          const uint8_t *mask, int bdmax) {
+    if (!mask) return set_error(-22, "mask: null mask");
+    return compound_common(CMP_MASK, dst, ds, t1, t2, w, h, 0, mask, bdmax);
+}
+extern "C" int rb200_w_mask(int ss, void *dst, ptrdiff_t ds, const int16_t *t1, const int16_t *t2, int w, int h,
+                            uint8_t *mask, int sign, int bdmax) {
+    if (ss < 0 || ss > 2 || !dst || !t1 || !t2 || !mask || w < 2 || h < 2 || w > 128 || h > 128)
+        return set_error(-22, "w_mask: bad argument");
+    const int ss_hor = ss > 0, ss_ver = ss == 2;
+    const size_t px = pxsz(bdmax), n = (size_t)w * h, nm = (size_t)(w >> ss_hor) * (h >> ss_ver);
+    HostCall hc(2 * (DevRect::bytes_for(w * px, h) + n * 5));
+    DevRect drect;
+    if (hc.rect_up(drect, dst, ds, w * px, h)) return hc.err;
+    const int16_t *d1 = (const int16_t *)hc.up(t1, n * 2), *d2 = (const int16_t *)hc.up(t2, n * 2);
+    uint8_t *dm = (uint8_t *)hc.dev(nm);
+    if (hc.err) return hc.err;
+    const int grid = (int)((nm + 127) / 128);
+    if (bdmax > 255) w_mask_kernel<BD16><<<grid, 128, 0, hc.stream()>>>(drect.dptr, drect.dpitch, d1, d2, w, h, dm, sign, ss_hor, ss_ver, bdmax);
+    else w_mask_kernel<BD8><<<grid, 128, 0, hc.stream()>>>(drect.dptr, drect.dpitch, d1, d2, w, h, dm, sign, ss_hor, ss_ver, bdmax);
+    hc.rect_down(drect);
+    void *ms = hc.down(dm, nm);
+    if (hc.sync()) return hc.err;
+    drect.finish(dst);
+    memcpy(mask, ms, nm);
+    return 0;
+}
+extern "C" int rb200_blend(int dir, void *dst, ptrdiff_t ds, const void *tmp, int w, int h, const uint8_t *mask,
+                           int bdmax) {
+    if (dir < 0 || dir > 2 || !dst || !tmp || (dir == 0 && !mask) || w < 1 || h < 1 || w > 128 || h > 128)
+        return set_error(-22, "blend: bad argument");
+    const size_t px = pxsz(bdmax), n = (size_t)w * h;
+    HostCall hc(2 * (DevRect::bytes_for(w * px, h) + n * 3));
+    DevRect drect;
+    if (hc.rect_up(drect, dst, ds, w * px, h)) return hc.err;
+    const void *dt = hc.up(tmp, n * px);
+    const uint8_t *dm = dir == 0 ? (const uint8_t *)hc.up(mask, n) : nullptr;
+    if (hc.err) return hc.err;
+    const int grid = (int)((n + 127) / 128);
+    if (bdmax > 255) blend_kernel<BD16><<<grid, 128, 0, hc.stream()>>>(dir, drect.dptr, drect.dpitch, dt, w, h, dm);
+    else blend_kernel<BD8><<<grid, 128, 0, hc.stream()>>>(dir, drect.dptr, drect.dpitch, dt, w, h, dm);
+    hc.rect_down(drect);
+    if (hc.sync()) return hc.err;
+    drect.finish(dst);
+    return 0;
+}
+
+static int warp_common(bool prep, void *dst, ptrdiff_t ds, const void *src, ptrdiff_t ss, const int16_t *abcd, int mx,
+                       int my, int bdmax) {
+    if (!dst || !src || !abcd) return set_error(-22, "warp8x8: bad argument");
+    const size_t px = pxsz(bdmax);
+    HostCall hc(2 * (DevRect::bytes_for(15 * px, 15) + 8 * 8 * 2 + 64));
+    SrcStage s;
+    if (s.setup(hc, src, ss, 8, 8, 3, 4, 3, 4, bdmax)) return hc.err;
+    const int16_t *dabcd = (const int16_t *)hc.up(abcd, 8);
+    DevRect drect;
+    void *out; int64_t pitch;
+    if (prep) { out = hc.dev(8 * 8 * 2); pitch = 8; }
+    else { if (hc.rect_up(drect, dst, ds, 8 * px, 8)) return hc.err; out = drect.dptr; pitch = drect.dpitch; }
+    if (hc.err) return hc.err;
+#define L(BD, P) warp8x8_kernel<BD, P><<<1, 64, 0, hc.stream()>>>(s.ref, s.ox, s.oy, out, pitch, dabcd, mx, my, bdmax)
+    if (bdmax > 255) { if (prep) L(BD16, true); else L(BD16, false); } else { if (prep) L(BD8, true); else L(BD8, false); }
+#undef L
+    void *stage = nullptr;
+    if (prep) stage = hc.down(out, 128); else hc.rect_down(drect);
+    if (hc.sync()) return hc.err;
+    if (prep) { for (int y = 0; y < 8; y++) memcpy((int16_t *)dst + (int64_t)y * ds, (int16_t *)stage + y * 8, 16); }
+    else drect.finish(dst);
+    return 0;
+}
+extern "C" int rb200_warp8x8(void *dst, ptrdiff_t ds, const void *src, ptrdiff_t ss, const int16_t *abcd, int mx,
+                             int my, int bdmax) {
+    return warp_common(false, dst, ds, src, ss, abcd, mx, my, bdmax);
+}
+extern "C" int rb200_warp8x8t(int16_t *tmp, ptrdiff_t tmp_stride, const void *src, ptrdiff_t ss, const int16_t *abcd,
+                              int mx, int my, int bdmax) {
+    return warp_common(true, tmp, tmp_stride, src, ss, abcd, mx, my, bdmax);
+}
+
+extern "C" int rb200_emu_edge(intptr_t bw, intptr_t bh, intptr_t iw, intptr_t ih, intptr_t x, intptr_t y, void *dst,
+                              ptrdiff_t ds, const void *ref, ptrdiff_t rs, int bdmax) {
+    if (!dst || !ref || bw < 1 || bh < 1 || iw < 1 || ih < 1 || bw > 1024 || bh > 1024)
+        return set_error(-22, "emu_edge: bad argument");
+    const size_t px = pxsz(bdmax);
+    // only the visible part of the reference that the block touches is uploaded
+    const int x0 = iclip((int)x, 0, (int)iw - 1), y0 = iclip((int)y, 0, (int)ih - 1);
+    const int x1 = iclip((int)(x + bw - 1), 0, (int)iw - 1), y1 = iclip((int)(y + bh - 1), 0, (int)ih - 1);
+    const int cw = x1 - x0 + 1, ch = y1 - y0 + 1;
+    HostCall hc(2 * (DevRect::bytes_for(cw * px, ch) + DevRect::bytes_for(bw * px, (int)bh)));
+    DevRect srect, drect;
+    if (hc.rect_up(srect, (const uint8_t *)ref + (int64_t)y0 * rs + (int64_t)x0 * (int64_t)px, rs, cw * px, ch)) return hc.err;
+    if (hc.rect_up(drect, dst, ds, bw * px, (int)bh)) return hc.err;
+    McRef r; r.base = srect.dptr; r.stride = srect.dpitch; r.w = cw; r.h = ch;
+    dim3 grid(((int)bw + 63) / 64, (int)bh);
+    if (bdmax > 255) emu_edge_kernel<BD16><<<grid, 64, 0, hc.stream()>>>(r, (int)x - x0, (int)y - y0, (int)bw, (int)bh, drect.dptr, drect.dpitch);
+    else emu_edge_kernel<BD8><<<grid, 64, 0, hc.stream()>>>(r, (int)x - x0, (int)y - y0, (int)bw, (int)bh, drect.dptr, drect.dpitch);
+    hc.rect_down(drect);
+    if (hc.sync()) return hc.err;
+    drect.finish(dst);
+    return 0;
+}
+
+extern "C" int rb200_resize(void *dst, ptrdiff_t ds, const void *src, ptrdiff_t ss, int dst_w, int h, int src_w,
+                            int dx, int mx, int bdmax) {
+    if (!dst || !src || dst_w < 1 || h < 1 || src_w < 1) return set_error(-22, "resize: bad argument");
+    const size_t px = pxsz(bdmax);
+    HostCall hc(2 * (DevRect::bytes_for(src_w * px, h) + DevRect::bytes_for(dst_w * px, h)));
+    DevRect srect, drect;
+    if (hc.rect_up(srect, src, ss, src_w * px, h)) return hc.err;
+    if (hc.rect_up(drect, dst, ds, dst_w * px, h)) return hc.err;
+    dim3 grid((dst_w + 127) / 128, h);
+    if (bdmax > 255) resize_kernel<BD16><<<grid, 128, 0, hc.stream()>>>(drect.dptr, drect.dpitch, srect.dptr, srect.dpitch, dst_w, h, src_w, dx, mx, bdmax);
+    else resize_kernel<BD8><<<grid, 128, 0, hc.stream()>>>(drect.dptr, drect.dpitch, srect.dptr, srect.dpitch, dst_w, h, src_w, dx, mx, bdmax);
+    hc.rect_down(drect);
+    if (hc.sync()) return hc.err;
+    drect.finish(dst);
+    return 0;
+}
+
+// ---- function-pointer table (drop-in for rav1d_mc_dsp_init, src/mc.rs:2495-2566) ----
+namespace {
+#define FATAL_IF(x, name) do { if (x) rb200_report_fatal(name); } while (0)
+template <int F> void mc_slot(void *d, ptrdiff_t ds, const void *s, ptrdiff_t ss, int w, int h, int mx, int my, int bd) { FATAL_IF(rb200_mc(F, d, ds, s, ss, w, h, mx, my, bd), "mc"); }
+template <int F> void mct_slot(int16_t *t, const void *s, ptrdiff_t ss, int w, int h, int mx, int my, int bd) { FATAL_IF(rb200_mct(F, t, s, ss, w, h, mx, my, bd), "mct"); }
+template <int F> void mcs_slot(void *d, ptrdiff_t ds, const void *s, ptrdiff_t ss, int w, int h, int mx, int my, int dx, int dy, int bd) { FATAL_IF(rb200_mc_scaled(F, d, ds, s, ss, w, h, mx, my, dx, dy, bd), "mc_scaled"); }
+template <int F> void mcts_slot(int16_t *t, const void *s, ptrdiff_t ss, int w, int h, int mx, int my, int dx, int dy, int bd) { FATAL_IF(rb200_mct_scaled(F, t, s, ss, w, h, mx, my, dx, dy, bd), "mct_scaled"); }
+void avg_slot(void *d, ptrdiff_t ds, const int16_t *a, const int16_t *b, int w, int h, int bd) { FATAL_IF(rb200_avg(d, ds, a, b, w, h, bd), "avg"); }
+void w_avg_slot(void *d, ptrdiff_t ds, const int16_t *a, const int16_t *b, int w, int h, int wt, int bd) { FATAL_IF(rb200_w_avg(d, ds, a, b, w, h, wt, bd), "w_avg"); }
+void mask_slot(void *d, ptrdiff_t ds, const int16_t *a, const int16_t *b, int w, int h, const uint8_t *m, int bd) { FATAL_IF(rb200_mask(d, ds, a, b, w, h, m, bd), "mask"); }
+template <int SS> void w_mask_slot(void *d, ptrdiff_t ds, const int16_t *a, const int16_t *b, int w, int h, uint8_t *m, int sign, int bd) { FATAL_IF(rb200_w_mask(SS, d, ds, a, b, w, h, m, sign, bd), "w_mask"); }
+template <int BDMAX> void blend_slot(void *d, ptrdiff_t ds, const void *t, int w, int h, const uint8_t *m) { FATAL_IF(rb200_blend(0, d, ds, t, w, h, m, BDMAX), "blend"); }
+template <int BDMAX, int DIR> void blend_dir_slot(void *d, ptrdiff_t ds, const void *t, int w, int h) { FATAL_IF(rb200_blend(DIR, d, ds, t, w, h, nullptr, BDMAX), "blend_dir"); }
+void warp_slot(void *d, ptrdiff_t ds, const void *s, ptrdiff_t ss, const int16_t *abcd, int mx, int my, int bd) { FATAL_IF(rb200_warp8x8(d, ds, s, ss, abcd, mx, my, bd), "warp8x8"); }
+void warpt_slot(int16_t *t, ptrdiff_t ts, const void *s, ptrdiff_t ss, const int16_t *abcd, int mx, int my, int bd) { FATAL_IF(rb200_warp8x8t(t, ts, s, ss, abcd, mx, my, bd), "warp8x8t"); }
+template <int BDMAX> void emu_slot(intptr_t bw, intptr_t bh, intptr_t iw, intptr_t ih, intptr_t x, intptr_t y, void *d, ptrdiff_t ds, const void *r, ptrdiff_t rs) { FATAL_IF(rb200_emu_edge(bw, bh, iw, ih, x, y, d, ds, r, rs, BDMAX), "emu_edge"); }
+void resize_slot(void *d, ptrdiff_t ds, const void *s, ptrdiff_t ss, int dw, int h, int sw, int dx, int mx, int bd) { FATAL_IF(rb200_resize(d, ds, s, ss, dw, h, sw, dx, mx, bd), "resize"); }
+
+template <int... F>
+void fill_mc(Rb200MCDSPContext *c, std::integer_sequence<int, F...>) {
+    ((c->mc[F] = &mc_slot<F>, c->mct[F] = &mct_slot<F>, c->mc_scaled[F] = &mcs_slot<F>, c->mct_scaled[F] = &mcts_slot<F>), ...);
+}
+}  // namespace
+
+extern "C" void rb200_mc_dsp_init(Rb200MCDSPContext *c, int bpc) {
+    fill_mc(c, std::make_integer_sequence<int, RB200_N_2D_FILTERS>{});
+    c->avg = &avg_slot; c->w_avg = &w_avg_slot; c->mask = &mask_slot;
+    c->w_mask[0] = &w_mask_slot<0>; c->w_mask[1] = &w_mask_slot<1>; c->w_mask[2] = &w_mask_slot<2>;
+    if (bpc > 8) {
+        c->blend = &blend_slot<1023>; c->blend_v = &blend_dir_slot<1023, 1>; c->blend_h = &blend_dir_slot<1023, 2>;
+        c->emu_edge = &emu_slot<1023>;
+    } else {
+        c->blend = &blend_slot<255>; c->blend_v = &blend_dir_slot<255, 1>; c->blend_h = &blend_dir_slot<255, 2>;
+        c->emu_edge = &emu_slot<255>;
+    }
+    c->warp8x8 = &warp_slot; c->warp8x8t = &warpt_slot; c->resize = &resize_slot;
+}

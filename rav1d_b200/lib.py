@@ -80,3 +80,107 @@ def check(rc, what=""):
     if rc != 0:
         raise Rb200Error(f"{what or 'rav1d_b200'} failed ({rc}): {last_error().decode(errors='replace')}")
     return rc
+
+
+# ---------------------------------------------------------------- mc / filters / frame
+import numpy as _np
+
+N_2D_FILTERS = 10
+FILTER_2D_NAMES = ["8TAP_REGULAR", "8TAP_REGULAR_SMOOTH", "8TAP_REGULAR_SHARP", "8TAP_SHARP_REGULAR",
+                   "8TAP_SHARP_SMOOTH", "8TAP_SHARP", "8TAP_SMOOTH_REGULAR", "8TAP_SMOOTH", "8TAP_SMOOTH_SHARP",
+                   "BILINEAR"]
+STAGE_RECON, STAGE_DEBLOCK, STAGE_CDEF, STAGE_LR = 1, 2, 4, 8
+STAGE_ALL = 15
+LAYOUT_I400, LAYOUT_I420, LAYOUT_I422, LAYOUT_I444 = 0, 1, 2, 3
+RESTORATION_NONE, RESTORATION_SWITCHABLE, RESTORATION_WIENER, RESTORATION_SGRPROJ = 0, 1, 2, 3
+
+# numpy mirrors of the C records (include/rav1d_b200.h)
+MC_ITEM_DT = _np.dtype([("dst_x", "<i2"), ("dst_y", "<i2"), ("src_x", "<i2"), ("src_y", "<i2"), ("w", "u1"),
+                        ("h", "u1"), ("plane", "u1"), ("ref", "u1"), ("mx", "u1"), ("my", "u1"),
+                        ("filter2d", "u1"), ("flags", "u1")])
+ITX_ITEM_DT = _np.dtype([("cf_off", "<u4"), ("x", "<u2"), ("y", "<u2"), ("plane", "u1"), ("tx", "u1"),
+                         ("txtp", "u1"), ("flags", "u1"), ("eob", "<i2"), ("pad", "<i2")])
+AV1_FILTER_DT = _np.dtype([("filter_y", "<u2", (2, 32, 3, 2)), ("filter_uv", "<u2", (2, 32, 2, 2)),
+                           ("cdef_idx", "i1", (4,)), ("noskip_mask", "<u2", (16, 2))])
+LR_UNIT_DT = _np.dtype([("type", "u1"), ("filter_h", "i1", (3,)), ("filter_v", "i1", (3,)),
+                        ("sgr_weights", "i1", (2,))])
+AV1_RESTORATION_DT = _np.dtype([("lr", LR_UNIT_DT, (3, 4))])
+assert MC_ITEM_DT.itemsize == 16 and ITX_ITEM_DT.itemsize == 16
+assert AV1_FILTER_DT.itemsize == 1348 and AV1_RESTORATION_DT.itemsize == 108
+
+
+class FilterLUT(C.Structure):
+    _fields_ = [("e", C.c_uint8 * 64), ("i", C.c_uint8 * 64), ("sharp", C.c_uint64 * 2)]
+
+
+class LrParams(C.Union):
+    class _Sgr(C.Structure):
+        _fields_ = [("s0", C.c_uint32), ("s1", C.c_uint32), ("w0", C.c_int16), ("w1", C.c_int16)]
+    _fields_ = [("filter", (C.c_int16 * 8) * 2), ("sgr", _Sgr), ("_align", C.c_byte * 32)]
+
+
+class FrameHeader(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("bpc", C.c_int32), ("layout", C.c_int32),
+                ("sb128", C.c_int32), ("lf_level_y", C.c_int32 * 2), ("lf_level_u", C.c_int32),
+                ("lf_level_v", C.c_int32), ("cdef_damping", C.c_int32), ("cdef_y_strength", C.c_int32 * 8),
+                ("cdef_uv_strength", C.c_int32 * 8), ("lr_type", C.c_int32 * 3),
+                ("lr_unit_size_log2", C.c_int32 * 2)]
+
+
+class FrameGeometry(C.Structure):
+    _fields_ = [("bw", C.c_int32), ("bh", C.c_int32), ("w4", C.c_int32), ("h4", C.c_int32),
+                ("sb128w", C.c_int32), ("sb128h", C.c_int32), ("sbh", C.c_int32), ("b4_stride", C.c_int32),
+                ("ss_hor", C.c_int32), ("ss_ver", C.c_int32), ("stride", C.c_int64 * 2),
+                ("plane_h", C.c_int32 * 2), ("n_planes", C.c_int32)]
+
+
+_vp, _i, _ss, _sz = C.c_void_p, C.c_int, C.c_ssize_t, C.c_size_t
+mc = _sig("rb200_mc", _i, _i, _vp, _ss, _vp, _ss, _i, _i, _i, _i, _i)
+mct = _sig("rb200_mct", _i, _i, _vp, _vp, _ss, _i, _i, _i, _i, _i)
+mc_scaled = _sig("rb200_mc_scaled", _i, _i, _vp, _ss, _vp, _ss, _i, _i, _i, _i, _i, _i, _i)
+mct_scaled = _sig("rb200_mct_scaled", _i, _i, _vp, _vp, _ss, _i, _i, _i, _i, _i, _i, _i)
+avg = _sig("rb200_avg", _i, _vp, _ss, _vp, _vp, _i, _i, _i)
+w_avg = _sig("rb200_w_avg", _i, _vp, _ss, _vp, _vp, _i, _i, _i, _i)
+mask = _sig("rb200_mask", _i, _vp, _ss, _vp, _vp, _i, _i, _vp, _i)
+w_mask = _sig("rb200_w_mask", _i, _i, _vp, _ss, _vp, _vp, _i, _i, _vp, _i, _i)
+blend = _sig("rb200_blend", _i, _i, _vp, _ss, _vp, _i, _i, _vp, _i)
+warp8x8 = _sig("rb200_warp8x8", _i, _vp, _ss, _vp, _ss, _vp, _i, _i, _i)
+warp8x8t = _sig("rb200_warp8x8t", _i, _vp, _ss, _vp, _ss, _vp, _i, _i, _i)
+emu_edge = _sig("rb200_emu_edge", _i, _ss, _ss, _ss, _ss, _ss, _ss, _vp, _ss, _vp, _ss, _i)
+resize = _sig("rb200_resize", _i, _vp, _ss, _vp, _ss, _i, _i, _i, _i, _i, _i)
+mc_batch = _sig("rb200_mc_batch", _i, C.POINTER(Planes), C.POINTER(Planes), _i, _i, _i, _i, _i, _vp, _i, _i, _vp)
+loop_filter_sb = _sig("rb200_loop_filter_sb", _i, _i, _i, _vp, _ss, _vp, _vp, _ss, C.POINTER(FilterLUT), _i, _i)
+cdef_dir = _sig("rb200_cdef_dir", _i, _vp, _ss, C.POINTER(C.c_uint), _i, C.POINTER(C.c_int))
+cdef_fb = _sig("rb200_cdef_fb", _i, _i, _vp, _ss, _vp, _vp, _vp, _i, _i, _i, _i, C.c_uint32, _i)
+lr = _sig("rb200_lr", _i, _i, _vp, _ss, _vp, _vp, _i, _i, C.POINTER(LrParams), C.c_uint32, _i)
+mc_dsp_init = _sig("rb200_mc_dsp_init", None, _vp, _i)
+loop_filter_dsp_init = _sig("rb200_loop_filter_dsp_init", None, _vp, _i)
+cdef_dsp_init = _sig("rb200_cdef_dsp_init", None, _vp, _i)
+loop_restoration_dsp_init = _sig("rb200_loop_restoration_dsp_init", None, _vp, _i)
+
+frame_create = _sig("rb200_frame_create", _i, C.POINTER(_vp), C.POINTER(FrameHeader), _sz, _i, _i)
+frame_destroy = _sig("rb200_frame_destroy", _i, _vp)
+frame_geometry = _sig("rb200_frame_geometry", _i, _vp, C.POINTER(FrameGeometry))
+frame_coef_buffer = _sig("rb200_frame_coef_buffer", _vp, _vp)
+frame_itx_items = _sig("rb200_frame_itx_items", _vp, _vp)
+frame_mc_items = _sig("rb200_frame_mc_items", _vp, _vp)
+frame_lf_masks = _sig("rb200_frame_lf_masks", _vp, _vp)
+frame_lf_levels = _sig("rb200_frame_lf_levels", _vp, _vp)
+frame_lf_lut = _sig("rb200_frame_lf_lut", _vp, _vp)
+frame_lr_masks = _sig("rb200_frame_lr_masks", _vp, _vp)
+frame_set_ref = _sig("rb200_frame_set_ref", _i, _vp, _i, C.POINTER(Planes))
+frame_upload_planes = _sig("rb200_frame_upload_planes", _i, _vp, _i, C.POINTER(_vp), C.POINTER(_ss))
+frame_output_planes = _sig("rb200_frame_output_planes", _i, _vp, C.POINTER(Planes))
+frame_stage_planes = _sig("rb200_frame_stage_planes", _i, _vp, _i, C.POINTER(Planes))
+frame_submit = _sig("rb200_frame_submit", _i, _vp, _sz, C.POINTER(C.c_int32), _i, _i, _i)
+frame_wait = _sig("rb200_frame_wait", _i, _vp)
+frame_readback = _sig("rb200_frame_readback", _i, _vp, C.POINTER(_vp), C.POINTER(_ss))
+frame_stream = _sig("rb200_frame_stream", _vp, _vp)
+frame_last_launches = _sig("rb200_frame_last_launches", _i, _vp)
+
+
+def np_view(ptr, dtype, count):
+    """numpy view of `count` records of `dtype` at raw address `ptr` (pinned staging owned by the library)."""
+    dtype = _np.dtype(dtype)
+    buf = (C.c_ubyte * (dtype.itemsize * count)).from_address(ptr)
+    return _np.frombuffer(buf, dtype=dtype, count=count)

@@ -1,0 +1,380 @@
+"""Synthetic inter frame for the recon + post-filter path (BASELINE.json configs 2-4).
+
+Produces, with numpy only, every array the reference's pass 1 would hand to pass 2
+and to the filter tasks, in the reference's own formats:
+
+* a smooth-plus-noise reference picture (so that deblock / CDEF / LR decisions
+  actually fire, unlike on white noise);
+* per-block motion vectors -> `McItem`s, following recon.rs `mc()` addressing
+  (src/recon.rs:2047-2055: mx = mvx & (15 >> !ss_hor), dx = bx*h_mul + (mvx >> (3 + ss_hor)));
+* residual coefficients from the checkasm `ftx` recipe (rav1d_b200.synth.itxgen) packed
+  back to back like `f.frame_thread.cf` (src/recon.rs:1706-1707), `ItxItem`s sorted by tx size;
+* `Av1Filter` edge masks built with the min-of-both-sides rule of mask_edges_inter
+  (src/lf_mask.rs:230-330), per-4x4 `level[4]`, `Av1FilterLUT` (rav1d_calc_eih, src/lf_mask.rs:608-626);
+* `cdef_idx` / `noskip_mask` (src/decode.rs:1996-2004) and per-unit `Av1RestorationUnit`s with the
+  tap / weight ranges of read_restoration_info (src/decode.rs:2559-2620).
+
+Layout is 4:2:0; luma prediction blocks are 16x16 (8x8 chroma).
+"""
+import ctypes as C
+
+import numpy as np
+
+from .. import lib
+from .itxgen import gen_coefs
+
+BLK = 16  # luma prediction block edge
+
+
+def calc_eih(sharp):
+    """rav1d_calc_eih (src/lf_mask.rs:608-626) -> lib.FilterLUT"""
+    lut = lib.FilterLUT()
+    for level in range(64):
+        limit = level
+        if sharp > 0:
+            limit >>= (sharp + 3) >> 2
+            limit = min(limit, 9 - sharp)
+        limit = max(limit, 1)
+        lut.i[level] = limit
+        lut.e[level] = 2 * (level + 2) + limit
+    lut.sharp[0] = (sharp + 3) >> 2
+    lut.sharp[1] = 9 - sharp if sharp else 0xff
+    return lut
+
+
+def smooth_plane(rng, h, w, bdmax, cell=16, noise=2):
+    """Low-frequency content plus a little noise."""
+    gh, gw = h // cell + 2, w // cell + 2
+    coarse = rng.integers(bdmax // 8, bdmax - bdmax // 8, size=(gh, gw)).astype(np.float32)
+    # bilinear upsample
+    ys = (np.arange(h) + 0.5) / cell
+    xs = (np.arange(w) + 0.5) / cell
+    y0 = np.floor(ys).astype(np.int64); x0 = np.floor(xs).astype(np.int64)
+    fy = (ys - y0)[:, None].astype(np.float32); fx = (xs - x0)[None, :].astype(np.float32)
+    a = coarse[y0][:, x0]; b = coarse[y0][:, x0 + 1]; c = coarse[y0 + 1][:, x0]; d = coarse[y0 + 1][:, x0 + 1]
+    img = (a * (1 - fx) + b * fx) * (1 - fy) + (c * (1 - fx) + d * fx) * fy
+    img += rng.integers(-noise, noise + 1, size=(h, w))
+    return np.clip(np.rint(img), 0, bdmax)
+
+
+class SynthFrame:
+    pass
+
+
+def make_header(w, h, bpc, rng):
+    hd = lib.FrameHeader()
+    hd.width, hd.height, hd.bpc, hd.layout, hd.sb128 = w, h, bpc, lib.LAYOUT_I420, 0
+    hd.lf_level_y[0] = hd.lf_level_y[1] = 32
+    hd.lf_level_u = hd.lf_level_v = 32
+    hd.cdef_damping = int(rng.integers(3, 7))
+    for i in range(8):
+        hd.cdef_y_strength[i] = int(rng.integers(0, 64))
+        hd.cdef_uv_strength[i] = int(rng.integers(0, 64))
+    hd.cdef_y_strength[1] = 0          # one preset without luma filtering
+    hd.cdef_uv_strength[2] = 0         # one without chroma
+    hd.cdef_y_strength[3] = 3          # secondary only
+    for p in range(3):
+        hd.lr_type[p] = lib.RESTORATION_SWITCHABLE
+    hd.lr_unit_size_log2[0] = 6
+    hd.lr_unit_size_log2[1] = 6
+    return hd
+
+
+def geometry(hd):
+    w, h = hd.width, hd.height
+    g = lib.FrameGeometry()
+    g.bw = ((w + 7) >> 3) << 1; g.bh = ((h + 7) >> 3) << 1
+    g.w4 = (w + 3) >> 2; g.h4 = (h + 3) >> 2
+    g.sb128w = (g.bw + 31) >> 5; g.sb128h = (g.bh + 31) >> 5
+    g.sbh = (g.bh + (16 << hd.sb128) - 1) >> (4 + hd.sb128)
+    g.b4_stride = (g.bw + 31) & ~31
+    g.ss_hor = g.ss_ver = 1
+    g.n_planes = 3
+    return g
+
+
+def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1):
+    """Returns a SynthFrame with numpy arrays; see module docstring."""
+    rng = np.random.default_rng(seed)
+    bdmax = (1 << bpc) - 1
+    hbd = bpc > 8
+    pdt = np.uint16 if hbd else np.uint8
+    cdt = np.int32 if hbd else np.int16
+    s = SynthFrame()
+    s.w, s.h, s.bpc, s.bdmax = w, h, bpc, bdmax
+    s.hdr = make_header(w, h, bpc, rng)
+    g = s.geom = geometry(s.hdr)
+    aw, ah = (w + 127) & ~127, (h + 127) & ~127
+    s.aw, s.ah = aw, ah
+
+    # ---- reference picture (visible area w x h; the padding is left zero and never read: MC clamps)
+    s.ref = [np.zeros((ah, aw), pdt), np.zeros((ah // 2, aw // 2), pdt), np.zeros((ah // 2, aw // 2), pdt)]
+    s.ref[0][:h, :w] = smooth_plane(rng, h, w, bdmax)
+    for p in (1, 2):
+        s.ref[p][:(h + 1) // 2, :(w + 1) // 2] = smooth_plane(rng, (h + 1) // 2, (w + 1) // 2, bdmax, cell=8)
+
+    # ---- blocks
+    nbx, nby = (w + BLK - 1) // BLK, (h + BLK - 1) // BLK
+    nb = nbx * nby
+    by, bx = np.divmod(np.arange(nb), nbx)
+    mvx = rng.integers(-512, 513, size=nb)      # 1/8 luma pel, +-64 px
+    mvy = rng.integers(-512, 513, size=nb)
+    zero = rng.random(nb) < 0.15                # some full-pel / zero-phase vectors (copy and 1-D paths)
+    mvx[zero] &= ~7
+    zero = rng.random(nb) < 0.15
+    mvy[zero] &= ~7
+    f2d = rng.integers(0, 10, size=nb)          # 9 8-tap combinations + bilinear
+    skip = rng.random(nb) < skip_frac
+    ytx_split = (rng.random(nb) < 0.3) & ~skip  # luma: TX_16X16 or 4 x TX_8X8
+    ctx_split = (rng.random(nb) < 0.2) & ~skip  # chroma: TX_8X8 or 4 x TX_4X4
+    s.n_blocks = nb
+
+    mc = np.zeros(nb * 3, lib.MC_ITEM_DT)
+    y_it = mc[:nb]
+    y_it["dst_x"] = bx * BLK; y_it["dst_y"] = by * BLK
+    y_it["src_x"] = bx * BLK + (mvx >> 3); y_it["src_y"] = by * BLK + (mvy >> 3)
+    y_it["w"] = BLK; y_it["h"] = BLK; y_it["plane"] = 0
+    y_it["mx"] = (mvx & 7) << 1; y_it["my"] = (mvy & 7) << 1
+    y_it["filter2d"] = f2d
+    for p in (1, 2):
+        c_it = mc[p * nb:(p + 1) * nb]
+        c_it["dst_x"] = bx * (BLK // 2); c_it["dst_y"] = by * (BLK // 2)
+        c_it["src_x"] = bx * (BLK // 2) + (mvx >> 4); c_it["src_y"] = by * (BLK // 2) + (mvy >> 4)
+        c_it["w"] = BLK // 2; c_it["h"] = BLK // 2; c_it["plane"] = p
+        c_it["mx"] = mvx & 15; c_it["my"] = mvy & 15
+        c_it["filter2d"] = f2d
+    s.mc_items = mc
+
+    # ---- transform blocks: (plane, x, y, tx, txtp)
+    TX_4X4, TX_8X8, TX_16X16 = 0, 1, 2
+    recs = []
+    ns = ~skip
+    def add(plane, xs, ys, tx):
+        recs.append((np.full(xs.size, plane), xs, ys, np.full(xs.size, tx)))
+    sel = ns & ~ytx_split
+    add(0, bx[sel] * 16, by[sel] * 16, TX_16X16)
+    sel = ns & ytx_split
+    for oy in (0, 8):
+        for ox in (0, 8):
+            add(0, bx[sel] * 16 + ox, by[sel] * 16 + oy, TX_8X8)
+    for p in (1, 2):
+        sel = ns & ~ctx_split
+        add(p, bx[sel] * 8, by[sel] * 8, TX_8X8)
+        sel = ns & ctx_split
+        for oy in (0, 4):
+            for ox in (0, 4):
+                add(p, bx[sel] * 8 + ox, by[sel] * 8 + oy, TX_4X4)
+    plane = np.concatenate([r[0] for r in recs]); xs = np.concatenate([r[1] for r in recs])
+    ys = np.concatenate([r[2] for r in recs]); tx = np.concatenate([r[3] for r in recs])
+    order = np.argsort(tx, kind="stable")
+    plane, xs, ys, tx = plane[order], xs[order], ys[order], tx[order]
+    n_itx = tx.size
+    txtp = np.zeros(n_itx, np.int64)
+    r = rng.random(n_itx)
+    ntypes = np.where(tx == TX_16X16, 12, 16)
+    txtp = np.where(r < 0.6, 0, rng.integers(0, 16, size=n_itx) % ntypes)
+    itx = np.zeros(n_itx, lib.ITX_ITEM_DT)
+    itx["x"] = xs; itx["y"] = ys; itx["plane"] = plane; itx["tx"] = tx; itx["txtp"] = txtp
+    counts = np.zeros(19, np.int32)
+    for t in range(19):
+        counts[t] = int((tx == t).sum())
+    dims = {TX_4X4: 16, TX_8X8: 64, TX_16X16: 256}
+    ncoef = np.array([dims[int(t)] for t in (TX_4X4, TX_8X8, TX_16X16)])
+    per = np.where(tx == TX_4X4, 16, np.where(tx == TX_8X8, 64, 256))
+    cf_off = np.concatenate([[0], np.cumsum(per)[:-1]]) if n_itx else np.zeros(0, np.int64)
+    itx["cf_off"] = cf_off
+    n_coefs = int(per.sum())
+    coef = np.zeros(n_coefs, cdt)
+    eobs = np.zeros(n_itx, np.int32)
+    res_max = max(bdmax >> res_amp_shift, 2)
+    for t in (TX_4X4, TX_8X8, TX_16X16):
+        for tp in range(16):
+            idx = np.nonzero((tx == t) & (txtp == tp))[0]
+            if not idx.size:
+                continue
+            c, e = gen_coefs(rng, t, tp, res_max, idx.size, "full")
+            # eob uniform in [0, full]: zero everything above a random scan position
+            n = dims[t]
+            cut = rng.integers(0, n, size=idx.size)
+            c[np.arange(n)[None, :] > cut[:, None]] = 0
+            nz = c != 0
+            last = np.where(nz.any(axis=1), n - 1 - np.argmax(nz[:, ::-1], axis=1), 0)
+            if tp == 0:
+                e = last  # DCT_DCT: eob 0 takes the dc-only shortcut (src/itx.rs:90)
+            else:
+                e = np.maximum(last, 1)
+            eobs[idx] = e
+            dst = cf_off[idx][:, None] + np.arange(n)[None, :]
+            coef[dst.ravel()] = c.ravel().astype(cdt)
+    itx["eob"] = eobs
+    s.itx_items, s.itx_counts, s.coef, s.n_coefs = itx, counts, coef, n_coefs
+
+    # ---- per-4x4 transform-size maps -> edge masks
+    H4, W4 = g.sb128h * 32, g.b4_stride
+    ylog = np.full((H4, W4), 2, np.int8)        # log2 of luma tx edge in 4-px units (2 = 16)
+    yb = np.zeros((H4, W4), bool)               # 4x4 columns / rows that start a tx block
+    split_map = np.zeros((nby, nbx), bool); split_map.ravel()[:] = ytx_split
+    big = np.kron(split_map, np.ones((4, 4), bool))
+    ylog[:big.shape[0], :big.shape[1]][big] = 1
+    y4, x4 = np.mgrid[0:H4, 0:W4]
+    step = (1 << ylog.astype(np.int64))
+    col_edge = (x4 % step) == 0
+    row_edge = (y4 % step) == 0
+    inside = (y4 < g.h4) & (x4 < g.w4)
+    masks = np.zeros(g.sb128w * g.sb128h, lib.AV1_FILTER_DT)
+    fy = masks["filter_y"]
+    left = np.empty_like(ylog); left[:, 1:] = ylog[:, :-1]; left[:, 0] = ylog[:, 0]
+    top = np.empty_like(ylog); top[1:, :] = ylog[:-1, :]; top[0, :] = ylog[0, :]
+    def setbits(arr, d, sel, a_idx, bitpos, idx, sb):
+        halfw = 16
+        yy = np.nonzero(sel)
+        sbv = sb[yy]; a = a_idx[yy]; b = bitpos[yy]; i = idx[yy]
+        np.bitwise_or.at(arr, (sbv, d, a, i, b // halfw), (1 << (b % halfw)).astype(np.uint16))
+    sb = (y4 >> 5) * g.sb128w + (x4 >> 5)
+    setbits(fy, 0, col_edge & inside, x4 & 31, y4 & 31, np.minimum(ylog, left).astype(np.int64), sb)
+    setbits(fy, 1, row_edge & inside, y4 & 31, x4 & 31, np.minimum(ylog, top).astype(np.int64), sb)
+    # chroma (4:2:0): units are chroma 4x4; sb128 holds 16 x 16 of them
+    CH4, CW4 = H4 // 2, W4 // 2
+    clog = np.full((CH4, CW4), 1, np.int8)      # 8x8 chroma tx
+    csplit = np.zeros((nby, nbx), bool); csplit.ravel()[:] = ctx_split
+    cbig = np.kron(csplit, np.ones((2, 2), bool))
+    clog[:cbig.shape[0], :cbig.shape[1]][cbig] = 0
+    cy4, cx4 = np.mgrid[0:CH4, 0:CW4]
+    cstep = (1 << clog.astype(np.int64))
+    ccol = (cx4 % cstep) == 0; crow = (cy4 % cstep) == 0
+    cinside = (cy4 < (g.h4 + 1) // 2) & (cx4 < (g.w4 + 1) // 2)
+    cleft = np.empty_like(clog); cleft[:, 1:] = clog[:, :-1]; cleft[:, 0] = clog[:, 0]
+    ctop = np.empty_like(clog); ctop[1:, :] = clog[:-1, :]; ctop[0, :] = clog[0, :]
+    csb = (cy4 >> 4) * g.sb128w + (cx4 >> 4)
+    fuv = masks["filter_uv"]
+    def setbits_uv(d, sel, a_idx, bitpos, idx):
+        yy = np.nonzero(sel)
+        sbv = csb[yy]; a = a_idx[yy]; b = bitpos[yy]; i = idx[yy]
+        np.bitwise_or.at(fuv, (sbv, d, a, i, b // 8), (1 << (b % 8)).astype(np.uint16))
+    setbits_uv(0, ccol & cinside, cx4 & 15, cy4 & 15, np.minimum(clog, cleft).astype(np.int64))
+    setbits_uv(1, crow & cinside, cy4 & 15, cx4 & 15, np.minimum(clog, ctop).astype(np.int64))
+
+    # ---- levels: per prediction block, a few zeros to exercise the neighbour fallback
+    lv = rng.integers(0, 64, size=(4, nby, nbx)).astype(np.uint8)
+    lv[rng.random(lv.shape) < 0.08] = 0
+    levels = np.zeros((H4, W4, 4), np.uint8)
+    for k in (0, 1):
+        up = np.kron(lv[k], np.ones((4, 4), np.uint8))
+        levels[:up.shape[0], :up.shape[1], k] = up[:H4, :W4]
+    for k in (2, 3):
+        up = np.kron(lv[k], np.ones((2, 2), np.uint8))
+        levels[:up.shape[0], :up.shape[1], k] = up[:H4, :W4]
+    s.levels = levels
+    s.lut = calc_eih(int(rng.integers(0, 3)))
+
+    # ---- CDEF: cdef_idx per 64x64, noskip bits per non-skip block
+    n64y, n64x = g.sb128h * 2, g.sb128w * 2
+    cidx = rng.integers(0, 8, size=(n64y, n64x)).astype(np.int8)
+    cidx[rng.random(cidx.shape) < 0.05] = -1
+    masks["cdef_idx"] = cidx.reshape(g.sb128h, 2, g.sb128w, 2).transpose(0, 2, 1, 3).reshape(-1, 4)
+    nsk = masks["noskip_mask"]
+    bsel = np.nonzero(ns)[0]
+    bx4 = bx[bsel] * 4; by4 = by[bsel] * 4
+    sbb = (by4 >> 5) * g.sb128w + (bx4 >> 5)
+    for dy in (0, 2):
+        np.bitwise_or.at(nsk, (sbb, ((by4 + dy) & 31) >> 1, (bx4 & 16) >> 4), (0xF << (bx4 & 15)).astype(np.uint16))
+    s.masks = masks
+
+    # ---- loop restoration units
+    lrm = np.zeros(g.sb128w * g.sb128h, lib.AV1_RESTORATION_DT)
+    u = lrm["lr"]
+    shape = u["type"].shape
+    kind = rng.random(shape)
+    sgr_idx = rng.integers(0, 16, size=shape)
+    typ = np.where(kind < 0.1, 0, np.where(kind < 0.55, lib.RESTORATION_WIENER, lib.RESTORATION_SGRPROJ + sgr_idx))
+    u["type"] = typ.astype(np.uint8)
+    for name in ("filter_h", "filter_v"):
+        t0 = rng.integers(-5, 11, size=shape); t1 = rng.integers(-23, 9, size=shape); t2 = rng.integers(-17, 47, size=shape)
+        t0[rng.random(shape) < 0.3] = 0           # 5-tap variant
+        t0[:, 1:, :] = 0                          # chroma has no outer tap (src/decode.rs:2578)
+        u[name] = np.stack([t0, t1, t2], axis=-1).astype(np.int8)
+    sp = np.array([[140, 3236], [112, 2158], [93, 1618], [80, 1438], [70, 1295], [58, 1177], [47, 1079], [37, 996],
+                   [30, 925], [25, 863], [0, 2589], [0, 1618], [0, 1177], [0, 925], [56, 0], [22, 0]])
+    w0 = np.where(sp[sgr_idx, 0] != 0, rng.integers(-96, 32, size=shape), 0)
+    w1 = np.where(sp[sgr_idx, 1] != 0, rng.integers(-32, 96, size=shape), 95)
+    u["sgr_weights"] = np.stack([w0, w1], axis=-1).astype(np.int8)
+    s.lr_masks = lrm
+    return s
+
+
+def recon_input_planes(s, rng=None):
+    """A plausible pre-filter picture for post-filter-only tests (BASELINE config 4)."""
+    rng = rng or np.random.default_rng(7)
+    pdt = s.ref[0].dtype
+    out = [np.zeros_like(p) for p in s.ref]
+    out[0][:s.h, :s.w] = smooth_plane(rng, s.h, s.w, s.bdmax, noise=3)
+    for p in (1, 2):
+        out[p][:(s.h + 1) // 2, :(s.w + 1) // 2] = smooth_plane(rng, (s.h + 1) // 2, (s.w + 1) // 2, s.bdmax, cell=8, noise=3)
+    return [o.astype(pdt) for o in out]
+
+
+class DeviceFrame:
+    """Host-side driver of one rb200 frame object: fills the pinned staging from a SynthFrame."""
+
+    def __init__(self, s):
+        self.s = s
+        self.h = C.c_void_p()
+        lib.check(lib.frame_create(C.byref(self.h), C.byref(s.hdr), max(s.n_coefs, 1), max(len(s.itx_items), 1),
+                                   max(len(s.mc_items), 1)), "frame_create")
+        g = lib.FrameGeometry()
+        lib.check(lib.frame_geometry(self.h, C.byref(g)))
+        self.g = g
+        self.ref_handle = None
+
+    def close(self):
+        if self.h:
+            lib.frame_destroy(self.h)
+            self.h = None
+        if self.ref_handle:
+            lib.frame_destroy(self.ref_handle)
+            self.ref_handle = None
+
+    def load_batch(self):
+        s, g = self.s, self.g
+        lib.np_view(lib.frame_coef_buffer(self.h), s.coef.dtype, max(s.n_coefs, 1))[:s.n_coefs] = s.coef
+        lib.np_view(lib.frame_itx_items(self.h), lib.ITX_ITEM_DT, max(len(s.itx_items), 1))[:len(s.itx_items)] = s.itx_items
+        lib.np_view(lib.frame_mc_items(self.h), lib.MC_ITEM_DT, max(len(s.mc_items), 1))[:len(s.mc_items)] = s.mc_items
+        n = g.sb128w * g.sb128h
+        lib.np_view(lib.frame_lf_masks(self.h), lib.AV1_FILTER_DT, n)[:] = s.masks
+        lv = lib.np_view(lib.frame_lf_levels(self.h), np.uint8, g.b4_stride * 32 * g.sb128h * 4)
+        lv[:] = s.levels.reshape(-1)
+        C.memmove(lib.frame_lf_lut(self.h), C.byref(s.lut), C.sizeof(lib.FilterLUT))
+        lib.np_view(lib.frame_lr_masks(self.h), lib.AV1_RESTORATION_DT, n)[:] = s.lr_masks
+
+    def upload(self, which, planes):
+        data = (C.c_void_p * 3)(*[p.ctypes.data for p in planes])
+        strides = (C.c_ssize_t * 2)(planes[0].strides[0], planes[1].strides[0])
+        lib.check(lib.frame_upload_planes(self.h, which, data, strides), "frame_upload_planes")
+
+    def set_ref_from_host(self, planes):
+        """Reference pictures live in a second frame object's plane set 0 (device resident)."""
+        if self.ref_handle is None:
+            self.ref_handle = C.c_void_p()
+            lib.check(lib.frame_create(C.byref(self.ref_handle), C.byref(self.s.hdr), 1, 1, 1), "frame_create(ref)")
+        data = (C.c_void_p * 3)(*[p.ctypes.data for p in planes])
+        strides = (C.c_ssize_t * 2)(planes[0].strides[0], planes[1].strides[0])
+        lib.check(lib.frame_upload_planes(self.ref_handle, 0, data, strides))
+        pl = lib.Planes()
+        lib.check(lib.frame_stage_planes(self.ref_handle, 0, C.byref(pl)))
+        lib.check(lib.frame_set_ref(self.h, 0, C.byref(pl)))
+
+    def submit(self, stages, upload=True):
+        s = self.s
+        counts = (C.c_int32 * 19)(*[int(c) for c in s.itx_counts])
+        lib.check(lib.frame_submit(self.h, s.n_coefs, counts, len(s.mc_items), stages, 1 if upload else 0), "frame_submit")
+
+    def wait(self):
+        lib.check(lib.frame_wait(self.h), "frame_wait")
+
+    def readback(self):
+        s = self.s
+        out = [np.zeros_like(p) for p in s.ref]
+        data = (C.c_void_p * 3)(*[p.ctypes.data for p in out])
+        strides = (C.c_ssize_t * 2)(out[0].strides[0], out[1].strides[0])
+        lib.check(lib.frame_readback(self.h, data, strides), "frame_readback")
+        return out

@@ -1,0 +1,55 @@
+"""Shared helpers: run one synthetic frame through the oracle (reference drivers) and
+through the product (CUDA, C ABI) and compare visible planes."""
+import numpy as np
+
+import refharness
+
+
+def oracle_frame(ref, s, stages, n_tc=1, start_planes=None):
+    """Returns the visible planes after `stages`. start_planes: pre-filter picture when RECON is not in stages."""
+    from rav1d_b200 import lib
+    cur = refharness.RefFrame(ref, s, n_tc)
+    rf = refharness.RefFrame(ref, s, 1)
+    try:
+        rf.set_planes(s.ref)
+        cur.load_filter_meta()
+        if stages & lib.STAGE_RECON:
+            cur.recon(rf, n_threads=n_tc)
+        else:
+            cur.set_planes(start_planes)
+        if stages & ~lib.STAGE_RECON:
+            cur.filter(stages, n_threads=n_tc)
+        return visible(s, cur.get_planes())
+    finally:
+        cur.close()
+        rf.close()
+
+
+def product_frame(s, stages, start_planes=None):
+    from rav1d_b200 import lib
+    from rav1d_b200.synth.framegen import DeviceFrame
+    d = DeviceFrame(s)
+    try:
+        d.load_batch()
+        if stages & lib.STAGE_RECON:
+            d.set_ref_from_host(s.ref)
+        else:
+            d.upload(0, start_planes)
+        d.submit(stages)
+        d.wait()
+        return visible(s, d.readback())
+    finally:
+        d.close()
+
+
+def visible(s, planes):
+    return [planes[0][:s.h, :s.w], planes[1][:(s.h + 1) // 2, :(s.w + 1) // 2], planes[2][:(s.h + 1) // 2, :(s.w + 1) // 2]]
+
+
+def assert_planes_equal(a, b, what=""):
+    for p in range(3):
+        if not np.array_equal(a[p], b[p]):
+            bad = np.argwhere(a[p] != b[p])
+            y, x = bad[0]
+            raise AssertionError(f"{what}: plane {p} differs at {len(bad)} px, first (x={x}, y={y}): "
+                                 f"oracle {a[p][y, x]} vs product {b[p][y, x]}; rows {np.unique(bad[:, 0])[:12]}")

@@ -1,6 +1,7 @@
 """ctypes access to the ORACLE: oracle/_ref/libdav1d_ref.so, the reference's
-own portable C DSP compiled in place from /root/reference by oracle/Makefile
-(plus oracle/ref_harness.c glue).  Test infrastructure only."""
+own portable C DSP and frame drivers compiled in place from /root/reference by
+oracle/Makefile (plus oracle/ref_harness.c and oracle/ref_frame.c glue).
+Test infrastructure only."""
 import ctypes as C
 import os
 
@@ -24,15 +25,103 @@ def load():
             pytest.skip("oracle/_ref/libdav1d_ref.so not built (run `make -C oracle` where /root/reference exists)")
         _lib = C.CDLL(REF_SO)
         _lib.ref_init()
-        vp, i, ss = C.c_void_p, C.c_int, C.c_ssize_t
-        _lib.ref_itxfm_add.argtypes = [i, i, vp, ss, vp, i, i]
-        _lib.ref_itxfm_add.restype = None
-        _lib.ref_itx_has.argtypes = [i, i]
-        _lib.ref_itx_has.restype = i
-        _lib.ref_itxfm_add_many.argtypes = [i, vp, vp, ss, vp, i]
-        _lib.ref_itxfm_add_many.restype = None
+        vp, i, ss, sz = C.c_void_p, C.c_int, C.c_ssize_t, C.c_size_t
+
+        def sig(name, res, *args):
+            f = getattr(_lib, name)
+            f.restype = res
+            f.argtypes = list(args)
+
+        sig("ref_itxfm_add", None, i, i, vp, ss, vp, i, i)
+        sig("ref_itx_has", i, i, i)
+        sig("ref_itxfm_add_many", None, i, vp, vp, ss, vp, i)
+        sig("ref_mc", None, i, vp, ss, vp, ss, i, i, i, i, i)
+        sig("ref_mct", None, i, vp, vp, ss, i, i, i, i, i)
+        sig("ref_mc_scaled", None, i, vp, ss, vp, ss, i, i, i, i, i, i, i)
+        sig("ref_mct_scaled", None, i, vp, vp, ss, i, i, i, i, i, i, i)
+        sig("ref_avg", None, vp, ss, vp, vp, i, i, i)
+        sig("ref_w_avg", None, vp, ss, vp, vp, i, i, i, i)
+        sig("ref_mask", None, vp, ss, vp, vp, i, i, vp, i)
+        sig("ref_w_mask", None, i, vp, ss, vp, vp, i, i, vp, i, i)
+        sig("ref_blend", None, i, vp, ss, vp, i, i, vp, i)
+        sig("ref_warp8x8", None, vp, ss, vp, ss, vp, i, i, i)
+        sig("ref_warp8x8t", None, vp, ss, vp, ss, vp, i, i, i)
+        sig("ref_emu_edge", None, ss, ss, ss, ss, ss, ss, vp, ss, vp, ss, i)
+        sig("ref_resize", None, vp, ss, vp, ss, i, i, i, i, i, i)
+        sig("ref_lpf_sb", None, i, i, vp, ss, vp, vp, ss, vp, i, i)
+        sig("ref_cdef_dir", i, vp, ss, C.POINTER(C.c_uint), i)
+        sig("ref_cdef_fb", None, i, vp, ss, vp, vp, vp, i, i, i, i, i, i)
+        sig("ref_lr", None, i, vp, ss, vp, vp, i, i, vp, i, i)
+        sig("ref_calc_eih", None, vp, i)
+        sig("ref_sizeof", sz, i)
+        sig("ref_frame_new", vp, vp, i)
+        sig("ref_frame_free", None, vp)
+        sig("ref_frame_plane", vp, vp, i)
+        sig("ref_frame_stride", ss, vp, i)
+        sig("ref_frame_masks", vp, vp)
+        sig("ref_frame_levels", vp, vp)
+        sig("ref_frame_lut", vp, vp)
+        sig("ref_frame_lr_masks", vp, vp)
+        sig("ref_frame_sbh", i, vp)
+        sig("ref_frame_filter", None, vp, i, i)
+        sig("ref_frame_recon", None, vp, vp, i, vp, i, vp, i, vp, i)
     return _lib
 
 
 def ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+class RefFrame:
+    """One picture inside the reference's own Dav1dFrameContext (oracle/ref_frame.c)."""
+
+    def __init__(self, ref, s, n_tc=1):
+        self.ref, self.s = ref, s
+        self.h = ref.ref_frame_new(C.addressof(s.hdr), n_tc)
+        self.px = 2 if s.bpc > 8 else 1
+        self.strides = [ref.ref_frame_stride(self.h, 0), ref.ref_frame_stride(self.h, 1)]
+
+    def close(self):
+        if self.h:
+            self.ref.ref_frame_free(self.h)
+            self.h = None
+
+    def plane_view(self, p):
+        s = self.s
+        rows = s.ah if p == 0 else s.ah // 2
+        stride = self.strides[1 if p else 0]
+        buf = (C.c_ubyte * (stride * rows)).from_address(self.ref.ref_frame_plane(self.h, p))
+        a = np.frombuffer(buf, dtype=np.uint8).reshape(rows, stride)
+        cols = s.aw if p == 0 else s.aw // 2
+        return a[:, :cols * self.px].view(np.uint16 if self.px == 2 else np.uint8)
+
+    def set_planes(self, planes):
+        for p in range(3):
+            self.plane_view(p)[:] = planes[p]
+
+    def get_planes(self):
+        return [self.plane_view(p).copy() for p in range(3)]
+
+    def load_filter_meta(self):
+        from rav1d_b200 import lib
+        s, ref = self.s, self.ref
+        g = s.geom
+        n = g.sb128w * g.sb128h
+        assert ref.ref_sizeof(0) == lib.AV1_FILTER_DT.itemsize and ref.ref_sizeof(1) == lib.AV1_RESTORATION_DT.itemsize
+        assert ref.ref_sizeof(2) == C.sizeof(lib.FilterLUT)
+        lib.np_view(ref.ref_frame_masks(self.h), lib.AV1_FILTER_DT, n)[:] = s.masks
+        lib.np_view(ref.ref_frame_levels(self.h), np.uint8, s.levels.size)[:] = s.levels.reshape(-1)
+        C.memmove(ref.ref_frame_lut(self.h), C.byref(s.lut), C.sizeof(lib.FilterLUT))
+        lib.np_view(ref.ref_frame_lr_masks(self.h), lib.AV1_RESTORATION_DT, n)[:] = s.lr_masks
+
+    def recon(self, ref_frame, n_threads=1, coef_work=None):
+        s = self.s
+        cw = s.coef.copy() if coef_work is None else coef_work
+        refs = (C.c_void_p * 1)(ref_frame.h)
+        mc = np.ascontiguousarray(s.mc_items)
+        itx = np.ascontiguousarray(s.itx_items)
+        self.ref.ref_frame_recon(self.h, refs, 1, ptr(mc), len(mc), ptr(itx), len(itx), ptr(cw), n_threads)
+        return cw
+
+    def filter(self, stages, n_threads=1):
+        self.ref.ref_frame_filter(self.h, stages, n_threads)
