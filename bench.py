@@ -1,0 +1,378 @@
+#!/usr/bin/env python3
+"""Throughput of the recon + post-filter path on synthetic frames (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload 4k10|1080p8|8k10]
+
+A *step* is one pass of the hot path over one batch of FRAMES_PER_STEP synthetic frames:
+recon (8-tap MC + itx add) -> deblock -> CDEF -> Wiener/SGR loop restoration (4k10: BASELINE
+configs[2], the configuration the metric is quoted on).
+
+* `value`  : Mpixel/s (luma pixels of output frames / s) with the batch resident in HBM, timed
+             with CUDA events on the launching stream; frames cycle over N_CTX frame contexts
+             whose working sets (> 190 MB each at 4K) exceed the 126 MB L2.
+* `e2e`    : same metric through the C ABI with HOST buffers: per frame H2D of coefficients,
+             work items and filter metadata from pinned staging, the stage launches, D2H of the
+             output picture into pinned host planes; N_CTX frames in flight on their own streams.
+* `roofline`: the dominant kernel's algorithmic bytes / its CUDA-event duration (stage marks of
+             rb200_frame_stage_times, recorded inside the timed region) against MEASURED_PEAKS.json.
+* `cpu_baseline`: the reference's own C DSP + frame drivers (oracle/_ref, all host threads) on a
+             bounded sample of the same workload.
+* `--impl reference`: only that CPU arm, in the same JSON shape.
+
+N > 1 (torchrun): independent streams, one per GPU, no data-path collective;
+value = pixels of all ranks / max-over-ranks device time; "scaling": "weak".
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (w, h, bpc, stages, description)
+    "4k10": (3840, 2160, 10, 15, "4K 10-bit 4:2:0 synthetic inter frame: recon (8-tap/bilinear MC + itx) + deblock + CDEF + Wiener/SGR LR"),
+    "1080p8": (1920, 1080, 8, 3, "1080p 8-bit 4:2:0 synthetic inter frame: recon (8-tap/bilinear MC + itx) + deblock"),
+    "8k10": (7680, 4320, 10, 14, "8K 10-bit 4:2:0 post-filters only: deblock + CDEF + Wiener/SGR LR"),
+}
+FRAMES_PER_STEP = 16
+N_CTX = 4
+METRIC = "recon+post-filter throughput (itx+MC+LF/CDEF/LR), luma pixels of output frames"
+STAGE_NAMES = ["h2d", "mc", "itx", "deblock", "cdef", "lr"]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(w, h, bpc):
+    """SURVEY 8(d) / BASELINE.md 4: S = one 4:2:0 plane set, C = dense coefficients."""
+    px, cs = (2, 4) if bpc > 8 else (1, 2)
+    S = w * h * 3 // 2 * px
+    Cb = w * h * 3 // 2 * cs
+    return {"mc": 2 * S, "itx": Cb + 2 * S, "recon": 2 * S + Cb, "deblock": 2 * S, "cdef": 2 * S, "lr": 2 * S,
+            "S": S, "C": Cb}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        gid = vis.split(",")[index] if vis else str(index)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", gid, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 6]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ CPU arm
+def cpu_frames(s, stages, n_frames, n_threads):
+    """Time `n_frames` passes of the reference's C path (oracle/_ref) over the synthetic frame.
+    Returns seconds (restoring the consumed coefficient buffer is not timed)."""
+    import refharness
+    ref = refharness.load()
+    cur = refharness.RefFrame(ref, s, max(n_threads, 2))
+    rf = refharness.RefFrame(ref, s, 1)
+    start = None
+    if not stages & 1:
+        from rav1d_b200.synth import framegen
+        start = framegen.recon_input_planes(s)
+    try:
+        rf.set_planes(s.ref)
+        cur.load_filter_meta()
+        cw = s.coef.copy()
+        total = 0.0
+        for _ in range(n_frames):
+            if stages & 1:
+                np.copyto(cw, s.coef)
+            else:
+                cur.set_planes(start)
+            t0 = time.perf_counter()
+            if stages & 1:
+                cur.recon(rf, n_threads=n_threads, coef_work=cw)
+            if stages & ~1:
+                cur.filter(stages, n_threads=n_threads)
+            total += time.perf_counter() - t0
+        return total
+    finally:
+        cur.close()
+        rf.close()
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference(args, s, wl):
+    w, h, bpc, stages, desc = wl
+    cores = os.cpu_count() or 1
+    t1 = cpu_frames(s, stages, 1, cores)                       # warm-up + estimate
+    per_step = max(1, min(FRAMES_PER_STEP, int(1.5 / max(t1, 1e-3))))   # ~1.5 s of CPU work per step
+    for _ in range(max(args.warmup - 1, 0)):
+        cpu_frames(s, stages, 1, cores)
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_frames(s, stages, per_step, cores)
+    frames = per_step * args.steps
+    mpx = frames * w * h / t / 1e6
+    sample = f"{frames} frames of the workload ({per_step} per step), {cores} threads, sbrow-parallel stages"
+    line = {"impl": "reference", "metric": METRIC, "value": mpx, "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": desc, "frames_per_step": per_step, "width": w, "height": h, "bpc": bpc,
+                       "cpu": cpu_model(), "note": "reference's portable C DSP (no asm: nasm unavailable), -O3 x86-64-v3"},
+            "cpu_baseline": {"value": mpx, "unit": "Mpixel/s", "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": mpx, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def run_gpu(args, s, wl):
+    import torch
+    import torch.distributed as dist
+    from rav1d_b200 import lib
+    from rav1d_b200.synth import framegen
+
+    w, h, bpc, stages, desc = wl
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; rav1d_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib.check(lib.init(local), "rb200_init")
+
+    ctxs = []
+    start_planes = None if stages & 1 else framegen.recon_input_planes(s)
+    for i in range(N_CTX):
+        d = framegen.DeviceFrame(s)
+        d.load_batch()
+        if stages & 1:
+            d.set_ref_from_host(s.ref)
+        else:
+            d.upload(0, start_planes)
+        lib.check(lib.frame_enable_timing(d.h, 1))
+        ctxs.append(d)
+    # pinned host output planes for the e2e leg
+    px = 2 if bpc > 8 else 1
+    out_bytes = [w * h * px, ((w + 1) // 2) * ((h + 1) // 2) * px, ((w + 1) // 2) * ((h + 1) // 2) * px]
+    host_out = []
+    for d in ctxs:
+        ptrs = []
+        for nb in out_bytes:
+            p = C.c_void_p()
+            lib.check(lib.malloc_host(C.byref(p), nb))
+            ptrs.append(p.value)
+        host_out.append(((C.c_void_p * 3)(*ptrs), (C.c_ssize_t * 2)(w * px, ((w + 1) // 2) * px)))
+
+    counts = (C.c_int32 * 19)(*[int(c) for c in s.itx_counts])
+    n_mc = len(s.mc_items)
+
+    def submit(d, upload):
+        lib.check(lib.frame_submit(d.h, s.n_coefs, counts, n_mc, stages, 1 if upload else 0), "frame_submit")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- resident leg: one stream, CUDA events around K steps
+    main = torch.cuda.Stream()
+    for d in ctxs:
+        lib.check(lib.frame_set_stream(d.h, C.c_void_p(main.cuda_stream)))
+        submit(d, True)                      # batch becomes resident (not timed)
+    for _ in range(args.warmup):
+        for i in range(FRAMES_PER_STEP):
+            submit(ctxs[i % N_CTX], False)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    stage_ms = np.zeros(6)
+    stage_n = 0
+    buf = (C.c_float * 6)()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    e0.record(main)
+    for _ in range(args.steps):
+        for i in range(FRAMES_PER_STEP):
+            submit(ctxs[i % N_CTX], False)
+            launches += lib.frame_last_launches(ctxs[i % N_CTX].h)
+        main.synchronize()                   # read the stage marks of this step's last N_CTX frames
+        for d in ctxs:
+            lib.check(lib.frame_stage_times(d.h, buf))
+            stage_ms += np.array(buf[:])
+            stage_n += 1
+    e1.record(main)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    frames_total = world * args.steps * FRAMES_PER_STEP
+    value = frames_total * w * h / (ms_max * 1e-3) / 1e6
+    stage_ms /= max(stage_n, 1)
+
+    # ---------------- e2e leg: host buffers, N_CTX frames in flight on their own streams
+    for d in ctxs:
+        lib.check(lib.frame_set_stream(d.h, None))
+    streams = [torch.cuda.ExternalStream(lib.frame_stream(d.h)) for d in ctxs]
+
+    def e2e_frame(i):
+        d = ctxs[i % N_CTX]
+        d.wait()                             # the context's previous frame (incl. its readback) is done;
+        submit(d, True)                      # the front end would refill the pinned staging here
+        lib.check(lib.frame_readback_async(d.h, host_out[i % N_CTX][0], host_out[i % N_CTX][1]))
+
+    for i in range(args.warmup * FRAMES_PER_STEP):
+        e2e_frame(i)
+    barrier()
+    s0 = torch.cuda.Event(enable_timing=True)
+    ends = [torch.cuda.Event(enable_timing=True) for _ in ctxs]
+    s0.record(streams[0])
+    for st in streams[1:]:
+        st.wait_event(s0)
+    for i in range(args.steps * FRAMES_PER_STEP):
+        e2e_frame(i)
+    for st, ev in zip(streams, ends):
+        ev.record(st)
+    barrier()
+    e2e_ms = max(s0.elapsed_time(ev) for ev in ends)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = frames_total * w * h / (float(t.item()) * 1e-3) / 1e6
+    g = ctxs[0].g
+    n_sb = g.sb128w * g.sb128h
+    h2d = 0
+    if stages & 1:
+        h2d += s.n_coefs * (4 if bpc > 8 else 2) + 16 * (len(s.itx_items) + n_mc)
+    h2d += n_sb * 1348 + (g.b4_stride * 32 * g.sb128h + 32) * 4 + 144 + n_sb * 108
+    d2h = sum(out_bytes)
+
+    line = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        ab = algorithmic_bytes(w, h, bpc)
+        per_stage = {}
+        for name, t_ms in zip(STAGE_NAMES, stage_ms):
+            if name == "h2d" or t_ms <= 0:
+                continue
+            per_stage[name] = {"ms": round(float(t_ms), 4), "algorithmic_bytes": ab[name],
+                               "gbs": round(ab[name] / (t_ms * 1e-3) / 1e9, 1)}
+        dom = max(per_stage, key=lambda k: per_stage[k]["ms"]) if per_stage else None
+        roofline = None
+        if dom:
+            ach = per_stage[dom]["gbs"]
+            roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                        "frac": round(ach / peak, 4), "traffic": TRAFFIC.get((args.workload, dom)),
+                        "peak_source": peak_src, "share_of_step": round(per_stage[dom]["ms"] / sum(v["ms"] for v in per_stage.values()), 3)}
+        frame_bytes = sum(ab[k] for k in per_stage)
+        line = {"metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int32", "data": "synthetic",
+                "config": {"workload": desc, "frames_per_step": FRAMES_PER_STEP, "width": w, "height": h, "bpc": bpc,
+                           "l2": f"inputs larger than L2: {N_CTX} frame contexts cycled, > {ab['S'] * 4 // 1000000} MB working set each",
+                           "parallelism": f"{world} independent streams (one per GPU)" if world > 1 else "1 stream"},
+                "fps": value * 1e6 / (w * h),
+                "frame_roofline_frac": round(frame_bytes * (value * 1e6 / (w * h)) / world / (peak * 1e9), 4),
+                "stages": per_stage, "roofline": roofline, "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d * FRAMES_PER_STEP,
+                        "d2h_bytes_per_step": d2h * FRAMES_PER_STEP},
+                "gpu_launches": launches}
+    for d in ctxs:
+        d.close()
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            t1 = cpu_frames(s, stages, 1, cores)
+            n = max(2, min(64, int(12.0 / max(t1, 1e-3))))
+            tt = cpu_frames(s, stages, n, cores)
+            line["cpu_baseline"] = {"value": n * w * h / tt / 1e6, "unit": "Mpixel/s", "cores": cores, "kind": "reference",
+                                    "sample": f"{n} frames of the workload, {cores} threads, reference C DSP (no asm), {cpu_model()}"}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
+# capture of the dominant kernel (profiles/), keyed by (workload, stage); None until captured.
+TRAFFIC = {}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="4k10", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+    rank = int(os.environ.get("RANK", 0))
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference" and rank != 0:
+        return
+    from rav1d_b200.synth import framegen
+    s = framegen.generate(wl[0], wl[1], wl[2], seed=1 + (rank if args.impl == "b200" else 0))
+    if args.impl == "reference":
+        run_reference(args, s, wl)
+    else:
+        run_gpu(args, s, wl)
+
+
+if __name__ == "__main__":
+    main()

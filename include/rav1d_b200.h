@@ -359,7 +359,17 @@ int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t itx_counts[R
 int rb200_frame_wait(Rb200Frame *f);
 /* D2H of the output picture into host planes (stride in bytes, may be negative). */
 int rb200_frame_readback(Rb200Frame *f, void *const data[3], const ptrdiff_t stride[2]);
+/* Same, queued on the frame's stream without waiting (use pinned host planes, then rb200_frame_wait). */
+int rb200_frame_readback_async(Rb200Frame *f, void *const data[3], const ptrdiff_t stride[2]);
 void *rb200_frame_stream(Rb200Frame *f);
+/* Run the frame's copies and launches on `stream` instead of the frame's own (NULL restores it). */
+int rb200_frame_set_stream(Rb200Frame *f, void *stream);
+/* Per-stage device times of the last submit (CUDA events on the frame's stream), the analogue
+ * of the reference CLI's --frametimes (tools/dav1d.rs:127-150).  ms[] = H2D, MC, itx, deblock,
+ * CDEF, LR; valid after rb200_frame_wait(). */
+#define RB200_N_FRAME_MARKS 7
+int rb200_frame_enable_timing(Rb200Frame *f, int on);
+int rb200_frame_stage_times(Rb200Frame *f, float ms[RB200_N_FRAME_MARKS - 1]);
 /* Number of kernels launched by the last submit (bench bookkeeping). */
 int rb200_frame_last_launches(const Rb200Frame *f);
 

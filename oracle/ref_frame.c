@@ -113,8 +113,6 @@ RefFrame *ref_frame_new(const Rb200FrameHeader *h, int n_tc) {
     r->seq.layout = h->layout; r->seq.hbd = h->bpc == 8 ? 0 : h->bpc == 10 ? 1 : 2;
     r->hdr.width[0] = r->hdr.width[1] = h->width; r->hdr.height = h->height;
     r->hdr.tiling.cols = r->hdr.tiling.rows = 1;
-    r->hdr.tiling.col_start_sb[0] = 0; r->hdr.tiling.col_start_sb[1] = 1 << 20;
-    r->hdr.tiling.row_start_sb[0] = 0; r->hdr.tiling.row_start_sb[1] = 1 << 20;
     r->hdr.loopfilter.level_y[0] = h->lf_level_y[0]; r->hdr.loopfilter.level_y[1] = h->lf_level_y[1];
     r->hdr.loopfilter.level_u = h->lf_level_u; r->hdr.loopfilter.level_v = h->lf_level_v;
     r->hdr.cdef.damping = h->cdef_damping;
@@ -129,6 +127,10 @@ RefFrame *ref_frame_new(const Rb200FrameHeader *h, int n_tc) {
     f->sb_shift = 4 + h->sb128; f->sb_step = 16 << h->sb128;
     f->sbh = (f->bh + f->sb_step - 1) >> f->sb_shift;
     f->b4_stride = (f->bw + 31) & ~31;
+    /* one tile: col/row_start_sb[n_tiles] = picture size in superblocks (src/obu.c parse_tile_hdr);
+     * the loop-filter driver walks col_start_sb[] until it passes the right edge (src/lf_apply_tmpl.c:335) */
+    r->hdr.tiling.col_start_sb[0] = 0; r->hdr.tiling.col_start_sb[1] = (f->bw + f->sb_step - 1) >> f->sb_shift;
+    r->hdr.tiling.row_start_sb[0] = 0; r->hdr.tiling.row_start_sb[1] = f->sbh;
 
     /* picture: dav1d_default_picture_alloc, src/picture.c:47-90 */
     const int px = r->hbd ? 2 : 1;

@@ -43,6 +43,11 @@ struct Rb200Frame {
     Rb200Av1Restoration *h_lr, *d_lr;
     size_t n_masks, n_lvl;
     int launches;
+    // optional per-stage timing (the analogue of the reference CLI's --frametimes, tools/dav1d.rs:127-150)
+    cudaStream_t own_stream;
+    bool timing;
+    cudaEvent_t ev[RB200_N_FRAME_MARKS];
+    bool ev_valid[RB200_N_FRAME_MARKS];
 };
 
 using namespace rb200;
@@ -114,6 +119,7 @@ extern "C" int rb200_frame_create(Rb200Frame **out, const Rb200FrameHeader *hdr,
     int r = 0;
     cudaError_t e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { r = cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); delete f; return r; }
+    f->own_stream = f->stream;
     for (int i = 0; i < 3 && !r; i++) r = alloc_planes(f, i);
     if (!r) {
         RB_CUDA(cudaMallocHost(&f->h_coef, (max_coefs ? max_coefs : 1) * f->cs));
@@ -136,6 +142,7 @@ extern "C" int rb200_frame_create(Rb200Frame **out, const Rb200FrameHeader *hdr,
 extern "C" int rb200_frame_destroy(Rb200Frame *f) {
     if (!f) return 0;
     if (f->stream) cudaStreamSynchronize(f->stream);
+    for (int i = 0; i < RB200_N_FRAME_MARKS; i++) if (f->ev[i]) cudaEventDestroy(f->ev[i]);
     for (int i = 0; i < 3; i++) if (f->plane_mem[i]) cudaFree(f->plane_mem[i]);
     if (f->h_coef) cudaFreeHost(f->h_coef);
     if (f->d_coef) cudaFree(f->d_coef);
@@ -151,7 +158,7 @@ extern "C" int rb200_frame_destroy(Rb200Frame *f) {
     if (f->d_lut) cudaFree(f->d_lut);
     if (f->h_lr) cudaFreeHost(f->h_lr);
     if (f->d_lr) cudaFree(f->d_lr);
-    if (f->stream) cudaStreamDestroy(f->stream);
+    if (f->own_stream) cudaStreamDestroy(f->own_stream);
     delete f;
     return 0;
 }
@@ -172,6 +179,34 @@ extern "C" Rb200Av1FilterLUT *rb200_frame_lf_lut(Rb200Frame *f) { return f ? f->
 extern "C" Rb200Av1Restoration *rb200_frame_lr_masks(Rb200Frame *f) { return f ? f->h_lr : nullptr; }
 extern "C" void *rb200_frame_stream(Rb200Frame *f) { return f ? (void *)f->stream : nullptr; }
 extern "C" int rb200_frame_last_launches(const Rb200Frame *f) { return f ? f->launches : 0; }
+
+extern "C" int rb200_frame_set_stream(Rb200Frame *f, void *stream) {
+    if (!f) return set_error(-22, "frame_set_stream: null frame");
+    RB_CUDA(cudaStreamSynchronize(f->stream));
+    f->stream = stream ? (cudaStream_t)stream : f->own_stream;
+    return 0;
+}
+
+extern "C" int rb200_frame_enable_timing(Rb200Frame *f, int on) {
+    if (!f) return set_error(-22, "frame_enable_timing: null frame");
+    if (on)
+        for (int i = 0; i < RB200_N_FRAME_MARKS; i++)
+            if (!f->ev[i]) RB_CUDA(cudaEventCreate(&f->ev[i]));
+    f->timing = on != 0;
+    return 0;
+}
+
+// ms between consecutive marks of the last submit: [0] H2D, [1] MC, [2] itx, [3] deblock, [4] CDEF, [5] LR.
+// A stage that did not run reports 0.  Valid after rb200_frame_wait().
+extern "C" int rb200_frame_stage_times(Rb200Frame *f, float ms[RB200_N_FRAME_MARKS - 1]) {
+    if (!f || !ms) return set_error(-22, "frame_stage_times: bad argument");
+    if (!f->timing) return set_error(-22, "frame_stage_times: timing not enabled");
+    for (int i = 0; i + 1 < RB200_N_FRAME_MARKS; i++) {
+        ms[i] = 0.f;
+        if (f->ev_valid[i] && f->ev_valid[i + 1]) RB_CUDA(cudaEventElapsedTime(&ms[i], f->ev[i], f->ev[i + 1]));
+    }
+    return 0;
+}
 
 extern "C" int rb200_frame_set_ref(Rb200Frame *f, int slot, const Rb200Planes *planes) {
     if (!f || slot < 0 || slot > 7 || !planes) return set_error(-22, "frame_set_ref: bad argument");
@@ -220,7 +255,7 @@ extern "C" int rb200_frame_upload_planes(Rb200Frame *f, int which, const void *c
     return 0;
 }
 
-extern "C" int rb200_frame_readback(Rb200Frame *f, void *const data[3], const ptrdiff_t stride[2]) {
+extern "C" int rb200_frame_readback_async(Rb200Frame *f, void *const data[3], const ptrdiff_t stride[2]) {
     if (!f || !data || !stride) return set_error(-22, "frame_readback: bad argument");
     for (int p = 0; p < f->g.n_planes; p++) {
         const int rows = plane_rows(f, p);
@@ -235,6 +270,12 @@ extern "C" int rb200_frame_readback(Rb200Frame *f, void *const data[3], const pt
                                         plane_row_bytes(f, p), cudaMemcpyDeviceToHost, f->stream));
         }
     }
+    return 0;
+}
+
+extern "C" int rb200_frame_readback(Rb200Frame *f, void *const data[3], const ptrdiff_t stride[2]) {
+    const int r = rb200_frame_readback_async(f, data, stride);
+    if (r) return r;
     RB_CUDA(cudaStreamSynchronize(f->stream));
     return 0;
 }
@@ -264,6 +305,9 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         if (n_mc && f->n_refs < 1) return set_error(-22, "frame_submit: no reference picture set");
     }
     f->launches = 0;
+    for (int i = 0; i < RB200_N_FRAME_MARKS; i++) f->ev_valid[i] = false;
+#define MARK(i) do { if (f->timing) { RB_CUDA(cudaEventRecord(f->ev[i], st)); f->ev_valid[i] = true; } } while (0)
+    MARK(0);
     const bool do_lf = (stages & RB200_STAGE_DEBLOCK) && (h.lf_level_y[0] || h.lf_level_y[1]);
     const bool do_cdef = (stages & RB200_STAGE_CDEF) != 0;
     int restore_planes = 0;
@@ -287,6 +331,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
             RB_CUDA(cudaMemcpyAsync(f->d_lr, f->h_lr, f->n_masks * sizeof(Rb200Av1Restoration), cudaMemcpyHostToDevice, st));
     }
 
+    MARK(1);
     int r;
     // ---- reconstruction: prediction, then residual add
     if (stages & RB200_STAGE_RECON) {
@@ -295,6 +340,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
                                      n_mc, f->bdmax, st))) return r;
             f->launches++;
         }
+        MARK(2);
         int off = 0;
         for (int t = 0; t < RB200_N_RECT_TX_SIZES; t++) {
             if (itx_counts[t]) {
@@ -305,12 +351,14 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         }
     }
     f->out = f->planes[0];
+    if (stages & RB200_STAGE_RECON) MARK(3); else { MARK(2); MARK(3); }
     // ---- deblock (in place): all column edges, then all row edges (src/recon.rs:4047-4170)
     if (do_lf) {
         if ((r = deblock_frame_launch(f->planes[0], g.n_planes, g.w4, g.h4, g.sb128w, g.b4_stride, g.ss_hor, g.ss_ver,
                                       h.lf_level_u || h.lf_level_v, f->d_masks, f->d_lvl + 32, f->d_lut, f->bdmax, st,
                                       &f->launches))) return r;
     }
+    MARK(4);
     // ---- CDEF: cur -> p2 (src/recon.rs:4172-4213)
     if (do_cdef) {
         CdefFrameParams P;
@@ -322,6 +370,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         f->launches++;
         f->out = f->planes[1];
     }
+    MARK(5);
     // ---- loop restoration: (p2 | cur) + cur -> p3 for the restored planes (src/recon.rs:4283-4317)
     if (restore_planes) {
         const Rb200Planes cdefp = f->out;
@@ -341,5 +390,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
             f->out.stride[p] = f->planes[2].stride[p];
         }
     }
+    MARK(6);
+#undef MARK
     return 0;
 }

@@ -175,7 +175,11 @@ frame_stage_planes = _sig("rb200_frame_stage_planes", _i, _vp, _i, C.POINTER(Pla
 frame_submit = _sig("rb200_frame_submit", _i, _vp, _sz, C.POINTER(C.c_int32), _i, _i, _i)
 frame_wait = _sig("rb200_frame_wait", _i, _vp)
 frame_readback = _sig("rb200_frame_readback", _i, _vp, C.POINTER(_vp), C.POINTER(_ss))
+frame_readback_async = _sig("rb200_frame_readback_async", _i, _vp, C.POINTER(_vp), C.POINTER(_ss))
 frame_stream = _sig("rb200_frame_stream", _vp, _vp)
+frame_set_stream = _sig("rb200_frame_set_stream", _i, _vp, _vp)
+frame_enable_timing = _sig("rb200_frame_enable_timing", _i, _vp, _i)
+frame_stage_times = _sig("rb200_frame_stage_times", _i, _vp, C.POINTER(C.c_float))
 frame_last_launches = _sig("rb200_frame_last_launches", _i, _vp)
 
 
