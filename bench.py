@@ -315,7 +315,8 @@ def run_gpu(args, s, wl):
             roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                         "frac": round(ach / peak, 4), "traffic": TRAFFIC.get((args.workload, dom)),
                         "peak_source": peak_src, "share_of_step": round(per_stage[dom]["ms"] / sum(v["ms"] for v in per_stage.values()), 3)}
-        frame_bytes = sum(ab[k] for k in per_stage)
+        # frame-level algorithmic bytes as BASELINE.md 4 counts them (MC + itx = one fused recon stage: 2S + C)
+        frame_bytes = (ab["recon"] if stages & 1 else 0) + sum(ab[k] for k in ("deblock", "cdef", "lr") if k in per_stage)
         line = {"metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32", "data": "synthetic",
