@@ -297,6 +297,63 @@ int rb200_lr(int kind /* 0 wiener7, 1 wiener5, 2 sgr5x5, 3 sgr3x3, 4 sgr mix */,
              const void *left, const void *lpf, int w, int h, const Rb200LooprestorationParams *params,
              uint32_t edges, int bitdepth_max);
 
+/* ------------------------------------------------------------ film grain */
+/* Dav1dFilmGrainData / Rav1dFilmGrainData, include/dav1d/headers.rs:1610-1661 (same layout) */
+typedef struct Rb200FilmGrainData {
+    unsigned seed;
+    int num_y_points;
+    uint8_t y_points[14][2]; /* value, scaling */
+    int chroma_scaling_from_luma;
+    int num_uv_points[2];
+    uint8_t uv_points[2][10][2];
+    int scaling_shift;
+    int ar_coeff_lag;
+    int8_t ar_coeffs_y[24];
+    int8_t ar_coeffs_uv[2][25 + 3];
+    uint64_t ar_coeff_shift;
+    int grain_scale_shift;
+    int uv_mult[2];
+    int uv_luma_mult[2];
+    int uv_offset[2];
+    int overlap_flag;
+    int clip_to_restricted_range;
+} Rb200FilmGrainData;
+#define RB200_GRAIN_WIDTH 82
+#define RB200_GRAIN_HEIGHT 73
+/* fn-pointer types of Rav1dFilmGrainDSPContext, src/filmgrain.rs:41-143.  `buf` / `grain_lut` are
+ * entry[GRAIN_HEIGHT + 1][GRAIN_WIDTH] with entry = int8_t (8 bpc) or int16_t; scaling is
+ * uint8_t[256] (8 bpc) or uint8_t[4096]. */
+typedef void (*rb200_generate_grain_y_fn)(void *buf, const Rb200FilmGrainData *data, int bitdepth_max);
+typedef void (*rb200_generate_grain_uv_fn)(void *buf, const void *buf_y, const Rb200FilmGrainData *data,
+                                           intptr_t uv, int bitdepth_max);
+typedef void (*rb200_fgy_32x32xn_fn)(void *dst_row, const void *src_row, ptrdiff_t stride,
+                                     const Rb200FilmGrainData *data, size_t pw, const uint8_t *scaling,
+                                     const void *grain_lut, int bh, int row_num, int bitdepth_max);
+typedef void (*rb200_fguv_32x32xn_fn)(void *dst_row, const void *src_row, ptrdiff_t stride,
+                                      const Rb200FilmGrainData *data, size_t pw, const uint8_t *scaling,
+                                      const void *grain_lut, int bh, int row_num, const void *luma_row,
+                                      ptrdiff_t luma_stride, int uv_pl, int is_id, int bitdepth_max);
+/* Rav1dFilmGrainDSPContext, src/filmgrain.rs:195-201: [layout - 1] = 420, 422, 444 */
+typedef struct Rb200FilmGrainDSPContext {
+    rb200_generate_grain_y_fn generate_grain_y;
+    rb200_generate_grain_uv_fn generate_grain_uv[3];
+    rb200_fgy_32x32xn_fn fgy_32x32xn;
+    rb200_fguv_32x32xn_fn fguv_32x32xn[3];
+} Rb200FilmGrainDSPContext;
+void rb200_film_grain_dsp_init(Rb200FilmGrainDSPContext *c, int bpc);
+int rb200_generate_grain_y(void *buf, const Rb200FilmGrainData *data, int bitdepth_max);
+int rb200_generate_grain_uv(int layout /* RB200_LAYOUT_I420.. */, void *buf, const void *buf_y,
+                            const Rb200FilmGrainData *data, intptr_t uv, int bitdepth_max);
+int rb200_fgy_32x32xn(void *dst_row, const void *src_row, ptrdiff_t stride, const Rb200FilmGrainData *data,
+                      size_t pw, const uint8_t *scaling, const void *grain_lut, int bh, int row_num,
+                      int bitdepth_max);
+int rb200_fguv_32x32xn(int layout, void *dst_row, const void *src_row, ptrdiff_t stride,
+                       const Rb200FilmGrainData *data, size_t pw, const uint8_t *scaling, const void *grain_lut,
+                       int bh, int row_num, const void *luma_row, ptrdiff_t luma_stride, int uv_pl, int is_id,
+                       int bitdepth_max);
+/* generate_scaling, src/fg_apply.rs:14-72: piecewise-linear scaling LUT (256 or 4096 bytes). */
+int rb200_generate_scaling(int bitdepth, const uint8_t points[][2], int num, uint8_t *scaling);
+
 /* ------------------------------------------------------------ frame level */
 /* The coarser drop-in: Rav1dFrameContext_bd_fn.filter_sbrow_{deblock_cols,deblock_rows,
  * cdef,lr} (src/internal.rs:368-395, bodies src/recon.rs:4047-4338 driving
@@ -305,7 +362,8 @@ int rb200_lr(int kind /* 0 wiener7, 1 wiener5, 2 sgr5x5, 3 sgr3x3, 4 sgr mix */,
  * device-resident planes.  The host hands over the arrays the reference's
  * pass 1 already produces, in the reference's own layouts. */
 enum { RB200_LAYOUT_I400, RB200_LAYOUT_I420, RB200_LAYOUT_I422, RB200_LAYOUT_I444 };
-enum { RB200_STAGE_RECON = 1, RB200_STAGE_DEBLOCK = 2, RB200_STAGE_CDEF = 4, RB200_STAGE_LR = 8 };
+enum { RB200_STAGE_RECON = 1, RB200_STAGE_DEBLOCK = 2, RB200_STAGE_CDEF = 4, RB200_STAGE_LR = 8,
+       RB200_STAGE_FILM_GRAIN = 16 /* needs rb200_frame_set_film_grain */ };
 typedef struct Rb200FrameHeader {
     int32_t width, height;       /* picture size in pixels (plane 0) */
     int32_t bpc;                 /* 8, 10 or 12 */
@@ -349,6 +407,12 @@ Rb200Av1Restoration *rb200_frame_lr_masks(Rb200Frame *f);     /* [sb128h * sb128
 int rb200_frame_set_ref(Rb200Frame *f, int slot, const Rb200Planes *planes);
 /* Upload a host picture into one of the frame's own plane sets (0 = current/recon). */
 int rb200_frame_upload_planes(Rb200Frame *f, int which, const void *const data[3], const ptrdiff_t stride[2]);
+/* Film grain on output (rav1d_apply_grain, src/lib.rs:604 -> src/fg_apply.rs:272): parameters of the
+ * RB200_STAGE_FILM_GRAIN stage.  The grained picture is a separate plane set (it is never used as a
+ * reference); rb200_frame_readback returns it when the stage ran, rb200_frame_output_planes stays
+ * the reference picture. */
+int rb200_frame_set_film_grain(Rb200Frame *f, const Rb200FilmGrainData *data, int is_identity_matrix);
+int rb200_frame_display_planes(Rb200Frame *f, Rb200Planes *out);
 /* The device planes holding the result of the last submit (valid after rb200_frame_wait). */
 int rb200_frame_output_planes(Rb200Frame *f, Rb200Planes *out);
 int rb200_frame_stage_planes(Rb200Frame *f, int which, Rb200Planes *out);
@@ -366,8 +430,8 @@ void *rb200_frame_stream(Rb200Frame *f);
 int rb200_frame_set_stream(Rb200Frame *f, void *stream);
 /* Per-stage device times of the last submit (CUDA events on the frame's stream), the analogue
  * of the reference CLI's --frametimes (tools/dav1d.rs:127-150).  ms[] = H2D, MC, itx, deblock,
- * CDEF, LR; valid after rb200_frame_wait(). */
-#define RB200_N_FRAME_MARKS 7
+ * CDEF, LR, film grain; valid after rb200_frame_wait(). */
+#define RB200_N_FRAME_MARKS 8
 int rb200_frame_enable_timing(Rb200Frame *f, int on);
 int rb200_frame_stage_times(Rb200Frame *f, float ms[RB200_N_FRAME_MARKS - 1]);
 /* Number of kernels launched by the last submit (bench bookkeeping). */

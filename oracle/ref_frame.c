@@ -48,6 +48,8 @@ typedef struct RefFrame {
     size_t plane_bytes;
     uint8_t *lvl_mem;
     uint8_t start_of_tile_row[1024];
+    uint8_t *grain_mem;     /* output picture of dav1d_apply_grain */
+    Dav1dPicture grain_out;
 } RefFrame;
 
 void ref_init(void);
@@ -61,6 +63,10 @@ void dav1d_filter_sbrow_cdef_8bpc(Dav1dTaskContext *tc, int sby);
 void dav1d_filter_sbrow_cdef_16bpc(Dav1dTaskContext *tc, int sby);
 void dav1d_filter_sbrow_lr_8bpc(Dav1dFrameContext *f, int sby);
 void dav1d_filter_sbrow_lr_16bpc(Dav1dFrameContext *f, int sby);
+void dav1d_film_grain_dsp_init_8bpc(Dav1dFilmGrainDSPContext *c);
+void dav1d_film_grain_dsp_init_16bpc(Dav1dFilmGrainDSPContext *c);
+void dav1d_apply_grain_8bpc(const Dav1dFilmGrainDSPContext *dsp, Dav1dPicture *out, const Dav1dPicture *in);
+void dav1d_apply_grain_16bpc(const Dav1dFilmGrainDSPContext *dsp, Dav1dPicture *out, const Dav1dPicture *in);
 void dav1d_itx_dsp_init_8bpc(Dav1dInvTxfmDSPContext *c, int bpc);
 void dav1d_itx_dsp_init_16bpc(Dav1dInvTxfmDSPContext *c, int bpc);
 void dav1d_mc_dsp_init_8bpc(Dav1dMCDSPContext *c);
@@ -80,7 +86,7 @@ void ref_frame_free(RefFrame *r) {
         free(r->f->lf.cdef_line_buf); free(r->f->lf.lr_line_buf); free(r->f->lf.mask); free(r->f->lf.lr_mask);
         free(r->f->lf.tx_lpf_right_edge[0]);
     }
-    free(r->lvl_mem); free(r->plane_mem); free(r->tc); free(r->f); free(r->c); free(r);
+    free(r->grain_mem); free(r->lvl_mem); free(r->plane_mem); free(r->tc); free(r->f); free(r->c); free(r);
 }
 
 /* layout: 0 I400, 1 I420, 2 I422, 3 I444 (same values as Dav1dPixelLayout) */
@@ -102,7 +108,9 @@ RefFrame *ref_frame_new(const Rb200FrameHeader *h, int n_tc) {
         dav1d_itx_dsp_init_16bpc(&dsp->itx, h->bpc); dav1d_mc_dsp_init_16bpc(&dsp->mc);
         dav1d_loop_filter_dsp_init_16bpc(&dsp->lf); dav1d_cdef_dsp_init_16bpc(&dsp->cdef);
         dav1d_loop_restoration_dsp_init_16bpc(&dsp->lr, h->bpc);
+        dav1d_film_grain_dsp_init_16bpc(&dsp->fg);
     } else {
+        dav1d_film_grain_dsp_init_8bpc(&dsp->fg);
         dav1d_itx_dsp_init_8bpc(&dsp->itx, 8); dav1d_mc_dsp_init_8bpc(&dsp->mc);
         dav1d_loop_filter_dsp_init_8bpc(&dsp->lf); dav1d_cdef_dsp_init_8bpc(&dsp->cdef);
         dav1d_loop_restoration_dsp_init_8bpc(&dsp->lr, 8);
@@ -324,3 +332,24 @@ void ref_frame_recon(RefFrame *r, RefFrame *const refs[], int n_refs, const Rb20
     parallel_for(r, n_threads, (n_mc + a.chunk - 1) / a.chunk, do_mc_chunk, &a);
     parallel_for(r, n_threads, (n_itx + a.chunk - 1) / a.chunk, do_itx_chunk, &a);
 }
+
+/* ------------------------------------------------------------- film grain */
+/* dav1d_apply_grain (src/fg_apply_tmpl.c:229-245) from the frame's current picture into a
+ * separate output picture, as rav1d_apply_grain does on output (src/lib.c output_image). */
+void ref_frame_apply_grain(RefFrame *r, const Dav1dFilmGrainData *data, int is_identity) {
+    Dav1dFrameContext *f = r->f;
+    if (!r->grain_mem) r->grain_mem = zalloc(r->plane_bytes);
+    r->hdr.film_grain.data = *data;
+    r->seq.mtrx = is_identity ? DAV1D_MC_IDENTITY : DAV1D_MC_BT709;
+    Dav1dPicture in;
+    memset(&in, 0, sizeof(in));
+    in.data[0] = f->cur.data[0]; in.data[1] = f->cur.data[1]; in.data[2] = f->cur.data[2];
+    in.stride[0] = f->cur.stride[0]; in.stride[1] = f->cur.stride[1];
+    in.p = f->cur.p; in.seq_hdr = &r->seq; in.frame_hdr = &r->hdr;
+    r->grain_out = in;
+    for (int i = 0; i < 3; i++)
+        r->grain_out.data[i] = f->cur.data[i] ? r->grain_mem + ((uint8_t *)f->cur.data[i] - r->plane_mem) : NULL;
+    if (r->hbd) dav1d_apply_grain_16bpc(&f->dsp->fg, &r->grain_out, &in);
+    else dav1d_apply_grain_8bpc(&f->dsp->fg, &r->grain_out, &in);
+}
+void *ref_frame_grain_plane(RefFrame *r, int pl) { return r->grain_out.data[pl]; }

@@ -218,7 +218,7 @@ void ref_fg_gen_y(void *buf, const Dav1dFilmGrainData *d, int bdmax) {
     if (!hbd(bdmax)) ((void (*)(void *, const Dav1dFilmGrainData *))T.fg[0].generate_grain_y)(buf, d);
     else ((void (*)(void *, const Dav1dFilmGrainData *, int))T.fg[1].generate_grain_y)(buf, d, bdmax);
 }
-void ref_fg_gen_uv(int ss /*0:444 1:422 2:420 (layout index)*/, void *buf, const void *buf_y, const Dav1dFilmGrainData *d, intptr_t uv, int bdmax) {
+void ref_fg_gen_uv(int ss /* layout - 1: 0 = 4:2:0, 1 = 4:2:2, 2 = 4:4:4 */, void *buf, const void *buf_y, const Dav1dFilmGrainData *d, intptr_t uv, int bdmax) {
     init_once();
     if (!hbd(bdmax)) ((void (*)(void *, const void *, const Dav1dFilmGrainData *, intptr_t))T.fg[0].generate_grain_uv[ss])(buf, buf_y, d, uv);
     else ((void (*)(void *, const void *, const Dav1dFilmGrainData *, intptr_t, int))T.fg[1].generate_grain_uv[ss])(buf, buf_y, d, uv, bdmax);

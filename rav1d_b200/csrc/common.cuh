@@ -80,6 +80,28 @@ int cdef_frame_launch(const Rb200Planes &src, const Rb200Planes &dst, const Cdef
 int lr_plane_launch(const uint8_t *cdef, const uint8_t *dbl, uint8_t *out, int64_t stride, const LrFrameParams &P,
                     const Rb200Av1Restoration *lrm, int bdmax, cudaStream_t st);
 
+// film grain (fg.cu), used by the frame stage
+struct FgApplyParams {
+    int pw, ph;            // plane region in pixels
+    int row0;              // block-row number of y == 0 (row_num of the per-call form)
+    int off_row0, ncols;   // first block row held by the offsets table, its row pitch
+    int sx, sy;            // subsampling of this plane (0 for luma)
+    int chroma;            // 0 luma, 1 chroma
+    int uv;                // chroma plane index 0/1
+    int is_id;
+    int luma_w;            // luma columns readable (lx + 1 is clamped to luma_w - 1)
+    int overlap, clip, scaling_shift, csfl;
+    int uv_mult, uv_luma_mult, uv_offset;
+};
+int fg_generate(void *lut, const void *lut_y, const Rb200FilmGrainData &d, int uv, int subx, int suby, int bdmax,
+                cudaStream_t st);
+int fg_apply(uint8_t *dst, const uint8_t *src, int64_t stride, const uint8_t *luma, int64_t luma_stride,
+             const FgApplyParams &P, const uint8_t *scaling, const void *lut, const uint8_t *off, int bdmax,
+             cudaStream_t st);
+int fg_offsets(uint8_t *off, unsigned seed, int row0, int nrows, int ncols, cudaStream_t st);
+int fg_scaling(uint8_t *scaling, const uint8_t *d_points, int num, int bitdepth, cudaStream_t st);
+FgApplyParams fg_params(const Rb200FilmGrainData &d, int chroma, int uv, int sx, int sy, int is_id);
+
 // ---- error plumbing --------------------------------------------------
 int set_error(int code, const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);

@@ -43,6 +43,12 @@ struct Rb200Frame {
     Rb200Av1Restoration *h_lr, *d_lr;
     size_t n_masks, n_lvl;
     int launches;
+    // film grain on output (src/fg_apply.rs): parameters, LUTs, display planes
+    bool fg_set; int fg_is_id;
+    Rb200FilmGrainData fg;
+    uint8_t *fg_mem;            // device: 3 grain LUTs, 3 scaling LUTs, points, offsets
+    uint8_t *h_fgpts;           // pinned: 3 x 32 bytes of scaling points
+    uint8_t *plane_mem_fg; Rb200Planes planes_fg, display;
     // optional per-stage timing (the analogue of the reference CLI's --frametimes, tools/dav1d.rs:127-150)
     cudaStream_t own_stream;
     bool timing;
@@ -135,6 +141,7 @@ extern "C" int rb200_frame_create(Rb200Frame **out, const Rb200FrameHeader *hdr,
     if (!r) { e = cudaStreamSynchronize(f->stream); if (e != cudaSuccess) r = cuda_fail(e, "sync", __FILE__, __LINE__); }
     if (r) { rb200_frame_destroy(f); return r; }
     f->out = f->planes[0];
+    f->display = f->out;
     *out = f;
     return 0;
 }
@@ -144,6 +151,9 @@ extern "C" int rb200_frame_destroy(Rb200Frame *f) {
     if (f->stream) cudaStreamSynchronize(f->stream);
     for (int i = 0; i < RB200_N_FRAME_MARKS; i++) if (f->ev[i]) cudaEventDestroy(f->ev[i]);
     for (int i = 0; i < 3; i++) if (f->plane_mem[i]) cudaFree(f->plane_mem[i]);
+    if (f->fg_mem) cudaFree(f->fg_mem);
+    if (f->h_fgpts) cudaFreeHost(f->h_fgpts);
+    if (f->plane_mem_fg) cudaFree(f->plane_mem_fg);
     if (f->h_coef) cudaFreeHost(f->h_coef);
     if (f->d_coef) cudaFree(f->d_coef);
     if (f->h_itx) cudaFreeHost(f->h_itx);
@@ -180,6 +190,89 @@ extern "C" Rb200Av1Restoration *rb200_frame_lr_masks(Rb200Frame *f) { return f ?
 extern "C" void *rb200_frame_stream(Rb200Frame *f) { return f ? (void *)f->stream : nullptr; }
 extern "C" int rb200_frame_last_launches(const Rb200Frame *f) { return f ? f->launches : 0; }
 
+constexpr size_t FG_LUT_BYTES = (size_t)(RB200_GRAIN_HEIGHT + 1) * RB200_GRAIN_WIDTH * 2;
+constexpr size_t FG_OFF_LUT = 0, FG_OFF_SCALING = 3 * FG_LUT_BYTES + 64, FG_OFF_PTS = FG_OFF_SCALING + 3 * 4096,
+                 FG_OFF_OFFSETS = FG_OFF_PTS + 128;
+
+extern "C" int rb200_frame_set_film_grain(Rb200Frame *f, const Rb200FilmGrainData *data, int is_id) {
+    if (!f || !data) return set_error(-22, "frame_set_film_grain: null argument");
+    if (data->num_y_points < 0 || data->num_y_points > 14 || data->num_uv_points[0] < 0 || data->num_uv_points[0] > 10 ||
+        data->num_uv_points[1] < 0 || data->num_uv_points[1] > 10 || data->ar_coeff_lag < 0 || data->ar_coeff_lag > 3)
+        return set_error(-22, "frame_set_film_grain: bad parameters");
+    if (!f->fg_mem) {
+        const int rows = (f->hdr.height + 31) >> 5, cols = (f->hdr.width + 31) >> 5;
+        RB_CUDA(cudaMalloc((void **)&f->fg_mem, FG_OFF_OFFSETS + (size_t)rows * (cols + 1) + 64));
+        RB_CUDA(cudaMallocHost((void **)&f->h_fgpts, 128));
+        const size_t ysz = (size_t)f->g.stride[0] * f->g.plane_h[0];
+        const size_t uvsz = f->g.n_planes > 1 ? (size_t)f->g.stride[1] * f->g.plane_h[1] : 0;
+        RB_CUDA(cudaMalloc((void **)&f->plane_mem_fg, ysz + 2 * uvsz + 256));
+        Rb200Planes &p = f->planes_fg;
+        p.data[0] = f->plane_mem_fg; p.stride[0] = f->g.stride[0];
+        p.data[1] = uvsz ? f->plane_mem_fg + ysz : nullptr;
+        p.data[2] = uvsz ? f->plane_mem_fg + ysz + uvsz : nullptr;
+        p.stride[1] = p.stride[2] = uvsz ? f->g.stride[1] : 0;
+    }
+    f->fg = *data; f->fg_is_id = is_id; f->fg_set = true;
+    return 0;
+}
+
+extern "C" int rb200_frame_display_planes(Rb200Frame *f, Rb200Planes *out) {
+    if (!f || !out) return set_error(-22, "frame_display_planes: bad argument");
+    *out = f->display;
+    return 0;
+}
+
+// rav1d_prep_grain + rav1d_apply_grain_row over the whole picture (src/fg_apply.rs:74-284)
+static int film_grain_stage(Rb200Frame *f, cudaStream_t st) {
+    const Rb200FilmGrainData &d = f->fg;
+    const Rb200FrameGeometry &g = f->g;
+    const int w = f->hdr.width, h = f->hdr.height, bpc = f->hdr.bpc;
+    uint8_t *lut[3], *sc[3];
+    for (int i = 0; i < 3; i++) { lut[i] = f->fg_mem + FG_OFF_LUT + i * FG_LUT_BYTES; sc[i] = f->fg_mem + FG_OFF_SCALING + i * 4096; }
+    uint8_t *d_pts = f->fg_mem + FG_OFF_PTS, *d_off = f->fg_mem + FG_OFF_OFFSETS;
+    memset(f->h_fgpts, 0, 128);
+    memcpy(f->h_fgpts, d.y_points, sizeof(d.y_points));
+    memcpy(f->h_fgpts + 32, d.uv_points[0], sizeof(d.uv_points[0]));
+    memcpy(f->h_fgpts + 64, d.uv_points[1], sizeof(d.uv_points[1]));
+    RB_CUDA(cudaMemcpyAsync(d_pts, f->h_fgpts, 128, cudaMemcpyHostToDevice, st));
+    const bool chroma = g.n_planes > 1;
+    const bool do_uv[2] = { chroma && (d.num_uv_points[0] || d.chroma_scaling_from_luma),
+                            chroma && (d.num_uv_points[1] || d.chroma_scaling_from_luma) };
+    int r;
+    if ((r = fg_generate(lut[0], nullptr, d, -1, 0, 0, f->bdmax, st))) return r;
+    f->launches++;
+    for (int pl = 0; pl < 2; pl++)
+        if (do_uv[pl]) { if ((r = fg_generate(lut[1 + pl], lut[0], d, pl, g.ss_hor, g.ss_ver, f->bdmax, st))) return r; f->launches++; }
+    if (d.num_y_points || d.chroma_scaling_from_luma) { if ((r = fg_scaling(sc[0], d_pts, d.num_y_points, bpc, st))) return r; f->launches++; }
+    for (int pl = 0; pl < 2; pl++)
+        if (chroma && d.num_uv_points[pl]) { if ((r = fg_scaling(sc[1 + pl], d_pts + 32 * (1 + pl), d.num_uv_points[pl], bpc, st))) return r; f->launches++; }
+    const int rows = (h + 31) >> 5, ncols = ((w + 31) >> 5) + 1;
+    if ((r = fg_offsets(d_off, d.seed, 0, rows, ncols, st))) return r;
+    f->launches++;
+    const Rb200Planes in = f->out;
+    f->display = in;
+    if (d.num_y_points) {
+        FgApplyParams P = fg_params(d, 0, 0, 0, 0, f->fg_is_id);
+        P.pw = w; P.ph = h; P.row0 = 0; P.off_row0 = 0; P.ncols = ncols; P.luma_w = w;
+        if ((r = fg_apply((uint8_t *)f->planes_fg.data[0], (const uint8_t *)in.data[0], in.stride[0], nullptr, 0, P, sc[0],
+                          lut[0], d_off, f->bdmax, st))) return r;
+        f->launches++;
+        f->display.data[0] = f->planes_fg.data[0]; f->display.stride[0] = f->planes_fg.stride[0];
+    }
+    for (int pl = 0; pl < 2; pl++) {
+        if (!do_uv[pl]) continue;
+        FgApplyParams P = fg_params(d, 1, pl, g.ss_hor, g.ss_ver, f->fg_is_id);
+        P.pw = (w + g.ss_hor) >> g.ss_hor; P.ph = (h + g.ss_ver) >> g.ss_ver;
+        P.row0 = 0; P.off_row0 = 0; P.ncols = ncols; P.luma_w = w;
+        if ((r = fg_apply((uint8_t *)f->planes_fg.data[1 + pl], (const uint8_t *)in.data[1 + pl], in.stride[1 + pl],
+                          (const uint8_t *)in.data[0], in.stride[0], P,
+                          d.chroma_scaling_from_luma ? sc[0] : sc[1 + pl], lut[1 + pl], d_off, f->bdmax, st))) return r;
+        f->launches++;
+        f->display.data[1 + pl] = f->planes_fg.data[1 + pl]; f->display.stride[1 + pl] = f->planes_fg.stride[1 + pl];
+    }
+    return 0;
+}
+
 extern "C" int rb200_frame_set_stream(Rb200Frame *f, void *stream) {
     if (!f) return set_error(-22, "frame_set_stream: null frame");
     RB_CUDA(cudaStreamSynchronize(f->stream));
@@ -196,7 +289,7 @@ extern "C" int rb200_frame_enable_timing(Rb200Frame *f, int on) {
     return 0;
 }
 
-// ms between consecutive marks of the last submit: [0] H2D, [1] MC, [2] itx, [3] deblock, [4] CDEF, [5] LR.
+// ms between consecutive marks of the last submit: [0] H2D, [1] MC, [2] itx, [3] deblock, [4] CDEF, [5] LR, [6] film grain.
 // A stage that did not run reports 0.  Valid after rb200_frame_wait().
 extern "C" int rb200_frame_stage_times(Rb200Frame *f, float ms[RB200_N_FRAME_MARKS - 1]) {
     if (!f || !ms) return set_error(-22, "frame_stage_times: bad argument");
@@ -261,12 +354,12 @@ extern "C" int rb200_frame_readback_async(Rb200Frame *f, void *const data[3], co
         const int rows = plane_rows(f, p);
         const ptrdiff_t hs = stride[p ? 1 : 0];
         if (hs >= 0) {
-            RB_CUDA(cudaMemcpy2DAsync(data[p], (size_t)hs, f->out.data[p], (size_t)f->out.stride[p],
+            RB_CUDA(cudaMemcpy2DAsync(data[p], (size_t)hs, f->display.data[p], (size_t)f->display.stride[p],
                                       plane_row_bytes(f, p), rows, cudaMemcpyDeviceToHost, f->stream));
         } else {
             for (int y = 0; y < rows; y++)
                 RB_CUDA(cudaMemcpyAsync((uint8_t *)data[p] + (int64_t)y * hs,
-                                        (const uint8_t *)f->out.data[p] + (int64_t)y * f->out.stride[p],
+                                        (const uint8_t *)f->display.data[p] + (int64_t)y * f->display.stride[p],
                                         plane_row_bytes(f, p), cudaMemcpyDeviceToHost, f->stream));
         }
     }
@@ -391,6 +484,12 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         }
     }
     MARK(6);
+    f->display = f->out;
+    if (stages & RB200_STAGE_FILM_GRAIN) {
+        if (!f->fg_set) return set_error(-22, "frame_submit: RB200_STAGE_FILM_GRAIN without rb200_frame_set_film_grain");
+        if ((r = film_grain_stage(f, st))) return r;
+    }
+    MARK(7);
 #undef MARK
     return 0;
 }

@@ -89,7 +89,7 @@ N_2D_FILTERS = 10
 FILTER_2D_NAMES = ["8TAP_REGULAR", "8TAP_REGULAR_SMOOTH", "8TAP_REGULAR_SHARP", "8TAP_SHARP_REGULAR",
                    "8TAP_SHARP_SMOOTH", "8TAP_SHARP", "8TAP_SMOOTH_REGULAR", "8TAP_SMOOTH", "8TAP_SMOOTH_SHARP",
                    "BILINEAR"]
-STAGE_RECON, STAGE_DEBLOCK, STAGE_CDEF, STAGE_LR = 1, 2, 4, 8
+STAGE_RECON, STAGE_DEBLOCK, STAGE_CDEF, STAGE_LR, STAGE_FILM_GRAIN = 1, 2, 4, 8, 16
 STAGE_ALL = 15
 LAYOUT_I400, LAYOUT_I420, LAYOUT_I422, LAYOUT_I444 = 0, 1, 2, 3
 RESTORATION_NONE, RESTORATION_SWITCHABLE, RESTORATION_WIENER, RESTORATION_SGRPROJ = 0, 1, 2, 3
@@ -117,6 +117,19 @@ class LrParams(C.Union):
     class _Sgr(C.Structure):
         _fields_ = [("s0", C.c_uint32), ("s1", C.c_uint32), ("w0", C.c_int16), ("w1", C.c_int16)]
     _fields_ = [("filter", (C.c_int16 * 8) * 2), ("sgr", _Sgr), ("_align", C.c_byte * 32)]
+
+
+class FilmGrainData(C.Structure):
+    """Rb200FilmGrainData == Dav1dFilmGrainData (include/dav1d/headers.rs:1610-1661)"""
+    _fields_ = [("seed", C.c_uint), ("num_y_points", C.c_int), ("y_points", (C.c_uint8 * 2) * 14),
+                ("chroma_scaling_from_luma", C.c_int), ("num_uv_points", C.c_int * 2),
+                ("uv_points", ((C.c_uint8 * 2) * 10) * 2), ("scaling_shift", C.c_int), ("ar_coeff_lag", C.c_int),
+                ("ar_coeffs_y", C.c_int8 * 24), ("ar_coeffs_uv", (C.c_int8 * 28) * 2), ("ar_coeff_shift", C.c_uint64),
+                ("grain_scale_shift", C.c_int), ("uv_mult", C.c_int * 2), ("uv_luma_mult", C.c_int * 2),
+                ("uv_offset", C.c_int * 2), ("overlap_flag", C.c_int), ("clip_to_restricted_range", C.c_int)]
+
+
+GRAIN_WIDTH, GRAIN_HEIGHT = 82, 73
 
 
 class FrameHeader(C.Structure):
@@ -157,6 +170,16 @@ mc_dsp_init = _sig("rb200_mc_dsp_init", None, _vp, _i)
 loop_filter_dsp_init = _sig("rb200_loop_filter_dsp_init", None, _vp, _i)
 cdef_dsp_init = _sig("rb200_cdef_dsp_init", None, _vp, _i)
 loop_restoration_dsp_init = _sig("rb200_loop_restoration_dsp_init", None, _vp, _i)
+
+film_grain_dsp_init = _sig("rb200_film_grain_dsp_init", None, _vp, _i)
+generate_grain_y = _sig("rb200_generate_grain_y", _i, _vp, C.POINTER(FilmGrainData), _i)
+generate_grain_uv = _sig("rb200_generate_grain_uv", _i, _i, _vp, _vp, C.POINTER(FilmGrainData), _ss, _i)
+fgy_32x32xn = _sig("rb200_fgy_32x32xn", _i, _vp, _vp, _ss, C.POINTER(FilmGrainData), _sz, _vp, _vp, _i, _i, _i)
+fguv_32x32xn = _sig("rb200_fguv_32x32xn", _i, _i, _vp, _vp, _ss, C.POINTER(FilmGrainData), _sz, _vp, _vp, _i, _i,
+                    _vp, _ss, _i, _i, _i)
+generate_scaling = _sig("rb200_generate_scaling", _i, _i, _vp, _i, _vp)
+frame_set_film_grain = _sig("rb200_frame_set_film_grain", _i, _vp, C.POINTER(FilmGrainData), _i)
+frame_display_planes = _sig("rb200_frame_display_planes", _i, _vp, C.POINTER(Planes))
 
 frame_create = _sig("rb200_frame_create", _i, C.POINTER(_vp), C.POINTER(FrameHeader), _sz, _i, _i)
 frame_destroy = _sig("rb200_frame_destroy", _i, _vp)

@@ -65,6 +65,13 @@ def load():
         sig("ref_frame_sbh", i, vp)
         sig("ref_frame_filter", None, vp, i, i)
         sig("ref_frame_recon", None, vp, vp, i, vp, i, vp, i, vp, i)
+        sig("ref_frame_apply_grain", None, vp, vp, i)
+        sig("ref_frame_grain_plane", vp, vp, i)
+        sig("ref_fg_gen_y", None, vp, vp, i)
+        sig("ref_fg_gen_uv", None, i, vp, vp, vp, ss, i)
+        sig("ref_fgy", None, vp, vp, ss, vp, sz, vp, vp, i, i, i)
+        sig("ref_fguv", None, i, vp, vp, ss, vp, sz, vp, vp, i, i, vp, ss, i, i, i)
+        sig("ref_sizeof_film_grain_data", sz)
     return _lib
 
 
@@ -86,11 +93,12 @@ class RefFrame:
             self.ref.ref_frame_free(self.h)
             self.h = None
 
-    def plane_view(self, p):
+    def plane_view(self, p, grain=False):
         s = self.s
         rows = s.ah if p == 0 else s.ah // 2
         stride = self.strides[1 if p else 0]
-        buf = (C.c_ubyte * (stride * rows)).from_address(self.ref.ref_frame_plane(self.h, p))
+        addr = self.ref.ref_frame_grain_plane(self.h, p) if grain else self.ref.ref_frame_plane(self.h, p)
+        buf = (C.c_ubyte * (stride * rows)).from_address(addr)
         a = np.frombuffer(buf, dtype=np.uint8).reshape(rows, stride)
         cols = s.aw if p == 0 else s.aw // 2
         return a[:, :cols * self.px].view(np.uint16 if self.px == 2 else np.uint8)
@@ -122,6 +130,10 @@ class RefFrame:
         itx = np.ascontiguousarray(s.itx_items)
         self.ref.ref_frame_recon(self.h, refs, 1, ptr(mc), len(mc), ptr(itx), len(itx), ptr(cw), n_threads)
         return cw
+
+    def apply_grain(self, fg, is_id=0):
+        self.ref.ref_frame_apply_grain(self.h, C.addressof(fg), is_id)
+        return [self.plane_view(p, grain=True).copy() for p in range(3)]
 
     def filter(self, stages, n_threads=1):
         self.ref.ref_frame_filter(self.h, stages, n_threads)
