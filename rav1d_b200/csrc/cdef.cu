@@ -161,105 +161,276 @@ __device__ __forceinline__ int cdef_adjust_strength(int strength, unsigned var) 
 }
 
 
-struct CdefBlk {  // per 8x8 luma block of the tile
-    int16_t y_pri, y_sec, uv_pri, uv_sec;
-    int8_t dir, uvdir, do_y, do_uv;
+// ---------------------------------------------------------------- frame level
+// Two launches per frame:
+//  (1) cdef_dir_frame_kernel: one thread per 8x8 luma block reads the block straight from
+//      global memory (rows are coalesced across the 32 blocks of a warp), runs the direction
+//      search out of registers and resolves everything rav1d_cdef_brow decides per block
+//      (cdef_idx, noskip bits, strengths, adjust_strength, chroma direction) into an 8-byte
+//      record;
+//  (2) cdef_filter_frame_kernel: one CTA per 64x64 luma area and its chroma.  The pre-CDEF
+//      pixels (+2 halo) are staged in shared memory twice, the second copy shifted by one
+//      pixel, so that any horizontally adjacent pixel PAIR is one aligned 32-bit word in one
+//      of the copies.  A thread filters one row of one 8x8 block, two pixels per register:
+//      the constrain() of both pixels is evaluated with the packed 16x2 min/max/add
+//      instructions of sm_100a (VIMNMX.S16x2, VIADDMNMX.S16x2, VIMNMX3), the weighted sum
+//      with one IMAD per tap on values biased to stay positive in both halves.
+//      Blocks on the frame border (the only ones that can see the reference's INT16_MIN
+//      "unavailable" sentinel) take the scalar path.
+struct CdefBlk {  // per 8x8 luma block, written by (1), read by (2)
+    uint8_t y_pri, y_sec, uv_pri, uv_sec;  // y_pri already through adjust_strength
+    uint8_t dir, uvdir, do_y, do_uv;
 };
 
 template <typename BD>
-__device__ void cdef_stage_tile(int16_t *tile, const uint8_t *plane, int64_t stride, int x0, int y0, int tw, int th,
-                                int fw, int fh) {
+__global__ void __launch_bounds__(128)
+cdef_dir_frame_kernel(Rb200Planes src, CdefFrameParams P, const Rb200Av1Filter *__restrict__ masks,
+                      CdefBlk *__restrict__ out, int nbx, int nby) {
     using pixel = typename BD::pixel;
-    const int cols = tw + 4, rows = th + 4;
-    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
-        const int r = i / cols, c = i - r * cols;
-        const int y = y0 + r - 2, x = x0 + c - 2;
-        int16_t v = CDEF_SENTINEL;
-        if (x >= 0 && y >= 0 && x < fw && y < fh) v = (int16_t)((const pixel *)(plane + (int64_t)y * stride))[x];
-        tile[r * CDEF_PITCH + c] = v;
+    const int bx = blockIdx.x * 32 + threadIdx.x, by = blockIdx.y * 4 + threadIdx.y;
+    if (bx >= nbx || by >= nby) return;
+    CdefBlk b = {};
+    const Rb200Av1Filter &m = masks[(by >> 4) * P.sb128w + (bx >> 4)];
+    const int cdef_idx = m.cdef_idx[(((by >> 3) & 1) << 1) + ((bx >> 3) & 1)];
+    const int y_lvl = cdef_idx >= 0 ? P.y_strength[cdef_idx] : 0;
+    const int uv_lvl = cdef_idx >= 0 ? P.uv_strength[cdef_idx] : 0;
+    if (cdef_idx >= 0 && (y_lvl || uv_lvl)) {
+        const uint16_t *row = m.noskip_mask[by & 15];
+        const unsigned nm = ((unsigned)row[1] << 16) | row[0];
+        if (nm & (3u << ((bx & 15) * 2))) {
+            const int y_pri = (y_lvl >> 2) << P.bdmin8;
+            int y_sec = y_lvl & 3; y_sec += y_sec == 3; y_sec <<= P.bdmin8;
+            const int uv_pri = (uv_lvl >> 2) << P.bdmin8;
+            int uv_sec = uv_lvl & 3; uv_sec += uv_sec == 3; uv_sec <<= P.bdmin8;
+            int dir = 0; unsigned var = 0;
+            if (y_pri || uv_pri) {
+                // 8 rows of 8 pixels -> int16 registers
+                int16_t t[64];
+                const uint8_t *p = (const uint8_t *)src.data[0] + (int64_t)(by * 8) * src.stride[0] + (int64_t)bx * 8 * sizeof(pixel);
+#pragma unroll
+                for (int y = 0; y < 8; y++) {
+                    if (BD::hbd) {
+                        const uint4 v = *(const uint4 *)(p + (int64_t)y * src.stride[0]);
+                        t[y * 8 + 0] = (int16_t)(v.x & 0xffff); t[y * 8 + 1] = (int16_t)(v.x >> 16);
+                        t[y * 8 + 2] = (int16_t)(v.y & 0xffff); t[y * 8 + 3] = (int16_t)(v.y >> 16);
+                        t[y * 8 + 4] = (int16_t)(v.z & 0xffff); t[y * 8 + 5] = (int16_t)(v.z >> 16);
+                        t[y * 8 + 6] = (int16_t)(v.w & 0xffff); t[y * 8 + 7] = (int16_t)(v.w >> 16);
+                    } else {
+                        const uint2 v = *(const uint2 *)(p + (int64_t)y * src.stride[0]);
+#pragma unroll
+                        for (int x = 0; x < 4; x++) {
+                            t[y * 8 + x] = (int16_t)((v.x >> (8 * x)) & 0xff);
+                            t[y * 8 + 4 + x] = (int16_t)((v.y >> (8 * x)) & 0xff);
+                        }
+                    }
+                }
+                dir = cdef_find_dir(t, 8, P.bdmin8, &var);
+            }
+            if (y_pri) {
+                const int adj = cdef_adjust_strength(y_pri, var);
+                if (adj || y_sec) { b.do_y = 1; b.y_pri = (uint8_t)adj; b.y_sec = (uint8_t)y_sec; b.dir = (uint8_t)dir; }
+            } else if (y_sec) {
+                b.do_y = 1; b.y_pri = 0; b.y_sec = (uint8_t)y_sec; b.dir = 0;
+            }
+            if (uv_lvl) {
+                b.do_uv = 1; b.uv_pri = (uint8_t)uv_pri; b.uv_sec = (uint8_t)uv_sec;
+                const int d422 = (0x66654207 >> (4 * dir)) & 7;  // 4:2:2 remap, src/cdef_apply_tmpl.c:113-115
+                b.uvdir = (uint8_t)(uv_pri ? (P.layout_422 ? d422 : dir) : 0);
+            }
+        }
+    }
+    out[by * nbx + bx] = b;
+}
+
+constexpr int CDEF_TP = 74;                        // tile pitch in pixels: 37 words, odd -> rows spread over banks
+constexpr int CDEF_TROWS = 68;
+constexpr int CDEF_COPY = CDEF_TROWS * CDEF_TP;    // elements per copy
+constexpr int CDEF_X0 = 4;                         // tile column of the area's first pixel (even; 4 = one load group)
+constexpr unsigned CDEF_BIAS = 256;                // per-half bias of the constrained differences (|c| <= 240)
+
+// Stage rows y0-2 .. y0+th+1, columns x0-4 .. x0+tw+3 of `plane` (4-pixel groups, vector loads)
+// into copy A (tile[]) and the one-pixel-shifted copy B (tile[CDEF_COPY + i] = A[i + 1]).
+template <typename BD>
+__device__ __forceinline__ void cdef_stage2(int16_t *tile, const uint8_t *plane, int64_t stride, int x0, int y0, int tw,
+                                            int th, int fw, int fh) {
+    using pixel = typename BD::pixel;
+    const int groups = (tw + 8) >> 2, rows = th + 4;
+    for (int i = threadIdx.x; i < rows * groups; i += blockDim.x) {
+        const int r = i / groups, g = i - r * groups;
+        const int y = y0 + r - 2, x = x0 - 4 + g * 4;
+        int v[4] = {CDEF_SENTINEL, CDEF_SENTINEL, CDEF_SENTINEL, CDEF_SENTINEL};
+        if (y >= 0 && y < fh && x >= 0 && x < fw) {  // fw is a multiple of 8: a group is inside or outside as a whole
+            const uint8_t *p = plane + (int64_t)y * stride + (int64_t)x * sizeof(pixel);
+            if (BD::hbd) {
+                const uint2 q = *(const uint2 *)p;
+                v[0] = q.x & 0xffff; v[1] = q.x >> 16; v[2] = q.y & 0xffff; v[3] = q.y >> 16;
+            } else {
+                const unsigned q = *(const unsigned *)p;
+                v[0] = q & 0xff; v[1] = (q >> 8) & 0xff; v[2] = (q >> 16) & 0xff; v[3] = q >> 24;
+            }
+        }
+        int16_t *a = tile + r * CDEF_TP + g * 4;
+        // the odd word pitch makes rows only 4-byte aligned
+        ((unsigned *)a)[0] = (unsigned)(v[0] & 0xffff) | ((unsigned)v[1] << 16);
+        ((unsigned *)a)[1] = (unsigned)(v[2] & 0xffff) | ((unsigned)v[3] << 16);
+        int16_t *bcopy = a + CDEF_COPY - 1;
+        if (g) bcopy[0] = (int16_t)v[0];
+        bcopy[1] = (int16_t)v[1]; bcopy[2] = (int16_t)v[2]; bcopy[3] = (int16_t)v[3];
+    }
+}
+
+// byte offset (from the tile base) of the aligned word holding pixels (s, s + 1) of a row-major element index s
+__device__ __forceinline__ int cdef_pair_addr(int s) { return (s & 1) ? 2 * (CDEF_COPY + s - 1) : 2 * s; }
+
+// Filter NP pixel pairs of one block row.  `s0`: element index of the first pixel (even).
+// Returns the filtered pixels in out[2 * NP].  Interior blocks only (no sentinel in reach).
+template <int NP>
+__device__ __forceinline__ void cdef_row_packed(const int16_t *tile, int s0, int pri, int sec, int dir, int damping,
+                                                int bdmin8, int *out) {
+    const char *base = (const char *)tile;
+    unsigned px2[NP], cst[NP], sum[NP], mn[NP], mx[NP];
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+        px2[j] = *(const unsigned *)(base + 2 * (s0 + 2 * j));
+        cst[j] = __vneg2(px2[j]);   // -px per half
+        sum[j] = 0; mn[j] = px2[j]; mx[j] = px2[j];
+    }
+    const unsigned B2 = CDEF_BIAS * 0x10001u;
+    int ktot = 0;
+    auto tap = [&](int off_el, int thr, int shift, int w, bool track) {
+        const unsigned m = (0xffffu >> shift) * 0x10001u;
+        const unsigned thr1 = (unsigned)(thr + 1) * 0x10001u;
+        const unsigned bmt = (unsigned)(CDEF_BIAS - thr) * 0x10001u;
+#pragma unroll
+        for (int sgn = 0; sgn < 2; sgn++) {
+            const int a0 = cdef_pair_addr(s0 + (sgn ? -off_el : off_el));
+#pragma unroll
+            for (int j = 0; j < NP; j++) {
+                const unsigned p2 = *(const unsigned *)(base + a0 + 4 * j);
+                const unsigned d = __vadd2(p2, cst[j]);                 // p - px
+                const unsigned a = __vmaxs2(d, __vneg2(d));             // |d|
+                const unsigned x = a >> shift;
+                const unsigned sft = x & m;                             // |d| >> shift, per half
+                const unsigned t = __viaddmax_s16x2(~sft, thr1, 0u);    // max(thr - s, 0)
+                const unsigned ntb = __viaddmin_s16x2(sft, bmt, B2);    // BIAS - t
+                const unsigned c = __viaddmax_s16x2(__vmins2(d, t), B2, ntb);  // BIAS + clamp(d, -t, t)
+                sum[j] += (unsigned)w * c;
+                if (track) { mn[j] = __vminu2(mn[j], p2); mx[j] = __vmaxs2(mx[j], p2); }
+            }
+        }
+        ktot += 2 * w;
+    };
+    const bool both = pri && sec;
+    if (pri) {
+        const int pri_tap = 4 - ((pri >> bdmin8) & 1);
+        const int pri_shift = imax(0, damping - ulog2(pri));
+        int dy, dx;
+        tab::cdef_dir_off(dir, 0, dy, dx);
+        tap(dy * CDEF_TP + dx, pri, pri_shift, pri_tap, both);
+        tab::cdef_dir_off(dir, 1, dy, dx);
+        tap(dy * CDEF_TP + dx, pri, pri_shift, (pri_tap & 3) | 2, both);
+    }
+    if (sec) {
+        const int sec_shift = damping - ulog2(sec);
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            int dy, dx;
+            tab::cdef_dir_off((dir + 2) & 7, k, dy, dx);
+            tap(dy * CDEF_TP + dx, sec, sec_shift, 2 - k, both);
+            tab::cdef_dir_off((dir + 6) & 7, k, dy, dx);
+            tap(dy * CDEF_TP + dx, sec, sec_shift, 2 - k, both);
+        }
+    }
+    const int kb = ktot * (int)CDEF_BIAS;
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int s = (int)((sum[j] >> (16 * h)) & 0xffff) - kb;
+            const int px = (int)((px2[j] >> (16 * h)) & 0xffff);
+            int v = px + ((s - (s < 0) + 8) >> 4);
+            if (both) v = iclip(v, (int)((mn[j] >> (16 * h)) & 0xffff), (int)((mx[j] >> (16 * h)) & 0xffff));
+            out[2 * j + h] = v;
+        }
+    }
+}
+
+// One plane of the area.  bw/bh: block size in this plane (8 or 4); tile staged already.
+template <typename BD, int BW>
+__device__ __forceinline__ void cdef_filter_plane(const int16_t *tile, const CdefBlk *blk, uint8_t *dbase, int64_t dstride,
+                                                  int px0, int py0, int tw, int th, int bh_log2, bool chroma, int damping,
+                                                  int bdmin8, int nbx, int nby, int gbx0, int gby0) {
+    using pixel = typename BD::pixel;
+    constexpr int NP = BW / 2;
+    const int bh = 1 << bh_log2;
+    const int n_tasks = 64 << bh_log2;   // 64 blocks x rows
+    for (int t = threadIdx.x; t < n_tasks; t += blockDim.x) {
+        // a warp covers 8 blocks along x times 4 rows: conflict-free centre loads with the odd word pitch
+        const int lane = t & 31, grp = t >> 5;
+        const int bxl = lane & 7, rlow = lane >> 3;
+        const int rows_per_blk_grp = bh >> 2;                  // 4-row groups per block (1 or 2)
+        const int byl = grp / rows_per_blk_grp, r = rlow + 4 * (grp - byl * rows_per_blk_grp);
+        const int x = bxl * BW, y = byl * bh + r;
+        if (x >= tw || y >= th) continue;
+        const CdefBlk b = blk[byl * 8 + bxl];
+        const int s0 = (2 + y) * CDEF_TP + CDEF_X0 + x;
+        int out[BW];
+        const bool on = chroma ? b.do_uv : b.do_y;
+        const int pri = chroma ? b.uv_pri : b.y_pri, sec = chroma ? b.uv_sec : b.y_sec, dir = chroma ? b.uvdir : b.dir;
+        const int gbx = gbx0 + bxl, gby = gby0 + byl;
+        const bool border = gbx == 0 || gby == 0 || gbx == nbx - 1 || gby == nby - 1;
+        if (!on) {
+#pragma unroll
+            for (int i = 0; i < BW; i++) out[i] = tile[s0 + i];
+        } else if (border) {
+#pragma unroll
+            for (int i = 0; i < BW; i++) out[i] = cdef_filter_px(tile + s0 + i, CDEF_TP, pri, sec, dir, damping, bdmin8);
+        } else {
+            cdef_row_packed<NP>(tile, s0, pri, sec, dir, damping, bdmin8, out);
+        }
+        pixel *d = (pixel *)(dbase + (int64_t)(py0 + y) * dstride) + px0 + x;
+        if (BD::hbd) {
+            if (BW == 8) *(uint4 *)d = make_uint4(out[0] | (out[1] << 16), out[2] | (out[3] << 16), out[4] | (out[5] << 16), out[6] | (out[7] << 16));
+            else *(uint2 *)d = make_uint2(out[0] | (out[1] << 16), out[2] | (out[3] << 16));
+        } else {
+            if (BW == 8) *(uint2 *)d = make_uint2(out[0] | (out[1] << 8) | (out[2] << 16) | (out[3] << 24), out[4] | (out[5] << 8) | (out[6] << 16) | (out[7] << 24));
+            else *(unsigned *)d = out[0] | (out[1] << 8) | (out[2] << 16) | (out[3] << 24);
+        }
     }
 }
 
 template <typename BD>
 __global__ void __launch_bounds__(256)
-cdef_frame_kernel(Rb200Planes src, Rb200Planes dst, CdefFrameParams P, const Rb200Av1Filter *__restrict__ masks,
-                  int bdmax) {
-    using pixel = typename BD::pixel;
-    __shared__ int16_t tile[CDEF_PITCH * CDEF_PITCH];
+cdef_filter_frame_kernel(Rb200Planes src, Rb200Planes dst, CdefFrameParams P, const CdefBlk *__restrict__ blocks, int nbx,
+                         int nby) {
+    __shared__ __align__(16) int16_t tile[2 * CDEF_COPY + 8];
     __shared__ CdefBlk blk[64];
-    const int sbx = blockIdx.x, sby = blockIdx.y;  // 64x64 units
+    const int sbx = blockIdx.x, sby = blockIdx.y;
     const int x0 = sbx * 64, y0 = sby * 64;
     const int fw = P.bw * 4, fh = P.bh * 4;
     const int tw = imin(64, fw - x0), th = imin(64, fh - y0);
-
-    const Rb200Av1Filter &m = masks[(sby >> 1) * P.sb128w + (sbx >> 1)];
-    const int cdef_idx = m.cdef_idx[((sby & 1) << 1) + (sbx & 1)];
-    const int y_lvl = cdef_idx >= 0 ? P.y_strength[cdef_idx] : 0;
-    const int uv_lvl = cdef_idx >= 0 ? P.uv_strength[cdef_idx] : 0;
-    const bool sb_on = cdef_idx >= 0 && (y_lvl || uv_lvl);
-
-    // ---- luma
-    cdef_stage_tile<BD>(tile, (const uint8_t *)src.data[0], src.stride[0], x0, y0, tw, th, fw, fh);
-    __syncthreads();
     if (threadIdx.x < 64) {
-        const int bx = threadIdx.x & 7, by = threadIdx.x >> 3;  // 8x8 block inside the tile
+        const int bx = sbx * 8 + (threadIdx.x & 7), by = sby * 8 + (threadIdx.x >> 3);
         CdefBlk b = {};
-        if (sb_on && bx * 8 < tw && by * 8 < th) {
-            // noskip_mask row = 8-pixel row pair inside the sb128, bits = 4-pixel columns inside the sb128
-            const int by4 = (y0 >> 2) + by * 2, bx4 = (x0 >> 2) + bx * 2;
-            const uint16_t *row = m.noskip_mask[(by4 & 30) >> 1];
-            const unsigned nm = ((unsigned)row[1] << 16) | row[0];
-            if (nm & (3u << (bx4 & 30))) {
-                const int y_pri = (y_lvl >> 2) << P.bdmin8;
-                int y_sec = y_lvl & 3; y_sec += y_sec == 3; y_sec <<= P.bdmin8;
-                const int uv_pri = (uv_lvl >> 2) << P.bdmin8;
-                int uv_sec = uv_lvl & 3; uv_sec += uv_sec == 3; uv_sec <<= P.bdmin8;
-                int dir = 0; unsigned var = 0;
-                if (y_pri || uv_pri) dir = cdef_find_dir(tile + (2 + by * 8) * CDEF_PITCH + 2 + bx * 8, CDEF_PITCH, P.bdmin8, &var);
-                if (y_pri) {
-                    const int adj = cdef_adjust_strength(y_pri, var);
-                    if (adj || y_sec) { b.do_y = 1; b.y_pri = (int16_t)adj; b.y_sec = (int16_t)y_sec; b.dir = (int8_t)dir; }
-                } else if (y_sec) {
-                    b.do_y = 1; b.y_pri = 0; b.y_sec = (int16_t)y_sec; b.dir = 0;
-                }
-                if (uv_lvl) {
-                    b.do_uv = 1; b.uv_pri = (int16_t)uv_pri; b.uv_sec = (int16_t)uv_sec;
-                    // 4:2:2 remaps directions (src/cdef_apply_tmpl.c:113-115)
-                    const int d422 = (0x66654207 >> (4 * dir)) & 7;
-                    b.uvdir = (int8_t)(uv_pri ? (P.layout_422 ? d422 : dir) : 0);
-                }
-            }
-        }
+        if (bx < nbx && by < nby) b = blocks[by * nbx + bx];
         blk[threadIdx.x] = b;
     }
+    cdef_stage2<BD>(tile, (const uint8_t *)src.data[0], src.stride[0], x0, y0, tw, th, fw, fh);
     __syncthreads();
-    {
-        uint8_t *dbase = (uint8_t *)dst.data[0];
-        for (int i = threadIdx.x; i < th * tw; i += 256) {
-            const int r = i / tw, c = i - r * tw;
-            const CdefBlk b = blk[(r >> 3) * 8 + (c >> 3)];
-            const int16_t *t = tile + (2 + r) * CDEF_PITCH + 2 + c;
-            int v = t[0];
-            if (b.do_y) v = cdef_filter_px(t, CDEF_PITCH, b.y_pri, b.y_sec, b.dir, P.damping, P.bdmin8);
-            ((pixel *)(dbase + (int64_t)(y0 + r) * dst.stride[0]))[x0 + c] = (pixel)v;
-        }
-    }
-    // ---- chroma
+    cdef_filter_plane<BD, 8>(tile, blk, (uint8_t *)dst.data[0], dst.stride[0], x0, y0, tw, th, 3, false, P.damping, P.bdmin8,
+                             nbx, nby, sbx * 8, sby * 8);
     for (int p = 1; p < P.n_planes; p++) {
         __syncthreads();
         const int cx0 = x0 >> P.ss_hor, cy0 = y0 >> P.ss_ver;
         const int ctw = tw >> P.ss_hor, cth = th >> P.ss_ver, cfw = fw >> P.ss_hor, cfh = fh >> P.ss_ver;
-        cdef_stage_tile<BD>(tile, (const uint8_t *)src.data[p], src.stride[p], cx0, cy0, ctw, cth, cfw, cfh);
+        cdef_stage2<BD>(tile, (const uint8_t *)src.data[p], src.stride[p], cx0, cy0, ctw, cth, cfw, cfh);
         __syncthreads();
-        uint8_t *dbase = (uint8_t *)dst.data[p];
-        for (int i = threadIdx.x; i < cth * ctw; i += 256) {
-            const int r = i / ctw, c = i - r * ctw;
-            const CdefBlk b = blk[(r >> (3 - P.ss_ver)) * 8 + (c >> (3 - P.ss_hor))];
-            const int16_t *t = tile + (2 + r) * CDEF_PITCH + 2 + c;
-            int v = t[0];
-            if (b.do_uv) v = cdef_filter_px(t, CDEF_PITCH, b.uv_pri, b.uv_sec, b.uvdir, P.damping - 1, P.bdmin8);
-            ((pixel *)(dbase + (int64_t)(cy0 + r) * dst.stride[p]))[cx0 + c] = (pixel)v;
-        }
+        if (P.ss_hor)
+            cdef_filter_plane<BD, 4>(tile, blk, (uint8_t *)dst.data[p], dst.stride[p], cx0, cy0, ctw, cth, 3 - P.ss_ver, true,
+                                     P.damping - 1, P.bdmin8, nbx, nby, sbx * 8, sby * 8);
+        else
+            cdef_filter_plane<BD, 8>(tile, blk, (uint8_t *)dst.data[p], dst.stride[p], cx0, cy0, ctw, cth, 3, true,
+                                     P.damping - 1, P.bdmin8, nbx, nby, sbx * 8, sby * 8);
     }
 }
 
@@ -312,10 +483,18 @@ __global__ void cdef_fb_kernel(uint8_t *dst, int64_t stride, const uint8_t *left
 }
 
 int cdef_frame_launch(const Rb200Planes &src, const Rb200Planes &dst, const CdefFrameParams &P,
-                      const Rb200Av1Filter *masks, int bdmax, cudaStream_t st) {
+                      const Rb200Av1Filter *masks, void *blk_scratch, int bdmax, cudaStream_t st) {
+    const int nbx = P.bw >> 1, nby = P.bh >> 1;
+    CdefBlk *blocks = (CdefBlk *)blk_scratch;
+    dim3 g1((nbx + 31) / 32, (nby + 3) / 4), b1(32, 4);
     dim3 grid((P.bw * 4 + 63) / 64, (P.bh * 4 + 63) / 64);
-    if (bdmax > 255) cdef_frame_kernel<BD16><<<grid, 256, 0, st>>>(src, dst, P, masks, bdmax);
-    else cdef_frame_kernel<BD8><<<grid, 256, 0, st>>>(src, dst, P, masks, bdmax);
+    if (bdmax > 255) {
+        cdef_dir_frame_kernel<BD16><<<g1, b1, 0, st>>>(src, P, masks, blocks, nbx, nby);
+        cdef_filter_frame_kernel<BD16><<<grid, 256, 0, st>>>(src, dst, P, blocks, nbx, nby);
+    } else {
+        cdef_dir_frame_kernel<BD8><<<g1, b1, 0, st>>>(src, P, masks, blocks, nbx, nby);
+        cdef_filter_frame_kernel<BD8><<<grid, 256, 0, st>>>(src, dst, P, blocks, nbx, nby);
+    }
     RB_LAUNCH_CHECK();
     return 0;
 }

@@ -41,6 +41,7 @@ struct Rb200Frame {
     uint8_t (*h_lvl)[4], (*d_lvl)[4];
     Rb200Av1FilterLUT *h_lut, *d_lut;
     Rb200Av1Restoration *h_lr, *d_lr;
+    void *d_cdef_blk;   // per-8x8 CDEF decisions (direction, strengths), device only
     size_t n_masks, n_lvl;
     int launches;
     // film grain on output (src/fg_apply.rs): parameters, LUTs, display planes
@@ -138,6 +139,7 @@ extern "C" int rb200_frame_create(Rb200Frame **out, const Rb200FrameHeader *hdr,
     if (!r) r = alloc_pair((uint8_t **)&f->h_lvl, (uint8_t **)&f->d_lvl, f->n_lvl * 4);
     if (!r) r = alloc_pair(&f->h_lut, &f->d_lut, 1);
     if (!r) r = alloc_pair(&f->h_lr, &f->d_lr, f->n_masks);
+    if (!r) { e = cudaMalloc(&f->d_cdef_blk, (size_t)(g.bw >> 1) * (g.bh >> 1) * 8 + 64); if (e != cudaSuccess) r = cuda_fail(e, "cudaMalloc", __FILE__, __LINE__); }
     if (!r) { e = cudaStreamSynchronize(f->stream); if (e != cudaSuccess) r = cuda_fail(e, "sync", __FILE__, __LINE__); }
     if (r) { rb200_frame_destroy(f); return r; }
     f->out = f->planes[0];
@@ -168,6 +170,7 @@ extern "C" int rb200_frame_destroy(Rb200Frame *f) {
     if (f->d_lut) cudaFree(f->d_lut);
     if (f->h_lr) cudaFreeHost(f->h_lr);
     if (f->d_lr) cudaFree(f->d_lr);
+    if (f->d_cdef_blk) cudaFree(f->d_cdef_blk);
     if (f->own_stream) cudaStreamDestroy(f->own_stream);
     delete f;
     return 0;
@@ -459,8 +462,8 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         P.n_planes = g.n_planes; P.bdmin8 = h.bpc - 8; P.damping = h.cdef_damping + P.bdmin8;
         for (int i = 0; i < 8; i++) { P.y_strength[i] = h.cdef_y_strength[i]; P.uv_strength[i] = h.cdef_uv_strength[i]; }
         P.layout_422 = h.layout == RB200_LAYOUT_I422;
-        if ((r = cdef_frame_launch(f->planes[0], f->planes[1], P, f->d_masks, f->bdmax, st))) return r;
-        f->launches++;
+        if ((r = cdef_frame_launch(f->planes[0], f->planes[1], P, f->d_masks, f->d_cdef_blk, f->bdmax, st))) return r;
+        f->launches += 2;
         f->out = f->planes[1];
     }
     MARK(5);
