@@ -127,25 +127,107 @@ __device__ __forceinline__ int lf_mask_idx(const Rb200Av1Filter *__restrict__ ma
     return -1;
 }
 
-// DIR 0: column edges (filter across x), thread = (x4, y).  DIR 1: row edges, thread = (x, y4).
-template <typename BD, int DIR>
-__global__ void __launch_bounds__(256)
-deblock_plane_kernel(uint8_t *plane, int64_t stride, LfGeom g, const Rb200Av1Filter *__restrict__ masks,
-                     const uint8_t (*__restrict__ lvl)[4], const Rb200Av1FilterLUT *__restrict__ lut, int bdmax) {
-    using pixel = typename BD::pixel;
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int x4, y4, x, y;
-    if (DIR == 0) {
-        const int64_t n = (int64_t)g.w4 * g.h4 * 4;
-        if (gid >= n) return;
-        x4 = (int)(gid % g.w4); y = (int)(gid / g.w4); y4 = y >> 2; x = x4 * 4;
-        if (x4 == 0) return;  // have_left
-    } else {
-        const int64_t n = (int64_t)g.w4 * 4 * g.h4;
-        if (gid >= n) return;
-        x = (int)(gid % (g.w4 * 4)); y4 = (int)(gid / (g.w4 * 4)); x4 = x >> 2; y = y4 * 4;
-        if (y4 == 0) return;  // have_top
+// Register form of the edge filter for one line: P[i] = p_i, Q[i] = q_i (i = 0 next to the edge).
+// Returns how many samples on each side may have changed (0, 1, 2, 3 or 6).  Same arithmetic as
+// lf_line / src/loopfilter_tmpl.c:48-160.
+__device__ __forceinline__ int lf_line_regs(int *P, int *Q, int E, int I, int H, const int wd, const int bdmin8,
+                                            const int bdmax) {
+    auto A = [](int v) { return v < 0 ? -v : v; };
+    const int F = 1 << bdmin8;
+    const int p0 = P[0], p1 = P[1], q0 = Q[0], q1 = Q[1];
+    bool fm = A(p1 - p0) <= I && A(q1 - q0) <= I && A(p0 - q0) * 2 + (A(p1 - q1) >> 1) <= E;
+    if (wd > 4) {
+        fm = fm && A(P[2] - p1) <= I && A(Q[2] - q1) <= I;
+        if (wd > 6) fm = fm && A(P[3] - P[2]) <= I && A(Q[3] - Q[2]) <= I;
     }
+    if (!fm) return 0;
+    bool flat8out = false, flat8in = false;
+    if (wd >= 16)
+        flat8out = A(P[6] - p0) <= F && A(P[5] - p0) <= F && A(P[4] - p0) <= F && A(Q[4] - q0) <= F && A(Q[5] - q0) <= F &&
+                   A(Q[6] - q0) <= F;
+    if (wd >= 6) flat8in = A(P[2] - p0) <= F && A(p1 - p0) <= F && A(q1 - q0) <= F && A(Q[2] - q0) <= F;
+    if (wd >= 8) flat8in = flat8in && A(P[3] - p0) <= F && A(Q[3] - q0) <= F;
+    if (wd >= 16 && flat8out && flat8in) {
+        const int p6 = P[6], p5 = P[5], p4 = P[4], p3 = P[3], p2 = P[2], q2 = Q[2], q3 = Q[3], q4 = Q[4], q5 = Q[5], q6 = Q[6];
+        P[5] = (p6 + p6 + p6 + p6 + p6 + p6 * 2 + p5 * 2 + p4 * 2 + p3 + p2 + p1 + p0 + q0 + 8) >> 4;
+        P[4] = (p6 + p6 + p6 + p6 + p6 + p5 * 2 + p4 * 2 + p3 * 2 + p2 + p1 + p0 + q0 + q1 + 8) >> 4;
+        P[3] = (p6 + p6 + p6 + p6 + p5 + p4 * 2 + p3 * 2 + p2 * 2 + p1 + p0 + q0 + q1 + q2 + 8) >> 4;
+        P[2] = (p6 + p6 + p6 + p5 + p4 + p3 * 2 + p2 * 2 + p1 * 2 + p0 + q0 + q1 + q2 + q3 + 8) >> 4;
+        P[1] = (p6 + p6 + p5 + p4 + p3 + p2 * 2 + p1 * 2 + p0 * 2 + q0 + q1 + q2 + q3 + q4 + 8) >> 4;
+        P[0] = (p6 + p5 + p4 + p3 + p2 + p1 * 2 + p0 * 2 + q0 * 2 + q1 + q2 + q3 + q4 + q5 + 8) >> 4;
+        Q[0] = (p5 + p4 + p3 + p2 + p1 + p0 * 2 + q0 * 2 + q1 * 2 + q2 + q3 + q4 + q5 + q6 + 8) >> 4;
+        Q[1] = (p4 + p3 + p2 + p1 + p0 + q0 * 2 + q1 * 2 + q2 * 2 + q3 + q4 + q5 + q6 + q6 + 8) >> 4;
+        Q[2] = (p3 + p2 + p1 + p0 + q0 + q1 * 2 + q2 * 2 + q3 * 2 + q4 + q5 + q6 + q6 + q6 + 8) >> 4;
+        Q[3] = (p2 + p1 + p0 + q0 + q1 + q2 * 2 + q3 * 2 + q4 * 2 + q5 + q6 + q6 + q6 + q6 + 8) >> 4;
+        Q[4] = (p1 + p0 + q0 + q1 + q2 + q3 * 2 + q4 * 2 + q5 * 2 + q6 + q6 + q6 + q6 + q6 + 8) >> 4;
+        Q[5] = (p0 + q0 + q1 + q2 + q3 + q4 * 2 + q5 * 2 + q6 * 2 + q6 + q6 + q6 + q6 + q6 + 8) >> 4;
+        return 6;
+    }
+    if (wd >= 8 && flat8in) {
+        const int p3 = P[3], p2 = P[2], q2 = Q[2], q3 = Q[3];
+        P[2] = (p3 + p3 + p3 + 2 * p2 + p1 + p0 + q0 + 4) >> 3;
+        P[1] = (p3 + p3 + p2 + 2 * p1 + p0 + q0 + q1 + 4) >> 3;
+        P[0] = (p3 + p2 + p1 + 2 * p0 + q0 + q1 + q2 + 4) >> 3;
+        Q[0] = (p2 + p1 + p0 + 2 * q0 + q1 + q2 + q3 + 4) >> 3;
+        Q[1] = (p1 + p0 + q0 + 2 * q1 + q2 + q3 + q3 + 4) >> 3;
+        Q[2] = (p0 + q0 + q1 + 2 * q2 + q3 + q3 + q3 + 4) >> 3;
+        return 3;
+    }
+    if (wd == 6 && flat8in) {
+        const int p2 = P[2], q2 = Q[2];
+        P[1] = (p2 + 2 * p2 + 2 * p1 + 2 * p0 + q0 + 4) >> 3;
+        P[0] = (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3;
+        Q[0] = (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3;
+        Q[1] = (p0 + 2 * q0 + 2 * q1 + 2 * q2 + q2 + 4) >> 3;
+        return 2;
+    }
+    const bool hev = A(p1 - p0) > H || A(q1 - q0) > H;
+    const int lo = -128 * (1 << bdmin8), hi = 128 * (1 << bdmin8) - 1;
+    if (hev) {
+        int f = iclip(p1 - q1, lo, hi);
+        f = iclip(3 * (q0 - p0) + f, lo, hi);
+        const int f1 = imin(f + 4, hi) >> 3, f2 = imin(f + 3, hi) >> 3;
+        P[0] = iclip(p0 + f2, 0, bdmax);
+        Q[0] = iclip(q0 - f1, 0, bdmax);
+        return 1;
+    }
+    int f = iclip(3 * (q0 - p0), lo, hi);
+    const int f1 = imin(f + 4, hi) >> 3, f2 = imin(f + 3, hi) >> 3;
+    P[0] = iclip(p0 + f2, 0, bdmax);
+    Q[0] = iclip(q0 - f1, 0, bdmax);
+    f = (f1 + 1) >> 1;
+    P[1] = iclip(p1 + f, 0, bdmax);
+    Q[1] = iclip(q1 - f, 0, bdmax);
+    return 2;
+}
+
+struct LfPlaneSet {
+    uint8_t *plane[3];
+    int64_t stride[3];
+    LfGeom g[3];
+    int unit_start[4];   // prefix sums of w4 * h4 over the planes in this launch
+    int n_planes;
+};
+
+// One thread per 4-pixel edge unit, 4 lines each, all planes of a pass in one launch.
+// DIR 0: column edges -- per line the thread loads the 4/8/16 pixels straddling the edge with
+// aligned vector loads and writes back only what the filter may modify.
+// DIR 1: row edges -- the thread owns 4 adjacent columns; every row of the stencil is one
+// aligned 4-pixel load, coalesced across the warp.
+template <typename BD, int DIR>
+__global__ void __launch_bounds__(128)
+deblock_units_kernel(LfPlaneSet S, const Rb200Av1Filter *__restrict__ masks, const uint8_t (*__restrict__ lvl)[4],
+                     const Rb200Av1FilterLUT *__restrict__ lut, int bdmax) {
+    using pixel = typename BD::pixel;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= S.unit_start[S.n_planes]) return;
+    const int pi = (S.n_planes > 1 && gid >= S.unit_start[1]) ? ((S.n_planes > 2 && gid >= S.unit_start[2]) ? 2 : 1) : 0;
+    const LfGeom g = pi == 0 ? S.g[0] : (pi == 1 ? S.g[1] : S.g[2]);
+    uint8_t *plane = pi == 0 ? S.plane[0] : (pi == 1 ? S.plane[1] : S.plane[2]);
+    const int64_t stride = pi == 0 ? S.stride[0] : (pi == 1 ? S.stride[1] : S.stride[2]);
+    const int u = gid - (pi == 0 ? 0 : (pi == 1 ? S.unit_start[1] : S.unit_start[2]));
+    const int y4 = u / g.w4, x4 = u - y4 * g.w4;
+    if (DIR == 0 ? x4 == 0 : y4 == 0) return;  // have_left / have_top
     const int idx = lf_mask_idx(masks, g, DIR, x4, y4);
     if (idx < 0) return;
     const uint8_t(*l)[4] = lvl + (int64_t)y4 * g.b4_stride + x4;
@@ -155,9 +237,53 @@ deblock_plane_kernel(uint8_t *plane, int64_t stride, LfGeom g, const Rb200Av1Fil
     const int bdmin8 = BD::hbd ? bpc_from_max(bdmax) - 8 : 0;
     const int H = (L >> 4) << bdmin8, E = (int)lut->e[L] << bdmin8, I = (int)lut->i[L] << bdmin8;
     const int wd = g.uv ? 4 + 2 * idx : 4 << idx;
+    const int ng = wd == 16 ? 2 : 1;           // 4-pixel groups loaded on each side of the edge
     const int64_t ps = stride / (int64_t)sizeof(pixel);
-    pixel *p = (pixel *)plane + (int64_t)y * ps + x;
-    lf_line<BD>(p, DIR == 0 ? 1 : ps, E, I, H, wd, bdmin8, bdmax);
+    pixel *base = (pixel *)plane + (int64_t)(y4 * 4) * ps + x4 * 4;   // q0 of line 0
+    auto load4 = [](const pixel *p, int *v) {
+        if (BD::hbd) { const uint2 q = *(const uint2 *)p; v[0] = q.x & 0xffff; v[1] = q.x >> 16; v[2] = q.y & 0xffff; v[3] = q.y >> 16; }
+        else { const unsigned q = *(const unsigned *)p; v[0] = q & 0xff; v[1] = (q >> 8) & 0xff; v[2] = (q >> 16) & 0xff; v[3] = q >> 24; }
+    };
+    if (DIR == 0) {
+#pragma unroll 1
+        for (int line = 0; line < 4; line++) {
+            pixel *p = base + (int64_t)line * ps;
+            int P[8], Q[8], t[4];
+            load4(p - 4, t); P[0] = t[3]; P[1] = t[2]; P[2] = t[1]; P[3] = t[0];
+            load4(p, Q);
+            if (ng == 2) { load4(p - 8, t); P[4] = t[3]; P[5] = t[2]; P[6] = t[1]; P[7] = t[0]; load4(p + 4, Q + 4); }
+            const int n = lf_line_regs(P, Q, E, I, H, wd, bdmin8, bdmax);
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+                if (i < n) { p[-1 - i] = (pixel)P[i]; p[i] = (pixel)Q[i]; }
+        }
+    } else {
+        // rows y-4ng .. y+4ng-1, 4 columns each, kept packed; column c is unpacked, filtered, re-packed
+        int rows[16][4];
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            const int rel = r - 8;   // row offset from the edge
+            if (rel >= -4 * ng && rel < 4 * ng) load4(base + (int64_t)rel * ps, rows[r]);
+        }
+        int nmax = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            int P[8], Q[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) { P[i] = rows[7 - i][c]; Q[i] = rows[8 + i][c]; }
+            const int n = lf_line_regs(P, Q, E, I, H, wd, bdmin8, bdmax);
+            nmax = imax(nmax, n);
+#pragma unroll
+            for (int i = 0; i < 6; i++) { rows[7 - i][c] = P[i]; rows[8 + i][c] = Q[i]; }
+        }
+        auto store4 = [](pixel *p, const int *v) {
+            if (BD::hbd) *(uint2 *)p = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
+            else *(unsigned *)p = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+        };
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+            if (i < nmax) { store4(base + (int64_t)(-1 - i) * ps, rows[7 - i]); store4(base + (int64_t)i * ps, rows[8 + i]); }
+    }
 }
 
 // Per-call form of loop_filter_{h,v}_sb128{y,uv}: explicit mask words and level pointer.
@@ -184,29 +310,35 @@ __global__ void lpf_sb_kernel(uint8_t *dst, int64_t stride, int uv, int dir, uin
     else lf_line<BD>(p + u * 4 + line, ps, E, I, H, wd, bdmin8, bdmax);
 }
 
-// Whole-frame deblock: column edges of every plane, then row edges of every plane.
+// Whole-frame deblock: column edges of every plane (one launch), then row edges (one launch).
 int deblock_frame_launch(const Rb200Planes &pl, int n_planes, int w4, int h4, int sb128w, int b4_stride, int ss_hor,
                          int ss_ver, bool do_uv, const Rb200Av1Filter *masks, const uint8_t (*lvl)[4],
                          const Rb200Av1FilterLUT *lut, int bdmax, cudaStream_t st, int *launches) {
     for (int dir = 0; dir < 2; dir++) {
+        LfPlaneSet S = {};
+        int n = 0, total = 0;
         for (int p = 0; p < n_planes; p++) {
             if (p && !do_uv) continue;
-            LfGeom g;
+            LfGeom &g = S.g[n];
             g.uv = p ? 1 : 0;
             g.ss_hor = p ? ss_hor : 0; g.ss_ver = p ? ss_ver : 0;
             g.w4 = (w4 + g.ss_hor) >> g.ss_hor; g.h4 = (h4 + g.ss_ver) >> g.ss_ver;
             g.sb128w = sb128w; g.b4_stride = b4_stride;
             g.lvl_idx = p ? 1 + p : dir;
-            const int64_t n = (int64_t)g.w4 * g.h4 * 4;
-            const int grid = (int)((n + 255) / 256);
-            uint8_t *base = (uint8_t *)pl.data[p];
-            const int64_t stride = pl.stride[p];
-#define L(BD, D) deblock_plane_kernel<BD, D><<<grid, 256, 0, st>>>(base, stride, g, masks, lvl, lut, bdmax)
-            if (bdmax > 255) { if (dir) L(BD16, 1); else L(BD16, 0); } else { if (dir) L(BD8, 1); else L(BD8, 0); }
-#undef L
-            RB_LAUNCH_CHECK();
-            if (launches) ++*launches;
+            S.plane[n] = (uint8_t *)pl.data[p]; S.stride[n] = pl.stride[p];
+            S.unit_start[n] = total;
+            total += g.w4 * g.h4;
+            n++;
         }
+        S.unit_start[n] = total;
+        for (int k = n + 1; k < 4; k++) S.unit_start[k] = total;
+        S.n_planes = n;
+        const int grid = (total + 127) / 128;
+#define L(BD, D) deblock_units_kernel<BD, D><<<grid, 128, 0, st>>>(S, masks, lvl, lut, bdmax)
+        if (bdmax > 255) { if (dir) L(BD16, 1); else L(BD16, 0); } else { if (dir) L(BD8, 1); else L(BD8, 0); }
+#undef L
+        RB_LAUNCH_CHECK();
+        if (launches) ++*launches;
     }
     return 0;
 }
