@@ -255,19 +255,37 @@ __device__ __forceinline__ void cdef_stage2(int16_t *tile, const uint8_t *plane,
                                             int th, int fw, int fh) {
     using pixel = typename BD::pixel;
     const int groups = (tw + 8) >> 2, rows = th + 4;
-    for (int i = threadIdx.x; i < rows * groups; i += blockDim.x) {
-        const int r = i / groups, g = i - r * groups;
-        const int y = y0 + r - 2, x = x0 - 4 + g * 4;
-        int v[4] = {CDEF_SENTINEL, CDEF_SENTINEL, CDEF_SENTINEL, CDEF_SENTINEL};
-        if (y >= 0 && y < fh && x >= 0 && x < fw) {  // fw is a multiple of 8: a group is inside or outside as a whole
-            const uint8_t *p = plane + (int64_t)y * stride + (int64_t)x * sizeof(pixel);
-            if (BD::hbd) {
-                const uint2 q = *(const uint2 *)p;
-                v[0] = q.x & 0xffff; v[1] = q.x >> 16; v[2] = q.y & 0xffff; v[3] = q.y >> 16;
+    constexpr int NIT = (68 * 18 + 255) / 256;   // 256 threads
+    uint2 q[NIT];
+    // loads first, then stores: NIT loads in flight per thread
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+        const int i = threadIdx.x + it * 256;
+        q[it] = make_uint2(0, 0);
+        if (i < rows * groups) {
+            const int r = i / groups, g = i - r * groups;
+            const int y = y0 + r - 2, x = x0 - 4 + g * 4;
+            if (y >= 0 && y < fh && x >= 0 && x < fw) {  // fw is a multiple of 8: a group is inside or outside as a whole
+                const uint8_t *p = plane + (int64_t)y * stride + (int64_t)x * sizeof(pixel);
+                if (BD::hbd) q[it] = *(const uint2 *)p;
+                else q[it].x = *(const unsigned *)p;
             } else {
-                const unsigned q = *(const unsigned *)p;
-                v[0] = q & 0xff; v[1] = (q >> 8) & 0xff; v[2] = (q >> 16) & 0xff; v[3] = q >> 24;
+                q[it].y = 0xffffffffu;   // marks "outside the frame" (a pixel never has the top bit set)
             }
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+        const int i = threadIdx.x + it * 256;
+        if (i >= rows * groups) continue;
+        const int r = i / groups, g = i - r * groups;
+        int v[4];
+        if (q[it].y == 0xffffffffu) {
+            v[0] = v[1] = v[2] = v[3] = CDEF_SENTINEL;
+        } else if (BD::hbd) {
+            v[0] = q[it].x & 0xffff; v[1] = q[it].x >> 16; v[2] = q[it].y & 0xffff; v[3] = q[it].y >> 16;
+        } else {
+            v[0] = q[it].x & 0xff; v[1] = (q[it].x >> 8) & 0xff; v[2] = (q[it].x >> 16) & 0xff; v[3] = q[it].x >> 24;
         }
         int16_t *a = tile + r * CDEF_TP + g * 4;
         // the odd word pitch makes rows only 4-byte aligned

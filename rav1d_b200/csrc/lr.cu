@@ -185,13 +185,237 @@ __device__ void lr_sgr_tile(LrSmem &sm, int tw, int th, int kind, unsigned s0, u
 }
 
 
+// ---------------------------------------------------------------- frame level
+// Layout of the frame kernel's shared memory.  Window column e holds picture column
+// x0 - 3 + e, so that output column i reads its 7 Wiener taps at e = i .. i + 6 and groups of
+// four outputs start on 8-byte boundaries; A/B column c holds box column i = c - 1.
+constexpr int L2_WP = 40;                 // window pitch, pixels
+constexpr int L2_WROWS = LR_TH + 6;       // 70
+constexpr int L2_AP = 36;                 // A/B pitch, ints
+constexpr int L2_AROWS = LR_TH + 2;       // 66
+
+struct Lr2Smem {
+    __align__(16) uint16_t win[L2_WROWS * L2_WP];
+    union {
+        __align__(16) uint16_t hor[L2_WROWS * LR_TW];
+        struct { __align__(16) int32_t A[L2_AROWS * L2_AP]; __align__(16) int32_t B[L2_AROWS * L2_AP]; } s;
+    } u;
+};
+
+__device__ __forceinline__ void lr2_unpack8(const uint16_t *p, int *v) {  // 8 pixels from an 8-byte aligned address
+    const uint2 a = *(const uint2 *)p, b = *(const uint2 *)(p + 4);
+    v[0] = a.x & 0xffff; v[1] = a.x >> 16; v[2] = a.y & 0xffff; v[3] = a.y >> 16;
+    v[4] = b.x & 0xffff; v[5] = b.x >> 16; v[6] = b.y & 0xffff; v[7] = b.y >> 16;
+}
+
+template <typename BD>
+__device__ __forceinline__ void lr2_store4(typename BD::pixel *o, const int *v, int n) {
+    if (n >= 4) {
+        if (BD::hbd) *(uint2 *)o = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
+        else *(unsigned *)o = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+    } else {
+        for (int i = 0; i < n; i++) o[i] = (typename BD::pixel)v[i];
+    }
+}
+
+// Wiener: each thread produces 4 horizontally adjacent samples per pass from registers.
+template <typename BD>
+__device__ void lr2_wiener(Lr2Smem &sm, int tw, int th, const int16_t *fh, const int16_t *fv, int bdmax,
+                           typename BD::pixel *o, int64_t ps) {
+    const int bitdepth = BD::hbd ? bpc_from_max(bdmax) : 8;
+    const int rbh = 3 + (bitdepth == 12) * 2, rbv = 11 - (bitdepth == 12) * 2;
+    const int clip_limit = 1 << (bitdepth + 1 + 7 - rbh);
+    int F[7];
+#pragma unroll
+    for (int k = 0; k < 7; k++) F[k] = fh[k];
+    for (int t = threadIdx.x; t < (th + 6) * 8; t += 256) {
+        const int g = t & 7, r = t >> 3;
+        int px[10];
+        lr2_unpack8(sm.win + r * L2_WP + 4 * g, px);
+        const unsigned last = *(const unsigned *)(sm.win + r * L2_WP + 4 * g + 8);
+        px[8] = last & 0xffff; px[9] = last >> 16;
+        unsigned outv[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int sum = 1 << (bitdepth + 6);
+#pragma unroll
+            for (int k = 0; k < 7; k++) sum += px[j + k] * F[k];
+            outv[j] = (unsigned)iclip((sum + (1 << (rbh - 1))) >> rbh, 0, clip_limit - 1);
+        }
+        *(uint2 *)(sm.u.hor + r * LR_TW + 4 * g) = make_uint2(outv[0] | (outv[1] << 16), outv[2] | (outv[3] << 16));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 7; k++) F[k] = fv[k];
+    {
+        const int g = threadIdx.x & 7, rp = threadIdx.x >> 3;   // 8 column groups x 32 row pairs
+        const int r0 = 2 * rp;
+        if (r0 < th && 4 * g < tw) {
+            int hv[8][4];
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const uint2 q = *(const uint2 *)(sm.u.hor + (r0 + r) * LR_TW + 4 * g);
+                hv[r][0] = q.x & 0xffff; hv[r][1] = q.x >> 16; hv[r][2] = q.y & 0xffff; hv[r][3] = q.y >> 16;
+            }
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                if (r0 + rr >= th) break;
+                int outv[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    int sum = -(1 << (bitdepth + (rbv - 1)));
+#pragma unroll
+                    for (int k = 0; k < 7; k++) sum += hv[rr + k][j] * F[k];
+                    outv[j] = iclip((sum + (1 << (rbv - 1))) >> rbv, 0, bdmax);
+                }
+                lr2_store4<BD>(o + (int64_t)(r0 + rr) * ps + 4 * g, outv, tw - 4 * g);
+            }
+        }
+    }
+}
+
+// Box sums + the a/b -> (x, x * sum * one_by_x) transform for four horizontally adjacent boxes.
+// N = 9: every row j in [-1, th]; N = 25: rows j = -1, 1, 3, ...   src/looprestoration_tmpl.c:282-373
+template <typename BD, int N>
+__device__ void lr2_sgr_ab(Lr2Smem &sm, int th, unsigned s, int bdmin8) {
+    constexpr int RAD = N == 25 ? 2 : 1, STEP = N == 25 ? 2 : 1;
+    constexpr unsigned one_by_x = N == 25 ? 164 : 455;
+    const int rows = (th + 2 + STEP - 1) / STEP;
+    for (int t = threadIdx.x; t < rows * 9; t += 256) {
+        const int jr = t / 9, k = t - jr * 9;
+        const int j = jr * STEP - 1;
+        int cs[8], cq[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) { cs[c] = 0; cq[c] = 0; }
+#pragma unroll
+        for (int dy = -RAD; dy <= RAD; dy++) {
+            int px[8];
+            lr2_unpack8(sm.win + (j + 3 + dy) * L2_WP + 4 * k, px);
+#pragma unroll
+            for (int c = (N == 25 ? 0 : 1); c < (N == 25 ? 8 : 7); c++) { cs[c] += px[c]; cq[c] += px[c] * px[c]; }
+        }
+        int av[4], bv[4];
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            int sum, sumsq;
+            if (N == 25) { sum = cs[m] + cs[m + 1] + cs[m + 2] + cs[m + 3] + cs[m + 4]; sumsq = cq[m] + cq[m + 1] + cq[m + 2] + cq[m + 3] + cq[m + 4]; }
+            else { sum = cs[m + 1] + cs[m + 2] + cs[m + 3]; sumsq = cq[m + 1] + cq[m + 2] + cq[m + 3]; }
+            const int a = (sumsq + ((1 << (2 * bdmin8)) >> 1)) >> (2 * bdmin8);
+            const int b = (sum + ((1 << bdmin8) >> 1)) >> bdmin8;
+            const unsigned p = (unsigned)imax(a * N - b * b, 0);
+            const unsigned z = (p * s + (1u << 19)) >> 20;
+            const unsigned x = tab::k_sgr_x_by_x[z < 255 ? z : 255];
+            av[m] = (int)((x * (unsigned)sum * one_by_x + (1u << 11)) >> 12);
+            bv[m] = (int)x;
+        }
+        *(int4 *)(sm.u.s.A + (j + 1) * L2_AP + 4 * k) = make_int4(av[0], av[1], av[2], av[3]);
+        *(int4 *)(sm.u.s.B + (j + 1) * L2_AP + 4 * k) = make_int4(bv[0], bv[1], bv[2], bv[3]);
+    }
+}
+
+// acc[m] += wgt * (weighted-neighbourhood output) for the 4 pixels (j, 4g .. 4g+3).
+template <typename BD, int N>
+__device__ __forceinline__ void lr2_sgr_out4(const Lr2Smem &sm, int j, int g, int wgt, const int *src, int *acc) {
+    auto row6 = [&](const int32_t *base, int row, int *v) {   // columns i = 4g-1 .. 4g+4 of A/B row `row`
+        const int32_t *p = base + (row + 1) * L2_AP + 4 * g;
+        const int4 q = *(const int4 *)p; const int2 q2 = *(const int2 *)(p + 4);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; v[4] = q2.x; v[5] = q2.y;
+    };
+    int a[4], b[4], sh, rnd;
+    if (N == 9) {
+        int au[6], am[6], ad[6];
+        row6(sm.u.s.B, j - 1, au); row6(sm.u.s.B, j, am); row6(sm.u.s.B, j + 1, ad);
+#pragma unroll
+        for (int c = 0; c < 6; c++) au[c] += am[c] + ad[c];
+#pragma unroll
+        for (int m = 0; m < 4; m++) a[m] = 3 * (au[m] + au[m + 1] + au[m + 2]) + am[m] + au[m + 1] + am[m + 2];
+        row6(sm.u.s.A, j - 1, au); row6(sm.u.s.A, j, am); row6(sm.u.s.A, j + 1, ad);
+#pragma unroll
+        for (int c = 0; c < 6; c++) au[c] += am[c] + ad[c];
+#pragma unroll
+        for (int m = 0; m < 4; m++) b[m] = 3 * (au[m] + au[m + 1] + au[m + 2]) + am[m] + au[m + 1] + am[m + 2];
+        sh = 9; rnd = 1 << 8;
+    } else if (!(j & 1)) {
+        int u[6], d[6];
+        row6(sm.u.s.B, j - 1, u); row6(sm.u.s.B, j + 1, d);
+#pragma unroll
+        for (int c = 0; c < 6; c++) u[c] += d[c];
+#pragma unroll
+        for (int m = 0; m < 4; m++) a[m] = u[m + 1] * 6 + (u[m] + u[m + 2]) * 5;
+        row6(sm.u.s.A, j - 1, u); row6(sm.u.s.A, j + 1, d);
+#pragma unroll
+        for (int c = 0; c < 6; c++) u[c] += d[c];
+#pragma unroll
+        for (int m = 0; m < 4; m++) b[m] = u[m + 1] * 6 + (u[m] + u[m + 2]) * 5;
+        sh = 9; rnd = 1 << 8;
+    } else {
+        int u[6];
+        row6(sm.u.s.B, j, u);
+#pragma unroll
+        for (int m = 0; m < 4; m++) a[m] = u[m + 1] * 6 + (u[m] + u[m + 2]) * 5;
+        row6(sm.u.s.A, j, u);
+#pragma unroll
+        for (int m = 0; m < 4; m++) b[m] = u[m + 1] * 6 + (u[m] + u[m + 2]) * 5;
+        sh = 8; rnd = 1 << 7;
+    }
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const int v = (b[m] - a[m] * src[m] + rnd) >> sh;
+        acc[m] += wgt * (BD::hbd ? v : (int)(int16_t)v);
+    }
+}
+
+// kind: 2 5x5, 3 3x3, 4 mix.  src/looprestoration_tmpl.c:446-520
+template <typename BD>
+__device__ void lr2_sgr(Lr2Smem &sm, int tw, int th, int kind, unsigned s0, unsigned s1, int w0, int w1, int bdmax,
+                        typename BD::pixel *o, int64_t ps) {
+    const int bdmin8 = BD::hbd ? bpc_from_max(bdmax) - 8 : 0;
+    const int g = threadIdx.x & 7, r_lo = threadIdx.x >> 3;   // rows r_lo and r_lo + 32
+    int acc[2][4], src[2][4];
+#pragma unroll
+    for (int it = 0; it < 2; it++) {
+        const int r = r_lo + 32 * it;
+#pragma unroll
+        for (int m = 0; m < 4; m++) { acc[it][m] = 0; src[it][m] = sm.win[(r + 3) * L2_WP + 3 + 4 * g + m]; }
+    }
+    if (kind != 3) {
+        lr2_sgr_ab<BD, 25>(sm, th, s0, bdmin8);
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < 2; it++) {
+            const int r = r_lo + 32 * it;
+            if (r < th && 4 * g < tw) lr2_sgr_out4<BD, 25>(sm, r, g, w0, src[it], acc[it]);
+        }
+        __syncthreads();
+    }
+    if (kind != 2) {
+        lr2_sgr_ab<BD, 9>(sm, th, s1, bdmin8);
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < 2; it++) {
+            const int r = r_lo + 32 * it;
+            if (r < th && 4 * g < tw) lr2_sgr_out4<BD, 9>(sm, r, g, w1, src[it], acc[it]);
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < 2; it++) {
+        const int r = r_lo + 32 * it;
+        if (r < th && 4 * g < tw) {
+            int outv[4];
+#pragma unroll
+            for (int m = 0; m < 4; m++) outv[m] = iclip(src[it][m] + ((acc[it][m] + (1 << 10)) >> 11), 0, bdmax);
+            lr2_store4<BD>(o + (int64_t)r * ps + 4 * g, outv, tw - 4 * g);
+        }
+    }
+}
+
 // cdef: CDEF output (the picture being restored); dbl: deblocked pre-CDEF picture; out: restored picture
 template <typename BD>
 __global__ void __launch_bounds__(256)
 lr_frame_kernel(const uint8_t *__restrict__ cdef, const uint8_t *__restrict__ dbl, uint8_t *__restrict__ outp,
                 int64_t stride, LrFrameParams P, const Rb200Av1Restoration *__restrict__ lrm, int bdmax) {
     using pixel = typename BD::pixel;
-    __shared__ LrSmem sm;
+    __shared__ Lr2Smem sm;
     const int x0 = blockIdx.x * LR_TW, s = blockIdx.y;
     const int sh = 64 >> P.ss_ver, off = 8 >> P.ss_ver;
     const int top = imax(0, s * sh - off), bot = imin(P.h, (s + 1) * sh - off);
@@ -218,34 +442,53 @@ lr_frame_kernel(const uint8_t *__restrict__ cdef, const uint8_t *__restrict__ db
     pixel *o = (pixel *)outp + (int64_t)top * ps + x0;
     if (U.kind == 0) {  // unit not restored: copy through
         const pixel *c = (const pixel *)cdef + (int64_t)top * ps + x0;
-        for (int i = threadIdx.x; i < th * tw; i += 256) {
-            const int r = i / tw, cc = i - r * tw;
-            o[(int64_t)r * ps + cc] = c[(int64_t)r * ps + cc];
+        for (int i = threadIdx.x; i < th * 8; i += 256) {
+            const int r = i >> 3, g = i & 7;
+            if (4 * g >= tw) continue;
+            int v[4];
+#pragma unroll
+            for (int m = 0; m < 4; m++) v[m] = 4 * g + m < tw ? c[(int64_t)r * ps + 4 * g + m] : 0;
+            lr2_store4<BD>(o + (int64_t)r * ps + 4 * g, v, tw - 4 * g);
         }
         return;
     }
     // ---- stage the padded window (padding(), src/looprestoration_tmpl.c:41-137, with
-    //      lpf rows = deblocked rows saved by backup_lpf, src/lf_apply_tmpl.c:41-106)
-    for (int i = threadIdx.x; i < (th + 6) * (tw + 6); i += 256) {
-        const int r = i / (tw + 6), c = i - r * (tw + 6);
-        const int xx = iclip(x0 + c - 3, 0, P.w - 1);
-        const int yy = top + r - 3;
-        pixel v;
-        if (yy < top) {
-            if (top == 0) v = ((const pixel *)cdef)[xx];                                   // no LR_HAVE_TOP
-            else v = ((const pixel *)dbl)[(int64_t)imax(yy, top - 2) * ps + xx];
-        } else if (yy >= bot) {
-            if (bot >= P.h) v = ((const pixel *)cdef)[(int64_t)(bot - 1) * ps + xx];      // no LR_HAVE_BOTTOM
-            else v = ((const pixel *)dbl)[(int64_t)imin(imin(yy, bot + 1), P.h - 1) * ps + xx];
-        } else {
-            v = ((const pixel *)cdef)[(int64_t)yy * ps + xx];
+    //      lpf rows = deblocked rows saved by backup_lpf, src/lf_apply_tmpl.c:41-106).
+    //      A warp owns rows r = warp, warp + 8, ...; lanes own columns e and e + 32.
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int xa = iclip(x0 + lane - 3, 0, P.w - 1), xb = iclip(x0 + lane + 29, 0, P.w - 1);
+        constexpr int NIT = (L2_WROWS + 7) / 8;
+        pixel va[NIT], vb[NIT];
+        // all loads of the thread are issued before the first store: the window is fetched with
+        // NIT-fold memory-level parallelism instead of one DRAM/L2 round trip per row
+#pragma unroll
+        for (int it = 0; it < NIT; it++) {
+            const int r = warp + 8 * it;
+            va[it] = 0; vb[it] = 0;
+            if (r < th + 6) {
+                const int yy = top + r - 3;
+                const pixel *row;
+                if (yy < top) row = top == 0 ? (const pixel *)cdef : (const pixel *)dbl + (int64_t)imax(yy, top - 2) * ps;
+                else if (yy >= bot) row = bot >= P.h ? (const pixel *)cdef + (int64_t)(bot - 1) * ps
+                                                     : (const pixel *)dbl + (int64_t)imin(imin(yy, bot + 1), P.h - 1) * ps;
+                else row = (const pixel *)cdef + (int64_t)yy * ps;
+                va[it] = row[xa];
+                if (lane < 6) vb[it] = row[xb];
+            }
         }
-        sm.win[r * LR_WP + c] = v;
+#pragma unroll
+        for (int it = 0; it < NIT; it++) {
+            const int r = warp + 8 * it;
+            if (r < th + 6) {
+                sm.win[r * L2_WP + lane] = va[it];
+                if (lane < 8) sm.win[r * L2_WP + 32 + lane] = vb[it];
+            }
+        }
     }
     __syncthreads();
-    auto out = [&](int r, int c, int v) { o[(int64_t)r * ps + c] = (pixel)v; };
-    if (U.kind == 1) lr_wiener_tile<BD>(sm, tw, th, U.fh, U.fv, bdmax, out);
-    else lr_sgr_tile<BD>(sm, tw, th, U.kind, U.s0, U.s1, U.w0, U.w1, bdmax, out);
+    if (U.kind == 1) lr2_wiener<BD>(sm, tw, th, U.fh, U.fv, bdmax, o, ps);
+    else lr2_sgr<BD>(sm, tw, th, U.kind, U.s0, U.s1, U.w0, U.w1, bdmax, o, ps);
 }
 
 // ---- per-call: window from an explicit padded buffer tmp[(h+6)][pitch], built by lr_pad_kernel

@@ -17,6 +17,7 @@
 // that are not split in that dimension.
 #include "common.cuh"
 #include "tables.cuh"
+#include <mutex>
 #include <utility>
 
 namespace rb200 {
@@ -178,35 +179,339 @@ __device__ void mc_tile(McSmem &sm, const McRef ref, int sx, int sy, int w, int 
     __syncwarp();
 }
 
+// ---------------------------------------------------------------- fast 8-tap tile (batch path)
+// Same arithmetic as mc_tile, restated for the integer dot-product unit: the source window is
+// staged as 32-bit words holding two horizontally adjacent pixels, the horizontal pass packs
+// its int16 results as vertical pairs, and both passes run on IDP.2A (dp2a: two 16-bit x 8-bit
+// multiply-adds per instruction).  An output whose first tap falls on the low half of a word
+// needs 4 IDP, one that starts on the high half 5 (with the taps shifted by one byte), so a
+// pair of outputs costs 9 instead of 16 IMADs.  Rows of the window are clamped to the
+// reference (free); windows that leave it horizontally are staged with the clamped per-pixel
+// gather (emu_edge, src/mc.rs:1032-1112) into the same layout.
+constexpr int MCF_WROWS = 24;   // window rows (16 + 7, rounded to pairs)
+constexpr int MCF_WPW = 13;     // words per window row (26 pixels >= 1 + 23 + 1), odd: rows spread over banks
+constexpr int MCF_MPW = 17;     // words per row pair of the intermediate
+
+struct McFastSmem {
+    uint32_t win[2][MCF_WROWS * MCF_WPW];       // double buffered: the next item's window streams in during the arithmetic
+    uint32_t midv[(MCF_WROWS / 2) * MCF_MPW];   // [row pair][column] = (mid[2j][c], mid[2j + 1][c])
+    __align__(16) uint16_t out[MC_TILE * MC_TILE];
+};
+
+struct McTaps {
+    int e0, e1;        // first tap on the low half:  (F0 F1 F2 F3) (F4 F5 F6 F7)
+    int o0, o1, o2;    // first tap on the high half: (0 F0 F1 F2) (F3 F4 F5 F6) (F7 0 0 0)
+    int pad[3];
+};
+// the 6 x 15 sub-pel filters of tab::k_subpel_filters in packed form (mc_pack_taps), built once
+__device__ McTaps g_subpel_packed[6 * 15];
+__device__ __forceinline__ McTaps mc_pack_taps(const int8_t *f) {
+    unsigned b[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) b[k] = (unsigned)(uint8_t)f[k];
+    McTaps t;
+    t.e0 = (int)(b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24));
+    t.e1 = (int)(b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24));
+    t.o0 = (int)((b[0] << 8) | (b[1] << 16) | (b[2] << 24));
+    t.o1 = (int)(b[3] | (b[4] << 8) | (b[5] << 16) | (b[6] << 24));
+    t.o2 = (int)b[7];
+    t.pad[0] = t.pad[1] = t.pad[2] = 0;
+    return t;
+}
+__device__ __forceinline__ int mc_fir_even(const McTaps &t, unsigned w0, unsigned w1, unsigned w2, unsigned w3, int init) {
+    int a = __dp2a_lo((int)w0, t.e0, init);
+    a = __dp2a_hi((int)w1, t.e0, a);
+    a = __dp2a_lo((int)w2, t.e1, a);
+    return __dp2a_hi((int)w3, t.e1, a);
+}
+__device__ __forceinline__ int mc_fir_odd(const McTaps &t, unsigned w0, unsigned w1, unsigned w2, unsigned w3, unsigned w4, int init) {
+    int a = __dp2a_lo((int)w0, t.o0, init);
+    a = __dp2a_hi((int)w1, t.o0, a);
+    a = __dp2a_lo((int)w2, t.o1, a);
+    a = __dp2a_hi((int)w3, t.o1, a);
+    return __dp2a_lo((int)w4, t.o2, a);
+}
+
+__global__ void mc_pack_table_kernel() {
+    const int i = threadIdx.x;
+    if (i < 6 * 15) g_subpel_packed[i] = mc_pack_taps(tab::k_subpel_filters + i * 8);
+}
+__device__ __forceinline__ McTaps mc_load_taps(int set, int phase_minus1) {
+    const int4 *p = (const int4 *)&g_subpel_packed[set * 15 + phase_minus1];
+    const int4 a = p[0]; const int b = ((const int *)p)[4];
+    McTaps t; t.e0 = a.x; t.e1 = a.y; t.o0 = a.z; t.o1 = a.w; t.o2 = b;
+    return t;
+}
+
+// Bilinear is the 2-tap FIR (16 - m, m) at tap positions 0 and 1 (its window has no left/top margin) with a gain of 16 instead of 64
+// (src/mc.rs:431-541); its two-step roundings collapse to the same single-shift forms.
+__device__ __forceinline__ McTaps mc_bilin_taps(int m) {
+    McTaps t;
+    t.e0 = (int)((unsigned)(16 - m) | ((unsigned)m << 8)); t.e1 = 0;
+    t.o0 = (int)(((unsigned)(16 - m) << 8) | ((unsigned)m << 16)); t.o1 = 0; t.o2 = 0;
+    t.pad[0] = t.pad[1] = t.pad[2] = 0;
+    return t;
+}
+
+// Window geometry of one tile: the filter support (8-tap: -3 .. +4, bilinear: 0 .. +1) decides
+// where the window starts; it is staged from the even column at or left of it.
+struct McWin {
+    int xs, ys, ncols, nrows2, xa, par, nw;
+    bool fh, fv, inside;
+};
+__device__ __forceinline__ McWin mc_window(const McRef &ref, int sx, int sy, int w, int h, int mx, int my, int filter2d) {
+    McWin W;
+    const int pre = filter2d == RB200_FILTER_2D_BILINEAR ? 0 : 3, ext = filter2d == RB200_FILTER_2D_BILINEAR ? 1 : 7;
+    W.fh = mx != 0; W.fv = my != 0;
+    W.xs = sx - (W.fh ? pre : 0); W.ys = sy - (W.fv ? pre : 0);
+    W.ncols = w + (W.fh ? ext : 0);
+    const int nrows = h + (W.fv ? ext : 0);
+    W.nrows2 = (nrows + 1) & ~1;
+    W.xa = W.xs & ~1; W.par = W.xs & 1;
+    W.nw = (W.par + W.ncols + 1) >> 1;
+    W.inside = W.xs >= 0 && W.xs + W.ncols <= ref.w;
+    return W;
+}
+
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// Stage the window of a tile: word k of row r = pixels (xa + 2k, xa + 2k + 1) of source row ys + r.
+// 16-bit pixels of a window inside the picture go global -> shared asynchronously (LDGSTS), so
+// the caller can overlap the fetch with the previous tile's arithmetic; the caller commits/waits.
+// Other cases are staged synchronously.
+template <typename BD>
+__device__ __forceinline__ void mc_stage(uint32_t *win, const McRef &ref, const McWin &W) {
+    using pixel = typename BD::pixel;
+    const int lane = threadIdx.x & 31;
+    if (W.inside) {
+        const int k = lane & 15;
+        if (k < W.nw) {
+            if (BD::hbd && W.ys >= 0 && W.ys + W.nrows2 <= ref.h) {
+                // no row is clamped: one pointer bump per row
+                const int r0 = lane >> 4;
+                const uint8_t *src = ref.base + (int64_t)(W.ys + r0) * ref.stride + (int64_t)(W.xa + 2 * k) * 2;
+                uint32_t *d = win + r0 * MCF_WPW + k;
+                const int64_t step = 2 * ref.stride;
+                for (int r = r0; r < W.nrows2; r += 2, src += step, d += 2 * MCF_WPW) cp_async4(d, src);
+            } else {
+                for (int r = lane >> 4; r < W.nrows2; r += 2) {
+                    const int yy = iclip(W.ys + r, 0, ref.h - 1);
+                    const pixel *row = (const pixel *)(ref.base + (int64_t)yy * ref.stride) + W.xa + 2 * k;
+                    if (BD::hbd) cp_async4(win + r * MCF_WPW + k, row);
+                    else { const unsigned q = *(const uint16_t *)row; win[r * MCF_WPW + k] = (q & 0xff) | ((q & 0xff00) << 8); }
+                }
+            }
+        }
+    } else {
+        uint16_t *we = (uint16_t *)win;
+        const int ne = 2 * W.nw;
+        for (int i = lane; i < W.nrows2 * ne; i += 32) {
+            const int r = i / ne, e = i - r * ne;
+            const int yy = iclip(W.ys + r, 0, ref.h - 1), xx = iclip(W.xa + e, 0, ref.w - 1);
+            we[r * (2 * MCF_WPW) + e] = ((const pixel *)(ref.base + (int64_t)yy * ref.stride))[xx];
+        }
+    }
+}
+
+// put, w and h even and <= 16; `win` already staged (mc_stage) and visible to the warp.
+// TW / TH: compile-time tile size (0 = use the run-time w / h) -- the common 16x16 and 8x8 tiles get
+// fully unrolled task loops with constant index arithmetic.
+template <typename BD, int TW, int TH>
+__device__ void mc_tile_fast(McFastSmem &sm, const uint32_t *win, const McWin &W, int w_rt, int h_rt, int bw, int bh, int mx,
+                             int my, int filter2d, uint8_t *out, int64_t out_pitch, int bdmax) {
+    const int w = TW ? TW : w_rt, h = TH ? TH : h_rt;
+    const int lane = threadIdx.x & 31;
+    const int ib = McBits<BD>::ib(bdmax);
+    const bool fh = W.fh, fv = W.fv;
+    const int nrows2 = W.nrows2, par = W.par;
+
+    const int th_ = (0x111222000LL >> (4 * filter2d)) & 3, tv_ = (0x210210210LL >> (4 * filter2d)) & 3;
+    const int ncp = w >> 1, cp_shift = 31 - __clz(ncp), w_shift = cp_shift + 1;
+    uint32_t *out32 = (uint32_t *)sm.out;   // row pitch MC_TILE pixels = 8 words
+
+    const bool bilin = filter2d == RB200_FILTER_2D_BILINEAR;
+    const int base = bilin ? 4 : 6;
+    if (fh) {
+        const McTaps T = bilin ? mc_bilin_taps(mx) : mc_load_taps(bw > 4 ? th_ : 3 + (th_ & 1), mx - 1);
+        const int sh1 = base - ib, r1 = (1 << sh1) >> 1;
+        const int n_tasks = (nrows2 >> 1) << cp_shift;
+        const int init = fv ? r1 : (1 << (base - 1)) + r1, sh = fv ? sh1 : base;
+        constexpr int MAX_IT = TW ? ((TH + 8) / 2 * (TW / 2) + 31) / 32 : 3;
+#pragma unroll
+        for (int it = 0; it < MAX_IT; it++) {
+            const int t = lane + 32 * it;
+            if (t >= n_tasks) break;
+            const int cp = t & (ncp - 1), rp = t >> cp_shift;
+            int a[2][2];
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                const uint32_t *wv = win + (2 * rp + rr) * MCF_WPW + cp;
+                const unsigned w0 = wv[0], w1 = wv[1], w2 = wv[2], w3 = wv[3], w4 = wv[4];
+                if (par == 0) { a[rr][0] = mc_fir_even(T, w0, w1, w2, w3, init); a[rr][1] = mc_fir_odd(T, w0, w1, w2, w3, w4, init); }
+                else { a[rr][0] = mc_fir_odd(T, w0, w1, w2, w3, w4, init); a[rr][1] = mc_fir_even(T, w1, w2, w3, w4, init); }
+            }
+            if (fv) {
+#pragma unroll
+                for (int cc = 0; cc < 2; cc++)
+                    sm.midv[rp * MCF_MPW + 2 * cp + cc] = __byte_perm((unsigned)(a[0][cc] >> sh), (unsigned)(a[1][cc] >> sh), 0x5410);
+            } else {
+#pragma unroll
+                for (int rr = 0; rr < 2; rr++) {
+                    const unsigned p0 = (unsigned)iclip(a[rr][0] >> sh, 0, bdmax);
+                    const unsigned p1 = (unsigned)iclip(a[rr][1] >> sh, 0, bdmax);
+                    out32[(2 * rp + rr) * (MC_TILE / 2) + cp] = p0 | (p1 << 16);
+                }
+            }
+        }
+    } else if (fv) {
+        // no horizontal filter: re-pack the raw pixels as vertical pairs
+        const int n_tasks = (nrows2 >> 1) << cp_shift;
+        for (int t = lane; t < n_tasks; t += 32) {
+            const int cp = t & (ncp - 1), rp = t >> cp_shift;
+            const uint32_t *r0 = win + (2 * rp) * MCF_WPW + cp, *r1p = r0 + MCF_WPW;
+            unsigned a0, a1;   // pixels (c, c + 1) of the two rows
+            if (par == 0) { a0 = r0[0]; a1 = r1p[0]; }
+            else { a0 = __funnelshift_r(r0[0], r0[1], 16); a1 = __funnelshift_r(r1p[0], r1p[1], 16); }
+            sm.midv[rp * MCF_MPW + 2 * cp] = __byte_perm(a0, a1, 0x5410);
+            sm.midv[rp * MCF_MPW + 2 * cp + 1] = __byte_perm(a0, a1, 0x7632);
+        }
+    } else {
+        const int n_tasks = h << cp_shift;
+        for (int t = lane; t < n_tasks; t += 32) {
+            const int cp = t & (ncp - 1), r = t >> cp_shift;
+            const uint32_t *wv = win + r * MCF_WPW + cp;
+            out32[r * (MC_TILE / 2) + cp] = par == 0 ? wv[0] : __funnelshift_r(wv[0], wv[1], 16);
+        }
+    }
+    __syncwarp();
+    if (fv) {
+        const McTaps T = bilin ? mc_bilin_taps(my) : mc_load_taps(bh > 4 ? tv_ : 3 + (tv_ & 1), my - 1);
+        const int sh2 = fh ? base + ib : base, r2 = (1 << sh2) >> 1;
+        const int n_tasks = (h >> 1) << w_shift;
+        constexpr int MAX_IT = TW ? (TH / 2 * TW + 31) / 32 : 4;
+#pragma unroll
+        for (int it = 0; it < MAX_IT; it++) {
+            const int t = lane + 32 * it;
+            if (t >= n_tasks) break;
+            const int c = t & (w - 1), rp = t >> w_shift;
+            const uint32_t *mv = sm.midv + rp * MCF_MPW + c;
+            const unsigned v0 = mv[0], v1 = mv[MCF_MPW], v2 = mv[2 * MCF_MPW], v3 = mv[3 * MCF_MPW], v4 = mv[4 * MCF_MPW];
+            const int a0 = mc_fir_even(T, v0, v1, v2, v3, r2), a1 = mc_fir_odd(T, v0, v1, v2, v3, v4, r2);
+            sm.out[(2 * rp) * MC_TILE + c] = (uint16_t)iclip(a0 >> sh2, 0, bdmax);
+            sm.out[(2 * rp + 1) * MC_TILE + c] = (uint16_t)iclip(a1 >> sh2, 0, bdmax);
+        }
+        __syncwarp();
+    }
+    // ---- tile -> picture, widest aligned stores the row allows
+    if (BD::hbd) {
+        const int row_bytes = w * 2;
+        if (row_bytes >= 16 && !(((uintptr_t)out | (uintptr_t)out_pitch) & 15)) {
+            const int upr = row_bytes >> 4;   // 16-byte units per row (1 or 2)
+            for (int t = lane; t < h * upr; t += 32) {
+                const int r = upr == 2 ? t >> 1 : t, u = upr == 2 ? t & 1 : 0;
+                *(uint4 *)(out + (int64_t)r * out_pitch + u * 16) = *(const uint4 *)(sm.out + r * MC_TILE + u * 8);
+            }
+        } else {
+            for (int t = lane; t < h << cp_shift; t += 32) {
+                const int cp = t & (ncp - 1), r = t >> cp_shift;
+                *(uint32_t *)(out + (int64_t)r * out_pitch + cp * 4) = out32[r * (MC_TILE / 2) + cp];
+            }
+        }
+    } else {
+        for (int t = lane; t < h << cp_shift; t += 32) {
+            const int cp = t & (ncp - 1), r = t >> cp_shift;
+            const unsigned v = out32[r * (MC_TILE / 2) + cp];
+            *(uint16_t *)(out + (int64_t)r * out_pitch + cp * 2) = (uint16_t)((v & 0xff) | ((v >> 8) & 0xff00));
+        }
+    }
+    __syncwarp();
+}
+
 struct McRefSet {
     Rb200Planes p[8];
 };
 
-// Frame batch: one warp per item, items wider/taller than 16 are walked tile by tile.
+// Frame batch: warps walk the item list with a stride of the number of warps in the grid; while a
+// warp filters item i the first window of its item i + 1 is already in flight (cp.async).
+// Items wider/taller than 16 are walked tile by tile.
 template <typename BD>
-__global__ void __launch_bounds__(MC_WARPS * 32)
+__global__ void __launch_bounds__(MC_WARPS * 32, 6)
 mc_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int ss_hor, int ss_ver,
                 const Rb200McItem *__restrict__ items, int n_items, int bdmax) {
-    __shared__ McSmem smem[MC_WARPS];
+    __shared__ struct { McFastSmem fast; McSmem slow; } smem[MC_WARPS];   // not a union: a prefetch may be in flight
     const int warp = threadIdx.x >> 5;
-    const int idx = blockIdx.x * MC_WARPS + warp;
+    const int n_warps = gridDim.x * MC_WARPS;
+    McFastSmem &sm = smem[warp].fast;
+    auto ref_of = [&](const Rb200McItem &it) {
+        const Rb200Planes &rp = refs.p[it.ref & 7];
+        McRef ref;
+        ref.base = plane_ptr(rp, it.plane);
+        ref.stride = plane_stride(rp, it.plane);
+        ref.w = it.plane ? (ref_w + ss_hor) >> ss_hor : ref_w;
+        ref.h = it.plane ? (ref_h + ss_ver) >> ss_ver : ref_h;
+        return ref;
+    };
+    auto is_fast = [](const Rb200McItem &it) { return !((it.w | it.h) & 1) && (it.w >= MC_TILE || !(it.w & (it.w - 1))); };
+    int idx = blockIdx.x * MC_WARPS + warp;
     if (idx >= n_items) return;
-    const Rb200McItem it = items[idx];
-    const Rb200Planes &rp = refs.p[it.ref & 7];
-    McRef ref;
-    ref.base = plane_ptr(rp, it.plane);
-    ref.stride = plane_stride(rp, it.plane);
-    ref.w = it.plane ? (ref_w + ss_hor) >> ss_hor : ref_w;
-    ref.h = it.plane ? (ref_h + ss_ver) >> ss_ver : ref_h;
-    uint8_t *dbase = plane_ptr(dst, it.plane);
-    const int64_t dstride = plane_stride(dst, it.plane);
-    for (int ty = 0; ty < it.h; ty += MC_TILE) {
-        for (int tx = 0; tx < it.w; tx += MC_TILE) {
-            uint8_t *o = dbase + (int64_t)(it.dst_y + ty) * dstride + (int64_t)(it.dst_x + tx) * sizeof(typename BD::pixel);
-            mc_tile<BD, false>(smem[warp], ref, it.src_x + tx, it.src_y + ty, imin(MC_TILE, it.w - tx),
-                               imin(MC_TILE, it.h - ty), it.w, it.h, it.mx, it.my, it.filter2d, o, dstride, bdmax);
-        }
+    Rb200McItem it = items[idx];
+    int buf = 0;
+    if (is_fast(it)) {
+        const McRef ref = ref_of(it);
+        mc_stage<BD>(sm.win[0], ref, mc_window(ref, it.src_x, it.src_y, imin(MC_TILE, it.w), imin(MC_TILE, it.h), it.mx, it.my, it.filter2d));
     }
+    cp_async_commit();
+    for (;;) {
+        const int nidx = idx + n_warps;
+        Rb200McItem nit;
+        const bool have_next = nidx < n_items;
+        if (have_next) {
+            nit = items[nidx];
+            if (is_fast(nit)) {
+                const McRef nref = ref_of(nit);
+                mc_stage<BD>(sm.win[buf ^ 1], nref, mc_window(nref, nit.src_x, nit.src_y, imin(MC_TILE, nit.w), imin(MC_TILE, nit.h), nit.mx, nit.my, nit.filter2d));
+            }
+        }
+        cp_async_commit();
+        cp_async_wait<1>();      // the current item's first window has landed
+        __syncwarp();
+        const McRef ref = ref_of(it);
+        uint8_t *dbase = plane_ptr(dst, it.plane);
+        const int64_t dstride = plane_stride(dst, it.plane);
+        const bool fast = is_fast(it);
+        for (int ty = 0; ty < it.h; ty += MC_TILE) {
+            for (int tx = 0; tx < it.w; tx += MC_TILE) {
+                uint8_t *o = dbase + (int64_t)(it.dst_y + ty) * dstride + (int64_t)(it.dst_x + tx) * sizeof(typename BD::pixel);
+                const int tw = imin(MC_TILE, it.w - tx), th = imin(MC_TILE, it.h - ty);
+                if (fast) {
+                    const McWin W = mc_window(ref, it.src_x + tx, it.src_y + ty, tw, th, it.mx, it.my, it.filter2d);
+                    if (tx | ty) {   // further tiles of a large block: staged in place, not prefetched
+                        mc_stage<BD>(sm.win[buf], ref, W);
+                        cp_async_commit();
+                        cp_async_wait<0>();
+                        __syncwarp();
+                    }
+                    if (tw == 16 && th == 16)
+                        mc_tile_fast<BD, 16, 16>(sm, sm.win[buf], W, tw, th, it.w, it.h, it.mx, it.my, it.filter2d, o, dstride, bdmax);
+                    else if (tw == 8 && th == 8)
+                        mc_tile_fast<BD, 8, 8>(sm, sm.win[buf], W, tw, th, it.w, it.h, it.mx, it.my, it.filter2d, o, dstride, bdmax);
+                    else
+                        mc_tile_fast<BD, 0, 0>(sm, sm.win[buf], W, tw, th, it.w, it.h, it.mx, it.my, it.filter2d, o, dstride, bdmax);
+                } else {
+                    mc_tile<BD, false>(smem[warp].slow, ref, it.src_x + tx, it.src_y + ty, tw, th, it.w, it.h, it.mx, it.my,
+                                       it.filter2d, o, dstride, bdmax);
+                }
+            }
+        }
+        if (!have_next) break;
+        it = nit; idx = nidx; buf ^= 1;
+    }
+    cp_async_wait<0>();
 }
 
 // Per-call: a single prediction block over a staged source rectangle; one warp per 16x16 tile.
@@ -420,7 +725,21 @@ int mc_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs,
     if (n <= 0) return 0;
     McRefSet rs = {};
     for (int i = 0; i < n_refs && i < 8; i++) rs.p[i] = refs[i];
-    const int grid = (n + MC_WARPS - 1) / MC_WARPS;
+    {
+        static std::mutex mu;
+        static bool packed[64] = {};
+        std::lock_guard<std::mutex> lock(mu);
+        int dev = 0;
+        RB_CUDA(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < 64 && !packed[dev]) {
+            mc_pack_table_kernel<<<1, 96, 0, st>>>();
+            RB_LAUNCH_CHECK();
+            RB_CUDA(cudaStreamSynchronize(st));   // once per device: visible to every stream that follows
+            packed[dev] = true;
+        }
+    }
+    // persistent warps: 148 SMs x 6 resident CTAs, capped by the item count
+    const int grid = imin((n + MC_WARPS - 1) / MC_WARPS, 148 * 6);
     if (bdmax > 255)
         mc_batch_kernel<BD16><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, ss_hor, ss_ver, d_items, n, bdmax);
     else

@@ -166,13 +166,14 @@ def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1):
                 add(p, bx[sel] * 8 + ox, by[sel] * 8 + oy, TX_4X4)
     plane = np.concatenate([r[0] for r in recs]); xs = np.concatenate([r[1] for r in recs])
     ys = np.concatenate([r[2] for r in recs]); tx = np.concatenate([r[3] for r in recs])
-    order = np.argsort(tx, kind="stable")
-    plane, xs, ys, tx = plane[order], xs[order], ys[order], tx[order]
     n_itx = tx.size
-    txtp = np.zeros(n_itx, np.int64)
     r = rng.random(n_itx)
     ntypes = np.where(tx == TX_16X16, 12, 16)
     txtp = np.where(r < 0.6, 0, rng.integers(0, 16, size=n_itx) % ntypes)
+    # the appender buckets transform blocks by (size, type): a counting sort on the host that keeps
+    # the 1-D transform kind uniform across the threads of a warp (csrc/itx.cu)
+    order = np.argsort(tx * 32 + txtp, kind="stable")
+    plane, xs, ys, tx, txtp = plane[order], xs[order], ys[order], tx[order], txtp[order]
     itx = np.zeros(n_itx, lib.ITX_ITEM_DT)
     itx["x"] = xs; itx["y"] = ys; itx["plane"] = plane; itx["tx"] = tx; itx["txtp"] = txtp
     counts = np.zeros(19, np.int32)
