@@ -216,7 +216,7 @@ def run_gpu(args, s, wl):
     n_mc = len(s.mc_items)
 
     def submit(d, upload):
-        lib.check(lib.frame_submit(d.h, s.n_coefs, counts, n_mc, stages, 1 if upload else 0), "frame_submit")
+        lib.check(lib.frame_submit(d.h, s.n_coefs, counts, n_mc, stages, int(upload)), "frame_submit")
 
     def barrier():
         torch.cuda.synchronize()
@@ -224,42 +224,76 @@ def run_gpu(args, s, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- resident leg: one stream, CUDA events around K steps
+    # ---------------- resident leg: CUDA events around K steps.
+    # --streams 1: every frame on one stream (kernels strictly serial).  --streams N_CTX (default): each
+    # frame context on its own stream, so stages of different frames overlap on the device the way
+    # the reference's frame threads (n_fc) overlap frames; the timed region is bracketed by one start
+    # event and one end event per stream, the slowest stream decides.
+    multi = args.streams > 1
     main = torch.cuda.Stream()
     for d in ctxs:
-        lib.check(lib.frame_set_stream(d.h, C.c_void_p(main.cuda_stream)))
+        lib.check(lib.frame_set_stream(d.h, None if multi else C.c_void_p(main.cuda_stream)))
         submit(d, True)                      # batch becomes resident (not timed)
+    rstreams = [torch.cuda.ExternalStream(lib.frame_stream(d.h)) for d in ctxs] if multi else [main]
     for _ in range(args.warmup):
         for i in range(FRAMES_PER_STEP):
             submit(ctxs[i % N_CTX], False)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    stage_ms = np.zeros(6)
+    stage_ms = np.zeros(7)
     stage_n = 0
-    buf = (C.c_float * 6)()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    buf = (C.c_float * 7)()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1s = [torch.cuda.Event(enable_timing=True) for _ in rstreams]
     launches = 0
-    e0.record(main)
+    e0.record(rstreams[0])
+    for st in rstreams[1:]:
+        st.wait_event(e0)
     for _ in range(args.steps):
         for i in range(FRAMES_PER_STEP):
             submit(ctxs[i % N_CTX], False)
             launches += lib.frame_last_launches(ctxs[i % N_CTX].h)
-        main.synchronize()                   # read the stage marks of this step's last N_CTX frames
-        for d in ctxs:
-            lib.check(lib.frame_stage_times(d.h, buf))
-            stage_ms += np.array(buf[:])
-            stage_n += 1
-    e1.record(main)
+        if not multi:
+            main.synchronize()               # read the stage marks of this step's last N_CTX frames
+            for d in ctxs:
+                lib.check(lib.frame_stage_times(d.h, buf))
+                stage_ms += np.array(buf[:])
+                stage_n += 1
+    for st, ev in zip(rstreams, e1s):
+        ev.record(st)
     barrier()
     clocks = sampler.stop() if sampler else None
-    ms = e0.elapsed_time(e1)
+    ms = max(e0.elapsed_time(ev) for ev in e1s)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     frames_total = world * args.steps * FRAMES_PER_STEP
     value = frames_total * w * h / (ms_max * 1e-3) / 1e6
-    stage_ms /= max(stage_n, 1)
+    # ---- per-stage kernel durations: with frames overlapping on several streams the stage marks of one
+    # frame include other frames' kernels, so the stage table (and the roofline of the dominant kernel)
+    # comes from a second pass of the same K steps with every frame on ONE stream (kernels serial).
+    value_serial = value
+    if multi:
+        for d in ctxs:
+            lib.check(lib.frame_set_stream(d.h, C.c_void_p(main.cuda_stream)))
+        for i in range(FRAMES_PER_STEP):
+            submit(ctxs[i % N_CTX], False)
+        barrier()
+        s0e, s1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0e.record(main)
+        for _ in range(args.steps):
+            for i in range(FRAMES_PER_STEP):
+                submit(ctxs[i % N_CTX], False)
+            main.synchronize()
+            for d in ctxs:
+                lib.check(lib.frame_stage_times(d.h, buf))
+                stage_ms += np.array(buf[:])
+                stage_n += 1
+        s1e.record(main)
+        barrier()
+        value_serial = args.steps * FRAMES_PER_STEP * w * h / (s0e.elapsed_time(s1e) * 1e-3) / 1e6
+    stage_ms = stage_ms[:6] / max(stage_n, 1)
 
     # ---------------- e2e leg: host buffers, N_CTX frames in flight on their own streams
     for d in ctxs:
@@ -269,7 +303,7 @@ def run_gpu(args, s, wl):
     def e2e_frame(i):
         d = ctxs[i % N_CTX]
         d.wait()                             # the context's previous frame (incl. its readback) is done;
-        submit(d, True)                      # the front end would refill the pinned staging here
+        submit(d, 2 if args.zero_copy else 1)   # the front end would refill the pinned staging here
         lib.check(lib.frame_readback_async(d.h, host_out[i % N_CTX][0], host_out[i % N_CTX][1]))
 
     for i in range(args.warmup * FRAMES_PER_STEP):
@@ -294,7 +328,14 @@ def run_gpu(args, s, wl):
     n_sb = g.sb128w * g.sb128h
     h2d = 0
     if stages & 1:
-        h2d += s.n_coefs * (4 if bpc > 8 else 2) + 16 * (len(s.itx_items) + n_mc)
+        cs = 4 if bpc > 8 else 2
+        if args.zero_copy:   # only the leading ncols columns of every block cross PCIe
+            from rav1d_b200.lib import TX_DIMS
+            sh = np.array([min(TX_DIMS[t][1], 32) for t in range(19)])[s.itx_items["tx"]]
+            h2d += int((s.itx_items["ncols"].astype(np.int64) * sh).sum()) * cs
+        else:
+            h2d += s.n_coefs * cs
+        h2d += 16 * (len(s.itx_items) + n_mc)
     h2d += n_sb * 1348 + (g.b4_stride * 32 * g.sb128h + 32) * 4 + 144 + n_sb * 108
     d2h = sum(out_bytes)
 
@@ -322,12 +363,17 @@ def run_gpu(args, s, wl):
                 "dtype": "int32", "data": "synthetic",
                 "config": {"workload": desc, "frames_per_step": FRAMES_PER_STEP, "width": w, "height": h, "bpc": bpc,
                            "l2": f"inputs larger than L2: {N_CTX} frame contexts cycled, > {ab['S'] * 4 // 1000000} MB working set each",
-                           "parallelism": f"{world} independent streams (one per GPU)" if world > 1 else "1 stream"},
+                           "frames_in_flight": N_CTX if multi else 1,
+                           "parallelism": f"{world} independent streams (one per GPU)" if world > 1 else "1 video stream"},
                 "fps": value * 1e6 / (w * h),
+                "value_one_stream": value_serial,
+                "stage_timing": "CUDA-event marks of a one-stream pass over the same steps (kernels serial)" if multi
+                                else "CUDA-event marks inside the timed region",
                 "frame_roofline_frac": round(frame_bytes * (value * 1e6 / (w * h)) / world / (peak * 1e9), 4),
                 "stages": per_stage, "roofline": roofline, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d * FRAMES_PER_STEP,
-                        "d2h_bytes_per_step": d2h * FRAMES_PER_STEP},
+                        "d2h_bytes_per_step": d2h * FRAMES_PER_STEP,
+                        "coefficients": "zero-copy from pinned host memory, column-bounded" if args.zero_copy else "H2D copy"},
                 "gpu_launches": launches}
     for d in ctxs:
         d.close()
@@ -361,6 +407,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="4k10", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--streams", type=int, default=N_CTX, help="resident leg: 1 = all frames on one stream, >1 = one stream per frame context")
+    ap.add_argument("--copy-coefs", dest="zero_copy", action="store_false",
+                    help="e2e leg: H2D-copy the whole coefficient buffer instead of zero-copy reads from pinned memory")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", 0))

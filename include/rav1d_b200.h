@@ -103,7 +103,9 @@ typedef struct Rb200ItxItem {
     uint8_t plane;    /* 0..2 */
     uint8_t tx;       /* RB200_TX_* / RB200_RTX_* */
     uint8_t txtp;     /* RB200_*_* */
-    uint8_t flags;    /* reserved, 0 */
+    uint8_t ncols;    /* number of leading coefficient columns that can be non-zero (1 + the largest x of a
+                         non-zero coefficient, as the front end saw while writing them); 0 = unknown, read
+                         all min(w, 32).  Lets the kernel skip the zero tail of the column-major block. */
     int16_t eob;
     int16_t pad;
 } Rb200ItxItem;       /* 16 bytes */
@@ -417,7 +419,12 @@ int rb200_frame_display_planes(Rb200Frame *f, Rb200Planes *out);
 int rb200_frame_output_planes(Rb200Frame *f, Rb200Planes *out);
 int rb200_frame_stage_planes(Rb200Frame *f, int which, Rb200Planes *out);
 /* Launch: H2D of `n_coefs` coefficients, the item lists and the filter metadata, then one
- * kernel sequence per stage on the frame's stream.  Asynchronous. */
+ * kernel sequence per stage on the frame's stream.  Asynchronous.
+ * upload: RB200_UPLOAD_NONE (batch already on the device), RB200_UPLOAD_ALL, or
+ * RB200_UPLOAD_ZERO_COPY_COEF: everything but the coefficients is copied; the inverse-transform
+ * kernels read the coefficients directly from the pinned staging buffer, column-bounded by
+ * Rb200ItxItem.ncols, so only the non-zero part of each block crosses PCIe. */
+enum { RB200_UPLOAD_NONE = 0, RB200_UPLOAD_ALL = 1, RB200_UPLOAD_ZERO_COPY_COEF = 2 };
 int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t itx_counts[RB200_N_RECT_TX_SIZES],
                        int n_mc_items, int stages, int upload);
 int rb200_frame_wait(Rb200Frame *f);

@@ -413,7 +413,8 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
     // ---- host -> device: the per-frame batch
     if (upload) {
         if (stages & RB200_STAGE_RECON) {
-            if (n_coefs) RB_CUDA(cudaMemcpyAsync(f->d_coef, f->h_coef, n_coefs * f->cs, cudaMemcpyHostToDevice, st));
+            if (n_coefs && upload != RB200_UPLOAD_ZERO_COPY_COEF)
+                RB_CUDA(cudaMemcpyAsync(f->d_coef, f->h_coef, n_coefs * f->cs, cudaMemcpyHostToDevice, st));
             if (n_itx) RB_CUDA(cudaMemcpyAsync(f->d_itx, f->h_itx, (size_t)n_itx * sizeof(Rb200ItxItem), cudaMemcpyHostToDevice, st));
             if (n_mc) RB_CUDA(cudaMemcpyAsync(f->d_mc, f->h_mc, (size_t)n_mc * sizeof(Rb200McItem), cudaMemcpyHostToDevice, st));
         }
@@ -440,7 +441,10 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         int off = 0;
         for (int t = 0; t < RB200_N_RECT_TX_SIZES; t++) {
             if (itx_counts[t]) {
-                if ((r = itx_launch(t, f->planes[0], f->d_coef, f->d_itx + off, itx_counts[t], f->bdmax, st))) return r;
+                // zero-copy: the kernel pulls exactly the coefficient columns it needs (Rb200ItxItem.ncols)
+                // over PCIe from the pinned staging instead of a full H2D copy first
+                const void *cf = upload == RB200_UPLOAD_ZERO_COPY_COEF ? f->h_coef : f->d_coef;
+                if ((r = itx_launch(t, f->planes[0], cf, f->d_itx + off, itx_counts[t], f->bdmax, st))) return r;
                 f->launches++;
             }
             off += itx_counts[t];

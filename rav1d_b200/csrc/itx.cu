@@ -99,7 +99,7 @@ itx_add_kernel(Rb200Planes planes, const typename BD::coef *__restrict__ cf,
 
     Rb200ItxItem it;
     if (live) it = items[idx];
-    else { it.cf_off = 0; it.x = it.y = 0; it.plane = 0; it.tx = TX; it.txtp = 0; it.eob = 0; it.flags = 0; }
+    else { it.cf_off = 0; it.x = it.y = 0; it.plane = 0; it.tx = TX; it.txtp = 0; it.eob = 0; it.ncols = 0; }
 
     const int row_lo = BD::hbd ? (int)((unsigned)~bdmax << 7) : -32768;
     const int col_lo = BD::hbd ? (int)((unsigned)~bdmax << 5) : -32768;
@@ -111,13 +111,14 @@ itx_add_kernel(Rb200Planes planes, const typename BD::coef *__restrict__ cf,
     // ---- first pass: rows ----
     if (live && !dconly && lane < SH) {
         int x[W];
+        const int nc = it.ncols ? it.ncols : SW;   // columns beyond nc hold zeros by contract and are not read
         if (wht) {
 #pragma unroll
-            for (int i = 0; i < SW; i++) x[i] = (int)c[lane + i * SH] >> 2;
+            for (int i = 0; i < SW; i++) x[i] = i < nc ? (int)c[lane + i * SH] >> 2 : 0;
         } else {
 #pragma unroll
             for (int i = 0; i < SW; i++) {
-                const int v = c[lane + i * SH];
+                const int v = i < nc ? (int)c[lane + i * SH] : 0;
                 x[i] = rect2 ? (v * 181 + 128) >> 8 : v;
             }
         }

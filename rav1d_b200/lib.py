@@ -34,7 +34,7 @@ class Planes(C.Structure):
 
 class ItxItem(C.Structure):
     _fields_ = [("cf_off", C.c_uint32), ("x", C.c_uint16), ("y", C.c_uint16), ("plane", C.c_uint8),
-                ("tx", C.c_uint8), ("txtp", C.c_uint8), ("flags", C.c_uint8), ("eob", C.c_int16),
+                ("tx", C.c_uint8), ("txtp", C.c_uint8), ("ncols", C.c_uint8), ("eob", C.c_int16),
                 ("pad", C.c_int16)]
 
 
@@ -99,7 +99,7 @@ MC_ITEM_DT = _np.dtype([("dst_x", "<i2"), ("dst_y", "<i2"), ("src_x", "<i2"), ("
                         ("h", "u1"), ("plane", "u1"), ("ref", "u1"), ("mx", "u1"), ("my", "u1"),
                         ("filter2d", "u1"), ("flags", "u1")])
 ITX_ITEM_DT = _np.dtype([("cf_off", "<u4"), ("x", "<u2"), ("y", "<u2"), ("plane", "u1"), ("tx", "u1"),
-                         ("txtp", "u1"), ("flags", "u1"), ("eob", "<i2"), ("pad", "<i2")])
+                         ("txtp", "u1"), ("ncols", "u1"), ("eob", "<i2"), ("pad", "<i2")])
 AV1_FILTER_DT = _np.dtype([("filter_y", "<u2", (2, 32, 3, 2)), ("filter_uv", "<u2", (2, 32, 2, 2)),
                            ("cdef_idx", "i1", (4,)), ("noskip_mask", "<u2", (16, 2))])
 LR_UNIT_DT = _np.dtype([("type", "u1"), ("filter_h", "i1", (3,)), ("filter_v", "i1", (3,)),

@@ -187,6 +187,7 @@ def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1):
     n_coefs = int(per.sum())
     coef = np.zeros(n_coefs, cdt)
     eobs = np.zeros(n_itx, np.int32)
+    ncols = np.zeros(n_itx, np.int32)
     res_max = max(bdmax >> res_amp_shift, 2)
     for t in (TX_4X4, TX_8X8, TX_16X16):
         for tp in range(16):
@@ -205,9 +206,13 @@ def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1):
             else:
                 e = np.maximum(last, 1)
             eobs[idx] = e
+            # leading coefficient columns that hold a non-zero value (column-major blocks of `sh` rows)
+            sh = {TX_4X4: 4, TX_8X8: 8, TX_16X16: 16}[t]
+            ncols[idx] = np.maximum(((np.arange(n) // sh + 1)[None, :] * nz).max(axis=1), 1)
             dst = cf_off[idx][:, None] + np.arange(n)[None, :]
             coef[dst.ravel()] = c.ravel().astype(cdt)
     itx["eob"] = eobs
+    itx["ncols"] = ncols
     s.itx_items, s.itx_counts, s.coef, s.n_coefs = itx, counts, coef, n_coefs
 
     # ---- per-4x4 transform-size maps -> edge masks
@@ -365,9 +370,11 @@ class DeviceFrame:
         lib.check(lib.frame_set_ref(self.h, 0, C.byref(pl)))
 
     def submit(self, stages, upload=True):
+        """upload: False / 0 = batch already on the device, True / 1 = copy the batch, 2 = copy everything but the
+        coefficients, which the itx kernels read straight from the pinned staging (zero-copy)."""
         s = self.s
         counts = (C.c_int32 * 19)(*[int(c) for c in s.itx_counts])
-        lib.check(lib.frame_submit(self.h, s.n_coefs, counts, len(s.mc_items), stages, 1 if upload else 0), "frame_submit")
+        lib.check(lib.frame_submit(self.h, s.n_coefs, counts, len(s.mc_items), stages, int(upload)), "frame_submit")
 
     def wait(self):
         lib.check(lib.frame_wait(self.h), "frame_wait")

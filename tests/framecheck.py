@@ -25,7 +25,7 @@ def oracle_frame(ref, s, stages, n_tc=1, start_planes=None):
         rf.close()
 
 
-def product_frame(s, stages, start_planes=None):
+def product_frame(s, stages, start_planes=None, upload=1):
     from rav1d_b200 import lib
     from rav1d_b200.synth.framegen import DeviceFrame
     d = DeviceFrame(s)
@@ -35,7 +35,7 @@ def product_frame(s, stages, start_planes=None):
             d.set_ref_from_host(s.ref)
         else:
             d.upload(0, start_planes)
-        d.submit(stages)
+        d.submit(stages, upload)
         d.wait()
         return visible(s, d.readback())
     finally:

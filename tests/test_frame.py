@@ -80,6 +80,19 @@ def test_config3_4k_10bit(rb, ref):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("w,h,bpc", [(200, 120, 8), (640, 360, 10)])
+def test_zero_copy_coefficients(rb, ref, w, h, bpc):
+    """RB200_UPLOAD_ZERO_COPY_COEF: the itx kernels read the pinned coefficient staging directly,
+    bounded by Rb200ItxItem.ncols; and ncols = 0 (unknown) still reads whole blocks."""
+    s = framegen.generate(w, h, bpc, seed=21)
+    a = framecheck.oracle_frame(ref, s, R | D)
+    framecheck.assert_planes_equal(a, framecheck.product_frame(s, R | D, upload=2), "zero-copy")
+    s.itx_items["ncols"] = 0
+    framecheck.assert_planes_equal(a, framecheck.product_frame(s, R | D, upload=2), "zero-copy, ncols unknown")
+    framecheck.assert_planes_equal(a, framecheck.product_frame(s, R | D, upload=1), "copy, ncols unknown")
+
+
+@pytest.mark.gpu
 def test_resubmit_is_idempotent(rb, ref):
     """Submitting the same batch twice gives the same picture (recon overwrites, filters are
     out of place or restart from recon)."""
