@@ -432,6 +432,28 @@ int rb200_frame_wait(Rb200Frame *f);
 int rb200_frame_readback(Rb200Frame *f, void *const data[3], const ptrdiff_t stride[2]);
 /* Same, queued on the frame's stream without waiting (use pinned host planes, then rb200_frame_wait). */
 int rb200_frame_readback_async(Rb200Frame *f, void *const data[3], const ptrdiff_t stride[2]);
+/* ---- one picture split over several GPUs by superblock rows (post-filters) ----
+ * A context can be restricted to a band named by the 64-row loop-restoration stripes
+ * [stripe_begin, stripe_end) it must deliver (stripe s = luma rows 64 s - 8 .. 64 s + 55; (0, 0) = the
+ * whole picture).  rb200_frame_band_rows reports the reconstructed luma rows the band reads (its own
+ * rows plus the halo the earlier stages need) and the rows it delivers.  The halo comes from the
+ * neighbour GPU over NVLink: rb200_frame_pull_rows copies rows of a plane set from a peer copy of the
+ * same picture, addressed by the base of its memory block (rb200_frame_plane_block, mapped into this
+ * process with rb200_ipc_open_handle when the peer is another process). */
+int rb200_frame_set_band(Rb200Frame *f, int stripe_begin, int stripe_end);
+int rb200_frame_band_rows(const Rb200Frame *f, int *in_row_begin, int *in_row_end, int *out_row_begin,
+                          int *out_row_end);
+int rb200_frame_upload_rows(Rb200Frame *f, int which, const void *const data[3], const ptrdiff_t stride[2],
+                            int row_begin, int row_end);
+int rb200_frame_readback_rows(Rb200Frame *f, void *const data[3], const ptrdiff_t stride[2], int row_begin,
+                              int row_end);
+int rb200_frame_plane_block(Rb200Frame *f, int which, void **base, size_t *bytes);
+int rb200_frame_pull_rows(Rb200Frame *f, int which, const void *peer_base, int row_begin, int row_end);
+#define RB200_IPC_HANDLE_BYTES 64
+int rb200_ipc_get_handle(void *dptr, uint8_t handle[RB200_IPC_HANDLE_BYTES]);
+int rb200_ipc_open_handle(const uint8_t handle[RB200_IPC_HANDLE_BYTES], void **dptr);
+int rb200_ipc_close_handle(void *dptr);
+int rb200_enable_peer_access(int peer_device);
 void *rb200_frame_stream(Rb200Frame *f);
 /* Run the frame's copies and launches on `stream` instead of the frame's own (NULL restores it). */
 int rb200_frame_set_stream(Rb200Frame *f, void *stream);

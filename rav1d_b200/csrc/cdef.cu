@@ -185,10 +185,10 @@ struct CdefBlk {  // per 8x8 luma block, written by (1), read by (2)
 template <typename BD>
 __global__ void __launch_bounds__(128)
 cdef_dir_frame_kernel(Rb200Planes src, CdefFrameParams P, const Rb200Av1Filter *__restrict__ masks,
-                      CdefBlk *__restrict__ out, int nbx, int nby) {
+                      CdefBlk *__restrict__ out, int nbx, int nby, int by_first, int by_end) {
     using pixel = typename BD::pixel;
-    const int bx = blockIdx.x * 32 + threadIdx.x, by = blockIdx.y * 4 + threadIdx.y;
-    if (bx >= nbx || by >= nby) return;
+    const int bx = blockIdx.x * 32 + threadIdx.x, by = by_first + blockIdx.y * 4 + threadIdx.y;
+    if (bx >= nbx || by >= by_end) return;
     CdefBlk b = {};
     const Rb200Av1Filter &m = masks[(by >> 4) * P.sb128w + (bx >> 4)];
     const int cdef_idx = m.cdef_idx[(((by >> 3) & 1) << 1) + ((bx >> 3) & 1)];
@@ -420,10 +420,10 @@ __device__ __forceinline__ void cdef_filter_plane(const int16_t *tile, const Cde
 template <typename BD>
 __global__ void __launch_bounds__(256)
 cdef_filter_frame_kernel(Rb200Planes src, Rb200Planes dst, CdefFrameParams P, const CdefBlk *__restrict__ blocks, int nbx,
-                         int nby) {
+                         int nby, int tile_row_first) {
     __shared__ __align__(16) int16_t tile[2 * CDEF_COPY + 8];
     __shared__ CdefBlk blk[64];
-    const int sbx = blockIdx.x, sby = blockIdx.y;
+    const int sbx = blockIdx.x, sby = tile_row_first + blockIdx.y;
     const int x0 = sbx * 64, y0 = sby * 64;
     const int fw = P.bw * 4, fh = P.bh * 4;
     const int tw = imin(64, fw - x0), th = imin(64, fh - y0);
@@ -500,18 +500,21 @@ __global__ void cdef_fb_kernel(uint8_t *dst, int64_t stride, const uint8_t *left
     }
 }
 
+// t0 / t1: 64-row tile rows to produce (whole picture: 0, ceil(height / 64))
 int cdef_frame_launch(const Rb200Planes &src, const Rb200Planes &dst, const CdefFrameParams &P,
-                      const Rb200Av1Filter *masks, void *blk_scratch, int bdmax, cudaStream_t st) {
+                      const Rb200Av1Filter *masks, void *blk_scratch, int bdmax, cudaStream_t st, int t0, int t1) {
     const int nbx = P.bw >> 1, nby = P.bh >> 1;
     CdefBlk *blocks = (CdefBlk *)blk_scratch;
-    dim3 g1((nbx + 31) / 32, (nby + 3) / 4), b1(32, 4);
-    dim3 grid((P.bw * 4 + 63) / 64, (P.bh * 4 + 63) / 64);
+    const int by0 = t0 * 8, by1 = imin(t1 * 8, nby);
+    if (by1 <= by0) return 0;
+    dim3 g1((nbx + 31) / 32, (by1 - by0 + 3) / 4), b1(32, 4);
+    dim3 grid((P.bw * 4 + 63) / 64, t1 - t0);
     if (bdmax > 255) {
-        cdef_dir_frame_kernel<BD16><<<g1, b1, 0, st>>>(src, P, masks, blocks, nbx, nby);
-        cdef_filter_frame_kernel<BD16><<<grid, 256, 0, st>>>(src, dst, P, blocks, nbx, nby);
+        cdef_dir_frame_kernel<BD16><<<g1, b1, 0, st>>>(src, P, masks, blocks, nbx, nby, by0, by1);
+        cdef_filter_frame_kernel<BD16><<<grid, 256, 0, st>>>(src, dst, P, blocks, nbx, nby, t0);
     } else {
-        cdef_dir_frame_kernel<BD8><<<g1, b1, 0, st>>>(src, P, masks, blocks, nbx, nby);
-        cdef_filter_frame_kernel<BD8><<<grid, 256, 0, st>>>(src, dst, P, blocks, nbx, nby);
+        cdef_dir_frame_kernel<BD8><<<g1, b1, 0, st>>>(src, P, masks, blocks, nbx, nby, by0, by1);
+        cdef_filter_frame_kernel<BD8><<<grid, 256, 0, st>>>(src, dst, P, blocks, nbx, nby, t0);
     }
     RB_LAUNCH_CHECK();
     return 0;

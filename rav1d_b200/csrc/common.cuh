@@ -67,6 +67,7 @@ struct LrFrameParams {
     int plane;
     int unit_log2;
     int sb128, sbh, sr_sb128w;
+    int stripe_first, stripe_end;   // band restriction (all stripes: 0, 0)
 };
 int itx_launch(int tx, const Rb200Planes &planes, const void *cf, const Rb200ItxItem *items, int n, int bdmax,
                cudaStream_t st);
@@ -74,10 +75,10 @@ int mc_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs,
                     int ss_ver, const Rb200McItem *d_items, int n, int bdmax, cudaStream_t st);
 int deblock_frame_launch(const Rb200Planes &pl, int n_planes, int w4, int h4, int sb128w, int b4_stride, int ss_hor,
                          int ss_ver, bool do_uv, const Rb200Av1Filter *masks, const uint8_t (*lvl)[4],
-                         const Rb200Av1FilterLUT *lut, int bdmax, cudaStream_t st, int *launches);
+                         const Rb200Av1FilterLUT *lut, int bdmax, cudaStream_t st, int *launches, int y4b, int y4e);
 // blk_scratch: device, 8 bytes per 8x8 luma block ((bw / 2) * (bh / 2) records)
 int cdef_frame_launch(const Rb200Planes &src, const Rb200Planes &dst, const CdefFrameParams &P,
-                      const Rb200Av1Filter *masks, void *blk_scratch, int bdmax, cudaStream_t st);
+                      const Rb200Av1Filter *masks, void *blk_scratch, int bdmax, cudaStream_t st, int t0, int t1);
 int lr_plane_launch(const uint8_t *cdef, const uint8_t *dbl, uint8_t *out, int64_t stride, const LrFrameParams &P,
                     const Rb200Av1Restoration *lrm, int bdmax, cudaStream_t st);
 

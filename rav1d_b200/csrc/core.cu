@@ -141,3 +141,29 @@ extern "C" int rb200_memset(void *dst, int value, size_t bytes, void *stream) {
     RB_CUDA(cudaMemsetAsync(dst, value, bytes, (cudaStream_t)stream)); return 0;
 }
 extern "C" int rb200_stream_sync(void *stream) { RB_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); return 0; }
+
+// ---- CUDA IPC: map another process's device allocation (halo exchange between ranks, one process per GPU)
+static_assert(sizeof(cudaIpcMemHandle_t) == RB200_IPC_HANDLE_BYTES, "ipc handle size");
+extern "C" int rb200_ipc_get_handle(void *dptr, uint8_t handle[RB200_IPC_HANDLE_BYTES]) {
+    cudaIpcMemHandle_t h;
+    RB_CUDA(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle, &h, sizeof(h));
+    return 0;
+}
+extern "C" int rb200_ipc_open_handle(const uint8_t handle[RB200_IPC_HANDLE_BYTES], void **dptr) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    RB_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+extern "C" int rb200_ipc_close_handle(void *dptr) { RB_CUDA(cudaIpcCloseMemHandle(dptr)); return 0; }
+extern "C" int rb200_enable_peer_access(int peer_device) {
+    int can = 0, dev = 0;
+    RB_CUDA(cudaGetDevice(&dev));
+    RB_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+    if (!can) return set_error(-19, "device %d cannot access peer %d", dev, peer_device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+    RB_CUDA(e);
+    return 0;
+}

@@ -42,6 +42,7 @@ struct Rb200Frame {
     Rb200Av1FilterLUT *h_lut, *d_lut;
     Rb200Av1Restoration *h_lr, *d_lr;
     void *d_cdef_blk;   // per-8x8 CDEF decisions (direction, strengths), device only
+    int band_s0, band_s1;   // loop-restoration stripes this context produces (0, 0 = whole picture)
     size_t n_masks, n_lvl;
     int launches;
     // film grain on output (src/fg_apply.rs): parameters, LUTs, display planes
@@ -276,6 +277,116 @@ static int film_grain_stage(Rb200Frame *f, cudaStream_t st) {
     return 0;
 }
 
+// Row ranges of one band (multi-GPU split of one picture by superblock rows).
+// The band is named by the 64-row loop-restoration stripes [s0, s1) it must deliver; each earlier
+// stage is widened by exactly what the next one reads: CDEF whole 64-row tiles, deblocked rows
+// +-2 around them, row edges +-8 around those, column edges +-8 more.
+struct BandRows {
+    int s0, s1;           // stripes
+    int t0, t1;           // CDEF tile rows
+    int y4b, y4e;         // deblock row-edge unit rows (luma 4-px units)
+    int in0, in1;         // reconstructed luma rows read
+    int out0, out1;       // luma rows delivered
+};
+static BandRows band_rows(const Rb200Frame *f) {
+    const int h = f->hdr.height;
+    const int n_stripes = (h + 8 + 63) / 64, n_tiles = (f->g.bh * 4 + 63) / 64;
+    BandRows b;
+    const bool all = f->band_s1 <= f->band_s0;
+    b.s0 = all ? 0 : imax(f->band_s0, 0);
+    b.s1 = all ? n_stripes : imin(f->band_s1, n_stripes);
+    b.out0 = imax(64 * b.s0 - 8, 0);
+    b.out1 = b.s1 >= n_stripes ? h : 64 * b.s1 - 8;
+    b.t0 = b.out0 / 64;
+    b.t1 = imin((b.out1 + 63) / 64, n_tiles);
+    if (b.s1 >= n_stripes) b.t1 = n_tiles;
+    b.y4b = imax(16 * b.t0 - 3, 0);
+    b.y4e = b.t1 >= n_tiles ? f->g.h4 : imin(16 * b.t1 + 3, f->g.h4);
+    b.in0 = imax(4 * (b.y4b - 2), 0);
+    b.in1 = b.y4e >= f->g.h4 ? f->g.plane_h[0] : imin(4 * (b.y4e + 2), f->g.plane_h[0]);
+    return b;
+}
+
+extern "C" int rb200_frame_set_band(Rb200Frame *f, int stripe_begin, int stripe_end) {
+    if (!f || stripe_begin < 0 || stripe_end < 0) return set_error(-22, "frame_set_band: bad argument");
+    f->band_s0 = stripe_begin; f->band_s1 = stripe_end;
+    return 0;
+}
+
+extern "C" int rb200_frame_band_rows(const Rb200Frame *f, int *in_begin, int *in_end, int *out_begin, int *out_end) {
+    if (!f) return set_error(-22, "frame_band_rows: null frame");
+    const BandRows b = band_rows(f);
+    if (in_begin) *in_begin = b.in0;
+    if (in_end) *in_end = b.in1;
+    if (out_begin) *out_begin = b.out0;
+    if (out_end) *out_end = b.out1;
+    return 0;
+}
+
+// Copy luma rows [row_begin, row_end) (and the chroma rows they cover) between a host picture and a plane set.
+static int copy_rows(Rb200Frame *f, const Rb200Planes &dev, void *const data[3], const ptrdiff_t stride[2], int row_begin,
+                     int row_end, bool to_device) {
+    for (int p = 0; p < f->g.n_planes; p++) {
+        const int ss = p ? f->g.ss_ver : 0;
+        const int full = p ? (f->hdr.height + ss) >> ss : f->hdr.height;
+        const int r0 = imax(row_begin >> ss, 0), r1 = imin((row_end + ss) >> ss, full);
+        if (r1 <= r0) continue;
+        const ptrdiff_t hs = stride[p ? 1 : 0];
+        if (hs < 0) return set_error(-22, "row-range copies need a positive host stride");
+        const size_t rb = (size_t)(p ? (f->hdr.width + f->g.ss_hor) >> f->g.ss_hor : f->hdr.width) * f->px;
+        uint8_t *h = (uint8_t *)data[p] + (int64_t)r0 * hs;
+        uint8_t *d = (uint8_t *)dev.data[p] + (int64_t)r0 * dev.stride[p];
+        if (to_device) RB_CUDA(cudaMemcpy2DAsync(d, (size_t)dev.stride[p], h, (size_t)hs, rb, r1 - r0, cudaMemcpyHostToDevice, f->stream));
+        else RB_CUDA(cudaMemcpy2DAsync(h, (size_t)hs, d, (size_t)dev.stride[p], rb, r1 - r0, cudaMemcpyDeviceToHost, f->stream));
+    }
+    return 0;
+}
+
+extern "C" int rb200_frame_upload_rows(Rb200Frame *f, int which, const void *const data[3], const ptrdiff_t stride[2],
+                                       int row_begin, int row_end) {
+    if (!f || which < 0 || which > 2 || !data || !stride) return set_error(-22, "frame_upload_rows: bad argument");
+    const int r = copy_rows(f, f->planes[which], (void *const *)data, stride, row_begin, row_end, true);
+    if (r) return r;
+    RB_CUDA(cudaStreamSynchronize(f->stream));
+    return 0;
+}
+
+extern "C" int rb200_frame_readback_rows(Rb200Frame *f, void *const data[3], const ptrdiff_t stride[2], int row_begin,
+                                         int row_end) {
+    if (!f || !data || !stride) return set_error(-22, "frame_readback_rows: bad argument");
+    const int r = copy_rows(f, f->display, data, stride, row_begin, row_end, false);
+    if (r) return r;
+    RB_CUDA(cudaStreamSynchronize(f->stream));
+    return 0;
+}
+
+// The device memory block behind plane set `which` (one allocation: Y, U, V back to back), for
+// peer access from another process / device (rb200_ipc_*).
+extern "C" int rb200_frame_plane_block(Rb200Frame *f, int which, void **base, size_t *bytes) {
+    if (!f || which < 0 || which > 2 || !base || !bytes) return set_error(-22, "frame_plane_block: bad argument");
+    const size_t ysz = (size_t)f->g.stride[0] * f->g.plane_h[0];
+    const size_t uvsz = f->g.n_planes > 1 ? (size_t)f->g.stride[1] * f->g.plane_h[1] : 0;
+    *base = f->plane_mem[which];
+    *bytes = ysz + 2 * uvsz + 256;
+    return 0;
+}
+
+// Pull luma rows [row_begin, row_end) (and their chroma rows) of plane set `which` from a peer copy of
+// the same picture whose memory block starts at `peer_base` (same geometry) -- the halo exchange.
+extern "C" int rb200_frame_pull_rows(Rb200Frame *f, int which, const void *peer_base, int row_begin, int row_end) {
+    if (!f || which < 0 || which > 2 || !peer_base) return set_error(-22, "frame_pull_rows: bad argument");
+    for (int p = 0; p < f->g.n_planes; p++) {
+        const int ss = p ? f->g.ss_ver : 0;
+        const int full = f->g.plane_h[p ? 1 : 0];
+        const int r0 = imax(row_begin >> ss, 0), r1 = imin((row_end + ss) >> ss, full);
+        if (r1 <= r0) continue;
+        const int64_t off = (uint8_t *)f->planes[which].data[p] - f->plane_mem[which] + (int64_t)r0 * f->planes[which].stride[p];
+        RB_CUDA(cudaMemcpyAsync(f->plane_mem[which] + off, (const uint8_t *)peer_base + off,
+                                (size_t)(r1 - r0) * f->planes[which].stride[p], cudaMemcpyDefault, f->stream));
+    }
+    return 0;
+}
+
 extern "C" int rb200_frame_set_stream(Rb200Frame *f, void *stream) {
     if (!f) return set_error(-22, "frame_set_stream: null frame");
     RB_CUDA(cudaStreamSynchronize(f->stream));
@@ -401,6 +512,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         if (n_mc && f->n_refs < 1) return set_error(-22, "frame_submit: no reference picture set");
     }
     f->launches = 0;
+    const BandRows band = band_rows(f);
     for (int i = 0; i < RB200_N_FRAME_MARKS; i++) f->ev_valid[i] = false;
 #define MARK(i) do { if (f->timing) { RB_CUDA(cudaEventRecord(f->ev[i], st)); f->ev_valid[i] = true; } } while (0)
     MARK(0);
@@ -456,7 +568,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
     if (do_lf) {
         if ((r = deblock_frame_launch(f->planes[0], g.n_planes, g.w4, g.h4, g.sb128w, g.b4_stride, g.ss_hor, g.ss_ver,
                                       h.lf_level_u || h.lf_level_v, f->d_masks, f->d_lvl + 32, f->d_lut, f->bdmax, st,
-                                      &f->launches))) return r;
+                                      &f->launches, band.y4b, band.y4e))) return r;
     }
     MARK(4);
     // ---- CDEF: cur -> p2 (src/recon.rs:4172-4213)
@@ -466,7 +578,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         P.n_planes = g.n_planes; P.bdmin8 = h.bpc - 8; P.damping = h.cdef_damping + P.bdmin8;
         for (int i = 0; i < 8; i++) { P.y_strength[i] = h.cdef_y_strength[i]; P.uv_strength[i] = h.cdef_uv_strength[i]; }
         P.layout_422 = h.layout == RB200_LAYOUT_I422;
-        if ((r = cdef_frame_launch(f->planes[0], f->planes[1], P, f->d_masks, f->d_cdef_blk, f->bdmax, st))) return r;
+        if ((r = cdef_frame_launch(f->planes[0], f->planes[1], P, f->d_masks, f->d_cdef_blk, f->bdmax, st, band.t0, band.t1))) return r;
         f->launches += 2;
         f->out = f->planes[1];
     }
@@ -482,6 +594,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
             P.w = (h.width + P.ss_hor) >> P.ss_hor; P.h = (h.height + P.ss_ver) >> P.ss_ver;
             P.unit_log2 = h.lr_unit_size_log2[p ? 1 : 0];
             P.sb128 = h.sb128; P.sbh = g.sbh; P.sr_sb128w = g.sb128w;
+            P.stripe_first = band.s0; P.stripe_end = band.s1;
             if ((r = lr_plane_launch((const uint8_t *)cdefp.data[p], (const uint8_t *)f->planes[0].data[p],
                                      (uint8_t *)f->planes[2].data[p], f->planes[2].stride[p], P, f->d_lr, f->bdmax, st)))
                 return r;

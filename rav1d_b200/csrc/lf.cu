@@ -205,7 +205,8 @@ struct LfPlaneSet {
     uint8_t *plane[3];
     int64_t stride[3];
     LfGeom g[3];
-    int unit_start[4];   // prefix sums of w4 * h4 over the planes in this launch
+    int unit_start[4];   // prefix sums of the unit counts of the planes in this launch
+    int y4_first[3];     // first 4-pixel unit row processed in each plane (band restriction)
     int n_planes;
 };
 
@@ -226,7 +227,8 @@ deblock_units_kernel(LfPlaneSet S, const Rb200Av1Filter *__restrict__ masks, con
     uint8_t *plane = pi == 0 ? S.plane[0] : (pi == 1 ? S.plane[1] : S.plane[2]);
     const int64_t stride = pi == 0 ? S.stride[0] : (pi == 1 ? S.stride[1] : S.stride[2]);
     const int u = gid - (pi == 0 ? 0 : (pi == 1 ? S.unit_start[1] : S.unit_start[2]));
-    const int y4 = u / g.w4, x4 = u - y4 * g.w4;
+    const int yl = u / g.w4, x4 = u - yl * g.w4;
+    const int y4 = yl + (pi == 0 ? S.y4_first[0] : (pi == 1 ? S.y4_first[1] : S.y4_first[2]));
     if (DIR == 0 ? x4 == 0 : y4 == 0) return;  // have_left / have_top
     const int idx = lf_mask_idx(masks, g, DIR, x4, y4);
     if (idx < 0) return;
@@ -311,9 +313,11 @@ __global__ void lpf_sb_kernel(uint8_t *dst, int64_t stride, int uv, int dir, uin
 }
 
 // Whole-frame deblock: column edges of every plane (one launch), then row edges (one launch).
+// y4b / y4e: luma 4-pixel unit rows whose ROW edges are filtered (the whole picture: 0, h4); the
+// column-edge pass covers two more unit rows on each side, which is everything those row edges read.
 int deblock_frame_launch(const Rb200Planes &pl, int n_planes, int w4, int h4, int sb128w, int b4_stride, int ss_hor,
                          int ss_ver, bool do_uv, const Rb200Av1Filter *masks, const uint8_t (*lvl)[4],
-                         const Rb200Av1FilterLUT *lut, int bdmax, cudaStream_t st, int *launches) {
+                         const Rb200Av1FilterLUT *lut, int bdmax, cudaStream_t st, int *launches, int y4b, int y4e) {
     for (int dir = 0; dir < 2; dir++) {
         LfPlaneSet S = {};
         int n = 0, total = 0;
@@ -327,7 +331,11 @@ int deblock_frame_launch(const Rb200Planes &pl, int n_planes, int w4, int h4, in
             g.lvl_idx = p ? 1 + p : dir;
             S.plane[n] = (uint8_t *)pl.data[p]; S.stride[n] = pl.stride[p];
             S.unit_start[n] = total;
-            total += g.w4 * g.h4;
+            // band in this plane's unit rows; chroma rows round outwards
+            int b = dir ? y4b : y4b - 2, e = dir ? y4e : y4e + 2;
+            b = imax(b >> g.ss_ver, 0); e = imin((e + g.ss_ver) >> g.ss_ver, g.h4);
+            S.y4_first[n] = b;
+            total += g.w4 * imax(e - b, 0);
             n++;
         }
         S.unit_start[n] = total;

@@ -416,7 +416,7 @@ lr_frame_kernel(const uint8_t *__restrict__ cdef, const uint8_t *__restrict__ db
                 int64_t stride, LrFrameParams P, const Rb200Av1Restoration *__restrict__ lrm, int bdmax) {
     using pixel = typename BD::pixel;
     __shared__ Lr2Smem sm;
-    const int x0 = blockIdx.x * LR_TW, s = blockIdx.y;
+    const int x0 = blockIdx.x * LR_TW, s = P.stripe_first + blockIdx.y;
     const int sh = 64 >> P.ss_ver, off = 8 >> P.ss_ver;
     const int top = imax(0, s * sh - off), bot = imin(P.h, (s + 1) * sh - off);
     const int tw = imin(LR_TW, P.w - x0), th = bot - top;
@@ -542,11 +542,14 @@ lr_call_kernel(const uint8_t *tmp, int pitch, uint8_t *dst, int64_t stride, int 
     else lr_sgr_tile<BD>(sm, tw, th, U.kind, U.s0, U.s1, U.w0, U.w1, bdmax, out);
 }
 
+// P.stripe_first / P.stripe_end: stripes to produce (whole plane: 0, number of stripes; end <= 0 means all)
 int lr_plane_launch(const uint8_t *cdef, const uint8_t *dbl, uint8_t *out, int64_t stride, const LrFrameParams &P,
                     const Rb200Av1Restoration *lrm, int bdmax, cudaStream_t st) {
     const int sh = 64 >> P.ss_ver, off = 8 >> P.ss_ver;
     const int n_stripes = (P.h + off + sh - 1) / sh;
-    dim3 grid((P.w + LR_TW - 1) / LR_TW, n_stripes);
+    const int s1 = P.stripe_end > 0 ? imin(P.stripe_end, n_stripes) : n_stripes;
+    if (s1 <= P.stripe_first) return 0;
+    dim3 grid((P.w + LR_TW - 1) / LR_TW, s1 - P.stripe_first);
     if (bdmax > 255) lr_frame_kernel<BD16><<<grid, 256, 0, st>>>(cdef, dbl, out, stride, P, lrm, bdmax);
     else lr_frame_kernel<BD8><<<grid, 256, 0, st>>>(cdef, dbl, out, stride, P, lrm, bdmax);
     RB_LAUNCH_CHECK();

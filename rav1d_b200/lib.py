@@ -200,6 +200,16 @@ frame_wait = _sig("rb200_frame_wait", _i, _vp)
 frame_readback = _sig("rb200_frame_readback", _i, _vp, C.POINTER(_vp), C.POINTER(_ss))
 frame_readback_async = _sig("rb200_frame_readback_async", _i, _vp, C.POINTER(_vp), C.POINTER(_ss))
 frame_stream = _sig("rb200_frame_stream", _vp, _vp)
+frame_set_band = _sig("rb200_frame_set_band", _i, _vp, _i, _i)
+frame_band_rows = _sig("rb200_frame_band_rows", _i, _vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i))
+frame_upload_rows = _sig("rb200_frame_upload_rows", _i, _vp, _i, C.POINTER(_vp), C.POINTER(_ss), _i, _i)
+frame_readback_rows = _sig("rb200_frame_readback_rows", _i, _vp, C.POINTER(_vp), C.POINTER(_ss), _i, _i)
+frame_plane_block = _sig("rb200_frame_plane_block", _i, _vp, _i, C.POINTER(_vp), C.POINTER(_sz))
+frame_pull_rows = _sig("rb200_frame_pull_rows", _i, _vp, _i, _vp, _i, _i)
+ipc_get_handle = _sig("rb200_ipc_get_handle", _i, _vp, _vp)
+ipc_open_handle = _sig("rb200_ipc_open_handle", _i, _vp, C.POINTER(_vp))
+ipc_close_handle = _sig("rb200_ipc_close_handle", _i, _vp)
+enable_peer_access = _sig("rb200_enable_peer_access", _i, _i)
 frame_set_stream = _sig("rb200_frame_set_stream", _i, _vp, _vp)
 frame_enable_timing = _sig("rb200_frame_enable_timing", _i, _vp, _i)
 frame_stage_times = _sig("rb200_frame_stage_times", _i, _vp, C.POINTER(C.c_float))
