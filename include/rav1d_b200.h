@@ -221,6 +221,25 @@ int rb200_mc_batch(const Rb200Planes *dst, const Rb200Planes *refs, int n_refs, 
                    int ss_hor, int ss_ver, const Rb200McItem *d_items, int n_items, int bitdepth_max,
                    void *stream);
 
+/* Compound prediction, one record per BLOCK (all planes): recon.rs rav1d_recon_b_inter's compound
+ * branch (src/recon.rs:3290-3346 luma, :3742-3850 chroma; C: src/recon_tmpl.c:1836-1921) -- two
+ * `mct` predictions per plane combined by avg / w_avg / w_mask (+ `mask` with the luma-derived,
+ * sub-sampled segmentation mask for chroma).  The two int16 predictions and the mask never leave
+ * shared memory.  Motion vectors are the block's own (1/8 luma pel, {y, x} like Av1Block.mv); the
+ * kernel derives the per-plane position and phase as recon.rs `mc()` does (:2047-2055). */
+enum { RB200_COMP_AVG = 0, RB200_COMP_WEIGHTED_AVG = 1, RB200_COMP_SEG = 2 };
+typedef struct Rb200CompItem {
+    int16_t x, y;        /* top-left of the block in the luma plane, pixels */
+    uint8_t w, h;        /* luma block size, 8..128 */
+    uint8_t ref[2];      /* reference slots */
+    int16_t mv[2][2];    /* mv[i] = {y, x}, 1/8 luma pel */
+    uint8_t filter2d;
+    uint8_t comp_type;   /* RB200_COMP_* */
+    uint8_t jnt_weight;  /* w_avg weight, f.jnt_weights[ref0][ref1] (src/decode.rs:4354-4386) */
+    uint8_t mask_sign;
+    uint8_t pad[12];
+} Rb200CompItem;         /* 32 bytes */
+
 /* ------------------------------------------------------------ loop filter */
 /* Av1FilterLUT, src/lf_mask.rs:24-28 */
 typedef struct Rb200Av1FilterLUT {
@@ -405,6 +424,11 @@ Rb200Av1Filter *rb200_frame_lf_masks(Rb200Frame *f);          /* [sb128h * sb128
 uint8_t (*rb200_frame_lf_levels(Rb200Frame *f))[4];           /* [b4_stride * 32 * sb128h] */
 Rb200Av1FilterLUT *rb200_frame_lf_lut(Rb200Frame *f);
 Rb200Av1Restoration *rb200_frame_lr_masks(Rb200Frame *f);     /* [sb128h * sb128w] */
+/* Compound blocks: reserve the staging once, then set the count before each submit that has
+ * RB200_STAGE_RECON (blocks of put items and compound items must not overlap). */
+int rb200_frame_reserve_comp_items(Rb200Frame *f, int max_comp_items);
+Rb200CompItem *rb200_frame_comp_items(Rb200Frame *f);
+int rb200_frame_set_comp_count(Rb200Frame *f, int n_comp_items);
 /* Reference pictures: device planes (layout of rb200_frame_geometry) that stay resident. */
 int rb200_frame_set_ref(Rb200Frame *f, int slot, const Rb200Planes *planes);
 /* Upload a host picture into one of the frame's own plane sets (0 = current/recon). */

@@ -353,3 +353,85 @@ void ref_frame_apply_grain(RefFrame *r, const Dav1dFilmGrainData *data, int is_i
     else dav1d_apply_grain_8bpc(&f->dsp->fg, &r->grain_out, &in);
 }
 void *ref_frame_grain_plane(RefFrame *r, int pl) { return r->grain_out.data[pl]; }
+
+/* ------------------------------------------------------- compound blocks */
+/* The compound branch of dav1d_recon_b_inter (src/recon_tmpl.c:1836-1921) for avg / w_avg / seg,
+ * with the addressing of mc() (src/recon_tmpl.c:1036-1106). */
+typedef void (*mct_fn8)(int16_t *, const void *, ptrdiff_t, int, int, int, int);
+typedef void (*mct_fn16)(int16_t *, const void *, ptrdiff_t, int, int, int, int, int);
+typedef struct CompArgs { const Rb200CompItem *it; RefFrame *refs[8]; int n, chunk; } CompArgs;
+
+static void comp_prep(RefFrame *r, const RefFrame *rfr, int16_t *tmp, int pl, int px0, int py0, int bw, int bh,
+                      int mvx, int mvy, int filter2d, uint8_t *emu) {
+    Dav1dFrameContext *f = r->f;
+    const Dav1dFrameContext *rf = rfr->f;
+    const int px = r->hbd ? 2 : 1;
+    const int ss_hor = pl && f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444, ss_ver = pl && f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420;
+    const int w = (f->cur.p.w + ss_hor) >> ss_hor, h = (f->cur.p.h + ss_ver) >> ss_ver;
+    const int mx = (mvx & (15 >> !ss_hor)) << !ss_hor, my = (mvy & (15 >> !ss_ver)) << !ss_ver;
+    const int dx = px0 + (mvx >> (3 + ss_hor)), dy = py0 + (mvy >> (3 + ss_ver));
+    ptrdiff_t ref_stride = rf->cur.stride[!!pl];
+    const uint8_t *ref;
+    if (dx < !!mx * 3 || dy < !!my * 3 || dx + bw + !!mx * 4 > w || dy + bh + !!my * 4 > h) {
+        ((void (*)(intptr_t, intptr_t, intptr_t, intptr_t, intptr_t, intptr_t, void *, ptrdiff_t, const void *, ptrdiff_t))
+             f->dsp->mc.emu_edge)(bw + !!mx * 7, bh + !!my * 7, w, h, dx - !!mx * 3, dy - !!my * 3, emu, 192 * px,
+                                  rf->cur.data[pl], ref_stride);
+        ref = emu + (192 * !!my * 3 + !!mx * 3) * px;
+        ref_stride = 192 * px;
+    } else {
+        ref = (const uint8_t *)rf->cur.data[pl] + ref_stride * dy + (ptrdiff_t)dx * px;
+    }
+    if (r->hbd) ((mct_fn16)f->dsp->mc.mct[filter2d])(tmp, ref, ref_stride, bw, bh, mx, my, r->bdmax);
+    else ((mct_fn8)f->dsp->mc.mct[filter2d])(tmp, ref, ref_stride, bw, bh, mx, my);
+}
+
+static void do_comp_chunk(RefFrame *r, int tid, int chunk, void *arg) {
+    (void)tid;
+    CompArgs *a = arg;
+    Dav1dFrameContext *f = r->f;
+    const int px = r->hbd ? 2 : 1;
+    const int layout = f->cur.p.layout;
+    const int ss_hor_c = layout != DAV1D_PIXEL_LAYOUT_I444, ss_ver_c = layout == DAV1D_PIXEL_LAYOUT_I420;
+    const int n_planes = layout == DAV1D_PIXEL_LAYOUT_I400 ? 1 : 3;
+    const int chr_layout_idx = layout == DAV1D_PIXEL_LAYOUT_I400 ? 0 : DAV1D_PIXEL_LAYOUT_I444 - layout;
+    uint8_t *emu = malloc(320 * (256 + 7) * 2);
+    int16_t (*tmp)[128 * 128] = malloc(2 * sizeof(*tmp));
+    uint8_t *seg_mask = malloc(128 * 128);
+    const int lo = chunk * a->chunk, hi = lo + a->chunk < a->n ? lo + a->chunk : a->n;
+    for (int i = lo; i < hi; i++) {
+        const Rb200CompItem *it = &a->it[i];
+        for (int pl = 0; pl < n_planes; pl++) {
+            const int ss_hor = pl && ss_hor_c, ss_ver = pl && ss_ver_c;
+            const int bw = it->w >> ss_hor, bh = it->h >> ss_ver, x0 = it->x >> ss_hor, y0 = it->y >> ss_ver;
+            for (int k = 0; k < 2; k++)
+                comp_prep(r, a->refs[it->ref[k]], tmp[k], pl, x0, y0, bw, bh, it->mv[k][1], it->mv[k][0], it->filter2d, emu);
+            uint8_t *dst = (uint8_t *)f->cur.data[pl] + f->cur.stride[!!pl] * y0 + (ptrdiff_t)x0 * px;
+            const ptrdiff_t ds = f->cur.stride[!!pl];
+            const int s = it->mask_sign;
+#define CALL8(fn, ...) ((void (*)())(fn))(__VA_ARGS__)
+            if (it->comp_type == RB200_COMP_AVG) {
+                if (r->hbd) ((void (*)(void *, ptrdiff_t, const int16_t *, const int16_t *, int, int, int))f->dsp->mc.avg)(dst, ds, tmp[0], tmp[1], bw, bh, r->bdmax);
+                else ((void (*)(void *, ptrdiff_t, const int16_t *, const int16_t *, int, int))f->dsp->mc.avg)(dst, ds, tmp[0], tmp[1], bw, bh);
+            } else if (it->comp_type == RB200_COMP_WEIGHTED_AVG) {
+                if (r->hbd) ((void (*)(void *, ptrdiff_t, const int16_t *, const int16_t *, int, int, int, int))f->dsp->mc.w_avg)(dst, ds, tmp[0], tmp[1], bw, bh, it->jnt_weight, r->bdmax);
+                else ((void (*)(void *, ptrdiff_t, const int16_t *, const int16_t *, int, int, int))f->dsp->mc.w_avg)(dst, ds, tmp[0], tmp[1], bw, bh, it->jnt_weight);
+            } else if (pl == 0) {
+                if (r->hbd) ((void (*)(void *, ptrdiff_t, const int16_t *, const int16_t *, int, int, uint8_t *, int, int))f->dsp->mc.w_mask[chr_layout_idx])(dst, ds, tmp[s], tmp[!s], bw, bh, seg_mask, s, r->bdmax);
+                else ((void (*)(void *, ptrdiff_t, const int16_t *, const int16_t *, int, int, uint8_t *, int))f->dsp->mc.w_mask[chr_layout_idx])(dst, ds, tmp[s], tmp[!s], bw, bh, seg_mask, s);
+            } else {
+                if (r->hbd) ((void (*)(void *, ptrdiff_t, const int16_t *, const int16_t *, int, int, const uint8_t *, int))f->dsp->mc.mask)(dst, ds, tmp[s], tmp[!s], bw, bh, seg_mask, r->bdmax);
+                else ((void (*)(void *, ptrdiff_t, const int16_t *, const int16_t *, int, int, const uint8_t *))f->dsp->mc.mask)(dst, ds, tmp[s], tmp[!s], bw, bh, seg_mask);
+            }
+#undef CALL8
+        }
+    }
+    free(seg_mask); free(tmp); free(emu);
+}
+
+void ref_frame_recon_comp(RefFrame *r, RefFrame *const refs[], int n_refs, const Rb200CompItem *items, int n, int n_threads) {
+    CompArgs a;
+    memset(&a, 0, sizeof(a));
+    a.it = items; a.n = n; a.chunk = 64;
+    for (int i = 0; i < n_refs && i < 8; i++) a.refs[i] = refs[i];
+    parallel_for(r, n_threads, (n + a.chunk - 1) / a.chunk, do_comp_chunk, &a);
+}

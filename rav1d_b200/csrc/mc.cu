@@ -514,6 +514,104 @@ mc_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int ss_hor
     cp_async_wait<0>();
 }
 
+// ---------------------------------------------------------------- compound blocks (batch)
+// One warp per block.  Per 16x16 luma tile: both references are predicted in `prep` form into
+// shared memory, combined into the luma plane, and -- for the segmentation compound -- the full
+// resolution blend mask stays in shared memory for the co-located chroma tiles, which derive
+// their sub-sampled mask exactly as w_mask does (src/mc.rs:812-883).
+struct McCompSmem {
+    McSmem slow;
+    int16_t tmp[2][MC_TILE * MC_TILE];
+    uint8_t mask[MC_TILE * MC_TILE];
+};
+
+template <typename BD>
+__global__ void __launch_bounds__(MC_WARPS * 32)
+mc_comp_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int layout,
+                     const Rb200CompItem *__restrict__ items, int n_items, int bdmax) {
+    using pixel = typename BD::pixel;
+    __shared__ McCompSmem smem[MC_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * MC_WARPS + warp;
+    if (idx >= n_items) return;
+    McCompSmem &sm = smem[warp];
+    const Rb200CompItem it = items[idx];
+    const int n_planes = layout == RB200_LAYOUT_I400 ? 1 : 3;
+    const int ss_hor_c = layout != RB200_LAYOUT_I444, ss_ver_c = layout == RB200_LAYOUT_I420;
+    const int ib = McBits<BD>::ib(bdmax), pb = McBits<BD>::prep_bias;
+    const int bitdepth = BD::hbd ? bpc_from_max(bdmax) : 8;
+    const int mask_sh = bitdepth + ib - 4, mask_rnd = 1 << (mask_sh - 5);
+    const int s1 = it.comp_type == RB200_COMP_AVG ? 0 : it.mask_sign;   // tmp1 = tmp[mask_sign] for masks
+    for (int ty = 0; ty < it.h; ty += MC_TILE) {
+        for (int tx = 0; tx < it.w; tx += MC_TILE) {
+            const int tw = imin(MC_TILE, it.w - tx), th = imin(MC_TILE, it.h - ty);
+            for (int pl = 0; pl < n_planes; pl++) {
+                const int ss_hor = pl ? ss_hor_c : 0, ss_ver = pl ? ss_ver_c : 0;
+                const int pw = tw >> ss_hor, ph = th >> ss_ver;          // tile size in this plane
+                const int px0 = (it.x + tx) >> ss_hor, py0 = (it.y + ty) >> ss_ver;
+#pragma unroll 1
+                for (int i = 0; i < 2; i++) {
+                    const Rb200Planes &rp = refs.p[it.ref[i] & 7];
+                    McRef ref;
+                    ref.base = plane_ptr(rp, pl);
+                    ref.stride = plane_stride(rp, pl);
+                    ref.w = pl ? (ref_w + ss_hor) >> ss_hor : ref_w;
+                    ref.h = pl ? (ref_h + ss_ver) >> ss_ver : ref_h;
+                    const int mvy = it.mv[i][0], mvx = it.mv[i][1];
+                    // src/recon.rs:2047-2055,2100-2101
+                    const int mx = (mvx & (15 >> !ss_hor)) << !ss_hor, my = (mvy & (15 >> !ss_ver)) << !ss_ver;
+                    const int sx = px0 + (mvx >> (3 + ss_hor)), sy = py0 + (mvy >> (3 + ss_ver));
+                    mc_tile<BD, true>(sm.slow, ref, sx, sy, pw, ph, it.w >> ss_hor, it.h >> ss_ver, mx, my, it.filter2d,
+                                      sm.tmp[i], MC_TILE, bdmax);
+                }
+                __syncwarp();
+                uint8_t *dbase = plane_ptr(dst, pl);
+                const int64_t dstride = plane_stride(dst, pl);
+                const int16_t *t1 = sm.tmp[s1], *t2 = sm.tmp[s1 ^ 1];
+                for (int e = lane; e < pw * ph; e += 32) {
+                    const int r = e / pw, c = e - r * pw;
+                    const int a = t1[r * MC_TILE + c], b = t2[r * MC_TILE + c];
+                    int v;
+                    if (it.comp_type == RB200_COMP_AVG) {
+                        v = (a + b + (1 << ib) + pb * 2) >> (ib + 1);
+                    } else if (it.comp_type == RB200_COMP_WEIGHTED_AVG) {
+                        // w_avg(tmp[0], tmp[1], weight): no sign swap
+                        const int a0 = sm.tmp[0][r * MC_TILE + c], b0 = sm.tmp[1][r * MC_TILE + c];
+                        v = (a0 * it.jnt_weight + b0 * (16 - it.jnt_weight) + (8 << ib) + pb * 16) >> (ib + 4);
+                    } else {
+                        int m;
+                        if (pl == 0) {
+                            const int d = a - b;
+                            m = imin(38 + (((d < 0 ? -d : d) + mask_rnd) >> mask_sh), 64);
+                            sm.mask[r * MC_TILE + c] = (uint8_t)m;
+                        } else {
+                            const uint8_t *mp = sm.mask + (r << ss_ver) * MC_TILE + (c << ss_hor);
+                            if (ss_hor && ss_ver) m = (mp[0] + mp[1] + mp[MC_TILE] + mp[MC_TILE + 1] + 2 - it.mask_sign) >> 2;
+                            else if (ss_hor) m = (mp[0] + mp[1] + 1 - it.mask_sign) >> 1;
+                            else m = mp[0];
+                        }
+                        v = (a * m + b * (64 - m) + (32 << ib) + pb * 64) >> (ib + 6);
+                    }
+                    ((pixel *)(dbase + (int64_t)(py0 + r) * dstride))[px0 + c] = (pixel)iclip(v, 0, bdmax);
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+int mc_comp_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int layout,
+                         const Rb200CompItem *d_items, int n, int bdmax, cudaStream_t st) {
+    if (n <= 0) return 0;
+    McRefSet rs = {};
+    for (int i = 0; i < n_refs && i < 8; i++) rs.p[i] = refs[i];
+    const int grid = (n + MC_WARPS - 1) / MC_WARPS;
+    if (bdmax > 255) mc_comp_batch_kernel<BD16><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, layout, d_items, n, bdmax);
+    else mc_comp_batch_kernel<BD8><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, layout, d_items, n, bdmax);
+    RB_LAUNCH_CHECK();
+    return 0;
+}
+
 // Per-call: a single prediction block over a staged source rectangle; one warp per 16x16 tile.
 template <typename BD, bool PREP>
 __global__ void __launch_bounds__(MC_WARPS * 32)

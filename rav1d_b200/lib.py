@@ -105,7 +105,11 @@ AV1_FILTER_DT = _np.dtype([("filter_y", "<u2", (2, 32, 3, 2)), ("filter_uv", "<u
 LR_UNIT_DT = _np.dtype([("type", "u1"), ("filter_h", "i1", (3,)), ("filter_v", "i1", (3,)),
                         ("sgr_weights", "i1", (2,))])
 AV1_RESTORATION_DT = _np.dtype([("lr", LR_UNIT_DT, (3, 4))])
-assert MC_ITEM_DT.itemsize == 16 and ITX_ITEM_DT.itemsize == 16
+COMP_ITEM_DT = _np.dtype([("x", "<i2"), ("y", "<i2"), ("w", "u1"), ("h", "u1"), ("ref", "u1", (2,)), ("mv", "<i2", (2, 2)),
+                          ("filter2d", "u1"), ("comp_type", "u1"), ("jnt_weight", "u1"), ("mask_sign", "u1"),
+                          ("pad", "u1", (12,))])
+COMP_AVG, COMP_WEIGHTED_AVG, COMP_SEG = 0, 1, 2
+assert MC_ITEM_DT.itemsize == 16 and ITX_ITEM_DT.itemsize == 16 and COMP_ITEM_DT.itemsize == 32
 assert AV1_FILTER_DT.itemsize == 1348 and AV1_RESTORATION_DT.itemsize == 108
 
 
@@ -191,6 +195,9 @@ frame_lf_masks = _sig("rb200_frame_lf_masks", _vp, _vp)
 frame_lf_levels = _sig("rb200_frame_lf_levels", _vp, _vp)
 frame_lf_lut = _sig("rb200_frame_lf_lut", _vp, _vp)
 frame_lr_masks = _sig("rb200_frame_lr_masks", _vp, _vp)
+frame_reserve_comp_items = _sig("rb200_frame_reserve_comp_items", _i, _vp, _i)
+frame_comp_items = _sig("rb200_frame_comp_items", _vp, _vp)
+frame_set_comp_count = _sig("rb200_frame_set_comp_count", _i, _vp, _i)
 frame_set_ref = _sig("rb200_frame_set_ref", _i, _vp, _i, C.POINTER(Planes))
 frame_upload_planes = _sig("rb200_frame_upload_planes", _i, _vp, _i, C.POINTER(_vp), C.POINTER(_ss))
 frame_output_planes = _sig("rb200_frame_output_planes", _i, _vp, C.POINTER(Planes))

@@ -93,7 +93,7 @@ def geometry(hd):
     return g
 
 
-def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1):
+def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1, comp_frac=0.0):
     """Returns a SynthFrame with numpy arrays; see module docstring."""
     rng = np.random.default_rng(seed)
     bdmax = (1 << bpc) - 1
@@ -129,6 +129,28 @@ def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1):
     ctx_split = (rng.random(nb) < 0.2) & ~skip  # chroma: TX_8X8 or 4 x TX_4X4
     s.n_blocks = nb
 
+    # compound blocks (BASELINE config 5): a second reference, a second vector, avg / w_avg / seg
+    is_comp = rng.random(nb) < comp_frac
+    mvx2 = rng.integers(-512, 513, size=nb); mvy2 = rng.integers(-512, 513, size=nb)
+    mvx2[rng.random(nb) < 0.15] &= ~7
+    mvy2[rng.random(nb) < 0.15] &= ~7
+    comp = np.zeros(int(is_comp.sum()), lib.COMP_ITEM_DT)
+    ci = np.nonzero(is_comp)[0]
+    comp["x"] = bx[ci] * BLK; comp["y"] = by[ci] * BLK; comp["w"] = BLK; comp["h"] = BLK
+    comp["ref"][:, 0] = 0; comp["ref"][:, 1] = 1
+    comp["mv"][:, 0, 0] = mvy[ci]; comp["mv"][:, 0, 1] = mvx[ci]
+    comp["mv"][:, 1, 0] = mvy2[ci]; comp["mv"][:, 1, 1] = mvx2[ci]
+    comp["filter2d"] = f2d[ci]
+    comp["comp_type"] = rng.integers(0, 3, size=ci.size)
+    comp["jnt_weight"] = rng.choice(np.array([3, 5, 7, 9, 11, 13]), size=ci.size)   # dav1d quant_dist_lookup_table values
+    comp["mask_sign"] = rng.integers(0, 2, size=ci.size)
+    s.comp_items = comp
+    if comp_frac > 0:
+        s.ref2 = [np.zeros((ah, aw), pdt), np.zeros((ah // 2, aw // 2), pdt), np.zeros((ah // 2, aw // 2), pdt)]
+        s.ref2[0][:h, :w] = smooth_plane(rng, h, w, bdmax)
+        for p in (1, 2):
+            s.ref2[p][:(h + 1) // 2, :(w + 1) // 2] = smooth_plane(rng, (h + 1) // 2, (w + 1) // 2, bdmax, cell=8)
+
     mc = np.zeros(nb * 3, lib.MC_ITEM_DT)
     y_it = mc[:nb]
     y_it["dst_x"] = bx * BLK; y_it["dst_y"] = by * BLK
@@ -143,7 +165,8 @@ def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1):
         c_it["w"] = BLK // 2; c_it["h"] = BLK // 2; c_it["plane"] = p
         c_it["mx"] = mvx & 15; c_it["my"] = mvy & 15
         c_it["filter2d"] = f2d
-    s.mc_items = mc
+    keep = np.tile(~is_comp, 3)
+    s.mc_items = np.ascontiguousarray(mc[keep])
 
     # ---- transform blocks: (plane, x, y, tx, txtp)
     TX_4X4, TX_8X8, TX_16X16 = 0, 1, 2
@@ -331,6 +354,7 @@ class DeviceFrame:
         lib.check(lib.frame_geometry(self.h, C.byref(g)))
         self.g = g
         self.ref_handle = None
+        self.ref_handles = {}
 
     def close(self):
         if self.h:
@@ -339,6 +363,9 @@ class DeviceFrame:
         if self.ref_handle:
             lib.frame_destroy(self.ref_handle)
             self.ref_handle = None
+        for hnd in self.ref_handles.values():
+            lib.frame_destroy(hnd)
+        self.ref_handles = {}
 
     def load_batch(self):
         s, g = self.s, self.g
@@ -351,6 +378,11 @@ class DeviceFrame:
         lv[:] = s.levels.reshape(-1)
         C.memmove(lib.frame_lf_lut(self.h), C.byref(s.lut), C.sizeof(lib.FilterLUT))
         lib.np_view(lib.frame_lr_masks(self.h), lib.AV1_RESTORATION_DT, n)[:] = s.lr_masks
+        comp = getattr(s, "comp_items", None)
+        if comp is not None and len(comp):
+            lib.check(lib.frame_reserve_comp_items(self.h, len(comp)), "reserve_comp_items")
+            lib.np_view(lib.frame_comp_items(self.h), lib.COMP_ITEM_DT, len(comp))[:] = comp
+            lib.check(lib.frame_set_comp_count(self.h, len(comp)))
 
     def upload(self, which, planes):
         data = (C.c_void_p * 3)(*[p.ctypes.data for p in planes])
@@ -368,6 +400,20 @@ class DeviceFrame:
         pl = lib.Planes()
         lib.check(lib.frame_stage_planes(self.ref_handle, 0, C.byref(pl)))
         lib.check(lib.frame_set_ref(self.h, 0, C.byref(pl)))
+
+    def set_ref_slot(self, slot, planes):
+        """Upload a reference picture into its own device-resident frame object and bind it to `slot`."""
+        if slot not in self.ref_handles:
+            hnd = C.c_void_p()
+            lib.check(lib.frame_create(C.byref(hnd), C.byref(self.s.hdr), 1, 1, 1), "frame_create(ref)")
+            self.ref_handles[slot] = hnd
+        hnd = self.ref_handles[slot]
+        data = (C.c_void_p * 3)(*[p.ctypes.data for p in planes])
+        strides = (C.c_ssize_t * 2)(planes[0].strides[0], planes[1].strides[0])
+        lib.check(lib.frame_upload_planes(hnd, 0, data, strides))
+        pl = lib.Planes()
+        lib.check(lib.frame_stage_planes(hnd, 0, C.byref(pl)))
+        lib.check(lib.frame_set_ref(self.h, slot, C.byref(pl)))
 
     def submit(self, stages, upload=True):
         """upload: False / 0 = batch already on the device, True / 1 = copy the batch, 2 = copy everything but the

@@ -10,11 +10,14 @@ def oracle_frame(ref, s, stages, n_tc=1, start_planes=None):
     from rav1d_b200 import lib
     cur = refharness.RefFrame(ref, s, n_tc)
     rf = refharness.RefFrame(ref, s, 1)
+    rf2 = refharness.RefFrame(ref, s, 1) if hasattr(s, "ref2") else None
     try:
         rf.set_planes(s.ref)
+        if rf2:
+            rf2.set_planes(s.ref2)
         cur.load_filter_meta()
         if stages & lib.STAGE_RECON:
-            cur.recon(rf, n_threads=n_tc)
+            cur.recon(rf, n_threads=n_tc, ref_frame2=rf2)
         else:
             cur.set_planes(start_planes)
         if stages & ~lib.STAGE_RECON:
@@ -23,6 +26,8 @@ def oracle_frame(ref, s, stages, n_tc=1, start_planes=None):
     finally:
         cur.close()
         rf.close()
+        if rf2:
+            rf2.close()
 
 
 def product_frame(s, stages, start_planes=None, upload=1):
@@ -33,6 +38,8 @@ def product_frame(s, stages, start_planes=None, upload=1):
         d.load_batch()
         if stages & lib.STAGE_RECON:
             d.set_ref_from_host(s.ref)
+            if hasattr(s, "ref2"):
+                d.set_ref_slot(1, s.ref2)
         else:
             d.upload(0, start_planes)
         d.submit(stages, upload)

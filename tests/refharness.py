@@ -65,6 +65,7 @@ def load():
         sig("ref_frame_sbh", i, vp)
         sig("ref_frame_filter", None, vp, i, i)
         sig("ref_frame_recon", None, vp, vp, i, vp, i, vp, i, vp, i)
+        sig("ref_frame_recon_comp", None, vp, vp, i, vp, i, i)
         sig("ref_frame_apply_grain", None, vp, vp, i)
         sig("ref_frame_grain_plane", vp, vp, i)
         sig("ref_fg_gen_y", None, vp, vp, i)
@@ -122,13 +123,21 @@ class RefFrame:
         C.memmove(ref.ref_frame_lut(self.h), C.byref(s.lut), C.sizeof(lib.FilterLUT))
         lib.np_view(ref.ref_frame_lr_masks(self.h), lib.AV1_RESTORATION_DT, n)[:] = s.lr_masks
 
-    def recon(self, ref_frame, n_threads=1, coef_work=None):
+    def recon(self, ref_frame, n_threads=1, coef_work=None, ref_frame2=None):
+        """Prediction (put items, then compound blocks) and residual, in the reference's DSP calls."""
         s = self.s
         cw = s.coef.copy() if coef_work is None else coef_work
-        refs = (C.c_void_p * 1)(ref_frame.h)
+        frames = [ref_frame] + ([ref_frame2] if ref_frame2 is not None else [])
+        refs = (C.c_void_p * len(frames))(*[f.h for f in frames])
         mc = np.ascontiguousarray(s.mc_items)
         itx = np.ascontiguousarray(s.itx_items)
-        self.ref.ref_frame_recon(self.h, refs, 1, ptr(mc), len(mc), ptr(itx), len(itx), ptr(cw), n_threads)
+        comp = np.ascontiguousarray(getattr(s, "comp_items", np.zeros(0, np.uint8)))
+        if len(comp):
+            self.ref.ref_frame_recon(self.h, refs, len(frames), ptr(mc), len(mc), ptr(itx), 0, ptr(cw), n_threads)
+            self.ref.ref_frame_recon_comp(self.h, refs, len(frames), ptr(comp), len(comp), n_threads)
+            self.ref.ref_frame_recon(self.h, refs, len(frames), ptr(mc), 0, ptr(itx), len(itx), ptr(cw), n_threads)
+        else:
+            self.ref.ref_frame_recon(self.h, refs, len(frames), ptr(mc), len(mc), ptr(itx), len(itx), ptr(cw), n_threads)
         return cw
 
     def apply_grain(self, fg, is_id=0):

@@ -91,9 +91,9 @@ def main():
         for p in range(3):
             a, b = (lo, hi) if p == 0 else (lo >> 1, (hi + 1) >> 1)
             good &= bool(np.array_equal(exp[p][a:b], out[p][a:b, :exp[p].shape[1]]))
-        flag = torch.tensor([1 if good else 0], device="cuda")
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        ok = bool(flag.item())
+        good_t = torch.tensor([1 if good else 0], device="cuda")
+        dist.all_reduce(good_t, op=dist.ReduceOp.MIN)
+        ok = bool(good_t.item())
     hb = torch.tensor([band.halo_bytes()], dtype=torch.float64, device="cuda")
     dist.all_reduce(hb, op=dist.ReduceOp.MAX)
     if rank == 0:
