@@ -240,6 +240,19 @@ typedef struct Rb200CompItem {
     uint8_t pad[12];
 } Rb200CompItem;         /* 32 bytes */
 
+/* Warped (affine) prediction, one record per BLOCK (all planes): recon.rs `warp_affine`
+ * (src/recon.rs:2311-2400; C: src/recon_tmpl.c:1139-1198) -- per 8x8 the position and phase follow from
+ * the warp matrix, then warp8x8 with the shear parameters.  Plane sizes must be multiples of 8. */
+typedef struct Rb200WarpItem {
+    int16_t x, y;        /* top-left of the block in the luma plane, pixels */
+    uint8_t w, h;        /* luma block size, 8..128 (chroma must come out >= 8: 16 with sub-sampling) */
+    uint8_t ref;
+    uint8_t pad0;
+    int32_t matrix[6];   /* Dav1dWarpedMotionParams.matrix */
+    int16_t abcd[4];     /* alpha, beta, gamma, delta */
+    uint8_t pad[8];
+} Rb200WarpItem;         /* 48 bytes */
+
 /* ------------------------------------------------------------ loop filter */
 /* Av1FilterLUT, src/lf_mask.rs:24-28 */
 typedef struct Rb200Av1FilterLUT {
@@ -429,6 +442,9 @@ Rb200Av1Restoration *rb200_frame_lr_masks(Rb200Frame *f);     /* [sb128h * sb128
 int rb200_frame_reserve_comp_items(Rb200Frame *f, int max_comp_items);
 Rb200CompItem *rb200_frame_comp_items(Rb200Frame *f);
 int rb200_frame_set_comp_count(Rb200Frame *f, int n_comp_items);
+int rb200_frame_reserve_warp_items(Rb200Frame *f, int max_warp_items);
+Rb200WarpItem *rb200_frame_warp_items(Rb200Frame *f);
+int rb200_frame_set_warp_count(Rb200Frame *f, int n_warp_items);
 /* Reference pictures: device planes (layout of rb200_frame_geometry) that stay resident. */
 int rb200_frame_set_ref(Rb200Frame *f, int slot, const Rb200Planes *planes);
 /* Upload a host picture into one of the frame's own plane sets (0 = current/recon). */

@@ -435,3 +435,58 @@ void ref_frame_recon_comp(RefFrame *r, RefFrame *const refs[], int n_refs, const
     for (int i = 0; i < n_refs && i < 8; i++) a.refs[i] = refs[i];
     parallel_for(r, n_threads, (n + a.chunk - 1) / a.chunk, do_comp_chunk, &a);
 }
+
+/* --------------------------------------------------------- warped blocks */
+/* warp_affine (src/recon_tmpl.c:1139-1198) for put, driven by Rb200WarpItem. */
+typedef struct WarpArgs { const Rb200WarpItem *it; RefFrame *refs[8]; int n; } WarpArgs;
+static void do_warp_item(RefFrame *r, int tid, int i, void *arg) {
+    (void)tid;
+    WarpArgs *a = arg;
+    Dav1dFrameContext *f = r->f;
+    const Rb200WarpItem *it = &a->it[i];
+    const Dav1dFrameContext *rf = a->refs[it->ref]->f;
+    const int px = r->hbd ? 2 : 1;
+    const int layout = f->cur.p.layout;
+    const int n_planes = layout == DAV1D_PIXEL_LAYOUT_I400 ? 1 : 3;
+    uint8_t emu[32 * 32 * 2];
+    for (int pl = 0; pl < n_planes; pl++) {
+        const int ss_ver = pl && layout == DAV1D_PIXEL_LAYOUT_I420, ss_hor = pl && layout != DAV1D_PIXEL_LAYOUT_I444;
+        const int32_t *mat = it->matrix;
+        const int width = (rf->cur.p.w + ss_hor) >> ss_hor, height = (rf->cur.p.h + ss_ver) >> ss_ver;
+        uint8_t *dst8 = (uint8_t *)f->cur.data[pl] + f->cur.stride[!!pl] * (it->y >> ss_ver) + (ptrdiff_t)(it->x >> ss_hor) * px;
+        for (int y = 0; y < it->h >> ss_ver; y += 8) {
+            const int src_y = it->y + ((y + 4) << ss_ver);
+            const int64_t mat3_y = (int64_t)mat[3] * src_y + mat[0];
+            const int64_t mat5_y = (int64_t)mat[5] * src_y + mat[1];
+            for (int x = 0; x < it->w >> ss_hor; x += 8) {
+                const int src_x = it->x + ((x + 4) << ss_hor);
+                const int64_t mvx = ((int64_t)mat[2] * src_x + mat3_y) >> ss_hor;
+                const int64_t mvy = ((int64_t)mat[4] * src_x + mat5_y) >> ss_ver;
+                const int dx = (int)(mvx >> 16) - 4;
+                const int mx = (((int)mvx & 0xffff) - it->abcd[0] * 4 - it->abcd[1] * 7) & ~0x3f;
+                const int dy = (int)(mvy >> 16) - 4;
+                const int my = (((int)mvy & 0xffff) - it->abcd[2] * 4 - it->abcd[3] * 4) & ~0x3f;
+                const uint8_t *ref_ptr;
+                ptrdiff_t ref_stride = rf->cur.stride[!!pl];
+                if (dx < 3 || dx + 8 + 4 > width || dy < 3 || dy + 8 + 4 > height) {
+                    ((void (*)(intptr_t, intptr_t, intptr_t, intptr_t, intptr_t, intptr_t, void *, ptrdiff_t, const void *, ptrdiff_t))
+                         f->dsp->mc.emu_edge)(15, 15, width, height, dx - 3, dy - 3, emu, 32 * px, rf->cur.data[pl], ref_stride);
+                    ref_ptr = emu + (32 * 3 + 3) * px;
+                    ref_stride = 32 * px;
+                } else {
+                    ref_ptr = (const uint8_t *)rf->cur.data[pl] + ref_stride * dy + (ptrdiff_t)dx * px;
+                }
+                uint8_t *d = dst8 + f->cur.stride[!!pl] * y + (ptrdiff_t)x * px;
+                if (r->hbd) ((void (*)(void *, ptrdiff_t, const void *, ptrdiff_t, const int16_t *, int, int, int))f->dsp->mc.warp8x8)(d, f->cur.stride[!!pl], ref_ptr, ref_stride, it->abcd, mx, my, r->bdmax);
+                else ((void (*)(void *, ptrdiff_t, const void *, ptrdiff_t, const int16_t *, int, int))f->dsp->mc.warp8x8)(d, f->cur.stride[!!pl], ref_ptr, ref_stride, it->abcd, mx, my);
+            }
+        }
+    }
+}
+void ref_frame_recon_warp(RefFrame *r, RefFrame *const refs[], int n_refs, const Rb200WarpItem *items, int n, int n_threads) {
+    WarpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.it = items; a.n = n;
+    for (int i = 0; i < n_refs && i < 8; i++) a.refs[i] = refs[i];
+    parallel_for(r, n_threads, n, do_warp_item, &a);
+}

@@ -19,6 +19,8 @@
 // packed cf).
 #include "common.cuh"
 #include <new>
+#include <stdio.h>
+#include <stdlib.h>
 
 struct Rb200Frame {
     Rb200FrameHeader hdr;
@@ -38,6 +40,7 @@ struct Rb200Frame {
     Rb200ItxItem *h_itx, *d_itx;
     Rb200McItem *h_mc, *d_mc;
     Rb200CompItem *h_comp, *d_comp; int max_comp, n_comp;
+    Rb200WarpItem *h_warp, *d_warp; int max_warp, n_warp;
     Rb200Av1Filter *h_masks, *d_masks;
     uint8_t (*h_lvl)[4], (*d_lvl)[4];
     Rb200Av1FilterLUT *h_lut, *d_lut;
@@ -162,6 +165,8 @@ extern "C" int rb200_frame_destroy(Rb200Frame *f) {
     if (f->d_coef) cudaFree(f->d_coef);
     if (f->h_itx) cudaFreeHost(f->h_itx);
     if (f->d_itx) cudaFree(f->d_itx);
+    if (f->h_warp) cudaFreeHost(f->h_warp);
+    if (f->d_warp) cudaFree(f->d_warp);
     if (f->h_comp) cudaFreeHost(f->h_comp);
     if (f->d_comp) cudaFree(f->d_comp);
     if (f->h_mc) cudaFreeHost(f->h_mc);
@@ -437,6 +442,25 @@ extern "C" int rb200_frame_set_comp_count(Rb200Frame *f, int n) {
     return 0;
 }
 
+extern "C" int rb200_frame_reserve_warp_items(Rb200Frame *f, int max_warp) {
+    if (!f || max_warp < 0) return set_error(-22, "frame_reserve_warp_items: bad argument");
+    if (max_warp <= f->max_warp) return 0;
+    RB_CUDA(cudaStreamSynchronize(f->stream));
+    if (f->h_warp) cudaFreeHost(f->h_warp);
+    if (f->d_warp) cudaFree(f->d_warp);
+    f->h_warp = nullptr; f->d_warp = nullptr; f->max_warp = 0; f->n_warp = 0;
+    const int r = alloc_pair(&f->h_warp, &f->d_warp, (size_t)max_warp);
+    if (r) return r;
+    f->max_warp = max_warp;
+    return 0;
+}
+extern "C" Rb200WarpItem *rb200_frame_warp_items(Rb200Frame *f) { return f ? f->h_warp : nullptr; }
+extern "C" int rb200_frame_set_warp_count(Rb200Frame *f, int n) {
+    if (!f || n < 0 || n > f->max_warp) return set_error(-22, "frame_set_warp_count: more items than reserved");
+    f->n_warp = n;
+    return 0;
+}
+
 extern "C" int rb200_frame_set_ref(Rb200Frame *f, int slot, const Rb200Planes *planes) {
     if (!f || slot < 0 || slot > 7 || !planes) return set_error(-22, "frame_set_ref: bad argument");
     f->refs[slot] = *planes;
@@ -531,7 +555,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         }
         if (n_coefs > f->max_coefs || n_itx > f->max_itx || n_mc > f->max_mc || n_mc < 0)
             return set_error(-22, "frame_submit: batch larger than the frame was created for");
-        if ((n_mc || f->n_comp) && f->n_refs < 1) return set_error(-22, "frame_submit: no reference picture set");
+        if ((n_mc || f->n_comp || f->n_warp) && f->n_refs < 1) return set_error(-22, "frame_submit: no reference picture set");
     }
     f->launches = 0;
     const BandRows band = band_rows(f);
@@ -552,6 +576,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
             if (n_itx) RB_CUDA(cudaMemcpyAsync(f->d_itx, f->h_itx, (size_t)n_itx * sizeof(Rb200ItxItem), cudaMemcpyHostToDevice, st));
             if (n_mc) RB_CUDA(cudaMemcpyAsync(f->d_mc, f->h_mc, (size_t)n_mc * sizeof(Rb200McItem), cudaMemcpyHostToDevice, st));
             if (f->n_comp) RB_CUDA(cudaMemcpyAsync(f->d_comp, f->h_comp, (size_t)f->n_comp * sizeof(Rb200CompItem), cudaMemcpyHostToDevice, st));
+            if (f->n_warp) RB_CUDA(cudaMemcpyAsync(f->d_warp, f->h_warp, (size_t)f->n_warp * sizeof(Rb200WarpItem), cudaMemcpyHostToDevice, st));
         }
         if (do_lf || do_cdef)
             RB_CUDA(cudaMemcpyAsync(f->d_masks, f->h_masks, f->n_masks * sizeof(Rb200Av1Filter), cudaMemcpyHostToDevice, st));
@@ -574,6 +599,11 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         }
         if (f->n_comp) {
             if ((r = mc_comp_batch_launch(f->planes[0], f->refs, f->n_refs, h.width, h.height, h.layout, f->d_comp, f->n_comp,
+                                          f->bdmax, st))) return r;
+            f->launches++;
+        }
+        if (f->n_warp) {
+            if ((r = mc_warp_batch_launch(f->planes[0], f->refs, f->n_refs, h.width, h.height, h.layout, f->d_warp, f->n_warp,
                                           f->bdmax, st))) return r;
             f->launches++;
         }
@@ -641,4 +671,4 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
 #undef MARK
     return 0;
 }
-static_assert(sizeof(Rb200CompItem) == 32 && sizeof(Rb200McItem) == 16 && sizeof(Rb200ItxItem) == 16, "batch record sizes");
+static_assert(sizeof(Rb200WarpItem) == 48 && sizeof(Rb200CompItem) == 32 && sizeof(Rb200McItem) == 16 && sizeof(Rb200ItxItem) == 16, "batch record sizes");

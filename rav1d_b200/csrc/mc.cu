@@ -612,6 +612,83 @@ int mc_comp_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_
     return 0;
 }
 
+// ---------------------------------------------------------------- warped blocks (batch)
+// One CTA per block, one warp per 8x8 (all planes): position / phase per 8x8 as warp_affine
+// (src/recon.rs:2311-2400), the 15x8 horizontal pass into warp-private shared memory, then the
+// vertical pass; source coordinates are clamped (emu_edge).
+template <typename BD>
+__global__ void __launch_bounds__(MC_WARPS * 32)
+mc_warp_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int layout,
+                     const Rb200WarpItem *__restrict__ items, int n_items, int bdmax) {
+    using pixel = typename BD::pixel;
+    __shared__ int16_t mid_s[MC_WARPS][15 * 8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if ((int)blockIdx.x >= n_items) return;
+    const Rb200WarpItem it = items[blockIdx.x];
+    int16_t *mid = mid_s[warp];
+    const int n_planes = layout == RB200_LAYOUT_I400 ? 1 : 3;
+    const int ss_hor_c = layout != RB200_LAYOUT_I444, ss_ver_c = layout == RB200_LAYOUT_I420;
+    const int ib = McBits<BD>::ib(bdmax);
+    const Rb200Planes &rp = refs.p[it.ref & 7];
+    const int a0 = it.abcd[0], a1 = it.abcd[1], a2 = it.abcd[2], a3 = it.abcd[3];
+    // enumerate the 8x8s of all planes
+    const int nbx0 = it.w >> 3, nby0 = it.h >> 3;
+    const int nbxc = it.w >> (3 + ss_hor_c), nbyc = it.h >> (3 + ss_ver_c);
+    const int n0 = nbx0 * nby0, nc = n_planes > 1 ? nbxc * nbyc : 0;
+    for (int t = warp; t < n0 + 2 * nc; t += MC_WARPS) {
+        const int pl = t < n0 ? 0 : (t < n0 + nc ? 1 : 2);
+        const int u = t - (pl == 0 ? 0 : (pl == 1 ? n0 : n0 + nc));
+        const int ss_hor = pl ? ss_hor_c : 0, ss_ver = pl ? ss_ver_c : 0;
+        const int nbx = pl ? nbxc : nbx0;
+        const int x = (u % nbx) * 8, y = (u / nbx) * 8;
+        const int width = pl ? (ref_w + ss_hor) >> ss_hor : ref_w, height = pl ? (ref_h + ss_ver) >> ss_ver : ref_h;
+        const int src_y = it.y + ((y + 4) << ss_ver), src_x = it.x + ((x + 4) << ss_hor);
+        const int64_t mvx = ((int64_t)it.matrix[2] * src_x + (int64_t)it.matrix[3] * src_y + it.matrix[0]) >> ss_hor;
+        const int64_t mvy = ((int64_t)it.matrix[4] * src_x + (int64_t)it.matrix[5] * src_y + it.matrix[1]) >> ss_ver;
+        const int dx = (int)(mvx >> 16) - 4, dy = (int)(mvy >> 16) - 4;
+        const int mx = (((int)mvx & 0xffff) - a0 * 4 - a1 * 7) & ~0x3f;
+        const int my = (((int)mvy & 0xffff) - a2 * 4 - a3 * 4) & ~0x3f;
+        const uint8_t *rbase = plane_ptr(rp, pl);
+        const int64_t rstride = plane_stride(rp, pl);
+        for (int i = lane; i < 15 * 8; i += 32) {
+            const int yy = i >> 3, xx = i & 7;
+            const int tmx = mx + yy * a1 + xx * a0;
+            const int8_t *f = tab::k_warp_filter + (64 + ((tmx + 512) >> 10)) * 8;
+            int acc = (1 << (7 - ib)) >> 1;
+            const pixel *row = (const pixel *)(rbase + (int64_t)iclip(dy + yy - 3, 0, height - 1) * rstride);
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc += f[k] * (int)row[iclip(dx + xx + k - 3, 0, width - 1)];
+            mid[i] = (int16_t)(acc >> (7 - ib));
+        }
+        __syncwarp();
+        uint8_t *dbase = plane_ptr(dst, pl);
+        const int64_t dstride = plane_stride(dst, pl);
+        const int px0 = (it.x >> ss_hor) + x, py0 = (it.y >> ss_ver) + y;
+        for (int i = lane; i < 64; i += 32) {
+            const int yy = i >> 3, xx = i & 7;
+            const int tmy = my + yy * a3 + xx * a2;
+            const int8_t *f = tab::k_warp_filter + (64 + ((tmy + 512) >> 10)) * 8;
+            int acc = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc += f[k] * (int)mid[(yy + k) * 8 + xx];
+            ((pixel *)(dbase + (int64_t)(py0 + yy) * dstride))[px0 + xx] =
+                (pixel)iclip((acc + ((1 << (7 + ib)) >> 1)) >> (7 + ib), 0, bdmax);
+        }
+        __syncwarp();
+    }
+}
+
+int mc_warp_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int layout,
+                         const Rb200WarpItem *d_items, int n, int bdmax, cudaStream_t st) {
+    if (n <= 0) return 0;
+    McRefSet rs = {};
+    for (int i = 0; i < n_refs && i < 8; i++) rs.p[i] = refs[i];
+    if (bdmax > 255) mc_warp_batch_kernel<BD16><<<n, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, layout, d_items, n, bdmax);
+    else mc_warp_batch_kernel<BD8><<<n, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, layout, d_items, n, bdmax);
+    RB_LAUNCH_CHECK();
+    return 0;
+}
+
 // Per-call: a single prediction block over a staged source rectangle; one warp per 16x16 tile.
 template <typename BD, bool PREP>
 __global__ void __launch_bounds__(MC_WARPS * 32)

@@ -108,6 +108,9 @@ AV1_RESTORATION_DT = _np.dtype([("lr", LR_UNIT_DT, (3, 4))])
 COMP_ITEM_DT = _np.dtype([("x", "<i2"), ("y", "<i2"), ("w", "u1"), ("h", "u1"), ("ref", "u1", (2,)), ("mv", "<i2", (2, 2)),
                           ("filter2d", "u1"), ("comp_type", "u1"), ("jnt_weight", "u1"), ("mask_sign", "u1"),
                           ("pad", "u1", (12,))])
+WARP_ITEM_DT = _np.dtype([("x", "<i2"), ("y", "<i2"), ("w", "u1"), ("h", "u1"), ("ref", "u1"), ("pad0", "u1"),
+                          ("matrix", "<i4", (6,)), ("abcd", "<i2", (4,)), ("pad", "u1", (8,))])
+assert WARP_ITEM_DT.itemsize == 48
 COMP_AVG, COMP_WEIGHTED_AVG, COMP_SEG = 0, 1, 2
 assert MC_ITEM_DT.itemsize == 16 and ITX_ITEM_DT.itemsize == 16 and COMP_ITEM_DT.itemsize == 32
 assert AV1_FILTER_DT.itemsize == 1348 and AV1_RESTORATION_DT.itemsize == 108
@@ -198,6 +201,9 @@ frame_lr_masks = _sig("rb200_frame_lr_masks", _vp, _vp)
 frame_reserve_comp_items = _sig("rb200_frame_reserve_comp_items", _i, _vp, _i)
 frame_comp_items = _sig("rb200_frame_comp_items", _vp, _vp)
 frame_set_comp_count = _sig("rb200_frame_set_comp_count", _i, _vp, _i)
+frame_reserve_warp_items = _sig("rb200_frame_reserve_warp_items", _i, _vp, _i)
+frame_warp_items = _sig("rb200_frame_warp_items", _vp, _vp)
+frame_set_warp_count = _sig("rb200_frame_set_warp_count", _i, _vp, _i)
 frame_set_ref = _sig("rb200_frame_set_ref", _i, _vp, _i, C.POINTER(Planes))
 frame_upload_planes = _sig("rb200_frame_upload_planes", _i, _vp, _i, C.POINTER(_vp), C.POINTER(_ss))
 frame_output_planes = _sig("rb200_frame_output_planes", _i, _vp, C.POINTER(Planes))

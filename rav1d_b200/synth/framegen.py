@@ -93,7 +93,7 @@ def geometry(hd):
     return g
 
 
-def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1, comp_frac=0.0):
+def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1, comp_frac=0.0, warp_frac=0.0):
     """Returns a SynthFrame with numpy arrays; see module docstring."""
     rng = np.random.default_rng(seed)
     bdmax = (1 << bpc) - 1
@@ -134,6 +134,25 @@ def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1, comp_frac=0.0):
     mvx2 = rng.integers(-512, 513, size=nb); mvy2 = rng.integers(-512, 513, size=nb)
     mvx2[rng.random(nb) < 0.15] &= ~7
     mvy2[rng.random(nb) < 0.15] &= ~7
+    # warped blocks: a random near-identity affine matrix per block and shear parameters in the range the
+    # reference's own test uses (tests/checkasm/mc.c:563-600)
+    is_warp = (rng.random(nb) < warp_frac) & ~is_comp
+    wi = np.nonzero(is_warp)[0]
+    warp = np.zeros(wi.size, lib.WARP_ITEM_DT)
+    warp["x"] = bx[wi] * BLK; warp["y"] = by[wi] * BLK; warp["w"] = BLK; warp["h"] = BLK; warp["ref"] = 0
+    mat = np.zeros((wi.size, 6), np.int64)
+    mat[:, 0] = rng.integers(-(40 << 16), 40 << 16, size=wi.size)
+    mat[:, 1] = rng.integers(-(40 << 16), 40 << 16, size=wi.size)
+    mat[:, 2] = (1 << 16) + rng.integers(-3000, 3000, size=wi.size)
+    mat[:, 3] = rng.integers(-3000, 3000, size=wi.size)
+    mat[:, 4] = rng.integers(-3000, 3000, size=wi.size)
+    mat[:, 5] = (1 << 16) + rng.integers(-3000, 3000, size=wi.size)
+    # keep the block near its own position: fold the linear part's effect at the block centre into the offset
+    mat[:, 0] -= (mat[:, 2] - (1 << 16)) * (bx[wi] * BLK) + mat[:, 3] * (by[wi] * BLK)
+    mat[:, 1] -= mat[:, 4] * (bx[wi] * BLK) + (mat[:, 5] - (1 << 16)) * (by[wi] * BLK)
+    warp["matrix"] = mat.astype(np.int32)
+    warp["abcd"] = (rng.integers(0, 0x2000, size=(wi.size, 4)) - 0xa00).astype(np.int16)
+    s.warp_items = warp
     comp = np.zeros(int(is_comp.sum()), lib.COMP_ITEM_DT)
     ci = np.nonzero(is_comp)[0]
     comp["x"] = bx[ci] * BLK; comp["y"] = by[ci] * BLK; comp["w"] = BLK; comp["h"] = BLK
@@ -165,7 +184,7 @@ def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1, comp_frac=0.0):
         c_it["w"] = BLK // 2; c_it["h"] = BLK // 2; c_it["plane"] = p
         c_it["mx"] = mvx & 15; c_it["my"] = mvy & 15
         c_it["filter2d"] = f2d
-    keep = np.tile(~is_comp, 3)
+    keep = np.tile(~(is_comp | is_warp), 3)
     s.mc_items = np.ascontiguousarray(mc[keep])
 
     # ---- transform blocks: (plane, x, y, tx, txtp)
@@ -378,6 +397,11 @@ class DeviceFrame:
         lv[:] = s.levels.reshape(-1)
         C.memmove(lib.frame_lf_lut(self.h), C.byref(s.lut), C.sizeof(lib.FilterLUT))
         lib.np_view(lib.frame_lr_masks(self.h), lib.AV1_RESTORATION_DT, n)[:] = s.lr_masks
+        warp = getattr(s, "warp_items", None)
+        if warp is not None and len(warp):
+            lib.check(lib.frame_reserve_warp_items(self.h, len(warp)), "reserve_warp_items")
+            lib.np_view(lib.frame_warp_items(self.h), lib.WARP_ITEM_DT, len(warp))[:] = warp
+            lib.check(lib.frame_set_warp_count(self.h, len(warp)))
         comp = getattr(s, "comp_items", None)
         if comp is not None and len(comp):
             lib.check(lib.frame_reserve_comp_items(self.h, len(comp)), "reserve_comp_items")

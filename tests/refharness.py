@@ -66,6 +66,7 @@ def load():
         sig("ref_frame_filter", None, vp, i, i)
         sig("ref_frame_recon", None, vp, vp, i, vp, i, vp, i, vp, i)
         sig("ref_frame_recon_comp", None, vp, vp, i, vp, i, i)
+        sig("ref_frame_recon_warp", None, vp, vp, i, vp, i, i)
         sig("ref_frame_apply_grain", None, vp, vp, i)
         sig("ref_frame_grain_plane", vp, vp, i)
         sig("ref_fg_gen_y", None, vp, vp, i)
@@ -132,6 +133,9 @@ class RefFrame:
         mc = np.ascontiguousarray(s.mc_items)
         itx = np.ascontiguousarray(s.itx_items)
         comp = np.ascontiguousarray(getattr(s, "comp_items", np.zeros(0, np.uint8)))
+        warp = np.ascontiguousarray(getattr(s, "warp_items", np.zeros(0, np.uint8)))
+        if len(warp):
+            self.ref.ref_frame_recon_warp(self.h, refs, len(frames), ptr(warp), len(warp), n_threads)
         if len(comp):
             self.ref.ref_frame_recon(self.h, refs, len(frames), ptr(mc), len(mc), ptr(itx), 0, ptr(cw), n_threads)
             self.ref.ref_frame_recon_comp(self.h, refs, len(frames), ptr(comp), len(comp), n_threads)

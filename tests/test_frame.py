@@ -55,6 +55,16 @@ def test_compound_blocks(rb, ref, w, h, bpc):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("w,h,bpc", [(176, 144, 8), (208, 128, 10), (256, 192, 12)])
+def test_warped_blocks(rb, ref, w, h, bpc):
+    """Affine-warped blocks next to translational and compound ones, all planes."""
+    s = framegen.generate(w, h, bpc, seed=w + 2, comp_frac=0.3, warp_frac=0.3)
+    assert len(s.warp_items) > 5
+    _check(ref, s, R)
+    _check(ref, s, R | D | Cd | L)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("unit_log2", [7, 8])
 def test_lr_unit_sizes(rb, ref, unit_log2):
     """Restoration units larger than the 64-pixel default, incl. the 1.5x last unit."""
