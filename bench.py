@@ -45,7 +45,7 @@ WORKLOADS = {
     "8k10": (7680, 4320, 10, 14, "8K 10-bit 4:2:0 post-filters only: deblock + CDEF + Wiener/SGR LR"),
 }
 FRAMES_PER_STEP = 16
-N_CTX = 4
+N_CTX = int(os.environ.get("RB200_BENCH_CTX", "8"))
 METRIC = "recon+post-filter throughput (itx+MC+LF/CDEF/LR), luma pixels of output frames"
 STAGE_NAMES = ["h2d", "mc", "itx", "deblock", "cdef", "lr"]
 
