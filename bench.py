@@ -396,7 +396,12 @@ def run_gpu(args, s, wl):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
 # capture of the dominant kernel (profiles/), keyed by (workload, stage); None until captured.
-TRAFFIC = {}
+TRAFFIC = {
+    # profiles/r01b_ncu_full_summary.csv: cdef_dir_frame_kernel 13.80 MB + cdef_filter_frame_kernel 26.04 + 2.63 MB
+    ("4k10", "cdef"): 42.47e6,
+    ("4k10", "mc"): 26.87e6,
+    ("4k10", "lr"): 27.24e6,
+}
 
 
 def main():

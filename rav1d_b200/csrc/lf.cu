@@ -260,31 +260,47 @@ deblock_units_kernel(LfPlaneSet S, const Rb200Av1Filter *__restrict__ masks, con
                 if (i < n) { p[-1 - i] = (pixel)P[i]; p[i] = (pixel)Q[i]; }
         }
     } else {
-        // rows y-4ng .. y+4ng-1, 4 columns each, kept packed; column c is unpacked, filtered, re-packed
-        int rows[16][4];
+        // rows y-4ng .. y+4ng-1, 4 columns each, kept PACKED (one or two registers per row) to leave room
+        // for more resident warps; column c is unpacked, filtered and re-packed
+        constexpr int WPR = BD::hbd ? 2 : 1;            // 32-bit words per 4-pixel row
+        unsigned rows[16][WPR];
 #pragma unroll
         for (int r = 0; r < 16; r++) {
             const int rel = r - 8;   // row offset from the edge
-            if (rel >= -4 * ng && rel < 4 * ng) load4(base + (int64_t)rel * ps, rows[r]);
+            if (rel >= -4 * ng && rel < 4 * ng) {
+                const pixel *p = base + (int64_t)rel * ps;
+                if (BD::hbd) { const uint2 q = *(const uint2 *)p; rows[r][0] = q.x; rows[r][WPR - 1] = q.y; }
+                else rows[r][0] = *(const unsigned *)p;
+            }
         }
+        auto get = [&](int r, int c) -> int {
+            if (BD::hbd) return (int)((rows[r][c >> 1] >> (16 * (c & 1))) & 0xffff);
+            return (int)((rows[r][0] >> (8 * c)) & 0xff);
+        };
+        auto put = [&](int r, int c, int v) {
+            if (BD::hbd) rows[r][c >> 1] = (rows[r][c >> 1] & ~(0xffffu << (16 * (c & 1)))) | ((unsigned)v << (16 * (c & 1)));
+            else rows[r][0] = (rows[r][0] & ~(0xffu << (8 * c))) | ((unsigned)v << (8 * c));
+        };
         int nmax = 0;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             int P[8], Q[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) { P[i] = rows[7 - i][c]; Q[i] = rows[8 + i][c]; }
+            for (int i = 0; i < 8; i++) { P[i] = get(7 - i, c); Q[i] = get(8 + i, c); }
             const int n = lf_line_regs(P, Q, E, I, H, wd, bdmin8, bdmax);
             nmax = imax(nmax, n);
 #pragma unroll
-            for (int i = 0; i < 6; i++) { rows[7 - i][c] = P[i]; rows[8 + i][c] = Q[i]; }
+            for (int i = 0; i < 6; i++)
+                if (i < n) { put(7 - i, c, P[i]); put(8 + i, c, Q[i]); }
         }
-        auto store4 = [](pixel *p, const int *v) {
-            if (BD::hbd) *(uint2 *)p = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
-            else *(unsigned *)p = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
-        };
 #pragma unroll
-        for (int i = 0; i < 6; i++)
-            if (i < nmax) { store4(base + (int64_t)(-1 - i) * ps, rows[7 - i]); store4(base + (int64_t)i * ps, rows[8 + i]); }
+        for (int i = 0; i < 6; i++) {
+            if (i < nmax) {
+                pixel *pu = base + (int64_t)(-1 - i) * ps, *pd = base + (int64_t)i * ps;
+                if (BD::hbd) { *(uint2 *)pu = make_uint2(rows[7 - i][0], rows[7 - i][WPR - 1]); *(uint2 *)pd = make_uint2(rows[8 + i][0], rows[8 + i][WPR - 1]); }
+                else { *(unsigned *)pu = rows[7 - i][0]; *(unsigned *)pd = rows[8 + i][0]; }
+            }
+        }
     }
 }
 
