@@ -108,6 +108,18 @@ itx_add_kernel(Rb200Planes planes, const typename BD::coef *__restrict__ cf,
     const bool dconly = live && it.txtp == RB200_DCT_DCT && it.eob < 1;
     const bool wht = it.txtp == RB200_WHT_WHT;
 
+    // The destination column of the second pass does not depend on the transform: fetch it now so that
+    // its latency overlaps the coefficient loads and the first pass (one global round trip less on the
+    // critical path of this latency-bound kernel).
+    const int64_t bstride = plane_stride(planes, it.plane);
+    const int64_t pstride = bstride / (int64_t)sizeof(pixel);
+    pixel *dst = (pixel *)(plane_ptr(planes, it.plane) + (int64_t)it.y * bstride) + it.x + lane;
+    pixel dpx[H];
+    if (live && lane < W) {
+#pragma unroll
+        for (int i = 0; i < H; i++) dpx[i] = dst[i * pstride];
+    }
+
     // ---- first pass: rows ----
     if (live && !dconly && lane < SH) {
         int x[W];
@@ -136,9 +148,6 @@ itx_add_kernel(Rb200Planes planes, const typename BD::coef *__restrict__ cf,
     if (!live || lane >= W) return;
 
     // ---- second pass: columns, add to destination ----
-    const int64_t bstride = plane_stride(planes, it.plane);
-    pixel *dst = (pixel *)(plane_ptr(planes, it.plane) + (int64_t)it.y * bstride) + it.x + lane;
-    const int64_t pstride = bstride / (int64_t)sizeof(pixel);
     if (dconly) {
         // src/itx.rs:90-111
         int dc = c[0];
@@ -146,8 +155,8 @@ itx_add_kernel(Rb200Planes planes, const typename BD::coef *__restrict__ cf,
         dc = (dc * 181 + 128) >> 8;
         dc = (dc + ((1 << shift) >> 1)) >> shift;
         dc = (dc * 181 + 128 + 2048) >> 12;
-#pragma unroll 8
-        for (int i = 0; i < H; i++) dst[i * pstride] = (pixel)iclip((int)dst[i * pstride] + dc, 0, bdmax);
+#pragma unroll
+        for (int i = 0; i < H; i++) dst[i * pstride] = (pixel)iclip((int)dpx[i] + dc, 0, bdmax);
         return;
     }
     int v[H];
@@ -156,10 +165,10 @@ itx_add_kernel(Rb200Planes planes, const typename BD::coef *__restrict__ cf,
     run_kind<H>(txtp_col_kind(it.txtp), v, col_lo, col_hi);
     if (wht) {
 #pragma unroll
-        for (int i = 0; i < H; i++) dst[i * pstride] = (pixel)iclip((int)dst[i * pstride] + v[i], 0, bdmax);
+        for (int i = 0; i < H; i++) dst[i * pstride] = (pixel)iclip((int)dpx[i] + v[i], 0, bdmax);
     } else {
 #pragma unroll
-        for (int i = 0; i < H; i++) dst[i * pstride] = (pixel)iclip((int)dst[i * pstride] + ((v[i] + 8) >> 4), 0, bdmax);
+        for (int i = 0; i < H; i++) dst[i * pstride] = (pixel)iclip((int)dpx[i] + ((v[i] + 8) >> 4), 0, bdmax);
     }
 }
 
