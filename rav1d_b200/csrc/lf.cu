@@ -230,6 +230,21 @@ deblock_units_kernel(LfPlaneSet S, const Rb200Av1Filter *__restrict__ masks, con
     const int yl = u / g.w4, x4 = u - yl * g.w4;
     const int y4 = yl + (pi == 0 ? S.y4_first[0] : (pi == 1 ? S.y4_first[1] : S.y4_first[2]));
     if (DIR == 0 ? x4 == 0 : y4 == 0) return;  // have_left / have_top
+    const int64_t ps = stride / (int64_t)sizeof(pixel);
+    pixel *base = (pixel *)plane + (int64_t)(y4 * 4) * ps + x4 * 4;   // q0 of line 0
+    // Row-edge pass: the 8 rows every filter width needs are requested before the mask / level lookups
+    // they would otherwise wait behind (the pass is latency-bound; units without an edge waste the loads,
+    // which L2 serves).
+    constexpr int WPR = BD::hbd ? 2 : 1;            // 32-bit words per 4-pixel row
+    unsigned rows[16][WPR];
+    if (DIR == 1) {
+#pragma unroll
+        for (int r = 4; r < 12; r++) {
+            const pixel *p = base + (int64_t)(r - 8) * ps;
+            if (BD::hbd) { const uint2 q = *(const uint2 *)p; rows[r][0] = q.x; rows[r][WPR - 1] = q.y; }
+            else rows[r][0] = *(const unsigned *)p;
+        }
+    }
     const int idx = lf_mask_idx(masks, g, DIR, x4, y4);
     if (idx < 0) return;
     const uint8_t(*l)[4] = lvl + (int64_t)y4 * g.b4_stride + x4;
@@ -240,8 +255,6 @@ deblock_units_kernel(LfPlaneSet S, const Rb200Av1Filter *__restrict__ masks, con
     const int H = (L >> 4) << bdmin8, E = (int)lut->e[L] << bdmin8, I = (int)lut->i[L] << bdmin8;
     const int wd = g.uv ? 4 + 2 * idx : 4 << idx;
     const int ng = wd == 16 ? 2 : 1;           // 4-pixel groups loaded on each side of the edge
-    const int64_t ps = stride / (int64_t)sizeof(pixel);
-    pixel *base = (pixel *)plane + (int64_t)(y4 * 4) * ps + x4 * 4;   // q0 of line 0
     auto load4 = [](const pixel *p, int *v) {
         if (BD::hbd) { const uint2 q = *(const uint2 *)p; v[0] = q.x & 0xffff; v[1] = q.x >> 16; v[2] = q.y & 0xffff; v[3] = q.y >> 16; }
         else { const unsigned q = *(const unsigned *)p; v[0] = q & 0xff; v[1] = (q >> 8) & 0xff; v[2] = (q >> 16) & 0xff; v[3] = q >> 24; }
@@ -262,13 +275,11 @@ deblock_units_kernel(LfPlaneSet S, const Rb200Av1Filter *__restrict__ masks, con
     } else {
         // rows y-4ng .. y+4ng-1, 4 columns each, kept PACKED (one or two registers per row) to leave room
         // for more resident warps; column c is unpacked, filtered and re-packed
-        constexpr int WPR = BD::hbd ? 2 : 1;            // 32-bit words per 4-pixel row
-        unsigned rows[16][WPR];
+        if (ng == 2) {
 #pragma unroll
-        for (int r = 0; r < 16; r++) {
-            const int rel = r - 8;   // row offset from the edge
-            if (rel >= -4 * ng && rel < 4 * ng) {
-                const pixel *p = base + (int64_t)rel * ps;
+            for (int r = 0; r < 16; r++) {
+                if (r >= 4 && r < 12) continue;
+                const pixel *p = base + (int64_t)(r - 8) * ps;
                 if (BD::hbd) { const uint2 q = *(const uint2 *)p; rows[r][0] = q.x; rows[r][WPR - 1] = q.y; }
                 else rows[r][0] = *(const unsigned *)p;
             }
