@@ -447,7 +447,9 @@ Rb200WarpItem *rb200_frame_warp_items(Rb200Frame *f);
 int rb200_frame_set_warp_count(Rb200Frame *f, int n_warp_items);
 /* Reference pictures: device planes (layout of rb200_frame_geometry) that stay resident. */
 int rb200_frame_set_ref(Rb200Frame *f, int slot, const Rb200Planes *planes);
-/* Upload a host picture into one of the frame's own plane sets (0 = current/recon). */
+/* Upload a host picture into one of the frame's own plane sets (0 = current/recon).  The copy covers the
+ * picture rounded up to 8 pixels in both directions (the part of the allocation reconstruction writes
+ * and CDEF reads), so the host planes must be at least that large (the reference's are 128-aligned). */
 int rb200_frame_upload_planes(Rb200Frame *f, int which, const void *const data[3], const ptrdiff_t stride[2]);
 /* Film grain on output (rav1d_apply_grain, src/lib.rs:604 -> src/fg_apply.rs:272): parameters of the
  * RB200_STAGE_FILM_GRAIN stage.  The grained picture is a separate plane set (it is never used as a

@@ -285,6 +285,11 @@ static int film_grain_stage(Rb200Frame *f, cudaStream_t st) {
     return 0;
 }
 
+// Uploads cover the picture rounded up to 8 pixels (f.bw * 4 x f.bh * 4): the reconstruction of blocks that
+// straddle the picture edge lives there and CDEF reads it (src/cdef_apply.rs:159-507 walks bw / bh).
+static int upload_rows(const Rb200Frame *f, int p) { return (f->g.bh * 4) >> (p ? f->g.ss_ver : 0); }
+static size_t upload_row_bytes(const Rb200Frame *f, int p) { return (size_t)((f->g.bw * 4) >> (p ? f->g.ss_hor : 0)) * f->px; }
+
 // Row ranges of one band (multi-GPU split of one picture by superblock rows).
 // The band is named by the 64-row loop-restoration stripes [s0, s1) it must deliver; each earlier
 // stage is widened by exactly what the next one reads: CDEF whole 64-row tiles, deblocked rows
@@ -336,12 +341,15 @@ static int copy_rows(Rb200Frame *f, const Rb200Planes &dev, void *const data[3],
                      int row_end, bool to_device) {
     for (int p = 0; p < f->g.n_planes; p++) {
         const int ss = p ? f->g.ss_ver : 0;
-        const int full = p ? (f->hdr.height + ss) >> ss : f->hdr.height;
-        const int r0 = imax(row_begin >> ss, 0), r1 = imin((row_end + ss) >> ss, full);
+        const int full = to_device ? upload_rows(f, p) : (p ? (f->hdr.height + ss) >> ss : f->hdr.height);
+        const int r0 = imax(row_begin >> ss, 0);
+        // the band that owns the last picture row also owns the rows up to the 8-pixel boundary
+        const int r1 = (to_device && row_end >= f->hdr.height) ? full : imin((row_end + ss) >> ss, full);
         if (r1 <= r0) continue;
         const ptrdiff_t hs = stride[p ? 1 : 0];
         if (hs < 0) return set_error(-22, "row-range copies need a positive host stride");
-        const size_t rb = (size_t)(p ? (f->hdr.width + f->g.ss_hor) >> f->g.ss_hor : f->hdr.width) * f->px;
+        const size_t rb = to_device ? upload_row_bytes(f, p)
+                                    : (size_t)(p ? (f->hdr.width + f->g.ss_hor) >> f->g.ss_hor : f->hdr.width) * f->px;
         uint8_t *h = (uint8_t *)data[p] + (int64_t)r0 * hs;
         uint8_t *d = (uint8_t *)dev.data[p] + (int64_t)r0 * dev.stride[p];
         if (to_device) RB_CUDA(cudaMemcpy2DAsync(d, (size_t)dev.stride[p], h, (size_t)hs, rb, r1 - r0, cudaMemcpyHostToDevice, f->stream));
@@ -490,17 +498,17 @@ extern "C" int rb200_frame_upload_planes(Rb200Frame *f, int which, const void *c
                                          const ptrdiff_t stride[2]) {
     if (!f || which < 0 || which > 2 || !data || !stride) return set_error(-22, "frame_upload_planes: bad argument");
     for (int p = 0; p < f->g.n_planes; p++) {
-        const int rows = plane_rows(f, p);
+        const int rows = upload_rows(f, p);
         const ptrdiff_t hs = stride[p ? 1 : 0];
         const uint8_t *src = (const uint8_t *)data[p];
         if (hs < 0) src += (int64_t)(rows - 1) * hs;  // lowest address; copy flipped below
         if (hs >= 0) {
             RB_CUDA(cudaMemcpy2DAsync(f->planes[which].data[p], (size_t)f->planes[which].stride[p], src, (size_t)hs,
-                                      plane_row_bytes(f, p), rows, cudaMemcpyHostToDevice, f->stream));
+                                      upload_row_bytes(f, p), rows, cudaMemcpyHostToDevice, f->stream));
         } else {
             for (int y = 0; y < rows; y++)
                 RB_CUDA(cudaMemcpyAsync((uint8_t *)f->planes[which].data[p] + (int64_t)y * f->planes[which].stride[p],
-                                        (const uint8_t *)data[p] + (int64_t)y * hs, plane_row_bytes(f, p),
+                                        (const uint8_t *)data[p] + (int64_t)y * hs, upload_row_bytes(f, p),
                                         cudaMemcpyHostToDevice, f->stream));
         }
     }

@@ -361,6 +361,14 @@ def recon_input_planes(s, rng=None):
     return [o.astype(pdt) for o in out]
 
 
+def _plane_args(planes):
+    """ctypes (data[3], stride[2]) of 1 (4:0:0) or 3 numpy planes."""
+    ptrs = [p.ctypes.data for p in planes] + [None] * (3 - len(planes))
+    data = (C.c_void_p * 3)(*ptrs)
+    strides = (C.c_ssize_t * 2)(planes[0].strides[0], planes[1].strides[0] if len(planes) > 1 else 0)
+    return data, strides
+
+
 class DeviceFrame:
     """Host-side driver of one rb200 frame object: fills the pinned staging from a SynthFrame."""
 
@@ -409,8 +417,7 @@ class DeviceFrame:
             lib.check(lib.frame_set_comp_count(self.h, len(comp)))
 
     def upload(self, which, planes):
-        data = (C.c_void_p * 3)(*[p.ctypes.data for p in planes])
-        strides = (C.c_ssize_t * 2)(planes[0].strides[0], planes[1].strides[0])
+        data, strides = _plane_args(planes)
         lib.check(lib.frame_upload_planes(self.h, which, data, strides), "frame_upload_planes")
 
     def set_ref_from_host(self, planes):
@@ -452,7 +459,6 @@ class DeviceFrame:
     def readback(self):
         s = self.s
         out = [np.zeros_like(p) for p in s.ref]
-        data = (C.c_void_p * 3)(*[p.ctypes.data for p in out])
-        strides = (C.c_ssize_t * 2)(out[0].strides[0], out[1].strides[0])
+        data, strides = _plane_args(out)
         lib.check(lib.frame_readback(self.h, data, strides), "frame_readback")
         return out

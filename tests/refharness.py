@@ -97,20 +97,25 @@ class RefFrame:
 
     def plane_view(self, p, grain=False):
         s = self.s
-        rows = s.ah if p == 0 else s.ah // 2
+        layout = s.hdr.layout
+        ss_ver, ss_hor = int(layout == 1), int(layout != 3)
+        rows = s.ah if p == 0 else s.ah >> ss_ver
         stride = self.strides[1 if p else 0]
         addr = self.ref.ref_frame_grain_plane(self.h, p) if grain else self.ref.ref_frame_plane(self.h, p)
         buf = (C.c_ubyte * (stride * rows)).from_address(addr)
         a = np.frombuffer(buf, dtype=np.uint8).reshape(rows, stride)
-        cols = s.aw if p == 0 else s.aw // 2
+        cols = s.aw if p == 0 else s.aw >> ss_hor
         return a[:, :cols * self.px].view(np.uint16 if self.px == 2 else np.uint8)
 
+    def n_planes(self):
+        return 1 if self.s.hdr.layout == 0 else 3
+
     def set_planes(self, planes):
-        for p in range(3):
+        for p in range(self.n_planes()):
             self.plane_view(p)[:] = planes[p]
 
     def get_planes(self):
-        return [self.plane_view(p).copy() for p in range(3)]
+        return [self.plane_view(p).copy() for p in range(self.n_planes())]
 
     def load_filter_meta(self):
         from rav1d_b200 import lib

@@ -1,0 +1,63 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/streams.npz: for a few small conformance streams of the reference tree,
+per decoded frame, the pre-filter picture, the decoder's filter metadata and the post-filter picture,
+as dumped by oracle/_ref/ref_dump (the reference decoder with dav1d_filter_sbrow_* interposed).
+Planes are cropped to the picture rounded up to 8 pixels.  Run where /root/reference exists:
+
+    python tools/make_stream_fixtures.py
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import streamdump  # noqa: E402
+
+STREAMS = [  # (path under tests/dav1d-test-data, frames)
+    ("8-bit/data/00000658.ivf", 2), ("8-bit/data/00000664.ivf", 2), ("8-bit/data/00000668.ivf", 2),
+    ("8-bit/data/00000593.ivf", 2), ("8-bit/issues/309_odd_width.ivf", 2), ("8-bit/data/00000527.ivf", 3),
+    ("10-bit/data/00000671.ivf", 2), ("10-bit/data/00000676.ivf", 2), ("10-bit/data/00000682.ivf", 2),
+    ("10-bit/argon/test185_302.obu", 2), ("10-bit/argon/test5606.obu", 2),
+    ("12-bit/data/00000686.ivf", 2), ("12-bit/data/00000692.ivf", 2), ("12-bit/data/00000696.ivf", 2),
+    ("12-bit/argon/test15240.obu", 2), ("multi-bit/argon/test10218_6914.obu", 2),
+]
+
+
+def pack(s):
+    """One StreamFrame -> dict of arrays (see tests/streamdump.py unpack())."""
+    h = s.hdr
+    ints = [s.w, s.h, s.bpc, s.layout, h.sb128, h.lf_level_y[0], h.lf_level_y[1], h.lf_level_u, h.lf_level_v, s.cdef_on,
+            h.cdef_damping, *h.cdef_y_strength, *h.cdef_uv_strength, *h.lr_type, *h.lr_unit_size_log2, *s.tiles, s.ah, s.stages]
+    g = s.geom
+    out = {"ints": np.array(ints, np.int32), "masks": s.masks.view(np.uint8), "levels": s.levels,
+           "lut": np.frombuffer(bytes(s.lut), np.uint8), "lr_masks": s.lr_masks.view(np.uint8)}
+    for k, planes in (("pre", s.pre), ("post", s.post)):
+        for p, a in enumerate(planes):
+            rows, cols = (g.bh * 4) >> (g.ss_ver if p else 0), (g.bw * 4) >> (g.ss_hor if p else 0)
+            out[f"{k}{p}"] = a[:rows, :cols]
+    return out
+
+
+def main():
+    blob, index = {}, []
+    for rel, n in STREAMS:
+        frames = streamdump.dump(os.path.join(streamdump.REF_DATA, rel), n)
+        assert frames, rel
+        for s in frames:
+            key = f"{rel}#{s.index}"
+            index.append(key)
+            for k, v in pack(s).items():
+                blob[f"{key}/{k}"] = v
+    blob["index"] = np.array(index)
+    path = os.path.join(ROOT, "tests", "golden", "streams.npz")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    np.savez_compressed(path, **blob)
+    print(f"{len(index)} frames -> {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
+
+
+if __name__ == "__main__":
+    main()
