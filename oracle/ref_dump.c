@@ -21,7 +21,7 @@
  *
  * tests/test_streams.py replays the dump through the CUDA post-filter path and compares.
  *
- * usage: ref_dump <in.ivf|.obu> <out.bin> [max_frames]
+ * usage: ref_dump <in.ivf|.obu> <out.bin> [max_frames [max_grain_frames]]
  */
 #define _GNU_SOURCE
 #include "config.h"
@@ -110,6 +110,37 @@ static void hook(Dav1dFrameContext *const f, const int sby, const char *const sy
     g_frames++;
 }
 
+/* ---- film grain on output: dav1d_apply_grain_{8,16}bpc (src/fg_apply_tmpl.c:229-245), called from
+ * dav1d_apply_grain (src/lib.c:482-516).  Record: "RBFG", w, h, bpc, layout, is_identity, stride_y,
+ * stride_uv, sizeof(Dav1dFilmGrainData), the struct, the input planes, the output planes (h rows each). */
+typedef void (*apply_grain_fn)(const Dav1dFilmGrainDSPContext *dsp, Dav1dPicture *out, const Dav1dPicture *in);
+static int g_grain_frames, g_max_grain = 0;
+static void grain_hook(const Dav1dFilmGrainDSPContext *dsp, Dav1dPicture *out, const Dav1dPicture *in, const char *sym) {
+    apply_grain_fn real = (apply_grain_fn)dlsym(RTLD_NEXT, sym);
+    if (!real) { fprintf(stderr, "ref_dump: cannot find %s\n", sym); exit(2); }
+    real(dsp, out, in);
+    if (g_grain_frames >= g_max_grain || in->stride[0] <= 0) return;
+    const int layout = in->p.layout;
+    const int ss_ver = layout == DAV1D_PIXEL_LAYOUT_I420;
+    const int n_planes = layout == DAV1D_PIXEL_LAYOUT_I400 ? 1 : 3;
+    put_i32(0x52424647);
+    put_i32(in->p.w); put_i32(in->p.h); put_i32(in->p.bpc); put_i32(layout);
+    put_i32(out->seq_hdr->mtrx == DAV1D_MC_IDENTITY);
+    put_i32((int32_t)in->stride[0]); put_i32((int32_t)in->stride[1]);
+    put_i32((int32_t)sizeof(Dav1dFilmGrainData));
+    fwrite(&out->frame_hdr->film_grain.data, sizeof(Dav1dFilmGrainData), 1, g_out);
+    for (int k = 0; k < 2; k++) {
+        const Dav1dPicture *p = k ? out : in;
+        for (int pl = 0; pl < n_planes; pl++) {
+            const int rows = pl ? (in->p.h + ss_ver) >> ss_ver : in->p.h;
+            fwrite(p->data[pl], 1, (size_t)p->stride[!!pl] * rows, g_out);
+        }
+    }
+    g_grain_frames++;
+}
+__attribute__((visibility("default"))) void dav1d_apply_grain_8bpc(const Dav1dFilmGrainDSPContext *dsp, Dav1dPicture *out, const Dav1dPicture *in) { grain_hook(dsp, out, in, "dav1d_apply_grain_8bpc"); }
+__attribute__((visibility("default"))) void dav1d_apply_grain_16bpc(const Dav1dFilmGrainDSPContext *dsp, Dav1dPicture *out, const Dav1dPicture *in) { grain_hook(dsp, out, in, "dav1d_apply_grain_16bpc"); }
+
 /* exported so that the library's address-of in src/decode.c:3457 binds here */
 __attribute__((visibility("default"))) void dav1d_filter_sbrow_8bpc(Dav1dFrameContext *f, int sby) { hook(f, sby, "dav1d_filter_sbrow_8bpc"); }
 __attribute__((visibility("default"))) void dav1d_filter_sbrow_16bpc(Dav1dFrameContext *f, int sby) { hook(f, sby, "dav1d_filter_sbrow_16bpc"); }
@@ -117,6 +148,7 @@ __attribute__((visibility("default"))) void dav1d_filter_sbrow_16bpc(Dav1dFrameC
 int main(int argc, char **argv) {
     if (argc < 3) { fprintf(stderr, "usage: %s in.ivf out.bin [max_frames]\n", argv[0]); return 2; }
     if (argc > 3) g_max_frames = atoi(argv[3]);
+    if (argc > 4) g_max_grain = atoi(argv[4]);      /* film-grain records (decoded with apply_grain = 1) */
     g_out = fopen(argv[2], "wb");
     if (!g_out) { perror(argv[2]); return 2; }
     DemuxerContext *in;
@@ -126,7 +158,7 @@ int main(int argc, char **argv) {
     dav1d_default_settings(&s);
     s.n_threads = 1;            /* the single-thread path is the one that calls filter_sbrow per sbrow */
     s.max_frame_delay = 1;
-    s.apply_grain = 0;
+    s.apply_grain = g_max_grain > 0;
     Dav1dContext *c;
     if (dav1d_open(&c, &s)) return 2;
     Dav1dData data;
@@ -141,7 +173,7 @@ int main(int argc, char **argv) {
         res = dav1d_get_picture(c, &p);
         if (res >= 0) dav1d_picture_unref(&p);
         else if (res != DAV1D_ERR(EAGAIN) && res != DAV1D_ERR(EINVAL)) break;
-        if (g_frames >= g_max_frames) break;
+        if (g_frames >= g_max_frames && g_grain_frames >= g_max_grain) break;
     } while (data.sz > 0 || !input_read(in, &data));
     if (data.sz > 0) dav1d_data_unref(&data);
     for (;;) {
@@ -153,6 +185,6 @@ int main(int argc, char **argv) {
     input_close(in);
     dav1d_close(&c);
     fclose(g_out);
-    fprintf(stderr, "ref_dump: %d frames\n", g_frames);
-    return g_frames > 0 ? 0 : 1;
+    fprintf(stderr, "ref_dump: %d frames, %d film-grain records\n", g_frames, g_grain_frames);
+    return g_frames + g_grain_frames > 0 ? 0 : 1;
 }

@@ -99,7 +99,42 @@ def dump(path, max_frames=4):
     return frames
 
 
+def dump_grain(path, max_frames=2):
+    """Film-grain records of `path` decoded with apply_grain = 1: [dict(w, h, bpc, layout, is_id, fg (bytes), inp, out)]."""
+    with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as tf:
+        out = tf.name
+    try:
+        r = subprocess.run([REF_DUMP, path, out, "0", str(max_frames)], capture_output=True, text=True)
+        if r.returncode != 0 or not os.path.getsize(out):
+            return []
+        buf = np.fromfile(out, dtype=np.uint8)
+    finally:
+        os.unlink(out)
+    recs, off = [], 0
+    while off + 36 <= buf.size:
+        hd = buf[off:off + 36].view("<i4"); off += 36
+        assert hd[0] == 0x52424647, "bad film-grain record"
+        w, h, bpc, layout, is_id, stride_y, stride_uv, fgsz = (int(v) for v in hd[1:9])
+        fg = buf[off:off + fgsz].tobytes(); off += fgsz
+        ss_ver, ss_hor = int(layout == 1), int(layout != 3)
+        n_planes = 1 if layout == 0 else 3
+        pdt, px = (np.uint16, 2) if bpc > 8 else (np.uint8, 1)
+        pics = []
+        for _ in range(2):
+            pl = []
+            for p in range(n_planes):
+                stride = stride_uv if p else stride_y
+                rows = (h + ss_ver) >> ss_ver if p else h
+                cols = (w + ss_hor) >> ss_hor if p else w
+                pl.append(buf[off:off + stride * rows].reshape(rows, stride)[:, :cols * px].view(pdt).copy())
+                off += stride * rows
+            pics.append(pl)
+        recs.append(dict(w=w, h=h, bpc=bpc, layout=layout, is_id=is_id, fg=np.frombuffer(fg, np.uint8).copy(), inp=pics[0], out=pics[1]))
+    return recs
+
+
 GOLDEN = os.path.join(ROOT, "tests", "golden", "streams.npz")
+GOLDEN_GRAIN = os.path.join(ROOT, "tests", "golden", "film_grain.npz")
 
 
 def load_golden():

@@ -73,3 +73,60 @@ def test_stream_postfilters_bit_exact(rb, key):
         _assert_equal(s, s.post, d.readback(), key)
     finally:
         d.close()
+
+
+# ---------------------------------------------------------------- film grain on real streams
+def _load_grain():
+    if not os.path.exists(streamdump.GOLDEN_GRAIN):
+        return []
+    z = np.load(streamdump.GOLDEN_GRAIN, allow_pickle=False)
+    return [(str(k), z) for k in z["index"]]
+
+
+GRAIN = _load_grain()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", [k for k, _ in GRAIN])
+def test_stream_film_grain_bit_exact(rb, key):
+    """dav1d_apply_grain's input / parameters / output captured from the reference decoder on the
+    film-grain conformance streams (tests/dav1d-test-data/{8,10}-bit/film_grain); the frame-level
+    RB200_STAGE_FILM_GRAIN must reproduce the output."""
+    import ctypes as C
+    from rav1d_b200 import lib
+    from rav1d_b200.synth import framegen
+    z = dict(GRAIN)[key]
+    w, h, bpc, layout, is_id = (int(v) for v in z[f"{key}/ints"])
+    fg = lib.FilmGrainData.from_buffer_copy(z[f"{key}/fg"].tobytes())
+    s = streamdump.StreamFrame()
+    s.w, s.h, s.bpc, s.layout = w, h, bpc, layout
+    s.aw, s.ah = (w + 127) & ~127, (h + 127) & ~127
+    hdr = lib.FrameHeader()
+    hdr.width, hdr.height, hdr.bpc, hdr.layout = w, h, bpc, layout
+    s.hdr = hdr
+    ss_ver, ss_hor = int(layout == 1), int(layout != 3)
+    n_planes = 1 if layout == 0 else 3
+    pdt = np.uint16 if bpc > 8 else np.uint8
+
+    def padded(kind):
+        out = []
+        for p in range(n_planes):
+            a = np.zeros((s.ah >> ss_ver if p else s.ah, s.aw >> ss_hor if p else s.aw), pdt)
+            c = z[f"{key}/{kind}{p}"]
+            a[:c.shape[0], :c.shape[1]] = c
+            out.append(a)
+        return out
+    inp, exp = padded("in"), padded("out")
+    s.ref = inp
+    s.n_coefs, s.itx_items, s.mc_items = 0, np.zeros(0, lib.ITX_ITEM_DT), np.zeros(0, lib.MC_ITEM_DT)
+    d = framegen.DeviceFrame(s)
+    try:
+        d.upload(0, inp)
+        lib.check(lib.frame_set_film_grain(d.h, C.byref(fg), is_id))
+        counts = (C.c_int32 * 19)()
+        lib.check(lib.frame_submit(d.h, 0, counts, 0, lib.STAGE_FILM_GRAIN, 0), "frame_submit")
+        d.wait()
+        _assert_equal(s, exp, d.readback(), key)
+        assert not np.array_equal(exp[0], inp[0])
+    finally:
+        d.close()

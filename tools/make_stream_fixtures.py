@@ -59,5 +59,26 @@ def main():
     print(f"{len(index)} frames -> {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
 
 
+GRAIN_STREAMS = [("10-bit/film_grain/av1-1-b10-23-film_grain-50.ivf", 2), ("8-bit/film_grain/av1-1-b8-23-film_grain-50.ivf", 2)]
+
+
+def main_grain():
+    blob, index = {}, []
+    for rel, n in GRAIN_STREAMS:
+        recs = streamdump.dump_grain(os.path.join(streamdump.REF_DATA, rel), n)
+        assert recs, rel
+        for i, r in enumerate(recs):
+            key = f"{rel}#{i}"
+            index.append(key)
+            blob[f"{key}/ints"] = np.array([r["w"], r["h"], r["bpc"], r["layout"], r["is_id"]], np.int32)
+            blob[f"{key}/fg"] = r["fg"]
+            for p in range(len(r["inp"])):
+                blob[f"{key}/in{p}"] = r["inp"][p]; blob[f"{key}/out{p}"] = r["out"][p]
+    blob["index"] = np.array(index)
+    np.savez_compressed(streamdump.GOLDEN_GRAIN, **blob)
+    print(f"{len(index)} film-grain frames -> {streamdump.GOLDEN_GRAIN} ({os.path.getsize(streamdump.GOLDEN_GRAIN) / 1e6:.2f} MB)")
+
+
 if __name__ == "__main__":
     main()
+    main_grain()
