@@ -214,7 +214,7 @@ typedef struct Rb200McItem {
     uint8_t filter2d;     /* RB200_FILTER_2D_* */
     uint8_t flags;        /* RB200_MC_* */
 } Rb200McItem;            /* 16 bytes */
-enum { RB200_MC_PUT = 0 };
+enum { RB200_MC_PUT = 0, RB200_MC_OBMC_ABOVE = 1, RB200_MC_OBMC_LEFT = 2 };
 /* refs[slot]: device planes of reference pictures; ref_w/ref_h: picture size of plane 0 in pixels;
  * ss_hor/ss_ver: chroma subsampling.  dst: device planes of the current picture. */
 int rb200_mc_batch(const Rb200Planes *dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h,
@@ -442,6 +442,15 @@ Rb200Av1Restoration *rb200_frame_lr_masks(Rb200Frame *f);     /* [sb128h * sb128
 int rb200_frame_reserve_comp_items(Rb200Frame *f, int max_comp_items);
 Rb200CompItem *rb200_frame_comp_items(Rb200Frame *f);
 int rb200_frame_set_comp_count(Rb200Frame *f, int n_comp_items);
+/* Overlapped block motion compensation, recon.rs `obmc()` (src/recon.rs:2205-2309; C: src/recon_tmpl.c:1076-1137):
+ * one Rb200McItem per neighbour strip and plane, flags = RB200_MC_OBMC_ABOVE (w x h = the blend_h area,
+ * h_mul * ow4 by v_mul * oh4; the neighbour's vector is predicted over w x ((oh4 * 3 + 3) >> 2) * v_mul and
+ * blended with dav1d_obmc_masks over the first h * 3 / 4 rows) or RB200_MC_OBMC_LEFT (blend_v over the
+ * first w * 3 / 4 columns).  The list holds all ABOVE strips first, then all LEFT strips; they run after
+ * every block's own prediction and before the residuals, in that order (the reference's order per block). */
+int rb200_frame_reserve_obmc_items(Rb200Frame *f, int max_obmc_items);
+Rb200McItem *rb200_frame_obmc_items(Rb200Frame *f);
+int rb200_frame_set_obmc_counts(Rb200Frame *f, int n_above, int n_left);
 int rb200_frame_reserve_warp_items(Rb200Frame *f, int max_warp_items);
 Rb200WarpItem *rb200_frame_warp_items(Rb200Frame *f);
 int rb200_frame_set_warp_count(Rb200Frame *f, int n_warp_items);

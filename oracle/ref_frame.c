@@ -490,3 +490,41 @@ void ref_frame_recon_warp(RefFrame *r, RefFrame *const refs[], int n_refs, const
     for (int i = 0; i < n_refs && i < 8; i++) a.refs[i] = refs[i];
     parallel_for(r, n_threads, n, do_warp_item, &a);
 }
+
+/* ------------------------------------------------------------ OBMC strips */
+/* obmc() (src/recon_tmpl.c:1076-1137): the neighbour's prediction of a strip into `lap`, then
+ * blend_h (above) / blend_v (left).  Items: all ABOVE first, then LEFT; run in list order. */
+void ref_frame_recon_obmc(RefFrame *r, RefFrame *const refs[], int n_refs, const Rb200McItem *items, int n) {
+    (void)n_refs;
+    Dav1dFrameContext *f = r->f;
+    const int px = r->hbd ? 2 : 1;
+    const int ss_ver_l = f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420, ss_hor_l = f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444;
+    uint8_t *emu = malloc(320 * (256 + 7) * 2), *lap = malloc(128 * 128 * 2);
+    for (int i = 0; i < n; i++) {
+        const Rb200McItem *it = &items[i];
+        const int pl = it->plane, ss_hor = pl && ss_hor_l, ss_ver = pl && ss_ver_l;
+        const Dav1dFrameContext *rf = refs[it->ref]->f;
+        const int w = (f->cur.p.w + ss_hor) >> ss_hor, h = (f->cur.p.h + ss_ver) >> ss_ver;
+        const int above = it->flags == RB200_MC_OBMC_ABOVE;
+        const int v_mul = 4 >> ss_ver;
+        const int bw = it->w, bh = above ? (((it->h / v_mul) * 3 + 3) >> 2) * v_mul : it->h;
+        const int mx = it->mx, my = it->my, dx = it->src_x, dy = it->src_y;
+        ptrdiff_t ref_stride = rf->cur.stride[!!pl];
+        const uint8_t *ref;
+        if (dx < !!mx * 3 || dy < !!my * 3 || dx + bw + !!mx * 4 > w || dy + bh + !!my * 4 > h) {
+            ((void (*)(intptr_t, intptr_t, intptr_t, intptr_t, intptr_t, intptr_t, void *, ptrdiff_t, const void *, ptrdiff_t))
+                 f->dsp->mc.emu_edge)(bw + !!mx * 7, bh + !!my * 7, w, h, dx - !!mx * 3, dy - !!my * 3, emu, 192 * px,
+                                      rf->cur.data[pl], ref_stride);
+            ref = emu + (192 * !!my * 3 + !!mx * 3) * px;
+            ref_stride = 192 * px;
+        } else {
+            ref = (const uint8_t *)rf->cur.data[pl] + ref_stride * dy + (ptrdiff_t)dx * px;
+        }
+        if (r->hbd) ((mc_fn16)f->dsp->mc.mc[it->filter2d])(lap, (ptrdiff_t)bw * px, ref, ref_stride, bw, bh, mx, my, r->bdmax);
+        else ((mc_fn8)f->dsp->mc.mc[it->filter2d])(lap, (ptrdiff_t)bw * px, ref, ref_stride, bw, bh, mx, my);
+        uint8_t *dst = (uint8_t *)f->cur.data[pl] + f->cur.stride[!!pl] * it->dst_y + (ptrdiff_t)it->dst_x * px;
+        ((void (*)(void *, ptrdiff_t, const void *, int, int))(above ? f->dsp->mc.blend_h : f->dsp->mc.blend_v))(
+            dst, f->cur.stride[!!pl], lap, it->w, it->h);
+    }
+    free(lap); free(emu);
+}

@@ -77,6 +77,8 @@ int mc_comp_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_
                          const Rb200CompItem *d_items, int n, int bdmax, cudaStream_t st);
 int mc_warp_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int layout,
                          const Rb200WarpItem *d_items, int n, int bdmax, cudaStream_t st);
+int mc_obmc_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int ss_hor,
+                         int ss_ver, const Rb200McItem *d_items, int n, int bdmax, cudaStream_t st);
 int deblock_frame_launch(const Rb200Planes &pl, int n_planes, int w4, int h4, int sb128w, int b4_stride, int ss_hor,
                          int ss_ver, bool do_uv, const Rb200Av1Filter *masks, const uint8_t (*lvl)[4],
                          const Rb200Av1FilterLUT *lut, int bdmax, cudaStream_t st, int *launches, int y4b, int y4e);

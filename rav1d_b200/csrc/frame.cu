@@ -41,6 +41,7 @@ struct Rb200Frame {
     Rb200McItem *h_mc, *d_mc;
     Rb200CompItem *h_comp, *d_comp; int max_comp, n_comp;
     Rb200WarpItem *h_warp, *d_warp; int max_warp, n_warp;
+    Rb200McItem *h_obmc, *d_obmc; int max_obmc, n_obmc_above, n_obmc_left;
     Rb200Av1Filter *h_masks, *d_masks;
     uint8_t (*h_lvl)[4], (*d_lvl)[4];
     Rb200Av1FilterLUT *h_lut, *d_lut;
@@ -165,6 +166,8 @@ extern "C" int rb200_frame_destroy(Rb200Frame *f) {
     if (f->d_coef) cudaFree(f->d_coef);
     if (f->h_itx) cudaFreeHost(f->h_itx);
     if (f->d_itx) cudaFree(f->d_itx);
+    if (f->h_obmc) cudaFreeHost(f->h_obmc);
+    if (f->d_obmc) cudaFree(f->d_obmc);
     if (f->h_warp) cudaFreeHost(f->h_warp);
     if (f->d_warp) cudaFree(f->d_warp);
     if (f->h_comp) cudaFreeHost(f->h_comp);
@@ -469,6 +472,26 @@ extern "C" int rb200_frame_set_warp_count(Rb200Frame *f, int n) {
     return 0;
 }
 
+extern "C" int rb200_frame_reserve_obmc_items(Rb200Frame *f, int max_obmc) {
+    if (!f || max_obmc < 0) return set_error(-22, "frame_reserve_obmc_items: bad argument");
+    if (max_obmc <= f->max_obmc) return 0;
+    RB_CUDA(cudaStreamSynchronize(f->stream));
+    if (f->h_obmc) cudaFreeHost(f->h_obmc);
+    if (f->d_obmc) cudaFree(f->d_obmc);
+    f->h_obmc = nullptr; f->d_obmc = nullptr; f->max_obmc = 0; f->n_obmc_above = f->n_obmc_left = 0;
+    const int r = alloc_pair(&f->h_obmc, &f->d_obmc, (size_t)max_obmc);
+    if (r) return r;
+    f->max_obmc = max_obmc;
+    return 0;
+}
+extern "C" Rb200McItem *rb200_frame_obmc_items(Rb200Frame *f) { return f ? f->h_obmc : nullptr; }
+extern "C" int rb200_frame_set_obmc_counts(Rb200Frame *f, int n_above, int n_left) {
+    if (!f || n_above < 0 || n_left < 0 || n_above + n_left > f->max_obmc)
+        return set_error(-22, "frame_set_obmc_counts: more items than reserved");
+    f->n_obmc_above = n_above; f->n_obmc_left = n_left;
+    return 0;
+}
+
 extern "C" int rb200_frame_set_ref(Rb200Frame *f, int slot, const Rb200Planes *planes) {
     if (!f || slot < 0 || slot > 7 || !planes) return set_error(-22, "frame_set_ref: bad argument");
     f->refs[slot] = *planes;
@@ -563,7 +586,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         }
         if (n_coefs > f->max_coefs || n_itx > f->max_itx || n_mc > f->max_mc || n_mc < 0)
             return set_error(-22, "frame_submit: batch larger than the frame was created for");
-        if ((n_mc || f->n_comp || f->n_warp) && f->n_refs < 1) return set_error(-22, "frame_submit: no reference picture set");
+        if ((n_mc || f->n_comp || f->n_warp || f->n_obmc_above || f->n_obmc_left) && f->n_refs < 1) return set_error(-22, "frame_submit: no reference picture set");
     }
     f->launches = 0;
     const BandRows band = band_rows(f);
@@ -585,6 +608,8 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
             if (n_mc) RB_CUDA(cudaMemcpyAsync(f->d_mc, f->h_mc, (size_t)n_mc * sizeof(Rb200McItem), cudaMemcpyHostToDevice, st));
             if (f->n_comp) RB_CUDA(cudaMemcpyAsync(f->d_comp, f->h_comp, (size_t)f->n_comp * sizeof(Rb200CompItem), cudaMemcpyHostToDevice, st));
             if (f->n_warp) RB_CUDA(cudaMemcpyAsync(f->d_warp, f->h_warp, (size_t)f->n_warp * sizeof(Rb200WarpItem), cudaMemcpyHostToDevice, st));
+            if (f->n_obmc_above + f->n_obmc_left)
+                RB_CUDA(cudaMemcpyAsync(f->d_obmc, f->h_obmc, (size_t)(f->n_obmc_above + f->n_obmc_left) * sizeof(Rb200McItem), cudaMemcpyHostToDevice, st));
         }
         if (do_lf || do_cdef)
             RB_CUDA(cudaMemcpyAsync(f->d_masks, f->h_masks, f->n_masks * sizeof(Rb200Av1Filter), cudaMemcpyHostToDevice, st));
@@ -613,6 +638,17 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         if (f->n_warp) {
             if ((r = mc_warp_batch_launch(f->planes[0], f->refs, f->n_refs, h.width, h.height, h.layout, f->d_warp, f->n_warp,
                                           f->bdmax, st))) return r;
+            f->launches++;
+        }
+        // OBMC: every ABOVE strip, then every LEFT strip, on top of the finished predictions
+        if (f->n_obmc_above) {
+            if ((r = mc_obmc_batch_launch(f->planes[0], f->refs, f->n_refs, h.width, h.height, g.ss_hor, g.ss_ver, f->d_obmc,
+                                          f->n_obmc_above, f->bdmax, st))) return r;
+            f->launches++;
+        }
+        if (f->n_obmc_left) {
+            if ((r = mc_obmc_batch_launch(f->planes[0], f->refs, f->n_refs, h.width, h.height, g.ss_hor, g.ss_ver,
+                                          f->d_obmc + f->n_obmc_above, f->n_obmc_left, f->bdmax, st))) return r;
             f->launches++;
         }
         MARK(2);

@@ -689,6 +689,64 @@ int mc_warp_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_
     return 0;
 }
 
+// ---------------------------------------------------------------- OBMC strips (batch)
+// One warp per strip: the neighbour's prediction of the strip goes into a warp-private tile, then
+// blend_h / blend_v (src/mc.rs:742-810) onto the block's own prediction.
+template <typename BD>
+__global__ void __launch_bounds__(MC_WARPS * 32)
+mc_obmc_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int ss_hor_c, int ss_ver_c,
+                     const Rb200McItem *__restrict__ items, int n_items, int bdmax) {
+    using pixel = typename BD::pixel;
+    __shared__ struct { McSmem slow; pixel lap[MC_TILE * MC_TILE]; } smem[MC_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * MC_WARPS + warp;
+    if (idx >= n_items) return;
+    const Rb200McItem it = items[idx];
+    const Rb200Planes &rp = refs.p[it.ref & 7];
+    const int ss_hor = it.plane ? ss_hor_c : 0, ss_ver = it.plane ? ss_ver_c : 0;
+    McRef ref;
+    ref.base = plane_ptr(rp, it.plane);
+    ref.stride = plane_stride(rp, it.plane);
+    ref.w = it.plane ? (ref_w + ss_hor) >> ss_hor : ref_w;
+    ref.h = it.plane ? (ref_h + ss_ver) >> ss_ver : ref_h;
+    const bool above = it.flags == RB200_MC_OBMC_ABOVE;
+    const int v_mul = 4 >> ss_ver;
+    // the prediction the reference makes for an ABOVE strip is ((oh4 * 3 + 3) >> 2) units tall
+    const int pred_h = above ? (((it.h / v_mul) * 3 + 3) >> 2) * v_mul : it.h;
+    const int lim_r = above ? (it.h * 3) >> 2 : it.h, lim_c = above ? it.w : (it.w * 3) >> 2;
+    uint8_t *dbase = plane_ptr(dst, it.plane);
+    const int64_t dstride = plane_stride(dst, it.plane);
+    for (int ty = 0; ty < pred_h; ty += MC_TILE) {
+        for (int tx = 0; tx < it.w; tx += MC_TILE) {
+            const int tw = imin(MC_TILE, it.w - tx), th = imin(MC_TILE, pred_h - ty);
+            mc_tile<BD, false>(smem[warp].slow, ref, it.src_x + tx, it.src_y + ty, tw, th, it.w, pred_h, it.mx, it.my,
+                               it.filter2d, smem[warp].lap, MC_TILE * sizeof(pixel), bdmax);
+            __syncwarp();
+            for (int e = lane; e < tw * th; e += 32) {
+                const int r = e / tw, c = e - r * tw;
+                const int row = ty + r, col = tx + c;
+                if (row >= lim_r || col >= lim_c) continue;
+                const int m = above ? tab::k_obmc_masks[it.h + row] : tab::k_obmc_masks[it.w + col];
+                pixel *d = (pixel *)(dbase + (int64_t)(it.dst_y + row) * dstride) + it.dst_x + col;
+                *d = (pixel)(((int)*d * (64 - m) + (int)smem[warp].lap[r * MC_TILE + c] * m + 32) >> 6);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+int mc_obmc_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int ss_hor,
+                         int ss_ver, const Rb200McItem *d_items, int n, int bdmax, cudaStream_t st) {
+    if (n <= 0) return 0;
+    McRefSet rs = {};
+    for (int i = 0; i < n_refs && i < 8; i++) rs.p[i] = refs[i];
+    const int grid = (n + MC_WARPS - 1) / MC_WARPS;
+    if (bdmax > 255) mc_obmc_batch_kernel<BD16><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, ss_hor, ss_ver, d_items, n, bdmax);
+    else mc_obmc_batch_kernel<BD8><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, ss_hor, ss_ver, d_items, n, bdmax);
+    RB_LAUNCH_CHECK();
+    return 0;
+}
+
 // Per-call: a single prediction block over a staged source rectangle; one warp per 16x16 tile.
 template <typename BD, bool PREP>
 __global__ void __launch_bounds__(MC_WARPS * 32)

@@ -112,6 +112,7 @@ WARP_ITEM_DT = _np.dtype([("x", "<i2"), ("y", "<i2"), ("w", "u1"), ("h", "u1"), 
                           ("matrix", "<i4", (6,)), ("abcd", "<i2", (4,)), ("pad", "u1", (8,))])
 assert WARP_ITEM_DT.itemsize == 48
 COMP_AVG, COMP_WEIGHTED_AVG, COMP_SEG = 0, 1, 2
+MC_PUT, MC_OBMC_ABOVE, MC_OBMC_LEFT = 0, 1, 2
 assert MC_ITEM_DT.itemsize == 16 and ITX_ITEM_DT.itemsize == 16 and COMP_ITEM_DT.itemsize == 32
 assert AV1_FILTER_DT.itemsize == 1348 and AV1_RESTORATION_DT.itemsize == 108
 
@@ -201,6 +202,9 @@ frame_lr_masks = _sig("rb200_frame_lr_masks", _vp, _vp)
 frame_reserve_comp_items = _sig("rb200_frame_reserve_comp_items", _i, _vp, _i)
 frame_comp_items = _sig("rb200_frame_comp_items", _vp, _vp)
 frame_set_comp_count = _sig("rb200_frame_set_comp_count", _i, _vp, _i)
+frame_reserve_obmc_items = _sig("rb200_frame_reserve_obmc_items", _i, _vp, _i)
+frame_obmc_items = _sig("rb200_frame_obmc_items", _vp, _vp)
+frame_set_obmc_counts = _sig("rb200_frame_set_obmc_counts", _i, _vp, _i, _i)
 frame_reserve_warp_items = _sig("rb200_frame_reserve_warp_items", _i, _vp, _i)
 frame_warp_items = _sig("rb200_frame_warp_items", _vp, _vp)
 frame_set_warp_count = _sig("rb200_frame_set_warp_count", _i, _vp, _i)

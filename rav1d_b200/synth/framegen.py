@@ -93,7 +93,7 @@ def geometry(hd):
     return g
 
 
-def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1, comp_frac=0.0, warp_frac=0.0):
+def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1, comp_frac=0.0, warp_frac=0.0, obmc_frac=0.0):
     """Returns a SynthFrame with numpy arrays; see module docstring."""
     rng = np.random.default_rng(seed)
     bdmax = (1 << bpc) - 1
@@ -184,6 +184,29 @@ def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1, comp_frac=0.0, w
         c_it["w"] = BLK // 2; c_it["h"] = BLK // 2; c_it["plane"] = p
         c_it["mx"] = mvx & 15; c_it["my"] = mvy & 15
         c_it["filter2d"] = f2d
+    # OBMC (src/recon.rs:2205-2309) on some translational blocks: one strip from the block above
+    # (blend_h) and one from the block to the left (blend_v), per plane, predicted with that neighbour's
+    # vector and filter.  16x16 blocks: above strip 16x8 (4:2:0 chroma 8x4), left strip 8x16 (4x8).
+    is_obmc = (rng.random(nb) < obmc_frac) & ~is_comp & ~is_warp
+    def strips(above):
+        sel = np.nonzero(is_obmc & ((by > 0) if above else (bx > 0)))[0]
+        nbr = sel - nbx if above else sel - 1
+        out = np.zeros(sel.size * 3, lib.MC_ITEM_DT)
+        for p in range(3):
+            sh = 0 if p == 0 else 1
+            o = out[p * sel.size:(p + 1) * sel.size]
+            bw_, bh_ = (BLK, BLK // 2) if above else (BLK // 2, BLK)
+            o["dst_x"] = bx[sel] * BLK >> sh; o["dst_y"] = by[sel] * BLK >> sh
+            o["src_x"] = (bx[sel] * BLK >> sh) + (mvx[nbr] >> (3 + sh)); o["src_y"] = (by[sel] * BLK >> sh) + (mvy[nbr] >> (3 + sh))
+            o["w"] = bw_ >> sh; o["h"] = bh_ >> sh; o["plane"] = p
+            o["mx"] = ((mvx[nbr] & 7) << 1) if p == 0 else (mvx[nbr] & 15)
+            o["my"] = ((mvy[nbr] & 7) << 1) if p == 0 else (mvy[nbr] & 15)
+            o["filter2d"] = f2d[nbr]
+            o["flags"] = lib.MC_OBMC_ABOVE if above else lib.MC_OBMC_LEFT
+        return out
+    ab, lf_ = strips(True), strips(False)
+    s.obmc_items = np.concatenate([ab, lf_])
+    s.n_obmc = (len(ab), len(lf_))
     keep = np.tile(~(is_comp | is_warp), 3)
     s.mc_items = np.ascontiguousarray(mc[keep])
 
@@ -405,6 +428,11 @@ class DeviceFrame:
         lv[:] = s.levels.reshape(-1)
         C.memmove(lib.frame_lf_lut(self.h), C.byref(s.lut), C.sizeof(lib.FilterLUT))
         lib.np_view(lib.frame_lr_masks(self.h), lib.AV1_RESTORATION_DT, n)[:] = s.lr_masks
+        obmc = getattr(s, "obmc_items", None)
+        if obmc is not None and len(obmc):
+            lib.check(lib.frame_reserve_obmc_items(self.h, len(obmc)), "reserve_obmc_items")
+            lib.np_view(lib.frame_obmc_items(self.h), lib.MC_ITEM_DT, len(obmc))[:] = obmc
+            lib.check(lib.frame_set_obmc_counts(self.h, *s.n_obmc))
         warp = getattr(s, "warp_items", None)
         if warp is not None and len(warp):
             lib.check(lib.frame_reserve_warp_items(self.h, len(warp)), "reserve_warp_items")

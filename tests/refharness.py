@@ -67,6 +67,7 @@ def load():
         sig("ref_frame_recon", None, vp, vp, i, vp, i, vp, i, vp, i)
         sig("ref_frame_recon_comp", None, vp, vp, i, vp, i, i)
         sig("ref_frame_recon_warp", None, vp, vp, i, vp, i, i)
+        sig("ref_frame_recon_obmc", None, vp, vp, i, vp, i)
         sig("ref_frame_apply_grain", None, vp, vp, i)
         sig("ref_frame_grain_plane", vp, vp, i)
         sig("ref_fg_gen_y", None, vp, vp, i)
@@ -141,12 +142,13 @@ class RefFrame:
         warp = np.ascontiguousarray(getattr(s, "warp_items", np.zeros(0, np.uint8)))
         if len(warp):
             self.ref.ref_frame_recon_warp(self.h, refs, len(frames), ptr(warp), len(warp), n_threads)
+        obmc = np.ascontiguousarray(getattr(s, "obmc_items", np.zeros(0, np.uint8)))
+        self.ref.ref_frame_recon(self.h, refs, len(frames), ptr(mc), len(mc), ptr(itx), 0, ptr(cw), n_threads)
         if len(comp):
-            self.ref.ref_frame_recon(self.h, refs, len(frames), ptr(mc), len(mc), ptr(itx), 0, ptr(cw), n_threads)
             self.ref.ref_frame_recon_comp(self.h, refs, len(frames), ptr(comp), len(comp), n_threads)
-            self.ref.ref_frame_recon(self.h, refs, len(frames), ptr(mc), 0, ptr(itx), len(itx), ptr(cw), n_threads)
-        else:
-            self.ref.ref_frame_recon(self.h, refs, len(frames), ptr(mc), len(mc), ptr(itx), len(itx), ptr(cw), n_threads)
+        if len(obmc):
+            self.ref.ref_frame_recon_obmc(self.h, refs, len(frames), ptr(obmc), len(obmc))
+        self.ref.ref_frame_recon(self.h, refs, len(frames), ptr(mc), 0, ptr(itx), len(itx), ptr(cw), n_threads)
         return cw
 
     def apply_grain(self, fg, is_id=0):

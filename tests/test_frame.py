@@ -65,6 +65,16 @@ def test_warped_blocks(rb, ref, w, h, bpc):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("w,h,bpc", [(176, 144, 8), (208, 128, 10), (256, 192, 12)])
+def test_obmc_strips(rb, ref, w, h, bpc):
+    """Overlapped block MC on top of translational, compound and warped neighbours (BASELINE config 5)."""
+    s = framegen.generate(w, h, bpc, seed=w + 3, comp_frac=0.25, warp_frac=0.1, obmc_frac=0.5)
+    assert s.n_obmc[0] > 10 and s.n_obmc[1] > 10
+    _check(ref, s, R)
+    _check(ref, s, R | D | Cd | L)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("unit_log2", [7, 8])
 def test_lr_unit_sizes(rb, ref, unit_log2):
     """Restoration units larger than the 64-pixel default, incl. the 1.5x last unit."""
