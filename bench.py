@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Throughput of the recon + post-filter path on synthetic frames (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload 4k10|1080p8|8k10]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload 4k10|1080p8|8k10|4k10c5]
 
 A *step* is one pass of the hot path over one batch of FRAMES_PER_STEP synthetic frames:
 recon (8-tap MC + itx add) -> deblock -> CDEF -> Wiener/SGR loop restoration (4k10: BASELINE
@@ -43,11 +43,15 @@ WORKLOADS = {
     "4k10": (3840, 2160, 10, 15, "4K 10-bit 4:2:0 synthetic inter frame: recon (8-tap/bilinear MC + itx) + deblock + CDEF + Wiener/SGR LR"),
     "1080p8": (1920, 1080, 8, 3, "1080p 8-bit 4:2:0 synthetic inter frame: recon (8-tap/bilinear MC + itx) + deblock"),
     "8k10": (7680, 4320, 10, 14, "8K 10-bit 4:2:0 post-filters only: deblock + CDEF + Wiener/SGR LR"),
+    # BASELINE configs[4] per GPU: 50 % compound blocks (avg / w_avg / segmentation mask), 5 % warped, OBMC on 10 %, film grain
+    "4k10c5": (3840, 2160, 10, 31, "4K 10-bit 4:2:0 synthetic inter frame, 50% compound / 5% warped / 10% OBMC blocks: "
+                                   "recon + deblock + CDEF + Wiener/SGR LR + film grain"),
 }
+GEN_ARGS = {"4k10c5": dict(comp_frac=0.5, warp_frac=0.05, obmc_frac=0.1)}
 FRAMES_PER_STEP = 16
 N_CTX = int(os.environ.get("RB200_BENCH_CTX", "8"))
 METRIC = "recon+post-filter throughput (itx+MC+LF/CDEF/LR), luma pixels of output frames"
-STAGE_NAMES = ["h2d", "mc", "itx", "deblock", "cdef", "lr"]
+STAGE_NAMES = ["h2d", "mc", "itx", "deblock", "cdef", "lr", "film_grain"]
 
 
 def peaks():
@@ -57,13 +61,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def algorithmic_bytes(w, h, bpc):
-    """SURVEY 8(d) / BASELINE.md 4: S = one 4:2:0 plane set, C = dense coefficients."""
+def algorithmic_bytes(w, h, bpc, comp_frac=0.0):
+    """SURVEY 8(d) / BASELINE.md 4: S = one 4:2:0 plane set, C = dense coefficients; a compound block
+    reads two references."""
     px, cs = (2, 4) if bpc > 8 else (1, 2)
     S = w * h * 3 // 2 * px
     Cb = w * h * 3 // 2 * cs
-    return {"mc": 2 * S, "itx": Cb + 2 * S, "recon": 2 * S + Cb, "deblock": 2 * S, "cdef": 2 * S, "lr": 2 * S,
-            "S": S, "C": Cb}
+    mc = int((2 + comp_frac) * S)
+    return {"mc": mc, "itx": Cb + 2 * S, "recon": mc + Cb, "deblock": 2 * S, "cdef": 2 * S, "lr": 2 * S,
+            "film_grain": 2 * S, "S": S, "C": Cb}
 
 
 class ClockSampler:
@@ -112,12 +118,15 @@ def cpu_frames(s, stages, n_frames, n_threads):
     ref = refharness.load()
     cur = refharness.RefFrame(ref, s, max(n_threads, 2))
     rf = refharness.RefFrame(ref, s, 1)
+    rf2 = refharness.RefFrame(ref, s, 1) if hasattr(s, "ref2") else None
     start = None
     if not stages & 1:
         from rav1d_b200.synth import framegen
         start = framegen.recon_input_planes(s)
     try:
         rf.set_planes(s.ref)
+        if rf2:
+            rf2.set_planes(s.ref2)
         cur.load_filter_meta()
         cw = s.coef.copy()
         total = 0.0
@@ -128,14 +137,18 @@ def cpu_frames(s, stages, n_frames, n_threads):
                 cur.set_planes(start)
             t0 = time.perf_counter()
             if stages & 1:
-                cur.recon(rf, n_threads=n_threads, coef_work=cw)
-            if stages & ~1:
-                cur.filter(stages, n_threads=n_threads)
+                cur.recon(rf, n_threads=n_threads, coef_work=cw, ref_frame2=rf2)
+            if stages & 14:
+                cur.filter(stages & 14, n_threads=n_threads)
+            if stages & 16:
+                cur.apply_grain_inplace(s.film_grain, 0)
             total += time.perf_counter() - t0
         return total
     finally:
         cur.close()
         rf.close()
+        if rf2:
+            rf2.close()
 
 
 def cpu_model():
@@ -149,7 +162,7 @@ def cpu_model():
 
 
 def run_reference(args, s, wl):
-    w, h, bpc, stages, desc = wl
+    w, h, bpc, stages, desc = wl[:5]
     cores = os.cpu_count() or 1
     t1 = cpu_frames(s, stages, 1, cores)                       # warm-up + estimate
     per_step = max(1, min(FRAMES_PER_STEP, int(1.5 / max(t1, 1e-3))))   # ~1.5 s of CPU work per step
@@ -196,8 +209,12 @@ def run_gpu(args, s, wl):
         d.load_batch()
         if stages & 1:
             d.set_ref_from_host(s.ref)
+            if hasattr(s, "ref2"):
+                d.set_ref_slot(1, s.ref2)
         else:
             d.upload(0, start_planes)
+        if stages & 16:
+            lib.check(lib.frame_set_film_grain(d.h, C.byref(s.film_grain), 0))
         lib.check(lib.frame_enable_timing(d.h, 1))
         ctxs.append(d)
     # pinned host output planes for the e2e leg
@@ -293,7 +310,7 @@ def run_gpu(args, s, wl):
         s1e.record(main)
         barrier()
         value_serial = args.steps * FRAMES_PER_STEP * w * h / (s0e.elapsed_time(s1e) * 1e-3) / 1e6
-    stage_ms = stage_ms[:6] / max(stage_n, 1)
+    stage_ms = stage_ms / max(stage_n, 1)
 
     # ---------------- e2e leg: host buffers, N_CTX frames in flight on their own streams
     for d in ctxs:
@@ -335,14 +352,15 @@ def run_gpu(args, s, wl):
             h2d += int((s.itx_items["ncols"].astype(np.int64) * sh).sum()) * cs
         else:
             h2d += s.n_coefs * cs
-        h2d += 16 * (len(s.itx_items) + n_mc)
+        h2d += 16 * (len(s.itx_items) + n_mc + len(getattr(s, "obmc_items", ()))) + 32 * len(getattr(s, "comp_items", ())) \
+            + 48 * len(getattr(s, "warp_items", ()))
     h2d += n_sb * 1348 + (g.b4_stride * 32 * g.sb128h + 32) * 4 + 144 + n_sb * 108
     d2h = sum(out_bytes)
 
     line = None
     if rank == 0:
         peak, peak_src = peaks()
-        ab = algorithmic_bytes(w, h, bpc)
+        ab = algorithmic_bytes(w, h, bpc, GEN_ARGS.get(args.workload, {}).get('comp_frac', 0.0))
         per_stage = {}
         for name, t_ms in zip(STAGE_NAMES, stage_ms):
             if name == "h2d" or t_ms <= 0:
@@ -357,7 +375,7 @@ def run_gpu(args, s, wl):
                         "frac": round(ach / peak, 4), "traffic": TRAFFIC.get((args.workload, dom)),
                         "peak_source": peak_src, "share_of_step": round(per_stage[dom]["ms"] / sum(v["ms"] for v in per_stage.values()), 3)}
         # frame-level algorithmic bytes as BASELINE.md 4 counts them (MC + itx = one fused recon stage: 2S + C)
-        frame_bytes = (ab["recon"] if stages & 1 else 0) + sum(ab[k] for k in ("deblock", "cdef", "lr") if k in per_stage)
+        frame_bytes = (ab["recon"] if stages & 1 else 0) + sum(ab[k] for k in ("deblock", "cdef", "lr", "film_grain") if k in per_stage)
         line = {"metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32", "data": "synthetic",
@@ -422,7 +440,9 @@ def main():
     if args.impl == "reference" and rank != 0:
         return
     from rav1d_b200.synth import framegen
-    s = framegen.generate(wl[0], wl[1], wl[2], seed=1 + (rank if args.impl == "b200" else 0))
+    s = framegen.generate(wl[0], wl[1], wl[2], seed=1 + (rank if args.impl == "b200" else 0), **GEN_ARGS.get(args.workload, {}))
+    if wl[3] & 16:
+        s.film_grain = framegen.random_film_grain(np.random.default_rng(7), lag=3, overlap=1)
     if args.impl == "reference":
         run_reference(args, s, wl)
     else:

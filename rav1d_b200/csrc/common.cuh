@@ -102,12 +102,13 @@ struct FgApplyParams {
     int uv_mult, uv_luma_mult, uv_offset;
 };
 int fg_generate(void *lut, const void *lut_y, const Rb200FilmGrainData &d, int uv, int subx, int suby, int bdmax,
-                cudaStream_t st);
+                cudaStream_t st, int n_luts = 1, int lut_pitch_bytes = 0);
 int fg_apply(uint8_t *dst, const uint8_t *src, int64_t stride, const uint8_t *luma, int64_t luma_stride,
              const FgApplyParams &P, const uint8_t *scaling, const void *lut, const uint8_t *off, int bdmax,
              cudaStream_t st);
 int fg_offsets(uint8_t *off, unsigned seed, int row0, int nrows, int ncols, cudaStream_t st);
-int fg_scaling(uint8_t *scaling, const uint8_t *d_points, int num, int bitdepth, cudaStream_t st);
+struct FgPoints { uint8_t p[32]; };   // up to 14 (x, y) scaling points, passed by value
+int fg_scaling(uint8_t *scaling, const uint8_t points[][2], int num, int bitdepth, cudaStream_t st);
 FgApplyParams fg_params(const Rb200FilmGrainData &d, int chroma, int uv, int sx, int sy, int is_id);
 
 // ---- error plumbing --------------------------------------------------

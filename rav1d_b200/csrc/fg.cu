@@ -33,68 +33,93 @@ __device__ __forceinline__ int fg_round2(int x, int shift) { return (x + ((1 << 
 template <typename BD> struct FgEntry { using type = int8_t; };
 template <> struct FgEntry<BD16> { using type = int16_t; };
 
-// One CTA generates one grain LUT.  uv < 0: luma.  lut_y: finished luma LUT (chroma only).
-template <typename BD>
+// y = M * s over GF(2), M given as the images of the 16 basis vectors
+__device__ __forceinline__ unsigned fg_gf2_apply(const uint16_t *M, unsigned s) {
+    unsigned n = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) n ^= ((s >> i) & 1) ? M[i] : 0;
+    return n;
+}
+
+// One CTA generates one grain LUT.  uv0 < 0: luma; otherwise CTA b generates chroma plane uv0 + b into
+// lut + b * lut_pitch.  lut_y: finished luma LUT (chroma only).  LAG = ar_coeff_lag.
+template <typename BD, int LAG>
 __global__ void __launch_bounds__(96)
 fg_generate_kernel(typename FgEntry<BD>::type *__restrict__ lut, const typename FgEntry<BD>::type *__restrict__ lut_y,
-                   Rb200FilmGrainData d, int uv, int subx, int suby, int bdmax) {
+                   Rb200FilmGrainData d, int uv0, int subx, int suby, int bdmax, int lut_pitch) {
     __shared__ int16_t buf[GH][GW];
-    __shared__ uint16_t J[16];
-    __shared__ int8_t coef[28];
+    __shared__ int16_t lum[GH][GW];
+    __shared__ uint16_t Jp[7][16];
     const int tid = threadIdx.x;
+    const int uv = uv0 < 0 ? -1 : uv0 + (int)blockIdx.x;
+    lut += (size_t)blockIdx.x * lut_pitch;
     const int bdmin8 = BD::hbd ? bpc_from_max(bdmax) - 8 : 0;
     const int W = (uv >= 0 && subx) ? SUB_GW : GW, H = (uv >= 0 && suby) ? SUB_GH : GH;
     const int shift = 4 - bdmin8 + d.grain_scale_shift;
     const int grain_ctr = 128 << bdmin8, grain_min = -grain_ctr, grain_max = grain_ctr - 1;
-    if (tid < 28) coef[tid] = uv < 0 ? (tid < 24 ? d.ar_coeffs_y[tid] : 0) : d.ar_coeffs_uv[uv][tid];
-    if (tid < 16) {  // J = (LFSR step)^W, stored as the images of the 16 basis vectors
+    // J = (LFSR step)^W and its squarings J^2, J^4, .. J^64
+    if (tid < 16) {
         unsigned v = 1u << tid;
         for (int i = 0; i < W; i++) v = fg_lfsr_step(v);
-        J[tid] = (uint16_t)v;
+        Jp[0][tid] = (uint16_t)v;
     }
     __syncthreads();
-    if (tid < H) {
-        unsigned s = uv < 0 ? d.seed : d.seed ^ (uv ? 0x49d8u : 0xb524u);
-        for (int r = 0; r < tid; r++) {  // s = J * s
-            unsigned n = 0;
-#pragma unroll
-            for (int i = 0; i < 16; i++) n ^= ((s >> i) & 1) ? J[i] : 0;
-            s = n;
-        }
-        for (int x = 0; x < W; x++) {
-            s = fg_lfsr_step(s);
-            const int value = (s >> 5) & 0x7ff;
-            buf[tid][x] = (int16_t)fg_round2(tab::k_gaussian_sequence[value], shift);
-        }
-    }
-    __syncthreads();
-    // auto-regressive filter, raster-causal (src/filmgrain_tmpl.c:66-84,112-148)
-    const int lag = d.ar_coeff_lag, ar_shift = (int)d.ar_coeff_shift;
-    const bool luma_term = uv >= 0 && d.num_y_points != 0;
-    const int y = tid;
-    const int n_steps = (W - 6) + 4 * (H - 4) + 1;
-    for (int t = 0; t < n_steps; t++) {
-        const int x = t - 4 * (y - 3) + 3;
-        if (y >= 3 && y < H && x >= 3 && x < W - 3) {
-            int sum = 0, c = 0;
-            for (int dy = -lag; dy <= 0; dy++) {
-                for (int dx = -lag; dx <= lag; dx++) {
-                    if (!dx && !dy) break;
-                    sum += coef[c++] * buf[y + dy][x + dx];
-                }
-            }
-            if (luma_term) {
-                int luma = 0;
-                const int lx = ((x - 3) << subx) + 3, ly = ((y - 3) << suby) + 3;
-                for (int i = 0; i <= suby; i++)
-                    for (int j = 0; j <= subx; j++) luma += lut_y[(ly + i) * GW + lx + j];
-                luma = fg_round2(luma, subx + suby);
-                sum += luma * coef[c];
-            }
-            buf[y][x] = (int16_t)iclip(buf[y][x] + fg_round2(sum, ar_shift), grain_min, grain_max);
-        }
+    for (int k = 1; k < 7; k++) {
+        if (tid < 16) Jp[k][tid] = (uint16_t)fg_gf2_apply(Jp[k - 1], Jp[k - 1][tid]);
         __syncthreads();
     }
+    if (tid < H) {
+        unsigned s = uv < 0 ? d.seed : d.seed ^ (uv ? 0x49d8u : 0xb524u);
+        for (int k = 0; k < 7; k++)
+            if ((tid >> k) & 1) s = fg_gf2_apply(Jp[k], s);          // s = J^tid * seed
+        for (int x = 0; x < W; x++) {
+            s = fg_lfsr_step(s);
+            buf[tid][x] = (int16_t)fg_round2(tab::k_gaussian_sequence[(s >> 5) & 0x7ff], shift);
+        }
+    }
+    // auto-regressive filter, raster-causal (src/filmgrain_tmpl.c:66-84,112-148)
+    constexpr int NC = 2 * LAG * (LAG + 1);
+    int coef[NC + 1];
+#pragma unroll
+    for (int i = 0; i <= NC; i++) coef[i] = uv < 0 ? (i < 24 ? d.ar_coeffs_y[i < 24 ? i : 0] : 0) : d.ar_coeffs_uv[uv][i];
+    const int ar_shift = (int)d.ar_coeff_shift;
+    const bool luma_term = uv >= 0 && d.num_y_points != 0;
+    if (luma_term) {   // the luma-grain term of every chroma entry, up front
+        for (int i = tid; i < (H - 3) * (W - 6); i += blockDim.x) {
+            const int y = 3 + i / (W - 6), x = 3 + i % (W - 6);
+            const int lx = ((x - 3) << subx) + 3, ly = ((y - 3) << suby) + 3;
+            int l = 0;
+            for (int a = 0; a <= suby; a++)
+                for (int b = 0; b <= subx; b++) l += lut_y[(ly + a) * GW + lx + b];
+            lum[y][x] = (int16_t)fg_round2(l, subx + suby);
+        }
+    }
+    __syncthreads();
+    // row y computes column x at step t = x - 3 + (LAG + 1) * (y - 3): row y - 1 has then finished x + LAG
+    constexpr int SKEW = LAG + 1;
+    const int y = tid;
+    const int n_steps = LAG ? SKEW * (H - 4) + W - 6 : W - 6;
+    for (int t = 0; t < n_steps; t++) {
+        const int x = LAG ? t - SKEW * (y - 3) + 3 : t + 3;
+        if (y >= 3 && y < H && x >= 3 && x < W - 3) {
+            int v[NC ? NC : 1];
+            int c = 0;
+#pragma unroll
+            for (int dy = -LAG; dy <= 0; dy++) {
+#pragma unroll
+                for (int dx = -LAG; dx <= LAG; dx++) {
+                    if (dy == 0 && dx >= 0) continue;
+                    v[c++] = buf[y + dy][x + dx];
+                }
+            }
+            int sum = luma_term ? (int)lum[y][x] * coef[NC] : 0;
+#pragma unroll
+            for (int i = 0; i < NC; i++) sum += coef[i] * v[i];
+            buf[y][x] = (int16_t)iclip(buf[y][x] + fg_round2(sum, ar_shift), grain_min, grain_max);
+        }
+        if (LAG) __syncthreads();
+    }
+    __syncthreads();
     for (int i = tid; i < H * W; i += blockDim.x) {
         const int r = i / W, c = i - r * W;
         lut[r * GW + c] = (typename FgEntry<BD>::type)buf[r][c];
@@ -103,8 +128,9 @@ fg_generate_kernel(typename FgEntry<BD>::type *__restrict__ lut, const typename 
 
 // generate_scaling, src/fg_apply_tmpl.c:41-96.  One CTA of 256 threads; thread x owns 8-bit index x.
 __global__ void __launch_bounds__(256)
-fg_scaling_kernel(uint8_t *__restrict__ scaling, const uint8_t *__restrict__ points /* [num][2] */, int num, int bitdepth) {
+fg_scaling_kernel(uint8_t *__restrict__ scaling, const FgPoints pts /* [num][2] */, int num, int bitdepth) {
     __shared__ uint8_t v8[257];
+    const uint8_t *points = pts.p;
     const int x = threadIdx.x;
     const int shift_x = bitdepth - 8, pad = 1 << shift_x, rnd = pad >> 1;
     if (num == 0) {
@@ -212,18 +238,26 @@ fg_apply_kernel(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int6
 
 // ---- launch helpers shared by the per-call entry points and the frame stage
 template <typename BD>
-static int fg_generate_launch(void *lut, const void *lut_y, const Rb200FilmGrainData &d, int uv, int subx, int suby,
-                              int bdmax, cudaStream_t st) {
+static int fg_generate_launch(void *lut, const void *lut_y, const Rb200FilmGrainData &d, int uv, int n_luts, int lut_pitch_bytes,
+                              int subx, int suby, int bdmax, cudaStream_t st) {
     using E = typename FgEntry<BD>::type;
-    fg_generate_kernel<BD><<<1, 96, 0, st>>>((E *)lut, (const E *)lut_y, d, uv, subx, suby, bdmax);
+    const int pitch = lut_pitch_bytes / (int)sizeof(E);
+    switch (d.ar_coeff_lag) {
+    case 0: fg_generate_kernel<BD, 0><<<n_luts, 96, 0, st>>>((E *)lut, (const E *)lut_y, d, uv, subx, suby, bdmax, pitch); break;
+    case 1: fg_generate_kernel<BD, 1><<<n_luts, 96, 0, st>>>((E *)lut, (const E *)lut_y, d, uv, subx, suby, bdmax, pitch); break;
+    case 2: fg_generate_kernel<BD, 2><<<n_luts, 96, 0, st>>>((E *)lut, (const E *)lut_y, d, uv, subx, suby, bdmax, pitch); break;
+    case 3: fg_generate_kernel<BD, 3><<<n_luts, 96, 0, st>>>((E *)lut, (const E *)lut_y, d, uv, subx, suby, bdmax, pitch); break;
+    default: return set_error(-22, "film grain: ar_coeff_lag > 3");
+    }
     RB_LAUNCH_CHECK();
     return 0;
 }
 
+// uv < 0: the luma LUT.  Otherwise n_luts (1 or 2) chroma LUTs for planes uv, uv + 1 at lut, lut + lut_pitch_bytes.
 int fg_generate(void *lut, const void *lut_y, const Rb200FilmGrainData &d, int uv, int subx, int suby, int bdmax,
-                cudaStream_t st) {
-    return bdmax > 255 ? fg_generate_launch<BD16>(lut, lut_y, d, uv, subx, suby, bdmax, st)
-                       : fg_generate_launch<BD8>(lut, lut_y, d, uv, subx, suby, bdmax, st);
+                cudaStream_t st, int n_luts, int lut_pitch_bytes) {
+    return bdmax > 255 ? fg_generate_launch<BD16>(lut, lut_y, d, uv, n_luts, lut_pitch_bytes, subx, suby, bdmax, st)
+                       : fg_generate_launch<BD8>(lut, lut_y, d, uv, n_luts, lut_pitch_bytes, subx, suby, bdmax, st);
 }
 
 int fg_apply(uint8_t *dst, const uint8_t *src, int64_t stride, const uint8_t *luma, int64_t luma_stride,
@@ -244,8 +278,10 @@ int fg_offsets(uint8_t *off, unsigned seed, int row0, int nrows, int ncols, cuda
     return 0;
 }
 
-int fg_scaling(uint8_t *scaling, const uint8_t *d_points, int num, int bitdepth, cudaStream_t st) {
-    fg_scaling_kernel<<<1, 256, 0, st>>>(scaling, d_points, num, bitdepth);
+int fg_scaling(uint8_t *scaling, const uint8_t points[][2], int num, int bitdepth, cudaStream_t st) {
+    FgPoints pts = {};
+    if (num > 0) memcpy(pts.p, points, (size_t)(num > 14 ? 14 : num) * 2);
+    fg_scaling_kernel<<<1, 256, 0, st>>>(scaling, pts, num, bitdepth);
     RB_LAUNCH_CHECK();
     return 0;
 }
@@ -301,12 +337,9 @@ extern "C" int rb200_generate_scaling(int bitdepth, const uint8_t points[][2], i
         return set_error(-22, "generate_scaling: bad argument");
     const size_t n = (size_t)1 << bitdepth;
     HostCall hc(2 * n + 4096);
-    uint8_t pts[32] = {};
-    if (num) memcpy(pts, points, (size_t)num * 2);
-    const uint8_t *dp = (const uint8_t *)hc.up(pts, 32);
     uint8_t *d = (uint8_t *)hc.dev(n);
     if (hc.err) return hc.err;
-    if (fg_scaling(d, dp, num, bitdepth, hc.stream())) return -5;
+    if (fg_scaling(d, points, num, bitdepth, hc.stream())) return -5;
     void *s = hc.down(d, n);
     if (hc.sync()) return hc.err;
     memcpy(scaling, s, n);

@@ -54,7 +54,8 @@ struct Rb200Frame {
     bool fg_set; int fg_is_id;
     Rb200FilmGrainData fg;
     uint8_t *fg_mem;            // device: 3 grain LUTs, 3 scaling LUTs, points, offsets
-    uint8_t *h_fgpts;           // pinned: 3 x 32 bytes of scaling points
+    cudaStream_t fg_stream;     // LUT / scaling / offset preparation runs beside the reconstruction
+    cudaEvent_t fg_fork, fg_join;
     uint8_t *plane_mem_fg; Rb200Planes planes_fg, display;
     // optional per-stage timing (the analogue of the reference CLI's --frametimes, tools/dav1d.rs:127-150)
     cudaStream_t own_stream;
@@ -160,7 +161,9 @@ extern "C" int rb200_frame_destroy(Rb200Frame *f) {
     for (int i = 0; i < RB200_N_FRAME_MARKS; i++) if (f->ev[i]) cudaEventDestroy(f->ev[i]);
     for (int i = 0; i < 3; i++) if (f->plane_mem[i]) cudaFree(f->plane_mem[i]);
     if (f->fg_mem) cudaFree(f->fg_mem);
-    if (f->h_fgpts) cudaFreeHost(f->h_fgpts);
+    if (f->fg_stream) { cudaStreamSynchronize(f->fg_stream); cudaStreamDestroy(f->fg_stream); }
+    if (f->fg_fork) cudaEventDestroy(f->fg_fork);
+    if (f->fg_join) cudaEventDestroy(f->fg_join);
     if (f->plane_mem_fg) cudaFree(f->plane_mem_fg);
     if (f->h_coef) cudaFreeHost(f->h_coef);
     if (f->d_coef) cudaFree(f->d_coef);
@@ -217,7 +220,9 @@ extern "C" int rb200_frame_set_film_grain(Rb200Frame *f, const Rb200FilmGrainDat
     if (!f->fg_mem) {
         const int rows = (f->hdr.height + 31) >> 5, cols = (f->hdr.width + 31) >> 5;
         RB_CUDA(cudaMalloc((void **)&f->fg_mem, FG_OFF_OFFSETS + (size_t)rows * (cols + 1) + 64));
-        RB_CUDA(cudaMallocHost((void **)&f->h_fgpts, 128));
+        RB_CUDA(cudaStreamCreateWithFlags(&f->fg_stream, cudaStreamNonBlocking));
+        RB_CUDA(cudaEventCreateWithFlags(&f->fg_fork, cudaEventDisableTiming));
+        RB_CUDA(cudaEventCreateWithFlags(&f->fg_join, cudaEventDisableTiming));
         const size_t ysz = (size_t)f->g.stride[0] * f->g.plane_h[0];
         const size_t uvsz = f->g.n_planes > 1 ? (size_t)f->g.stride[1] * f->g.plane_h[1] : 0;
         RB_CUDA(cudaMalloc((void **)&f->plane_mem_fg, ysz + 2 * uvsz + 256));
@@ -237,33 +242,49 @@ extern "C" int rb200_frame_display_planes(Rb200Frame *f, Rb200Planes *out) {
     return 0;
 }
 
-// rav1d_prep_grain + rav1d_apply_grain_row over the whole picture (src/fg_apply.rs:74-284)
-static int film_grain_stage(Rb200Frame *f, cudaStream_t st) {
+// rav1d_prep_grain (src/fg_apply.rs:74-172): grain LUTs, scaling LUTs and block offsets.  None of it
+// depends on the picture, so it is launched on the frame's side stream at submit time and overlaps
+// the reconstruction and the in-loop filters; film_grain_apply joins it.
+static int film_grain_prepare(Rb200Frame *f, cudaStream_t st) {
     const Rb200FilmGrainData &d = f->fg;
     const Rb200FrameGeometry &g = f->g;
     const int w = f->hdr.width, h = f->hdr.height, bpc = f->hdr.bpc;
     uint8_t *lut[3], *sc[3];
     for (int i = 0; i < 3; i++) { lut[i] = f->fg_mem + FG_OFF_LUT + i * FG_LUT_BYTES; sc[i] = f->fg_mem + FG_OFF_SCALING + i * 4096; }
-    uint8_t *d_pts = f->fg_mem + FG_OFF_PTS, *d_off = f->fg_mem + FG_OFF_OFFSETS;
-    memset(f->h_fgpts, 0, 128);
-    memcpy(f->h_fgpts, d.y_points, sizeof(d.y_points));
-    memcpy(f->h_fgpts + 32, d.uv_points[0], sizeof(d.uv_points[0]));
-    memcpy(f->h_fgpts + 64, d.uv_points[1], sizeof(d.uv_points[1]));
-    RB_CUDA(cudaMemcpyAsync(d_pts, f->h_fgpts, 128, cudaMemcpyHostToDevice, st));
+    uint8_t *d_off = f->fg_mem + FG_OFF_OFFSETS;
     const bool chroma = g.n_planes > 1;
     const bool do_uv[2] = { chroma && (d.num_uv_points[0] || d.chroma_scaling_from_luma),
                             chroma && (d.num_uv_points[1] || d.chroma_scaling_from_luma) };
     int r;
     if ((r = fg_generate(lut[0], nullptr, d, -1, 0, 0, f->bdmax, st))) return r;
     f->launches++;
+    if (do_uv[0] || do_uv[1]) {   // both chroma LUTs in one launch (they only depend on the luma LUT)
+        const int first = do_uv[0] ? 0 : 1, n = (int)do_uv[0] + (int)do_uv[1];
+        if ((r = fg_generate(lut[1 + first], lut[0], d, first, g.ss_hor, g.ss_ver, f->bdmax, st, n, FG_LUT_BYTES))) return r;
+        f->launches++;
+    }
+    if (d.num_y_points || d.chroma_scaling_from_luma) { if ((r = fg_scaling(sc[0], d.y_points, d.num_y_points, bpc, st))) return r; f->launches++; }
     for (int pl = 0; pl < 2; pl++)
-        if (do_uv[pl]) { if ((r = fg_generate(lut[1 + pl], lut[0], d, pl, g.ss_hor, g.ss_ver, f->bdmax, st))) return r; f->launches++; }
-    if (d.num_y_points || d.chroma_scaling_from_luma) { if ((r = fg_scaling(sc[0], d_pts, d.num_y_points, bpc, st))) return r; f->launches++; }
-    for (int pl = 0; pl < 2; pl++)
-        if (chroma && d.num_uv_points[pl]) { if ((r = fg_scaling(sc[1 + pl], d_pts + 32 * (1 + pl), d.num_uv_points[pl], bpc, st))) return r; f->launches++; }
+        if (chroma && d.num_uv_points[pl]) { if ((r = fg_scaling(sc[1 + pl], d.uv_points[pl], d.num_uv_points[pl], bpc, st))) return r; f->launches++; }
     const int rows = (h + 31) >> 5, ncols = ((w + 31) >> 5) + 1;
     if ((r = fg_offsets(d_off, d.seed, 0, rows, ncols, st))) return r;
     f->launches++;
+    return 0;
+}
+
+// rav1d_apply_grain_row over the whole picture (src/fg_apply.rs:174-284)
+static int film_grain_apply(Rb200Frame *f, cudaStream_t st) {
+    const Rb200FilmGrainData &d = f->fg;
+    const Rb200FrameGeometry &g = f->g;
+    const int w = f->hdr.width, h = f->hdr.height;
+    uint8_t *lut[3], *sc[3];
+    for (int i = 0; i < 3; i++) { lut[i] = f->fg_mem + FG_OFF_LUT + i * FG_LUT_BYTES; sc[i] = f->fg_mem + FG_OFF_SCALING + i * 4096; }
+    uint8_t *d_off = f->fg_mem + FG_OFF_OFFSETS;
+    const bool chroma = g.n_planes > 1;
+    const bool do_uv[2] = { chroma && (d.num_uv_points[0] || d.chroma_scaling_from_luma),
+                            chroma && (d.num_uv_points[1] || d.chroma_scaling_from_luma) };
+    const int ncols = ((w + 31) >> 5) + 1;
+    int r;
     const Rb200Planes in = f->out;
     f->display = in;
     if (d.num_y_points) {
@@ -593,6 +614,15 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
     for (int i = 0; i < RB200_N_FRAME_MARKS; i++) f->ev_valid[i] = false;
 #define MARK(i) do { if (f->timing) { RB_CUDA(cudaEventRecord(f->ev[i], st)); f->ev_valid[i] = true; } } while (0)
     MARK(0);
+    if (stages & RB200_STAGE_FILM_GRAIN) {
+        if (!f->fg_set) return set_error(-22, "frame_submit: RB200_STAGE_FILM_GRAIN without rb200_frame_set_film_grain");
+        // fork: the previous frame's grain application (on st) still reads the tables prepared here
+        RB_CUDA(cudaEventRecord(f->fg_fork, st));
+        RB_CUDA(cudaStreamWaitEvent(f->fg_stream, f->fg_fork, 0));
+        int r0;
+        if ((r0 = film_grain_prepare(f, f->fg_stream))) return r0;
+        RB_CUDA(cudaEventRecord(f->fg_join, f->fg_stream));
+    }
     const bool do_lf = (stages & RB200_STAGE_DEBLOCK) && (h.lf_level_y[0] || h.lf_level_y[1]);
     const bool do_cdef = (stages & RB200_STAGE_CDEF) != 0;
     int restore_planes = 0;
@@ -709,7 +739,8 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
     f->display = f->out;
     if (stages & RB200_STAGE_FILM_GRAIN) {
         if (!f->fg_set) return set_error(-22, "frame_submit: RB200_STAGE_FILM_GRAIN without rb200_frame_set_film_grain");
-        if ((r = film_grain_stage(f, st))) return r;
+        RB_CUDA(cudaStreamWaitEvent(st, f->fg_join, 0));
+        if ((r = film_grain_apply(f, st))) return r;
     }
     MARK(7);
 #undef MARK

@@ -321,9 +321,13 @@ __device__ __forceinline__ void mc_stage(uint32_t *win, const McRef &ref, const 
 // put, w and h even and <= 16; `win` already staged (mc_stage) and visible to the warp.
 // TW / TH: compile-time tile size (0 = use the run-time w / h) -- the common 16x16 and 8x8 tiles get
 // fully unrolled task loops with constant index arithmetic.
-template <typename BD, int TW, int TH>
+// PREP: the `prep` form (int16, no clip, minus PREP_BIAS; src/mc.rs:277-349,543-606) is left in `tile`
+// (row pitch MC_TILE) instead of pixels going to the picture.
+template <typename BD, int TW, int TH, bool PREP = false>
 __device__ void mc_tile_fast(McFastSmem &sm, const uint32_t *win, const McWin &W, int w_rt, int h_rt, int bw, int bh, int mx,
-                             int my, int filter2d, uint8_t *out, int64_t out_pitch, int bdmax) {
+                             int my, int filter2d, uint8_t *out, int64_t out_pitch, int bdmax, uint16_t *tile = nullptr) {
+    if (!PREP) tile = sm.out;
+    constexpr int pb = PREP ? McBits<BD>::prep_bias : 0;
     const int w = TW ? TW : w_rt, h = TH ? TH : h_rt;
     const int lane = threadIdx.x & 31;
     const int ib = McBits<BD>::ib(bdmax);
@@ -332,7 +336,7 @@ __device__ void mc_tile_fast(McFastSmem &sm, const uint32_t *win, const McWin &W
 
     const int th_ = (0x111222000LL >> (4 * filter2d)) & 3, tv_ = (0x210210210LL >> (4 * filter2d)) & 3;
     const int ncp = w >> 1, cp_shift = 31 - __clz(ncp), w_shift = cp_shift + 1;
-    uint32_t *out32 = (uint32_t *)sm.out;   // row pitch MC_TILE pixels = 8 words
+    uint32_t *out32 = (uint32_t *)tile;   // row pitch MC_TILE pixels = 8 words
 
     const bool bilin = filter2d == RB200_FILTER_2D_BILINEAR;
     const int base = bilin ? 4 : 6;
@@ -340,7 +344,7 @@ __device__ void mc_tile_fast(McFastSmem &sm, const uint32_t *win, const McWin &W
         const McTaps T = bilin ? mc_bilin_taps(mx) : mc_load_taps(bw > 4 ? th_ : 3 + (th_ & 1), mx - 1);
         const int sh1 = base - ib, r1 = (1 << sh1) >> 1;
         const int n_tasks = (nrows2 >> 1) << cp_shift;
-        const int init = fv ? r1 : (1 << (base - 1)) + r1, sh = fv ? sh1 : base;
+        const int init = (fv || PREP) ? r1 : (1 << (base - 1)) + r1, sh = (fv || PREP) ? sh1 : base;
         constexpr int MAX_IT = TW ? ((TH + 8) / 2 * (TW / 2) + 31) / 32 : 3;
 #pragma unroll
         for (int it = 0; it < MAX_IT; it++) {
@@ -362,9 +366,9 @@ __device__ void mc_tile_fast(McFastSmem &sm, const uint32_t *win, const McWin &W
             } else {
 #pragma unroll
                 for (int rr = 0; rr < 2; rr++) {
-                    const unsigned p0 = (unsigned)iclip(a[rr][0] >> sh, 0, bdmax);
-                    const unsigned p1 = (unsigned)iclip(a[rr][1] >> sh, 0, bdmax);
-                    out32[(2 * rp + rr) * (MC_TILE / 2) + cp] = p0 | (p1 << 16);
+                    const unsigned p0 = PREP ? (unsigned)((a[rr][0] >> sh) - pb) : (unsigned)iclip(a[rr][0] >> sh, 0, bdmax);
+                    const unsigned p1 = PREP ? (unsigned)((a[rr][1] >> sh) - pb) : (unsigned)iclip(a[rr][1] >> sh, 0, bdmax);
+                    out32[(2 * rp + rr) * (MC_TILE / 2) + cp] = (p0 & 0xffff) | (p1 << 16);
                 }
             }
         }
@@ -385,13 +389,19 @@ __device__ void mc_tile_fast(McFastSmem &sm, const uint32_t *win, const McWin &W
         for (int t = lane; t < n_tasks; t += 32) {
             const int cp = t & (ncp - 1), r = t >> cp_shift;
             const uint32_t *wv = win + r * MCF_WPW + cp;
-            out32[r * (MC_TILE / 2) + cp] = par == 0 ? wv[0] : __funnelshift_r(wv[0], wv[1], 16);
+            const unsigned v = par == 0 ? wv[0] : __funnelshift_r(wv[0], wv[1], 16);
+            if (PREP) {
+                const unsigned p0 = (unsigned)((int)((v & 0xffff) << ib) - pb), p1 = (unsigned)((int)((v >> 16) << ib) - pb);
+                out32[r * (MC_TILE / 2) + cp] = (p0 & 0xffff) | (p1 << 16);
+            } else {
+                out32[r * (MC_TILE / 2) + cp] = v;
+            }
         }
     }
     __syncwarp();
     if (fv) {
         const McTaps T = bilin ? mc_bilin_taps(my) : mc_load_taps(bh > 4 ? tv_ : 3 + (tv_ & 1), my - 1);
-        const int sh2 = fh ? base + ib : base, r2 = (1 << sh2) >> 1;
+        const int sh2 = PREP ? (fh ? base : base - ib) : (fh ? base + ib : base), r2 = (1 << sh2) >> 1;
         const int n_tasks = (h >> 1) << w_shift;
         constexpr int MAX_IT = TW ? (TH / 2 * TW + 31) / 32 : 4;
 #pragma unroll
@@ -402,11 +412,12 @@ __device__ void mc_tile_fast(McFastSmem &sm, const uint32_t *win, const McWin &W
             const uint32_t *mv = sm.midv + rp * MCF_MPW + c;
             const unsigned v0 = mv[0], v1 = mv[MCF_MPW], v2 = mv[2 * MCF_MPW], v3 = mv[3 * MCF_MPW], v4 = mv[4 * MCF_MPW];
             const int a0 = mc_fir_even(T, v0, v1, v2, v3, r2), a1 = mc_fir_odd(T, v0, v1, v2, v3, v4, r2);
-            sm.out[(2 * rp) * MC_TILE + c] = (uint16_t)iclip(a0 >> sh2, 0, bdmax);
-            sm.out[(2 * rp + 1) * MC_TILE + c] = (uint16_t)iclip(a1 >> sh2, 0, bdmax);
+            tile[(2 * rp) * MC_TILE + c] = PREP ? (uint16_t)((a0 >> sh2) - pb) : (uint16_t)iclip(a0 >> sh2, 0, bdmax);
+            tile[(2 * rp + 1) * MC_TILE + c] = PREP ? (uint16_t)((a1 >> sh2) - pb) : (uint16_t)iclip(a1 >> sh2, 0, bdmax);
         }
         __syncwarp();
     }
+    if (PREP) return;
     // ---- tile -> picture, widest aligned stores the row allows
     if (BD::hbd) {
         const int row_bytes = w * 2;
@@ -520,9 +531,17 @@ mc_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int ss_hor
 // resolution blend mask stays in shared memory for the co-located chroma tiles, which derive
 // their sub-sampled mask exactly as w_mask does (src/mc.rs:812-883).
 struct McCompSmem {
+    McFastSmem fast;
     McSmem slow;
-    int16_t tmp[2][MC_TILE * MC_TILE];
+    __align__(16) int16_t tmp[2][MC_TILE * MC_TILE];
     uint8_t mask[MC_TILE * MC_TILE];
+};
+
+// One prediction of the compound walk: block `idx`, luma tile (tx, ty), plane pl, reference i.
+struct McCompJob {
+    Rb200CompItem it;
+    int idx, tx, ty, pl, i;
+    bool valid;
 };
 
 template <typename BD>
@@ -532,72 +551,122 @@ mc_comp_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int l
     using pixel = typename BD::pixel;
     __shared__ McCompSmem smem[MC_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int idx = blockIdx.x * MC_WARPS + warp;
-    if (idx >= n_items) return;
+    const int n_warps = gridDim.x * MC_WARPS;
     McCompSmem &sm = smem[warp];
-    const Rb200CompItem it = items[idx];
     const int n_planes = layout == RB200_LAYOUT_I400 ? 1 : 3;
     const int ss_hor_c = layout != RB200_LAYOUT_I444, ss_ver_c = layout == RB200_LAYOUT_I420;
     const int ib = McBits<BD>::ib(bdmax), pb = McBits<BD>::prep_bias;
     const int bitdepth = BD::hbd ? bpc_from_max(bdmax) : 8;
     const int mask_sh = bitdepth + ib - 4, mask_rnd = 1 << (mask_sh - 5);
-    const int s1 = it.comp_type == RB200_COMP_AVG ? 0 : it.mask_sign;   // tmp1 = tmp[mask_sign] for masks
-    for (int ty = 0; ty < it.h; ty += MC_TILE) {
-        for (int tx = 0; tx < it.w; tx += MC_TILE) {
-            const int tw = imin(MC_TILE, it.w - tx), th = imin(MC_TILE, it.h - ty);
-            for (int pl = 0; pl < n_planes; pl++) {
-                const int ss_hor = pl ? ss_hor_c : 0, ss_ver = pl ? ss_ver_c : 0;
-                const int pw = tw >> ss_hor, ph = th >> ss_ver;          // tile size in this plane
-                const int px0 = (it.x + tx) >> ss_hor, py0 = (it.y + ty) >> ss_ver;
-#pragma unroll 1
-                for (int i = 0; i < 2; i++) {
-                    const Rb200Planes &rp = refs.p[it.ref[i] & 7];
-                    McRef ref;
-                    ref.base = plane_ptr(rp, pl);
-                    ref.stride = plane_stride(rp, pl);
-                    ref.w = pl ? (ref_w + ss_hor) >> ss_hor : ref_w;
-                    ref.h = pl ? (ref_h + ss_ver) >> ss_ver : ref_h;
-                    const int mvy = it.mv[i][0], mvx = it.mv[i][1];
-                    // src/recon.rs:2047-2055,2100-2101
-                    const int mx = (mvx & (15 >> !ss_hor)) << !ss_hor, my = (mvy & (15 >> !ss_ver)) << !ss_ver;
-                    const int sx = px0 + (mvx >> (3 + ss_hor)), sy = py0 + (mvy >> (3 + ss_ver));
-                    mc_tile<BD, true>(sm.slow, ref, sx, sy, pw, ph, it.w >> ss_hor, it.h >> ss_ver, mx, my, it.filter2d,
-                                      sm.tmp[i], MC_TILE, bdmax);
-                }
-                __syncwarp();
-                uint8_t *dbase = plane_ptr(dst, pl);
-                const int64_t dstride = plane_stride(dst, pl);
-                const int16_t *t1 = sm.tmp[s1], *t2 = sm.tmp[s1 ^ 1];
-                for (int e = lane; e < pw * ph; e += 32) {
-                    const int r = e / pw, c = e - r * pw;
-                    const int a = t1[r * MC_TILE + c], b = t2[r * MC_TILE + c];
-                    int v;
-                    if (it.comp_type == RB200_COMP_AVG) {
-                        v = (a + b + (1 << ib) + pb * 2) >> (ib + 1);
-                    } else if (it.comp_type == RB200_COMP_WEIGHTED_AVG) {
-                        // w_avg(tmp[0], tmp[1], weight): no sign swap
-                        const int a0 = sm.tmp[0][r * MC_TILE + c], b0 = sm.tmp[1][r * MC_TILE + c];
-                        v = (a0 * it.jnt_weight + b0 * (16 - it.jnt_weight) + (8 << ib) + pb * 16) >> (ib + 4);
-                    } else {
-                        int m;
-                        if (pl == 0) {
-                            const int d = a - b;
-                            m = imin(38 + (((d < 0 ? -d : d) + mask_rnd) >> mask_sh), 64);
-                            sm.mask[r * MC_TILE + c] = (uint8_t)m;
-                        } else {
-                            const uint8_t *mp = sm.mask + (r << ss_ver) * MC_TILE + (c << ss_hor);
-                            if (ss_hor && ss_ver) m = (mp[0] + mp[1] + mp[MC_TILE] + mp[MC_TILE + 1] + 2 - it.mask_sign) >> 2;
-                            else if (ss_hor) m = (mp[0] + mp[1] + 1 - it.mask_sign) >> 1;
-                            else m = mp[0];
-                        }
-                        v = (a * m + b * (64 - m) + (32 << ib) + pb * 64) >> (ib + 6);
-                    }
-                    ((pixel *)(dbase + (int64_t)(py0 + r) * dstride))[px0 + c] = (pixel)iclip(v, 0, bdmax);
-                }
-                __syncwarp();
-            }
+
+    // geometry of a job: reference plane, source position and phase (src/recon.rs:2047-2055,2100-2101)
+    struct Geo { McRef ref; int pw, ph, bw, bh, px0, py0, sx, sy, mx, my; bool fast; };
+    auto geo = [&](const McCompJob &j) {
+        Geo g;
+        const int ss_hor = j.pl ? ss_hor_c : 0, ss_ver = j.pl ? ss_ver_c : 0;
+        const Rb200Planes &rp = refs.p[(j.i ? j.it.ref[1] : j.it.ref[0]) & 7];
+        g.ref.base = plane_ptr(rp, j.pl);
+        g.ref.stride = plane_stride(rp, j.pl);
+        g.ref.w = j.pl ? (ref_w + ss_hor) >> ss_hor : ref_w;
+        g.ref.h = j.pl ? (ref_h + ss_ver) >> ss_ver : ref_h;
+        g.pw = imin(MC_TILE, j.it.w - j.tx) >> ss_hor; g.ph = imin(MC_TILE, j.it.h - j.ty) >> ss_ver;
+        g.bw = j.it.w >> ss_hor; g.bh = j.it.h >> ss_ver;
+        g.px0 = (j.it.x + j.tx) >> ss_hor; g.py0 = (j.it.y + j.ty) >> ss_ver;
+        const int mvy = j.i ? j.it.mv[1][0] : j.it.mv[0][0], mvx = j.i ? j.it.mv[1][1] : j.it.mv[0][1];
+        g.mx = (mvx & (15 >> !ss_hor)) << !ss_hor; g.my = (mvy & (15 >> !ss_ver)) << !ss_ver;
+        g.sx = g.px0 + (mvx >> (3 + ss_hor)); g.sy = g.py0 + (mvy >> (3 + ss_ver));
+        g.fast = !((g.pw | g.ph) & 1) && !(g.pw & (g.pw - 1));
+        return g;
+    };
+    auto advance = [&](McCompJob &j) {
+        if (++j.i < 2) return;
+        j.i = 0;
+        if (++j.pl < n_planes) return;
+        j.pl = 0;
+        if ((j.tx += MC_TILE) < j.it.w) return;
+        j.tx = 0;
+        if ((j.ty += MC_TILE) < j.it.h) return;
+        j.ty = 0;
+        j.idx += n_warps;
+        j.valid = j.idx < n_items;
+        if (j.valid) j.it = items[j.idx];
+    };
+    auto stage = [&](const McCompJob &j, uint32_t *win) {
+        const Geo g = geo(j);
+        if (g.fast) mc_stage<BD>(win, g.ref, mc_window(g.ref, g.sx, g.sy, g.pw, g.ph, g.mx, g.my, j.it.filter2d));
+    };
+
+    McCompJob cur;
+    cur.idx = blockIdx.x * MC_WARPS + warp;
+    if (cur.idx >= n_items) return;
+    cur.it = items[cur.idx];
+    cur.tx = cur.ty = cur.pl = cur.i = 0; cur.valid = true;
+    int buf = 0;
+    stage(cur, sm.fast.win[0]);
+    cp_async_commit();
+    while (cur.valid) {
+        McCompJob nxt = cur;
+        advance(nxt);
+        if (nxt.valid) stage(nxt, sm.fast.win[buf ^ 1]);    // streams in during this job's arithmetic
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        const Geo g = geo(cur);
+        const Rb200CompItem &it = cur.it;
+        if (g.fast) {
+            const McWin W = mc_window(g.ref, g.sx, g.sy, g.pw, g.ph, g.mx, g.my, it.filter2d);
+            if (g.pw == 16 && g.ph == 16)
+                mc_tile_fast<BD, 16, 16, true>(sm.fast, sm.fast.win[buf], W, g.pw, g.ph, g.bw, g.bh, g.mx, g.my, it.filter2d, nullptr, 0, bdmax, (uint16_t *)sm.tmp[cur.i]);
+            else if (g.pw == 8 && g.ph == 8)
+                mc_tile_fast<BD, 8, 8, true>(sm.fast, sm.fast.win[buf], W, g.pw, g.ph, g.bw, g.bh, g.mx, g.my, it.filter2d, nullptr, 0, bdmax, (uint16_t *)sm.tmp[cur.i]);
+            else
+                mc_tile_fast<BD, 0, 0, true>(sm.fast, sm.fast.win[buf], W, g.pw, g.ph, g.bw, g.bh, g.mx, g.my, it.filter2d, nullptr, 0, bdmax, (uint16_t *)sm.tmp[cur.i]);
+        } else {
+            mc_tile<BD, true>(sm.slow, g.ref, g.sx, g.sy, g.pw, g.ph, g.bw, g.bh, g.mx, g.my, it.filter2d, sm.tmp[cur.i], MC_TILE, bdmax);
         }
+        if (cur.i == 1) {
+            // ---- both predictions of this plane's tile are in tmp[]: combine into the picture
+            __syncwarp();
+            const int pl = cur.pl, pw = g.pw, ph = g.ph;
+            const int ss_hor = pl ? ss_hor_c : 0, ss_ver = pl ? ss_ver_c : 0;
+            const int s1 = it.comp_type == RB200_COMP_AVG ? 0 : it.mask_sign;   // tmp1 = tmp[mask_sign] for masks
+            uint8_t *dbase = plane_ptr(dst, pl);
+            const int64_t dstride = plane_stride(dst, pl);
+            const int16_t *t1 = sm.tmp[s1], *t2 = sm.tmp[s1 ^ 1];
+            const int pw_shift = 31 - __clz(pw);
+            const bool pow2 = !(pw & (pw - 1));
+            for (int e = lane; e < pw * ph; e += 32) {
+                const int r = pow2 ? e >> pw_shift : e / pw, c = e - r * pw;
+                const int a = t1[r * MC_TILE + c], b = t2[r * MC_TILE + c];
+                int v;
+                if (it.comp_type == RB200_COMP_AVG) {
+                    v = (a + b + (1 << ib) + pb * 2) >> (ib + 1);
+                } else if (it.comp_type == RB200_COMP_WEIGHTED_AVG) {
+                    // w_avg(tmp[0], tmp[1], weight): no sign swap
+                    const int a0 = sm.tmp[0][r * MC_TILE + c], b0 = sm.tmp[1][r * MC_TILE + c];
+                    v = (a0 * it.jnt_weight + b0 * (16 - it.jnt_weight) + (8 << ib) + pb * 16) >> (ib + 4);
+                } else {
+                    int m;
+                    if (pl == 0) {
+                        const int d = a - b;
+                        m = imin(38 + (((d < 0 ? -d : d) + mask_rnd) >> mask_sh), 64);
+                        sm.mask[r * MC_TILE + c] = (uint8_t)m;
+                    } else {
+                        const uint8_t *mp = sm.mask + (r << ss_ver) * MC_TILE + (c << ss_hor);
+                        if (ss_hor && ss_ver) m = (mp[0] + mp[1] + mp[MC_TILE] + mp[MC_TILE + 1] + 2 - it.mask_sign) >> 2;
+                        else if (ss_hor) m = (mp[0] + mp[1] + 1 - it.mask_sign) >> 1;
+                        else m = mp[0];
+                    }
+                    v = (a * m + b * (64 - m) + (32 << ib) + pb * 64) >> (ib + 6);
+                }
+                ((pixel *)(dbase + (int64_t)(g.py0 + r) * dstride))[g.px0 + c] = (pixel)iclip(v, 0, bdmax);
+            }
+            __syncwarp();
+        }
+        cur = nxt;
+        buf ^= 1;
     }
+    cp_async_wait<0>();
 }
 
 int mc_comp_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int layout,
@@ -605,7 +674,7 @@ int mc_comp_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_
     if (n <= 0) return 0;
     McRefSet rs = {};
     for (int i = 0; i < n_refs && i < 8; i++) rs.p[i] = refs[i];
-    const int grid = (n + MC_WARPS - 1) / MC_WARPS;
+    const int grid = imin((n + MC_WARPS - 1) / MC_WARPS, 148 * 4);   // persistent warps walk the list
     if (bdmax > 255) mc_comp_batch_kernel<BD16><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, layout, d_items, n, bdmax);
     else mc_comp_batch_kernel<BD8><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, layout, d_items, n, bdmax);
     RB_LAUNCH_CHECK();

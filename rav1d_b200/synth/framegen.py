@@ -373,6 +373,42 @@ def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1, comp_frac=0.0, w
     return s
 
 
+def random_film_grain(rng, lag=None, luma_points=True, csfl=0, uv_points=(True, True), overlap=None):
+    """Random Dav1dFilmGrainData within the ranges of tests/checkasm/filmgrain.c:156-190."""
+    d = lib.FilmGrainData()
+    d.seed = int(rng.integers(0, 0x10000))
+    d.grain_scale_shift = int(rng.integers(0, 4))
+    d.ar_coeff_shift = int(rng.integers(0, 4)) + 6
+    d.ar_coeff_lag = int(rng.integers(0, 4)) if lag is None else lag
+    n_y = 2 * d.ar_coeff_lag * (d.ar_coeff_lag + 1)
+    for n in range(n_y):
+        d.ar_coeffs_y[n] = int(rng.integers(0, 256)) - 128
+    for uv in range(2):
+        for n in range(n_y + 1):
+            d.ar_coeffs_uv[uv][n] = int(rng.integers(0, 256)) - 128
+
+    def points(arr, num):
+        pad = 0xff // num
+        for n in range(num):
+            arr[n][0] = 0xff * n // num + int(rng.integers(0, pad))
+            arr[n][1] = int(rng.integers(0, 256))
+    if luma_points:
+        d.num_y_points = 2 + int(rng.integers(0, 13))
+        points(d.y_points, d.num_y_points)
+    d.chroma_scaling_from_luma = csfl
+    for uv in range(2):
+        if uv_points[uv] and not csfl:
+            d.num_uv_points[uv] = 2 + int(rng.integers(0, 9))
+            points(d.uv_points[uv], d.num_uv_points[uv])
+        d.uv_mult[uv] = int(rng.integers(0, 256)) - 128
+        d.uv_luma_mult[uv] = int(rng.integers(0, 256)) - 128
+        d.uv_offset[uv] = int(rng.integers(0, 512)) - 256
+    d.clip_to_restricted_range = int(rng.integers(0, 2))
+    d.scaling_shift = int(rng.integers(0, 4)) + 8
+    d.overlap_flag = int(rng.integers(0, 2)) if overlap is None else overlap
+    return d
+
+
 def recon_input_planes(s, rng=None):
     """A plausible pre-filter picture for post-filter-only tests (BASELINE config 4)."""
     rng = rng or np.random.default_rng(7)

@@ -18,39 +18,9 @@ def _entry(bdmax):
     return np.int16 if bdmax > 255 else np.int8
 
 
-def _rand_fg(rb, rng, lag=None, luma_points=True, csfl=0, uv_points=(True, True), overlap=None):
-    d = rb.FilmGrainData()
-    d.seed = int(rng.integers(0, 0x10000))
-    d.grain_scale_shift = int(rng.integers(0, 4))
-    d.ar_coeff_shift = int(rng.integers(0, 4)) + 6
-    d.ar_coeff_lag = int(rng.integers(0, 4)) if lag is None else lag
-    n_y = 2 * d.ar_coeff_lag * (d.ar_coeff_lag + 1)
-    for n in range(n_y):
-        d.ar_coeffs_y[n] = int(rng.integers(0, 256)) - 128
-    for uv in range(2):
-        for n in range(n_y + 1):
-            d.ar_coeffs_uv[uv][n] = int(rng.integers(0, 256)) - 128
-
-    def points(arr, num):
-        pad = 0xff // num
-        for n in range(num):
-            arr[n][0] = 0xff * n // num + int(rng.integers(0, pad))
-            arr[n][1] = int(rng.integers(0, 256))
-    if luma_points:
-        d.num_y_points = 2 + int(rng.integers(0, 13))
-        points(d.y_points, d.num_y_points)
-    d.chroma_scaling_from_luma = csfl
-    for uv in range(2):
-        if uv_points[uv] and not csfl:
-            d.num_uv_points[uv] = 2 + int(rng.integers(0, 9))
-            points(d.uv_points[uv], d.num_uv_points[uv])
-        d.uv_mult[uv] = int(rng.integers(0, 256)) - 128
-        d.uv_luma_mult[uv] = int(rng.integers(0, 256)) - 128
-        d.uv_offset[uv] = int(rng.integers(0, 512)) - 256
-    d.clip_to_restricted_range = int(rng.integers(0, 2))
-    d.scaling_shift = int(rng.integers(0, 4)) + 8
-    d.overlap_flag = int(rng.integers(0, 2)) if overlap is None else overlap
-    return d
+def _rand_fg(rb, rng, **kw):
+    from rav1d_b200.synth import framegen
+    return framegen.random_film_grain(rng, **kw)
 
 
 def test_film_grain_struct_layout(ref):

@@ -55,6 +55,31 @@ def test_compound_blocks(rb, ref, w, h, bpc):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("w,h,bpc", [(256, 192, 8), (320, 256, 10), (256, 192, 12)])
+def test_compound_block_sizes(rb, ref, w, h, bpc):
+    """Compound blocks from 8x8 to 32x32 (the generator only makes 16x16): smaller ones leave part of
+    their cell to the start picture, larger ones overwrite translational neighbours (compound blocks run
+    after the single-reference ones in both the oracle replay and the batch)."""
+    s = framegen.generate(w, h, bpc, seed=w + 7, comp_frac=0.4)
+    rng = np.random.default_rng(w + bpc)
+    it = s.comp_items
+    cells = {(int(x) // 16, int(y) // 16) for x, y in zip(it["x"], it["y"])}
+    grown = set()
+    for k in range(len(it)):
+        cx, cy = int(it["x"][k]) // 16, int(it["y"][k]) // 16
+        big = [(32, 32), (32, 16), (16, 32)][int(rng.integers(0, 3))]
+        need = {(cx + dx, cy + dy) for dx in range(big[0] // 16) for dy in range(big[1] // 16)} - {(cx, cy)}
+        if (rng.random() < 0.5 and not (need & cells) and not (need & grown)
+                and it["x"][k] + big[0] <= (w & ~15) and it["y"][k] + big[1] <= (h & ~15)):
+            it["w"][k], it["h"][k] = big
+            grown |= need
+        elif (cx, cy) not in grown:
+            it["w"][k], it["h"][k] = [(8, 8), (8, 16), (16, 8), (16, 16)][int(rng.integers(0, 4))]
+    assert {(int(a), int(b)) for a, b in zip(it["w"], it["h"])} >= {(8, 8), (32, 32), (16, 32), (32, 16)}
+    _check(ref, s, R)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("w,h,bpc", [(176, 144, 8), (208, 128, 10), (256, 192, 12)])
 def test_warped_blocks(rb, ref, w, h, bpc):
     """Affine-warped blocks next to translational and compound ones, all planes."""
@@ -107,6 +132,35 @@ def test_config3_4k_10bit(rb, ref):
     """BASELINE.json configs[2]: full recon + deblock + CDEF + Wiener/SGR on a 4K 10-bit frame."""
     s = framegen.generate(3840, 2160, 10, seed=3)
     _check(ref, s, R | D | Cd | L)
+
+
+@pytest.mark.gpu
+def test_config5_4k_10bit(rb, ref):
+    """BASELINE.json configs[4] (one GPU's stream): 50 % compound, 5 % warped, 10 % OBMC blocks, all
+    post-filters and film grain on a 4K 10-bit frame."""
+    import ctypes as C
+    import refharness
+    s = framegen.generate(3840, 2160, 10, seed=5, comp_frac=0.5, warp_frac=0.05, obmc_frac=0.1)
+    fg = framegen.random_film_grain(np.random.default_rng(5), lag=3, overlap=1)
+    cur, rf, rf2 = (refharness.RefFrame(ref, s, n) for n in (8, 1, 1))
+    try:
+        rf.set_planes(s.ref); rf2.set_planes(s.ref2)
+        cur.load_filter_meta()
+        cur.recon(rf, n_threads=8, ref_frame2=rf2)
+        cur.filter(D | Cd | L, n_threads=8)
+        exp = framecheck.visible(s, cur.apply_grain(fg, 0))
+    finally:
+        for f in (cur, rf, rf2):
+            f.close()
+    dev = framegen.DeviceFrame(s)
+    try:
+        dev.load_batch(); dev.set_ref_from_host(s.ref); dev.set_ref_slot(1, s.ref2)
+        rb.check(rb.frame_set_film_grain(dev.h, C.byref(fg), 0))
+        dev.submit(R | D | Cd | L | rb.STAGE_FILM_GRAIN); dev.wait()
+        got = framecheck.visible(s, dev.readback())
+    finally:
+        dev.close()
+    framecheck.assert_planes_equal(exp, got, "config 5")
 
 
 @pytest.mark.gpu
