@@ -189,6 +189,9 @@ int rb200_mask(void *dst, ptrdiff_t dst_stride, const int16_t *tmp1, const int16
                const uint8_t *mask, int bitdepth_max);
 int rb200_w_mask(int ss /* 0:444 1:422 2:420 */, void *dst, ptrdiff_t dst_stride, const int16_t *tmp1,
                  const int16_t *tmp2, int w, int h, uint8_t *mask, int sign, int bitdepth_max);
+/* One entry of dav1d_wedge_masks[bs][ss][sign][wedge_idx] (src/wedge.rs:377; C: src/wedge.c:83-243) as the compound
+ * kernel evaluates it; w, h in {8, 16, 32}; mask receives (w >> ss_hor) * (h >> ss_ver) bytes. */
+int rb200_wedge_mask(int w, int h, int ss /* 0:444 1:422 2:420 */, int sign, int wedge_idx, uint8_t *mask);
 int rb200_blend(int dir /* 0:mask 1:v 2:h */, void *dst, ptrdiff_t dst_stride, const void *tmp, int w, int h,
                 const uint8_t *mask, int bitdepth_max);
 int rb200_warp8x8(void *dst, ptrdiff_t dst_stride, const void *src, ptrdiff_t src_stride,
@@ -227,7 +230,7 @@ int rb200_mc_batch(const Rb200Planes *dst, const Rb200Planes *refs, int n_refs, 
  * sub-sampled segmentation mask for chroma).  The two int16 predictions and the mask never leave
  * shared memory.  Motion vectors are the block's own (1/8 luma pel, {y, x} like Av1Block.mv); the
  * kernel derives the per-plane position and phase as recon.rs `mc()` does (:2047-2055). */
-enum { RB200_COMP_AVG = 0, RB200_COMP_WEIGHTED_AVG = 1, RB200_COMP_SEG = 2 };
+enum { RB200_COMP_AVG = 0, RB200_COMP_WEIGHTED_AVG = 1, RB200_COMP_SEG = 2, RB200_COMP_WEDGE = 3 };
 typedef struct Rb200CompItem {
     int16_t x, y;        /* top-left of the block in the luma plane, pixels */
     uint8_t w, h;        /* luma block size, 8..128 */
@@ -237,7 +240,8 @@ typedef struct Rb200CompItem {
     uint8_t comp_type;   /* RB200_COMP_* */
     uint8_t jnt_weight;  /* w_avg weight, f.jnt_weights[ref0][ref1] (src/decode.rs:4354-4386) */
     uint8_t mask_sign;
-    uint8_t pad[12];
+    uint8_t wedge_idx;   /* RB200_COMP_WEDGE: 0..15, block sizes 8..32 (dav1d_wedge_masks, src/wedge.rs:377) */
+    uint8_t pad[11];
 } Rb200CompItem;         /* 32 bytes */
 
 /* Warped (affine) prediction, one record per BLOCK (all planes): recon.rs `warp_affine`

@@ -30,6 +30,7 @@
 #include <string.h>
 
 #include "src/internal.h"
+#include "src/wedge.h"
 #include "src/lf_mask.h"
 #include "src/levels.h"
 #include "src/tables.h"
@@ -385,6 +386,14 @@ static void comp_prep(RefFrame *r, const RefFrame *rfr, int16_t *tmp, int pl, in
     else ((mct_fn8)f->dsp->mc.mct[filter2d])(tmp, ref, ref_stride, bw, bh, mx, my);
 }
 
+static int wedge_bs(int w, int h) {
+    switch (w << 8 | h) {
+    case 32 << 8 | 32: return BS_32x32; case 32 << 8 | 16: return BS_32x16; case 32 << 8 | 8: return BS_32x8;
+    case 16 << 8 | 32: return BS_16x32; case 16 << 8 | 16: return BS_16x16; case 16 << 8 | 8: return BS_16x8;
+    case 8 << 8 | 32: return BS_8x32; case 8 << 8 | 16: return BS_8x16; default: return BS_8x8;
+    }
+}
+
 static void do_comp_chunk(RefFrame *r, int tid, int chunk, void *arg) {
     (void)tid;
     CompArgs *a = arg;
@@ -415,6 +424,13 @@ static void do_comp_chunk(RefFrame *r, int tid, int chunk, void *arg) {
             } else if (it->comp_type == RB200_COMP_WEIGHTED_AVG) {
                 if (r->hbd) ((void (*)(void *, ptrdiff_t, const int16_t *, const int16_t *, int, int, int, int))f->dsp->mc.w_avg)(dst, ds, tmp[0], tmp[1], bw, bh, it->jnt_weight, r->bdmax);
                 else ((void (*)(void *, ptrdiff_t, const int16_t *, const int16_t *, int, int, int))f->dsp->mc.w_avg)(dst, ds, tmp[0], tmp[1], bw, bh, it->jnt_weight);
+            } else if (it->comp_type == RB200_COMP_WEDGE) {
+                /* src/recon_tmpl.c:1874-1881,1913-1919 */
+                const int bs = wedge_bs(it->w, it->h);
+                const uint8_t *mask = pl ? dav1d_wedge_masks[bs][chr_layout_idx][s][it->wedge_idx]
+                                         : dav1d_wedge_masks[bs][0][0][it->wedge_idx];
+                if (r->hbd) ((void (*)(void *, ptrdiff_t, const int16_t *, const int16_t *, int, int, const uint8_t *, int))f->dsp->mc.mask)(dst, ds, tmp[s], tmp[!s], bw, bh, mask, r->bdmax);
+                else ((void (*)(void *, ptrdiff_t, const int16_t *, const int16_t *, int, int, const uint8_t *))f->dsp->mc.mask)(dst, ds, tmp[s], tmp[!s], bw, bh, mask);
             } else if (pl == 0) {
                 if (r->hbd) ((void (*)(void *, ptrdiff_t, const int16_t *, const int16_t *, int, int, uint8_t *, int, int))f->dsp->mc.w_mask[chr_layout_idx])(dst, ds, tmp[s], tmp[!s], bw, bh, seg_mask, s, r->bdmax);
                 else ((void (*)(void *, ptrdiff_t, const int16_t *, const int16_t *, int, int, uint8_t *, int))f->dsp->mc.w_mask[chr_layout_idx])(dst, ds, tmp[s], tmp[!s], bw, bh, seg_mask, s);
@@ -430,6 +446,8 @@ static void do_comp_chunk(RefFrame *r, int tid, int chunk, void *arg) {
 
 void ref_frame_recon_comp(RefFrame *r, RefFrame *const refs[], int n_refs, const Rb200CompItem *items, int n, int n_threads) {
     CompArgs a;
+    static int wedge_ready;
+    if (!wedge_ready) { dav1d_init_wedge_masks(); wedge_ready = 1; }   /* dav1d_open does this once (src/lib.c:59) */
     memset(&a, 0, sizeof(a));
     a.it = items; a.n = n; a.chunk = 64;
     for (int i = 0; i < n_refs && i < 8; i++) a.refs[i] = refs[i];
@@ -527,4 +545,12 @@ void ref_frame_recon_obmc(RefFrame *r, RefFrame *const refs[], int n_refs, const
             dst, f->cur.stride[!!pl], lap, it->w, it->h);
     }
     free(lap); free(emu);
+}
+
+/* dav1d_wedge_masks accessor (tests compare the closed-form device masks through frames; this lets a
+ * CPU test look at the table itself). layout_idx: 0 = 4:4:4 (luma), 1 = 4:2:2, 2 = 4:2:0. */
+const uint8_t *ref_wedge_mask(int w, int h, int layout_idx, int sign, int idx) {
+    static int ready;
+    if (!ready) { dav1d_init_wedge_masks(); ready = 1; }
+    return dav1d_wedge_masks[wedge_bs(w, h)][layout_idx][sign][idx];
 }

@@ -107,11 +107,11 @@ LR_UNIT_DT = _np.dtype([("type", "u1"), ("filter_h", "i1", (3,)), ("filter_v", "
 AV1_RESTORATION_DT = _np.dtype([("lr", LR_UNIT_DT, (3, 4))])
 COMP_ITEM_DT = _np.dtype([("x", "<i2"), ("y", "<i2"), ("w", "u1"), ("h", "u1"), ("ref", "u1", (2,)), ("mv", "<i2", (2, 2)),
                           ("filter2d", "u1"), ("comp_type", "u1"), ("jnt_weight", "u1"), ("mask_sign", "u1"),
-                          ("pad", "u1", (12,))])
+                          ("wedge_idx", "u1"), ("pad", "u1", (11,))])
 WARP_ITEM_DT = _np.dtype([("x", "<i2"), ("y", "<i2"), ("w", "u1"), ("h", "u1"), ("ref", "u1"), ("pad0", "u1"),
                           ("matrix", "<i4", (6,)), ("abcd", "<i2", (4,)), ("pad", "u1", (8,))])
 assert WARP_ITEM_DT.itemsize == 48
-COMP_AVG, COMP_WEIGHTED_AVG, COMP_SEG = 0, 1, 2
+COMP_AVG, COMP_WEIGHTED_AVG, COMP_SEG, COMP_WEDGE = 0, 1, 2, 3
 MC_PUT, MC_OBMC_ABOVE, MC_OBMC_LEFT = 0, 1, 2
 assert MC_ITEM_DT.itemsize == 16 and ITX_ITEM_DT.itemsize == 16 and COMP_ITEM_DT.itemsize == 32
 assert AV1_FILTER_DT.itemsize == 1348 and AV1_RESTORATION_DT.itemsize == 108
@@ -202,6 +202,7 @@ frame_lr_masks = _sig("rb200_frame_lr_masks", _vp, _vp)
 frame_reserve_comp_items = _sig("rb200_frame_reserve_comp_items", _i, _vp, _i)
 frame_comp_items = _sig("rb200_frame_comp_items", _vp, _vp)
 frame_set_comp_count = _sig("rb200_frame_set_comp_count", _i, _vp, _i)
+wedge_mask = _sig("rb200_wedge_mask", _i, _i, _i, _i, _i, _i, _vp)
 frame_reserve_obmc_items = _sig("rb200_frame_reserve_obmc_items", _i, _vp, _i)
 frame_obmc_items = _sig("rb200_frame_obmc_items", _vp, _vp)
 frame_set_obmc_counts = _sig("rb200_frame_set_obmc_counts", _i, _vp, _i, _i)

@@ -160,9 +160,10 @@ def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1, comp_frac=0.0, w
     comp["mv"][:, 0, 0] = mvy[ci]; comp["mv"][:, 0, 1] = mvx[ci]
     comp["mv"][:, 1, 0] = mvy2[ci]; comp["mv"][:, 1, 1] = mvx2[ci]
     comp["filter2d"] = f2d[ci]
-    comp["comp_type"] = rng.integers(0, 3, size=ci.size)
+    comp["comp_type"] = rng.integers(0, 4, size=ci.size)     # avg, w_avg, segmentation mask, wedge
     comp["jnt_weight"] = rng.choice(np.array([3, 5, 7, 9, 11, 13]), size=ci.size)   # dav1d quant_dist_lookup_table values
     comp["mask_sign"] = rng.integers(0, 2, size=ci.size)
+    comp["wedge_idx"] = rng.integers(0, 16, size=ci.size)
     s.comp_items = comp
     if comp_frac > 0:
         s.ref2 = [np.zeros((ah, aw), pdt), np.zeros((ah // 2, aw // 2), pdt), np.zeros((ah // 2, aw // 2), pdt)]

@@ -68,6 +68,7 @@ def load():
         sig("ref_frame_recon_comp", None, vp, vp, i, vp, i, i)
         sig("ref_frame_recon_warp", None, vp, vp, i, vp, i, i)
         sig("ref_frame_recon_obmc", None, vp, vp, i, vp, i)
+        sig("ref_wedge_mask", vp, i, i, i, i, i)
         sig("ref_frame_apply_grain", None, vp, vp, i)
         sig("ref_frame_grain_plane", vp, vp, i)
         sig("ref_fg_gen_y", None, vp, vp, i)

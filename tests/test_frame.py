@@ -47,9 +47,9 @@ def test_all_stages(rb, ref, w, h, bpc):
 @pytest.mark.gpu
 @pytest.mark.parametrize("w,h,bpc", [(176, 144, 8), (200, 120, 10), (264, 200, 12), (640, 360, 10)])
 def test_compound_blocks(rb, ref, w, h, bpc):
-    """Half of the blocks predicted from two references (avg / w_avg / segmentation mask), BASELINE config 5."""
+    """Half of the blocks predicted from two references (avg / w_avg / segmentation mask / wedge), BASELINE config 5."""
     s = framegen.generate(w, h, bpc, seed=w + 1, comp_frac=0.5)
-    assert len(s.comp_items) > 10 and set(s.comp_items["comp_type"]) == {0, 1, 2}
+    assert len(s.comp_items) > 10 and set(s.comp_items["comp_type"]) == {0, 1, 2, 3}
     _check(ref, s, R)
     _check(ref, s, R | D | Cd | L)
 

@@ -310,3 +310,20 @@ def test_mc_dsp_table(rb, ref):
     ref.ref_mc(0, ptr(a), 8, sp, 32, 8, 8, 3, 11, 255)
     fn(b.ctypes.data, 8, sp, 32, 8, 8, 3, 11, 255)
     assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+def test_wedge_masks(rb, ref):
+    """All of dav1d_wedge_masks: 9 block sizes x 3 layouts x 2 signs x 16 wedges, against the table the
+    reference builds at start-up (src/wedge.c:216-243)."""
+    import ctypes as C
+    for w in (8, 16, 32):
+        for h in (8, 16, 32):
+            for ss in range(3):
+                cw, ch = w >> (ss > 0), h >> (ss == 2)
+                for sign in range(2):
+                    for idx in range(16):
+                        exp = np.ctypeslib.as_array(C.cast(ref.ref_wedge_mask(w, h, ss, sign, idx), C.POINTER(C.c_uint8)), shape=(ch, cw))
+                        got = np.zeros((ch, cw), np.uint8)
+                        rb.check(rb.wedge_mask(w, h, ss, sign, idx, got.ctypes.data))
+                        assert np.array_equal(exp, got), (w, h, ss, sign, idx)
