@@ -320,7 +320,7 @@ def run_gpu(args, s, wl):
     def e2e_frame(i):
         d = ctxs[i % N_CTX]
         d.wait()                             # the context's previous frame (incl. its readback) is done;
-        submit(d, 2 if args.zero_copy else 1)   # the front end would refill the pinned staging here
+        submit(d, {"gather": 3, "zerocopy": 2, "copy": 1}[args.coefs])   # the front end would refill the pinned staging here
         lib.check(lib.frame_readback_async(d.h, host_out[i % N_CTX][0], host_out[i % N_CTX][1]))
 
     for i in range(args.warmup * FRAMES_PER_STEP):
@@ -346,7 +346,7 @@ def run_gpu(args, s, wl):
     h2d = 0
     if stages & 1:
         cs = 4 if bpc > 8 else 2
-        if args.zero_copy:   # only the leading ncols columns of every block cross PCIe
+        if args.coefs != "copy":   # only the leading ncols columns of every block cross PCIe
             from rav1d_b200.lib import TX_DIMS
             sh = np.array([min(TX_DIMS[t][1], 32) for t in range(19)])[s.itx_items["tx"]]
             h2d += int((s.itx_items["ncols"].astype(np.int64) * sh).sum()) * cs
@@ -391,7 +391,8 @@ def run_gpu(args, s, wl):
                 "stages": per_stage, "roofline": roofline, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d * FRAMES_PER_STEP,
                         "d2h_bytes_per_step": d2h * FRAMES_PER_STEP,
-                        "coefficients": "zero-copy from pinned host memory, column-bounded" if args.zero_copy else "H2D copy"},
+                        "coefficients": {"gather": "gather kernel over pinned host memory, column-bounded", "copy": "H2D copy",
+                                         "zerocopy": "transforms read pinned host memory, column-bounded"}[args.coefs]},
                 "gpu_launches": launches}
     for d in ctxs:
         d.close()
@@ -431,8 +432,9 @@ def main():
     ap.add_argument("--workload", default="4k10", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--streams", type=int, default=N_CTX, help="resident leg: 1 = all frames on one stream, >1 = one stream per frame context")
-    ap.add_argument("--copy-coefs", dest="zero_copy", action="store_false",
-                    help="e2e leg: H2D-copy the whole coefficient buffer instead of zero-copy reads from pinned memory")
+    ap.add_argument("--coefs", default="gather", choices=["gather", "zerocopy", "copy"],
+                    help="e2e leg, how coefficients cross PCIe: a gather kernel pulls each block's non-zero columns into "
+                         "HBM (default); the transforms read pinned memory directly; or the whole buffer is H2D-copied")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", 0))

@@ -455,6 +455,24 @@ int rb200_frame_set_comp_count(Rb200Frame *f, int n_comp_items);
 int rb200_frame_reserve_obmc_items(Rb200Frame *f, int max_obmc_items);
 Rb200McItem *rb200_frame_obmc_items(Rb200Frame *f);
 int rb200_frame_set_obmc_counts(Rb200Frame *f, int n_above, int n_left);
+/* Prediction from a reference picture of another size (scaled references: the second branch of recon.rs
+ * `mc()`, src/recon.rs:2116-2199; C: src/recon_tmpl.c:1014-1071 -> mc.mc_scaled[filter2d], src/mc.rs:212-275,
+ * 496-541).  The host does the position arithmetic of that branch (scale_mv) and hands over pos_x / pos_y,
+ * the 1/1024-sample position of the block's first pixel in the reference plane, and the per-pixel steps
+ * f.svc[ref][0 / 1].step; the kernel clamps source coordinates to the reference plane (emu_edge).  The
+ * reference's size is given with rb200_frame_set_ref_size. */
+typedef struct Rb200McScaledItem {
+    int16_t dst_x, dst_y;    /* in plane `plane` of the current picture, pixels */
+    uint8_t w, h, plane, ref;
+    int32_t pos_x, pos_y;
+    int32_t step_x, step_y;
+    uint8_t filter2d;
+    uint8_t pad[7];
+} Rb200McScaledItem;         /* 32 bytes */
+int rb200_frame_set_ref_size(Rb200Frame *f, int slot, int width, int height);   /* luma size of reference `slot` */
+int rb200_frame_reserve_scaled_items(Rb200Frame *f, int max_scaled_items);
+Rb200McScaledItem *rb200_frame_scaled_items(Rb200Frame *f);
+int rb200_frame_set_scaled_count(Rb200Frame *f, int n);
 int rb200_frame_reserve_warp_items(Rb200Frame *f, int max_warp_items);
 Rb200WarpItem *rb200_frame_warp_items(Rb200Frame *f);
 int rb200_frame_set_warp_count(Rb200Frame *f, int n_warp_items);
@@ -478,8 +496,10 @@ int rb200_frame_stage_planes(Rb200Frame *f, int which, Rb200Planes *out);
  * upload: RB200_UPLOAD_NONE (batch already on the device), RB200_UPLOAD_ALL, or
  * RB200_UPLOAD_ZERO_COPY_COEF: everything but the coefficients is copied; the inverse-transform
  * kernels read the coefficients directly from the pinned staging buffer, column-bounded by
- * Rb200ItxItem.ncols, so only the non-zero part of each block crosses PCIe. */
-enum { RB200_UPLOAD_NONE = 0, RB200_UPLOAD_ALL = 1, RB200_UPLOAD_ZERO_COPY_COEF = 2 };
+ * Rb200ItxItem.ncols, so only the non-zero part of each block crosses PCIe;
+ * RB200_UPLOAD_GATHER_COEF: the same bytes cross PCIe, but a gather kernel pulls each block's leading
+ * columns into the device mirror with wide loads first and the transforms read device memory. */
+enum { RB200_UPLOAD_NONE = 0, RB200_UPLOAD_ALL = 1, RB200_UPLOAD_ZERO_COPY_COEF = 2, RB200_UPLOAD_GATHER_COEF = 3 };
 int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t itx_counts[RB200_N_RECT_TX_SIZES],
                        int n_mc_items, int stages, int upload);
 int rb200_frame_wait(Rb200Frame *f);

@@ -554,3 +554,42 @@ const uint8_t *ref_wedge_mask(int w, int h, int layout_idx, int sign, int idx) {
     if (!ready) { dav1d_init_wedge_masks(); ready = 1; }
     return dav1d_wedge_masks[wedge_bs(w, h)][layout_idx][sign][idx];
 }
+
+/* ------------------------------------------------------ scaled references */
+/* The scaled branch of mc() (src/recon_tmpl.c:1014-1071) from the point where pos_x / pos_y are known:
+ * window bounds, emu_edge with the 320-pixel scratch stride, mc_scaled[filter2d]. */
+typedef void (*mcs_fn8)(void *, ptrdiff_t, const void *, ptrdiff_t, int, int, int, int, int, int);
+typedef void (*mcs_fn16)(void *, ptrdiff_t, const void *, ptrdiff_t, int, int, int, int, int, int, int);
+void ref_frame_recon_scaled(RefFrame *r, RefFrame *const refs[], int n_refs, const Rb200McScaledItem *items, int n) {
+    (void)n_refs;
+    Dav1dFrameContext *f = r->f;
+    const int px = r->hbd ? 2 : 1;
+    const int ss_ver_l = f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420, ss_hor_l = f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444;
+    uint8_t *emu = malloc(320 * (256 + 7) * 2);
+    for (int i = 0; i < n; i++) {
+        const Rb200McScaledItem *it = &items[i];
+        const int pl = it->plane, ss_hor = pl && ss_hor_l, ss_ver = pl && ss_ver_l;
+        const Dav1dFrameContext *rf = refs[it->ref]->f;
+        const int left = it->pos_x >> 10, top = it->pos_y >> 10;
+        const int right = ((it->pos_x + (it->w - 1) * it->step_x) >> 10) + 1;
+        const int bottom = ((it->pos_y + (it->h - 1) * it->step_y) >> 10) + 1;
+        const int w = (rf->cur.p.w + ss_hor) >> ss_hor, h = (rf->cur.p.h + ss_ver) >> ss_ver;
+        ptrdiff_t ref_stride = rf->cur.stride[!!pl];
+        const uint8_t *ref;
+        if (left < 3 || top < 3 || right + 4 > w || bottom + 4 > h) {
+            ((void (*)(intptr_t, intptr_t, intptr_t, intptr_t, intptr_t, intptr_t, void *, ptrdiff_t, const void *, ptrdiff_t))
+                 f->dsp->mc.emu_edge)(right - left + 7, bottom - top + 7, w, h, left - 3, top - 3, emu, 320 * px,
+                                      rf->cur.data[pl], ref_stride);
+            ref = emu + (320 * 3 + 3) * px;
+            ref_stride = 320 * px;
+        } else {
+            ref = (const uint8_t *)rf->cur.data[pl] + ref_stride * top + (ptrdiff_t)left * px;
+        }
+        uint8_t *dst = (uint8_t *)f->cur.data[pl] + f->cur.stride[!!pl] * it->dst_y + (ptrdiff_t)it->dst_x * px;
+        if (r->hbd) ((mcs_fn16)f->dsp->mc.mc_scaled[it->filter2d])(dst, f->cur.stride[!!pl], ref, ref_stride, it->w, it->h,
+                                                                  it->pos_x & 0x3ff, it->pos_y & 0x3ff, it->step_x, it->step_y, r->bdmax);
+        else ((mcs_fn8)f->dsp->mc.mc_scaled[it->filter2d])(dst, f->cur.stride[!!pl], ref, ref_stride, it->w, it->h,
+                                                           it->pos_x & 0x3ff, it->pos_y & 0x3ff, it->step_x, it->step_y);
+    }
+    free(emu);
+}

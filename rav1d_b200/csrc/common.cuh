@@ -69,6 +69,7 @@ struct LrFrameParams {
     int sb128, sbh, sr_sb128w;
     int stripe_first, stripe_end;   // band restriction (all stripes: 0, 0)
 };
+int coef_gather_launch(const void *h_cf, void *d_cf, const Rb200ItxItem *d_items, int n, int bdmax, cudaStream_t st);
 int itx_launch(int tx, const Rb200Planes &planes, const void *cf, const Rb200ItxItem *items, int n, int bdmax,
                cudaStream_t st);
 int mc_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int ss_hor,
@@ -77,6 +78,9 @@ int mc_comp_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_
                          const Rb200CompItem *d_items, int n, int bdmax, cudaStream_t st);
 int mc_warp_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int layout,
                          const Rb200WarpItem *d_items, int n, int bdmax, cudaStream_t st);
+struct McRefDims { int w[8], h[8]; };   // luma size of each reference slot
+int mc_scaled_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, const McRefDims &dims, int ss_hor,
+                           int ss_ver, const Rb200McScaledItem *d_items, int n, int bdmax, cudaStream_t st);
 int mc_obmc_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int ss_hor,
                          int ss_ver, const Rb200McItem *d_items, int n, int bdmax, cudaStream_t st);
 int deblock_frame_launch(const Rb200Planes &pl, int n_planes, int w4, int h4, int sb128w, int b4_stride, int ss_hor,

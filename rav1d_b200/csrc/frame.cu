@@ -42,6 +42,8 @@ struct Rb200Frame {
     Rb200CompItem *h_comp, *d_comp; int max_comp, n_comp;
     Rb200WarpItem *h_warp, *d_warp; int max_warp, n_warp;
     Rb200McItem *h_obmc, *d_obmc; int max_obmc, n_obmc_above, n_obmc_left;
+    Rb200McScaledItem *h_scaled, *d_scaled; int max_scaled, n_scaled;
+    rb200::McRefDims ref_dims;
     Rb200Av1Filter *h_masks, *d_masks;
     uint8_t (*h_lvl)[4], (*d_lvl)[4];
     Rb200Av1FilterLUT *h_lut, *d_lut;
@@ -171,6 +173,8 @@ extern "C" int rb200_frame_destroy(Rb200Frame *f) {
     if (f->d_itx) cudaFree(f->d_itx);
     if (f->h_obmc) cudaFreeHost(f->h_obmc);
     if (f->d_obmc) cudaFree(f->d_obmc);
+    if (f->h_scaled) cudaFreeHost(f->h_scaled);
+    if (f->d_scaled) cudaFree(f->d_scaled);
     if (f->h_warp) cudaFreeHost(f->h_warp);
     if (f->d_warp) cudaFree(f->d_warp);
     if (f->h_comp) cudaFreeHost(f->h_comp);
@@ -493,6 +497,30 @@ extern "C" int rb200_frame_set_warp_count(Rb200Frame *f, int n) {
     return 0;
 }
 
+extern "C" int rb200_frame_reserve_scaled_items(Rb200Frame *f, int max_scaled) {
+    if (!f || max_scaled < 0) return set_error(-22, "frame_reserve_scaled_items: bad argument");
+    if (max_scaled <= f->max_scaled) return 0;
+    RB_CUDA(cudaStreamSynchronize(f->stream));
+    if (f->h_scaled) cudaFreeHost(f->h_scaled);
+    if (f->d_scaled) cudaFree(f->d_scaled);
+    f->h_scaled = nullptr; f->d_scaled = nullptr; f->max_scaled = 0; f->n_scaled = 0;
+    const int r = alloc_pair(&f->h_scaled, &f->d_scaled, (size_t)max_scaled);
+    if (r) return r;
+    f->max_scaled = max_scaled;
+    return 0;
+}
+extern "C" Rb200McScaledItem *rb200_frame_scaled_items(Rb200Frame *f) { return f ? f->h_scaled : nullptr; }
+extern "C" int rb200_frame_set_scaled_count(Rb200Frame *f, int n) {
+    if (!f || n < 0 || n > f->max_scaled) return set_error(-22, "frame_set_scaled_count: more items than reserved");
+    f->n_scaled = n;
+    return 0;
+}
+extern "C" int rb200_frame_set_ref_size(Rb200Frame *f, int slot, int width, int height) {
+    if (!f || slot < 0 || slot > 7 || width < 1 || height < 1) return set_error(-22, "frame_set_ref_size: bad argument");
+    f->ref_dims.w[slot] = width; f->ref_dims.h[slot] = height;
+    return 0;
+}
+
 extern "C" int rb200_frame_reserve_obmc_items(Rb200Frame *f, int max_obmc) {
     if (!f || max_obmc < 0) return set_error(-22, "frame_reserve_obmc_items: bad argument");
     if (max_obmc <= f->max_obmc) return 0;
@@ -516,6 +544,7 @@ extern "C" int rb200_frame_set_obmc_counts(Rb200Frame *f, int n_above, int n_lef
 extern "C" int rb200_frame_set_ref(Rb200Frame *f, int slot, const Rb200Planes *planes) {
     if (!f || slot < 0 || slot > 7 || !planes) return set_error(-22, "frame_set_ref: bad argument");
     f->refs[slot] = *planes;
+    f->ref_dims.w[slot] = f->hdr.width; f->ref_dims.h[slot] = f->hdr.height;   // same size unless rb200_frame_set_ref_size says otherwise
     if (slot + 1 > f->n_refs) f->n_refs = slot + 1;
     return 0;
 }
@@ -607,7 +636,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         }
         if (n_coefs > f->max_coefs || n_itx > f->max_itx || n_mc > f->max_mc || n_mc < 0)
             return set_error(-22, "frame_submit: batch larger than the frame was created for");
-        if ((n_mc || f->n_comp || f->n_warp || f->n_obmc_above || f->n_obmc_left) && f->n_refs < 1) return set_error(-22, "frame_submit: no reference picture set");
+        if ((n_mc || f->n_comp || f->n_warp || f->n_scaled || f->n_obmc_above || f->n_obmc_left) && f->n_refs < 1) return set_error(-22, "frame_submit: no reference picture set");
     }
     f->launches = 0;
     const BandRows band = band_rows(f);
@@ -632,14 +661,20 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
     // ---- host -> device: the per-frame batch
     if (upload) {
         if (stages & RB200_STAGE_RECON) {
-            if (n_coefs && upload != RB200_UPLOAD_ZERO_COPY_COEF)
+            if (n_coefs && upload == RB200_UPLOAD_ALL)
                 RB_CUDA(cudaMemcpyAsync(f->d_coef, f->h_coef, n_coefs * f->cs, cudaMemcpyHostToDevice, st));
             if (n_itx) RB_CUDA(cudaMemcpyAsync(f->d_itx, f->h_itx, (size_t)n_itx * sizeof(Rb200ItxItem), cudaMemcpyHostToDevice, st));
             if (n_mc) RB_CUDA(cudaMemcpyAsync(f->d_mc, f->h_mc, (size_t)n_mc * sizeof(Rb200McItem), cudaMemcpyHostToDevice, st));
             if (f->n_comp) RB_CUDA(cudaMemcpyAsync(f->d_comp, f->h_comp, (size_t)f->n_comp * sizeof(Rb200CompItem), cudaMemcpyHostToDevice, st));
             if (f->n_warp) RB_CUDA(cudaMemcpyAsync(f->d_warp, f->h_warp, (size_t)f->n_warp * sizeof(Rb200WarpItem), cudaMemcpyHostToDevice, st));
+            if (f->n_scaled) RB_CUDA(cudaMemcpyAsync(f->d_scaled, f->h_scaled, (size_t)f->n_scaled * sizeof(Rb200McScaledItem), cudaMemcpyHostToDevice, st));
             if (f->n_obmc_above + f->n_obmc_left)
                 RB_CUDA(cudaMemcpyAsync(f->d_obmc, f->h_obmc, (size_t)(f->n_obmc_above + f->n_obmc_left) * sizeof(Rb200McItem), cudaMemcpyHostToDevice, st));
+        }
+        if ((stages & RB200_STAGE_RECON) && upload == RB200_UPLOAD_GATHER_COEF && n_itx) {
+            int rg;   // after the item list: it names the coefficient ranges to pull
+            if ((rg = coef_gather_launch(f->h_coef, f->d_coef, f->d_itx, n_itx, f->bdmax, st))) return rg;
+            f->launches++;
         }
         if (do_lf || do_cdef)
             RB_CUDA(cudaMemcpyAsync(f->d_masks, f->h_masks, f->n_masks * sizeof(Rb200Av1Filter), cudaMemcpyHostToDevice, st));
@@ -663,6 +698,11 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         if (f->n_comp) {
             if ((r = mc_comp_batch_launch(f->planes[0], f->refs, f->n_refs, h.width, h.height, h.layout, f->d_comp, f->n_comp,
                                           f->bdmax, st))) return r;
+            f->launches++;
+        }
+        if (f->n_scaled) {
+            if ((r = mc_scaled_batch_launch(f->planes[0], f->refs, f->n_refs, f->ref_dims, g.ss_hor, g.ss_ver, f->d_scaled,
+                                            f->n_scaled, f->bdmax, st))) return r;
             f->launches++;
         }
         if (f->n_warp) {
@@ -746,4 +786,4 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
 #undef MARK
     return 0;
 }
-static_assert(sizeof(Rb200WarpItem) == 48 && sizeof(Rb200CompItem) == 32 && sizeof(Rb200McItem) == 16 && sizeof(Rb200ItxItem) == 16, "batch record sizes");
+static_assert(sizeof(Rb200WarpItem) == 48 && sizeof(Rb200CompItem) == 32 && sizeof(Rb200McItem) == 16 && sizeof(Rb200ItxItem) == 16 && sizeof(Rb200McScaledItem) == 32, "batch record sizes");

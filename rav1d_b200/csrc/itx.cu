@@ -195,6 +195,40 @@ static int launch_tx(int tx, const Rb200Planes &planes, const void *cf, const Rb
     return set_error(-22, "itx: bad transform size %d", tx);
 }
 
+// The part of each block's coefficients that can be non-zero -- its leading `ncols` columns, a contiguous
+// prefix of the column-major block -- pulled from the pinned staging buffer into the device mirror.  One
+// warp per block, 16 bytes per lane and load: many wide reads in flight keep the PCIe link busy, which the
+// transform kernels' own 32..128-byte row reads would not.
+template <typename coef>
+__global__ void __launch_bounds__(256)
+coef_gather_kernel(const coef *__restrict__ h_cf, coef *__restrict__ d_cf, const Rb200ItxItem *__restrict__ items, int n) {
+    const int idx = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (idx >= n) return;
+    const Rb200ItxItem it = items[idx];
+    const int w = tx_w(it.tx), h = tx_h(it.tx), sw = w < 32 ? w : 32, sh = h < 32 ? h : 32;
+    const int nc = it.ncols && it.ncols < sw ? it.ncols : sw;
+    const int count = nc * sh;
+    const coef *src = h_cf + it.cf_off;
+    coef *dst = d_cf + it.cf_off;
+    constexpr int PER16 = 16 / (int)sizeof(coef);
+    if (!((uintptr_t)src & 15)) {
+        const int n16 = count / PER16;
+        for (int i = lane; i < n16; i += 32) ((uint4 *)dst)[i] = __ldcs((const uint4 *)src + i);
+        for (int i = n16 * PER16 + lane; i < count; i += 32) dst[i] = src[i];
+    } else {
+        for (int i = lane; i < count; i += 32) dst[i] = src[i];
+    }
+}
+
+int coef_gather_launch(const void *h_cf, void *d_cf, const Rb200ItxItem *d_items, int n, int bdmax, cudaStream_t st) {
+    if (n <= 0) return 0;
+    const int grid = (n + 7) / 8;
+    if (bdmax > 255) coef_gather_kernel<int32_t><<<grid, 256, 0, st>>>((const int32_t *)h_cf, (int32_t *)d_cf, d_items, n);
+    else coef_gather_kernel<int16_t><<<grid, 256, 0, st>>>((const int16_t *)h_cf, (int16_t *)d_cf, d_items, n);
+    RB_LAUNCH_CHECK();
+    return 0;
+}
+
 int itx_launch(int tx, const Rb200Planes &planes, const void *cf, const Rb200ItxItem *items, int n, int bdmax,
                cudaStream_t st) {
     return bdmax > 255 ? launch_tx<BD16>(tx, planes, cf, items, n, bdmax, st)

@@ -898,11 +898,9 @@ mc_one_kernel(McRef ref, int ox, int oy, int w, int h, int mx, int my, int filte
 // One thread per output pixel; position (mx + x*dx) is the closed form of the
 // reference's running imx / ioff accumulation.
 template <typename BD, bool PREP>
-__global__ void mc_scaled_kernel(McRef ref, int ox, int oy, int w, int h, int mx, int my, int dx, int dy,
-                                 int filter2d, void *out, int64_t out_pitch, int bdmax) {
+__device__ __forceinline__ int mc_scaled_px(const McRef &ref, int ox, int oy, int w, int h, int mx, int my, int dx, int dy,
+                                            int filter2d, int x, int y, int bdmax) {
     using pixel = typename BD::pixel;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= w || y >= h) return;
     const int ib = McBits<BD>::ib(bdmax);
     const int px = mx + x * dx, py = my + y * dy;
     const int ix = px >> 10, iy = py >> 10, fx = (px & 0x3ff) >> 6, fy = (py & 0x3ff) >> 6;
@@ -949,8 +947,55 @@ __global__ void mc_scaled_kernel(McRef ref, int ox, int oy, int w, int h, int mx
             v = PREP ? m[3] - McBits<BD>::prep_bias : iclip((m[3] + ((1 << ib) >> 1)) >> ib, 0, bdmax);
         }
     }
+    return v;
+}
+
+template <typename BD, bool PREP>
+__global__ void mc_scaled_kernel(McRef ref, int ox, int oy, int w, int h, int mx, int my, int dx, int dy,
+                                 int filter2d, void *out, int64_t out_pitch, int bdmax) {
+    using pixel = typename BD::pixel;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w || y >= h) return;
+    const int v = mc_scaled_px<BD, PREP>(ref, ox, oy, w, h, mx, my, dx, dy, filter2d, x, y, bdmax);
     if (PREP) ((int16_t *)out)[(int64_t)y * out_pitch + x] = (int16_t)v;
     else ((pixel *)((uint8_t *)out + (int64_t)y * out_pitch))[x] = (pixel)v;
+}
+
+// Frame batch of scaled predictions: one CTA per item, a thread per pixel.  (Scaled references are rare
+// -- spatial scalability and reference scaling -- so this path favours simplicity over the IDP pipeline.)
+template <typename BD>
+__global__ void __launch_bounds__(128)
+mc_scaled_batch_kernel(Rb200Planes dst, McRefSet refs, McRefDims dims, int ss_hor_c, int ss_ver_c,
+                       const Rb200McScaledItem *__restrict__ items, int bdmax) {
+    using pixel = typename BD::pixel;
+    const Rb200McScaledItem it = items[blockIdx.x];
+    const int ss_hor = it.plane ? ss_hor_c : 0, ss_ver = it.plane ? ss_ver_c : 0;
+    const Rb200Planes &rp = refs.p[it.ref & 7];
+    McRef ref;
+    ref.base = plane_ptr(rp, it.plane);
+    ref.stride = plane_stride(rp, it.plane);
+    ref.w = (dims.w[it.ref & 7] + ss_hor) >> ss_hor;
+    ref.h = (dims.h[it.ref & 7] + ss_ver) >> ss_ver;
+    uint8_t *dbase = plane_ptr(dst, it.plane);
+    const int64_t dstride = plane_stride(dst, it.plane);
+    // src/recon_tmpl.c:1029-1062: the block starts at (pos >> 10), phase pos & 0x3ff
+    const int ox = it.pos_x >> 10, oy = it.pos_y >> 10, mx = it.pos_x & 0x3ff, my = it.pos_y & 0x3ff;
+    for (int i = threadIdx.x; i < it.w * it.h; i += blockDim.x) {
+        const int y = i / it.w, x = i - y * it.w;
+        const int v = mc_scaled_px<BD, false>(ref, ox, oy, it.w, it.h, mx, my, it.step_x, it.step_y, it.filter2d, x, y, bdmax);
+        ((pixel *)(dbase + (int64_t)(it.dst_y + y) * dstride))[it.dst_x + x] = (pixel)v;
+    }
+}
+
+int mc_scaled_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, const McRefDims &dims, int ss_hor,
+                           int ss_ver, const Rb200McScaledItem *d_items, int n, int bdmax, cudaStream_t st) {
+    if (n <= 0) return 0;
+    McRefSet rs = {};
+    for (int i = 0; i < n_refs && i < 8; i++) rs.p[i] = refs[i];
+    if (bdmax > 255) mc_scaled_batch_kernel<BD16><<<n, 128, 0, st>>>(dst, rs, dims, ss_hor, ss_ver, d_items, bdmax);
+    else mc_scaled_batch_kernel<BD8><<<n, 128, 0, st>>>(dst, rs, dims, ss_hor, ss_ver, d_items, bdmax);
+    RB_LAUNCH_CHECK();
+    return 0;
 }
 
 // ---------------------------------------------------------------- compound

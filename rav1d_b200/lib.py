@@ -108,6 +108,10 @@ AV1_RESTORATION_DT = _np.dtype([("lr", LR_UNIT_DT, (3, 4))])
 COMP_ITEM_DT = _np.dtype([("x", "<i2"), ("y", "<i2"), ("w", "u1"), ("h", "u1"), ("ref", "u1", (2,)), ("mv", "<i2", (2, 2)),
                           ("filter2d", "u1"), ("comp_type", "u1"), ("jnt_weight", "u1"), ("mask_sign", "u1"),
                           ("wedge_idx", "u1"), ("pad", "u1", (11,))])
+SCALED_ITEM_DT = _np.dtype([("dst_x", "<i2"), ("dst_y", "<i2"), ("w", "u1"), ("h", "u1"), ("plane", "u1"), ("ref", "u1"),
+                            ("pos_x", "<i4"), ("pos_y", "<i4"), ("step_x", "<i4"), ("step_y", "<i4"), ("filter2d", "u1"),
+                            ("pad", "u1", (7,))])
+assert SCALED_ITEM_DT.itemsize == 32
 WARP_ITEM_DT = _np.dtype([("x", "<i2"), ("y", "<i2"), ("w", "u1"), ("h", "u1"), ("ref", "u1"), ("pad0", "u1"),
                           ("matrix", "<i4", (6,)), ("abcd", "<i2", (4,)), ("pad", "u1", (8,))])
 assert WARP_ITEM_DT.itemsize == 48
@@ -203,6 +207,10 @@ frame_reserve_comp_items = _sig("rb200_frame_reserve_comp_items", _i, _vp, _i)
 frame_comp_items = _sig("rb200_frame_comp_items", _vp, _vp)
 frame_set_comp_count = _sig("rb200_frame_set_comp_count", _i, _vp, _i)
 wedge_mask = _sig("rb200_wedge_mask", _i, _i, _i, _i, _i, _i, _vp)
+frame_reserve_scaled_items = _sig("rb200_frame_reserve_scaled_items", _i, _vp, _i)
+frame_scaled_items = _sig("rb200_frame_scaled_items", _vp, _vp)
+frame_set_scaled_count = _sig("rb200_frame_set_scaled_count", _i, _vp, _i)
+frame_set_ref_size = _sig("rb200_frame_set_ref_size", _i, _vp, _i, _i, _i)
 frame_reserve_obmc_items = _sig("rb200_frame_reserve_obmc_items", _i, _vp, _i)
 frame_obmc_items = _sig("rb200_frame_obmc_items", _vp, _vp)
 frame_set_obmc_counts = _sig("rb200_frame_set_obmc_counts", _i, _vp, _i, _i)

@@ -93,7 +93,14 @@ def geometry(hd):
     return g
 
 
-def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1, comp_frac=0.0, warp_frac=0.0, obmc_frac=0.0):
+def scale_mv(val, scale):
+    """scale_mv of the reference's mc() (src/recon.rs:2128-2140; C: src/recon_tmpl.c:1018-1021)."""
+    tmp = val.astype(np.int64) * scale + (scale - 0x4000) * 8
+    return (np.sign(tmp) * ((np.abs(tmp) + 128) >> 8) + 32).astype(np.int64)
+
+
+def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1, comp_frac=0.0, warp_frac=0.0, obmc_frac=0.0,
+             scaled_frac=0.0, scaled_size=None):
     """Returns a SynthFrame with numpy arrays; see module docstring."""
     rng = np.random.default_rng(seed)
     bdmax = (1 << bpc) - 1
@@ -208,7 +215,34 @@ def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1, comp_frac=0.0, w
     ab, lf_ = strips(True), strips(False)
     s.obmc_items = np.concatenate([ab, lf_])
     s.n_obmc = (len(ab), len(lf_))
-    keep = np.tile(~(is_comp | is_warp), 3)
+    # Blocks predicted from a reference of another size (slot 2), src/recon.rs:2116-2199
+    is_scaled = np.zeros(nb, bool)
+    if scaled_frac > 0:
+        is_scaled = (np.random.default_rng(seed + 77).random(nb) < scaled_frac) & ~is_comp & ~is_warp & ~is_obmc
+        rw, rh = scaled_size
+        s.scaled_ref_size = (rw, rh)
+        sc = [((rw << 14) + (w >> 1)) // w, ((rh << 14) + (h >> 1)) // h]         # scale_fac, src/decode.rs (svc)
+        st = [(sc[0] + 8) >> 4, (sc[1] + 8) >> 4]
+        si = np.nonzero(is_scaled)[0]
+        out = np.zeros(si.size * 3, lib.SCALED_ITEM_DT)
+        for p in range(3):
+            sh = 0 if p == 0 else 1
+            o = out[p * si.size:(p + 1) * si.size]
+            o["dst_x"] = bx[si] * BLK >> sh; o["dst_y"] = by[si] * BLK >> sh
+            o["w"] = BLK >> sh; o["h"] = BLK >> sh; o["plane"] = p; o["ref"] = 2
+            # orig_pos = (b4 * mul << 4) + mv * (1 << !ss): block position in 1/16 pel of this plane
+            o["pos_x"] = scale_mv(((bx[si] * BLK >> sh) << 4) + mvx[si] * (2 >> sh), sc[0])
+            o["pos_y"] = scale_mv(((by[si] * BLK >> sh) << 4) + mvy[si] * (2 >> sh), sc[1])
+            o["step_x"] = st[0]; o["step_y"] = st[1]
+            o["filter2d"] = f2d[si]
+        s.scaled_items = out
+        raw, rah = (rw + 127) & ~127, (rh + 127) & ~127
+        rrng = np.random.default_rng(seed + 78)
+        s.ref3 = [np.zeros((rah, raw), pdt), np.zeros((rah // 2, raw // 2), pdt), np.zeros((rah // 2, raw // 2), pdt)]
+        s.ref3[0][:rh, :rw] = smooth_plane(rrng, rh, rw, bdmax)
+        for p in (1, 2):
+            s.ref3[p][:(rh + 1) // 2, :(rw + 1) // 2] = smooth_plane(rrng, (rh + 1) // 2, (rw + 1) // 2, bdmax, cell=8)
+    keep = np.tile(~(is_comp | is_warp | is_scaled), 3)
     s.mc_items = np.ascontiguousarray(mc[keep])
 
     # ---- transform blocks: (plane, x, y, tx, txtp)
@@ -470,6 +504,11 @@ class DeviceFrame:
             lib.check(lib.frame_reserve_obmc_items(self.h, len(obmc)), "reserve_obmc_items")
             lib.np_view(lib.frame_obmc_items(self.h), lib.MC_ITEM_DT, len(obmc))[:] = obmc
             lib.check(lib.frame_set_obmc_counts(self.h, *s.n_obmc))
+        scaled = getattr(s, "scaled_items", None)
+        if scaled is not None and len(scaled):
+            lib.check(lib.frame_reserve_scaled_items(self.h, len(scaled)), "reserve_scaled_items")
+            lib.np_view(lib.frame_scaled_items(self.h), lib.SCALED_ITEM_DT, len(scaled))[:] = scaled
+            lib.check(lib.frame_set_scaled_count(self.h, len(scaled)))
         warp = getattr(s, "warp_items", None)
         if warp is not None and len(warp):
             lib.check(lib.frame_reserve_warp_items(self.h, len(warp)), "reserve_warp_items")
@@ -497,11 +536,16 @@ class DeviceFrame:
         lib.check(lib.frame_stage_planes(self.ref_handle, 0, C.byref(pl)))
         lib.check(lib.frame_set_ref(self.h, 0, C.byref(pl)))
 
-    def set_ref_slot(self, slot, planes):
-        """Upload a reference picture into its own device-resident frame object and bind it to `slot`."""
+    def set_ref_slot(self, slot, planes, size=None):
+        """Upload a reference picture into its own device-resident frame object and bind it to `slot`.
+        size = (w, h): a reference of another size than the current picture (scaled prediction)."""
         if slot not in self.ref_handles:
             hnd = C.c_void_p()
-            lib.check(lib.frame_create(C.byref(hnd), C.byref(self.s.hdr), 1, 1, 1), "frame_create(ref)")
+            hdr = self.s.hdr
+            if size is not None:
+                hdr = lib.FrameHeader.from_buffer_copy(bytes(self.s.hdr))
+                hdr.width, hdr.height = size
+            lib.check(lib.frame_create(C.byref(hnd), C.byref(hdr), 1, 1, 1), "frame_create(ref)")
             self.ref_handles[slot] = hnd
         hnd = self.ref_handles[slot]
         data = (C.c_void_p * 3)(*[p.ctypes.data for p in planes])
@@ -510,6 +554,8 @@ class DeviceFrame:
         pl = lib.Planes()
         lib.check(lib.frame_stage_planes(hnd, 0, C.byref(pl)))
         lib.check(lib.frame_set_ref(self.h, slot, C.byref(pl)))
+        if size is not None:
+            lib.check(lib.frame_set_ref_size(self.h, slot, size[0], size[1]))
 
     def submit(self, stages, upload=True):
         """upload: False / 0 = batch already on the device, True / 1 = copy the batch, 2 = copy everything but the

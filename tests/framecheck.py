@@ -11,13 +11,24 @@ def oracle_frame(ref, s, stages, n_tc=1, start_planes=None):
     cur = refharness.RefFrame(ref, s, n_tc)
     rf = refharness.RefFrame(ref, s, 1)
     rf2 = refharness.RefFrame(ref, s, 1) if hasattr(s, "ref2") else None
+    rf3 = None
+    if hasattr(s, "ref3"):      # a reference of another size: its own header
+        import copy
+        s3 = copy.copy(s)
+        s3.hdr = lib.FrameHeader.from_buffer_copy(bytes(s.hdr))
+        s3.hdr.width, s3.hdr.height = s.scaled_ref_size
+        s3.w, s3.h = s.scaled_ref_size
+        s3.aw, s3.ah = (s3.w + 127) & ~127, (s3.h + 127) & ~127
+        rf3 = refharness.RefFrame(ref, s3, 1)
     try:
         rf.set_planes(s.ref)
         if rf2:
             rf2.set_planes(s.ref2)
+        if rf3:
+            rf3.set_planes(s.ref3)
         cur.load_filter_meta()
         if stages & lib.STAGE_RECON:
-            cur.recon(rf, n_threads=n_tc, ref_frame2=rf2)
+            cur.recon(rf, n_threads=n_tc, ref_frame2=rf2, ref_frame3=rf3)
         else:
             cur.set_planes(start_planes)
         if stages & ~lib.STAGE_RECON:
@@ -28,6 +39,8 @@ def oracle_frame(ref, s, stages, n_tc=1, start_planes=None):
         rf.close()
         if rf2:
             rf2.close()
+        if rf3:
+            rf3.close()
 
 
 def product_frame(s, stages, start_planes=None, upload=1):
@@ -40,6 +53,8 @@ def product_frame(s, stages, start_planes=None, upload=1):
             d.set_ref_from_host(s.ref)
             if hasattr(s, "ref2"):
                 d.set_ref_slot(1, s.ref2)
+            if hasattr(s, "ref3"):
+                d.set_ref_slot(2, s.ref3, size=s.scaled_ref_size)
         else:
             d.upload(0, start_planes)
         d.submit(stages, upload)

@@ -69,6 +69,7 @@ def load():
         sig("ref_frame_recon_warp", None, vp, vp, i, vp, i, i)
         sig("ref_frame_recon_obmc", None, vp, vp, i, vp, i)
         sig("ref_wedge_mask", vp, i, i, i, i, i)
+        sig("ref_frame_recon_scaled", None, vp, vp, i, vp, i)
         sig("ref_frame_apply_grain", None, vp, vp, i)
         sig("ref_frame_grain_plane", vp, vp, i)
         sig("ref_fg_gen_y", None, vp, vp, i)
@@ -131,11 +132,13 @@ class RefFrame:
         C.memmove(ref.ref_frame_lut(self.h), C.byref(s.lut), C.sizeof(lib.FilterLUT))
         lib.np_view(ref.ref_frame_lr_masks(self.h), lib.AV1_RESTORATION_DT, n)[:] = s.lr_masks
 
-    def recon(self, ref_frame, n_threads=1, coef_work=None, ref_frame2=None):
+    def recon(self, ref_frame, n_threads=1, coef_work=None, ref_frame2=None, ref_frame3=None):
         """Prediction (put items, then compound blocks) and residual, in the reference's DSP calls."""
         s = self.s
         cw = s.coef.copy() if coef_work is None else coef_work
         frames = [ref_frame] + ([ref_frame2] if ref_frame2 is not None else [])
+        if ref_frame3 is not None:       # slot 2: the scaled reference
+            frames = (frames + [ref_frame])[:2] + [ref_frame3]
         refs = (C.c_void_p * len(frames))(*[f.h for f in frames])
         mc = np.ascontiguousarray(s.mc_items)
         itx = np.ascontiguousarray(s.itx_items)
@@ -145,6 +148,9 @@ class RefFrame:
             self.ref.ref_frame_recon_warp(self.h, refs, len(frames), ptr(warp), len(warp), n_threads)
         obmc = np.ascontiguousarray(getattr(s, "obmc_items", np.zeros(0, np.uint8)))
         self.ref.ref_frame_recon(self.h, refs, len(frames), ptr(mc), len(mc), ptr(itx), 0, ptr(cw), n_threads)
+        scaled = np.ascontiguousarray(getattr(s, "scaled_items", np.zeros(0, np.uint8)))
+        if len(scaled):
+            self.ref.ref_frame_recon_scaled(self.h, refs, len(frames), ptr(scaled), len(scaled))
         if len(comp):
             self.ref.ref_frame_recon_comp(self.h, refs, len(frames), ptr(comp), len(comp), n_threads)
         if len(obmc):

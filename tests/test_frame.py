@@ -90,6 +90,18 @@ def test_warped_blocks(rb, ref, w, h, bpc):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("w,h,bpc,rsize", [(176, 144, 8, (128, 112)), (208, 128, 10, (320, 160)), (256, 192, 12, (200, 300)),
+                                           (320, 192, 10, (640, 96))])
+def test_scaled_reference_blocks(rb, ref, w, h, bpc, rsize):
+    """Blocks predicted from a reference of another size (mc_scaled through the batch), next to
+    translational and compound ones; down- and up-scaling, different ratios per axis."""
+    s = framegen.generate(w, h, bpc, seed=w + 4, comp_frac=0.2, scaled_frac=0.4, scaled_size=rsize)
+    assert len(s.scaled_items) > 30
+    _check(ref, s, R)
+    _check(ref, s, R | D | Cd | L)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("w,h,bpc", [(176, 144, 8), (208, 128, 10), (256, 192, 12)])
 def test_obmc_strips(rb, ref, w, h, bpc):
     """Overlapped block MC on top of translational, compound and warped neighbours (BASELINE config 5)."""
@@ -167,12 +179,15 @@ def test_config5_4k_10bit(rb, ref):
 @pytest.mark.parametrize("w,h,bpc", [(200, 120, 8), (640, 360, 10)])
 def test_zero_copy_coefficients(rb, ref, w, h, bpc):
     """RB200_UPLOAD_ZERO_COPY_COEF: the itx kernels read the pinned coefficient staging directly,
-    bounded by Rb200ItxItem.ncols; and ncols = 0 (unknown) still reads whole blocks."""
+    bounded by Rb200ItxItem.ncols; RB200_UPLOAD_GATHER_COEF: a gather kernel pulls the same columns into
+    the device mirror first; and ncols = 0 (unknown) still reads whole blocks."""
     s = framegen.generate(w, h, bpc, seed=21)
     a = framecheck.oracle_frame(ref, s, R | D)
     framecheck.assert_planes_equal(a, framecheck.product_frame(s, R | D, upload=2), "zero-copy")
+    framecheck.assert_planes_equal(a, framecheck.product_frame(s, R | D, upload=3), "gather")
     s.itx_items["ncols"] = 0
     framecheck.assert_planes_equal(a, framecheck.product_frame(s, R | D, upload=2), "zero-copy, ncols unknown")
+    framecheck.assert_planes_equal(a, framecheck.product_frame(s, R | D, upload=3), "gather, ncols unknown")
     framecheck.assert_planes_equal(a, framecheck.product_frame(s, R | D, upload=1), "copy, ncols unknown")
 
 
