@@ -102,6 +102,67 @@ def test_itxfm_add_all_types_sizes(rb, ref, bdmax):
 
 
 @pytest.mark.gpu
+def test_config1_itx_batch_8bit(rb, ref):
+    """BASELINE.json configs[0] through the batch path: every valid (size, type) pair, N blocks each with the
+    checkasm coefficient recipe (5 variants), laid out in one 4096x4096 8-bit plane whose pixels start random;
+    the whole plane must equal the reference's itxfm_add applied block by block."""
+    from rav1d_b200.lib import TX_DIMS
+    from rav1d_b200.synth.itxgen import gen_coefs, valid_txtps
+    N, W = 384, 4096
+    rng = np.random.default_rng(1)
+    hdr = rb.FrameHeader()
+    hdr.width, hdr.height, hdr.bpc, hdr.layout = W, W, 8, rb.LAYOUT_I400
+    plane = rng.integers(0, 256, size=(W, W)).astype(np.uint8)
+    exp = plane.copy()
+    items, coefs, counts = [], [], np.zeros(19, np.int32)
+    cf_off, cx, cy, band = 0, 0, 0, 0
+    variants = ("dc", "sub", "full", "full", "extreme")
+    for tx in range(19):
+        w, h = TX_DIMS[tx]
+        sw, sh = min(w, 32), min(h, 32)
+        for txtp in valid_txtps(tx):
+            c, eob = gen_coefs(rng, tx, txtp, 255, N, "full")
+            for k, v in enumerate(variants):               # a fifth of the blocks per variant
+                ck, ek = gen_coefs(rng, tx, txtp, 255, N // 5, v)
+                c[k * (N // 5):(k + 1) * (N // 5)] = ck
+                eob[k * (N // 5):(k + 1) * (N // 5)] = ek
+            c = np.clip(c, -32768, 32767).astype(np.int16)
+            it = np.zeros(N, rb.ITX_ITEM_DT)
+            for i in range(N):
+                if cx + w > W:
+                    cx, cy = 0, cy + band
+                    band = 0
+                band = max(band, h)
+                it[i] = (cf_off + i * sw * sh, cx, cy, 0, tx, txtp, 0, eob[i], 0)
+                cx += w
+            assert cy + band <= W
+            items.append(it); coefs.append(c.reshape(-1)); counts[tx] += N
+            cf_off += N * sw * sh
+            cw = c.copy()
+            for i in range(N):
+                ref.ref_itxfm_add(tx, txtp, C.c_void_p(exp.ctypes.data + int(it["y"][i]) * W + int(it["x"][i])), W, ptr(cw[i]), int(eob[i]), 255)
+            assert not cw.any()                              # the reference consumed (zeroed) every block
+    items, coefs = np.concatenate(items), np.concatenate(coefs)
+    assert len(items) == 156 * N
+    f = C.c_void_p()
+    rb.check(rb.frame_create(C.byref(f), C.byref(hdr), len(coefs), len(items), 1))
+    try:
+        rb.np_view(rb.frame_coef_buffer(f), np.int16, len(coefs))[:] = coefs
+        rb.np_view(rb.frame_itx_items(f), rb.ITX_ITEM_DT, len(items))[:] = items
+        data = (C.c_void_p * 3)(plane.ctypes.data, None, None)
+        strides = (C.c_ssize_t * 2)(W, 0)
+        rb.check(rb.frame_upload_planes(f, 0, data, strides))
+        rb.check(rb.frame_submit(f, len(coefs), (C.c_int32 * 19)(*[int(v) for v in counts]), 0, rb.STAGE_RECON, 1))
+        rb.check(rb.frame_wait(f))
+        got = np.zeros_like(plane)
+        data = (C.c_void_p * 3)(got.ctypes.data, None, None)
+        rb.check(rb.frame_readback(f, data, strides))
+    finally:
+        rb.frame_destroy(f)
+    assert np.array_equal(exp, got), np.argwhere(exp != got)[:5]
+
+
+@pytest.mark.gpu
 def test_itx_dsp_table_slots(rb, ref):
     """rb200_itx_dsp_init fills the same slots as the reference's init and each slot works."""
     from rav1d_b200.lib import InvTxfmDSPContext, TX_DIMS
