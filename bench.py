@@ -363,7 +363,7 @@ def run_gpu(args, s, wl):
         ab = algorithmic_bytes(w, h, bpc, GEN_ARGS.get(args.workload, {}).get('comp_frac', 0.0))
         per_stage = {}
         for name, t_ms in zip(STAGE_NAMES, stage_ms):
-            if name == "h2d" or t_ms <= 0:
+            if name == "h2d" or t_ms <= 0 or (name == "film_grain" and not stages & 16):
                 continue
             per_stage[name] = {"ms": round(float(t_ms), 4), "algorithmic_bytes": ab[name],
                                "gbs": round(ab[name] / (t_ms * 1e-3) / 1e9, 1)}

@@ -58,6 +58,8 @@ struct Rb200Frame {
     uint8_t *fg_mem;            // device: 3 grain LUTs, 3 scaling LUTs, points, offsets
     cudaStream_t fg_stream;     // LUT / scaling / offset preparation runs beside the reconstruction
     cudaEvent_t fg_fork, fg_join;
+    cudaStream_t up_stream;     // high priority: the coefficient gather over PCIe (RB200_UPLOAD_GATHER_COEF)
+    cudaEvent_t up_fork, up_join;
     uint8_t *plane_mem_fg; Rb200Planes planes_fg, display;
     // optional per-stage timing (the analogue of the reference CLI's --frametimes, tools/dav1d.rs:127-150)
     cudaStream_t own_stream;
@@ -164,6 +166,9 @@ extern "C" int rb200_frame_destroy(Rb200Frame *f) {
     for (int i = 0; i < 3; i++) if (f->plane_mem[i]) cudaFree(f->plane_mem[i]);
     if (f->fg_mem) cudaFree(f->fg_mem);
     if (f->fg_stream) { cudaStreamSynchronize(f->fg_stream); cudaStreamDestroy(f->fg_stream); }
+    if (f->up_stream) { cudaStreamSynchronize(f->up_stream); cudaStreamDestroy(f->up_stream); }
+    if (f->up_fork) cudaEventDestroy(f->up_fork);
+    if (f->up_join) cudaEventDestroy(f->up_join);
     if (f->fg_fork) cudaEventDestroy(f->fg_fork);
     if (f->fg_join) cudaEventDestroy(f->fg_join);
     if (f->plane_mem_fg) cudaFree(f->plane_mem_fg);
@@ -663,18 +668,34 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         if (stages & RB200_STAGE_RECON) {
             if (n_coefs && upload == RB200_UPLOAD_ALL)
                 RB_CUDA(cudaMemcpyAsync(f->d_coef, f->h_coef, n_coefs * f->cs, cudaMemcpyHostToDevice, st));
-            if (n_itx) RB_CUDA(cudaMemcpyAsync(f->d_itx, f->h_itx, (size_t)n_itx * sizeof(Rb200ItxItem), cudaMemcpyHostToDevice, st));
+            const bool gather = upload == RB200_UPLOAD_GATHER_COEF && n_itx;
+            if (gather) {
+                // The coefficient gather runs on a high-priority side stream: its CTAs are scheduled ahead of the
+                // stage kernels of other frames, so the PCIe link stays busy, and it overlaps this frame's
+                // prediction.  Fork after the previous frame's transforms (they read what is overwritten here).
+                if (!f->up_stream) {
+                    int lo = 0, hi = 0;
+                    RB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                    RB_CUDA(cudaStreamCreateWithPriority(&f->up_stream, cudaStreamNonBlocking, hi));
+                    RB_CUDA(cudaEventCreateWithFlags(&f->up_fork, cudaEventDisableTiming));
+                    RB_CUDA(cudaEventCreateWithFlags(&f->up_join, cudaEventDisableTiming));
+                }
+                RB_CUDA(cudaEventRecord(f->up_fork, st));
+                RB_CUDA(cudaStreamWaitEvent(f->up_stream, f->up_fork, 0));
+                RB_CUDA(cudaMemcpyAsync(f->d_itx, f->h_itx, (size_t)n_itx * sizeof(Rb200ItxItem), cudaMemcpyHostToDevice, f->up_stream));
+                int rg;
+                if ((rg = coef_gather_launch(f->h_coef, f->d_coef, f->d_itx, n_itx, f->bdmax, f->up_stream))) return rg;
+                f->launches++;
+                RB_CUDA(cudaEventRecord(f->up_join, f->up_stream));
+            } else if (n_itx) {
+                RB_CUDA(cudaMemcpyAsync(f->d_itx, f->h_itx, (size_t)n_itx * sizeof(Rb200ItxItem), cudaMemcpyHostToDevice, st));
+            }
             if (n_mc) RB_CUDA(cudaMemcpyAsync(f->d_mc, f->h_mc, (size_t)n_mc * sizeof(Rb200McItem), cudaMemcpyHostToDevice, st));
             if (f->n_comp) RB_CUDA(cudaMemcpyAsync(f->d_comp, f->h_comp, (size_t)f->n_comp * sizeof(Rb200CompItem), cudaMemcpyHostToDevice, st));
             if (f->n_warp) RB_CUDA(cudaMemcpyAsync(f->d_warp, f->h_warp, (size_t)f->n_warp * sizeof(Rb200WarpItem), cudaMemcpyHostToDevice, st));
             if (f->n_scaled) RB_CUDA(cudaMemcpyAsync(f->d_scaled, f->h_scaled, (size_t)f->n_scaled * sizeof(Rb200McScaledItem), cudaMemcpyHostToDevice, st));
             if (f->n_obmc_above + f->n_obmc_left)
                 RB_CUDA(cudaMemcpyAsync(f->d_obmc, f->h_obmc, (size_t)(f->n_obmc_above + f->n_obmc_left) * sizeof(Rb200McItem), cudaMemcpyHostToDevice, st));
-        }
-        if ((stages & RB200_STAGE_RECON) && upload == RB200_UPLOAD_GATHER_COEF && n_itx) {
-            int rg;   // after the item list: it names the coefficient ranges to pull
-            if ((rg = coef_gather_launch(f->h_coef, f->d_coef, f->d_itx, n_itx, f->bdmax, st))) return rg;
-            f->launches++;
         }
         if (do_lf || do_cdef)
             RB_CUDA(cudaMemcpyAsync(f->d_masks, f->h_masks, f->n_masks * sizeof(Rb200Av1Filter), cudaMemcpyHostToDevice, st));
@@ -722,6 +743,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
             f->launches++;
         }
         MARK(2);
+        if (upload == RB200_UPLOAD_GATHER_COEF && n_itx) RB_CUDA(cudaStreamWaitEvent(st, f->up_join, 0));
         int off = 0;
         for (int t = 0; t < RB200_N_RECT_TX_SIZES; t++) {
             if (itx_counts[t]) {

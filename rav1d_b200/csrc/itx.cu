@@ -202,27 +202,51 @@ static int launch_tx(int tx, const Rb200Planes &planes, const void *cf, const Rb
 template <typename coef>
 __global__ void __launch_bounds__(256)
 coef_gather_kernel(const coef *__restrict__ h_cf, coef *__restrict__ d_cf, const Rb200ItxItem *__restrict__ items, int n) {
-    const int idx = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (idx >= n) return;
-    const Rb200ItxItem it = items[idx];
-    const int w = tx_w(it.tx), h = tx_h(it.tx), sw = w < 32 ? w : 32, sh = h < 32 ? h : 32;
-    const int nc = it.ncols && it.ncols < sw ? it.ncols : sw;
-    const int count = nc * sh;
-    const coef *src = h_cf + it.cf_off;
-    coef *dst = d_cf + it.cf_off;
+    const int lane = threadIdx.x & 31;
+    const int n_warps = (int)((gridDim.x * (unsigned)blockDim.x) >> 5);
     constexpr int PER16 = 16 / (int)sizeof(coef);
-    if (!((uintptr_t)src & 15)) {
-        const int n16 = count / PER16;
-        for (int i = lane; i < n16; i += 32) ((uint4 *)dst)[i] = __ldcs((const uint4 *)src + i);
-        for (int i = n16 * PER16 + lane; i < count; i += 32) dst[i] = src[i];
-    } else {
-        for (int i = lane; i < count; i += 32) dst[i] = src[i];
+    // persistent warps; two blocks' loads are issued before either is stored (more PCIe reads in flight)
+    for (int idx = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5); idx < n; idx += 2 * n_warps) {
+        const coef *src[2]; coef *dst[2]; int count[2]; uint4 v[2][2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int i = idx + k * n_warps;
+            count[k] = 0;
+            if (i >= n) continue;
+            const Rb200ItxItem it = items[i];
+            const int w = tx_w(it.tx), h = tx_h(it.tx), sw = w < 32 ? w : 32, sh = h < 32 ? h : 32;
+            const int nc = it.ncols && it.ncols < sw ? it.ncols : sw;
+            count[k] = nc * sh;
+            src[k] = h_cf + it.cf_off; dst[k] = d_cf + it.cf_off;
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            if (!count[k] || ((uintptr_t)src[k] & 15)) continue;
+            const int n16 = count[k] / PER16;
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+                if (lane + 32 * u < n16) v[k][u] = __ldcs((const uint4 *)src[k] + lane + 32 * u);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            if (!count[k]) continue;
+            if ((uintptr_t)src[k] & 15) {
+                for (int i = lane; i < count[k]; i += 32) dst[k][i] = src[k][i];
+                continue;
+            }
+            const int n16 = count[k] / PER16;
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+                if (lane + 32 * u < n16) ((uint4 *)dst[k])[lane + 32 * u] = v[k][u];
+            for (int i = lane + 64; i < n16; i += 32) ((uint4 *)dst[k])[i] = __ldcs((const uint4 *)src[k] + i);   // > 1 KB blocks
+            for (int i = n16 * PER16 + lane; i < count[k]; i += 32) dst[k][i] = src[k][i];
+        }
     }
 }
 
 int coef_gather_launch(const void *h_cf, void *d_cf, const Rb200ItxItem *d_items, int n, int bdmax, cudaStream_t st) {
     if (n <= 0) return 0;
-    const int grid = (n + 7) / 8;
+    const int grid = imin((n + 15) / 16, 148 * 4);
     if (bdmax > 255) coef_gather_kernel<int32_t><<<grid, 256, 0, st>>>((const int32_t *)h_cf, (int32_t *)d_cf, d_items, n);
     else coef_gather_kernel<int16_t><<<grid, 256, 0, st>>>((const int16_t *)h_cf, (int16_t *)d_cf, d_items, n);
     RB_LAUNCH_CHECK();

@@ -447,80 +447,101 @@ struct McRefSet {
     Rb200Planes p[8];
 };
 
+// One work item unpacked into registers together with everything derived from it once: the reference
+// plane and the window of its first tile.  (The 16-byte record is fetched with one 128-bit load.)
+#ifndef MC_BATCH_CTAS
+#define MC_BATCH_CTAS 4      // resident CTAs per SM the batch kernel is compiled for (register budget 128)
+#endif
+struct McJob {
+    int dst_x, dst_y, src_x, src_y, w, h, plane, mx, my, filter2d;
+    McRef ref;
+    McWin W;      // first tile
+    bool fast;
+};
+__device__ __forceinline__ McJob mc_load_job(const Rb200McItem *__restrict__ items, int idx, const McRefSet &refs, int ref_w,
+                                             int ref_h, int ss_hor, int ss_ver) {
+    const uint4 q = __ldg((const uint4 *)(items + idx));
+    McJob j;
+    j.dst_x = (int)(short)(q.x & 0xffff); j.dst_y = (int)q.x >> 16;
+    j.src_x = (int)(short)(q.y & 0xffff); j.src_y = (int)q.y >> 16;
+    j.w = q.z & 0xff; j.h = (q.z >> 8) & 0xff; j.plane = (q.z >> 16) & 0xff;
+    const int slot = (q.z >> 24) & 7;
+    j.mx = q.w & 0xff; j.my = (q.w >> 8) & 0xff; j.filter2d = (q.w >> 16) & 0xff;
+    const Rb200Planes &rp = refs.p[slot];
+    j.ref.base = plane_ptr(rp, j.plane);
+    j.ref.stride = plane_stride(rp, j.plane);
+    j.ref.w = j.plane ? (ref_w + ss_hor) >> ss_hor : ref_w;
+    j.ref.h = j.plane ? (ref_h + ss_ver) >> ss_ver : ref_h;
+    j.fast = !((j.w | j.h) & 1) && (j.w >= MC_TILE || !(j.w & (j.w - 1)));
+    j.W = mc_window(j.ref, j.src_x, j.src_y, imin(MC_TILE, j.w), imin(MC_TILE, j.h), j.mx, j.my, j.filter2d);
+    return j;
+}
+
 // Frame batch: warps walk the item list with a stride of the number of warps in the grid; while a
 // warp filters item i the first window of its item i + 1 is already in flight (cp.async).
 // Items wider/taller than 16 are walked tile by tile.
 template <typename BD>
-__global__ void __launch_bounds__(MC_WARPS * 32, 6)
+__global__ void __launch_bounds__(MC_WARPS * 32, MC_BATCH_CTAS)
 mc_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int ss_hor, int ss_ver,
                 const Rb200McItem *__restrict__ items, int n_items, int bdmax) {
     __shared__ struct { McFastSmem fast; McSmem slow; } smem[MC_WARPS];   // not a union: a prefetch may be in flight
     const int warp = threadIdx.x >> 5;
     const int n_warps = gridDim.x * MC_WARPS;
     McFastSmem &sm = smem[warp].fast;
-    auto ref_of = [&](const Rb200McItem &it) {
-        const Rb200Planes &rp = refs.p[it.ref & 7];
-        McRef ref;
-        ref.base = plane_ptr(rp, it.plane);
-        ref.stride = plane_stride(rp, it.plane);
-        ref.w = it.plane ? (ref_w + ss_hor) >> ss_hor : ref_w;
-        ref.h = it.plane ? (ref_h + ss_ver) >> ss_ver : ref_h;
-        return ref;
-    };
-    auto is_fast = [](const Rb200McItem &it) { return !((it.w | it.h) & 1) && (it.w >= MC_TILE || !(it.w & (it.w - 1))); };
     int idx = blockIdx.x * MC_WARPS + warp;
     if (idx >= n_items) return;
-    Rb200McItem it = items[idx];
+    McJob cur = mc_load_job(items, idx, refs, ref_w, ref_h, ss_hor, ss_ver);
     int buf = 0;
-    if (is_fast(it)) {
-        const McRef ref = ref_of(it);
-        mc_stage<BD>(sm.win[0], ref, mc_window(ref, it.src_x, it.src_y, imin(MC_TILE, it.w), imin(MC_TILE, it.h), it.mx, it.my, it.filter2d));
-    }
+    if (cur.fast) mc_stage<BD>(sm.win[0], cur.ref, cur.W);
     cp_async_commit();
     for (;;) {
         const int nidx = idx + n_warps;
-        Rb200McItem nit;
         const bool have_next = nidx < n_items;
+        McJob nxt = cur;
         if (have_next) {
-            nit = items[nidx];
-            if (is_fast(nit)) {
-                const McRef nref = ref_of(nit);
-                mc_stage<BD>(sm.win[buf ^ 1], nref, mc_window(nref, nit.src_x, nit.src_y, imin(MC_TILE, nit.w), imin(MC_TILE, nit.h), nit.mx, nit.my, nit.filter2d));
-            }
+            nxt = mc_load_job(items, nidx, refs, ref_w, ref_h, ss_hor, ss_ver);
+            if (nxt.fast) mc_stage<BD>(sm.win[buf ^ 1], nxt.ref, nxt.W);
         }
         cp_async_commit();
         cp_async_wait<1>();      // the current item's first window has landed
         __syncwarp();
-        const McRef ref = ref_of(it);
-        uint8_t *dbase = plane_ptr(dst, it.plane);
-        const int64_t dstride = plane_stride(dst, it.plane);
-        const bool fast = is_fast(it);
-        for (int ty = 0; ty < it.h; ty += MC_TILE) {
-            for (int tx = 0; tx < it.w; tx += MC_TILE) {
-                uint8_t *o = dbase + (int64_t)(it.dst_y + ty) * dstride + (int64_t)(it.dst_x + tx) * sizeof(typename BD::pixel);
-                const int tw = imin(MC_TILE, it.w - tx), th = imin(MC_TILE, it.h - ty);
-                if (fast) {
-                    const McWin W = mc_window(ref, it.src_x + tx, it.src_y + ty, tw, th, it.mx, it.my, it.filter2d);
-                    if (tx | ty) {   // further tiles of a large block: staged in place, not prefetched
-                        mc_stage<BD>(sm.win[buf], ref, W);
-                        cp_async_commit();
-                        cp_async_wait<0>();
-                        __syncwarp();
+        uint8_t *dbase = plane_ptr(dst, cur.plane);
+        const int64_t dstride = plane_stride(dst, cur.plane);
+        if (cur.fast && cur.w <= MC_TILE && cur.h <= MC_TILE) {
+            // the common case: the whole block is the prefetched tile
+            uint8_t *o = dbase + (int64_t)cur.dst_y * dstride + (int64_t)cur.dst_x * sizeof(typename BD::pixel);
+            if (cur.w == 16 && cur.h == 16)
+                mc_tile_fast<BD, 16, 16>(sm, sm.win[buf], cur.W, 16, 16, 16, 16, cur.mx, cur.my, cur.filter2d, o, dstride, bdmax);
+            else if (cur.w == 8 && cur.h == 8)
+                mc_tile_fast<BD, 8, 8>(sm, sm.win[buf], cur.W, 8, 8, 8, 8, cur.mx, cur.my, cur.filter2d, o, dstride, bdmax);
+            else
+                mc_tile_fast<BD, 0, 0>(sm, sm.win[buf], cur.W, cur.w, cur.h, cur.w, cur.h, cur.mx, cur.my, cur.filter2d, o, dstride, bdmax);
+        } else {
+            for (int ty = 0; ty < cur.h; ty += MC_TILE) {
+                for (int tx = 0; tx < cur.w; tx += MC_TILE) {
+                    uint8_t *o = dbase + (int64_t)(cur.dst_y + ty) * dstride + (int64_t)(cur.dst_x + tx) * sizeof(typename BD::pixel);
+                    const int tw = imin(MC_TILE, cur.w - tx), th = imin(MC_TILE, cur.h - ty);
+                    if (cur.fast) {
+                        const McWin W = mc_window(cur.ref, cur.src_x + tx, cur.src_y + ty, tw, th, cur.mx, cur.my, cur.filter2d);
+                        if (tx | ty) {   // further tiles of a large block: staged in place, not prefetched
+                            mc_stage<BD>(sm.win[buf], cur.ref, W);
+                            cp_async_commit();
+                            cp_async_wait<0>();
+                            __syncwarp();
+                        }
+                        if (tw == 16 && th == 16)
+                            mc_tile_fast<BD, 16, 16>(sm, sm.win[buf], W, tw, th, cur.w, cur.h, cur.mx, cur.my, cur.filter2d, o, dstride, bdmax);
+                        else
+                            mc_tile_fast<BD, 0, 0>(sm, sm.win[buf], W, tw, th, cur.w, cur.h, cur.mx, cur.my, cur.filter2d, o, dstride, bdmax);
+                    } else {
+                        mc_tile<BD, false>(smem[warp].slow, cur.ref, cur.src_x + tx, cur.src_y + ty, tw, th, cur.w, cur.h, cur.mx, cur.my,
+                                           cur.filter2d, o, dstride, bdmax);
                     }
-                    if (tw == 16 && th == 16)
-                        mc_tile_fast<BD, 16, 16>(sm, sm.win[buf], W, tw, th, it.w, it.h, it.mx, it.my, it.filter2d, o, dstride, bdmax);
-                    else if (tw == 8 && th == 8)
-                        mc_tile_fast<BD, 8, 8>(sm, sm.win[buf], W, tw, th, it.w, it.h, it.mx, it.my, it.filter2d, o, dstride, bdmax);
-                    else
-                        mc_tile_fast<BD, 0, 0>(sm, sm.win[buf], W, tw, th, it.w, it.h, it.mx, it.my, it.filter2d, o, dstride, bdmax);
-                } else {
-                    mc_tile<BD, false>(smem[warp].slow, ref, it.src_x + tx, it.src_y + ty, tw, th, it.w, it.h, it.mx, it.my,
-                                       it.filter2d, o, dstride, bdmax);
                 }
             }
         }
         if (!have_next) break;
-        it = nit; idx = nidx; buf ^= 1;
+        cur = nxt; idx = nidx; buf ^= 1;
     }
     cp_async_wait<0>();
 }
@@ -1146,7 +1167,7 @@ int mc_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs,
         }
     }
     // persistent warps: 148 SMs x 6 resident CTAs, capped by the item count
-    const int grid = imin((n + MC_WARPS - 1) / MC_WARPS, 148 * 6);
+    const int grid = imin((n + MC_WARPS - 1) / MC_WARPS, 148 * MC_BATCH_CTAS);
     if (bdmax > 255)
         mc_batch_kernel<BD16><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, ss_hor, ss_ver, d_items, n, bdmax);
     else
