@@ -31,6 +31,14 @@
 #include <stddef.h>
 #include <stdint.h>
 
+/* Batch records are 16 or 32 bytes and live in 16-byte aligned arrays (the library allocates them); the
+ * attribute only tells compilers so -- it does not change any field offset or size. */
+#if defined(__GNUC__) || defined(__clang__) || defined(__CUDACC__)
+#define RB200_ALIGN16 __attribute__((aligned(16)))
+#else
+#define RB200_ALIGN16
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -108,7 +116,7 @@ typedef struct Rb200ItxItem {
                          all min(w, 32).  Lets the kernel skip the zero tail of the column-major block. */
     int16_t eob;
     int16_t pad;
-} Rb200ItxItem;       /* 16 bytes */
+} RB200_ALIGN16 Rb200ItxItem;       /* 16 bytes */
 /* d_items (device) sorted by tx size; counts[t] = number of items of size t.
  * Coefficients are read, not zeroed: the host zeroes its own staging copy. */
 int rb200_itx_add_batch(const Rb200Planes *planes, const void *d_coef, const Rb200ItxItem *d_items,
@@ -216,7 +224,7 @@ typedef struct Rb200McItem {
     uint8_t mx, my;       /* sub-pel phase 0..15 (already << !ss, src/recon.rs:2100-2101) */
     uint8_t filter2d;     /* RB200_FILTER_2D_* */
     uint8_t flags;        /* RB200_MC_* */
-} Rb200McItem;            /* 16 bytes */
+} RB200_ALIGN16 Rb200McItem;            /* 16 bytes */
 enum { RB200_MC_PUT = 0, RB200_MC_OBMC_ABOVE = 1, RB200_MC_OBMC_LEFT = 2 };
 /* refs[slot]: device planes of reference pictures; ref_w/ref_h: picture size of plane 0 in pixels;
  * ss_hor/ss_ver: chroma subsampling.  dst: device planes of the current picture. */
@@ -242,7 +250,7 @@ typedef struct Rb200CompItem {
     uint8_t mask_sign;
     uint8_t wedge_idx;   /* RB200_COMP_WEDGE: 0..15, block sizes 8..32 (dav1d_wedge_masks, src/wedge.rs:377) */
     uint8_t pad[11];
-} Rb200CompItem;         /* 32 bytes */
+} RB200_ALIGN16 Rb200CompItem;         /* 32 bytes */
 
 /* Warped (affine) prediction, one record per BLOCK (all planes): recon.rs `warp_affine`
  * (src/recon.rs:2311-2400; C: src/recon_tmpl.c:1139-1198) -- per 8x8 the position and phase follow from
@@ -255,7 +263,7 @@ typedef struct Rb200WarpItem {
     int32_t matrix[6];   /* Dav1dWarpedMotionParams.matrix */
     int16_t abcd[4];     /* alpha, beta, gamma, delta */
     uint8_t pad[8];
-} Rb200WarpItem;         /* 48 bytes */
+} RB200_ALIGN16 Rb200WarpItem;         /* 48 bytes */
 
 /* ------------------------------------------------------------ loop filter */
 /* Av1FilterLUT, src/lf_mask.rs:24-28 */
@@ -468,7 +476,7 @@ typedef struct Rb200McScaledItem {
     int32_t step_x, step_y;
     uint8_t filter2d;
     uint8_t pad[7];
-} Rb200McScaledItem;         /* 32 bytes */
+} RB200_ALIGN16 Rb200McScaledItem;         /* 32 bytes */
 int rb200_frame_set_ref_size(Rb200Frame *f, int slot, int width, int height);   /* luma size of reference `slot` */
 int rb200_frame_reserve_scaled_items(Rb200Frame *f, int max_scaled_items);
 Rb200McScaledItem *rb200_frame_scaled_items(Rb200Frame *f);

@@ -14,12 +14,20 @@ namespace rb200 {
 struct BD8 {
     using pixel = uint8_t;
     using coef = int16_t;
+    using pair = uint16_t;      // two horizontally adjacent pixels
     static constexpr bool hbd = false;
+    static __host__ __device__ __forceinline__ int lo(pair q) { return q & 0xff; }
+    static __host__ __device__ __forceinline__ int hi(pair q) { return q >> 8; }
+    static __host__ __device__ __forceinline__ pair pack(int a, int b) { return (pair)(a | (b << 8)); }
 };
 struct BD16 {
     using pixel = uint16_t;
     using coef = int32_t;
+    using pair = uint32_t;
     static constexpr bool hbd = true;
+    static __host__ __device__ __forceinline__ int lo(pair q) { return (int)(q & 0xffff); }
+    static __host__ __device__ __forceinline__ int hi(pair q) { return (int)(q >> 16); }
+    static __host__ __device__ __forceinline__ pair pack(int a, int b) { return (pair)a | ((pair)b << 16); }
 };
 
 __host__ __device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }

@@ -236,6 +236,98 @@ fg_apply_kernel(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int6
     ((pixel *)dst)[(int64_t)y * ps + x] = (pixel)iclip(s + noise, min_value, max_value);
 }
 
+// Two horizontally adjacent pixels per thread, sub-sampling known at compile time (block geometry is
+// shifts, pixels move as 32-bit pairs).  Same arithmetic as fg_apply_kernel; used whenever the planes
+// are aligned for pair accesses (always for the frame stage).
+template <typename BD, int SX, int SY, bool CHROMA>
+__global__ void __launch_bounds__(256)
+fg_apply_pair_kernel(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int64_t stride,
+                     const uint8_t *__restrict__ luma, int64_t luma_stride, FgApplyParams P,
+                     const uint8_t *__restrict__ scaling, const typename FgEntry<BD>::type *__restrict__ lut,
+                     const uint8_t *__restrict__ off, int bdmax) {
+    using pixel = typename BD::pixel;
+    using pair_t = typename BD::pair;            // two pixels in one word
+    constexpr int BWL = 5 - SX, BHL = 5 - SY, BW = 1 << BWL, BH = 1 << BHL;
+    const int x = blockIdx.x * 128 + (threadIdx.x & 63) * 2, y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= P.pw || y >= P.ph) return;
+    const int bdmin8 = BD::hbd ? bpc_from_max(bdmax) - 8 : 0;
+    const int grain_ctr = 128 << bdmin8, grain_min = -grain_ctr, grain_max = grain_ctr - 1;
+    const int bx = x >> BWL, lx0 = x & (BW - 1), byr = y >> BHL, ly = y & (BH - 1);
+    const int row = P.row0 + byr;
+    const int bw = imin(BW, P.pw - (bx << BWL)), bh = imin(BH, P.ph - (byr << BHL));
+    const int ystart = (P.overlap && row) ? imin(2 >> SY, bh) : 0;
+    const int xstart = (P.overlap && bx) ? imin(2 >> SX, bw) : 0;
+    const uint8_t *orow = off + (row - P.off_row0) * P.ncols;
+    const int rv = orow[bx];
+    const int offx = 3 + (2 >> SX) * (3 + (rv >> 4)), offy = 3 + (2 >> SY) * (3 + (rv & 0xF));
+    const typename FgEntry<BD>::type *lp = lut + (offy + ly) * GW + offx + lx0;
+    int grain[2] = { lp[0], lp[1] };
+    if (ly < ystart || lx0 < xstart) {
+        // overlap with the block above and/or to the left (2 rows / columns at full resolution, 1 sub-sampled)
+        auto sample = [&](int lx, int bxi, int byi) -> int {
+            const int r = (byi ? orow - P.ncols : orow)[bx - bxi];
+            const int ox = 3 + (2 >> SX) * (3 + (r >> 4)), oy = 3 + (2 >> SY) * (3 + (r & 0xF));
+            return lut[(oy + ly + BH * byi) * GW + ox + lx + BW * bxi];
+        };
+        auto wgt = [](int sub, int i, int k) -> int { return sub ? (k ? 22 : 23) : ((i ^ k) ? 17 : 27); };
+        auto blend = [&](int old, int cur, int sub, int i) -> int {
+            return iclip(fg_round2(old * wgt(sub, i, 0) + cur * wgt(sub, i, 1), 5), grain_min, grain_max);
+        };
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int lx = lx0 + k;
+            int g = grain[k];
+            if (ly >= ystart) {
+                if (lx < xstart) g = blend(sample(lx, 1, 0), g, SX, lx);
+            } else if (lx >= xstart) {
+                g = blend(sample(lx, 0, 1), g, SY, ly);
+            } else {
+                const int top = blend(sample(lx, 1, 1), sample(lx, 0, 1), SX, lx);
+                g = blend(sample(lx, 1, 0), g, SX, lx);
+                g = blend(top, g, SY, ly);
+            }
+            grain[k] = g;
+        }
+    }
+    const bool two = x + 1 < P.pw;
+    const pixel *srow = (const pixel *)(src + (int64_t)y * stride);
+    pixel *drow = (pixel *)(dst + (int64_t)y * stride);
+    int s[2];
+    if (two) { const pair_t q = *(const pair_t *)(srow + x); s[0] = BD::lo(q); s[1] = BD::hi(q); }
+    else { s[0] = srow[x]; s[1] = 0; }
+    int min_value = 0, max_value = bdmax;
+    if (P.clip) { min_value = 16 << bdmin8; max_value = ((CHROMA && !P.is_id) ? 240 : 235) << bdmin8; }
+    int val[2] = { s[0], s[1] };
+    if (CHROMA) {
+        const pixel *l = (const pixel *)(luma + (int64_t)(y << SY) * luma_stride);
+        int avg[2];
+        if (SX) {
+            const int l0 = x << 1;
+            // four luma samples; the last one of a row is clamped (odd luma widths)
+            const int a = l[l0], b = l[imin(l0 + 1, P.luma_w - 1)], c = l[imin(l0 + 2, P.luma_w - 1)], d = l[imin(l0 + 3, P.luma_w - 1)];
+            avg[0] = (a + b + 1) >> 1; avg[1] = (c + d + 1) >> 1;
+        } else {
+            avg[0] = l[x]; avg[1] = l[imin(x + 1, P.luma_w - 1)];
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            val[k] = avg[k];
+            if (!P.csfl) {
+                const int combined = avg[k] * P.uv_luma_mult + s[k] * P.uv_mult;
+                val[k] = iclip((combined >> 6) + P.uv_offset * (1 << bdmin8), 0, bdmax);
+            }
+        }
+    }
+    int o[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int noise = fg_round2(scaling[val[k]] * grain[k], P.scaling_shift);
+        o[k] = iclip(s[k] + noise, min_value, max_value);
+    }
+    if (two) *(pair_t *)(drow + x) = BD::pack(o[0], o[1]);
+    else drow[x] = (pixel)o[0];
+}
+
 // ---- launch helpers shared by the per-call entry points and the frame stage
 template <typename BD>
 static int fg_generate_launch(void *lut, const void *lut_y, const Rb200FilmGrainData &d, int uv, int n_luts, int lut_pitch_bytes,
@@ -260,14 +352,32 @@ int fg_generate(void *lut, const void *lut_y, const Rb200FilmGrainData &d, int u
                        : fg_generate_launch<BD8>(lut, lut_y, d, uv, n_luts, lut_pitch_bytes, subx, suby, bdmax, st);
 }
 
+template <typename BD>
+static void fg_apply_dispatch(uint8_t *dst, const uint8_t *src, int64_t stride, const uint8_t *luma, int64_t luma_stride,
+                              const FgApplyParams &P, const uint8_t *scaling, const void *lut, const uint8_t *off, int bdmax,
+                              cudaStream_t st) {
+    using E = typename FgEntry<BD>::type;
+    constexpr uintptr_t A = 2 * sizeof(typename BD::pixel) - 1;
+    const bool aligned = !(((uintptr_t)dst | (uintptr_t)src | (uintptr_t)stride) & A);
+    if (!aligned) {
+        dim3 grid((P.pw + 63) / 64, (P.ph + 3) / 4);
+        fg_apply_kernel<BD><<<grid, 256, 0, st>>>(dst, src, stride, luma, luma_stride, P, scaling, (const E *)lut, off, bdmax);
+        return;
+    }
+    dim3 grid((P.pw + 127) / 128, (P.ph + 3) / 4);
+#define L(SX, SY, C) fg_apply_pair_kernel<BD, SX, SY, C><<<grid, 256, 0, st>>>(dst, src, stride, luma, luma_stride, P, scaling, (const E *)lut, off, bdmax)
+    if (!P.chroma) L(0, 0, false);
+    else if (P.sx && P.sy) L(1, 1, true);
+    else if (P.sx) L(1, 0, true);
+    else L(0, 0, true);
+#undef L
+}
+
 int fg_apply(uint8_t *dst, const uint8_t *src, int64_t stride, const uint8_t *luma, int64_t luma_stride,
              const FgApplyParams &P, const uint8_t *scaling, const void *lut, const uint8_t *off, int bdmax,
              cudaStream_t st) {
-    dim3 grid((P.pw + 63) / 64, (P.ph + 3) / 4);
-    if (bdmax > 255)
-        fg_apply_kernel<BD16><<<grid, 256, 0, st>>>(dst, src, stride, luma, luma_stride, P, scaling, (const int16_t *)lut, off, bdmax);
-    else
-        fg_apply_kernel<BD8><<<grid, 256, 0, st>>>(dst, src, stride, luma, luma_stride, P, scaling, (const int8_t *)lut, off, bdmax);
+    if (bdmax > 255) fg_apply_dispatch<BD16>(dst, src, stride, luma, luma_stride, P, scaling, lut, off, bdmax, st);
+    else fg_apply_dispatch<BD8>(dst, src, stride, luma, luma_stride, P, scaling, lut, off, bdmax, st);
     RB_LAUNCH_CHECK();
     return 0;
 }
