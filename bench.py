@@ -363,7 +363,8 @@ def run_gpu(args, s, wl):
         ab = algorithmic_bytes(w, h, bpc, GEN_ARGS.get(args.workload, {}).get('comp_frac', 0.0))
         per_stage = {}
         for name, t_ms in zip(STAGE_NAMES, stage_ms):
-            if name == "h2d" or t_ms <= 0 or (name == "film_grain" and not stages & 16):
+            bit = {"mc": 1, "itx": 1, "deblock": 2, "cdef": 4, "lr": 8, "film_grain": 16}.get(name, 0)
+            if t_ms <= 0 or not stages & bit:
                 continue
             per_stage[name] = {"ms": round(float(t_ms), 4), "algorithmic_bytes": ab[name],
                                "gbs": round(ab[name] / (t_ms * 1e-3) / 1e9, 1)}
