@@ -409,7 +409,9 @@ int rb200_generate_scaling(int bitdepth, const uint8_t points[][2], int num, uin
  * pass 1 already produces, in the reference's own layouts. */
 enum { RB200_LAYOUT_I400, RB200_LAYOUT_I420, RB200_LAYOUT_I422, RB200_LAYOUT_I444 };
 enum { RB200_STAGE_RECON = 1, RB200_STAGE_DEBLOCK = 2, RB200_STAGE_CDEF = 4, RB200_STAGE_LR = 8,
-       RB200_STAGE_FILM_GRAIN = 16 /* needs rb200_frame_set_film_grain */ };
+       RB200_STAGE_FILM_GRAIN = 16 /* needs rb200_frame_set_film_grain */,
+       RB200_STAGE_SUPER_RES = 32  /* frames created with upscaled_width > width: horizontal upscaling between CDEF
+                                      and loop restoration (rav1d_filter_sbrow_resize, src/recon.rs:4215-4281) */ };
 typedef struct Rb200FrameHeader {
     int32_t width, height;       /* picture size in pixels (plane 0) */
     int32_t bpc;                 /* 8, 10 or 12 */
@@ -422,6 +424,9 @@ typedef struct Rb200FrameHeader {
     int32_t cdef_uv_strength[8];
     int32_t lr_type[3];          /* frame_hdr.restoration.type[plane]; NONE = plane not restored */
     int32_t lr_unit_size_log2[2];/* frame_hdr.restoration.unit_size[y, uv] */
+    int32_t upscaled_width;      /* frame_hdr.width[1] when super-resolution is on (> width), else 0: the picture is
+                                    coded `width` wide and upscaled after CDEF; loop restoration units, the output
+                                    picture and rb200_frame_readback then use the upscaled width */
 } Rb200FrameHeader;
 typedef struct Rb200Frame Rb200Frame;
 

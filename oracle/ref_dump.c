@@ -21,7 +21,7 @@
  *
  * tests/test_streams.py replays the dump through the CUDA post-filter path and compares.
  *
- * usage: ref_dump <in.ivf|.obu> <out.bin> [max_frames [max_grain_frames]]
+ * usage: ref_dump <in.ivf|.obu> <out.bin> [max_frames [max_grain_frames [sr_only]]]
  */
 #define _GNU_SOURCE
 #include "config.h"
@@ -38,7 +38,8 @@
 #include "input/input.h"
 
 static FILE *g_out;
-static int g_frames, g_max_frames = 1 << 30;
+static int g_frames, g_max_frames = 1 << 30, g_sr_seen;
+static int g_sr_mode;   /* 1: dump only super-resolution frames (record "RBSR": 8 more header ints, post = sr_cur) */
 static uint8_t *g_pre[3];
 static size_t g_pre_sz[3];
 
@@ -56,8 +57,9 @@ static void hook(Dav1dFrameContext *const f, const int sby, const char *const sy
     const int ss_ver = layout == DAV1D_PIXEL_LAYOUT_I420, ss_hor = layout != DAV1D_PIXEL_LAYOUT_I444;
     const int n_planes = layout == DAV1D_PIXEL_LAYOUT_I400 ? 1 : 3;
     const int ah = (f->cur.p.h + 127) & ~127;
-    const int dump = g_frames < g_max_frames && f->cur.stride[0] > 0 &&
-                     f->frame_hdr->width[0] == f->frame_hdr->width[1];   /* no super-resolution */
+    const int is_sr = f->frame_hdr->width[0] != f->frame_hdr->width[1];
+    const int dump = g_frames < g_max_frames && f->cur.stride[0] > 0 && is_sr == g_sr_mode;
+    if (sby == 0 && f->frame_hdr->width[0] != f->frame_hdr->width[1]) g_sr_seen++;
     if (dump) {
         /* copy the pristine rows of this superblock row (to the end of the allocation on the last one) */
         const int sbsz = f->sb_step * 4;
@@ -77,7 +79,7 @@ static void hook(Dav1dFrameContext *const f, const int sby, const char *const sy
     /* ---- the frame is complete: header, metadata, pre and post pictures */
     const Dav1dFrameHeader *const h = f->frame_hdr;
     const int n_sb128 = f->sb128w * f->sb128h;
-    put_i32(0x52423230);                       /* "RB20" */
+    put_i32(is_sr ? 0x52425352 : 0x52423230);  /* "RBSR" / "RB20" */
     put_i32(g_frames);
     put_i32(f->cur.p.w); put_i32(f->cur.p.h); put_i32(f->cur.p.bpc); put_i32(layout);
     put_i32(f->seq_hdr->sb128);
@@ -94,17 +96,22 @@ static void hook(Dav1dFrameContext *const f, const int sby, const char *const sy
     put_i32((int32_t)f->cur.stride[0]); put_i32((int32_t)f->cur.stride[1]);
     put_i32(ah); put_i32(n_planes);
     put_i32(h->frame_type); put_i32(h->show_frame);
+    if (is_sr) {
+        put_i32(h->width[1]); put_i32((int32_t)f->sr_cur.p.stride[0]); put_i32((int32_t)f->sr_cur.p.stride[1]);
+        put_i32(f->sr_sb128w);
+        put_i32(f->resize_step[0]); put_i32(f->resize_step[1]); put_i32(f->resize_start[0]); put_i32(f->resize_start[1]);
+    }
     fwrite(f->lf.mask, sizeof(Av1Filter), n_sb128, g_out);
     fwrite(f->lf.level, 4, (size_t)f->b4_stride * 32 * f->sb128h, g_out);
     fwrite(&f->lf.lim_lut, sizeof(Av1FilterLUT), 1, g_out);
-    fwrite(f->lf.lr_mask, sizeof(Av1Restoration), n_sb128, g_out);
+    fwrite(f->lf.lr_mask, sizeof(Av1Restoration), (size_t)f->sr_sb128w * f->sb128h, g_out);
     for (int pl = 0; pl < n_planes; pl++) {
         const int rows = pl ? ah >> ss_ver : ah;
         fwrite(g_pre[pl], 1, (size_t)f->cur.stride[!!pl] * rows, g_out);
     }
-    for (int pl = 0; pl < n_planes; pl++) {
+    for (int pl = 0; pl < n_planes; pl++) {   /* the filtered picture: sr_cur is cur itself without super-resolution */
         const int rows = pl ? ah >> ss_ver : ah;
-        fwrite(f->cur.data[pl], 1, (size_t)f->cur.stride[!!pl] * rows, g_out);
+        fwrite(f->sr_cur.p.data[pl], 1, (size_t)f->sr_cur.p.stride[!!pl] * rows, g_out);
     }
     (void)px; (void)ss_hor;
     g_frames++;
@@ -149,6 +156,7 @@ int main(int argc, char **argv) {
     if (argc < 3) { fprintf(stderr, "usage: %s in.ivf out.bin [max_frames]\n", argv[0]); return 2; }
     if (argc > 3) g_max_frames = atoi(argv[3]);
     if (argc > 4) g_max_grain = atoi(argv[4]);      /* film-grain records (decoded with apply_grain = 1) */
+    if (argc > 5) g_sr_mode = atoi(argv[5]) != 0;   /* 1: super-resolution frames only */
     g_out = fopen(argv[2], "wb");
     if (!g_out) { perror(argv[2]); return 2; }
     DemuxerContext *in;
@@ -185,6 +193,6 @@ int main(int argc, char **argv) {
     input_close(in);
     dav1d_close(&c);
     fclose(g_out);
-    fprintf(stderr, "ref_dump: %d frames, %d film-grain records\n", g_frames, g_grain_frames);
+    fprintf(stderr, "ref_dump: %d frames, %d film-grain records, %d super-resolution frames seen\n", g_frames, g_grain_frames, g_sr_seen);
     return g_frames + g_grain_frames > 0 ? 0 : 1;
 }

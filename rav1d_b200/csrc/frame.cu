@@ -44,6 +44,13 @@ struct Rb200Frame {
     Rb200McItem *h_obmc, *d_obmc; int max_obmc, n_obmc_above, n_obmc_left;
     Rb200McScaledItem *h_scaled, *d_scaled; int max_scaled, n_scaled;
     rb200::McRefDims ref_dims;
+    // super-resolution (hdr.upscaled_width > hdr.width): plane sets at the upscaled width --
+    // 0 = upscaled CDEF output, 1 = upscaled deblocked picture (what lr_line_buf holds on the CPU), 2 = LR output
+    bool sr;
+    int sr_w, out_w;                    // upscaled luma width; luma width of `out` / `display`
+    int resize_step[2], resize_start[2];
+    uint8_t *sr_mem[3];
+    Rb200Planes sr_planes[3];
     Rb200Av1Filter *h_masks, *d_masks;
     uint8_t (*h_lvl)[4], (*d_lvl)[4];
     Rb200Av1FilterLUT *h_lut, *d_lut;
@@ -82,6 +89,26 @@ int alloc_planes(Rb200Frame *f, int which) {
     p.data[1] = uvsz ? f->plane_mem[which] + ysz : nullptr;
     p.data[2] = uvsz ? f->plane_mem[which] + ysz + uvsz : nullptr;
     p.stride[1] = p.stride[2] = uvsz ? f->g.stride[1] : 0;
+    return 0;
+}
+
+// src/decode.rs (rav1d_submit_frame) == src/decode.c:3325-3329,3509-3510,3567-3576
+int upscale_x0(int in_w, int out_w, int step) {
+    const int err = out_w * step - (in_w << 14);
+    const int x0 = (-((out_w - in_w) << 13) + (out_w >> 1)) / out_w + 128 - (err / 2);
+    return x0 & 0x3fff;
+}
+int alloc_sr_planes(Rb200Frame *f, int which) {
+    const int aw = (f->sr_w + 127) & ~127;
+    const int64_t sy = (int64_t)aw * (int64_t)f->px, suv = f->g.n_planes > 1 ? (int64_t)(aw >> f->g.ss_hor) * (int64_t)f->px : 0;
+    const size_t ysz = (size_t)sy * f->g.plane_h[0], uvsz = (size_t)suv * f->g.plane_h[1];
+    RB_CUDA(cudaMalloc((void **)&f->sr_mem[which], ysz + 2 * uvsz + 256));
+    RB_CUDA(cudaMemsetAsync(f->sr_mem[which], 0, ysz + 2 * uvsz + 256, f->stream));
+    Rb200Planes &p = f->sr_planes[which];
+    p.data[0] = f->sr_mem[which]; p.stride[0] = sy;
+    p.data[1] = uvsz ? f->sr_mem[which] + ysz : nullptr;
+    p.data[2] = uvsz ? f->sr_mem[which] + ysz + uvsz : nullptr;
+    p.stride[1] = p.stride[2] = suv;
     return 0;
 }
 
@@ -132,13 +159,29 @@ extern "C" int rb200_frame_create(Rb200Frame **out, const Rb200FrameHeader *hdr,
     g.plane_h[0] = ah;
     g.plane_h[1] = g.n_planes > 1 ? ah >> g.ss_ver : 0;
     f->max_coefs = max_coefs; f->max_itx = max_itx; f->max_mc = max_mc;
-    f->n_masks = (size_t)g.sb128w * g.sb128h;
+    f->sr = hdr->upscaled_width > hdr->width;
+    if (hdr->upscaled_width && (hdr->upscaled_width < hdr->width || hdr->upscaled_width > 2 * hdr->width)) {
+        delete f;
+        return set_error(-22, "frame_create: upscaled_width must be in [width, 2 * width]");
+    }
+    f->sr_w = f->sr ? hdr->upscaled_width : hdr->width;
+    f->out_w = hdr->width;
+    if (f->sr) {
+        const int in_cw = (hdr->width + g.ss_hor) >> g.ss_hor, out_cw = (f->sr_w + g.ss_hor) >> g.ss_hor;
+        f->resize_step[0] = ((hdr->width << 14) + (f->sr_w >> 1)) / f->sr_w;
+        f->resize_step[1] = ((in_cw << 14) + (out_cw >> 1)) / out_cw;
+        f->resize_start[0] = upscale_x0(hdr->width, f->sr_w, f->resize_step[0]);
+        f->resize_start[1] = upscale_x0(in_cw, out_cw, f->resize_step[1]);
+    }
+    // loop-restoration units are indexed in upscaled coordinates (f.sr_sb128w)
+    f->n_masks = (size_t)imax(g.sb128w, (f->sr_w + 127) >> 7) * g.sb128h;
     f->n_lvl = (size_t)g.b4_stride * 32 * g.sb128h + 32;  // + guard for the level fallback of row/col 0
     int r = 0;
     cudaError_t e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { r = cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); delete f; return r; }
     f->own_stream = f->stream;
     for (int i = 0; i < 3 && !r; i++) r = alloc_planes(f, i);
+    for (int i = 0; i < 3 && !r && f->sr; i++) r = alloc_sr_planes(f, i);
     if (!r) {
         RB_CUDA(cudaMallocHost(&f->h_coef, (max_coefs ? max_coefs : 1) * f->cs));
         memset(f->h_coef, 0, (max_coefs ? max_coefs : 1) * f->cs);
@@ -176,6 +219,7 @@ extern "C" int rb200_frame_destroy(Rb200Frame *f) {
     if (f->d_coef) cudaFree(f->d_coef);
     if (f->h_itx) cudaFreeHost(f->h_itx);
     if (f->d_itx) cudaFree(f->d_itx);
+    for (int i = 0; i < 3; i++) if (f->sr_mem[i]) cudaFree(f->sr_mem[i]);
     if (f->h_obmc) cudaFreeHost(f->h_obmc);
     if (f->d_obmc) cudaFree(f->d_obmc);
     if (f->h_scaled) cudaFreeHost(f->h_scaled);
@@ -568,8 +612,8 @@ extern "C" int rb200_frame_output_planes(Rb200Frame *f, Rb200Planes *out) {
 static int plane_rows(const Rb200Frame *f, int p) {
     return p ? (f->hdr.height + f->g.ss_ver) >> f->g.ss_ver : f->hdr.height;
 }
-static size_t plane_row_bytes(const Rb200Frame *f, int p) {
-    return (size_t)(p ? (f->hdr.width + f->g.ss_hor) >> f->g.ss_hor : f->hdr.width) * f->px;
+static size_t plane_row_bytes(const Rb200Frame *f, int p) {   // of the output picture
+    return (size_t)(p ? (f->out_w + f->g.ss_hor) >> f->g.ss_hor : f->out_w) * f->px;
 }
 
 extern "C" int rb200_frame_upload_planes(Rb200Frame *f, int which, const void *const data[3],
@@ -777,6 +821,31 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         f->out = f->planes[1];
     }
     MARK(5);
+    // ---- super-resolution: the CDEF output and -- for the rows loop restoration takes from outside its
+    // stripes -- the deblocked picture are upscaled horizontally (rav1d_filter_sbrow_resize src/recon.rs:4215-4281,
+    // backup_lpf with resize src/lf_apply.rs:24-141)
+    f->out_w = h.width;
+    const bool do_sr = f->sr && (stages & RB200_STAGE_SUPER_RES);
+    if (do_sr && ((stages & RB200_STAGE_FILM_GRAIN) || f->band_s1 > f->band_s0))
+        return set_error(-38, "frame_submit: super-resolution together with film grain or a band restriction is not implemented");
+    if (do_sr) {
+        const Rb200Planes cdefp = f->out;
+        for (int p = 0; p < g.n_planes; p++) {
+            const int ssh = p ? g.ss_hor : 0, ssv = p ? g.ss_ver : 0;
+            const int dst_w = (f->sr_w + ssh) >> ssh, src_w = (4 * g.bw + ssh) >> ssh, rows = (h.height + ssv) >> ssv;
+            if ((r = resize_plane_launch(f->sr_planes[0].data[p], f->sr_planes[0].stride[p], cdefp.data[p], cdefp.stride[p], dst_w,
+                                         rows, src_w, f->resize_step[p ? 1 : 0], f->resize_start[p ? 1 : 0], f->bdmax, st))) return r;
+            f->launches++;
+            if ((restore_planes & (1 << p)) && cdefp.data[p] != f->planes[0].data[p]) {
+                if ((r = resize_plane_launch(f->sr_planes[1].data[p], f->sr_planes[1].stride[p], f->planes[0].data[p],
+                                             f->planes[0].stride[p], dst_w, rows, src_w, f->resize_step[p ? 1 : 0],
+                                             f->resize_start[p ? 1 : 0], f->bdmax, st))) return r;
+                f->launches++;
+            }
+        }
+        f->out = f->sr_planes[0];
+        f->out_w = f->sr_w;
+    }
     // ---- loop restoration: (p2 | cur) + cur -> p3 for the restored planes (src/recon.rs:4283-4317)
     if (restore_planes) {
         const Rb200Planes cdefp = f->out;
@@ -785,16 +854,20 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
             LrFrameParams P;
             P.plane = p;
             P.ss_hor = p ? g.ss_hor : 0; P.ss_ver = p ? g.ss_ver : 0;
-            P.w = (h.width + P.ss_hor) >> P.ss_hor; P.h = (h.height + P.ss_ver) >> P.ss_ver;
+            P.w = ((do_sr ? f->sr_w : h.width) + P.ss_hor) >> P.ss_hor; P.h = (h.height + P.ss_ver) >> P.ss_ver;
             P.unit_log2 = h.lr_unit_size_log2[p ? 1 : 0];
-            P.sb128 = h.sb128; P.sbh = g.sbh; P.sr_sb128w = g.sb128w;
+            P.sb128 = h.sb128; P.sbh = g.sbh; P.sr_sb128w = do_sr ? (f->sr_w + 127) >> 7 : g.sb128w;
             P.stripe_first = band.s0; P.stripe_end = band.s1;
-            if ((r = lr_plane_launch((const uint8_t *)cdefp.data[p], (const uint8_t *)f->planes[0].data[p],
-                                     (uint8_t *)f->planes[2].data[p], f->planes[2].stride[p], P, f->d_lr, f->bdmax, st)))
+            // rows outside a stripe come from the deblocked picture (upscaled alike under super-resolution;
+            // without CDEF the two are the same plane)
+            const Rb200Planes &dbl = !do_sr ? f->planes[0] : (cdefp.data[p] == f->sr_planes[0].data[p] && !do_cdef ? f->sr_planes[0] : f->sr_planes[1]);
+            const Rb200Planes &dst = do_sr ? f->sr_planes[2] : f->planes[2];
+            if ((r = lr_plane_launch((const uint8_t *)cdefp.data[p], (const uint8_t *)dbl.data[p],
+                                     (uint8_t *)dst.data[p], dst.stride[p], P, f->d_lr, f->bdmax, st)))
                 return r;
             f->launches++;
-            f->out.data[p] = f->planes[2].data[p];
-            f->out.stride[p] = f->planes[2].stride[p];
+            f->out.data[p] = dst.data[p];
+            f->out.stride[p] = dst.stride[p];
         }
     }
     MARK(6);

@@ -1148,6 +1148,15 @@ __global__ void resize_kernel(void *dst, int64_t dstride, const void *src, int64
     ((pixel *)((uint8_t *)dst + (int64_t)y * dstride))[x] = (pixel)iclip((-acc + 64) >> 7, 0, bdmax);
 }
 
+int resize_plane_launch(void *dst, int64_t dstride, const void *src, int64_t sstride, int dst_w, int h, int src_w, int dx,
+                        int mx0, int bdmax, cudaStream_t st) {
+    dim3 grid((dst_w + 127) / 128, h);
+    if (bdmax > 255) resize_kernel<BD16><<<grid, 128, 0, st>>>(dst, dstride, src, sstride, dst_w, h, src_w, dx, mx0, bdmax);
+    else resize_kernel<BD8><<<grid, 128, 0, st>>>(dst, dstride, src, sstride, dst_w, h, src_w, dx, mx0, bdmax);
+    RB_LAUNCH_CHECK();
+    return 0;
+}
+
 int mc_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int ss_hor,
                     int ss_ver, const Rb200McItem *d_items, int n, int bdmax, cudaStream_t st) {
     if (n <= 0) return 0;

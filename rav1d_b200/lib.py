@@ -89,7 +89,7 @@ N_2D_FILTERS = 10
 FILTER_2D_NAMES = ["8TAP_REGULAR", "8TAP_REGULAR_SMOOTH", "8TAP_REGULAR_SHARP", "8TAP_SHARP_REGULAR",
                    "8TAP_SHARP_SMOOTH", "8TAP_SHARP", "8TAP_SMOOTH_REGULAR", "8TAP_SMOOTH", "8TAP_SMOOTH_SHARP",
                    "BILINEAR"]
-STAGE_RECON, STAGE_DEBLOCK, STAGE_CDEF, STAGE_LR, STAGE_FILM_GRAIN = 1, 2, 4, 8, 16
+STAGE_RECON, STAGE_DEBLOCK, STAGE_CDEF, STAGE_LR, STAGE_FILM_GRAIN, STAGE_SUPER_RES = 1, 2, 4, 8, 16, 32
 STAGE_ALL = 15
 LAYOUT_I400, LAYOUT_I420, LAYOUT_I422, LAYOUT_I444 = 0, 1, 2, 3
 RESTORATION_NONE, RESTORATION_SWITCHABLE, RESTORATION_WIENER, RESTORATION_SGRPROJ = 0, 1, 2, 3
@@ -149,7 +149,7 @@ class FrameHeader(C.Structure):
                 ("sb128", C.c_int32), ("lf_level_y", C.c_int32 * 2), ("lf_level_u", C.c_int32),
                 ("lf_level_v", C.c_int32), ("cdef_damping", C.c_int32), ("cdef_y_strength", C.c_int32 * 8),
                 ("cdef_uv_strength", C.c_int32 * 8), ("lr_type", C.c_int32 * 3),
-                ("lr_unit_size_log2", C.c_int32 * 2)]
+                ("lr_unit_size_log2", C.c_int32 * 2), ("upscaled_width", C.c_int32)]
 
 
 class FrameGeometry(C.Structure):

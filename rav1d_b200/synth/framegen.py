@@ -498,7 +498,7 @@ class DeviceFrame:
         lv = lib.np_view(lib.frame_lf_levels(self.h), np.uint8, g.b4_stride * 32 * g.sb128h * 4)
         lv[:] = s.levels.reshape(-1)
         C.memmove(lib.frame_lf_lut(self.h), C.byref(s.lut), C.sizeof(lib.FilterLUT))
-        lib.np_view(lib.frame_lr_masks(self.h), lib.AV1_RESTORATION_DT, n)[:] = s.lr_masks
+        lib.np_view(lib.frame_lr_masks(self.h), lib.AV1_RESTORATION_DT, len(s.lr_masks))[:] = s.lr_masks   # sr_sb128w * sb128h
         obmc = getattr(s, "obmc_items", None)
         if obmc is not None and len(obmc):
             lib.check(lib.frame_reserve_obmc_items(self.h, len(obmc)), "reserve_obmc_items")
@@ -569,7 +569,7 @@ class DeviceFrame:
 
     def readback(self):
         s = self.s
-        out = [np.zeros_like(p) for p in s.ref]
+        out = [np.zeros_like(p) for p in getattr(s, "readback_like", s.ref)]
         data, strides = _plane_args(out)
         lib.check(lib.frame_readback(self.h, data, strides), "frame_readback")
         return out

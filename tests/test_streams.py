@@ -75,6 +75,48 @@ def test_stream_postfilters_bit_exact(rb, key):
         d.close()
 
 
+# ---------------------------------------------------------------- super-resolution frames of real streams
+GOLD_SR = streamdump.load_golden(streamdump.GOLDEN_SR) if os.path.exists(streamdump.GOLDEN_SR) else []
+
+
+def test_super_resolution_fixtures_cover_ratios_and_depths():
+    assert len(GOLD_SR) >= 10 and {s.bpc for _, s in GOLD_SR} == {8, 10}
+    assert len({(s.w, s.out_w) for _, s in GOLD_SR}) >= 6 and all(s.out_w > s.w for _, s in GOLD_SR)
+    assert any(s.stages & 8 for _, s in GOLD_SR) and any(not s.stages & 8 for _, s in GOLD_SR)
+
+
+@pytest.mark.skipif(not streamdump.available(), reason="reference tree / oracle build not present (GPU box)")
+def test_super_resolution_fixtures_match_a_fresh_dump():
+    for rel in ("8-bit/data/00000855.ivf", "10-bit/data/00000832.ivf"):
+        for s in streamdump.dump(os.path.join(streamdump.REF_DATA, rel), 2, sr=True):
+            g = dict(GOLD_SR)[f"{rel}#{s.index}"]
+            assert (s.w, s.out_w, s.stages) == (g.w, g.out_w, g.stages)   # (unused lr_mask entries are uninitialised memory)
+            for a, b in zip(streamdump.visible(s, s.post, out=True), streamdump.visible(g, g.post, out=True)):
+                assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", [k for k, _ in GOLD_SR])
+def test_stream_super_resolution_bit_exact(rb, key):
+    """Deblock + CDEF + horizontal upscaling + loop restoration of frames coded with super-resolution:
+    the coded-width picture before the filters must become the reference decoder's upscaled output."""
+    from rav1d_b200.synth import framegen
+    s = dict(GOLD_SR)[key]
+    d = framegen.DeviceFrame(s)
+    try:
+        d.load_batch()
+        d.upload(0, s.pre)
+        d.submit(s.stages); d.wait()
+        got = d.readback()
+    finally:
+        d.close()
+    for p, (a, b) in enumerate(zip(streamdump.visible(s, s.post, out=True), streamdump.visible(s, got, out=True))):
+        if not np.array_equal(a, b):
+            bad = np.argwhere(a != b)
+            raise AssertionError(f"{key}: plane {p} differs at {len(bad)} px, first (x={bad[0][1]}, y={bad[0][0]}): "
+                                 f"expected {a[tuple(bad[0])]} got {b[tuple(bad[0])]}; rows {np.unique(bad[:, 0])[:10]}")
+
+
 # ---------------------------------------------------------------- film grain on real streams
 def _load_grain():
     if not os.path.exists(streamdump.GOLDEN_GRAIN):

@@ -35,17 +35,27 @@ def pack(s):
     g = s.geom
     out = {"ints": np.array(ints, np.int32), "masks": s.masks.view(np.uint8), "levels": s.levels,
            "lut": np.frombuffer(bytes(s.lut), np.uint8), "lr_masks": s.lr_masks.view(np.uint8)}
+    out_w = getattr(s, "out_w", s.w)
+    if out_w != s.w:                       # super-resolution: the filtered picture is wider than the coded one
+        out["ints"] = np.array(ints + [out_w], np.int32)
     for k, planes in (("pre", s.pre), ("post", s.post)):
         for p, a in enumerate(planes):
-            rows, cols = (g.bh * 4) >> (g.ss_ver if p else 0), (g.bw * 4) >> (g.ss_hor if p else 0)
+            wk = (g.bw * 4) if k == "pre" or out_w == s.w else (out_w + 7) & ~7
+            rows, cols = (g.bh * 4) >> (g.ss_ver if p else 0), wk >> (g.ss_hor if p else 0)
             out[f"{k}{p}"] = a[:rows, :cols]
     return out
 
 
-def main():
+SR_STREAMS = [  # frames coded with super-resolution (8/10 bit, several scaling ratios, Wiener / SGR / no restoration)
+    ("8-bit/data/00000802.ivf", 2), ("8-bit/data/00000855.ivf", 3), ("8-bit/issues/323_tennis.ivf", 2),
+    ("8-bit/data/00000863.ivf", 1), ("10-bit/data/00000826.ivf", 2), ("10-bit/data/00000832.ivf", 2),
+]
+
+
+def main(streams=STREAMS, path=streamdump.GOLDEN, sr=False):
     blob, index = {}, []
-    for rel, n in STREAMS:
-        frames = streamdump.dump(os.path.join(streamdump.REF_DATA, rel), n)
+    for rel, n in streams:
+        frames = streamdump.dump(os.path.join(streamdump.REF_DATA, rel), n, sr=sr)
         assert frames, rel
         for s in frames:
             key = f"{rel}#{s.index}"
@@ -53,7 +63,6 @@ def main():
             for k, v in pack(s).items():
                 blob[f"{key}/{k}"] = v
     blob["index"] = np.array(index)
-    path = os.path.join(ROOT, "tests", "golden", "streams.npz")
     os.makedirs(os.path.dirname(path), exist_ok=True)
     np.savez_compressed(path, **blob)
     print(f"{len(index)} frames -> {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
@@ -81,4 +90,5 @@ def main_grain():
 
 if __name__ == "__main__":
     main()
+    main(SR_STREAMS, streamdump.GOLDEN_SR, sr=True)
     main_grain()
