@@ -199,6 +199,7 @@ def run_gpu(args, s, wl):
         raise SystemExit("bench.py: no CUDA device; rav1d_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"     # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib.check(lib.init(local), "rb200_init")
 
