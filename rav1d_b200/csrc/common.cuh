@@ -32,7 +32,9 @@ struct BD16 {
 
 __host__ __device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
 __host__ __device__ __forceinline__ int imax(int a, int b) { return a > b ? a : b; }
-__host__ __device__ __forceinline__ int iclip(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+// lo <= hi at every call site: max-then-min is the same value and compiles to two VIMNMX (or VIADDMNMX + VIMNMX
+// when v is a sum) instead of compare + select + min
+__host__ __device__ __forceinline__ int iclip(int v, int lo, int hi) { return imin(imax(v, lo), hi); }
 __host__ __device__ __forceinline__ int ulog2(unsigned v) {
 #ifdef __CUDA_ARCH__
     return 31 - __clz(v);

@@ -53,7 +53,7 @@ RB_HD constexpr int brev(int bits, int v) {
 }
 RB_HD constexpr int ilog2c(int v) { return v <= 1 ? 0 : 1 + ilog2c(v >> 1); }
 
-RB_HD int clip3(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+RB_HD int clip3(int v, int lo, int hi) { const int m = v > lo ? v : lo; return m < hi ? m : hi; }   // lo <= hi: max, then min
 
 // exact (a*ca + b*cb + 2048) >> 12 without 32-bit overflow for 20-bit inputs:
 // a coefficient above 2048 in magnitude is folded by +-4096 and its operand is
