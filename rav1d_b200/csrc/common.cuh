@@ -83,7 +83,7 @@ int coef_gather_launch(const void *h_cf, void *d_cf, const Rb200ItxItem *d_items
 int itx_launch(int tx, const Rb200Planes &planes, const void *cf, const Rb200ItxItem *items, int n, int bdmax,
                cudaStream_t st);
 int mc_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int ss_hor,
-                    int ss_ver, const Rb200McItem *d_items, int n, int bdmax, cudaStream_t st);
+                    int ss_ver, const Rb200McItem *d_items, int n, int bdmax, cudaStream_t st, int *counter = nullptr);
 int mc_comp_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int layout,
                          const Rb200CompItem *d_items, int n, int bdmax, cudaStream_t st);
 int mc_warp_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int layout,

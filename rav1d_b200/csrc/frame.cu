@@ -56,6 +56,7 @@ struct Rb200Frame {
     Rb200Av1FilterLUT *h_lut, *d_lut;
     Rb200Av1Restoration *h_lr, *d_lr;
     void *d_cdef_blk;   // per-8x8 CDEF decisions (direction, strengths), device only
+    int *d_counters;    // work dispensers of the batch kernels (one int each)
     int band_s0, band_s1;   // loop-restoration stripes this context produces (0, 0 = whole picture)
     size_t n_masks, n_lvl;
     int launches;
@@ -194,6 +195,7 @@ extern "C" int rb200_frame_create(Rb200Frame **out, const Rb200FrameHeader *hdr,
     if (!r) r = alloc_pair(&f->h_lut, &f->d_lut, 1);
     if (!r) r = alloc_pair(&f->h_lr, &f->d_lr, f->n_masks);
     if (!r) { e = cudaMalloc(&f->d_cdef_blk, (size_t)(g.bw >> 1) * (g.bh >> 1) * 8 + 64); if (e != cudaSuccess) r = cuda_fail(e, "cudaMalloc", __FILE__, __LINE__); }
+    if (!r) { e = cudaMalloc((void **)&f->d_counters, 64); if (e != cudaSuccess) r = cuda_fail(e, "cudaMalloc", __FILE__, __LINE__); }
     if (!r) { e = cudaStreamSynchronize(f->stream); if (e != cudaSuccess) r = cuda_fail(e, "sync", __FILE__, __LINE__); }
     if (r) { rb200_frame_destroy(f); return r; }
     f->out = f->planes[0];
@@ -230,6 +232,7 @@ extern "C" int rb200_frame_destroy(Rb200Frame *f) {
     if (f->d_comp) cudaFree(f->d_comp);
     if (f->h_mc) cudaFreeHost(f->h_mc);
     if (f->d_mc) cudaFree(f->d_mc);
+    if (f->d_counters) cudaFree(f->d_counters);
     if (f->h_masks) cudaFreeHost(f->h_masks);
     if (f->d_masks) cudaFree(f->d_masks);
     if (f->h_lvl) cudaFreeHost(f->h_lvl);
@@ -757,7 +760,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
     if (stages & RB200_STAGE_RECON) {
         if (n_mc) {
             if ((r = mc_batch_launch(f->planes[0], f->refs, f->n_refs, h.width, h.height, g.ss_hor, g.ss_ver, f->d_mc,
-                                     n_mc, f->bdmax, st))) return r;
+                                     n_mc, f->bdmax, st, f->d_counters))) return r;
             f->launches++;
         }
         if (f->n_comp) {

@@ -450,7 +450,7 @@ struct McRefSet {
 // One work item unpacked into registers together with everything derived from it once: the reference
 // plane and the window of its first tile.  (The 16-byte record is fetched with one 128-bit load.)
 #ifndef MC_BATCH_CTAS
-#define MC_BATCH_CTAS 4      // resident CTAs per SM the batch kernel is compiled for (register budget 128)
+#define MC_BATCH_CTAS 5      // resident CTAs per SM the batch kernel is compiled for (register budget 96)
 #endif
 struct McJob {
     int dst_x, dst_y, src_x, src_y, w, h, plane, mx, my, filter2d;
@@ -477,73 +477,126 @@ __device__ __forceinline__ McJob mc_load_job(const Rb200McItem *__restrict__ ite
     return j;
 }
 
-// Frame batch: warps walk the item list with a stride of the number of warps in the grid; while a
-// warp filters item i the first window of its item i + 1 is already in flight (cp.async).
+// Frame batch.  Warps take chunks of MC_CHUNK consecutive items from a shared counter.  The per-item set-up
+// (unpack, reference plane, window geometry, destination pointer) is the same ~150 instructions whether one
+// lane or thirty-two execute it, so it is done lane-parallel -- lane k prepares item k of the chunk -- and
+// parked in shared memory; the warp then walks the chunk reading each prepared job back with six broadcast
+// 128-bit loads.  While item k is filtered, the first window of item k + 1 is already in flight (cp.async).
 // Items wider/taller than 16 are walked tile by tile.
+constexpr int MC_CHUNK = 16;
+struct __align__(16) McJobS {
+    const uint8_t *rbase; int64_t rstride;
+    uint8_t *dst; int64_t dstride;
+    int rw, rh, src_x, src_y;
+    int w, h, phase /* mx | my << 8 | filter2d << 16 | fast << 24 */, xs;
+    int ys, ncols, nrows2, xa;
+    int par, nw, flags /* fh | fv << 1 | inside << 2 */, pad;
+};
+static_assert(sizeof(McJobS) == 96, "six 128-bit words");
+
 template <typename BD>
 __global__ void __launch_bounds__(MC_WARPS * 32, MC_BATCH_CTAS)
 mc_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int ss_hor, int ss_ver,
-                const Rb200McItem *__restrict__ items, int n_items, int bdmax) {
+                const Rb200McItem *__restrict__ items, int n_items, int bdmax, int *__restrict__ chunk_counter) {
     __shared__ struct { McFastSmem fast; McSmem slow; } smem[MC_WARPS];   // not a union: a prefetch may be in flight
-    const int warp = threadIdx.x >> 5;
-    const int n_warps = gridDim.x * MC_WARPS;
+    __shared__ McJobS jobs[MC_WARPS][MC_CHUNK];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     McFastSmem &sm = smem[warp].fast;
-    int idx = blockIdx.x * MC_WARPS + warp;
-    if (idx >= n_items) return;
-    McJob cur = mc_load_job(items, idx, refs, ref_w, ref_h, ss_hor, ss_ver);
-    int buf = 0;
-    if (cur.fast) mc_stage<BD>(sm.win[0], cur.ref, cur.W);
-    cp_async_commit();
+    auto read_job = [&](int k) {
+        McJobS J;
+        const uint4 *p = (const uint4 *)&jobs[warp][k];
+        uint4 *q = (uint4 *)&J;
+#pragma unroll
+        for (int i = 0; i < 6; i++) q[i] = p[i];
+        return J;
+    };
+    auto win_of = [](const McJobS &J) {
+        McWin W;
+        W.xs = J.xs; W.ys = J.ys; W.ncols = J.ncols; W.nrows2 = J.nrows2; W.xa = J.xa; W.par = J.par; W.nw = J.nw;
+        W.fh = J.flags & 1; W.fv = (J.flags >> 1) & 1; W.inside = (J.flags >> 2) & 1;
+        return W;
+    };
+    auto ref_of = [](const McJobS &J) { McRef r; r.base = J.rbase; r.stride = J.rstride; r.w = J.rw; r.h = J.rh; return r; };
+    int c_static = blockIdx.x * MC_WARPS + warp;      // without a dispenser: chunks dealt round-robin
     for (;;) {
-        const int nidx = idx + n_warps;
-        const bool have_next = nidx < n_items;
-        McJob nxt = cur;
-        if (have_next) {
-            nxt = mc_load_job(items, nidx, refs, ref_w, ref_h, ss_hor, ss_ver);
-            if (nxt.fast) mc_stage<BD>(sm.win[buf ^ 1], nxt.ref, nxt.W);
+        int c = c_static;
+        if (chunk_counter) {
+            if (lane == 0) c = atomicAdd(chunk_counter, 1);
+            c = __shfl_sync(0xffffffffu, c, 0);
+        }
+        c_static += gridDim.x * MC_WARPS;
+        const int base = c * MC_CHUNK;
+        if (base >= n_items) break;
+        const int cnt = imin(MC_CHUNK, n_items - base);
+        if (lane < cnt) {
+            const McJob j = mc_load_job(items, base + lane, refs, ref_w, ref_h, ss_hor, ss_ver);
+            McJobS J;
+            J.rbase = j.ref.base; J.rstride = j.ref.stride; J.rw = j.ref.w; J.rh = j.ref.h;
+            J.dstride = plane_stride(dst, j.plane);
+            J.dst = plane_ptr(dst, j.plane) + (int64_t)j.dst_y * J.dstride + (int64_t)j.dst_x * sizeof(typename BD::pixel);
+            J.src_x = j.src_x; J.src_y = j.src_y; J.w = j.w; J.h = j.h;
+            J.phase = j.mx | (j.my << 8) | (j.filter2d << 16) | ((int)j.fast << 24);
+            J.xs = j.W.xs; J.ys = j.W.ys; J.ncols = j.W.ncols; J.nrows2 = j.W.nrows2; J.xa = j.W.xa; J.par = j.W.par; J.nw = j.W.nw;
+            J.flags = (int)j.W.fh | ((int)j.W.fv << 1) | ((int)j.W.inside << 2); J.pad = 0;
+            jobs[warp][lane] = J;
+        }
+        __syncwarp();
+        int buf = 0;
+        {
+            const McJobS first = read_job(0);
+            if (first.phase >> 24) mc_stage<BD>(sm.win[0], ref_of(first), win_of(first));
         }
         cp_async_commit();
-        cp_async_wait<1>();      // the current item's first window has landed
-        __syncwarp();
-        uint8_t *dbase = plane_ptr(dst, cur.plane);
-        const int64_t dstride = plane_stride(dst, cur.plane);
-        if (cur.fast && cur.w <= MC_TILE && cur.h <= MC_TILE) {
-            // the common case: the whole block is the prefetched tile
-            uint8_t *o = dbase + (int64_t)cur.dst_y * dstride + (int64_t)cur.dst_x * sizeof(typename BD::pixel);
-            if (cur.w == 16 && cur.h == 16)
-                mc_tile_fast<BD, 16, 16>(sm, sm.win[buf], cur.W, 16, 16, 16, 16, cur.mx, cur.my, cur.filter2d, o, dstride, bdmax);
-            else if (cur.w == 8 && cur.h == 8)
-                mc_tile_fast<BD, 8, 8>(sm, sm.win[buf], cur.W, 8, 8, 8, 8, cur.mx, cur.my, cur.filter2d, o, dstride, bdmax);
-            else
-                mc_tile_fast<BD, 0, 0>(sm, sm.win[buf], cur.W, cur.w, cur.h, cur.w, cur.h, cur.mx, cur.my, cur.filter2d, o, dstride, bdmax);
-        } else {
-            for (int ty = 0; ty < cur.h; ty += MC_TILE) {
-                for (int tx = 0; tx < cur.w; tx += MC_TILE) {
-                    uint8_t *o = dbase + (int64_t)(cur.dst_y + ty) * dstride + (int64_t)(cur.dst_x + tx) * sizeof(typename BD::pixel);
-                    const int tw = imin(MC_TILE, cur.w - tx), th = imin(MC_TILE, cur.h - ty);
-                    if (cur.fast) {
-                        const McWin W = mc_window(cur.ref, cur.src_x + tx, cur.src_y + ty, tw, th, cur.mx, cur.my, cur.filter2d);
-                        if (tx | ty) {   // further tiles of a large block: staged in place, not prefetched
-                            mc_stage<BD>(sm.win[buf], cur.ref, W);
-                            cp_async_commit();
-                            cp_async_wait<0>();
-                            __syncwarp();
+        for (int k = 0; k < cnt; k++) {
+            if (k + 1 < cnt) {   // only one prepared job is held in registers at a time
+                const McJobS nxt = read_job(k + 1);
+                if (nxt.phase >> 24) mc_stage<BD>(sm.win[buf ^ 1], ref_of(nxt), win_of(nxt));
+            }
+            cp_async_commit();
+            cp_async_wait<1>();      // the current item's first window has landed
+            __syncwarp();
+            const McJobS cur = read_job(k);
+            const int mx = cur.phase & 0xff, my = (cur.phase >> 8) & 0xff, filter2d = (cur.phase >> 16) & 0xff;
+            const bool fast = cur.phase >> 24;
+            if (fast && cur.w <= MC_TILE && cur.h <= MC_TILE) {
+                // the common case: the whole block is the prefetched tile
+                const McWin W = win_of(cur);
+                if (cur.w == 16 && cur.h == 16)
+                    mc_tile_fast<BD, 16, 16>(sm, sm.win[buf], W, 16, 16, 16, 16, mx, my, filter2d, cur.dst, cur.dstride, bdmax);
+                else if (cur.w == 8 && cur.h == 8)
+                    mc_tile_fast<BD, 8, 8>(sm, sm.win[buf], W, 8, 8, 8, 8, mx, my, filter2d, cur.dst, cur.dstride, bdmax);
+                else
+                    mc_tile_fast<BD, 0, 0>(sm, sm.win[buf], W, cur.w, cur.h, cur.w, cur.h, mx, my, filter2d, cur.dst, cur.dstride, bdmax);
+            } else {
+                const McRef ref = ref_of(cur);
+                for (int ty = 0; ty < cur.h; ty += MC_TILE) {
+                    for (int tx = 0; tx < cur.w; tx += MC_TILE) {
+                        uint8_t *o = cur.dst + (int64_t)ty * cur.dstride + (int64_t)tx * sizeof(typename BD::pixel);
+                        const int tw = imin(MC_TILE, cur.w - tx), th = imin(MC_TILE, cur.h - ty);
+                        if (fast) {
+                            const McWin W = mc_window(ref, cur.src_x + tx, cur.src_y + ty, tw, th, mx, my, filter2d);
+                            if (tx | ty) {   // further tiles of a large block: staged in place, not prefetched
+                                mc_stage<BD>(sm.win[buf], ref, W);
+                                cp_async_commit();
+                                cp_async_wait<0>();
+                                __syncwarp();
+                            }
+                            if (tw == 16 && th == 16)
+                                mc_tile_fast<BD, 16, 16>(sm, sm.win[buf], W, tw, th, cur.w, cur.h, mx, my, filter2d, o, cur.dstride, bdmax);
+                            else
+                                mc_tile_fast<BD, 0, 0>(sm, sm.win[buf], W, tw, th, cur.w, cur.h, mx, my, filter2d, o, cur.dstride, bdmax);
+                        } else {
+                            mc_tile<BD, false>(smem[warp].slow, ref, cur.src_x + tx, cur.src_y + ty, tw, th, cur.w, cur.h, mx, my,
+                                               filter2d, o, cur.dstride, bdmax);
                         }
-                        if (tw == 16 && th == 16)
-                            mc_tile_fast<BD, 16, 16>(sm, sm.win[buf], W, tw, th, cur.w, cur.h, cur.mx, cur.my, cur.filter2d, o, dstride, bdmax);
-                        else
-                            mc_tile_fast<BD, 0, 0>(sm, sm.win[buf], W, tw, th, cur.w, cur.h, cur.mx, cur.my, cur.filter2d, o, dstride, bdmax);
-                    } else {
-                        mc_tile<BD, false>(smem[warp].slow, cur.ref, cur.src_x + tx, cur.src_y + ty, tw, th, cur.w, cur.h, cur.mx, cur.my,
-                                           cur.filter2d, o, dstride, bdmax);
                     }
                 }
             }
+            buf ^= 1;
         }
-        if (!have_next) break;
-        cur = nxt; idx = nidx; buf ^= 1;
+        cp_async_wait<0>();
+        __syncwarp();      // every lane is done with jobs[] before the next chunk overwrites it
     }
-    cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------- compound blocks (batch)
@@ -1158,7 +1211,7 @@ int resize_plane_launch(void *dst, int64_t dstride, const void *src, int64_t sst
 }
 
 int mc_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int ss_hor,
-                    int ss_ver, const Rb200McItem *d_items, int n, int bdmax, cudaStream_t st) {
+                    int ss_ver, const Rb200McItem *d_items, int n, int bdmax, cudaStream_t st, int *counter) {
     if (n <= 0) return 0;
     McRefSet rs = {};
     for (int i = 0; i < n_refs && i < 8; i++) rs.p[i] = refs[i];
@@ -1176,11 +1229,13 @@ int mc_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs,
         }
     }
     // persistent warps: 148 SMs x 6 resident CTAs, capped by the item count
-    const int grid = imin((n + MC_WARPS - 1) / MC_WARPS, 148 * MC_BATCH_CTAS);
-    if (bdmax > 255)
-        mc_batch_kernel<BD16><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, ss_hor, ss_ver, d_items, n, bdmax);
-    else
-        mc_batch_kernel<BD8><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, ss_hor, ss_ver, d_items, n, bdmax);
+    const int n_chunks = (n + MC_CHUNK - 1) / MC_CHUNK;
+    const int grid = imin((n_chunks + MC_WARPS - 1) / MC_WARPS, 148 * MC_BATCH_CTAS);
+    // counter: chunk dispenser of this launch (4 bytes of device memory owned by the caller, e.g. one per frame
+    // context -- launches of different contexts overlap); nullptr = static round-robin
+    if (counter) RB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
+    if (bdmax > 255) mc_batch_kernel<BD16><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, ss_hor, ss_ver, d_items, n, bdmax, counter);
+    else mc_batch_kernel<BD8><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, ss_hor, ss_ver, d_items, n, bdmax, counter);
     RB_LAUNCH_CHECK();
     return 0;
 }
