@@ -497,7 +497,7 @@ static_assert(sizeof(McJobS) == 96, "six 128-bit words");
 template <typename BD>
 __global__ void __launch_bounds__(MC_WARPS * 32, MC_BATCH_CTAS)
 mc_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int ss_hor, int ss_ver,
-                const Rb200McItem *__restrict__ items, int n_items, int bdmax, int *__restrict__ chunk_counter) {
+                const Rb200McItem *__restrict__ items, int n_items, int bdmax, int *__restrict__ chunk_counter, int chunk) {
     __shared__ struct { McFastSmem fast; McSmem slow; } smem[MC_WARPS];   // not a union: a prefetch may be in flight
     __shared__ McJobS jobs[MC_WARPS][MC_CHUNK];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -525,9 +525,9 @@ mc_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int ss_hor
             c = __shfl_sync(0xffffffffu, c, 0);
         }
         c_static += gridDim.x * MC_WARPS;
-        const int base = c * MC_CHUNK;
+        const int base = c * chunk;
         if (base >= n_items) break;
-        const int cnt = imin(MC_CHUNK, n_items - base);
+        const int cnt = imin(chunk, n_items - base);
         if (lane < cnt) {
             const McJob j = mc_load_job(items, base + lane, refs, ref_w, ref_h, ss_hor, ss_ver);
             McJobS J;
@@ -1229,13 +1229,16 @@ int mc_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs,
         }
     }
     // persistent warps: 148 SMs x 6 resident CTAs, capped by the item count
-    const int n_chunks = (n + MC_CHUNK - 1) / MC_CHUNK;
+    // chunk size: as large as MC_CHUNK when there is enough work to give every resident warp a few chunks
+    const int resident_warps = 148 * MC_BATCH_CTAS * MC_WARPS;
+    const int chunk = imax(2, imin(bdmax > 255 ? MC_CHUNK : 4, n / (2 * resident_warps)));   // 8-bit windows are staged synchronously: short chunks
+    const int n_chunks = (n + chunk - 1) / chunk;
     const int grid = imin((n_chunks + MC_WARPS - 1) / MC_WARPS, 148 * MC_BATCH_CTAS);
     // counter: chunk dispenser of this launch (4 bytes of device memory owned by the caller, e.g. one per frame
     // context -- launches of different contexts overlap); nullptr = static round-robin
     if (counter) RB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
-    if (bdmax > 255) mc_batch_kernel<BD16><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, ss_hor, ss_ver, d_items, n, bdmax, counter);
-    else mc_batch_kernel<BD8><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, ss_hor, ss_ver, d_items, n, bdmax, counter);
+    if (bdmax > 255) mc_batch_kernel<BD16><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, ss_hor, ss_ver, d_items, n, bdmax, counter, chunk);
+    else mc_batch_kernel<BD8><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, ss_hor, ss_ver, d_items, n, bdmax, counter, chunk);
     RB_LAUNCH_CHECK();
     return 0;
 }
