@@ -216,7 +216,7 @@ struct LfPlaneSet {
 // DIR 1: row edges -- the thread owns 4 adjacent columns; every row of the stencil is one
 // aligned 4-pixel load, coalesced across the warp.
 template <typename BD, int DIR>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 deblock_units_kernel(LfPlaneSet S, const Rb200Av1Filter *__restrict__ masks, const uint8_t (*__restrict__ lvl)[4],
                      const Rb200Av1FilterLUT *__restrict__ lut, int bdmax) {
     using pixel = typename BD::pixel;

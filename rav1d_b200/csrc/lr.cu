@@ -411,7 +411,7 @@ __device__ void lr2_sgr(Lr2Smem &sm, int tw, int th, int kind, unsigned s0, unsi
 
 // cdef: CDEF output (the picture being restored); dbl: deblocked pre-CDEF picture; out: restored picture
 template <typename BD>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 lr_frame_kernel(const uint8_t *__restrict__ cdef, const uint8_t *__restrict__ dbl, uint8_t *__restrict__ outp,
                 int64_t stride, LrFrameParams P, const Rb200Av1Restoration *__restrict__ lrm, int bdmax) {
     using pixel = typename BD::pixel;

@@ -450,7 +450,7 @@ struct McRefSet {
 // One work item unpacked into registers together with everything derived from it once: the reference
 // plane and the window of its first tile.  (The 16-byte record is fetched with one 128-bit load.)
 #ifndef MC_BATCH_CTAS
-#define MC_BATCH_CTAS 5      // resident CTAs per SM the batch kernel is compiled for (register budget 96)
+#define MC_BATCH_CTAS 6      // resident CTAs per SM the batch kernel is compiled for (register budget 80)
 #endif
 struct McJob {
     int dst_x, dst_y, src_x, src_y, w, h, plane, mx, my, filter2d;

@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """One line per kernel launch from an `ncu --set full` report:
-    ncu -i file.ncu-rep --page raw --csv > raw.csv;  python tools/ncu_summary.py raw.csv > summary.csv
-Columns are picked by metric name, so missing metrics print as empty fields."""
+    ncu -i file.ncu-rep --page raw --csv > raw.csv;  python tools/ncu_summary.py raw.csv [last_n] > summary.csv
+Columns are picked by metric name, so missing metrics print as empty fields; last_n keeps only the last n
+launches (e.g. the second, warm submit of tools/one_frame.py)."""
 import csv
 import sys
 
@@ -22,9 +23,10 @@ names, units = rows[h], rows[h + 1]
 ix = {n: i for i, n in enumerate(names)}
 out = csv.writer(sys.stdout)
 out.writerow(["kernel", "grid", "block"] + [c[0] for c in COLS])
-for r in rows[h + 2:]:
-    if len(r) != len(names) or not r[0].isdigit():
-        continue
+body = [r for r in rows[h + 2:] if len(r) == len(names) and r[0].isdigit()]
+if len(sys.argv) > 2:
+    body = body[-int(sys.argv[2]):]
+for r in body:
     line = [r[ix["Kernel Name"]].split("(")[0], r[ix["Grid Size"]].split(",")[0].strip("( "), r[ix["Block Size"]].split(",")[0].strip("( ")]
     for _, metric, scale in COLS:
         if metric not in ix:
