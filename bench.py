@@ -376,6 +376,12 @@ def run_gpu(args, s, wl):
             roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                         "frac": round(ach / peak, 4), "traffic": TRAFFIC.get((args.workload, dom)),
                         "peak_source": peak_src, "share_of_step": round(per_stage[dom]["ms"] / sum(v["ms"] for v in per_stage.values()), 3)}
+        issue = None
+        if args.workload in WARP_INST_PER_FRAME and clocks and clocks.get("sm_mhz"):
+            peak_issue = 148 * 4 * clocks["sm_mhz"] * 1e6          # warp instructions / s
+            wi = WARP_INST_PER_FRAME[args.workload]
+            issue = {"warp_inst_per_frame": wi, "peak_warp_inst_per_s": peak_issue, "source": "profiles/r01c_ncu_full_summary_*.csv",
+                     "frac": round(wi * (value * 1e6 / (w * h)) / world / peak_issue, 4)}
         # frame-level algorithmic bytes as BASELINE.md 4 counts them (MC + itx = one fused recon stage: 2S + C)
         frame_bytes = (ab["recon"] if stages & 1 else 0) + sum(ab[k] for k in ("deblock", "cdef", "lr", "film_grain") if k in per_stage)
         line = {"metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -390,7 +396,7 @@ def run_gpu(args, s, wl):
                 "stage_timing": "CUDA-event marks of a one-stream pass over the same steps (kernels serial)" if multi
                                 else "CUDA-event marks inside the timed region",
                 "frame_roofline_frac": round(frame_bytes * (value * 1e6 / (w * h)) / world / (peak * 1e9), 4),
-                "stages": per_stage, "roofline": roofline, "clocks": clocks,
+                "stages": per_stage, "roofline": roofline, "issue": issue, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d * FRAMES_PER_STEP,
                         "d2h_bytes_per_step": d2h * FRAMES_PER_STEP,
                         "coefficients": {"gather": "gather kernel over pinned host memory, column-bounded", "copy": "H2D copy",
@@ -418,11 +424,16 @@ def run_gpu(args, s, wl):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
 # capture of the dominant kernel (profiles/), keyed by (workload, stage); None until captured.
 TRAFFIC = {
-    # profiles/r01b_ncu_full_summary.csv: cdef_dir_frame_kernel 13.80 MB + cdef_filter_frame_kernel 26.04 + 2.63 MB
-    ("4k10", "cdef"): 42.47e6,
-    ("4k10", "mc"): 26.87e6,
-    ("4k10", "lr"): 27.24e6,
+    # profiles/r01c_ncu_full_summary_4k10.csv: cdef_dir_frame_kernel 13.88 MB + cdef_filter_frame_kernel 26.05 + 2.43 MB
+    ("4k10", "cdef"): 42.36e6,
+    ("4k10", "mc"): 26.70e6,
+    ("4k10", "lr"): 27.22e6,
+    # profiles/r01c_ncu_full_summary_4k10c5.csv: mc_batch 25.2 + mc_comp_batch 53.7 + warp 5.8 + obmc 8.4 + 13.9 MB
+    ("4k10c5", "mc"): 107.0e6,
 }
+# Executed warp instructions per frame (smsp__inst_executed.sum over one frame's launches, same captures): the path is
+# integer-issue bound, so value x this / (SMs x 4 schedulers x clock) says how full the issue slots are.
+WARP_INST_PER_FRAME = {"4k10": 203.0e6, "4k10c5": 293.9e6}
 
 
 def main():
