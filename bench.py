@@ -324,7 +324,7 @@ def run_gpu(args, s, wl):
         submit(d, {"gather": 3, "zerocopy": 2, "copy": 1}[args.coefs])   # the front end would refill the pinned staging here
         lib.check(lib.frame_readback_async(d.h, host_out[i % N_CTX][0], host_out[i % N_CTX][1]))
 
-    for i in range(args.warmup * FRAMES_PER_STEP):
+    for i in range(max(args.warmup * FRAMES_PER_STEP, 256)):   # >= 0.25 s of traffic: lets the host link and clocks settle
         e2e_frame(i)
     barrier()
     s0 = torch.cuda.Event(enable_timing=True)
