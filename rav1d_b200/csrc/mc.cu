@@ -318,6 +318,34 @@ __device__ __forceinline__ void mc_stage(uint32_t *win, const McRef &ref, const 
     }
 }
 
+// 8-bit windows of the frame batch: the raw bytes go global -> shared asynchronously in 4-byte pieces (so that,
+// like the 16-bit windows, they stream in behind the previous item's arithmetic); mc_expand8 then widens them
+// into the pixel-pair words the filter passes read.
+constexpr int MCF_RAW8_WPR = 7;   // 28 bytes per window row: up to 3 bytes of alignment + 23 pixels
+__device__ __forceinline__ bool mc_raw8_ok(const McRef &ref, const McWin &W) {
+    return W.inside && (W.xs & ~3) + 4 * MCF_RAW8_WPR <= ref.stride && !(((uintptr_t)ref.base | (uintptr_t)ref.stride) & 3);
+}
+__device__ __forceinline__ void mc_stage8_async(uint32_t *raw8, const McRef &ref, const McWin &W) {
+    const int lane = threadIdx.x & 31, k = lane & 7;
+    const int xa4 = W.xs & ~3, nw4 = ((W.xs & 3) + W.ncols + 3) >> 2;
+    if (k < nw4) {
+        for (int r = lane >> 3; r < W.nrows2; r += 4) {
+            const int yy = iclip(W.ys + r, 0, ref.h - 1);
+            cp_async4(raw8 + r * MCF_RAW8_WPR + k, ref.base + (int64_t)yy * ref.stride + xa4 + 4 * k);
+        }
+    }
+}
+__device__ __forceinline__ void mc_expand8(uint32_t *win, const uint32_t *raw8, const McWin &W) {
+    const int lane = threadIdx.x & 31, k = lane & 15;
+    const uint8_t *rb = (const uint8_t *)raw8 + ((W.xs & 3) & ~1) + 2 * k;   // the window's pair k within a raw row
+    if (k < W.nw) {
+        for (int r = lane >> 4; r < W.nrows2; r += 2) {
+            const unsigned q = *(const uint16_t *)(rb + r * (4 * MCF_RAW8_WPR));
+            win[r * MCF_WPW + k] = (q & 0xff) | ((q & 0xff00) << 8);
+        }
+    }
+}
+
 // put, w and h even and <= 16; `win` already staged (mc_stage) and visible to the warp.
 // TW / TH: compile-time tile size (0 = use the run-time w / h) -- the common 16x16 and 8x8 tiles get
 // fully unrolled task loops with constant index arithmetic.
@@ -500,6 +528,12 @@ mc_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int ss_hor
                 const Rb200McItem *__restrict__ items, int n_items, int bdmax, int *__restrict__ chunk_counter, int chunk) {
     __shared__ struct { McFastSmem fast; McSmem slow; } smem[MC_WARPS];   // not a union: a prefetch may be in flight
     __shared__ McJobS jobs[MC_WARPS][MC_CHUNK];
+    __shared__ uint32_t raw8_s[BD::hbd ? 1 : MC_WARPS][2][BD::hbd ? 1 : MCF_WROWS * MCF_RAW8_WPR];   // 8-bit only
+    uint32_t (*raw8)[BD::hbd ? 1 : MCF_WROWS * MCF_RAW8_WPR] = raw8_s[BD::hbd ? 0 : threadIdx.x >> 5];
+    auto stage_first = [&](int b, const McRef &ref, const McWin &W) {
+        if (!BD::hbd && mc_raw8_ok(ref, W)) mc_stage8_async(raw8[b], ref, W);
+        else mc_stage<BD>(smem[threadIdx.x >> 5].fast.win[b], ref, W);
+    };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     McFastSmem &sm = smem[warp].fast;
     auto read_job = [&](int k) {
@@ -544,13 +578,13 @@ mc_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int ss_hor
         int buf = 0;
         {
             const McJobS first = read_job(0);
-            if (first.phase >> 24) mc_stage<BD>(sm.win[0], ref_of(first), win_of(first));
+            if (first.phase >> 24) stage_first(0, ref_of(first), win_of(first));
         }
         cp_async_commit();
         for (int k = 0; k < cnt; k++) {
             if (k + 1 < cnt) {   // only one prepared job is held in registers at a time
                 const McJobS nxt = read_job(k + 1);
-                if (nxt.phase >> 24) mc_stage<BD>(sm.win[buf ^ 1], ref_of(nxt), win_of(nxt));
+                if (nxt.phase >> 24) stage_first(buf ^ 1, ref_of(nxt), win_of(nxt));
             }
             cp_async_commit();
             cp_async_wait<1>();      // the current item's first window has landed
@@ -558,6 +592,10 @@ mc_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int ss_hor
             const McJobS cur = read_job(k);
             const int mx = cur.phase & 0xff, my = (cur.phase >> 8) & 0xff, filter2d = (cur.phase >> 16) & 0xff;
             const bool fast = cur.phase >> 24;
+            if (!BD::hbd && fast && mc_raw8_ok(ref_of(cur), win_of(cur))) {   // raw bytes have landed: widen them
+                mc_expand8(sm.win[buf], raw8[buf], win_of(cur));
+                __syncwarp();
+            }
             if (fast && cur.w <= MC_TILE && cur.h <= MC_TILE) {
                 // the common case: the whole block is the prefetched tile
                 const McWin W = win_of(cur);
@@ -1231,7 +1269,7 @@ int mc_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs,
     // persistent warps: 148 SMs x 6 resident CTAs, capped by the item count
     // chunk size: as large as MC_CHUNK when there is enough work to give every resident warp a few chunks
     const int resident_warps = 148 * MC_BATCH_CTAS * MC_WARPS;
-    const int chunk = imax(2, imin(bdmax > 255 ? MC_CHUNK : 4, n / (2 * resident_warps)));   // 8-bit windows are staged synchronously: short chunks
+    const int chunk = imax(2, imin(MC_CHUNK, n / (2 * resident_warps)));
     const int n_chunks = (n + chunk - 1) / chunk;
     const int grid = imin((n_chunks + MC_WARPS - 1) / MC_WARPS, 148 * MC_BATCH_CTAS);
     // counter: chunk dispenser of this launch (4 bytes of device memory owned by the caller, e.g. one per frame
