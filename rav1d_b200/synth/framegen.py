@@ -408,6 +408,131 @@ def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1, comp_frac=0.0, w
     return s
 
 
+def generate_recon_layout(w, h, bpc, layout, seed=1, comp_frac=0.3, warp_frac=0.1, obmc_frac=0.2):
+    """A reconstruction-only batch (prediction + residual, no filter metadata) for any pixel layout: 4:0:0, 4:2:0,
+    4:2:2 or 4:4:4.  16x16 luma blocks; chroma blocks, vectors, phases, OBMC strips and transform sizes follow the
+    sub-sampling as recon.rs `mc()` / `obmc()` derive them (src/recon.rs:2047-2055,2100-2101,2205-2309)."""
+    rng = np.random.default_rng(seed)
+    bdmax = (1 << bpc) - 1
+    pdt, cdt = (np.uint16, np.int32) if bpc > 8 else (np.uint8, np.int16)
+    ssx, ssy = int(layout != lib.LAYOUT_I444), int(layout == lib.LAYOUT_I420)
+    n_planes = 1 if layout == lib.LAYOUT_I400 else 3
+    s = SynthFrame()
+    s.w, s.h, s.bpc, s.bdmax, s.layout = w, h, bpc, bdmax, layout
+    hd = lib.FrameHeader()
+    hd.width, hd.height, hd.bpc, hd.layout = w, h, bpc, layout
+    s.hdr = hd
+    g = s.geom = geometry(hd)
+    g.ss_hor, g.ss_ver, g.n_planes = (ssx, ssy, 3) if n_planes == 3 else (0, 0, 1)
+    aw, ah = (w + 127) & ~127, (h + 127) & ~127
+    s.aw, s.ah = aw, ah
+
+    def picture():
+        pl = [np.zeros((ah, aw), pdt)]
+        pl[0][:h, :w] = smooth_plane(rng, h, w, bdmax)
+        for _ in range(n_planes - 1):
+            c = np.zeros((ah >> ssy, aw >> ssx), pdt)
+            ch, cw = (h + ssy) >> ssy, (w + ssx) >> ssx
+            c[:ch, :cw] = smooth_plane(rng, ch, cw, bdmax, cell=8)
+            pl.append(c)
+        return pl
+    s.ref, s.ref2 = picture(), picture()
+    nbx, nby = w // BLK, h // BLK                 # whole blocks only (warp / OBMC need them)
+    nb = nbx * nby
+    by, bx = np.divmod(np.arange(nb), nbx)
+    mvx = rng.integers(-256, 257, size=nb); mvy = rng.integers(-256, 257, size=nb)
+    mvx[rng.random(nb) < 0.15] &= ~7; mvy[rng.random(nb) < 0.15] &= ~7
+    mvx2 = rng.integers(-256, 257, size=nb); mvy2 = rng.integers(-256, 257, size=nb)
+    f2d = rng.integers(0, 10, size=nb)
+    is_comp = rng.random(nb) < comp_frac
+    is_warp = (rng.random(nb) < warp_frac) & ~is_comp
+    is_obmc = (rng.random(nb) < obmc_frac) & ~is_comp & ~is_warp
+
+    def plane_items(sel, p, bw, bh, vx, vy, fl, flags=0, dst_off=(0, 0)):
+        """Rb200McItems of plane p for blocks `sel`: a bw x bh (luma units) area at the block origin + dst_off, moved by (vx, vy)."""
+        sx, sy = (ssx, ssy) if p else (0, 0)
+        o = np.zeros(sel.size, lib.MC_ITEM_DT)
+        x0 = (bx[sel] * BLK + dst_off[0]) >> sx; y0 = (by[sel] * BLK + dst_off[1]) >> sy
+        o["dst_x"] = x0; o["dst_y"] = y0
+        o["src_x"] = x0 + (vx >> (3 + sx)); o["src_y"] = y0 + (vy >> (3 + sy))
+        o["w"] = bw >> sx; o["h"] = bh >> sy; o["plane"] = p
+        o["mx"] = (vx & (15 >> (1 - sx))) << (1 - sx); o["my"] = (vy & (15 >> (1 - sy))) << (1 - sy)
+        o["filter2d"] = fl; o["flags"] = flags
+        return o
+    put = np.nonzero(~(is_comp | is_warp))[0]
+    s.mc_items = np.concatenate([plane_items(put, p, BLK, BLK, mvx[put], mvy[put], f2d[put]) for p in range(n_planes)])
+    ab = np.nonzero(is_obmc & (by > 0))[0]; lf_ = np.nonzero(is_obmc & (bx > 0))[0]
+    above = [plane_items(ab, p, BLK, BLK // 2, mvx[ab - nbx], mvy[ab - nbx], f2d[ab - nbx], lib.MC_OBMC_ABOVE) for p in range(n_planes)]
+    left = [plane_items(lf_, p, BLK // 2, BLK, mvx[lf_ - 1], mvy[lf_ - 1], f2d[lf_ - 1], lib.MC_OBMC_LEFT) for p in range(n_planes)]
+    s.obmc_items = np.concatenate(above + left)
+    s.n_obmc = (sum(len(a) for a in above), sum(len(a) for a in left))
+    ci = np.nonzero(is_comp)[0]
+    comp = np.zeros(ci.size, lib.COMP_ITEM_DT)
+    comp["x"] = bx[ci] * BLK; comp["y"] = by[ci] * BLK; comp["w"] = BLK; comp["h"] = BLK
+    comp["ref"][:, 1] = 1
+    comp["mv"][:, 0, 0] = mvy[ci]; comp["mv"][:, 0, 1] = mvx[ci]; comp["mv"][:, 1, 0] = mvy2[ci]; comp["mv"][:, 1, 1] = mvx2[ci]
+    comp["filter2d"] = f2d[ci]; comp["comp_type"] = rng.integers(0, 4, size=ci.size)
+    comp["jnt_weight"] = rng.choice(np.array([3, 5, 7, 9, 11, 13]), size=ci.size)
+    comp["mask_sign"] = rng.integers(0, 2, size=ci.size); comp["wedge_idx"] = rng.integers(0, 16, size=ci.size)
+    s.comp_items = comp
+    wi = np.nonzero(is_warp)[0]
+    warp = np.zeros(wi.size, lib.WARP_ITEM_DT)
+    warp["x"] = bx[wi] * BLK; warp["y"] = by[wi] * BLK; warp["w"] = BLK; warp["h"] = BLK
+    mat = np.zeros((wi.size, 6), np.int64)
+    mat[:, 0] = rng.integers(-(20 << 16), 20 << 16, size=wi.size); mat[:, 1] = rng.integers(-(20 << 16), 20 << 16, size=wi.size)
+    mat[:, 2] = (1 << 16) + rng.integers(-3000, 3000, size=wi.size); mat[:, 3] = rng.integers(-3000, 3000, size=wi.size)
+    mat[:, 4] = rng.integers(-3000, 3000, size=wi.size); mat[:, 5] = (1 << 16) + rng.integers(-3000, 3000, size=wi.size)
+    mat[:, 0] -= (mat[:, 2] - (1 << 16)) * (bx[wi] * BLK) + mat[:, 3] * (by[wi] * BLK)
+    mat[:, 1] -= mat[:, 4] * (bx[wi] * BLK) + (mat[:, 5] - (1 << 16)) * (by[wi] * BLK)
+    warp["matrix"] = mat.astype(np.int32)
+    warp["abcd"] = (rng.integers(0, 0x2000, size=(wi.size, 4)) - 0xa00).astype(np.int16)
+    s.warp_items = warp
+
+    # residuals: one luma transform per block, one chroma transform of the sub-sampled block size per plane
+    from rav1d_b200.lib import TX_DIMS
+    TX_8X8, TX_16X16 = 1, 2
+    ctx = {(0, 0): TX_16X16, (1, 1): TX_8X8, (1, 0): next(t for t in range(19) if TX_DIMS[t] == (8, 16))}[(ssx, ssy)]
+    recs = [(0, bx * BLK, by * BLK, np.full(nb, TX_16X16))]
+    for p in range(1, n_planes):
+        recs.append((p, bx * BLK >> ssx, by * BLK >> ssy, np.full(nb, ctx)))
+    plane = np.concatenate([np.full(nb, r[0]) for r in recs]); xs = np.concatenate([r[1] for r in recs])
+    ys = np.concatenate([r[2] for r in recs]); tx = np.concatenate([r[3] for r in recs])
+    keep = rng.random(tx.size) > 0.2
+    plane, xs, ys, tx = plane[keep], xs[keep], ys[keep], tx[keep]
+    from rav1d_b200.synth.itxgen import valid_txtps
+    txtp = np.zeros(tx.size, np.int64)
+    for t in np.unique(tx):
+        m = tx == t
+        v = np.array([tp for tp in valid_txtps(int(t)) if tp < 16])
+        txtp[m] = np.where(rng.random(int(m.sum())) < 0.5, 0, rng.choice(v, size=int(m.sum())))
+    order = np.argsort(tx * 32 + txtp, kind="stable")
+    plane, xs, ys, tx, txtp = plane[order], xs[order], ys[order], tx[order], txtp[order]
+    itx = np.zeros(tx.size, lib.ITX_ITEM_DT)
+    itx["x"] = xs; itx["y"] = ys; itx["plane"] = plane; itx["tx"] = tx; itx["txtp"] = txtp
+    per = np.array([min(TX_DIMS[int(t)][0], 32) * min(TX_DIMS[int(t)][1], 32) for t in tx], np.int64)
+    cf_off = np.concatenate([[0], np.cumsum(per)[:-1]]) if tx.size else np.zeros(0, np.int64)
+    itx["cf_off"] = cf_off
+    coef = np.zeros(int(per.sum()), cdt)
+    for t in np.unique(tx):
+        for tp in np.unique(txtp[tx == t]):
+            idx = np.nonzero((tx == t) & (txtp == tp))[0]
+            c, e = gen_coefs(rng, int(t), int(tp), max(bdmax >> 4, 2), idx.size, "full")
+            n = c.shape[1]
+            cut = rng.integers(0, n, size=idx.size)
+            c[np.arange(n)[None, :] > cut[:, None]] = 0
+            nz = c != 0
+            last = np.where(nz.any(axis=1), n - 1 - np.argmax(nz[:, ::-1], axis=1), 0)
+            itx["eob"][idx] = last if tp == 0 else np.maximum(last, 1)
+            coef[(cf_off[idx][:, None] + np.arange(n)[None, :]).ravel()] = c.ravel().astype(cdt)
+    s.itx_items, s.coef, s.n_coefs = itx, coef, int(per.sum())
+    s.itx_counts = np.array([int((tx == t).sum()) for t in range(19)], np.int32)
+    n_sb = g.sb128w * g.sb128h
+    s.masks = np.zeros(n_sb, lib.AV1_FILTER_DT); s.lr_masks = np.zeros(n_sb, lib.AV1_RESTORATION_DT)
+    s.levels = np.zeros((g.sb128h * 32, g.b4_stride, 4), np.uint8)
+    s.lut = calc_eih(0)
+    return s
+
+
 def random_film_grain(rng, lag=None, luma_points=True, csfl=0, uv_points=(True, True), overlap=None):
     """Random Dav1dFilmGrainData within the ranges of tests/checkasm/filmgrain.c:156-190."""
     d = lib.FilmGrainData()
@@ -529,8 +654,7 @@ class DeviceFrame:
         if self.ref_handle is None:
             self.ref_handle = C.c_void_p()
             lib.check(lib.frame_create(C.byref(self.ref_handle), C.byref(self.s.hdr), 1, 1, 1), "frame_create(ref)")
-        data = (C.c_void_p * 3)(*[p.ctypes.data for p in planes])
-        strides = (C.c_ssize_t * 2)(planes[0].strides[0], planes[1].strides[0])
+        data, strides = _plane_args(planes)
         lib.check(lib.frame_upload_planes(self.ref_handle, 0, data, strides))
         pl = lib.Planes()
         lib.check(lib.frame_stage_planes(self.ref_handle, 0, C.byref(pl)))
@@ -548,8 +672,7 @@ class DeviceFrame:
             lib.check(lib.frame_create(C.byref(hnd), C.byref(hdr), 1, 1, 1), "frame_create(ref)")
             self.ref_handles[slot] = hnd
         hnd = self.ref_handles[slot]
-        data = (C.c_void_p * 3)(*[p.ctypes.data for p in planes])
-        strides = (C.c_ssize_t * 2)(planes[0].strides[0], planes[1].strides[0])
+        data, strides = _plane_args(planes)
         lib.check(lib.frame_upload_planes(hnd, 0, data, strides))
         pl = lib.Planes()
         lib.check(lib.frame_stage_planes(hnd, 0, C.byref(pl)))

@@ -65,11 +65,14 @@ def product_frame(s, stages, start_planes=None, upload=1):
 
 
 def visible(s, planes):
-    return [planes[0][:s.h, :s.w], planes[1][:(s.h + 1) // 2, :(s.w + 1) // 2], planes[2][:(s.h + 1) // 2, :(s.w + 1) // 2]]
+    layout = getattr(s, "layout", 1)
+    ssx, ssy = int(layout != 3), int(layout == 1)
+    return [planes[0][:s.h, :s.w]] + [planes[p][:(s.h + ssy) >> ssy, :(s.w + ssx) >> ssx] for p in range(1, len(planes))]
 
 
 def assert_planes_equal(a, b, what=""):
-    for p in range(3):
+    assert len(a) == len(b)
+    for p in range(len(a)):
         if not np.array_equal(a[p], b[p]):
             bad = np.argwhere(a[p] != b[p])
             y, x = bad[0]

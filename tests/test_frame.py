@@ -102,6 +102,20 @@ def test_scaled_reference_blocks(rb, ref, w, h, bpc, rsize):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("layout", [0, 1, 2, 3])
+@pytest.mark.parametrize("w,h,bpc", [(192, 128, 8), (256, 160, 10), (176, 144, 12)])
+def test_recon_all_layouts(rb, ref, layout, w, h, bpc):
+    """Prediction (translational, compound incl. wedge / segmentation masks, warped, OBMC) and residual in 4:0:0,
+    4:2:0, 4:2:2 and 4:4:4: chroma block sizes, vectors, phases, mask sub-sampling and transform sizes all change."""
+    s = framegen.generate_recon_layout(w, h, bpc, layout, seed=w + 10 * layout + bpc, warp_frac=0.15)
+    assert len(s.comp_items) > 5 and len(s.warp_items) >= 2 and min(s.n_obmc) > 3
+    a = framecheck.oracle_frame(ref, s, R)
+    b = framecheck.product_frame(s, R)
+    assert len(a) == (1 if layout == 0 else 3)
+    framecheck.assert_planes_equal(a, b, f"layout {layout} {w}x{h}@{bpc}")
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("w,h,bpc", [(176, 144, 8), (208, 128, 10), (256, 192, 12)])
 def test_obmc_strips(rb, ref, w, h, bpc):
     """Overlapped block MC on top of translational, compound and warped neighbours (BASELINE config 5)."""
