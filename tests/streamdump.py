@@ -153,6 +153,7 @@ def dump_grain(path, max_frames=2):
 GOLDEN = os.path.join(ROOT, "tests", "golden", "streams.npz")
 GOLDEN_GRAIN = os.path.join(ROOT, "tests", "golden", "film_grain.npz")
 GOLDEN_SR = os.path.join(ROOT, "tests", "golden", "streams_sr.npz")
+GOLDEN_SIZES = os.path.join(ROOT, "tests", "golden", "streams_sizes.npz")
 
 
 def load_golden(path=GOLDEN):

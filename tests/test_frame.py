@@ -161,6 +161,40 @@ def test_config3_4k_10bit(rb, ref):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("bpc", [8, 10])
+def test_empty_batch_and_idle_filters(rb, bpc):
+    """No work items and every filter switched off in the header: each stage is a no-op, the picture comes back
+    untouched, and nothing reads the (empty) lists."""
+    import ctypes as C
+    s = framegen.generate(96, 80, bpc, seed=9)
+    start = framegen.recon_input_planes(s)
+    hdr = rb.FrameHeader.from_buffer_copy(bytes(s.hdr))
+    hdr.lf_level_y[0] = hdr.lf_level_y[1] = 0
+    for i in range(8):
+        hdr.cdef_y_strength[i] = hdr.cdef_uv_strength[i] = 0
+    for p in range(3):
+        hdr.lr_type[p] = rb.RESTORATION_NONE
+    f = C.c_void_p()
+    rb.check(rb.frame_create(C.byref(f), C.byref(hdr), 0, 0, 0))
+    try:
+        data, strides = framegen._plane_args(start)
+        rb.check(rb.frame_upload_planes(f, 0, data, strides))
+        for stages in (R, R | D | Cd | L):
+            rb.check(rb.frame_submit(f, 0, (C.c_int32 * 19)(), 0, stages, 1))
+            rb.check(rb.frame_wait(f))
+            assert rb.frame_last_launches(f) <= 3          # at most the CDEF pass-through
+            out = [np.zeros_like(p) for p in start]
+            data2, strides2 = framegen._plane_args(out)
+            rb.check(rb.frame_readback(f, data2, strides2))
+            framecheck.assert_planes_equal(framecheck.visible(s, start), framecheck.visible(s, out), f"idle stages {stages}")
+        # more items than the frame was created for is an error, not a crash
+        assert rb.frame_submit(f, 0, (C.c_int32 * 19)(), 5, R, 1) != 0
+        assert b"batch larger" in rb.last_error()
+    finally:
+        rb.frame_destroy(f)
+
+
+@pytest.mark.gpu
 def test_config5_4k_10bit(rb, ref):
     """BASELINE.json configs[4] (one GPU's stream): 50 % compound, 5 % warped, 10 % OBMC blocks, all
     post-filters and film grain on a 4K 10-bit frame."""

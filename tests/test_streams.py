@@ -75,6 +75,38 @@ def test_stream_postfilters_bit_exact(rb, key):
         d.close()
 
 
+# ---------------------------------------------------------------- the reference's picture-size sweep
+GOLD_SIZES = streamdump.load_golden(streamdump.GOLDEN_SIZES) if os.path.exists(streamdump.GOLDEN_SIZES) else []
+
+
+@pytest.mark.parametrize("key", [k for k, _ in GOLD_SIZES])
+def test_size_sweep_replays_through_the_reference_drivers(ref, key):
+    s = dict(GOLD_SIZES)[key]
+    cur = refharness.RefFrame(ref, s, 1)
+    try:
+        cur.load_filter_meta(); cur.set_planes(s.pre); cur.filter(s.stages)
+        _assert_equal(s, s.post, cur.get_planes(), key)
+    finally:
+        cur.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", [k for k, _ in GOLD_SIZES])
+def test_stream_size_sweep_bit_exact(rb, key):
+    """Pictures of 16 .. 66 and 196 .. 226 pixels a side (tests/dav1d-test-data/8-bit/size): every edge rule of the
+    post-filters at sizes that are not multiples of 8, 64 or 128."""
+    from rav1d_b200.synth import framegen
+    s = dict(GOLD_SIZES)[key]
+    d = framegen.DeviceFrame(s)
+    try:
+        d.load_batch()
+        d.upload(0, s.pre)
+        d.submit(s.stages); d.wait()
+        _assert_equal(s, s.post, d.readback(), key)
+    finally:
+        d.close()
+
+
 # ---------------------------------------------------------------- super-resolution frames of real streams
 GOLD_SR = streamdump.load_golden(streamdump.GOLDEN_SR) if os.path.exists(streamdump.GOLDEN_SR) else []
 

@@ -52,6 +52,12 @@ SR_STREAMS = [  # frames coded with super-resolution (8/10 bit, several scaling 
 ]
 
 
+SIZE_STREAMS = [  # the reference's picture-size sweep (tests/dav1d-test-data/8-bit/size): 16 .. 66 and 196 .. 226 pixels
+    (f"8-bit/size/av1-1-b8-01-size-{w}x{h}.ivf", 2)
+    for w, h in ((16, 16), (16, 18), (18, 34), (34, 16), (32, 66), (66, 18), (64, 64), (66, 66), (196, 198), (202, 210), (226, 196), (226, 226))
+]
+
+
 def main(streams=STREAMS, path=streamdump.GOLDEN, sr=False):
     blob, index = {}, []
     for rel, n in streams:
@@ -91,4 +97,5 @@ def main_grain():
 if __name__ == "__main__":
     main()
     main(SR_STREAMS, streamdump.GOLDEN_SR, sr=True)
+    main(SIZE_STREAMS, streamdump.GOLDEN_SIZES)
     main_grain()
