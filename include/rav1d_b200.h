@@ -397,6 +397,38 @@ int rb200_fguv_32x32xn(int layout, void *dst_row, const void *src_row, ptrdiff_t
                        const Rb200FilmGrainData *data, size_t pw, const uint8_t *scaling, const void *grain_lut,
                        int bh, int row_num, const void *luma_row, ptrdiff_t luma_stride, int uv_pl, int is_id,
                        int bitdepth_max);
+/* ---------------------------------------------------------- intra prediction */
+/* The per-call slots of Rav1dIntraPredDSPContext (src/ipred.rs:47-169; C: src/ipred.h:37-93, src/ipred_tmpl.c).
+ * First step of the "next" row f1: function-level parity of every predictor.  `topleft` points INTO the caller's
+ * edge buffer (left neighbours at negative, top neighbours at positive indices), as in the reference; the call
+ * mirrors topleft[-(h + min(w, h)) .. w + min(w, h)], the range the reference's predictors may read.
+ * enum IntraPredMode incl. the implementation modes (src/levels.rs:85-130): */
+enum { RB200_DC_PRED = 0, RB200_VERT_PRED, RB200_HOR_PRED, RB200_LEFT_DC_PRED, RB200_TOP_DC_PRED, RB200_DC_128_PRED,
+       RB200_Z1_PRED, RB200_Z2_PRED, RB200_Z3_PRED, RB200_SMOOTH_PRED, RB200_SMOOTH_V_PRED, RB200_SMOOTH_H_PRED,
+       RB200_PAETH_PRED, RB200_FILTER_PRED, RB200_N_IMPL_INTRA_PRED_MODES };
+typedef void (*rb200_angular_ipred_fn)(void *dst, ptrdiff_t stride, const void *topleft, int width, int height, int angle,
+                                       int max_width, int max_height, int bitdepth_max);
+typedef void (*rb200_cfl_ac_fn)(int16_t *ac, const void *y, ptrdiff_t stride, int w_pad, int h_pad, int cw, int ch);
+typedef void (*rb200_cfl_pred_fn)(void *dst, ptrdiff_t stride, const void *topleft, int width, int height, const int16_t *ac,
+                                  int alpha, int bitdepth_max);
+typedef void (*rb200_pal_pred_fn)(void *dst, ptrdiff_t stride, const void *pal, const uint8_t *idx, int w, int h);
+typedef struct Rb200IntraPredDSPContext {
+    rb200_angular_ipred_fn intra_pred[RB200_N_IMPL_INTRA_PRED_MODES];
+    rb200_cfl_ac_fn cfl_ac[3];          /* [layout - 1] = 420, 422, 444 */
+    rb200_cfl_pred_fn cfl_pred[6];      /* DC, LEFT_DC, TOP_DC, DC_128 are set */
+    rb200_pal_pred_fn pal_pred;
+} Rb200IntraPredDSPContext;
+void rb200_intra_pred_dsp_init(Rb200IntraPredDSPContext *c, int bpc);
+/* angle: the reference's packed argument (angle | is_smooth << 9 | enable_intra_edge_filter << 10; the filter set for
+ * RB200_FILTER_PRED) */
+int rb200_ipred(int mode, void *dst, ptrdiff_t stride, const void *topleft, int width, int height, int angle,
+                int max_width, int max_height, int bitdepth_max);
+int rb200_cfl_ac(int ss /* layout - 1 */, int16_t *ac, const void *y, ptrdiff_t stride, int w_pad, int h_pad, int cw,
+                 int ch, int bitdepth_max);
+int rb200_cfl_pred(int mode, void *dst, ptrdiff_t stride, const void *topleft, int width, int height, const int16_t *ac,
+                   int alpha, int bitdepth_max);
+int rb200_pal_pred(void *dst, ptrdiff_t stride, const void *pal, const uint8_t *idx, int w, int h, int bitdepth_max);
+
 /* generate_scaling, src/fg_apply.rs:14-72: piecewise-linear scaling LUT (256 or 4096 bytes). */
 int rb200_generate_scaling(int bitdepth, const uint8_t points[][2], int num, uint8_t *scaling);
 

@@ -15,6 +15,7 @@
  *   Dav1dCdefDSPContext             src/cdef.h:64-67
  *   Dav1dLoopRestorationDSPContext  src/looprestoration.h:72-75
  *   Dav1dFilmGrainDSPContext        src/filmgrain.h:74-80
+ *   Dav1dIntraPredDSPContext        src/ipred.h:82-93  (Rust: src/ipred.rs:164-169)
  */
 #include "config.h"
 
@@ -40,6 +41,7 @@ typedef struct { fnptr loop_filter_sb[2][2]; } LfCtx;
 typedef struct { fnptr dir; fnptr fb[3]; } CdefCtx;
 typedef struct { fnptr wiener[2]; fnptr sgr[3]; } LrCtx;
 typedef struct { fnptr generate_grain_y; fnptr generate_grain_uv[3]; fnptr fgy_32x32xn; fnptr fguv_32x32xn[3]; } FgCtx;
+typedef struct { fnptr intra_pred[N_IMPL_INTRA_PRED_MODES]; fnptr cfl_ac[3]; fnptr cfl_pred[DC_128_PRED + 1]; fnptr pal_pred; } IpredCtx;
 
 void dav1d_itx_dsp_init_8bpc(ItxCtx *c, int bpc);
 void dav1d_itx_dsp_init_16bpc(ItxCtx *c, int bpc);
@@ -53,10 +55,12 @@ void dav1d_loop_restoration_dsp_init_8bpc(LrCtx *c, int bpc);
 void dav1d_loop_restoration_dsp_init_16bpc(LrCtx *c, int bpc);
 void dav1d_film_grain_dsp_init_8bpc(FgCtx *c);
 void dav1d_film_grain_dsp_init_16bpc(FgCtx *c);
+void dav1d_intra_pred_dsp_init_8bpc(IpredCtx *c);
+void dav1d_intra_pred_dsp_init_16bpc(IpredCtx *c);
 
 static struct Tables {
     int ready;
-    ItxCtx itx[3]; McCtx mc[2]; LfCtx lf[2]; CdefCtx cdef[2]; LrCtx lr[3]; FgCtx fg[2];
+    ItxCtx itx[3]; McCtx mc[2]; LfCtx lf[2]; CdefCtx cdef[2]; LrCtx lr[3]; FgCtx fg[2]; IpredCtx ipred[2];
 } T;
 
 static void init_once(void) {
@@ -75,6 +79,8 @@ static void init_once(void) {
     dav1d_loop_restoration_dsp_init_16bpc(&T.lr[2], 12);
     dav1d_film_grain_dsp_init_8bpc(&T.fg[0]);
     dav1d_film_grain_dsp_init_16bpc(&T.fg[1]);
+    dav1d_intra_pred_dsp_init_8bpc(&T.ipred[0]);
+    dav1d_intra_pred_dsp_init_16bpc(&T.ipred[1]);
     dav1d_init_wedge_masks();
     T.ready = 1;
 }
@@ -240,6 +246,33 @@ void ref_fguv(int ss, void *dst, const void *src, ptrdiff_t stride, const Dav1dF
     else ((void (*)(void *, const void *, ptrdiff_t, const Dav1dFilmGrainData *, size_t, const uint8_t *, const void *, int, int, const void *, ptrdiff_t, int, int, int))
               T.fg[1].fguv_32x32xn[ss])(dst, src, stride, d, pw, scaling, grain_lut, bh, row_num, luma, luma_stride, uv_pl, is_id, bdmax);
 }
+/* ------------------------------ intra prediction ------------------------ */
+/* mode: enum IntraPredMode incl. the implementation modes (src/levels.h:85-107): DC 0, VERT 1, HOR 2, ..., Z1 = 6 .. */
+void ref_ipred(int mode, void *dst, ptrdiff_t stride, const void *topleft, int w, int h, int angle, int max_w, int max_h, int bdmax) {
+    init_once();
+    if (bdmax > 255) ((void (*)(void *, ptrdiff_t, const void *, int, int, int, int, int, int))T.ipred[1].intra_pred[mode])(dst, stride, topleft, w, h, angle, max_w, max_h, bdmax);
+    else ((void (*)(void *, ptrdiff_t, const void *, int, int, int, int, int))T.ipred[0].intra_pred[mode])(dst, stride, topleft, w, h, angle, max_w, max_h);
+}
+void ref_cfl_ac(int ss /* layout - 1 */, int16_t *ac, const void *y, ptrdiff_t stride, int w_pad, int h_pad, int cw, int ch, int bdmax) {
+    init_once();
+    ((void (*)(int16_t *, const void *, ptrdiff_t, int, int, int, int))T.ipred[bdmax > 255].cfl_ac[ss])(ac, y, stride, w_pad, h_pad, cw, ch);
+}
+void ref_cfl_pred(int mode, void *dst, ptrdiff_t stride, const void *topleft, int w, int h, const int16_t *ac, int alpha, int bdmax) {
+    init_once();
+    if (bdmax > 255) ((void (*)(void *, ptrdiff_t, const void *, int, int, const int16_t *, int, int))T.ipred[1].cfl_pred[mode])(dst, stride, topleft, w, h, ac, alpha, bdmax);
+    else ((void (*)(void *, ptrdiff_t, const void *, int, int, const int16_t *, int))T.ipred[0].cfl_pred[mode])(dst, stride, topleft, w, h, ac, alpha);
+}
+void ref_pal_pred(void *dst, ptrdiff_t stride, const void *pal, const uint8_t *idx, int w, int h, int bdmax) {
+    init_once();
+    ((void (*)(void *, ptrdiff_t, const void *, const uint8_t *, int, int))T.ipred[bdmax > 255].pal_pred)(dst, stride, pal, idx, w, h);
+}
+int ref_ipred_mode_ids(int *out /* DC, VERT, HOR, PAETH, SMOOTH, SMOOTH_V, SMOOTH_H, Z1, Z2, Z3, LEFT_DC, TOP_DC, DC_128, FILTER */) {
+    const int ids[14] = { DC_PRED, VERT_PRED, HOR_PRED, PAETH_PRED, SMOOTH_PRED, SMOOTH_V_PRED, SMOOTH_H_PRED, Z1_PRED, Z2_PRED, Z3_PRED,
+                          LEFT_DC_PRED, TOP_DC_PRED, DC_128_PRED, FILTER_PRED };
+    for (int i = 0; i < 14; i++) out[i] = ids[i];
+    return N_IMPL_INTRA_PRED_MODES;
+}
+
 size_t ref_sizeof_film_grain_data(void) { return sizeof(Dav1dFilmGrainData); }
 
 /* ------------------------- constant tables ----------------------------- */
@@ -251,6 +284,7 @@ const void *ref_table(const char *name, size_t *size) {
     TAB(sgr_params) TAB(sgr_x_by_x) TAB(cdef_directions)
     TAB(obmc_masks) TAB(gaussian_sequence) TAB(txfm_dimensions)
     TAB(block_dimensions) TAB(filter_2d) TAB(filter_dir)
+    TAB(sm_weights) TAB(dr_intra_derivative) TAB(filter_intra_taps)
 #undef TAB
     *size = 0;
     return NULL;

@@ -1,0 +1,486 @@
+// Intra prediction for sm_100a: the per-call slots of Rav1dIntraPredDSPContext
+// { intra_pred[14], cfl_ac[3], cfl_pred[6], pal_pred } (src/ipred.rs:164-169; bodies src/ipred.rs:171-1500 ==
+// src/ipred_tmpl.c:39-735).  First step of SURVEY row f1: function-level parity of every predictor; the
+// frame-level wavefront over transform blocks is the next step.
+//
+// One CTA predicts one block.  The caller's edge (`topleft[-(h + min(w, h)) .. w + min(w, h)]`, everything the
+// reference may read) is mirrored into shared memory; the directional predictors prepare their filtered or
+// upsampled edge there in parallel (each output sample of filter_edge / upsample_edge is independent), then
+// every pixel is one thread's closed-form lookup -- the reference's running xpos / ypos accumulators become
+// dx * (y + 1) etc.  Filter-intra, the only predictor with a dependency inside the block, runs as a wavefront
+// over its 4x2 sub-blocks (a sub-block needs the ones to its left, above and above-left).
+#include "common.cuh"
+#include "tables.cuh"
+
+namespace rb200 {
+
+// enum IntraPredMode with the implementation modes (src/levels.rs:85-130)
+enum { IP_DC = 0, IP_VERT, IP_HOR, IP_LEFT_DC, IP_TOP_DC, IP_DC_128, IP_Z1, IP_Z2, IP_Z3, IP_SMOOTH, IP_SMOOTH_V, IP_SMOOTH_H,
+       IP_PAETH, IP_FILTER, IP_N_MODES };
+
+constexpr int IP_EC = 128;        // index of topleft inside the mirrored edge (the reference's edge[257] / topleft = edge + 128)
+constexpr int IP_EDGE = 2 * IP_EC + 1;
+
+__device__ __forceinline__ int ip_filter_strength(int wh, int angle, int is_sm) {   // src/ipred_tmpl.c:327-360
+    if (is_sm) {
+        if (wh <= 8) { if (angle >= 64) return 2; if (angle >= 40) return 1; }
+        else if (wh <= 16) { if (angle >= 48) return 2; if (angle >= 20) return 1; }
+        else if (wh <= 24) { if (angle >= 4) return 3; }
+        else return 3;
+    } else {
+        if (wh <= 8) { if (angle >= 56) return 1; }
+        else if (wh <= 16) { if (angle >= 40) return 1; }
+        else if (wh <= 24) { if (angle >= 32) return 3; if (angle >= 16) return 2; if (angle >= 8) return 1; }
+        else if (wh <= 32) { if (angle >= 32) return 3; if (angle >= 4) return 2; return 1; }
+        else return 3;
+    }
+    return 0;
+}
+__device__ __forceinline__ int ip_upsample(int wh, int angle, int is_sm) { return angle < 40 && wh <= (16 >> is_sm); }
+
+// out[i], i < sz: the 5-tap smoothing of in[] inside [lim_from, lim_to), a clamped copy outside (filter_edge, :362-385)
+template <typename P>
+__device__ void ip_filter_edge(P *out, int sz, int lim_from, int lim_to, const P *in, int from, int to, int strength) {
+    const int k0 = strength == 3 ? 2 : 0, k1 = strength == 1 ? 4 : (strength == 2 ? 5 : 4), k2 = strength == 1 ? 8 : (strength == 2 ? 6 : 4);
+    for (int i = threadIdx.x; i < sz; i += blockDim.x) {
+        int v;
+        if (i < imin(sz, lim_from) || i >= imin(lim_to, sz)) {
+            v = in[iclip(i, from, to - 1)];
+        } else {
+            const int s = k0 * (in[iclip(i - 2, from, to - 1)] + in[iclip(i + 2, from, to - 1)]) +
+                          k1 * (in[iclip(i - 1, from, to - 1)] + in[iclip(i + 1, from, to - 1)]) + k2 * in[iclip(i, from, to - 1)];
+            v = (s + 8) >> 4;
+        }
+        out[i] = (P)v;
+    }
+}
+// out[0 .. 2 * hsz - 2]: in[] with a (-1, 9, 9, -1) / 16 sample between neighbours (upsample_edge, :391-406)
+template <typename P>
+__device__ void ip_upsample_edge(P *out, int hsz, const P *in, int from, int to, int bdmax) {
+    for (int i = threadIdx.x; i < hsz; i += blockDim.x) {
+        out[2 * i] = in[iclip(i, from, to - 1)];
+        if (i < hsz - 1) {
+            const int s = 9 * (in[iclip(i, from, to - 1)] + in[iclip(i + 1, from, to - 1)]) - in[iclip(i - 1, from, to - 1)] -
+                          in[iclip(i + 2, from, to - 1)];
+            out[2 * i + 1] = (P)iclip((s + 8) >> 4, 0, bdmax);
+        }
+    }
+}
+
+template <typename BD>
+__global__ void __launch_bounds__(256)
+ipred_kernel(int mode, uint8_t *dst8, int64_t stride, const typename BD::pixel *__restrict__ edge_in, int lo, int hi, int w,
+             int h, int angle, int max_w, int max_h, int bdmax) {
+    using pixel = typename BD::pixel;
+    __shared__ pixel e_s[IP_EDGE];           // caller's edge, topleft at e_s[IP_EC]
+    __shared__ pixel work[2 * IP_EC + 2];    // prepared edge of the directional modes
+    __shared__ pixel tile[32 * 32];          // filter-intra block
+    __shared__ int dc_s;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < lo + hi + 1; i += blockDim.x) e_s[IP_EC - lo + i] = edge_in[i];
+    __syncthreads();
+    const pixel *tl = e_s + IP_EC;
+    auto put = [&](int x, int y, int v) { ((pixel *)(dst8 + (int64_t)y * stride))[x] = (pixel)v; };
+    const int n = w * h;
+
+    switch (mode) {
+    case IP_DC: case IP_TOP_DC: case IP_LEFT_DC: case IP_DC_128: {
+        if (tid == 0) {
+            unsigned dc;
+            if (mode == IP_DC_128) {
+                dc = BD::hbd ? (unsigned)(bdmax + 1) >> 1 : 128;
+            } else if (mode == IP_TOP_DC) {
+                dc = w >> 1;
+                for (int i = 0; i < w; i++) dc += tl[1 + i];
+                dc >>= ulog2(w);
+            } else if (mode == IP_LEFT_DC) {
+                dc = h >> 1;
+                for (int i = 0; i < h; i++) dc += tl[-(1 + i)];
+                dc >>= ulog2(h);
+            } else {   // dc_gen, src/ipred_tmpl.c:150-166
+                dc = (w + h) >> 1;
+                for (int i = 0; i < w; i++) dc += tl[1 + i];
+                for (int i = 0; i < h; i++) dc += tl[-(1 + i)];
+                dc >>= __ffs(w + h) - 1;
+                if (w != h) {
+                    const bool x4 = w > h * 2 || h > w * 2;
+                    dc *= BD::hbd ? (x4 ? 0x6667u : 0xAAABu) : (x4 ? 0x3334u : 0x5556u);
+                    dc >>= BD::hbd ? 17 : 16;
+                }
+            }
+            dc_s = (int)dc;
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += blockDim.x) put(i % w, i / w, dc_s);
+        break;
+    }
+    case IP_VERT:
+        for (int i = tid; i < n; i += blockDim.x) put(i % w, i / w, tl[1 + i % w]);
+        break;
+    case IP_HOR:
+        for (int i = tid; i < n; i += blockDim.x) put(i % w, i / w, tl[-(1 + i / w)]);
+        break;
+    case IP_PAETH:
+        for (int i = tid; i < n; i += blockDim.x) {
+            const int x = i % w, y = i / w;
+            const int left = tl[-(y + 1)], top = tl[1 + x], topleft = tl[0];
+            const int base = left + top - topleft;
+            const int ld = abs(left - base), td = abs(top - base), tld = abs(topleft - base);
+            put(x, y, ld <= td && ld <= tld ? left : (td <= tld ? top : topleft));
+        }
+        break;
+    case IP_SMOOTH: case IP_SMOOTH_V: case IP_SMOOTH_H: {
+        const uint8_t *wh = tab::k_sm_weights + w, *wv = tab::k_sm_weights + h;
+        const int right = tl[w], bottom = tl[-h];
+        for (int i = tid; i < n; i += blockDim.x) {
+            const int x = i % w, y = i / w;
+            int v;
+            if (mode == IP_SMOOTH)
+                v = (wv[y] * tl[1 + x] + (256 - wv[y]) * bottom + wh[x] * tl[-(1 + y)] + (256 - wh[x]) * right + 256) >> 9;
+            else if (mode == IP_SMOOTH_V)
+                v = (wv[y] * tl[1 + x] + (256 - wv[y]) * bottom + 128) >> 8;
+            else
+                v = (wh[x] * tl[-(1 + y)] + (256 - wh[x]) * right + 128) >> 8;
+            put(x, y, v);
+        }
+        break;
+    }
+    case IP_Z1: {   // src/ipred_tmpl.c:408-460
+        const int is_sm = (angle >> 9) & 1, eief = angle >> 10;
+        angle &= 511;
+        int dx = tab::k_dr_intra_derivative[angle >> 1];
+        const int ups = eief ? ip_upsample(w + h, 90 - angle, is_sm) : 0;
+        const pixel *top;
+        int max_base_x;
+        if (ups) {
+            ip_upsample_edge(work, w + h, tl + 1, -1, w + imin(w, h), bdmax);
+            top = work; max_base_x = 2 * (w + h) - 2; dx <<= 1;
+        } else {
+            const int fs = eief ? ip_filter_strength(w + h, 90 - angle, is_sm) : 0;
+            if (fs) {
+                ip_filter_edge(work, w + h, 0, w + h, tl + 1, -1, w + imin(w, h), fs);
+                top = work; max_base_x = w + h - 1;
+            } else {
+                top = tl + 1; max_base_x = w + imin(w, h) - 1;
+            }
+        }
+        __syncthreads();
+        const int inc = 1 + ups;
+        for (int i = tid; i < n; i += blockDim.x) {
+            const int x = i % w, y = i / w;
+            const int xpos = dx * (y + 1), frac = xpos & 0x3E, base = (xpos >> 6) + inc * x;
+            put(x, y, base < max_base_x ? (top[base] * (64 - frac) + top[base + 1] * frac + 32) >> 6 : top[max_base_x]);
+        }
+        break;
+    }
+    case IP_Z2: {   // src/ipred_tmpl.c:462-540
+        const int is_sm = (angle >> 9) & 1, eief = angle >> 10;
+        angle &= 511;
+        int dy = tab::k_dr_intra_derivative[(angle - 90) >> 1], dx = tab::k_dr_intra_derivative[(180 - angle) >> 1];
+        const int ul = eief ? ip_upsample(w + h, 180 - angle, is_sm) : 0;
+        const int ua = eief ? ip_upsample(w + h, angle - 90, is_sm) : 0;
+        pixel *t2 = work + IP_EC;                 // the prepared corner: t2[0] = topleft
+        if (ua) {
+            ip_upsample_edge(t2, w + 1, tl, 0, w + 1, bdmax);
+            dx <<= 1;
+        } else {
+            const int fs = eief ? ip_filter_strength(w + h, angle - 90, is_sm) : 0;
+            if (fs) ip_filter_edge(t2 + 1, w, 0, max_w, tl + 1, -1, w, fs);
+            else for (int i = tid; i < w; i += blockDim.x) t2[1 + i] = tl[1 + i];
+        }
+        if (ul) {
+            ip_upsample_edge(t2 - 2 * h, h + 1, tl - h, 0, h + 1, bdmax);
+            dy <<= 1;
+        } else {
+            const int fs = eief ? ip_filter_strength(w + h, 180 - angle, is_sm) : 0;
+            if (fs) ip_filter_edge(t2 - h, h, h - max_h, h, tl - h, 0, h + 1, fs);
+            else for (int i = tid; i < h; i += blockDim.x) t2[-h + i] = tl[-h + i];
+        }
+        __syncthreads();
+        if (tid == 0) t2[0] = tl[0];
+        __syncthreads();
+        const int incx = 1 + ua;
+        const pixel *left = t2 - (1 + ul);
+        for (int i = tid; i < n; i += blockDim.x) {
+            const int x = i % w, y = i / w;
+            const int xpos = ((1 + ua) << 6) - dx * (y + 1);
+            const int base_x = (xpos >> 6) + incx * x;
+            int v;
+            if (base_x >= 0) {
+                const int fx = xpos & 0x3E;
+                v = t2[base_x] * (64 - fx) + t2[base_x + 1] * fx;
+            } else {
+                const int ypos = (y << (6 + ul)) - dy * (x + 1);
+                const int base_y = ypos >> 6, fy = ypos & 0x3E;
+                v = left[-base_y] * (64 - fy) + left[-(base_y + 1)] * fy;
+            }
+            put(x, y, (v + 32) >> 6);
+        }
+        break;
+    }
+    case IP_Z3: {   // src/ipred_tmpl.c:542-600
+        const int is_sm = (angle >> 9) & 1, eief = angle >> 10;
+        angle &= 511;
+        int dy = tab::k_dr_intra_derivative[(270 - angle) >> 1];
+        const int ups = eief ? ip_upsample(w + h, angle - 180, is_sm) : 0;
+        const pixel *left;
+        int max_base_y;
+        if (ups) {
+            ip_upsample_edge(work, w + h, tl - (w + h), imax(w - h, 0), w + h + 1, bdmax);
+            left = work + 2 * (w + h) - 2; max_base_y = 2 * (w + h) - 2; dy <<= 1;
+        } else {
+            const int fs = eief ? ip_filter_strength(w + h, angle - 180, is_sm) : 0;
+            if (fs) {
+                ip_filter_edge(work, w + h, 0, w + h, tl - (w + h), imax(w - h, 0), w + h + 1, fs);
+                left = work + w + h - 1; max_base_y = w + h - 1;
+            } else {
+                left = tl - 1; max_base_y = h + imin(w, h) - 1;
+            }
+        }
+        __syncthreads();
+        const int inc = 1 + ups;
+        for (int i = tid; i < n; i += blockDim.x) {
+            const int x = i % w, y = i / w;
+            const int ypos = dy * (x + 1), frac = ypos & 0x3E, base = (ypos >> 6) + inc * y;
+            put(x, y, base < max_base_y ? (left[-base] * (64 - frac) + left[-(base + 1)] * frac + 32) >> 6 : left[-max_base_y]);
+        }
+        break;
+    }
+    case IP_FILTER: {   // src/ipred_tmpl.c:618-655; up to 32x32
+        const int8_t *flt = tab::k_filter_intra_taps + (angle & 511) * 64;
+        const int nbx = w >> 2, nby = h >> 1;
+        for (int t = 0; t < nbx + nby - 1; t++) {
+            // sub-blocks on the anti-diagonal bx + by = t; 8 threads (outputs) per sub-block
+            const int sb = tid >> 3, o = tid & 7;
+            for (int by = sb; by < nby; by += blockDim.x >> 3) {
+                const int bx = t - by;
+                if (bx < 0 || bx >= nbx) continue;
+                const int x0 = 4 * bx, y0 = 2 * by;
+                auto px = [&](int x, int y) -> int {   // reconstructed neighbourhood: the edge outside the block, the tile inside
+                    if (y < 0) return tl[1 + x];          // x = -1 gives topleft
+                    if (x < 0) return tl[-(1 + y)];
+                    return tile[y * 32 + x];
+                };
+                const int p0 = px(x0 - 1, y0 - 1), p1 = px(x0, y0 - 1), p2 = px(x0 + 1, y0 - 1), p3 = px(x0 + 2, y0 - 1),
+                          p4 = px(x0 + 3, y0 - 1), p5 = px(x0 - 1, y0), p6 = px(x0 - 1, y0 + 1);
+                const int acc = flt[o] * p0 + flt[8 + o] * p1 + flt[16 + o] * p2 + flt[24 + o] * p3 + flt[32 + o] * p4 +
+                                flt[40 + o] * p5 + flt[48 + o] * p6;
+                tile[(y0 + (o >> 2)) * 32 + x0 + (o & 3)] = (pixel)iclip((acc + 8) >> 4, 0, bdmax);
+            }
+            __syncthreads();
+        }
+        for (int i = tid; i < n; i += blockDim.x) put(i % w, i / w, tile[(i / w) * 32 + i % w]);
+        break;
+    }
+    default: break;
+    }
+}
+
+// cfl_ac (src/ipred_tmpl.c:657-703): sub-sampled luma, edge replication of the padded part, zero mean
+template <typename BD>
+__global__ void __launch_bounds__(256)
+cfl_ac_kernel(int16_t *__restrict__ ac, const uint8_t *__restrict__ ypx, int64_t stride, int w_pad, int h_pad, int width,
+              int height, int ss_hor, int ss_ver) {
+    using pixel = typename BD::pixel;
+    __shared__ int16_t a[32 * 32];
+    __shared__ int red[8];
+    const int tid = threadIdx.x, n = width * height;
+    const int vw = width - 4 * w_pad, vh = height - 4 * h_pad;
+    int part = 0;
+    for (int i = tid; i < n; i += blockDim.x) {
+        const int x = imin(i % width, vw - 1), y = imin(i / width, vh - 1);     // padding repeats the last valid column / row
+        const pixel *p = (const pixel *)(ypx + (int64_t)(y << ss_ver) * stride) + (x << ss_hor);
+        int s = p[0];
+        if (ss_hor) s += p[1];
+        if (ss_ver) {
+            const pixel *q = (const pixel *)((const uint8_t *)p + stride);
+            s += q[0];
+            if (ss_hor) s += q[1];
+        }
+        s <<= 1 + !ss_ver + !ss_hor;
+        a[i] = (int16_t)s;
+        part += s;
+    }
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((tid & 31) == 0) red[tid >> 5] = part;
+    __syncthreads();
+    const int log2sz = ulog2(width) + ulog2(height);
+    int sum = (1 << log2sz) >> 1;
+    for (int k = 0; k < 8; k++) sum += red[k];
+    sum >>= log2sz;
+    for (int i = tid; i < n; i += blockDim.x) ac[i] = (int16_t)(a[i] - sum);
+}
+
+// cfl_pred (src/ipred_tmpl.c:71-84 with the dc of the four variants)
+template <typename BD>
+__global__ void __launch_bounds__(256)
+cfl_pred_kernel(int mode, uint8_t *dst8, int64_t stride, const typename BD::pixel *__restrict__ edge_in, int lo, int w, int h,
+                const int16_t *__restrict__ ac, int alpha, int bdmax) {
+    using pixel = typename BD::pixel;
+    __shared__ int dc_s;
+    const pixel *tl = edge_in + lo;
+    if (threadIdx.x == 0) {
+        unsigned dc;
+        if (mode == IP_DC_128) {
+            dc = BD::hbd ? (unsigned)(bdmax + 1) >> 1 : 128;
+        } else if (mode == IP_TOP_DC) {
+            dc = w >> 1;
+            for (int i = 0; i < w; i++) dc += tl[1 + i];
+            dc >>= ulog2(w);
+        } else if (mode == IP_LEFT_DC) {
+            dc = h >> 1;
+            for (int i = 0; i < h; i++) dc += tl[-(1 + i)];
+            dc >>= ulog2(h);
+        } else {
+            dc = (w + h) >> 1;
+            for (int i = 0; i < w; i++) dc += tl[1 + i];
+            for (int i = 0; i < h; i++) dc += tl[-(1 + i)];
+            dc >>= __ffs(w + h) - 1;
+            if (w != h) {
+                const bool x4 = w > h * 2 || h > w * 2;
+                dc *= BD::hbd ? (x4 ? 0x6667u : 0xAAABu) : (x4 ? 0x3334u : 0x5556u);
+                dc >>= BD::hbd ? 17 : 16;
+            }
+        }
+        dc_s = (int)dc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
+        const int diff = alpha * ac[i];
+        const int m = (abs(diff) + 32) >> 6;
+        ((pixel *)(dst8 + (int64_t)(i / w) * stride))[i % w] = (pixel)iclip(dc_s + (diff < 0 ? -m : m), 0, bdmax);
+    }
+}
+
+template <typename BD>
+__global__ void __launch_bounds__(256)
+pal_pred_kernel(uint8_t *dst8, int64_t stride, const typename BD::pixel *__restrict__ pal, const uint8_t *__restrict__ idx, int w,
+                int h) {
+    using pixel = typename BD::pixel;
+    for (int i = threadIdx.x + blockIdx.x * blockDim.x; i < w * h; i += blockDim.x * gridDim.x)
+        ((pixel *)(dst8 + (int64_t)(i / w) * stride))[i % w] = pal[idx[i] & 7];
+}
+
+}  // namespace rb200
+
+using namespace rb200;
+
+namespace {
+inline size_t ip_px(int bdmax) { return bdmax > 255 ? 2 : 1; }
+inline bool ip_size_ok(int v) { return v == 4 || v == 8 || v == 16 || v == 32 || v == 64; }
+}  // namespace
+
+// ---------------------------------------------------------------- C ABI (per call)
+extern "C" int rb200_ipred(int mode, void *dst, ptrdiff_t stride, const void *topleft, int w, int h, int angle, int max_w,
+                           int max_h, int bdmax) {
+    if (mode < 0 || mode >= IP_N_MODES || !dst || !topleft || !ip_size_ok(w) || !ip_size_ok(h) ||
+        (mode == IP_FILTER && (w > 32 || h > 32 || (angle & 511) > 4)))
+        return set_error(-22, "ipred: bad argument");
+    const int a = angle & 511;
+    if ((mode == IP_Z1 && !(a > 0 && a < 90)) || (mode == IP_Z2 && !(a > 90 && a < 180)) || (mode == IP_Z3 && !(a > 180 && a < 270)))
+        return set_error(-22, "ipred: angle %d outside the range of the directional mode", a);
+    const size_t px = ip_px(bdmax);
+    const int lo = h + (w < h ? w : h), hi = w + (w < h ? w : h);   // everything the reference's predictors may read
+    HostCall hc(2 * DevRect::bytes_for(w * px, h) + (size_t)(lo + hi + 1) * px * 2 + 256);
+    DevRect drect;
+    if (hc.rect_up(drect, dst, stride, w * px, h)) return hc.err;
+    const void *de = hc.up((const uint8_t *)topleft - (size_t)lo * px, (size_t)(lo + hi + 1) * px);
+    if (hc.err) return hc.err;
+    if (bdmax > 255) ipred_kernel<BD16><<<1, 256, 0, hc.stream()>>>(mode, drect.dptr, drect.dpitch, (const uint16_t *)de, lo, hi, w, h, angle, max_w, max_h, bdmax);
+    else ipred_kernel<BD8><<<1, 256, 0, hc.stream()>>>(mode, drect.dptr, drect.dpitch, (const uint8_t *)de, lo, hi, w, h, angle, max_w, max_h, bdmax);
+    hc.rect_down(drect);
+    if (hc.sync()) return hc.err;
+    drect.finish(dst);
+    return 0;
+}
+
+extern "C" int rb200_cfl_ac(int ss, int16_t *ac, const void *ypx, ptrdiff_t stride, int w_pad, int h_pad, int cw, int ch,
+                            int bdmax) {
+    if (ss < 0 || ss > 2 || !ac || !ypx || cw < 4 || ch < 4 || cw > 32 || ch > 32 || (cw & (cw - 1)) || (ch & (ch - 1)) ||
+        w_pad < 0 || h_pad < 0 || w_pad * 4 >= cw || h_pad * 4 >= ch)
+        return set_error(-22, "cfl_ac: bad argument");
+    const int ss_hor = ss != 2, ss_ver = ss == 0;          // ss = layout - 1: 0 = 4:2:0, 1 = 4:2:2, 2 = 4:4:4
+    const size_t px = ip_px(bdmax);
+    const int lw = (cw - 4 * w_pad) << ss_hor, lh = (ch - 4 * h_pad) << ss_ver;
+    HostCall hc(2 * DevRect::bytes_for(lw * px, lh) + (size_t)cw * ch * 4 + 256);
+    DevRect yrect;
+    if (hc.rect_up(yrect, ypx, stride, lw * px, lh)) return hc.err;
+    int16_t *dac = (int16_t *)hc.dev((size_t)cw * ch * 2);
+    if (hc.err) return hc.err;
+    if (bdmax > 255) cfl_ac_kernel<BD16><<<1, 256, 0, hc.stream()>>>(dac, yrect.dptr, yrect.dpitch, w_pad, h_pad, cw, ch, ss_hor, ss_ver);
+    else cfl_ac_kernel<BD8><<<1, 256, 0, hc.stream()>>>(dac, yrect.dptr, yrect.dpitch, w_pad, h_pad, cw, ch, ss_hor, ss_ver);
+    void *s = hc.down(dac, (size_t)cw * ch * 2);
+    if (hc.sync()) return hc.err;
+    memcpy(ac, s, (size_t)cw * ch * 2);
+    return 0;
+}
+
+extern "C" int rb200_cfl_pred(int mode, void *dst, ptrdiff_t stride, const void *topleft, int w, int h, const int16_t *ac,
+                              int alpha, int bdmax) {
+    if ((mode != IP_DC && mode != IP_LEFT_DC && mode != IP_TOP_DC && mode != IP_DC_128) || !dst || !topleft || !ac ||
+        !ip_size_ok(w) || !ip_size_ok(h) || w > 32 || h > 32)
+        return set_error(-22, "cfl_pred: bad argument");
+    const size_t px = ip_px(bdmax);
+    HostCall hc(2 * DevRect::bytes_for(w * px, h) + (size_t)(w + h + 1) * px * 2 + (size_t)w * h * 4 + 256);
+    DevRect drect;
+    if (hc.rect_up(drect, dst, stride, w * px, h)) return hc.err;
+    const void *de = hc.up((const uint8_t *)topleft - (size_t)h * px, (size_t)(w + h + 1) * px);
+    const int16_t *dac = (const int16_t *)hc.up(ac, (size_t)w * h * 2);
+    if (hc.err) return hc.err;
+    if (bdmax > 255) cfl_pred_kernel<BD16><<<1, 256, 0, hc.stream()>>>(mode, drect.dptr, drect.dpitch, (const uint16_t *)de, h, w, h, dac, alpha, bdmax);
+    else cfl_pred_kernel<BD8><<<1, 256, 0, hc.stream()>>>(mode, drect.dptr, drect.dpitch, (const uint8_t *)de, h, w, h, dac, alpha, bdmax);
+    hc.rect_down(drect);
+    if (hc.sync()) return hc.err;
+    drect.finish(dst);
+    return 0;
+}
+
+extern "C" int rb200_pal_pred(void *dst, ptrdiff_t stride, const void *pal, const uint8_t *idx, int w, int h, int bdmax) {
+    if (!dst || !pal || !idx || w < 4 || h < 4 || w > 64 || h > 64) return set_error(-22, "pal_pred: bad argument");
+    const size_t px = ip_px(bdmax);
+    HostCall hc(2 * DevRect::bytes_for(w * px, h) + (size_t)w * h * 2 + 64 + 256);
+    DevRect drect;
+    if (hc.rect_up(drect, dst, stride, w * px, h)) return hc.err;
+    const void *dp = hc.up(pal, 8 * px);
+    const uint8_t *di = (const uint8_t *)hc.up(idx, (size_t)w * h);
+    if (hc.err) return hc.err;
+    if (bdmax > 255) pal_pred_kernel<BD16><<<(w * h + 255) / 256, 256, 0, hc.stream()>>>(drect.dptr, drect.dpitch, (const uint16_t *)dp, di, w, h);
+    else pal_pred_kernel<BD8><<<(w * h + 255) / 256, 256, 0, hc.stream()>>>(drect.dptr, drect.dpitch, (const uint8_t *)dp, di, w, h);
+    hc.rect_down(drect);
+    if (hc.sync()) return hc.err;
+    drect.finish(dst);
+    return 0;
+}
+
+// ---- function-pointer table (drop-in for rav1d_intra_pred_dsp_init, src/ipred.rs:1502-1560) ----
+namespace {
+#define IP_FATAL_IF(x, name) do { if (x) rb200_report_fatal(name); } while (0)
+template <int MODE> void ipred_slot(void *d, ptrdiff_t s, const void *tl, int w, int h, int a, int mw, int mh, int bd) {
+    IP_FATAL_IF(rb200_ipred(MODE, d, s, tl, w, h, a, mw, mh, bd), "intra_pred");
+}
+template <int SS, int BDMAX> void cfl_ac_slot(int16_t *ac, const void *y, ptrdiff_t s, int wp, int hp, int cw, int ch) {
+    IP_FATAL_IF(rb200_cfl_ac(SS, ac, y, s, wp, hp, cw, ch, BDMAX), "cfl_ac");
+}
+template <int MODE> void cfl_pred_slot(void *d, ptrdiff_t s, const void *tl, int w, int h, const int16_t *ac, int alpha, int bd) {
+    IP_FATAL_IF(rb200_cfl_pred(MODE, d, s, tl, w, h, ac, alpha, bd), "cfl_pred");
+}
+template <int BDMAX> void pal_pred_slot(void *d, ptrdiff_t s, const void *pal, const uint8_t *idx, int w, int h) {
+    IP_FATAL_IF(rb200_pal_pred(d, s, pal, idx, w, h, BDMAX), "pal_pred");
+}
+template <int... M>
+void fill_ipred(Rb200IntraPredDSPContext *c, std::integer_sequence<int, M...>) { ((c->intra_pred[M] = &ipred_slot<M>), ...); }
+}  // namespace
+
+extern "C" void rb200_intra_pred_dsp_init(Rb200IntraPredDSPContext *c, int bpc) {
+    memset(c, 0, sizeof(*c));
+    fill_ipred(c, std::make_integer_sequence<int, IP_N_MODES>{});
+    if (bpc > 8) {   // cfl_ac and pal_pred carry no bitdepth_max: 16-bit pixels for 10 / 12 bpc
+        c->cfl_ac[0] = &cfl_ac_slot<0, 1023>; c->cfl_ac[1] = &cfl_ac_slot<1, 1023>; c->cfl_ac[2] = &cfl_ac_slot<2, 1023>;
+        c->pal_pred = &pal_pred_slot<1023>;
+    } else {
+        c->cfl_ac[0] = &cfl_ac_slot<0, 255>; c->cfl_ac[1] = &cfl_ac_slot<1, 255>; c->cfl_ac[2] = &cfl_ac_slot<2, 255>;
+        c->pal_pred = &pal_pred_slot<255>;
+    }
+    c->cfl_pred[IP_DC] = &cfl_pred_slot<IP_DC>; c->cfl_pred[IP_LEFT_DC] = &cfl_pred_slot<IP_LEFT_DC>;
+    c->cfl_pred[IP_TOP_DC] = &cfl_pred_slot<IP_TOP_DC>; c->cfl_pred[IP_DC_128] = &cfl_pred_slot<IP_DC_128>;
+}

@@ -206,6 +206,19 @@ frame_lr_masks = _sig("rb200_frame_lr_masks", _vp, _vp)
 frame_reserve_comp_items = _sig("rb200_frame_reserve_comp_items", _i, _vp, _i)
 frame_comp_items = _sig("rb200_frame_comp_items", _vp, _vp)
 frame_set_comp_count = _sig("rb200_frame_set_comp_count", _i, _vp, _i)
+ipred = _sig("rb200_ipred", _i, _i, _vp, _ss, _vp, _i, _i, _i, _i, _i, _i)
+cfl_ac = _sig("rb200_cfl_ac", _i, _i, _vp, _vp, _ss, _i, _i, _i, _i, _i)
+cfl_pred = _sig("rb200_cfl_pred", _i, _i, _vp, _ss, _vp, _i, _i, _vp, _i, _i)
+pal_pred = _sig("rb200_pal_pred", _i, _vp, _ss, _vp, _vp, _i, _i, _i)
+(DC_PRED, VERT_PRED, HOR_PRED, LEFT_DC_PRED, TOP_DC_PRED, DC_128_PRED, Z1_PRED, Z2_PRED, Z3_PRED, SMOOTH_PRED, SMOOTH_V_PRED,
+ SMOOTH_H_PRED, PAETH_PRED, FILTER_PRED) = range(14)
+
+
+class IntraPredDSPContext(C.Structure):
+    _fields_ = [("intra_pred", C.c_void_p * 14), ("cfl_ac", C.c_void_p * 3), ("cfl_pred", C.c_void_p * 6), ("pal_pred", C.c_void_p)]
+
+
+intra_pred_dsp_init = _sig("rb200_intra_pred_dsp_init", None, C.POINTER(IntraPredDSPContext), _i)
 wedge_mask = _sig("rb200_wedge_mask", _i, _i, _i, _i, _i, _i, _vp)
 frame_reserve_scaled_items = _sig("rb200_frame_reserve_scaled_items", _i, _vp, _i)
 frame_scaled_items = _sig("rb200_frame_scaled_items", _vp, _vp)
