@@ -50,7 +50,15 @@ WORKLOADS = {
 GEN_ARGS = {"4k10c5": dict(comp_frac=0.5, warp_frac=0.05, obmc_frac=0.1)}
 FRAMES_PER_STEP = 16
 N_CTX = int(os.environ.get("RB200_BENCH_CTX", "8"))
-METRIC = "recon+post-filter throughput (itx+MC+LF/CDEF/LR), luma pixels of output frames"
+# BASELINE.json's metric, verbatim; `value` is its Mpixel/s part (luma pixels of output frames per second), the
+# "% of HBM roofline" part is `frame_roofline_frac` (whole frame) and `roofline` (dominant kernel).
+METRIC = "Mpixel/s recon+post-filter (itx+MC+LF/CDEF/LR) 4K 10-bit; % of HBM roofline"
+
+
+def metric_name(workload):
+    return METRIC if workload.startswith("4k10") else METRIC.replace("4K 10-bit", {"1080p8": "1080p 8-bit", "8k10": "8K 10-bit"}[workload])
+
+
 STAGE_NAMES = ["h2d", "mc", "itx", "deblock", "cdef", "lr", "film_grain"]
 
 
@@ -174,7 +182,7 @@ def run_reference(args, s, wl):
     frames = per_step * args.steps
     mpx = frames * w * h / t / 1e6
     sample = f"{frames} frames of the workload ({per_step} per step), {cores} threads, sbrow-parallel stages"
-    line = {"impl": "reference", "metric": METRIC, "value": mpx, "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": metric_name(args.workload), "value": mpx, "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": desc, "frames_per_step": per_step, "width": w, "height": h, "bpc": bpc,
@@ -384,7 +392,7 @@ def run_gpu(args, s, wl):
                      "frac": round(wi * (value * 1e6 / (w * h)) / world / peak_issue, 4)}
         # frame-level algorithmic bytes as BASELINE.md 4 counts them (MC + itx = one fused recon stage: 2S + C)
         frame_bytes = (ab["recon"] if stages & 1 else 0) + sum(ab[k] for k in ("deblock", "cdef", "lr", "film_grain") if k in per_stage)
-        line = {"metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        line = {"metric": metric_name(args.workload), "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32", "data": "synthetic",
                 "config": {"workload": desc, "frames_per_step": FRAMES_PER_STEP, "width": w, "height": h, "bpc": bpc,
