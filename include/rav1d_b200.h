@@ -442,6 +442,7 @@ int rb200_generate_scaling(int bitdepth, const uint8_t points[][2], int num, uin
 enum { RB200_LAYOUT_I400, RB200_LAYOUT_I420, RB200_LAYOUT_I422, RB200_LAYOUT_I444 };
 enum { RB200_STAGE_RECON = 1, RB200_STAGE_DEBLOCK = 2, RB200_STAGE_CDEF = 4, RB200_STAGE_LR = 8,
        RB200_STAGE_FILM_GRAIN = 16 /* needs rb200_frame_set_film_grain */,
+       RB200_STAGE_INTRA = 64      /* intra-predicted blocks, level by level (rb200_frame_set_intra_levels) */,
        RB200_STAGE_SUPER_RES = 32  /* frames created with upscaled_width > width: horizontal upscaling between CDEF
                                       and loop restoration (rav1d_filter_sbrow_resize, src/recon.rs:4215-4281) */ };
 typedef struct Rb200FrameHeader {
@@ -518,6 +519,32 @@ int rb200_frame_set_ref_size(Rb200Frame *f, int slot, int width, int height);   
 int rb200_frame_reserve_scaled_items(Rb200Frame *f, int max_scaled_items);
 Rb200McScaledItem *rb200_frame_scaled_items(Rb200Frame *f);
 int rb200_frame_set_scaled_count(Rb200Frame *f, int n);
+/* Frame level (stage RB200_STAGE_INTRA): the intra half of rav1d_recon_b_intra (src/recon.rs:2402-3160) as a
+ * wavefront.  One record per intra-predicted TRANSFORM block; the host gives each its dependency level (a block
+ * needs the reconstructed pixels left of, above, above-right and below-left of it, so level = 1 + the highest
+ * level among the intra blocks that own those pixels; blocks that only touch inter-predicted or absent
+ * neighbours are level 0).  Per level the library predicts every block (edge preparation as
+ * rav1d_prepare_intra_edges, src/ipred_prepare.rs:118, then the predictor) and adds the level's residuals.
+ * Not covered yet: CfL, palette and inter-intra blocks. */
+typedef struct Rb200IntraItem {
+    uint16_t x4, y4;          /* block position in `plane`, 4-pixel units (t.bx, t.by; >> ss for chroma) */
+    uint16_t w4_end, h4_end;  /* tile end in the same units: the `w`, `h` arguments of rav1d_prepare_intra_edges */
+    uint8_t plane;
+    uint8_t tw4, th4;         /* transform block size, 4-pixel units (1 .. 16) */
+    uint8_t mode;             /* coded IntraPredMode: DC 0, VERT 1, HOR 2, DIAG_DOWN_LEFT 3 .. VERT_LEFT 8, SMOOTH 9,
+                                 SMOOTH_V 10, SMOOTH_H 11, PAETH 12, FILTER 13 */
+    int8_t angle;             /* angle_delta -3 .. 3 (directional modes) or the filter-intra set 0 .. 4 */
+    uint8_t flags;            /* 1 have_left, 2 have_top, 4 EDGE_TOP_HAS_RIGHT, 8 EDGE_LEFT_HAS_BOTTOM, 16 smooth
+                                 neighbour (sm_flag), 32 seq_hdr.intra_edge_filter */
+    uint16_t level;
+} RB200_ALIGN16 Rb200IntraItem;   /* 16 bytes */
+int rb200_frame_reserve_intra_items(Rb200Frame *f, int max_items, int max_levels);
+Rb200IntraItem *rb200_frame_intra_items(Rb200Frame *f);   /* sorted by level */
+/* item_counts[level]; itx_counts[level][RB200_N_RECT_TX_SIZES]: the residuals of that level's blocks, stored in the
+ * frame's Rb200ItxItem list right after the inter ones (i.e. from index sum(itx_counts of rb200_frame_submit)),
+ * level by level and bucketed by size within a level. */
+int rb200_frame_set_intra_levels(Rb200Frame *f, int n_levels, const int32_t *item_counts, const int32_t *itx_counts);
+
 int rb200_frame_reserve_warp_items(Rb200Frame *f, int max_warp_items);
 Rb200WarpItem *rb200_frame_warp_items(Rb200Frame *f);
 int rb200_frame_set_warp_count(Rb200Frame *f, int n_warp_items);

@@ -66,6 +66,8 @@ void dav1d_filter_sbrow_lr_8bpc(Dav1dFrameContext *f, int sby);
 void dav1d_filter_sbrow_lr_16bpc(Dav1dFrameContext *f, int sby);
 void dav1d_film_grain_dsp_init_8bpc(Dav1dFilmGrainDSPContext *c);
 void dav1d_film_grain_dsp_init_16bpc(Dav1dFilmGrainDSPContext *c);
+void dav1d_intra_pred_dsp_init_8bpc(Dav1dIntraPredDSPContext *c);
+void dav1d_intra_pred_dsp_init_16bpc(Dav1dIntraPredDSPContext *c);
 void dav1d_apply_grain_8bpc(const Dav1dFilmGrainDSPContext *dsp, Dav1dPicture *out, const Dav1dPicture *in);
 void dav1d_apply_grain_16bpc(const Dav1dFilmGrainDSPContext *dsp, Dav1dPicture *out, const Dav1dPicture *in);
 void dav1d_itx_dsp_init_8bpc(Dav1dInvTxfmDSPContext *c, int bpc);
@@ -109,9 +111,9 @@ RefFrame *ref_frame_new(const Rb200FrameHeader *h, int n_tc) {
         dav1d_itx_dsp_init_16bpc(&dsp->itx, h->bpc); dav1d_mc_dsp_init_16bpc(&dsp->mc);
         dav1d_loop_filter_dsp_init_16bpc(&dsp->lf); dav1d_cdef_dsp_init_16bpc(&dsp->cdef);
         dav1d_loop_restoration_dsp_init_16bpc(&dsp->lr, h->bpc);
-        dav1d_film_grain_dsp_init_16bpc(&dsp->fg);
+        dav1d_film_grain_dsp_init_16bpc(&dsp->fg); dav1d_intra_pred_dsp_init_16bpc(&dsp->ipred);
     } else {
-        dav1d_film_grain_dsp_init_8bpc(&dsp->fg);
+        dav1d_film_grain_dsp_init_8bpc(&dsp->fg); dav1d_intra_pred_dsp_init_8bpc(&dsp->ipred);
         dav1d_itx_dsp_init_8bpc(&dsp->itx, 8); dav1d_mc_dsp_init_8bpc(&dsp->mc);
         dav1d_loop_filter_dsp_init_8bpc(&dsp->lf); dav1d_cdef_dsp_init_8bpc(&dsp->cdef);
         dav1d_loop_restoration_dsp_init_8bpc(&dsp->lr, 8);
@@ -592,4 +594,58 @@ void ref_frame_recon_scaled(RefFrame *r, RefFrame *const refs[], int n_refs, con
                                                            it->pos_x & 0x3ff, it->pos_y & 0x3ff, it->step_x, it->step_y);
     }
     free(emu);
+}
+
+/* ------------------------------------------------------------ intra blocks */
+/* The intra-prediction half of dav1d_recon_b_intra (src/recon_tmpl.c:1254-1345): per transform block, in DECODE
+ * order, dav1d_prepare_intra_edges, the predictor it selects, then the block's residual.  items[] is in decode
+ * order; itx_of[i] is the index of block i's residual in itx[] or -1.  The in-loop filters have not run, so the
+ * saved pre-filter superblock edge is the picture itself (prefilter_toplevel_sb_edge = NULL). */
+#include "src/intra_edge.h"
+enum IntraPredMode dav1d_prepare_intra_edges_8bpc(int x, int have_left, int y, int have_top, int w, int h, enum EdgeFlags edge_flags,
+                                                  const uint8_t *dst, ptrdiff_t stride, const uint8_t *prefilter_toplevel_sb_edge,
+                                                  enum IntraPredMode mode, int *angle, int tw, int th, int filter_edge,
+                                                  uint8_t *topleft_out);
+enum IntraPredMode dav1d_prepare_intra_edges_16bpc(int x, int have_left, int y, int have_top, int w, int h, enum EdgeFlags edge_flags,
+                                                   const uint16_t *dst, ptrdiff_t stride, const uint16_t *prefilter_toplevel_sb_edge,
+                                                   enum IntraPredMode mode, int *angle, int tw, int th, int filter_edge,
+                                                   uint16_t *topleft_out, int bitdepth_max);
+void ref_frame_recon_intra(RefFrame *r, const Rb200IntraItem *items, int n, const int32_t *itx_of, const Rb200ItxItem *itx,
+                           void *coef_work) {
+    Dav1dFrameContext *f = r->f;
+    const int px = r->hbd ? 2 : 1, cs = r->hbd ? 4 : 2;
+    const int ss_ver_l = f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420, ss_hor_l = f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444;
+    uint16_t edge_buf[257 + 32];
+    for (int i = 0; i < n; i++) {
+        const Rb200IntraItem *it = &items[i];
+        const int pl = it->plane, ss_hor = pl && ss_hor_l, ss_ver = pl && ss_ver_l;
+        const ptrdiff_t stride = f->cur.stride[!!pl];
+        uint8_t *dst = (uint8_t *)f->cur.data[pl] + stride * (it->y4 * 4) + (ptrdiff_t)(it->x4 * 4) * px;
+        const int have_left = it->flags & 1, have_top = (it->flags >> 1) & 1;
+        const int ef = (it->flags & 4 ? EDGE_I444_TOP_HAS_RIGHT : 0) | (it->flags & 8 ? EDGE_I444_LEFT_HAS_BOTTOM : 0);
+        const int is_sm = (it->flags >> 4) & 1, eief = (it->flags >> 5) & 1;
+        int angle = it->angle;
+        const int max_w = ((4 * f->bw) >> ss_hor) - 4 * it->x4, max_h = ((4 * f->bh) >> ss_ver) - 4 * it->y4;
+        const int intra_flags = (is_sm << 9) | (eief << 10);
+        if (r->hbd) {
+            uint16_t *edge = edge_buf + 128 + 16;
+            const int m = dav1d_prepare_intra_edges_16bpc(it->x4, have_left, it->y4, have_top, it->w4_end, it->h4_end, ef, (const uint16_t *)dst,
+                                                          stride, NULL, it->mode, &angle, it->tw4, it->th4, eief, edge, r->bdmax);
+            ((void (*)(void *, ptrdiff_t, const void *, int, int, int, int, int, int))f->dsp->ipred.intra_pred[m])(
+                dst, stride, edge, it->tw4 * 4, it->th4 * 4, angle | intra_flags, max_w, max_h, r->bdmax);
+        } else {
+            uint8_t *edge = (uint8_t *)edge_buf + 128 + 16;
+            const int m = dav1d_prepare_intra_edges_8bpc(it->x4, have_left, it->y4, have_top, it->w4_end, it->h4_end, ef, dst, stride, NULL,
+                                                         it->mode, &angle, it->tw4, it->th4, eief, edge);
+            ((void (*)(void *, ptrdiff_t, const void *, int, int, int, int, int))f->dsp->ipred.intra_pred[m])(
+                dst, stride, edge, it->tw4 * 4, it->th4 * 4, angle | intra_flags, max_w, max_h);
+        }
+        if (itx_of && itx_of[i] >= 0) {
+            const Rb200ItxItem *t = &itx[itx_of[i]];
+            uint8_t *d = (uint8_t *)f->cur.data[t->plane] + f->cur.stride[!!t->plane] * t->y + (ptrdiff_t)t->x * px;
+            void *cf = (uint8_t *)coef_work + (size_t)t->cf_off * cs;
+            if (r->hbd) ((itx_fn16)f->dsp->itx.itxfm_add[t->tx][t->txtp])(d, f->cur.stride[!!t->plane], cf, t->eob, r->bdmax);
+            else ((itx_fn8)f->dsp->itx.itxfm_add[t->tx][t->txtp])(d, f->cur.stride[!!t->plane], cf, t->eob);
+        }
+    }
 }

@@ -44,6 +44,9 @@ struct Rb200Frame {
     Rb200McItem *h_obmc, *d_obmc; int max_obmc, n_obmc_above, n_obmc_left;
     Rb200McScaledItem *h_scaled, *d_scaled; int max_scaled, n_scaled;
     rb200::McRefDims ref_dims;
+    // intra blocks, level by level (RB200_STAGE_INTRA)
+    Rb200IntraItem *h_intra, *d_intra; int max_intra, max_levels, n_levels;
+    int32_t *intra_counts, *intra_itx_counts;     // [max_levels], [max_levels][RB200_N_RECT_TX_SIZES]
     // super-resolution (hdr.upscaled_width > hdr.width): plane sets at the upscaled width --
     // 0 = upscaled CDEF output, 1 = upscaled deblocked picture (what lr_line_buf holds on the CPU), 2 = LR output
     bool sr;
@@ -226,6 +229,9 @@ extern "C" int rb200_frame_destroy(Rb200Frame *f) {
     if (f->d_obmc) cudaFree(f->d_obmc);
     if (f->h_scaled) cudaFreeHost(f->h_scaled);
     if (f->d_scaled) cudaFree(f->d_scaled);
+    if (f->h_intra) cudaFreeHost(f->h_intra);
+    if (f->d_intra) cudaFree(f->d_intra);
+    free(f->intra_counts); free(f->intra_itx_counts);
     if (f->h_warp) cudaFreeHost(f->h_warp);
     if (f->d_warp) cudaFree(f->d_warp);
     if (f->h_comp) cudaFreeHost(f->h_comp);
@@ -573,6 +579,44 @@ extern "C" int rb200_frame_set_ref_size(Rb200Frame *f, int slot, int width, int 
     return 0;
 }
 
+extern "C" int rb200_frame_reserve_intra_items(Rb200Frame *f, int max_items, int max_levels) {
+    if (!f || max_items < 0 || max_levels < 0) return set_error(-22, "frame_reserve_intra_items: bad argument");
+    if (max_items > f->max_intra) {
+        RB_CUDA(cudaStreamSynchronize(f->stream));
+        if (f->h_intra) cudaFreeHost(f->h_intra);
+        if (f->d_intra) cudaFree(f->d_intra);
+        f->h_intra = nullptr; f->d_intra = nullptr; f->max_intra = 0; f->n_levels = 0;
+        const int r = alloc_pair(&f->h_intra, &f->d_intra, (size_t)max_items);
+        if (r) return r;
+        f->max_intra = max_items;
+    }
+    if (max_levels > f->max_levels) {
+        free(f->intra_counts); free(f->intra_itx_counts);
+        f->intra_counts = (int32_t *)calloc((size_t)max_levels, sizeof(int32_t));
+        f->intra_itx_counts = (int32_t *)calloc((size_t)max_levels * RB200_N_RECT_TX_SIZES, sizeof(int32_t));
+        if (!f->intra_counts || !f->intra_itx_counts) return set_error(-12, "frame_reserve_intra_items: out of memory");
+        f->max_levels = max_levels; f->n_levels = 0;
+    }
+    return 0;
+}
+extern "C" Rb200IntraItem *rb200_frame_intra_items(Rb200Frame *f) { return f ? f->h_intra : nullptr; }
+extern "C" int rb200_frame_set_intra_levels(Rb200Frame *f, int n_levels, const int32_t *item_counts, const int32_t *itx_counts) {
+    if (!f || n_levels < 0 || n_levels > f->max_levels || (n_levels && (!item_counts || !itx_counts)))
+        return set_error(-22, "frame_set_intra_levels: more levels than reserved");
+    int64_t n = 0;
+    for (int l = 0; l < n_levels; l++) {
+        if (item_counts[l] < 0) return set_error(-22, "frame_set_intra_levels: negative count");
+        n += item_counts[l];
+    }
+    if (n > f->max_intra) return set_error(-22, "frame_set_intra_levels: more items than reserved");
+    if (n_levels) {
+        memcpy(f->intra_counts, item_counts, (size_t)n_levels * sizeof(int32_t));
+        memcpy(f->intra_itx_counts, itx_counts, (size_t)n_levels * RB200_N_RECT_TX_SIZES * sizeof(int32_t));
+    }
+    f->n_levels = n_levels;
+    return 0;
+}
+
 extern "C" int rb200_frame_reserve_obmc_items(Rb200Frame *f, int max_obmc) {
     if (!f || max_obmc < 0) return set_error(-22, "frame_reserve_obmc_items: bad argument");
     if (max_obmc <= f->max_obmc) return 0;
@@ -686,6 +730,9 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
             if (itx_counts[t] < 0) return set_error(-22, "frame_submit: negative itx count");
             n_itx += itx_counts[t];
         }
+        if (stages & RB200_STAGE_INTRA)   // the residuals of the intra blocks follow the inter ones in the same list
+            for (int l = 0; l < f->n_levels; l++)
+                for (int t = 0; t < RB200_N_RECT_TX_SIZES; t++) n_itx += f->intra_itx_counts[l * RB200_N_RECT_TX_SIZES + t];
         if (n_coefs > f->max_coefs || n_itx > f->max_itx || n_mc > f->max_mc || n_mc < 0)
             return set_error(-22, "frame_submit: batch larger than the frame was created for");
         if ((n_mc || f->n_comp || f->n_warp || f->n_scaled || f->n_obmc_above || f->n_obmc_left) && f->n_refs < 1) return set_error(-22, "frame_submit: no reference picture set");
@@ -740,6 +787,11 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
             if (n_mc) RB_CUDA(cudaMemcpyAsync(f->d_mc, f->h_mc, (size_t)n_mc * sizeof(Rb200McItem), cudaMemcpyHostToDevice, st));
             if (f->n_comp) RB_CUDA(cudaMemcpyAsync(f->d_comp, f->h_comp, (size_t)f->n_comp * sizeof(Rb200CompItem), cudaMemcpyHostToDevice, st));
             if (f->n_warp) RB_CUDA(cudaMemcpyAsync(f->d_warp, f->h_warp, (size_t)f->n_warp * sizeof(Rb200WarpItem), cudaMemcpyHostToDevice, st));
+            if ((stages & RB200_STAGE_INTRA) && f->n_levels) {
+                int n_in = 0;
+                for (int l = 0; l < f->n_levels; l++) n_in += f->intra_counts[l];
+                if (n_in) RB_CUDA(cudaMemcpyAsync(f->d_intra, f->h_intra, (size_t)n_in * sizeof(Rb200IntraItem), cudaMemcpyHostToDevice, st));
+            }
             if (f->n_scaled) RB_CUDA(cudaMemcpyAsync(f->d_scaled, f->h_scaled, (size_t)f->n_scaled * sizeof(Rb200McScaledItem), cudaMemcpyHostToDevice, st));
             if (f->n_obmc_above + f->n_obmc_left)
                 RB_CUDA(cudaMemcpyAsync(f->d_obmc, f->h_obmc, (size_t)(f->n_obmc_above + f->n_obmc_left) * sizeof(Rb200McItem), cudaMemcpyHostToDevice, st));
@@ -801,6 +853,27 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
                 f->launches++;
             }
             off += itx_counts[t];
+        }
+        // ---- intra blocks: per dependency level, predict every block of the level, then add its residuals
+        if ((stages & RB200_STAGE_INTRA) && f->n_levels) {
+            const void *cf = upload == RB200_UPLOAD_ZERO_COPY_COEF ? f->h_coef : f->d_coef;
+            int ioff = 0;
+            for (int l = 0; l < f->n_levels; l++) {
+                if (f->intra_counts[l]) {
+                    if ((r = intra_items_launch(f->planes[0], f->d_intra + ioff, f->intra_counts[l], g.bw, g.bh, g.ss_hor, g.ss_ver,
+                                                f->bdmax, st))) return r;
+                    f->launches++;
+                    ioff += f->intra_counts[l];
+                }
+                for (int t = 0; t < RB200_N_RECT_TX_SIZES; t++) {
+                    const int c = f->intra_itx_counts[l * RB200_N_RECT_TX_SIZES + t];
+                    if (c) {
+                        if ((r = itx_launch(t, f->planes[0], cf, f->d_itx + off, c, f->bdmax, st))) return r;
+                        f->launches++;
+                    }
+                    off += c;
+                }
+            }
         }
     }
     f->out = f->planes[0];
@@ -884,4 +957,4 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
 #undef MARK
     return 0;
 }
-static_assert(sizeof(Rb200WarpItem) == 48 && sizeof(Rb200CompItem) == 32 && sizeof(Rb200McItem) == 16 && sizeof(Rb200ItxItem) == 16 && sizeof(Rb200McScaledItem) == 32, "batch record sizes");
+static_assert(sizeof(Rb200WarpItem) == 48 && sizeof(Rb200CompItem) == 32 && sizeof(Rb200McItem) == 16 && sizeof(Rb200ItxItem) == 16 && sizeof(Rb200McScaledItem) == 32 && sizeof(Rb200IntraItem) == 16, "batch record sizes");

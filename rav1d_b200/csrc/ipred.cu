@@ -67,19 +67,25 @@ __device__ void ip_upsample_edge(P *out, int hsz, const P *in, int from, int to,
     }
 }
 
+// Scratch of one block prediction (shared memory of the calling CTA).
+template <typename P>
+struct IpScratch {
+    P e[IP_EDGE];             // the block's edge, topleft at e[IP_EC]
+    P work[2 * IP_EC + 2];    // prepared edge of the directional modes
+    P tile[32 * 32];          // filter-intra block
+    int dc;
+};
+
+// Predict one w x h block at dst8 from the edge in S.e (all threads of the CTA take part; S.e is complete and
+// visible on entry).  mode: IP_*; angle: the reference's packed argument.
 template <typename BD>
-__global__ void __launch_bounds__(256)
-ipred_kernel(int mode, uint8_t *dst8, int64_t stride, const typename BD::pixel *__restrict__ edge_in, int lo, int hi, int w,
-             int h, int angle, int max_w, int max_h, int bdmax) {
+__device__ void ipred_block(IpScratch<typename BD::pixel> &S, int mode, uint8_t *dst8, int64_t stride, int w, int h, int angle,
+                            int max_w, int max_h, int bdmax) {
     using pixel = typename BD::pixel;
-    __shared__ pixel e_s[IP_EDGE];           // caller's edge, topleft at e_s[IP_EC]
-    __shared__ pixel work[2 * IP_EC + 2];    // prepared edge of the directional modes
-    __shared__ pixel tile[32 * 32];          // filter-intra block
-    __shared__ int dc_s;
+    pixel *work = S.work, *tile = S.tile;
+    int &dc_s = S.dc;
     const int tid = threadIdx.x;
-    for (int i = tid; i < lo + hi + 1; i += blockDim.x) e_s[IP_EC - lo + i] = edge_in[i];
-    __syncthreads();
-    const pixel *tl = e_s + IP_EC;
+    const pixel *tl = S.e + IP_EC;
     auto put = [&](int x, int y, int v) { ((pixel *)(dst8 + (int64_t)y * stride))[x] = (pixel)v; };
     const int n = w * h;
 
@@ -274,6 +280,128 @@ ipred_kernel(int mode, uint8_t *dst8, int64_t stride, const typename BD::pixel *
     }
     default: break;
     }
+}
+
+template <typename BD>
+__global__ void __launch_bounds__(256)
+ipred_kernel(int mode, uint8_t *dst8, int64_t stride, const typename BD::pixel *__restrict__ edge_in, int lo, int hi, int w,
+             int h, int angle, int max_w, int max_h, int bdmax) {
+    __shared__ IpScratch<typename BD::pixel> S;
+    for (int i = threadIdx.x; i < lo + hi + 1; i += blockDim.x) S.e[IP_EC - lo + i] = edge_in[i];
+    __syncthreads();
+    ipred_block<BD>(S, mode, dst8, stride, w, h, angle, max_w, max_h, bdmax);
+}
+
+// ---------------------------------------------------------------- frame level: one wavefront level of intra blocks
+// rav1d_prepare_intra_edges (src/ipred_prepare.rs:118-330 == src/ipred_prepare_tmpl.c:77-204) restated per thread
+// index: which neighbouring pixels of the reconstructed picture form the edge, how the unavailable parts are
+// replicated, and which implementation mode the coded mode becomes; then the block is predicted in place.
+// The picture rows above a superblock row are still unfiltered when this runs (the in-loop filters come after
+// the whole reconstruction), so the reference's saved pre-filter edge (f.ipred_edge) is the picture itself.
+template <typename BD>
+__global__ void __launch_bounds__(256)
+intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, int frame_w4, int frame_h4, int ss_hor_c,
+                   int ss_ver_c, int bdmax) {
+    using pixel = typename BD::pixel;
+    __shared__ IpScratch<pixel> S;
+    const Rb200IntraItem it = items[blockIdx.x];
+    const int tid = threadIdx.x;
+    const int ss_hor = it.plane ? ss_hor_c : 0, ss_ver = it.plane ? ss_ver_c : 0;
+    const int64_t stride = plane_stride(cur, it.plane);
+    uint8_t *dst8 = plane_ptr(cur, it.plane) + (int64_t)(it.y4 * 4) * stride + (int64_t)(it.x4 * 4) * sizeof(pixel);
+    const int64_t ps = stride / (int64_t)sizeof(pixel);
+    const pixel *dst = (const pixel *)dst8;
+    const int have_left = it.flags & 1, have_top = (it.flags >> 1) & 1;
+    const int top_has_right = (it.flags >> 2) & 1, left_has_bottom = (it.flags >> 3) & 1;
+    const int is_sm = (it.flags >> 4) & 1, eief = (it.flags >> 5) & 1;
+    const int tw = it.tw4, th = it.th4, x = it.x4, y = it.y4, w = it.w4_end, h = it.h4_end;
+    const int bitdepth = BD::hbd ? bpc_from_max(bdmax) : 8;
+    // ---- coded mode -> implementation mode (src/ipred_prepare_tmpl.c:89-116); coded numbering: DC 0, VERT 1, HOR 2,
+    // DIAG_DOWN_LEFT 3, DIAG_DOWN_RIGHT 4, VERT_RIGHT 5, HOR_DOWN 6, HOR_UP 7, VERT_LEFT 8, SMOOTH 9 .. PAETH 12, FILTER 13
+    int mode = it.mode, angle = it.angle;
+    if (mode >= 1 && mode <= 8) {
+        const int map[8] = { 90, 180, 45, 135, 113, 157, 203, 67 };
+        angle = map[mode - 1] + 3 * angle;
+        if (angle <= 90) mode = (angle < 90 && have_top) ? IP_Z1 : IP_VERT;
+        else if (angle < 180) mode = IP_Z2;
+        else mode = (angle > 180 && have_left) ? IP_Z3 : IP_HOR;
+    } else if (mode == IP_DC) {
+        mode = have_left ? (have_top ? IP_DC : IP_LEFT_DC) : (have_top ? IP_TOP_DC : IP_DC_128);
+    } else if (mode == IP_PAETH) {
+        mode = have_left ? (have_top ? IP_PAETH : IP_HOR) : (have_top ? IP_VERT : IP_DC_128);
+    }
+    // needs_{left, top, topleft, topright, bottomleft} per implementation mode (:52-75)
+    const bool n_left = mode == IP_DC || mode == IP_HOR || mode == IP_LEFT_DC || mode == IP_Z2 || mode == IP_Z3 || (mode >= IP_SMOOTH && mode <= IP_FILTER);
+    const bool n_top = mode == IP_DC || mode == IP_VERT || mode == IP_TOP_DC || mode == IP_Z1 || mode == IP_Z2 || (mode >= IP_SMOOTH && mode <= IP_FILTER);
+    const bool n_tl = mode == IP_Z1 || mode == IP_Z2 || mode == IP_Z3 || mode == IP_PAETH || mode == IP_FILTER;
+    const bool n_tr = mode == IP_Z1, n_bl = mode == IP_Z3;
+    const pixel *dst_top = dst - ps;      // only dereferenced when have_top
+    pixel *tl = S.e + IP_EC;
+    // ---- left column and top row
+    if (n_left) {
+        const int sz = th << 2;
+        if (have_left) {
+            const int px_have = imin(sz, (h - y) << 2);
+            for (int i = tid; i < sz; i += blockDim.x) tl[-(1 + i)] = dst[(int64_t)imin(i, px_have - 1) * ps - 1];
+        } else {
+            const pixel v = have_top ? dst_top[0] : (pixel)(((1 << bitdepth) >> 1) + 1);
+            for (int i = tid; i < sz; i += blockDim.x) tl[-(1 + i)] = v;
+        }
+    }
+    if (n_top) {
+        const int sz = tw << 2;
+        if (have_top) {
+            const int px_have = imin(sz, (w - x) << 2);
+            for (int i = tid; i < sz; i += blockDim.x) tl[1 + i] = dst_top[imin(i, px_have - 1)];
+        } else {
+            const pixel v = have_left ? dst[-1] : (pixel)(((1 << bitdepth) >> 1) - 1);
+            for (int i = tid; i < sz; i += blockDim.x) tl[1 + i] = v;
+        }
+    }
+    __syncthreads();
+    // ---- bottom-left and top-right extensions
+    if (n_left && n_bl) {
+        const int sz = th << 2;
+        const int have_bl = (!have_left || y + th >= h) ? 0 : left_has_bottom;
+        if (have_bl) {
+            const int px_have = imin(sz, (h - y - th) << 2);
+            for (int i = tid; i < sz; i += blockDim.x) tl[-(sz + 1 + i)] = dst[(int64_t)(sz + imin(i, px_have - 1)) * ps - 1];
+        } else {
+            const pixel v = tl[-sz];
+            for (int i = tid; i < sz; i += blockDim.x) tl[-(sz + 1 + i)] = v;
+        }
+    }
+    if (n_top && n_tr) {
+        const int sz = tw << 2;
+        const int have_tr = (!have_top || x + tw >= w) ? 0 : top_has_right;
+        if (have_tr) {
+            const int px_have = imin(sz, (w - x - tw) << 2);
+            for (int i = tid; i < sz; i += blockDim.x) tl[1 + sz + i] = dst_top[sz + imin(i, px_have - 1)];
+        } else {
+            const pixel v = tl[sz];
+            for (int i = tid; i < sz; i += blockDim.x) tl[1 + sz + i] = v;
+        }
+    }
+    if (n_tl && tid == 0) {
+        int v;
+        if (have_left) v = have_top ? dst_top[-1] : dst[-1];
+        else v = have_top ? dst_top[0] : (1 << bitdepth) >> 1;
+        if (mode == IP_Z2 && tw + th >= 6 && eief) v = ((tl[-1] + tl[1]) * 5 + v * 6 + 8) >> 4;
+        tl[0] = (pixel)v;
+    }
+    __syncthreads();
+    const int max_w = ((frame_w4 * 4) >> ss_hor) - 4 * x, max_h = ((frame_h4 * 4) >> ss_ver) - 4 * y;
+    ipred_block<BD>(S, mode, dst8, stride, tw * 4, th * 4, mode == IP_FILTER ? (it.angle & 7) : (angle | (is_sm << 9) | (eief << 10)),
+                    max_w, max_h, bdmax);
+}
+
+int intra_items_launch(const Rb200Planes &cur, const Rb200IntraItem *d_items, int n, int frame_w4, int frame_h4, int ss_hor,
+                       int ss_ver, int bdmax, cudaStream_t st) {
+    if (n <= 0) return 0;
+    if (bdmax > 255) intra_items_kernel<BD16><<<n, 256, 0, st>>>(cur, d_items, frame_w4, frame_h4, ss_hor, ss_ver, bdmax);
+    else intra_items_kernel<BD8><<<n, 256, 0, st>>>(cur, d_items, frame_w4, frame_h4, ss_hor, ss_ver, bdmax);
+    RB_LAUNCH_CHECK();
+    return 0;
 }
 
 // cfl_ac (src/ipred_tmpl.c:657-703): sub-sampled luma, edge replication of the padded part, zero mean

@@ -89,7 +89,7 @@ N_2D_FILTERS = 10
 FILTER_2D_NAMES = ["8TAP_REGULAR", "8TAP_REGULAR_SMOOTH", "8TAP_REGULAR_SHARP", "8TAP_SHARP_REGULAR",
                    "8TAP_SHARP_SMOOTH", "8TAP_SHARP", "8TAP_SMOOTH_REGULAR", "8TAP_SMOOTH", "8TAP_SMOOTH_SHARP",
                    "BILINEAR"]
-STAGE_RECON, STAGE_DEBLOCK, STAGE_CDEF, STAGE_LR, STAGE_FILM_GRAIN, STAGE_SUPER_RES = 1, 2, 4, 8, 16, 32
+STAGE_RECON, STAGE_DEBLOCK, STAGE_CDEF, STAGE_LR, STAGE_FILM_GRAIN, STAGE_SUPER_RES, STAGE_INTRA = 1, 2, 4, 8, 16, 32, 64
 STAGE_ALL = 15
 LAYOUT_I400, LAYOUT_I420, LAYOUT_I422, LAYOUT_I444 = 0, 1, 2, 3
 RESTORATION_NONE, RESTORATION_SWITCHABLE, RESTORATION_WIENER, RESTORATION_SGRPROJ = 0, 1, 2, 3
@@ -112,6 +112,9 @@ SCALED_ITEM_DT = _np.dtype([("dst_x", "<i2"), ("dst_y", "<i2"), ("w", "u1"), ("h
                             ("pos_x", "<i4"), ("pos_y", "<i4"), ("step_x", "<i4"), ("step_y", "<i4"), ("filter2d", "u1"),
                             ("pad", "u1", (7,))])
 assert SCALED_ITEM_DT.itemsize == 32
+INTRA_ITEM_DT = _np.dtype([("x4", "<u2"), ("y4", "<u2"), ("w4_end", "<u2"), ("h4_end", "<u2"), ("plane", "u1"), ("tw4", "u1"),
+                           ("th4", "u1"), ("mode", "u1"), ("angle", "i1"), ("flags", "u1"), ("level", "<u2")])
+assert INTRA_ITEM_DT.itemsize == 16
 WARP_ITEM_DT = _np.dtype([("x", "<i2"), ("y", "<i2"), ("w", "u1"), ("h", "u1"), ("ref", "u1"), ("pad0", "u1"),
                           ("matrix", "<i4", (6,)), ("abcd", "<i2", (4,)), ("pad", "u1", (8,))])
 assert WARP_ITEM_DT.itemsize == 48
@@ -220,6 +223,9 @@ class IntraPredDSPContext(C.Structure):
 
 intra_pred_dsp_init = _sig("rb200_intra_pred_dsp_init", None, C.POINTER(IntraPredDSPContext), _i)
 wedge_mask = _sig("rb200_wedge_mask", _i, _i, _i, _i, _i, _i, _vp)
+frame_reserve_intra_items = _sig("rb200_frame_reserve_intra_items", _i, _vp, _i, _i)
+frame_intra_items = _sig("rb200_frame_intra_items", _vp, _vp)
+frame_set_intra_levels = _sig("rb200_frame_set_intra_levels", _i, _vp, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32))
 frame_reserve_scaled_items = _sig("rb200_frame_reserve_scaled_items", _i, _vp, _i)
 frame_scaled_items = _sig("rb200_frame_scaled_items", _vp, _vp)
 frame_set_scaled_count = _sig("rb200_frame_set_scaled_count", _i, _vp, _i)

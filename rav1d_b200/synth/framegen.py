@@ -533,6 +533,154 @@ def generate_recon_layout(w, h, bpc, layout, seed=1, comp_frac=0.3, warp_frac=0.
     return s
 
 
+def generate_intra(w, h, bpc, seed=1, inter_frac=0.0):
+    """A 4:2:0 frame whose 16x16 blocks are intra predicted (a fraction `inter_frac` of them translational inter blocks):
+    per transform block a coded mode, angle delta, edge-availability flags consistent with the decode order (raster over
+    blocks; inside a block luma transform blocks in raster order, then U, then V), the wavefront level the batch
+    path needs, and a residual.  Reconstruction only (no filter metadata)."""
+    from rav1d_b200.lib import TX_DIMS
+    from rav1d_b200.synth.itxgen import valid_txtps
+    rng = np.random.default_rng(seed)
+    bdmax = (1 << bpc) - 1
+    pdt, cdt = (np.uint16, np.int32) if bpc > 8 else (np.uint8, np.int16)
+    s = SynthFrame()
+    s.w, s.h, s.bpc, s.bdmax, s.layout = w, h, bpc, bdmax, lib.LAYOUT_I420
+    hd = lib.FrameHeader()
+    hd.width, hd.height, hd.bpc, hd.layout = w, h, bpc, lib.LAYOUT_I420
+    s.hdr = hd
+    g = s.geom = geometry(hd)
+    aw, ah = (w + 127) & ~127, (h + 127) & ~127
+    s.aw, s.ah = aw, ah
+    s.ref = [np.zeros((ah, aw), pdt), np.zeros((ah // 2, aw // 2), pdt), np.zeros((ah // 2, aw // 2), pdt)]
+    s.ref[0][:h, :w] = smooth_plane(rng, h, w, bdmax)
+    for p in (1, 2):
+        s.ref[p][:(h + 1) // 2, :(w + 1) // 2] = smooth_plane(rng, (h + 1) // 2, (w + 1) // 2, bdmax, cell=8)
+    nbx, nby = w // BLK, h // BLK
+    eief = int(rng.integers(0, 2))
+    TXS = {4: 0, 8: 1, 16: 2}
+    # per-plane maps in 4x4 cells: decode index of the transform block that owns the cell, its level
+    pw4 = [g.bw, g.bw >> 1, g.bw >> 1]; ph4 = [g.bh, g.bh >> 1, g.bh >> 1]
+    BIG = 1 << 60                                                         # not decoded yet: never available
+    dec = [np.full((ph4[p], pw4[p]), BIG, np.int64) for p in range(3)]
+    lvl = [np.full((ph4[p], pw4[p]), -1, np.int64) for p in range(3)]
+    is_inter = rng.random((nby, nbx)) < inter_frac
+    for byi, bxi in zip(*np.nonzero(is_inter)):                           # inter blocks are reconstructed before any intra block
+        for p in range(3):
+            c = BLK // 4 >> (1 if p else 0)
+            dec[p][byi * c:(byi + 1) * c, bxi * c:(bxi + 1) * c] = -1
+    items, itx_rows, mc_rows = [], [], []      # decode order
+    inter_itx = []
+    for byi in range(nby):
+        for bxi in range(nbx):
+            if is_inter[byi, bxi]:
+                mvx, mvy, f2d = int(rng.integers(-128, 129)), int(rng.integers(-128, 129)), int(rng.integers(0, 10))
+                for p in range(3):
+                    sh = 1 if p else 0
+                    x0, y0 = bxi * BLK >> sh, byi * BLK >> sh
+                    mc_rows.append((x0, y0, x0 + (mvx >> (3 + sh)), y0 + (mvy >> (3 + sh)), BLK >> sh, BLK >> sh, p, 0,
+                                    (mvx & 7) << 1 if p == 0 else mvx & 15, (mvy & 7) << 1 if p == 0 else mvy & 15, f2d, 0))
+                    if rng.random() < 0.7:
+                        inter_itx.append((p, x0, y0, 2 if p == 0 else 1))
+                continue
+            for p in range(3):
+                bsz = BLK >> (1 if p else 0)                       # block size in this plane, pixels
+                tsz = int(rng.choice([4, 8, 16] if p == 0 else [4, 8]))
+                mode = int(rng.integers(0, 14 if p == 0 else 13))  # filter-intra is luma only
+                delta = int(rng.integers(-3, 4)) if 1 <= mode <= 8 else (int(rng.integers(0, 5)) if mode == 13 else 0)
+                is_sm = int(rng.integers(0, 2))
+                x0, y0 = bxi * bsz // 4, byi * bsz // 4            # 4-px units
+                for ty in range(0, bsz // 4, tsz // 4):
+                    for tx_ in range(0, bsz // 4, tsz // 4):
+                        x4, y4, t4 = x0 + tx_, y0 + ty, tsz // 4
+                        idx = len(items)
+                        have_left, have_top = int(x4 > 0), int(y4 > 0)
+                        W4, H4 = pw4[p], ph4[p]
+                        deps = []
+
+                        def cells(xa, xb, ya, yb):
+                            return dec[p][max(ya, 0):min(yb, H4), max(xa, 0):min(xb, W4)], lvl[p][max(ya, 0):min(yb, H4), max(xa, 0):min(xb, W4)]
+                        tr_ok = have_top and x4 + t4 < W4 and (cells(x4 + t4, x4 + 2 * t4, y4 - 1, y4)[0] < idx).all()
+                        bl_ok = have_left and y4 + t4 < H4 and (cells(x4 - 1, x4, y4 + t4, y4 + 2 * t4)[0] < idx).all()
+                        has_tr = int(tr_ok and rng.random() < 0.9)
+                        has_bl = int(bl_ok and rng.random() < 0.9)
+                        rects = [(x4 - 1, x4, y4 - 1, y4 + t4), (x4, x4 + t4, y4 - 1, y4)]
+                        if has_tr: rects.append((x4 + t4, x4 + 2 * t4, y4 - 1, y4))
+                        if has_bl: rects.append((x4 - 1, x4, y4 + t4, y4 + 2 * t4))
+                        level = 0
+                        for r_ in rects:
+                            lv = cells(*r_)[1]
+                            if lv.size: level = max(level, int(lv.max()) + 1)
+                        dec[p][y4:y4 + t4, x4:x4 + t4] = idx
+                        lvl[p][y4:y4 + t4, x4:x4 + t4] = level
+                        flags = have_left | have_top << 1 | has_tr << 2 | has_bl << 3 | is_sm << 4 | eief << 5
+                        items.append((x4, y4, W4, H4, p, t4, t4, mode, delta, flags, level))
+                        itx_rows.append((p, x4 * 4, y4 * 4, TXS[tsz]) if rng.random() < 0.8 else None)
+    out_items = np.zeros(len(items), lib.INTRA_ITEM_DT)
+    for i, it in enumerate(items):
+        out_items[i] = it[:10] + (it[10],)
+    s.intra_items_decode = out_items
+    # ---- residuals: inter ones first (bucketed by size / type), then the intra ones level by level
+    def make_itx(rows):
+        plane = np.array([r[0] for r in rows], np.int64); xs = np.array([r[1] for r in rows], np.int64)
+        ys = np.array([r[2] for r in rows], np.int64); tx = np.array([r[3] for r in rows], np.int64)
+        txtp = np.zeros(len(rows), np.int64)
+        for t in np.unique(tx):
+            m = tx == t
+            v = np.array([tp for tp in valid_txtps(int(t)) if tp < 16])
+            txtp[m] = np.where(rng.random(int(m.sum())) < 0.5, 0, rng.choice(v, size=int(m.sum())))
+        return plane, xs, ys, tx, txtp
+    n_intra = len(items)
+    levels = out_items["level"].astype(np.int64)
+    n_levels = int(levels.max()) + 1 if n_intra else 0
+    order_items = np.argsort(levels, kind="stable")
+    s.intra_items = out_items[order_items]
+    s.intra_counts = np.bincount(levels, minlength=n_levels).astype(np.int32) if n_intra else np.zeros(0, np.int32)
+    ip, ix, iy, itx_, itp = make_itx(inter_itx) if inter_itx else (np.zeros(0, np.int64),) * 5
+    o = np.argsort(itx_ * 32 + itp, kind="stable")
+    ip, ix, iy, itx_, itp = ip[o], ix[o], iy[o], itx_[o], itp[o]
+    s.itx_counts = np.array([int((itx_ == t).sum()) for t in range(19)], np.int32)
+    have = [i for i, r in enumerate(itx_rows) if r is not None]
+    ap, ax, ay, atx, atp = make_itx([itx_rows[i] for i in have]) if have else (np.zeros(0, np.int64),) * 5
+    alv = levels[have] if have else np.zeros(0, np.int64)
+    o2 = np.argsort(alv * 1024 + atx * 32 + atp, kind="stable")
+    s.intra_itx_counts = np.zeros((n_levels, 19), np.int32)
+    for l_, t in zip(alv, atx):
+        s.intra_itx_counts[int(l_), int(t)] += 1
+    n_inter_itx = len(ip)
+    plane = np.concatenate([ip, ap[o2]]); xs = np.concatenate([ix, ax[o2]]); ys = np.concatenate([iy, ay[o2]])
+    tx = np.concatenate([itx_, atx[o2]]); txtp = np.concatenate([itp, atp[o2]])
+    s.intra_itx_of = np.full(n_intra, -1, np.int32)
+    for pos, k in enumerate(o2):
+        s.intra_itx_of[have[int(k)]] = n_inter_itx + pos
+    itx = np.zeros(tx.size, lib.ITX_ITEM_DT)
+    itx["x"] = xs; itx["y"] = ys; itx["plane"] = plane; itx["tx"] = tx; itx["txtp"] = txtp
+    per = np.array([TX_DIMS[int(t)][0] * TX_DIMS[int(t)][1] for t in tx], np.int64)
+    cf_off = np.concatenate([[0], np.cumsum(per)[:-1]]) if tx.size else np.zeros(0, np.int64)
+    itx["cf_off"] = cf_off
+    coef = np.zeros(int(per.sum()), cdt)
+    for t in np.unique(tx):
+        for tp in np.unique(txtp[tx == t]):
+            idx = np.nonzero((tx == t) & (txtp == tp))[0]
+            c, e = gen_coefs(rng, int(t), int(tp), max(bdmax >> 3, 2), idx.size, "full")
+            n = c.shape[1]
+            cut = rng.integers(0, n, size=idx.size)
+            c[np.arange(n)[None, :] > cut[:, None]] = 0
+            nz = c != 0
+            last = np.where(nz.any(axis=1), n - 1 - np.argmax(nz[:, ::-1], axis=1), 0)
+            itx["eob"][idx] = last if tp == 0 else np.maximum(last, 1)
+            coef[(cf_off[idx][:, None] + np.arange(n)[None, :]).ravel()] = c.ravel().astype(cdt)
+    s.itx_items, s.coef, s.n_coefs = itx, coef, int(per.sum())
+    mc = np.zeros(len(mc_rows), lib.MC_ITEM_DT)
+    for i, r_ in enumerate(mc_rows):
+        mc[i] = r_
+    s.mc_items = mc
+    n_sb = g.sb128w * g.sb128h
+    s.masks = np.zeros(n_sb, lib.AV1_FILTER_DT); s.lr_masks = np.zeros(n_sb, lib.AV1_RESTORATION_DT)
+    s.levels = np.zeros((g.sb128h * 32, g.b4_stride, 4), np.uint8)
+    s.lut = calc_eih(0)
+    return s
+
+
 def random_film_grain(rng, lag=None, luma_points=True, csfl=0, uv_points=(True, True), overlap=None):
     """Random Dav1dFilmGrainData within the ranges of tests/checkasm/filmgrain.c:156-190."""
     d = lib.FilmGrainData()
@@ -629,6 +777,12 @@ class DeviceFrame:
             lib.check(lib.frame_reserve_obmc_items(self.h, len(obmc)), "reserve_obmc_items")
             lib.np_view(lib.frame_obmc_items(self.h), lib.MC_ITEM_DT, len(obmc))[:] = obmc
             lib.check(lib.frame_set_obmc_counts(self.h, *s.n_obmc))
+        intra = getattr(s, "intra_items", None)
+        if intra is not None and len(intra):
+            lib.check(lib.frame_reserve_intra_items(self.h, len(intra), len(s.intra_counts)), "reserve_intra_items")
+            lib.np_view(lib.frame_intra_items(self.h), lib.INTRA_ITEM_DT, len(intra))[:] = intra
+            lib.check(lib.frame_set_intra_levels(self.h, len(s.intra_counts), s.intra_counts.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                 np.ascontiguousarray(s.intra_itx_counts).ctypes.data_as(C.POINTER(C.c_int32))))
         scaled = getattr(s, "scaled_items", None)
         if scaled is not None and len(scaled):
             lib.check(lib.frame_reserve_scaled_items(self.h, len(scaled)), "reserve_scaled_items")

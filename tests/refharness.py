@@ -70,6 +70,7 @@ def load():
         sig("ref_frame_recon_obmc", None, vp, vp, i, vp, i)
         sig("ref_wedge_mask", vp, i, i, i, i, i)
         sig("ref_frame_recon_scaled", None, vp, vp, i, vp, i)
+        sig("ref_frame_recon_intra", None, vp, vp, i, vp, vp, vp)
         sig("ref_frame_apply_grain", None, vp, vp, i)
         sig("ref_frame_grain_plane", vp, vp, i)
         sig("ref_fg_gen_y", None, vp, vp, i)
@@ -155,7 +156,12 @@ class RefFrame:
             self.ref.ref_frame_recon_comp(self.h, refs, len(frames), ptr(comp), len(comp), n_threads)
         if len(obmc):
             self.ref.ref_frame_recon_obmc(self.h, refs, len(frames), ptr(obmc), len(obmc))
-        self.ref.ref_frame_recon(self.h, refs, len(frames), ptr(mc), 0, ptr(itx), len(itx), ptr(cw), n_threads)
+        n_inter_itx = int(np.sum(s.itx_counts))      # the residuals of intra blocks follow in the same list
+        self.ref.ref_frame_recon(self.h, refs, len(frames), ptr(mc), 0, ptr(itx), n_inter_itx, ptr(cw), n_threads)
+        intra = getattr(s, "intra_items_decode", None)
+        if intra is not None and len(intra):
+            intra = np.ascontiguousarray(intra); of = np.ascontiguousarray(s.intra_itx_of)
+            self.ref.ref_frame_recon_intra(self.h, ptr(intra), len(intra), ptr(of), ptr(itx), ptr(cw))
         return cw
 
     def apply_grain(self, fg, is_id=0):

@@ -161,6 +161,21 @@ def test_config3_4k_10bit(rb, ref):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("w,h,bpc,inter_frac", [(96, 64, 8, 0.0), (160, 128, 10, 0.0), (192, 128, 12, 0.3), (256, 192, 8, 0.5),
+                                               (320, 256, 10, 0.15)])
+def test_intra_blocks_wavefront(rb, ref, w, h, bpc, inter_frac):
+    """Intra-predicted transform blocks reconstructed level by level on the device (edge preparation, all 14 modes,
+    angle deltas, filter-intra, availability flags) against the reference's decode-order loop
+    (rav1d_prepare_intra_edges + intra_pred + itxfm_add per block); also next to inter blocks."""
+    s = framegen.generate_intra(w, h, bpc, seed=w + bpc, inter_frac=inter_frac)
+    assert len(s.intra_counts) > 10 and set(s.intra_items["mode"]) == set(range(14))
+    INTRA = rb.STAGE_INTRA
+    a = framecheck.oracle_frame(ref, s, R)
+    b = framecheck.product_frame(s, R | INTRA)
+    framecheck.assert_planes_equal(a, b, f"intra {w}x{h}@{bpc}")
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("bpc", [8, 10])
 def test_empty_batch_and_idle_filters(rb, bpc):
     """No work items and every filter switched off in the header: each stage is a no-op, the picture comes back
