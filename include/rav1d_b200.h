@@ -524,7 +524,7 @@ int rb200_frame_set_scaled_count(Rb200Frame *f, int n);
  * needs the reconstructed pixels left of, above, above-right and below-left of it, so level = 1 + the highest
  * level among the intra blocks that own those pixels; blocks that only touch inter-predicted or absent
  * neighbours are level 0).  Per level the library predicts every block (edge preparation as
- * rav1d_prepare_intra_edges, src/ipred_prepare.rs:118, then the predictor) and adds the level's residuals.
+ * rav1d_prepare_intra_edges, src/ipred_prepare.rs:118, then the predictor, then the block's residual) in ONE launch.
  * Not covered yet: CfL, palette and inter-intra blocks. */
 typedef struct Rb200IntraItem {
     uint16_t x4, y4;          /* block position in `plane`, 4-pixel units (t.bx, t.by; >> ss for chroma) */
@@ -540,6 +540,8 @@ typedef struct Rb200IntraItem {
 } RB200_ALIGN16 Rb200IntraItem;   /* 16 bytes */
 int rb200_frame_reserve_intra_items(Rb200Frame *f, int max_items, int max_levels);
 Rb200IntraItem *rb200_frame_intra_items(Rb200Frame *f);   /* sorted by level */
+int32_t *rb200_frame_intra_itx_index(Rb200Frame *f);      /* per intra item: index of its residual in the frame's
+                                                             Rb200ItxItem list (>= the inter count), or -1 */
 /* item_counts[level]; itx_counts[level][RB200_N_RECT_TX_SIZES]: the residuals of that level's blocks, stored in the
  * frame's Rb200ItxItem list right after the inter ones (i.e. from index sum(itx_counts of rb200_frame_submit)),
  * level by level and bucketed by size within a level. */

@@ -46,6 +46,7 @@ struct Rb200Frame {
     rb200::McRefDims ref_dims;
     // intra blocks, level by level (RB200_STAGE_INTRA)
     Rb200IntraItem *h_intra, *d_intra; int max_intra, max_levels, n_levels;
+    int32_t *h_intra_itx, *d_intra_itx;           // per intra item: index of its residual in the itx list, -1 = none
     int32_t *intra_counts, *intra_itx_counts;     // [max_levels], [max_levels][RB200_N_RECT_TX_SIZES]
     // super-resolution (hdr.upscaled_width > hdr.width): plane sets at the upscaled width --
     // 0 = upscaled CDEF output, 1 = upscaled deblocked picture (what lr_line_buf holds on the CPU), 2 = LR output
@@ -231,6 +232,8 @@ extern "C" int rb200_frame_destroy(Rb200Frame *f) {
     if (f->d_scaled) cudaFree(f->d_scaled);
     if (f->h_intra) cudaFreeHost(f->h_intra);
     if (f->d_intra) cudaFree(f->d_intra);
+    if (f->h_intra_itx) cudaFreeHost(f->h_intra_itx);
+    if (f->d_intra_itx) cudaFree(f->d_intra_itx);
     free(f->intra_counts); free(f->intra_itx_counts);
     if (f->h_warp) cudaFreeHost(f->h_warp);
     if (f->d_warp) cudaFree(f->d_warp);
@@ -585,9 +588,13 @@ extern "C" int rb200_frame_reserve_intra_items(Rb200Frame *f, int max_items, int
         RB_CUDA(cudaStreamSynchronize(f->stream));
         if (f->h_intra) cudaFreeHost(f->h_intra);
         if (f->d_intra) cudaFree(f->d_intra);
-        f->h_intra = nullptr; f->d_intra = nullptr; f->max_intra = 0; f->n_levels = 0;
-        const int r = alloc_pair(&f->h_intra, &f->d_intra, (size_t)max_items);
+        if (f->h_intra_itx) cudaFreeHost(f->h_intra_itx);
+        if (f->d_intra_itx) cudaFree(f->d_intra_itx);
+        f->h_intra = nullptr; f->d_intra = nullptr; f->h_intra_itx = nullptr; f->d_intra_itx = nullptr; f->max_intra = 0; f->n_levels = 0;
+        int r = alloc_pair(&f->h_intra, &f->d_intra, (size_t)max_items);
+        if (!r) r = alloc_pair(&f->h_intra_itx, &f->d_intra_itx, (size_t)max_items);
         if (r) return r;
+        for (int i = 0; i < max_items; i++) f->h_intra_itx[i] = -1;
         f->max_intra = max_items;
     }
     if (max_levels > f->max_levels) {
@@ -600,6 +607,7 @@ extern "C" int rb200_frame_reserve_intra_items(Rb200Frame *f, int max_items, int
     return 0;
 }
 extern "C" Rb200IntraItem *rb200_frame_intra_items(Rb200Frame *f) { return f ? f->h_intra : nullptr; }
+extern "C" int32_t *rb200_frame_intra_itx_index(Rb200Frame *f) { return f ? f->h_intra_itx : nullptr; }
 extern "C" int rb200_frame_set_intra_levels(Rb200Frame *f, int n_levels, const int32_t *item_counts, const int32_t *itx_counts) {
     if (!f || n_levels < 0 || n_levels > f->max_levels || (n_levels && (!item_counts || !itx_counts)))
         return set_error(-22, "frame_set_intra_levels: more levels than reserved");
@@ -790,7 +798,10 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
             if ((stages & RB200_STAGE_INTRA) && f->n_levels) {
                 int n_in = 0;
                 for (int l = 0; l < f->n_levels; l++) n_in += f->intra_counts[l];
-                if (n_in) RB_CUDA(cudaMemcpyAsync(f->d_intra, f->h_intra, (size_t)n_in * sizeof(Rb200IntraItem), cudaMemcpyHostToDevice, st));
+                if (n_in) {
+                    RB_CUDA(cudaMemcpyAsync(f->d_intra, f->h_intra, (size_t)n_in * sizeof(Rb200IntraItem), cudaMemcpyHostToDevice, st));
+                    RB_CUDA(cudaMemcpyAsync(f->d_intra_itx, f->h_intra_itx, (size_t)n_in * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+                }
             }
             if (f->n_scaled) RB_CUDA(cudaMemcpyAsync(f->d_scaled, f->h_scaled, (size_t)f->n_scaled * sizeof(Rb200McScaledItem), cudaMemcpyHostToDevice, st));
             if (f->n_obmc_above + f->n_obmc_left)
@@ -854,25 +865,17 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
             }
             off += itx_counts[t];
         }
-        // ---- intra blocks: per dependency level, predict every block of the level, then add its residuals
+        // ---- intra blocks: one launch per dependency level; a CTA prepares a block's edge from the reconstructed
+        // picture, predicts it and adds its residual
         if ((stages & RB200_STAGE_INTRA) && f->n_levels) {
             const void *cf = upload == RB200_UPLOAD_ZERO_COPY_COEF ? f->h_coef : f->d_coef;
             int ioff = 0;
             for (int l = 0; l < f->n_levels; l++) {
-                if (f->intra_counts[l]) {
-                    if ((r = intra_items_launch(f->planes[0], f->d_intra + ioff, f->intra_counts[l], g.bw, g.bh, g.ss_hor, g.ss_ver,
-                                                f->bdmax, st))) return r;
-                    f->launches++;
-                    ioff += f->intra_counts[l];
-                }
-                for (int t = 0; t < RB200_N_RECT_TX_SIZES; t++) {
-                    const int c = f->intra_itx_counts[l * RB200_N_RECT_TX_SIZES + t];
-                    if (c) {
-                        if ((r = itx_launch(t, f->planes[0], cf, f->d_itx + off, c, f->bdmax, st))) return r;
-                        f->launches++;
-                    }
-                    off += c;
-                }
+                if (!f->intra_counts[l]) continue;
+                if ((r = intra_items_launch(f->planes[0], f->d_intra + ioff, f->d_intra_itx + ioff, f->d_itx, cf, f->intra_counts[l], g.bw,
+                                            g.bh, g.ss_hor, g.ss_ver, f->bdmax, st))) return r;
+                f->launches++;
+                ioff += f->intra_counts[l];
             }
         }
     }

@@ -11,6 +11,7 @@
 // over its 4x2 sub-blocks (a sub-block needs the ones to its left, above and above-left).
 #include "common.cuh"
 #include "tables.cuh"
+#include "itx_block.cuh"
 
 namespace rb200 {
 
@@ -299,11 +300,13 @@ ipred_kernel(int mode, uint8_t *dst8, int64_t stride, const typename BD::pixel *
 // The picture rows above a superblock row are still unfiltered when this runs (the in-loop filters come after
 // the whole reconstruction), so the reference's saved pre-filter edge (f.ipred_edge) is the picture itself.
 template <typename BD>
-__global__ void __launch_bounds__(256)
-intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, int frame_w4, int frame_h4, int ss_hor_c,
-                   int ss_ver_c, int bdmax) {
+__global__ void __launch_bounds__(128)
+intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, const int32_t *__restrict__ itx_of,
+                   const Rb200ItxItem *__restrict__ itx, const typename BD::coef *__restrict__ cf, int frame_w4, int frame_h4,
+                   int ss_hor_c, int ss_ver_c, int bdmax) {
     using pixel = typename BD::pixel;
     __shared__ IpScratch<pixel> S;
+    __shared__ int itile[65 * 32];          // the residual's transform tile (largest: 64 x 32 + padding)
     const Rb200IntraItem it = items[blockIdx.x];
     const int tid = threadIdx.x;
     const int ss_hor = it.plane ? ss_hor_c : 0, ss_ver = it.plane ? ss_ver_c : 0;
@@ -393,13 +396,25 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, in
     const int max_w = ((frame_w4 * 4) >> ss_hor) - 4 * x, max_h = ((frame_h4 * 4) >> ss_ver) - 4 * y;
     ipred_block<BD>(S, mode, dst8, stride, tw * 4, th * 4, mode == IP_FILTER ? (it.angle & 7) : (angle | (is_sm << 9) | (eief << 10)),
                     max_w, max_h, bdmax);
+    // ---- the block's residual on top of its prediction, in the same launch (the prediction is visible to the CTA)
+    const int ti = itx_of ? itx_of[blockIdx.x] : -1;
+    if (ti < 0) return;
+    __syncthreads();
+    const Rb200ItxItem t = itx[ti];
+    switch (t.tx) {
+#define CASE(TX) case TX: itx_add_block<BD, TX>(itile, tid, tid < ItxGeom<TX>::T, t, cur, cf, bdmax); break;
+        CASE(0) CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9)
+        CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16) CASE(17) CASE(18)
+#undef CASE
+    default: break;
+    }
 }
 
-int intra_items_launch(const Rb200Planes &cur, const Rb200IntraItem *d_items, int n, int frame_w4, int frame_h4, int ss_hor,
-                       int ss_ver, int bdmax, cudaStream_t st) {
+int intra_items_launch(const Rb200Planes &cur, const Rb200IntraItem *d_items, const int32_t *d_itx_of, const Rb200ItxItem *d_itx,
+                       const void *cf, int n, int frame_w4, int frame_h4, int ss_hor, int ss_ver, int bdmax, cudaStream_t st) {
     if (n <= 0) return 0;
-    if (bdmax > 255) intra_items_kernel<BD16><<<n, 256, 0, st>>>(cur, d_items, frame_w4, frame_h4, ss_hor, ss_ver, bdmax);
-    else intra_items_kernel<BD8><<<n, 256, 0, st>>>(cur, d_items, frame_w4, frame_h4, ss_hor, ss_ver, bdmax);
+    if (bdmax > 255) intra_items_kernel<BD16><<<n, 128, 0, st>>>(cur, d_items, d_itx_of, d_itx, (const int32_t *)cf, frame_w4, frame_h4, ss_hor, ss_ver, bdmax);
+    else intra_items_kernel<BD8><<<n, 128, 0, st>>>(cur, d_items, d_itx_of, d_itx, (const int16_t *)cf, frame_w4, frame_h4, ss_hor, ss_ver, bdmax);
     RB_LAUNCH_CHECK();
     return 0;
 }

@@ -634,6 +634,7 @@ def generate_intra(w, h, bpc, seed=1, inter_frac=0.0):
     n_levels = int(levels.max()) + 1 if n_intra else 0
     order_items = np.argsort(levels, kind="stable")
     s.intra_items = out_items[order_items]
+    s._order_items = order_items
     s.intra_counts = np.bincount(levels, minlength=n_levels).astype(np.int32) if n_intra else np.zeros(0, np.int32)
     ip, ix, iy, itx_, itp = make_itx(inter_itx) if inter_itx else (np.zeros(0, np.int64),) * 5
     o = np.argsort(itx_ * 32 + itp, kind="stable")
@@ -652,6 +653,7 @@ def generate_intra(w, h, bpc, seed=1, inter_frac=0.0):
     s.intra_itx_of = np.full(n_intra, -1, np.int32)
     for pos, k in enumerate(o2):
         s.intra_itx_of[have[int(k)]] = n_inter_itx + pos
+    s.intra_itx_of_sorted = s.intra_itx_of[s._order_items]       # same, in the level-sorted order of intra_items
     itx = np.zeros(tx.size, lib.ITX_ITEM_DT)
     itx["x"] = xs; itx["y"] = ys; itx["plane"] = plane; itx["tx"] = tx; itx["txtp"] = txtp
     per = np.array([TX_DIMS[int(t)][0] * TX_DIMS[int(t)][1] for t in tx], np.int64)
@@ -781,6 +783,7 @@ class DeviceFrame:
         if intra is not None and len(intra):
             lib.check(lib.frame_reserve_intra_items(self.h, len(intra), len(s.intra_counts)), "reserve_intra_items")
             lib.np_view(lib.frame_intra_items(self.h), lib.INTRA_ITEM_DT, len(intra))[:] = intra
+            lib.np_view(lib.frame_intra_itx_index(self.h), np.int32, len(intra))[:] = s.intra_itx_of_sorted
             lib.check(lib.frame_set_intra_levels(self.h, len(s.intra_counts), s.intra_counts.ctypes.data_as(C.POINTER(C.c_int32)),
                                                  np.ascontiguousarray(s.intra_itx_counts).ctypes.data_as(C.POINTER(C.c_int32))))
         scaled = getattr(s, "scaled_items", None)
