@@ -533,8 +533,8 @@ def generate_recon_layout(w, h, bpc, layout, seed=1, comp_frac=0.3, warp_frac=0.
     return s
 
 
-def generate_intra(w, h, bpc, seed=1, inter_frac=0.0):
-    """A 4:2:0 frame whose 16x16 blocks are intra predicted (a fraction `inter_frac` of them translational inter blocks):
+def generate_intra(w, h, bpc, seed=1, inter_frac=0.0, layout=None):
+    """A frame (4:2:0 unless `layout` says otherwise) whose 16x16 blocks are intra predicted (a fraction `inter_frac` of them translational inter blocks):
     per transform block a coded mode, angle delta, edge-availability flags consistent with the decode order (raster over
     blocks; inside a block luma transform blocks in raster order, then U, then V), the wavefront level the batch
     path needs, and a residual.  Reconstruction only (no filter metadata)."""
@@ -544,53 +544,59 @@ def generate_intra(w, h, bpc, seed=1, inter_frac=0.0):
     bdmax = (1 << bpc) - 1
     pdt, cdt = (np.uint16, np.int32) if bpc > 8 else (np.uint8, np.int16)
     s = SynthFrame()
-    s.w, s.h, s.bpc, s.bdmax, s.layout = w, h, bpc, bdmax, lib.LAYOUT_I420
+    layout = lib.LAYOUT_I420 if layout is None else layout
+    ssx, ssy = int(layout != lib.LAYOUT_I444), int(layout == lib.LAYOUT_I420)
+    n_planes = 1 if layout == lib.LAYOUT_I400 else 3
+    s.w, s.h, s.bpc, s.bdmax, s.layout = w, h, bpc, bdmax, layout
     hd = lib.FrameHeader()
-    hd.width, hd.height, hd.bpc, hd.layout = w, h, bpc, lib.LAYOUT_I420
+    hd.width, hd.height, hd.bpc, hd.layout = w, h, bpc, layout
     s.hdr = hd
     g = s.geom = geometry(hd)
+    g.ss_hor, g.ss_ver, g.n_planes = (ssx, ssy, 3) if n_planes == 3 else (0, 0, 1)
     aw, ah = (w + 127) & ~127, (h + 127) & ~127
     s.aw, s.ah = aw, ah
-    s.ref = [np.zeros((ah, aw), pdt), np.zeros((ah // 2, aw // 2), pdt), np.zeros((ah // 2, aw // 2), pdt)]
+    s.ref = [np.zeros((ah, aw), pdt)] + [np.zeros((ah >> ssy, aw >> ssx), pdt) for _ in range(n_planes - 1)]
     s.ref[0][:h, :w] = smooth_plane(rng, h, w, bdmax)
-    for p in (1, 2):
-        s.ref[p][:(h + 1) // 2, :(w + 1) // 2] = smooth_plane(rng, (h + 1) // 2, (w + 1) // 2, bdmax, cell=8)
+    for p in range(1, n_planes):
+        s.ref[p][:(h + ssy) >> ssy, :(w + ssx) >> ssx] = smooth_plane(rng, (h + ssy) >> ssy, (w + ssx) >> ssx, bdmax, cell=8)
     nbx, nby = w // BLK, h // BLK
     eief = int(rng.integers(0, 2))
     TXS = {4: 0, 8: 1, 16: 2}
     # per-plane maps in 4x4 cells: decode index of the transform block that owns the cell, its level
-    pw4 = [g.bw, g.bw >> 1, g.bw >> 1]; ph4 = [g.bh, g.bh >> 1, g.bh >> 1]
+    psx = [0] + [ssx] * (n_planes - 1); psy = [0] + [ssy] * (n_planes - 1)
+    pw4 = [g.bw >> psx[p] for p in range(n_planes)]; ph4 = [g.bh >> psy[p] for p in range(n_planes)]
     BIG = 1 << 60                                                         # not decoded yet: never available
-    dec = [np.full((ph4[p], pw4[p]), BIG, np.int64) for p in range(3)]
-    lvl = [np.full((ph4[p], pw4[p]), -1, np.int64) for p in range(3)]
+    dec = [np.full((ph4[p], pw4[p]), BIG, np.int64) for p in range(n_planes)]
+    lvl = [np.full((ph4[p], pw4[p]), -1, np.int64) for p in range(n_planes)]
     is_inter = rng.random((nby, nbx)) < inter_frac
     for byi, bxi in zip(*np.nonzero(is_inter)):                           # inter blocks are reconstructed before any intra block
-        for p in range(3):
-            c = BLK // 4 >> (1 if p else 0)
-            dec[p][byi * c:(byi + 1) * c, bxi * c:(bxi + 1) * c] = -1
+        for p in range(n_planes):
+            cx, cy = BLK // 4 >> psx[p], BLK // 4 >> psy[p]
+            dec[p][byi * cy:(byi + 1) * cy, bxi * cx:(bxi + 1) * cx] = -1
     items, itx_rows, mc_rows = [], [], []      # decode order
     inter_itx = []
     for byi in range(nby):
         for bxi in range(nbx):
             if is_inter[byi, bxi]:
                 mvx, mvy, f2d = int(rng.integers(-128, 129)), int(rng.integers(-128, 129)), int(rng.integers(0, 10))
-                for p in range(3):
-                    sh = 1 if p else 0
-                    x0, y0 = bxi * BLK >> sh, byi * BLK >> sh
-                    mc_rows.append((x0, y0, x0 + (mvx >> (3 + sh)), y0 + (mvy >> (3 + sh)), BLK >> sh, BLK >> sh, p, 0,
-                                    (mvx & 7) << 1 if p == 0 else mvx & 15, (mvy & 7) << 1 if p == 0 else mvy & 15, f2d, 0))
+                for p in range(n_planes):
+                    sx, sy = psx[p], psy[p]
+                    x0, y0 = bxi * BLK >> sx, byi * BLK >> sy
+                    mc_rows.append((x0, y0, x0 + (mvx >> (3 + sx)), y0 + (mvy >> (3 + sy)), BLK >> sx, BLK >> sy, p, 0,
+                                    (mvx & (15 >> (1 - sx))) << (1 - sx), (mvy & (15 >> (1 - sy))) << (1 - sy), f2d, 0))
                     if rng.random() < 0.7:
-                        inter_itx.append((p, x0, y0, 2 if p == 0 else 1))
+                        rect = {(0, 0): 2, (1, 1): 1, (1, 0): next(t for t in range(19) if TX_DIMS[t] == (8, 16))}[(sx, sy)]
+                        inter_itx.append((p, x0, y0, rect))
                 continue
-            for p in range(3):
-                bsz = BLK >> (1 if p else 0)                       # block size in this plane, pixels
-                tsz = int(rng.choice([4, 8, 16] if p == 0 else [4, 8]))
+            for p in range(n_planes):
+                bwp, bhp = BLK >> psx[p], BLK >> psy[p]            # block size in this plane, pixels
+                tsz = int(rng.choice([t for t in (4, 8, 16) if t <= min(bwp, bhp)]))
                 mode = int(rng.integers(0, 14 if p == 0 else 13))  # filter-intra is luma only
                 delta = int(rng.integers(-3, 4)) if 1 <= mode <= 8 else (int(rng.integers(0, 5)) if mode == 13 else 0)
                 is_sm = int(rng.integers(0, 2))
-                x0, y0 = bxi * bsz // 4, byi * bsz // 4            # 4-px units
-                for ty in range(0, bsz // 4, tsz // 4):
-                    for tx_ in range(0, bsz // 4, tsz // 4):
+                x0, y0 = bxi * bwp // 4, byi * bhp // 4            # 4-px units
+                for ty in range(0, bhp // 4, tsz // 4):
+                    for tx_ in range(0, bwp // 4, tsz // 4):
                         x4, y4, t4 = x0 + tx_, y0 + ty, tsz // 4
                         idx = len(items)
                         have_left, have_top = int(x4 > 0), int(y4 > 0)

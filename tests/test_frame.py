@@ -176,6 +176,16 @@ def test_intra_blocks_wavefront(rb, ref, w, h, bpc, inter_frac):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("layout", [0, 2, 3])
+def test_intra_blocks_other_layouts(rb, ref, layout):
+    """The intra wavefront in 4:0:0, 4:2:2 and 4:4:4 (chroma block and transform sizes follow the sub-sampling)."""
+    s = framegen.generate_intra(160, 128, 10, seed=40 + layout, inter_frac=0.25, layout=layout)
+    a = framecheck.oracle_frame(ref, s, R)
+    b = framecheck.product_frame(s, R | rb.STAGE_INTRA)
+    framecheck.assert_planes_equal(a, b, f"intra layout {layout}")
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("bpc", [8, 10])
 def test_empty_batch_and_idle_filters(rb, bpc):
     """No work items and every filter switched off in the header: each stage is a no-op, the picture comes back
