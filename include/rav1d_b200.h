@@ -525,10 +525,13 @@ int rb200_frame_set_scaled_count(Rb200Frame *f, int n);
  * level among the intra blocks that own those pixels; blocks that only touch inter-predicted or absent
  * neighbours are level 0).  Per level the library predicts every block (edge preparation as
  * rav1d_prepare_intra_edges, src/ipred_prepare.rs:118, then the predictor, then the block's residual) in ONE launch.
- * Not covered yet: CfL, palette and inter-intra blocks. */
+ * Chroma from luma: a chroma item with mode 13 (UV_CFL_PRED) covers the whole chroma block, `angle` carries cfl_alpha of
+ * its plane (non-zero; a plane with alpha 0 is a plain DC item) and bits 13-15 of w4_end / h4_end the w_pad / h_pad
+ * arguments of cfl_ac; its level must exceed the levels of the block's luma transform blocks.
+ * Not covered yet: palette and inter-intra blocks. */
 typedef struct Rb200IntraItem {
     uint16_t x4, y4;          /* block position in `plane`, 4-pixel units (t.bx, t.by; >> ss for chroma) */
-    uint16_t w4_end, h4_end;  /* tile end in the same units: the `w`, `h` arguments of rav1d_prepare_intra_edges */
+    uint16_t w4_end, h4_end;  /* tile end in the same units: the `w`, `h` arguments of rav1d_prepare_intra_edges (bits 0-12) */
     uint8_t plane;
     uint8_t tw4, th4;         /* transform block size, 4-pixel units (1 .. 16) */
     uint8_t mode;             /* coded IntraPredMode: DC 0, VERT 1, HOR 2, DIAG_DOWN_LEFT 3 .. VERT_LEFT 8, SMOOTH 9,

@@ -627,15 +627,36 @@ void ref_frame_recon_intra(RefFrame *r, const Rb200IntraItem *items, int n, cons
         int angle = it->angle;
         const int max_w = ((4 * f->bw) >> ss_hor) - 4 * it->x4, max_h = ((4 * f->bh) >> ss_ver) - 4 * it->y4;
         const int intra_flags = (is_sm << 9) | (eief << 10);
-        if (r->hbd) {
+        const int w4_end = it->w4_end & 0x1fff, h4_end = it->h4_end & 0x1fff;
+        if (pl && it->mode == 13) {   /* chroma from luma, src/recon_tmpl.c:1376-1422 */
+            int16_t ac[32 * 32];
+            const uint8_t *ysrc = (const uint8_t *)f->cur.data[0] + f->cur.stride[0] * ((it->y4 << ss_ver) * 4) +
+                                  (ptrdiff_t)((it->x4 << ss_hor) * 4) * px;
+            ((void (*)(int16_t *, const void *, ptrdiff_t, int, int, int, int))f->dsp->ipred.cfl_ac[f->cur.p.layout - 1])(
+                ac, ysrc, f->cur.stride[0], it->w4_end >> 13, it->h4_end >> 13, it->tw4 * 4, it->th4 * 4);
+            int a0 = 0;
+            if (r->hbd) {
+                uint16_t *edge = edge_buf + 128 + 16;
+                const int m = dav1d_prepare_intra_edges_16bpc(it->x4, have_left, it->y4, have_top, w4_end, h4_end, 0, (const uint16_t *)dst, stride,
+                                                              NULL, DC_PRED, &a0, it->tw4, it->th4, 0, edge, r->bdmax);
+                ((void (*)(void *, ptrdiff_t, const void *, int, int, const int16_t *, int, int))f->dsp->ipred.cfl_pred[m])(
+                    dst, stride, edge, it->tw4 * 4, it->th4 * 4, ac, it->angle, r->bdmax);
+            } else {
+                uint8_t *edge = (uint8_t *)edge_buf + 128 + 16;
+                const int m = dav1d_prepare_intra_edges_8bpc(it->x4, have_left, it->y4, have_top, w4_end, h4_end, 0, dst, stride, NULL, DC_PRED,
+                                                             &a0, it->tw4, it->th4, 0, edge);
+                ((void (*)(void *, ptrdiff_t, const void *, int, int, const int16_t *, int))f->dsp->ipred.cfl_pred[m])(
+                    dst, stride, edge, it->tw4 * 4, it->th4 * 4, ac, it->angle);
+            }
+        } else if (r->hbd) {
             uint16_t *edge = edge_buf + 128 + 16;
-            const int m = dav1d_prepare_intra_edges_16bpc(it->x4, have_left, it->y4, have_top, it->w4_end, it->h4_end, ef, (const uint16_t *)dst,
+            const int m = dav1d_prepare_intra_edges_16bpc(it->x4, have_left, it->y4, have_top, w4_end, h4_end, ef, (const uint16_t *)dst,
                                                           stride, NULL, it->mode, &angle, it->tw4, it->th4, eief, edge, r->bdmax);
             ((void (*)(void *, ptrdiff_t, const void *, int, int, int, int, int, int))f->dsp->ipred.intra_pred[m])(
                 dst, stride, edge, it->tw4 * 4, it->th4 * 4, angle | intra_flags, max_w, max_h, r->bdmax);
         } else {
             uint8_t *edge = (uint8_t *)edge_buf + 128 + 16;
-            const int m = dav1d_prepare_intra_edges_8bpc(it->x4, have_left, it->y4, have_top, it->w4_end, it->h4_end, ef, dst, stride, NULL,
+            const int m = dav1d_prepare_intra_edges_8bpc(it->x4, have_left, it->y4, have_top, w4_end, h4_end, ef, dst, stride, NULL,
                                                          it->mode, &angle, it->tw4, it->th4, eief, edge);
             ((void (*)(void *, ptrdiff_t, const void *, int, int, int, int, int))f->dsp->ipred.intra_pred[m])(
                 dst, stride, edge, it->tw4 * 4, it->th4 * 4, angle | intra_flags, max_w, max_h);

@@ -81,7 +81,7 @@ struct IpScratch {
 // visible on entry).  mode: IP_*; angle: the reference's packed argument.
 template <typename BD>
 __device__ void ipred_block(IpScratch<typename BD::pixel> &S, int mode, uint8_t *dst8, int64_t stride, int w, int h, int angle,
-                            int max_w, int max_h, int bdmax) {
+                            int max_w, int max_h, int bdmax, const int16_t *cfl_ac = nullptr, int cfl_alpha = 0) {
     using pixel = typename BD::pixel;
     pixel *work = S.work, *tile = S.tile;
     int &dc_s = S.dc;
@@ -118,7 +118,15 @@ __device__ void ipred_block(IpScratch<typename BD::pixel> &S, int mode, uint8_t 
             dc_s = (int)dc;
         }
         __syncthreads();
-        for (int i = tid; i < n; i += blockDim.x) put(i % w, i / w, dc_s);
+        if (cfl_ac) {   // chroma from luma: dc + alpha * ac (cfl_pred, src/ipred_tmpl.c:71-84)
+            for (int i = tid; i < n; i += blockDim.x) {
+                const int diff = cfl_alpha * cfl_ac[i];
+                const int m = (abs(diff) + 32) >> 6;
+                put(i % w, i / w, iclip(dc_s + (diff < 0 ? -m : m), 0, bdmax));
+            }
+        } else {
+            for (int i = tid; i < n; i += blockDim.x) put(i % w, i / w, dc_s);
+        }
         break;
     }
     case IP_VERT:
@@ -307,6 +315,8 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
     using pixel = typename BD::pixel;
     __shared__ IpScratch<pixel> S;
     __shared__ int itile[65 * 32];          // the residual's transform tile (largest: 64 x 32 + padding)
+    __shared__ int16_t ac_s[32 * 32];       // chroma-from-luma: the sub-sampled, zero-mean luma of the block
+    __shared__ int red_s[4];
     const Rb200IntraItem it = items[blockIdx.x];
     const int tid = threadIdx.x;
     const int ss_hor = it.plane ? ss_hor_c : 0, ss_ver = it.plane ? ss_ver_c : 0;
@@ -317,11 +327,12 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
     const int have_left = it.flags & 1, have_top = (it.flags >> 1) & 1;
     const int top_has_right = (it.flags >> 2) & 1, left_has_bottom = (it.flags >> 3) & 1;
     const int is_sm = (it.flags >> 4) & 1, eief = (it.flags >> 5) & 1;
-    const int tw = it.tw4, th = it.th4, x = it.x4, y = it.y4, w = it.w4_end, h = it.h4_end;
+    const int tw = it.tw4, th = it.th4, x = it.x4, y = it.y4, w = it.w4_end & 0x1fff, h = it.h4_end & 0x1fff;
+    const bool cfl = it.plane && it.mode == 13;     // UV_CFL_PRED shares the number of luma's FILTER_PRED
     const int bitdepth = BD::hbd ? bpc_from_max(bdmax) : 8;
     // ---- coded mode -> implementation mode (src/ipred_prepare_tmpl.c:89-116); coded numbering: DC 0, VERT 1, HOR 2,
     // DIAG_DOWN_LEFT 3, DIAG_DOWN_RIGHT 4, VERT_RIGHT 5, HOR_DOWN 6, HOR_UP 7, VERT_LEFT 8, SMOOTH 9 .. PAETH 12, FILTER 13
-    int mode = it.mode, angle = it.angle;
+    int mode = cfl ? IP_DC : it.mode, angle = cfl ? 0 : it.angle;
     if (mode >= 1 && mode <= 8) {
         const int map[8] = { 90, 180, 45, 135, 113, 157, 203, 67 };
         angle = map[mode - 1] + 3 * angle;
@@ -394,8 +405,40 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
     }
     __syncthreads();
     const int max_w = ((frame_w4 * 4) >> ss_hor) - 4 * x, max_h = ((frame_h4 * 4) >> ss_ver) - 4 * y;
-    ipred_block<BD>(S, mode, dst8, stride, tw * 4, th * 4, mode == IP_FILTER ? (it.angle & 7) : (angle | (is_sm << 9) | (eief << 10)),
-                    max_w, max_h, bdmax);
+    if (cfl) {
+        // cfl_ac (src/ipred_tmpl.c:657-703) on the block's reconstructed luma; the padding counts ride in the top bits
+        // of w4_end / h4_end
+        const int w_pad = it.w4_end >> 13, h_pad = it.h4_end >> 13;
+        const int cw = tw * 4, ch = th * 4, vw = cw - 4 * w_pad, vh = ch - 4 * h_pad;
+        const int64_t lstride = plane_stride(cur, 0);
+        const uint8_t *ypx = plane_ptr(cur, 0) + (int64_t)((y << ss_ver) * 4) * lstride + (int64_t)((x << ss_hor) * 4) * sizeof(pixel);
+        int part = 0;
+        for (int i = tid; i < cw * ch; i += blockDim.x) {
+            const int cx = imin(i % cw, vw - 1), cy = imin(i / cw, vh - 1);
+            const pixel *p = (const pixel *)(ypx + (int64_t)(cy << ss_ver) * lstride) + (cx << ss_hor);
+            int sum = p[0];
+            if (ss_hor) sum += p[1];
+            if (ss_ver) {
+                const pixel *q = (const pixel *)((const uint8_t *)p + lstride);
+                sum += q[0];
+                if (ss_hor) sum += q[1];
+            }
+            sum <<= 1 + !ss_ver + !ss_hor;
+            ac_s[i] = (int16_t)sum;
+            part += sum;
+        }
+        for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if ((tid & 31) == 0) red_s[tid >> 5] = part;
+        __syncthreads();
+        const int log2sz = ulog2(cw) + ulog2(ch);
+        const int mean = (((1 << log2sz) >> 1) + red_s[0] + red_s[1] + red_s[2] + red_s[3]) >> log2sz;
+        for (int i = tid; i < cw * ch; i += blockDim.x) ac_s[i] = (int16_t)(ac_s[i] - mean);
+        __syncthreads();
+        ipred_block<BD>(S, mode, dst8, stride, cw, ch, 0, max_w, max_h, bdmax, ac_s, it.angle);
+    } else {
+        ipred_block<BD>(S, mode, dst8, stride, tw * 4, th * 4, mode == IP_FILTER ? (it.angle & 7) : (angle | (is_sm << 9) | (eief << 10)),
+                        max_w, max_h, bdmax);
+    }
     // ---- the block's residual on top of its prediction, in the same launch (the prediction is visible to the CTA)
     const int ti = itx_of ? itx_of[blockIdx.x] : -1;
     if (ti < 0) return;

@@ -533,7 +533,7 @@ def generate_recon_layout(w, h, bpc, layout, seed=1, comp_frac=0.3, warp_frac=0.
     return s
 
 
-def generate_intra(w, h, bpc, seed=1, inter_frac=0.0, layout=None):
+def generate_intra(w, h, bpc, seed=1, inter_frac=0.0, layout=None, cfl_frac=0.25):
     """A frame (4:2:0 unless `layout` says otherwise) whose 16x16 blocks are intra predicted (a fraction `inter_frac` of them translational inter blocks):
     per transform block a coded mode, angle delta, edge-availability flags consistent with the decode order (raster over
     blocks; inside a block luma transform blocks in raster order, then U, then V), the wavefront level the batch
@@ -588,8 +588,30 @@ def generate_intra(w, h, bpc, seed=1, inter_frac=0.0, layout=None):
                         rect = {(0, 0): 2, (1, 1): 1, (1, 0): next(t for t in range(19) if TX_DIMS[t] == (8, 16))}[(sx, sy)]
                         inter_itx.append((p, x0, y0, rect))
                 continue
+            uv_cfl = rng.random() < cfl_frac                       # chroma from luma for this block (needs its luma first)
             for p in range(n_planes):
                 bwp, bhp = BLK >> psx[p], BLK >> psy[p]            # block size in this plane, pixels
+                if p and uv_cfl:
+                    # one item per plane over the whole chroma block; alpha 0 = plain DC prediction (src/recon.rs, CFL branch)
+                    alpha = int(rng.integers(-16, 17))
+                    x4, y4, tw4, th4 = bxi * bwp // 4, byi * bhp // 4, bwp // 4, bhp // 4
+                    idx = len(items)
+                    have_left, have_top = int(x4 > 0), int(y4 > 0)
+                    W4, H4 = pw4[p], ph4[p]
+                    level = int(lvl[0][byi * 4:(byi + 1) * 4, bxi * 4:(bxi + 1) * 4].max()) + 1 if alpha else 0
+                    for (xa, xb, ya, yb) in ((x4 - 1, x4, y4 - 1, y4 + th4), (x4, x4 + tw4, y4 - 1, y4)):
+                        lv = lvl[p][max(ya, 0):min(yb, H4), max(xa, 0):min(xb, W4)]
+                        if lv.size: level = max(level, int(lv.max()) + 1)
+                    dec[p][y4:y4 + th4, x4:x4 + tw4] = idx
+                    lvl[p][y4:y4 + th4, x4:x4 + tw4] = level
+                    w_pad = int(rng.integers(0, tw4)) if rng.random() < 0.3 else 0
+                    h_pad = int(rng.integers(0, th4)) if rng.random() < 0.3 else 0
+                    flags = have_left | have_top << 1 | eief << 5
+                    items.append((x4, y4, W4 | (w_pad << 13 if alpha else 0), H4 | (h_pad << 13 if alpha else 0), p, tw4, th4,
+                                  13 if alpha else 0, alpha, flags, level))
+                    rect = next(t for t in range(19) if TX_DIMS[t] == (bwp, bhp))
+                    itx_rows.append((p, x4 * 4, y4 * 4, rect) if rng.random() < 0.8 else None)
+                    continue
                 tsz = int(rng.choice([t for t in (4, 8, 16) if t <= min(bwp, bhp)]))
                 mode = int(rng.integers(0, 14 if p == 0 else 13))  # filter-intra is luma only
                 delta = int(rng.integers(-3, 4)) if 1 <= mode <= 8 else (int(rng.integers(0, 5)) if mode == 13 else 0)

@@ -169,6 +169,7 @@ def test_intra_blocks_wavefront(rb, ref, w, h, bpc, inter_frac):
     (rav1d_prepare_intra_edges + intra_pred + itxfm_add per block); also next to inter blocks."""
     s = framegen.generate_intra(w, h, bpc, seed=w + bpc, inter_frac=inter_frac)
     assert len(s.intra_counts) > 10 and set(s.intra_items["mode"]) == set(range(14))
+    assert ((s.intra_items["plane"] > 0) & (s.intra_items["mode"] == 13)).sum() > 3          # chroma-from-luma blocks
     INTRA = rb.STAGE_INTRA
     a = framecheck.oracle_frame(ref, s, R)
     b = framecheck.product_frame(s, R | INTRA)
