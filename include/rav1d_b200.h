@@ -528,7 +528,10 @@ int rb200_frame_set_scaled_count(Rb200Frame *f, int n);
  * Chroma from luma: a chroma item with mode 13 (UV_CFL_PRED) covers the whole chroma block, `angle` carries cfl_alpha of
  * its plane (non-zero; a plane with alpha 0 is a plain DC item) and bits 13-15 of w4_end / h4_end the w_pad / h_pad
  * arguments of cfl_ac; its level must exceed the levels of the block's luma transform blocks.
- * Not covered yet: palette and inter-intra blocks. */
+ * Inter-intra (src/recon.rs:3475-3550,3742-3850): flags bit 6; one item per plane over the whole block with mode DC / VERT /
+ * HOR / SMOOTH, angle = -1 for the inter-intra mask of that mode (dav1d_ii_masks) or the wedge index 0 .. 15; the block's
+ * inter prediction comes from the ordinary Rb200McItem lists, its residual must be attached to the intra item.
+ * Not covered yet: palette blocks. */
 typedef struct Rb200IntraItem {
     uint16_t x4, y4;          /* block position in `plane`, 4-pixel units (t.bx, t.by; >> ss for chroma) */
     uint16_t w4_end, h4_end;  /* tile end in the same units: the `w`, `h` arguments of rav1d_prepare_intra_edges (bits 0-12) */
@@ -538,7 +541,7 @@ typedef struct Rb200IntraItem {
                                  SMOOTH_V 10, SMOOTH_H 11, PAETH 12, FILTER 13 */
     int8_t angle;             /* angle_delta -3 .. 3 (directional modes) or the filter-intra set 0 .. 4 */
     uint8_t flags;            /* 1 have_left, 2 have_top, 4 EDGE_TOP_HAS_RIGHT, 8 EDGE_LEFT_HAS_BOTTOM, 16 smooth
-                                 neighbour (sm_flag), 32 seq_hdr.intra_edge_filter */
+                                 neighbour (sm_flag), 32 seq_hdr.intra_edge_filter, 64 inter-intra */
     uint16_t level;
 } RB200_ALIGN16 Rb200IntraItem;   /* 16 bytes */
 int rb200_frame_reserve_intra_items(Rb200Frame *f, int max_items, int max_levels);

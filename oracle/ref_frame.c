@@ -648,6 +648,28 @@ void ref_frame_recon_intra(RefFrame *r, const Rb200IntraItem *items, int n, cons
                 ((void (*)(void *, ptrdiff_t, const void *, int, int, const int16_t *, int))f->dsp->ipred.cfl_pred[m])(
                     dst, stride, edge, it->tw4 * 4, it->th4 * 4, ac, it->angle);
             }
+        } else if (it->flags & 64) {   /* inter-intra, src/recon_tmpl.c:1665-1692,1795-1831 */
+            static int ii_ready;
+            if (!ii_ready) { dav1d_init_interintra_masks(); dav1d_init_wedge_masks(); ii_ready = 1; }
+            uint16_t tmp[32 * 32];
+            const int bw = it->tw4 * 4, bh = it->th4 * 4;
+            const int bs = wedge_bs(bw << ss_hor, bh << ss_ver);
+            const int li = pl ? DAV1D_PIXEL_LAYOUT_I444 - f->cur.p.layout : 0;
+            const int ii_mode = it->mode == SMOOTH_PRED ? II_SMOOTH_PRED : it->mode;
+            const uint8_t *mask = it->angle < 0 ? dav1d_ii_masks[bs][li][ii_mode] : dav1d_wedge_masks[bs][li][0][it->angle & 15];
+            int a0 = 0;
+            if (r->hbd) {
+                uint16_t *edge = edge_buf + 128 + 16;
+                const int m = dav1d_prepare_intra_edges_16bpc(it->x4, have_left, it->y4, have_top, w4_end, h4_end, 0, (const uint16_t *)dst, stride,
+                                                              NULL, it->mode, &a0, it->tw4, it->th4, 0, edge, r->bdmax);
+                ((void (*)(void *, ptrdiff_t, const void *, int, int, int, int, int, int))f->dsp->ipred.intra_pred[m])(tmp, bw * 2, edge, bw, bh, 0, 0, 0, r->bdmax);
+            } else {
+                uint8_t *edge = (uint8_t *)edge_buf + 128 + 16;
+                const int m = dav1d_prepare_intra_edges_8bpc(it->x4, have_left, it->y4, have_top, w4_end, h4_end, 0, dst, stride, NULL, it->mode,
+                                                             &a0, it->tw4, it->th4, 0, edge);
+                ((void (*)(void *, ptrdiff_t, const void *, int, int, int, int, int))f->dsp->ipred.intra_pred[m])(tmp, bw, edge, bw, bh, 0, 0, 0);
+            }
+            ((void (*)(void *, ptrdiff_t, const void *, int, int, const uint8_t *))f->dsp->mc.blend)(dst, stride, tmp, bw, bh, mask);
         } else if (r->hbd) {
             uint16_t *edge = edge_buf + 128 + 16;
             const int m = dav1d_prepare_intra_edges_16bpc(it->x4, have_left, it->y4, have_top, w4_end, h4_end, ef, (const uint16_t *)dst,

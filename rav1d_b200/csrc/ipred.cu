@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "tables.cuh"
 #include "itx_block.cuh"
+#include "wedge.cuh"
 
 namespace rb200 {
 
@@ -329,10 +330,11 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
     const int is_sm = (it.flags >> 4) & 1, eief = (it.flags >> 5) & 1;
     const int tw = it.tw4, th = it.th4, x = it.x4, y = it.y4, w = it.w4_end & 0x1fff, h = it.h4_end & 0x1fff;
     const bool cfl = it.plane && it.mode == 13;     // UV_CFL_PRED shares the number of luma's FILTER_PRED
+    const bool inter_intra = (it.flags >> 6) & 1;
     const int bitdepth = BD::hbd ? bpc_from_max(bdmax) : 8;
     // ---- coded mode -> implementation mode (src/ipred_prepare_tmpl.c:89-116); coded numbering: DC 0, VERT 1, HOR 2,
     // DIAG_DOWN_LEFT 3, DIAG_DOWN_RIGHT 4, VERT_RIGHT 5, HOR_DOWN 6, HOR_UP 7, VERT_LEFT 8, SMOOTH 9 .. PAETH 12, FILTER 13
-    int mode = cfl ? IP_DC : it.mode, angle = cfl ? 0 : it.angle;
+    int mode = cfl ? IP_DC : it.mode, angle = (cfl || inter_intra) ? 0 : it.angle;
     if (mode >= 1 && mode <= 8) {
         const int map[8] = { 90, 180, 45, 135, 113, 157, 203, 67 };
         angle = map[mode - 1] + 3 * angle;
@@ -435,6 +437,32 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
         for (int i = tid; i < cw * ch; i += blockDim.x) ac_s[i] = (int16_t)(ac_s[i] - mean);
         __syncthreads();
         ipred_block<BD>(S, mode, dst8, stride, cw, ch, 0, max_w, max_h, bdmax, ac_s, it.angle);
+    } else if (inter_intra) {
+        // inter-intra (src/recon.rs:3475-3550, chroma :3742-3850): the intra prediction of the whole block goes into shared
+        // memory and is blended over the inter prediction already in the picture, with the inter-intra mask of the
+        // mode (it.angle < 0) or a wedge mask (it.angle = wedge index)
+        const int bw = tw * 4, bh = th * 4;
+        ipred_block<BD>(S, mode, (uint8_t *)S.tile, (int64_t)bw * sizeof(pixel), bw, bh, 0, 0, 0, bdmax);
+        __syncthreads();
+        const int ii_mode = it.mode == 9 ? 3 : it.mode;          // SMOOTH_PRED is II_SMOOTH_PRED
+        const int lw = bw << ss_hor, lh = bh << ss_ver;            // the luma block the wedge is defined on
+        for (int i = tid; i < bw * bh; i += blockDim.x) {
+            const int px = i % bw, py = i / bw;
+            int m;
+            if (it.angle < 0) {
+                m = ii_mask_at(bw, bh, ii_mode, px, py);
+            } else {
+                m = wedge_mask_at(lw, lh, it.angle & 15, px << ss_hor, py << ss_ver);
+                if (ss_hor) {
+                    m += wedge_mask_at(lw, lh, it.angle & 15, (px << 1) + 1, py << ss_ver) + 1;
+                    if (ss_ver) m += wedge_mask_at(lw, lh, it.angle & 15, px << 1, (py << 1) + 1) +
+                                     wedge_mask_at(lw, lh, it.angle & 15, (px << 1) + 1, (py << 1) + 1) + 1;
+                    m >>= 1 + ss_ver;
+                }
+            }
+            pixel *d = (pixel *)(dst8 + (int64_t)py * stride) + px;
+            *d = (pixel)(((int)*d * (64 - m) + (int)S.tile[py * bw + px] * m + 32) >> 6);
+        }
     } else {
         ipred_block<BD>(S, mode, dst8, stride, tw * 4, th * 4, mode == IP_FILTER ? (it.angle & 7) : (angle | (is_sm << 9) | (eief << 10)),
                         max_w, max_h, bdmax);

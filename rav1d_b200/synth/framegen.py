@@ -533,7 +533,7 @@ def generate_recon_layout(w, h, bpc, layout, seed=1, comp_frac=0.3, warp_frac=0.
     return s
 
 
-def generate_intra(w, h, bpc, seed=1, inter_frac=0.0, layout=None, cfl_frac=0.25):
+def generate_intra(w, h, bpc, seed=1, inter_frac=0.0, layout=None, cfl_frac=0.25, ii_frac=0.3):
     """A frame (4:2:0 unless `layout` says otherwise) whose 16x16 blocks are intra predicted (a fraction `inter_frac` of them translational inter blocks):
     per transform block a coded mode, angle delta, edge-availability flags consistent with the decode order (raster over
     blocks; inside a block luma transform blocks in raster order, then U, then V), the wavefront level the batch
@@ -569,7 +569,8 @@ def generate_intra(w, h, bpc, seed=1, inter_frac=0.0, layout=None, cfl_frac=0.25
     dec = [np.full((ph4[p], pw4[p]), BIG, np.int64) for p in range(n_planes)]
     lvl = [np.full((ph4[p], pw4[p]), -1, np.int64) for p in range(n_planes)]
     is_inter = rng.random((nby, nbx)) < inter_frac
-    for byi, bxi in zip(*np.nonzero(is_inter)):                           # inter blocks are reconstructed before any intra block
+    is_ii = is_inter & (rng.random((nby, nbx)) < ii_frac)                 # inter-intra: inter prediction blended with an intra one
+    for byi, bxi in zip(*np.nonzero(is_inter & ~is_ii)):                  # plain inter blocks are reconstructed before any intra block
         for p in range(n_planes):
             cx, cy = BLK // 4 >> psx[p], BLK // 4 >> psy[p]
             dec[p][byi * cy:(byi + 1) * cy, bxi * cx:(bxi + 1) * cx] = -1
@@ -584,8 +585,24 @@ def generate_intra(w, h, bpc, seed=1, inter_frac=0.0, layout=None, cfl_frac=0.25
                     x0, y0 = bxi * BLK >> sx, byi * BLK >> sy
                     mc_rows.append((x0, y0, x0 + (mvx >> (3 + sx)), y0 + (mvy >> (3 + sy)), BLK >> sx, BLK >> sy, p, 0,
                                     (mvx & (15 >> (1 - sx))) << (1 - sx), (mvy & (15 >> (1 - sy))) << (1 - sy), f2d, 0))
-                    if rng.random() < 0.7:
-                        rect = {(0, 0): 2, (1, 1): 1, (1, 0): next(t for t in range(19) if TX_DIMS[t] == (8, 16))}[(sx, sy)]
+                    rect = {(0, 0): 2, (1, 1): 1, (1, 0): next(t for t in range(19) if TX_DIMS[t] == (8, 16))}[(sx, sy)]
+                    if is_ii[byi, bxi]:
+                        # the intra half: one item per plane over the whole block (src/recon.rs:3475-3550); its residual hangs on it
+                        x4, y4, tw4, th4 = x0 // 4, y0 // 4, (BLK >> sx) // 4, (BLK >> sy) // 4
+                        idx = len(items)
+                        if p == 0:
+                            ii_mode = int(rng.choice([0, 1, 2, 9])); ii_wedge = int(rng.integers(0, 16)) if rng.random() < 0.5 else -1
+                        have_left, have_top = int(x4 > 0), int(y4 > 0)
+                        W4, H4 = pw4[p], ph4[p]
+                        level = 0
+                        for (xa, xb, ya, yb) in ((x4 - 1, x4, y4 - 1, y4 + th4), (x4, x4 + tw4, y4 - 1, y4)):
+                            lv = lvl[p][max(ya, 0):min(yb, H4), max(xa, 0):min(xb, W4)]
+                            if lv.size: level = max(level, int(lv.max()) + 1)
+                        dec[p][y4:y4 + th4, x4:x4 + tw4] = idx
+                        lvl[p][y4:y4 + th4, x4:x4 + tw4] = level
+                        items.append((x4, y4, W4, H4, p, tw4, th4, ii_mode, ii_wedge, have_left | have_top << 1 | 64, level))
+                        itx_rows.append((p, x0, y0, rect) if rng.random() < 0.7 else None)
+                    elif rng.random() < 0.7:
                         inter_itx.append((p, x0, y0, rect))
                 continue
             uv_cfl = rng.random() < cfl_frac                       # chroma from luma for this block (needs its luma first)
