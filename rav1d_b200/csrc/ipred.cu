@@ -318,6 +318,9 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
     __shared__ int itile[65 * 32];          // the residual's transform tile (largest: 64 x 32 + padding)
     __shared__ int16_t ac_s[32 * 32];       // chroma-from-luma: the sub-sampled, zero-mean luma of the block
     __shared__ int red_s[4];
+    // Programmatic dependent launch: let the next level's grid be scheduled now; it (like this one) does its
+    // picture-independent set-up and then waits below for the previous level to have completed.
+    asm volatile("griddepcontrol.launch_dependents;");
     const Rb200IntraItem it = items[blockIdx.x];
     const int tid = threadIdx.x;
     const int ss_hor = it.plane ? ss_hor_c : 0, ss_ver = it.plane ? ss_ver_c : 0;
@@ -353,6 +356,8 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
     const bool n_tr = mode == IP_Z1, n_bl = mode == IP_Z3;
     const pixel *dst_top = dst - ps;      // only dereferenced when have_top
     pixel *tl = S.e + IP_EC;
+    const int ti = itx_of ? itx_of[blockIdx.x] : -1;
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // everything before this level is in the picture now
     // ---- left column and top row
     if (n_left) {
         const int sz = th << 2;
@@ -468,7 +473,6 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
                         max_w, max_h, bdmax);
     }
     // ---- the block's residual on top of its prediction, in the same launch (the prediction is visible to the CTA)
-    const int ti = itx_of ? itx_of[blockIdx.x] : -1;
     if (ti < 0) return;
     __syncthreads();
     const Rb200ItxItem t = itx[ti];
@@ -484,8 +488,15 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
 int intra_items_launch(const Rb200Planes &cur, const Rb200IntraItem *d_items, const int32_t *d_itx_of, const Rb200ItxItem *d_itx,
                        const void *cf, int n, int frame_w4, int frame_h4, int ss_hor, int ss_ver, int bdmax, cudaStream_t st) {
     if (n <= 0) return 0;
-    if (bdmax > 255) intra_items_kernel<BD16><<<n, 128, 0, st>>>(cur, d_items, d_itx_of, d_itx, (const int32_t *)cf, frame_w4, frame_h4, ss_hor, ss_ver, bdmax);
-    else intra_items_kernel<BD8><<<n, 128, 0, st>>>(cur, d_items, d_itx_of, d_itx, (const int16_t *)cf, frame_w4, frame_h4, ss_hor, ss_ver, bdmax);
+    // launched with programmatic stream serialization: consecutive levels overlap their launch latency and set-up
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n); cfg.blockDim = dim3(128); cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (bdmax > 255) RB_CUDA(cudaLaunchKernelEx(&cfg, intra_items_kernel<BD16>, cur, d_items, d_itx_of, d_itx, (const int32_t *)cf, frame_w4, frame_h4, ss_hor, ss_ver, bdmax));
+    else RB_CUDA(cudaLaunchKernelEx(&cfg, intra_items_kernel<BD8>, cur, d_items, d_itx_of, d_itx, (const int16_t *)cf, frame_w4, frame_h4, ss_hor, ss_ver, bdmax));
     RB_LAUNCH_CHECK();
     return 0;
 }
