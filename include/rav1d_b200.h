@@ -531,7 +531,9 @@ int rb200_frame_set_scaled_count(Rb200Frame *f, int n);
  * Inter-intra (src/recon.rs:3475-3550,3742-3850): flags bit 6; one item per plane over the whole block with mode DC / VERT /
  * HOR / SMOOTH, angle = -1 for the inter-intra mask of that mode (dav1d_ii_masks) or the wedge index 0 .. 15; the block's
  * inter prediction comes from the ordinary Rb200McItem lists, its residual must be attached to the intra item.
- * Not covered yet: palette blocks. */
+ * Palette blocks (pal_pred): mode 14, tw4 x th4 = the whole block, w4_end | h4_end << 16 = offset in 16-byte units of the
+ * block's record { 8 palette entries padded to 16 bytes, w * h index bytes } in rb200_frame_palette_buffer(); the further
+ * transform blocks of such a block are items of mode 15 (no prediction, only the residual). */
 typedef struct Rb200IntraItem {
     uint16_t x4, y4;          /* block position in `plane`, 4-pixel units (t.bx, t.by; >> ss for chroma) */
     uint16_t w4_end, h4_end;  /* tile end in the same units: the `w`, `h` arguments of rav1d_prepare_intra_edges (bits 0-12) */
@@ -552,6 +554,9 @@ int32_t *rb200_frame_intra_itx_index(Rb200Frame *f);      /* per intra item: ind
  * frame's Rb200ItxItem list right after the inter ones (i.e. from index sum(itx_counts of rb200_frame_submit)),
  * level by level and bucketed by size within a level. */
 int rb200_frame_set_intra_levels(Rb200Frame *f, int n_levels, const int32_t *item_counts, const int32_t *itx_counts);
+int rb200_frame_reserve_palette(Rb200Frame *f, size_t bytes);
+uint8_t *rb200_frame_palette_buffer(Rb200Frame *f);
+int rb200_frame_set_palette_bytes(Rb200Frame *f, size_t bytes);
 
 int rb200_frame_reserve_warp_items(Rb200Frame *f, int max_warp_items);
 Rb200WarpItem *rb200_frame_warp_items(Rb200Frame *f);

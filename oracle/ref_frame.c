@@ -611,7 +611,7 @@ enum IntraPredMode dav1d_prepare_intra_edges_16bpc(int x, int have_left, int y, 
                                                    enum IntraPredMode mode, int *angle, int tw, int th, int filter_edge,
                                                    uint16_t *topleft_out, int bitdepth_max);
 void ref_frame_recon_intra(RefFrame *r, const Rb200IntraItem *items, int n, const int32_t *itx_of, const Rb200ItxItem *itx,
-                           void *coef_work) {
+                           void *coef_work, const uint8_t *pal_buf) {
     Dav1dFrameContext *f = r->f;
     const int px = r->hbd ? 2 : 1, cs = r->hbd ? 4 : 2;
     const int ss_ver_l = f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420, ss_hor_l = f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444;
@@ -628,7 +628,13 @@ void ref_frame_recon_intra(RefFrame *r, const Rb200IntraItem *items, int n, cons
         const int max_w = ((4 * f->bw) >> ss_hor) - 4 * it->x4, max_h = ((4 * f->bh) >> ss_ver) - 4 * it->y4;
         const int intra_flags = (is_sm << 9) | (eief << 10);
         const int w4_end = it->w4_end & 0x1fff, h4_end = it->h4_end & 0x1fff;
-        if (pl && it->mode == 13) {   /* chroma from luma, src/recon_tmpl.c:1376-1422 */
+        if (it->mode >= 14) {        /* palette block (src/recon_tmpl.c:1231-1252,1429-1462) / residual-only transform block */
+            if (it->mode == 14) {
+                const uint8_t *rec = pal_buf + ((size_t)it->w4_end | (size_t)it->h4_end << 16) * 16;
+                ((void (*)(void *, ptrdiff_t, const void *, const uint8_t *, int, int))f->dsp->ipred.pal_pred)(dst, stride, rec, rec + 16,
+                                                                                                         it->tw4 * 4, it->th4 * 4);
+            }
+        } else if (pl && it->mode == 13) {   /* chroma from luma, src/recon_tmpl.c:1376-1422 */
             int16_t ac[32 * 32];
             const uint8_t *ysrc = (const uint8_t *)f->cur.data[0] + f->cur.stride[0] * ((it->y4 << ss_ver) * 4) +
                                   (ptrdiff_t)((it->x4 << ss_hor) * 4) * px;

@@ -92,7 +92,8 @@ struct McRefDims { int w[8], h[8]; };   // luma size of each reference slot
 int mc_scaled_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, const McRefDims &dims, int ss_hor,
                            int ss_ver, const Rb200McScaledItem *d_items, int n, int bdmax, cudaStream_t st);
 int intra_items_launch(const Rb200Planes &cur, const Rb200IntraItem *d_items, const int32_t *d_itx_of, const Rb200ItxItem *d_itx,
-                       const void *cf, int n, int frame_w4, int frame_h4, int ss_hor, int ss_ver, int bdmax, cudaStream_t st);
+                       const void *cf, const uint8_t *d_pal, int n, int frame_w4, int frame_h4, int ss_hor, int ss_ver, int bdmax,
+                       cudaStream_t st);
 // super-resolution: one plane, all rows (src/mc.rs:1114-1172 resize)
 int resize_plane_launch(void *dst, int64_t dstride, const void *src, int64_t sstride, int dst_w, int h, int src_w, int dx,
                         int mx0, int bdmax, cudaStream_t st);

@@ -47,6 +47,7 @@ struct Rb200Frame {
     // intra blocks, level by level (RB200_STAGE_INTRA)
     Rb200IntraItem *h_intra, *d_intra; int max_intra, max_levels, n_levels;
     int32_t *h_intra_itx, *d_intra_itx;           // per intra item: index of its residual in the itx list, -1 = none
+    uint8_t *h_pal, *d_pal; size_t max_pal, n_pal; // palette records of the palette blocks
     int32_t *intra_counts, *intra_itx_counts;     // [max_levels], [max_levels][RB200_N_RECT_TX_SIZES]
     // super-resolution (hdr.upscaled_width > hdr.width): plane sets at the upscaled width --
     // 0 = upscaled CDEF output, 1 = upscaled deblocked picture (what lr_line_buf holds on the CPU), 2 = LR output
@@ -234,6 +235,8 @@ extern "C" int rb200_frame_destroy(Rb200Frame *f) {
     if (f->d_intra) cudaFree(f->d_intra);
     if (f->h_intra_itx) cudaFreeHost(f->h_intra_itx);
     if (f->d_intra_itx) cudaFree(f->d_intra_itx);
+    if (f->h_pal) cudaFreeHost(f->h_pal);
+    if (f->d_pal) cudaFree(f->d_pal);
     free(f->intra_counts); free(f->intra_itx_counts);
     if (f->h_warp) cudaFreeHost(f->h_warp);
     if (f->d_warp) cudaFree(f->d_warp);
@@ -608,6 +611,24 @@ extern "C" int rb200_frame_reserve_intra_items(Rb200Frame *f, int max_items, int
 }
 extern "C" Rb200IntraItem *rb200_frame_intra_items(Rb200Frame *f) { return f ? f->h_intra : nullptr; }
 extern "C" int32_t *rb200_frame_intra_itx_index(Rb200Frame *f) { return f ? f->h_intra_itx : nullptr; }
+extern "C" int rb200_frame_reserve_palette(Rb200Frame *f, size_t bytes) {
+    if (!f) return set_error(-22, "frame_reserve_palette: null frame");
+    if (bytes <= f->max_pal) return 0;
+    RB_CUDA(cudaStreamSynchronize(f->stream));
+    if (f->h_pal) cudaFreeHost(f->h_pal);
+    if (f->d_pal) cudaFree(f->d_pal);
+    f->h_pal = nullptr; f->d_pal = nullptr; f->max_pal = 0; f->n_pal = 0;
+    const int r = alloc_pair(&f->h_pal, &f->d_pal, bytes);
+    if (r) return r;
+    f->max_pal = bytes;
+    return 0;
+}
+extern "C" uint8_t *rb200_frame_palette_buffer(Rb200Frame *f) { return f ? f->h_pal : nullptr; }
+extern "C" int rb200_frame_set_palette_bytes(Rb200Frame *f, size_t bytes) {
+    if (!f || bytes > f->max_pal) return set_error(-22, "frame_set_palette_bytes: more than reserved");
+    f->n_pal = bytes;
+    return 0;
+}
 extern "C" int rb200_frame_set_intra_levels(Rb200Frame *f, int n_levels, const int32_t *item_counts, const int32_t *itx_counts) {
     if (!f || n_levels < 0 || n_levels > f->max_levels || (n_levels && (!item_counts || !itx_counts)))
         return set_error(-22, "frame_set_intra_levels: more levels than reserved");
@@ -801,6 +822,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
                 if (n_in) {
                     RB_CUDA(cudaMemcpyAsync(f->d_intra, f->h_intra, (size_t)n_in * sizeof(Rb200IntraItem), cudaMemcpyHostToDevice, st));
                     RB_CUDA(cudaMemcpyAsync(f->d_intra_itx, f->h_intra_itx, (size_t)n_in * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+                    if (f->n_pal) RB_CUDA(cudaMemcpyAsync(f->d_pal, f->h_pal, f->n_pal, cudaMemcpyHostToDevice, st));
                 }
             }
             if (f->n_scaled) RB_CUDA(cudaMemcpyAsync(f->d_scaled, f->h_scaled, (size_t)f->n_scaled * sizeof(Rb200McScaledItem), cudaMemcpyHostToDevice, st));
@@ -872,8 +894,8 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
             int ioff = 0;
             for (int l = 0; l < f->n_levels; l++) {
                 if (!f->intra_counts[l]) continue;
-                if ((r = intra_items_launch(f->planes[0], f->d_intra + ioff, f->d_intra_itx + ioff, f->d_itx, cf, f->intra_counts[l], g.bw,
-                                            g.bh, g.ss_hor, g.ss_ver, f->bdmax, st))) return r;
+                if ((r = intra_items_launch(f->planes[0], f->d_intra + ioff, f->d_intra_itx + ioff, f->d_itx, cf, f->d_pal, f->intra_counts[l],
+                                            g.bw, g.bh, g.ss_hor, g.ss_ver, f->bdmax, st))) return r;
                 f->launches++;
                 ioff += f->intra_counts[l];
             }

@@ -311,8 +311,8 @@ ipred_kernel(int mode, uint8_t *dst8, int64_t stride, const typename BD::pixel *
 template <typename BD>
 __global__ void __launch_bounds__(128)
 intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, const int32_t *__restrict__ itx_of,
-                   const Rb200ItxItem *__restrict__ itx, const typename BD::coef *__restrict__ cf, int frame_w4, int frame_h4,
-                   int ss_hor_c, int ss_ver_c, int bdmax) {
+                   const Rb200ItxItem *__restrict__ itx, const typename BD::coef *__restrict__ cf, const uint8_t *__restrict__ pal_buf,
+                   int frame_w4, int frame_h4, int ss_hor_c, int ss_ver_c, int bdmax) {
     using pixel = typename BD::pixel;
     __shared__ IpScratch<pixel> S;
     __shared__ int itile[65 * 32];          // the residual's transform tile (largest: 64 x 32 + padding)
@@ -358,6 +358,29 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
     pixel *tl = S.e + IP_EC;
     const int ti = itx_of ? itx_of[blockIdx.x] : -1;
     asm volatile("griddepcontrol.wait;" ::: "memory");      // everything before this level is in the picture now
+    if (it.mode >= 14) {
+        // 14: palette block (pal_pred, src/ipred_tmpl.c:717-729): w4_end | h4_end << 16 is the offset, in 16-byte units, of
+        // { 8 palette entries (16 bytes), w * h index bytes } in the frame's palette buffer.  15: no prediction, only the
+        // residual (the further transform blocks of a palette block).
+        if (it.mode == 14) {
+            const uint8_t *rec = pal_buf + ((size_t)it.w4_end | (size_t)it.h4_end << 16) * 16;
+            const pixel *pal = (const pixel *)rec;
+            const uint8_t *idx = rec + 16;
+            for (int i = tid; i < tw * th * 16; i += blockDim.x)
+                ((pixel *)(dst8 + (int64_t)(i / (tw * 4)) * stride))[i % (tw * 4)] = pal[idx[i] & 7];
+        }
+        if (ti < 0) return;
+        __syncthreads();
+        const Rb200ItxItem t = itx[ti];
+        switch (t.tx) {
+#define CASE(TX) case TX: itx_add_block<BD, TX>(itile, tid, tid < ItxGeom<TX>::T, t, cur, cf, bdmax); break;
+            CASE(0) CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9)
+            CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16) CASE(17) CASE(18)
+#undef CASE
+        default: break;
+        }
+        return;
+    }
     // ---- left column and top row
     if (n_left) {
         const int sz = th << 2;
@@ -486,7 +509,8 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
 }
 
 int intra_items_launch(const Rb200Planes &cur, const Rb200IntraItem *d_items, const int32_t *d_itx_of, const Rb200ItxItem *d_itx,
-                       const void *cf, int n, int frame_w4, int frame_h4, int ss_hor, int ss_ver, int bdmax, cudaStream_t st) {
+                       const void *cf, const uint8_t *d_pal, int n, int frame_w4, int frame_h4, int ss_hor, int ss_ver, int bdmax,
+                       cudaStream_t st) {
     if (n <= 0) return 0;
     // launched with programmatic stream serialization: consecutive levels overlap their launch latency and set-up
     cudaLaunchConfig_t cfg = {};
@@ -495,8 +519,8 @@ int intra_items_launch(const Rb200Planes &cur, const Rb200IntraItem *d_items, co
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (bdmax > 255) RB_CUDA(cudaLaunchKernelEx(&cfg, intra_items_kernel<BD16>, cur, d_items, d_itx_of, d_itx, (const int32_t *)cf, frame_w4, frame_h4, ss_hor, ss_ver, bdmax));
-    else RB_CUDA(cudaLaunchKernelEx(&cfg, intra_items_kernel<BD8>, cur, d_items, d_itx_of, d_itx, (const int16_t *)cf, frame_w4, frame_h4, ss_hor, ss_ver, bdmax));
+    if (bdmax > 255) RB_CUDA(cudaLaunchKernelEx(&cfg, intra_items_kernel<BD16>, cur, d_items, d_itx_of, d_itx, (const int32_t *)cf, d_pal, frame_w4, frame_h4, ss_hor, ss_ver, bdmax));
+    else RB_CUDA(cudaLaunchKernelEx(&cfg, intra_items_kernel<BD8>, cur, d_items, d_itx_of, d_itx, (const int16_t *)cf, d_pal, frame_w4, frame_h4, ss_hor, ss_ver, bdmax));
     RB_LAUNCH_CHECK();
     return 0;
 }

@@ -226,6 +226,9 @@ wedge_mask = _sig("rb200_wedge_mask", _i, _i, _i, _i, _i, _i, _vp)
 frame_reserve_intra_items = _sig("rb200_frame_reserve_intra_items", _i, _vp, _i, _i)
 frame_intra_items = _sig("rb200_frame_intra_items", _vp, _vp)
 frame_intra_itx_index = _sig("rb200_frame_intra_itx_index", _vp, _vp)
+frame_reserve_palette = _sig("rb200_frame_reserve_palette", _i, _vp, _sz)
+frame_palette_buffer = _sig("rb200_frame_palette_buffer", _vp, _vp)
+frame_set_palette_bytes = _sig("rb200_frame_set_palette_bytes", _i, _vp, _sz)
 frame_set_intra_levels = _sig("rb200_frame_set_intra_levels", _i, _vp, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32))
 frame_reserve_scaled_items = _sig("rb200_frame_reserve_scaled_items", _i, _vp, _i)
 frame_scaled_items = _sig("rb200_frame_scaled_items", _vp, _vp)

@@ -533,7 +533,7 @@ def generate_recon_layout(w, h, bpc, layout, seed=1, comp_frac=0.3, warp_frac=0.
     return s
 
 
-def generate_intra(w, h, bpc, seed=1, inter_frac=0.0, layout=None, cfl_frac=0.25, ii_frac=0.3):
+def generate_intra(w, h, bpc, seed=1, inter_frac=0.0, layout=None, cfl_frac=0.25, ii_frac=0.3, pal_frac=0.1):
     """A frame (4:2:0 unless `layout` says otherwise) whose 16x16 blocks are intra predicted (a fraction `inter_frac` of them translational inter blocks):
     per transform block a coded mode, angle delta, edge-availability flags consistent with the decode order (raster over
     blocks; inside a block luma transform blocks in raster order, then U, then V), the wavefront level the batch
@@ -575,6 +575,7 @@ def generate_intra(w, h, bpc, seed=1, inter_frac=0.0, layout=None, cfl_frac=0.25
             cx, cy = BLK // 4 >> psx[p], BLK // 4 >> psy[p]
             dec[p][byi * cy:(byi + 1) * cy, bxi * cx:(bxi + 1) * cx] = -1
     items, itx_rows, mc_rows = [], [], []      # decode order
+    pal_records, pal_bytes = [], 0             # palette blocks: { 8 entries padded to 16 bytes, w * h indices }
     inter_itx = []
     for byi in range(nby):
         for bxi in range(nbx):
@@ -606,8 +607,31 @@ def generate_intra(w, h, bpc, seed=1, inter_frac=0.0, layout=None, cfl_frac=0.25
                         inter_itx.append((p, x0, y0, rect))
                 continue
             uv_cfl = rng.random() < cfl_frac                       # chroma from luma for this block (needs its luma first)
+            pal_y, pal_uv = rng.random() < pal_frac, rng.random() < pal_frac
             for p in range(n_planes):
                 bwp, bhp = BLK >> psx[p], BLK >> psy[p]            # block size in this plane, pixels
+                if (pal_y and p == 0) or (pal_uv and p > 0):
+                    # palette prediction of the whole block (no neighbours needed), then its residual transform blocks
+                    x4, y4, tw4, th4 = bxi * bwp // 4, byi * bhp // 4, bwp // 4, bhp // 4
+                    rec = np.zeros(16 + ((bwp * bhp + 15) & ~15), np.uint8)
+                    rec[:8 * np.dtype(pdt).itemsize] = rng.integers(0, bdmax + 1, size=8).astype(pdt).view(np.uint8)
+                    rec[16:16 + bwp * bhp] = rng.integers(0, 8, size=bwp * bhp)
+                    off16 = pal_bytes // 16
+                    pal_records.append(rec); pal_bytes += rec.size
+                    tsz = int(rng.choice([t for t in (4, 8, 16) if t <= min(bwp, bhp)]))
+                    whole = tsz == bwp == bhp
+                    dec[p][y4:y4 + th4, x4:x4 + tw4] = len(items)
+                    lvl[p][y4:y4 + th4, x4:x4 + tw4] = 0
+                    items.append((x4, y4, off16 & 0xffff, off16 >> 16, p, tw4, th4, 14, 0, 0, 0))
+                    itx_rows.append((p, x4 * 4, y4 * 4, TXS[tsz]) if whole and rng.random() < 0.8 else None)
+                    if not whole:
+                        for ty in range(0, th4, tsz // 4):
+                            for tx_ in range(0, tw4, tsz // 4):
+                                if rng.random() < 0.8:
+                                    items.append((x4 + tx_, y4 + ty, 0, 0, p, tsz // 4, tsz // 4, 15, 0, 0, 1))
+                                    itx_rows.append((p, (x4 + tx_) * 4, (y4 + ty) * 4, TXS[tsz]))
+                                    lvl[p][y4 + ty:y4 + ty + tsz // 4, x4 + tx_:x4 + tx_ + tsz // 4] = 1
+                    continue
                 if p and uv_cfl:
                     # one item per plane over the whole chroma block; alpha 0 = plain DC prediction (src/recon.rs, CFL branch)
                     alpha = int(rng.integers(-16, 17))
@@ -664,6 +688,7 @@ def generate_intra(w, h, bpc, seed=1, inter_frac=0.0, layout=None, cfl_frac=0.25
     for i, it in enumerate(items):
         out_items[i] = it[:10] + (it[10],)
     s.intra_items_decode = out_items
+    s.palette = np.concatenate(pal_records) if pal_records else np.zeros(16, np.uint8)
     # ---- residuals: inter ones first (bucketed by size / type), then the intra ones level by level
     def make_itx(rows):
         plane = np.array([r[0] for r in rows], np.int64); xs = np.array([r[1] for r in rows], np.int64)
@@ -829,6 +854,11 @@ class DeviceFrame:
             lib.check(lib.frame_reserve_intra_items(self.h, len(intra), len(s.intra_counts)), "reserve_intra_items")
             lib.np_view(lib.frame_intra_items(self.h), lib.INTRA_ITEM_DT, len(intra))[:] = intra
             lib.np_view(lib.frame_intra_itx_index(self.h), np.int32, len(intra))[:] = s.intra_itx_of_sorted
+            pal = getattr(s, "palette", None)
+            if pal is not None and len(pal):
+                lib.check(lib.frame_reserve_palette(self.h, len(pal)), "reserve_palette")
+                lib.np_view(lib.frame_palette_buffer(self.h), np.uint8, len(pal))[:] = pal
+                lib.check(lib.frame_set_palette_bytes(self.h, len(pal)))
             lib.check(lib.frame_set_intra_levels(self.h, len(s.intra_counts), s.intra_counts.ctypes.data_as(C.POINTER(C.c_int32)),
                                                  np.ascontiguousarray(s.intra_itx_counts).ctypes.data_as(C.POINTER(C.c_int32))))
         scaled = getattr(s, "scaled_items", None)

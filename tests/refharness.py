@@ -70,7 +70,7 @@ def load():
         sig("ref_frame_recon_obmc", None, vp, vp, i, vp, i)
         sig("ref_wedge_mask", vp, i, i, i, i, i)
         sig("ref_frame_recon_scaled", None, vp, vp, i, vp, i)
-        sig("ref_frame_recon_intra", None, vp, vp, i, vp, vp, vp)
+        sig("ref_frame_recon_intra", None, vp, vp, i, vp, vp, vp, vp)
         sig("ref_frame_apply_grain", None, vp, vp, i)
         sig("ref_frame_grain_plane", vp, vp, i)
         sig("ref_fg_gen_y", None, vp, vp, i)
@@ -161,7 +161,8 @@ class RefFrame:
         intra = getattr(s, "intra_items_decode", None)
         if intra is not None and len(intra):
             intra = np.ascontiguousarray(intra); of = np.ascontiguousarray(s.intra_itx_of)
-            self.ref.ref_frame_recon_intra(self.h, ptr(intra), len(intra), ptr(of), ptr(itx), ptr(cw))
+            pal = np.ascontiguousarray(getattr(s, "palette", np.zeros(16, np.uint8)))
+            self.ref.ref_frame_recon_intra(self.h, ptr(intra), len(intra), ptr(of), ptr(itx), ptr(cw), ptr(pal))
         return cw
 
     def apply_grain(self, fg, is_id=0):

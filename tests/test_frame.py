@@ -170,6 +170,7 @@ def test_intra_blocks_wavefront(rb, ref, w, h, bpc, inter_frac):
     s = framegen.generate_intra(w, h, bpc, seed=w + bpc, inter_frac=inter_frac)
     assert len(s.intra_counts) > 10 and len(set(s.intra_items["mode"])) >= 12      # (every mode: see test_intra_modes_all_present)
     assert ((s.intra_items["plane"] > 0) & (s.intra_items["mode"] == 13)).sum() > 3          # chroma-from-luma blocks
+    assert (s.intra_items["mode"] == 14).sum() >= 2 and (s.intra_items["mode"] == 15).sum() >= 1   # palette blocks
     if inter_frac >= 0.3:                                                                      # inter-intra: mask and wedge kinds
         ii = s.intra_items[(s.intra_items["flags"] & 64) != 0]
         assert (ii["angle"] < 0).any() and (ii["angle"] >= 0).any()
@@ -184,7 +185,7 @@ def test_intra_modes_all_present():
     modes = set()
     for w, h, bpc, fr in [(96, 64, 8, 0.0), (160, 128, 10, 0.0), (192, 128, 12, 0.3)]:
         modes |= set(int(m) for m in framegen.generate_intra(w, h, bpc, seed=w + bpc, inter_frac=fr).intra_items["mode"])
-    assert modes == set(range(14))
+    assert modes == set(range(16))
 
 
 @pytest.mark.gpu
