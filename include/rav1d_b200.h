@@ -554,6 +554,11 @@ int32_t *rb200_frame_intra_itx_index(Rb200Frame *f);      /* per intra item: ind
  * frame's Rb200ItxItem list right after the inter ones (i.e. from index sum(itx_counts of rb200_frame_submit)),
  * level by level and bucketed by size within a level. */
 int rb200_frame_set_intra_levels(Rb200Frame *f, int n_levels, const int32_t *item_counts, const int32_t *itx_counts);
+/* Host helper (no GPU work): fills Rb200IntraItem.level of `items`, given in DECODE order, from their positions, sizes and
+ * availability flags (see above), and returns the level-sorted order (order[k] = index of the k-th item to append) and the
+ * number of items per level.  frame_w4 / frame_h4: luma picture size in 4-pixel units (f.bw, f.bh). */
+int rb200_intra_assign_levels(Rb200IntraItem *items, int n, int frame_w4, int frame_h4, int ss_hor, int ss_ver,
+                              int32_t *order, int32_t *level_counts, int max_levels, int *n_levels);
 int rb200_frame_reserve_palette(Rb200Frame *f, size_t bytes);
 uint8_t *rb200_frame_palette_buffer(Rb200Frame *f);
 int rb200_frame_set_palette_bytes(Rb200Frame *f, size_t bytes);

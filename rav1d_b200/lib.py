@@ -226,6 +226,7 @@ wedge_mask = _sig("rb200_wedge_mask", _i, _i, _i, _i, _i, _i, _vp)
 frame_reserve_intra_items = _sig("rb200_frame_reserve_intra_items", _i, _vp, _i, _i)
 frame_intra_items = _sig("rb200_frame_intra_items", _vp, _vp)
 frame_intra_itx_index = _sig("rb200_frame_intra_itx_index", _vp, _vp)
+intra_assign_levels = _sig("rb200_intra_assign_levels", _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, C.POINTER(_i))
 frame_reserve_palette = _sig("rb200_frame_reserve_palette", _i, _vp, _sz)
 frame_palette_buffer = _sig("rb200_frame_palette_buffer", _vp, _vp)
 frame_set_palette_bytes = _sig("rb200_frame_set_palette_bytes", _i, _vp, _sz)

@@ -180,6 +180,26 @@ def test_intra_blocks_wavefront(rb, ref, w, h, bpc, inter_frac):
     framecheck.assert_planes_equal(a, b, f"intra {w}x{h}@{bpc}")
 
 
+@pytest.mark.parametrize("layout", [0, 1, 2, 3])
+def test_intra_levels_host_helper(layout):
+    """rb200_intra_assign_levels (host code) reproduces the generator's wavefront levels from the items in decode order,
+    and its level-sorted order is the one the frames are submitted in."""
+    import ctypes as C
+    from rav1d_b200 import lib
+    s = framegen.generate_intra(192, 160, 10, seed=90 + layout, inter_frac=0.3, layout=layout)
+    items = s.intra_items_decode.copy()
+    want = items["level"].copy()
+    items["level"] = 0xffff
+    n = len(items)
+    order = np.zeros(n, np.int32); counts = np.zeros(4096, np.int32); nl = C.c_int()
+    g = s.geom
+    lib.check(lib.intra_assign_levels(items.ctypes.data, n, g.bw, g.bh, g.ss_hor, g.ss_ver, order.ctypes.data, counts.ctypes.data, 4096, C.byref(nl)))
+    assert np.array_equal(items["level"], want)
+    assert nl.value == len(s.intra_counts) and np.array_equal(counts[:nl.value], s.intra_counts)
+    assert np.array_equal(items[order], s.intra_items)
+    assert lib.intra_assign_levels(items.ctypes.data, n, g.bw, g.bh, g.ss_hor, g.ss_ver, order.ctypes.data, counts.ctypes.data, 3, C.byref(nl)) != 0
+
+
 def test_intra_modes_all_present():
     """The frames of test_intra_blocks_wavefront together exercise every coded mode."""
     modes = set()
