@@ -628,6 +628,32 @@ int rb200_frame_set_stream(Rb200Frame *f, void *stream);
 #define RB200_N_FRAME_MARKS 8
 int rb200_frame_enable_timing(Rb200Frame *f, int on);
 int rb200_frame_stage_times(Rb200Frame *f, float ms[RB200_N_FRAME_MARKS - 1]);
+/* ---- loop-filter masks and levels generated on the device ----
+ * rav1d_create_lf_mask_intra / rav1d_create_lf_mask_inter (src/lf_mask.rs:380-606; C: src/lf_mask.c:286-406)
+ * run once per coded block inside decode_b (src/decode.rs; C: src/decode.c:1260-1271,1926-1947) and carry the
+ * above / left transform-size contexts from block to block.  Here the front end appends one 16-byte record per
+ * block -- exactly the arguments of those two calls, plus b->skip for the noskip mask (src/decode.c:1996-2005) --
+ * and the submit builds Av1Filter.filter_y / filter_uv / noskip_mask and lf.level[][4] on the device in two
+ * launches: a scatter of per-4x4 cell facts, then a gather that assembles every mask word without atomics.
+ * The result is the mask set the filters consume, i.e. AFTER the tile-edge fix-ups of
+ * src/lf_apply.rs (C: src/lf_apply_tmpl.c:331-400): a block edge is min(own, neighbour's) transform size whether
+ * or not a tile boundary lies between them.  Records may come in any order.  cdef_idx is still taken from
+ * rb200_frame_lf_masks(); with records set, that array's masks and rb200_frame_lf_levels() are not read. */
+enum { RB200_LFB_INTRA = 1 /* create_lf_mask_intra: ytx = b->tx, no split, inner edges even if skipped */,
+       RB200_LFB_SKIP = 2 /* b->skip */, RB200_LFB_HAS_CHROMA = 4 /* auv / luv passed (has_chroma) */ };
+typedef struct Rb200LfBlock {
+    uint16_t bx, by;        /* t->bx, t->by: block origin in 4-pixel luma units */
+    uint8_t bs;             /* enum BlockSize, src/levels.rs (BS_128x128 = 0 .. BS_4x4 = 21) */
+    uint8_t flags;          /* RB200_LFB_* */
+    uint8_t ytx, uvtx;      /* RB200_TX_* : b->tx (intra) or max_ytx (inter); uvtx */
+    uint16_t tx_split[2];   /* b->tx_split0, b->tx_split1 (inter) */
+    uint8_t lvl[4];         /* filter_level[0..3][0][0]: y column edges, y row edges, u, v */
+} RB200_ALIGN16 Rb200LfBlock;           /* 16 bytes */
+int rb200_frame_reserve_lf_blocks(Rb200Frame *f, int max_blocks);
+Rb200LfBlock *rb200_frame_lf_blocks(Rb200Frame *f);
+int rb200_frame_set_lf_block_count(Rb200Frame *f, int n_blocks);   /* 0 = masks and levels come from the host arrays */
+/* Test / debugging aid: copies the device's mask and level arrays of the last submit back (waits for the stream). */
+int rb200_frame_download_lf(Rb200Frame *f, Rb200Av1Filter *masks, uint8_t (*levels)[4]);
 /* Number of kernels launched by the last submit (bench bookkeeping). */
 int rb200_frame_last_launches(const Rb200Frame *f);
 

@@ -37,6 +37,8 @@
 #include "src/lf_mask.h"
 #include "input/input.h"
 
+#include "../include/rav1d_b200.h"
+
 static FILE *g_out;
 static int g_frames, g_max_frames = 1 << 30, g_sr_seen;
 static int g_sr_mode;   /* 1: dump only super-resolution frames (record "RBSR": 8 more header ints, post = sr_cur) */
@@ -44,6 +46,46 @@ static uint8_t *g_pre[3];
 static size_t g_pre_sz[3];
 
 typedef void (*filter_sbrow_fn)(Dav1dFrameContext *f, int sby);
+
+/* ---- the arguments of every dav1d_create_lf_mask_{intra,inter} call of the frame (src/decode.c:
+ * 1260-1271,1926-1947), interposed like filter_sbrow (the library calls them through its PLT).  With
+ * RB200_DUMP_LFB=<file> each dumped frame also appends "RBLB", frame index, n, n Rb200LfBlock records there. */
+static FILE *g_lfb_out;
+static Rb200LfBlock *g_lfb;
+static int g_n_lfb, g_cap_lfb;
+static void lfb_push(int bx, int by, int bs, int flags, int ytx, int uvtx, const uint16_t *tx_masks,
+                     const uint8_t (*filter_level)[8][2]) {
+    if (g_n_lfb == g_cap_lfb) { g_cap_lfb = g_cap_lfb ? 2 * g_cap_lfb : 4096; g_lfb = realloc(g_lfb, (size_t)g_cap_lfb * sizeof(*g_lfb)); }
+    Rb200LfBlock *b = &g_lfb[g_n_lfb++];
+    b->bx = bx; b->by = by; b->bs = bs; b->flags = flags; b->ytx = ytx; b->uvtx = uvtx;
+    b->tx_split[0] = tx_masks ? tx_masks[0] : 0; b->tx_split[1] = tx_masks ? tx_masks[1] : 0;
+    for (int k = 0; k < 4; k++) b->lvl[k] = filter_level[k][0][0];
+}
+typedef void (*lf_intra_fn)(Av1Filter *, uint8_t (*)[4], ptrdiff_t, const uint8_t (*)[8][2], int, int, int, int,
+                            enum BlockSize, enum RectTxfmSize, enum RectTxfmSize, enum Dav1dPixelLayout, uint8_t *, uint8_t *,
+                            uint8_t *, uint8_t *);
+typedef void (*lf_inter_fn)(Av1Filter *, uint8_t (*)[4], ptrdiff_t, const uint8_t (*)[8][2], int, int, int, int, int,
+                            enum BlockSize, enum RectTxfmSize, const uint16_t *, enum RectTxfmSize, enum Dav1dPixelLayout,
+                            uint8_t *, uint8_t *, uint8_t *, uint8_t *);
+__attribute__((visibility("default"))) void dav1d_create_lf_mask_intra(Av1Filter *lflvl, uint8_t (*level_cache)[4], ptrdiff_t b4_stride,
+        const uint8_t (*filter_level)[8][2], int bx, int by, int iw, int ih, enum BlockSize bs, enum RectTxfmSize ytx,
+        enum RectTxfmSize uvtx, enum Dav1dPixelLayout layout, uint8_t *ay, uint8_t *ly, uint8_t *auv, uint8_t *luv) {
+    static lf_intra_fn real;
+    if (!real) real = (lf_intra_fn)dlsym(RTLD_NEXT, "dav1d_create_lf_mask_intra");
+    if (!real) { fprintf(stderr, "ref_dump: cannot find dav1d_create_lf_mask_intra\n"); exit(2); }
+    real(lflvl, level_cache, b4_stride, filter_level, bx, by, iw, ih, bs, ytx, uvtx, layout, ay, ly, auv, luv);
+    if (g_lfb_out) lfb_push(bx, by, bs, RB200_LFB_INTRA | (auv ? RB200_LFB_HAS_CHROMA : 0), ytx, uvtx, NULL, filter_level);
+}
+__attribute__((visibility("default"))) void dav1d_create_lf_mask_inter(Av1Filter *lflvl, uint8_t (*level_cache)[4], ptrdiff_t b4_stride,
+        const uint8_t (*filter_level)[8][2], int bx, int by, int iw, int ih, int skip, enum BlockSize bs,
+        enum RectTxfmSize max_ytx, const uint16_t *tx_masks, enum RectTxfmSize uvtx, enum Dav1dPixelLayout layout,
+        uint8_t *ay, uint8_t *ly, uint8_t *auv, uint8_t *luv) {
+    static lf_inter_fn real;
+    if (!real) real = (lf_inter_fn)dlsym(RTLD_NEXT, "dav1d_create_lf_mask_inter");
+    if (!real) { fprintf(stderr, "ref_dump: cannot find dav1d_create_lf_mask_inter\n"); exit(2); }
+    real(lflvl, level_cache, b4_stride, filter_level, bx, by, iw, ih, skip, bs, max_ytx, tx_masks, uvtx, layout, ay, ly, auv, luv);
+    if (g_lfb_out) lfb_push(bx, by, bs, (skip ? RB200_LFB_SKIP : 0) | (auv ? RB200_LFB_HAS_CHROMA : 0), max_ytx, uvtx, tx_masks, filter_level);
+}
 
 static void put_i32(int32_t v) { fwrite(&v, 4, 1, g_out); }
 
@@ -74,6 +116,14 @@ static void hook(Dav1dFrameContext *const f, const int sby, const char *const sy
         }
     }
     (*real)(f, sby);
+    if (sby + 1 == f->sbh) {    /* the frame's blocks are complete */
+        if (dump && g_lfb_out) {
+            int32_t hd[3] = { 0x52424c42, g_frames, g_n_lfb };
+            fwrite(hd, 4, 3, g_lfb_out);
+            fwrite(g_lfb, sizeof(*g_lfb), g_n_lfb, g_lfb_out);
+        }
+        g_n_lfb = 0;
+    }
     if (!dump || sby + 1 != f->sbh) return;
 
     /* ---- the frame is complete: header, metadata, pre and post pictures */
@@ -157,6 +207,7 @@ int main(int argc, char **argv) {
     if (argc > 3) g_max_frames = atoi(argv[3]);
     if (argc > 4) g_max_grain = atoi(argv[4]);      /* film-grain records (decoded with apply_grain = 1) */
     if (argc > 5) g_sr_mode = atoi(argv[5]) != 0;   /* 1: super-resolution frames only */
+    if (getenv("RB200_DUMP_LFB")) g_lfb_out = fopen(getenv("RB200_DUMP_LFB"), "wb");
     g_out = fopen(argv[2], "wb");
     if (!g_out) { perror(argv[2]); return 2; }
     DemuxerContext *in;
@@ -193,6 +244,7 @@ int main(int argc, char **argv) {
     input_close(in);
     dav1d_close(&c);
     fclose(g_out);
+    if (g_lfb_out) fclose(g_lfb_out);
     fprintf(stderr, "ref_dump: %d frames, %d film-grain records, %d super-resolution frames seen\n", g_frames, g_grain_frames, g_sr_seen);
     return g_frames + g_grain_frames > 0 ? 0 : 1;
 }

@@ -102,6 +102,10 @@ int mc_obmc_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_
 int deblock_frame_launch(const Rb200Planes &pl, int n_planes, int w4, int h4, int sb128w, int b4_stride, int ss_hor,
                          int ss_ver, bool do_uv, const Rb200Av1Filter *masks, const uint8_t (*lvl)[4],
                          const Rb200Av1FilterLUT *lut, int bdmax, cudaStream_t st, int *launches, int y4b, int y4e);
+// lfmask.cu: Av1Filter masks + lf.level built from per-block records (cells: 2 * 32 sb128w * 32 sb128h bytes of scratch)
+int lf_build_launch(const Rb200LfBlock *d_blocks, int n, int w4, int h4, int sb128w, int sb128h, int b4_stride, int ss_hor,
+                    int ss_ver, int n_planes, uint8_t *cells, const int8_t *cdef_idx, Rb200Av1Filter *masks, uint8_t (*lvl)[4],
+                    cudaStream_t st);
 // blk_scratch: device, 8 bytes per 8x8 luma block ((bw / 2) * (bh / 2) records)
 int cdef_frame_launch(const Rb200Planes &src, const Rb200Planes &dst, const CdefFrameParams &P,
                       const Rb200Av1Filter *masks, void *blk_scratch, int bdmax, cudaStream_t st, int t0, int t1);

@@ -60,6 +60,12 @@ struct Rb200Frame {
     uint8_t (*h_lvl)[4], (*d_lvl)[4];
     Rb200Av1FilterLUT *h_lut, *d_lut;
     Rb200Av1Restoration *h_lr, *d_lr;
+    // loop-filter masks / levels generated on the device from per-block records (lfmask.cu)
+    Rb200LfBlock *h_lfb, *d_lfb; int max_lfb, n_lfb;
+    uint8_t *d_lf_cells;                // per-4x4 cell facts, luma + chroma
+    int8_t *h_cdef_idx, *d_cdef_idx;    // [n_masks][4], the only Av1Filter member still uploaded in that mode
+    cudaStream_t lf_stream;             // records upload + mask build run beside the reconstruction
+    cudaEvent_t lf_fork, lf_join;
     void *d_cdef_blk;   // per-8x8 CDEF decisions (direction, strengths), device only
     int *d_counters;    // work dispensers of the batch kernels (one int each)
     int band_s0, band_s1;   // loop-restoration stripes this context produces (0, 0 = whole picture)
@@ -216,6 +222,9 @@ extern "C" int rb200_frame_destroy(Rb200Frame *f) {
     for (int i = 0; i < 3; i++) if (f->plane_mem[i]) cudaFree(f->plane_mem[i]);
     if (f->fg_mem) cudaFree(f->fg_mem);
     if (f->fg_stream) { cudaStreamSynchronize(f->fg_stream); cudaStreamDestroy(f->fg_stream); }
+    if (f->lf_stream) { cudaStreamSynchronize(f->lf_stream); cudaStreamDestroy(f->lf_stream); }
+    if (f->lf_fork) cudaEventDestroy(f->lf_fork);
+    if (f->lf_join) cudaEventDestroy(f->lf_join);
     if (f->up_stream) { cudaStreamSynchronize(f->up_stream); cudaStreamDestroy(f->up_stream); }
     if (f->up_fork) cudaEventDestroy(f->up_fork);
     if (f->up_join) cudaEventDestroy(f->up_join);
@@ -245,6 +254,11 @@ extern "C" int rb200_frame_destroy(Rb200Frame *f) {
     if (f->h_mc) cudaFreeHost(f->h_mc);
     if (f->d_mc) cudaFree(f->d_mc);
     if (f->d_counters) cudaFree(f->d_counters);
+    if (f->h_lfb) cudaFreeHost(f->h_lfb);
+    if (f->d_lfb) cudaFree(f->d_lfb);
+    if (f->d_lf_cells) cudaFree(f->d_lf_cells);
+    if (f->h_cdef_idx) cudaFreeHost(f->h_cdef_idx);
+    if (f->d_cdef_idx) cudaFree(f->d_cdef_idx);
     if (f->h_masks) cudaFreeHost(f->h_masks);
     if (f->d_masks) cudaFree(f->d_masks);
     if (f->h_lvl) cudaFreeHost(f->h_lvl);
@@ -646,6 +660,39 @@ extern "C" int rb200_frame_set_intra_levels(Rb200Frame *f, int n_levels, const i
     return 0;
 }
 
+extern "C" int rb200_frame_reserve_lf_blocks(Rb200Frame *f, int max_blocks) {
+    if (!f || max_blocks < 0) return set_error(-22, "frame_reserve_lf_blocks: bad argument");
+    if (max_blocks <= f->max_lfb) return 0;
+    RB_CUDA(cudaStreamSynchronize(f->stream));
+    if (f->h_lfb) cudaFreeHost(f->h_lfb);
+    if (f->d_lfb) cudaFree(f->d_lfb);
+    f->h_lfb = nullptr; f->d_lfb = nullptr; f->max_lfb = 0; f->n_lfb = 0;
+    int r = alloc_pair(&f->h_lfb, &f->d_lfb, (size_t)max_blocks);
+    if (!r && !f->d_lf_cells) {
+        RB_CUDA(cudaMalloc((void **)&f->d_lf_cells, (size_t)2 * 32 * f->g.sb128w * 32 * f->g.sb128h));
+        r = alloc_pair(&f->h_cdef_idx, &f->d_cdef_idx, f->n_masks * 4);
+        RB_CUDA(cudaStreamCreateWithFlags(&f->lf_stream, cudaStreamNonBlocking));
+        RB_CUDA(cudaEventCreateWithFlags(&f->lf_fork, cudaEventDisableTiming));
+        RB_CUDA(cudaEventCreateWithFlags(&f->lf_join, cudaEventDisableTiming));
+    }
+    if (r) return r;
+    f->max_lfb = max_blocks;
+    return 0;
+}
+extern "C" Rb200LfBlock *rb200_frame_lf_blocks(Rb200Frame *f) { return f ? f->h_lfb : nullptr; }
+extern "C" int rb200_frame_set_lf_block_count(Rb200Frame *f, int n) {
+    if (!f || n < 0 || n > f->max_lfb) return set_error(-22, "frame_set_lf_block_count: more blocks than reserved");
+    f->n_lfb = n;
+    return 0;
+}
+extern "C" int rb200_frame_download_lf(Rb200Frame *f, Rb200Av1Filter *masks, uint8_t (*levels)[4]) {
+    if (!f) return set_error(-22, "frame_download_lf: null frame");
+    RB_CUDA(cudaStreamSynchronize(f->stream));
+    if (masks) RB_CUDA(cudaMemcpy(masks, f->d_masks, (size_t)f->g.sb128w * f->g.sb128h * sizeof(Rb200Av1Filter), cudaMemcpyDeviceToHost));
+    if (levels) RB_CUDA(cudaMemcpy(levels, f->d_lvl + 32, (f->n_lvl - 32) * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 extern "C" int rb200_frame_reserve_obmc_items(Rb200Frame *f, int max_obmc) {
     if (!f || max_obmc < 0) return set_error(-22, "frame_reserve_obmc_items: bad argument");
     if (max_obmc <= f->max_obmc) return 0;
@@ -786,6 +833,14 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
     if (stages & RB200_STAGE_LR)
         for (int p = 0; p < g.n_planes; p++) if (h.lr_type[p] != RB200_RESTORATION_NONE) restore_planes |= 1 << p;
 
+    // Loop-filter masks / levels from block records (lfmask.cu): nothing in them depends on the picture, so the records'
+    // upload and the two launches run on a side stream beside the reconstruction.  Fork here: the previous frame's
+    // filters (on st) still read the arrays that are rebuilt.
+    const bool build_lf = f->n_lfb && (do_lf || do_cdef);
+    if (build_lf) {
+        RB_CUDA(cudaEventRecord(f->lf_fork, st));
+        RB_CUDA(cudaStreamWaitEvent(f->lf_stream, f->lf_fork, 0));
+    }
     // ---- host -> device: the per-frame batch
     if (upload) {
         if (stages & RB200_STAGE_RECON) {
@@ -829,10 +884,16 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
             if (f->n_obmc_above + f->n_obmc_left)
                 RB_CUDA(cudaMemcpyAsync(f->d_obmc, f->h_obmc, (size_t)(f->n_obmc_above + f->n_obmc_left) * sizeof(Rb200McItem), cudaMemcpyHostToDevice, st));
         }
-        if (do_lf || do_cdef)
+        if (build_lf) {
+            // masks and levels are built on the device from the block records; only cdef_idx travels
+            const size_t n_sb = (size_t)g.sb128w * g.sb128h;
+            for (size_t i = 0; i < n_sb; i++) memcpy(f->h_cdef_idx + 4 * i, f->h_masks[i].cdef_idx, 4);
+            RB_CUDA(cudaMemcpyAsync(f->d_cdef_idx, f->h_cdef_idx, n_sb * 4, cudaMemcpyHostToDevice, f->lf_stream));
+            RB_CUDA(cudaMemcpyAsync(f->d_lfb, f->h_lfb, (size_t)f->n_lfb * sizeof(Rb200LfBlock), cudaMemcpyHostToDevice, f->lf_stream));
+        } else if (do_lf || do_cdef)
             RB_CUDA(cudaMemcpyAsync(f->d_masks, f->h_masks, f->n_masks * sizeof(Rb200Av1Filter), cudaMemcpyHostToDevice, st));
         if (do_lf) {
-            RB_CUDA(cudaMemcpyAsync(f->d_lvl, f->h_lvl, f->n_lvl * 4, cudaMemcpyHostToDevice, st));
+            if (!f->n_lfb) RB_CUDA(cudaMemcpyAsync(f->d_lvl, f->h_lvl, f->n_lvl * 4, cudaMemcpyHostToDevice, st));
             RB_CUDA(cudaMemcpyAsync(f->d_lut, f->h_lut, sizeof(Rb200Av1FilterLUT), cudaMemcpyHostToDevice, st));
         }
         if (restore_planes)
@@ -841,6 +902,12 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
 
     MARK(1);
     int r;
+    if (build_lf) {
+        if ((r = lf_build_launch(f->d_lfb, f->n_lfb, g.w4, g.h4, g.sb128w, g.sb128h, g.b4_stride, g.ss_hor, g.ss_ver, g.n_planes,
+                                 f->d_lf_cells, f->d_cdef_idx, f->d_masks, f->d_lvl + 32, f->lf_stream))) return r;
+        f->launches += 2;
+        RB_CUDA(cudaEventRecord(f->lf_join, f->lf_stream));
+    }
     // ---- reconstruction: prediction, then residual add
     if (stages & RB200_STAGE_RECON) {
         if (n_mc) {
@@ -903,6 +970,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
     }
     f->out = f->planes[0];
     if (stages & RB200_STAGE_RECON) MARK(3); else { MARK(2); MARK(3); }
+    if (build_lf) RB_CUDA(cudaStreamWaitEvent(st, f->lf_join, 0));
     // ---- deblock (in place): all column edges, then all row edges (src/recon.rs:4047-4170)
     if (do_lf) {
         if ((r = deblock_frame_launch(f->planes[0], g.n_planes, g.w4, g.h4, g.sb128w, g.b4_stride, g.ss_hor, g.ss_ver,
@@ -982,4 +1050,4 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
 #undef MARK
     return 0;
 }
-static_assert(sizeof(Rb200WarpItem) == 48 && sizeof(Rb200CompItem) == 32 && sizeof(Rb200McItem) == 16 && sizeof(Rb200ItxItem) == 16 && sizeof(Rb200McScaledItem) == 32 && sizeof(Rb200IntraItem) == 16, "batch record sizes");
+static_assert(sizeof(Rb200WarpItem) == 48 && sizeof(Rb200CompItem) == 32 && sizeof(Rb200McItem) == 16 && sizeof(Rb200ItxItem) == 16 && sizeof(Rb200McScaledItem) == 32 && sizeof(Rb200IntraItem) == 16 && sizeof(Rb200LfBlock) == 16, "batch record sizes");

@@ -118,6 +118,10 @@ assert INTRA_ITEM_DT.itemsize == 16
 WARP_ITEM_DT = _np.dtype([("x", "<i2"), ("y", "<i2"), ("w", "u1"), ("h", "u1"), ("ref", "u1"), ("pad0", "u1"),
                           ("matrix", "<i4", (6,)), ("abcd", "<i2", (4,)), ("pad", "u1", (8,))])
 assert WARP_ITEM_DT.itemsize == 48
+LF_BLOCK_DT = _np.dtype([("bx", "<u2"), ("by", "<u2"), ("bs", "u1"), ("flags", "u1"), ("ytx", "u1"), ("uvtx", "u1"),
+                         ("tx_split", "<u2", (2,)), ("lvl", "u1", (4,))])
+assert LF_BLOCK_DT.itemsize == 16
+LFB_INTRA, LFB_SKIP, LFB_HAS_CHROMA = 1, 2, 4
 COMP_AVG, COMP_WEIGHTED_AVG, COMP_SEG, COMP_WEDGE = 0, 1, 2, 3
 MC_PUT, MC_OBMC_ABOVE, MC_OBMC_LEFT = 0, 1, 2
 assert MC_ITEM_DT.itemsize == 16 and ITX_ITEM_DT.itemsize == 16 and COMP_ITEM_DT.itemsize == 32
@@ -264,6 +268,10 @@ frame_set_stream = _sig("rb200_frame_set_stream", _i, _vp, _vp)
 frame_enable_timing = _sig("rb200_frame_enable_timing", _i, _vp, _i)
 frame_stage_times = _sig("rb200_frame_stage_times", _i, _vp, C.POINTER(C.c_float))
 frame_last_launches = _sig("rb200_frame_last_launches", _i, _vp)
+frame_reserve_lf_blocks = _sig("rb200_frame_reserve_lf_blocks", _i, _vp, _i)
+frame_lf_blocks = _sig("rb200_frame_lf_blocks", _vp, _vp)
+frame_set_lf_block_count = _sig("rb200_frame_set_lf_block_count", _i, _vp, _i)
+frame_download_lf = _sig("rb200_frame_download_lf", _i, _vp, _vp, _vp)
 
 
 def np_view(ptr, dtype, count):

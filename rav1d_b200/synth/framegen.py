@@ -871,6 +871,11 @@ class DeviceFrame:
             lib.check(lib.frame_reserve_warp_items(self.h, len(warp)), "reserve_warp_items")
             lib.np_view(lib.frame_warp_items(self.h), lib.WARP_ITEM_DT, len(warp))[:] = warp
             lib.check(lib.frame_set_warp_count(self.h, len(warp)))
+        lfb = getattr(s, "lf_blocks", None)
+        if lfb is not None and len(lfb):       # masks and levels built on the device
+            lib.check(lib.frame_reserve_lf_blocks(self.h, len(lfb)), "reserve_lf_blocks")
+            lib.np_view(lib.frame_lf_blocks(self.h), lib.LF_BLOCK_DT, len(lfb))[:] = lfb
+            lib.check(lib.frame_set_lf_block_count(self.h, len(lfb)))
         comp = getattr(s, "comp_items", None)
         if comp is not None and len(comp):
             lib.check(lib.frame_reserve_comp_items(self.h, len(comp)), "reserve_comp_items")
@@ -922,9 +927,93 @@ class DeviceFrame:
     def wait(self):
         lib.check(lib.frame_wait(self.h), "frame_wait")
 
+    def download_lf(self):
+        """(Av1Filter[sb128h * sb128w], level[32 sb128h][b4_stride][4]) as the device holds them after the last submit."""
+        g = self.g
+        masks = np.zeros(g.sb128w * g.sb128h, lib.AV1_FILTER_DT)
+        levels = np.zeros((32 * g.sb128h, g.b4_stride, 4), np.uint8)
+        lib.check(lib.frame_download_lf(self.h, masks.ctypes.data, levels.ctypes.data), "frame_download_lf")
+        return masks, levels
+
     def readback(self):
         s = self.s
         out = [np.zeros_like(p) for p in getattr(s, "readback_like", s.ref)]
         data, strides = _plane_args(out)
         lib.check(lib.frame_readback(self.h, data, strides), "frame_readback")
         return out
+
+
+# ---- loop-filter block records (SURVEY 8 row f2): a random partition tree per superblock, in decode order
+_BS_DIMS = [(32, 32), (32, 16), (16, 32), (16, 16), (16, 8), (16, 4), (8, 16), (8, 8), (8, 4), (8, 2), (4, 16), (4, 8), (4, 4),
+            (4, 2), (4, 1), (2, 8), (2, 4), (2, 2), (2, 1), (1, 4), (1, 2), (1, 1)]     # BlockSize -> (w4, h4)
+_TX_OF_LOG = {(0, 0): 0, (1, 1): 1, (2, 2): 2, (3, 3): 3, (4, 4): 4, (0, 1): 5, (1, 0): 6, (1, 2): 7, (2, 1): 8, (2, 3): 9,
+              (3, 2): 10, (3, 4): 11, (4, 3): 12, (0, 2): 13, (2, 0): 14, (1, 3): 15, (3, 1): 16, (2, 4): 17, (4, 2): 18}
+
+
+def _tx_for(lw, lh, cap):
+    """Largest transform (RectTxfmSize) that fits a 2^lw x 2^lh (4-px units) area, sides capped, aspect <= 4:1."""
+    lw, lh = min(lw, cap), min(lh, cap)
+    lw, lh = min(lw, lh + 2), min(lh, lw + 2)
+    return _TX_OF_LOG[(lw, lh)]
+
+
+def generate_lf_blocks(w, h, layout=1, sb128=1, seed=1, intra_frac=0.3, skip_frac=0.3, min_log=0):
+    """Block records (lib.LF_BLOCK_DT) covering a w x h picture in decode order (one tile): every superblock is split
+    by a random partition tree (none / horizontal / vertical / 4-way horizontal / 4-way vertical / quad), blocks whose
+    origin lies outside the 8-pixel aligned picture are not coded (src/decode.rs decode_sb), sizes are real BlockSizes.
+    Inter blocks carry random tx_split words, max_ytx / uvtx follow the block size; levels are random with some zeros."""
+    rng = np.random.default_rng(seed)
+    ss_hor, ss_ver = int(layout not in (0, 3)), int(layout == 1)
+    bw, bh = ((w + 7) >> 3) << 1, ((h + 7) >> 3) << 1
+    sb = 32 if sb128 else 16
+    bs_of = {d: i for i, d in enumerate(_BS_DIMS)}
+    out = []
+
+    def emit(x, y, bw4, bh4):
+        if x >= bw or y >= bh:
+            return
+        lw, lh = bw4.bit_length() - 1, bh4.bit_length() - 1
+        intra = rng.random() < intra_frac
+        has_chroma = layout != 0 and (bw4 > ss_hor or (x & 1)) and (bh4 > ss_ver or (y & 1))
+        flags = (lib.LFB_INTRA if intra else 0) | (lib.LFB_SKIP if rng.random() < skip_frac else 0) | \
+                (lib.LFB_HAS_CHROMA if has_chroma else 0)
+        ytx = _tx_for(lw, lh, 4)
+        if intra and rng.random() < 0.5:        # intra blocks may use a smaller uniform transform
+            k = int(rng.integers(0, 3))
+            ytx = _tx_for(max(lw - k, 0), max(lh - k, 0), 4)
+        uvtx = _tx_for(max(lw - ss_hor, 0), max(lh - ss_ver, 0), 3)
+        split = rng.integers(0, 1 << 16, size=2) & rng.integers(0, 1 << 16, size=2) if rng.random() < 0.7 else (0, 0)
+        lvl = rng.integers(0, 64, size=4)
+        lvl[rng.random(4) < 0.1] = 0
+        out.append((x, y, bs_of[(bw4, bh4)], flags, ytx, uvtx, (int(split[0]), int(split[1])), tuple(int(v) for v in lvl)))
+
+    def part(x, y, n):      # n: side of the square in 4-px units
+        if x >= bw or y >= bh:
+            return
+        r = rng.random()
+        if n == 1 or (r < (0.08 if n >= 16 else 0.25) and n > (1 << min_log)):
+            return emit(x, y, n, n)
+        hn = n >> 1
+        if n == 2 and ss_hor + ss_ver and r < 0.5:      # 8x8 stays whole half of the time (chroma 4x4)
+            return emit(x, y, n, n)
+        if r < 0.35:
+            emit(x, y, n, hn); emit(x, y + hn, n, hn)
+        elif r < 0.45:
+            emit(x, y, hn, n); emit(x + hn, y, hn, n)
+        elif r < 0.50 and n >= 4 and n <= 16:
+            q = n >> 2
+            for i in range(4):
+                emit(x, y + i * q, n, q)
+        elif r < 0.55 and n >= 4 and n <= 16:
+            q = n >> 2
+            for i in range(4):
+                emit(x + i * q, y, q, n)
+        else:
+            for dy in (0, hn):
+                for dx in (0, hn):
+                    part(x + dx, y + dy, hn)
+
+    for sy in range(0, bh, sb):
+        for sx in range(0, bw, sb):
+            part(sx, sy, sb)
+    return np.array(out, dtype=lib.LF_BLOCK_DT)

@@ -55,6 +55,7 @@ def load():
         sig("ref_calc_eih", None, vp, i)
         sig("ref_sizeof", sz, i)
         sig("ref_frame_new", vp, vp, i)
+        sig("ref_lf_build", i, vp, i, i, i, i, i, i, i, i, vp, vp)
         sig("ref_frame_free", None, vp)
         sig("ref_frame_plane", vp, vp, i)
         sig("ref_frame_stride", ss, vp, i)

@@ -154,6 +154,34 @@ GOLDEN = os.path.join(ROOT, "tests", "golden", "streams.npz")
 GOLDEN_GRAIN = os.path.join(ROOT, "tests", "golden", "film_grain.npz")
 GOLDEN_SR = os.path.join(ROOT, "tests", "golden", "streams_sr.npz")
 GOLDEN_SIZES = os.path.join(ROOT, "tests", "golden", "streams_sizes.npz")
+GOLDEN_LFB = os.path.join(ROOT, "tests", "golden", "streams_lfb.npz")
+
+
+def dump_lfb(path, max_frames=4):
+    """{frame index: Rb200LfBlock records} -- the arguments of every dav1d_create_lf_mask_{intra,inter} call the reference
+    decoder made for the frame, in decode order (oracle/ref_dump.c, RB200_DUMP_LFB).  Frames without deblocking have none."""
+    from rav1d_b200 import lib
+    with tempfile.TemporaryDirectory() as td:
+        out, lfb = os.path.join(td, "o.bin"), os.path.join(td, "lfb.bin")
+        r = subprocess.run([REF_DUMP, path, out, str(max_frames)], capture_output=True, text=True, env=dict(os.environ, RB200_DUMP_LFB=lfb))
+        if r.returncode != 0 or not os.path.exists(lfb):
+            return {}
+        buf = np.fromfile(lfb, dtype=np.uint8)
+    res, off = {}, 0
+    while off + 12 <= buf.size:
+        magic, idx, n = (int(v) for v in buf[off:off + 12].view("<i4"))
+        assert magic == 0x52424c42, "bad lf-block dump magic"
+        off += 12
+        res[idx] = buf[off:off + 16 * n].view(lib.LF_BLOCK_DT).copy()
+        off += 16 * n
+    return res
+
+
+def load_golden_lfb(path=GOLDEN_LFB):
+    """{key: records} for the frames of tests/golden/streams.npz that were deblocked."""
+    from rav1d_b200 import lib
+    z = np.load(path, allow_pickle=False)
+    return {str(k): z[str(k)].view(lib.LF_BLOCK_DT).reshape(-1) for k in z["index"]}
 
 
 def load_golden(path=GOLDEN):

@@ -94,8 +94,27 @@ def main_grain():
     print(f"{len(index)} film-grain frames -> {streamdump.GOLDEN_GRAIN} ({os.path.getsize(streamdump.GOLDEN_GRAIN) / 1e6:.2f} MB)")
 
 
+def main_lfb():
+    """tests/golden/streams_lfb.npz: the per-block create_lf_mask arguments of the deblocked frames of STREAMS
+    (same keys as streams.npz, which holds the masks and levels the decoder derived from them)."""
+    blob, index = {}, []
+    for rel, n in STREAMS:
+        for idx, rec in sorted(streamdump.dump_lfb(os.path.join(streamdump.REF_DATA, rel), n).items()):
+            if len(rec):
+                key = f"{rel}#{idx}"
+                index.append(key)
+                blob[key] = rec.view(np.uint8)
+    blob["index"] = np.array(index)
+    np.savez_compressed(streamdump.GOLDEN_LFB, **blob)
+    print(f"{len(index)} frames -> {streamdump.GOLDEN_LFB} ({os.path.getsize(streamdump.GOLDEN_LFB) / 1e6:.2f} MB)")
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["lfb"]:
+        main_lfb()
+        sys.exit(0)
     main()
     main(SR_STREAMS, streamdump.GOLDEN_SR, sr=True)
     main(SIZE_STREAMS, streamdump.GOLDEN_SIZES)
     main_grain()
+    main_lfb()
