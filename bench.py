@@ -213,6 +213,8 @@ def run_gpu(args, s, wl):
 
     ctxs = []
     start_planes = None if stages & 1 else framegen.recon_input_planes(s)
+    if args.lf == "records":
+        s.lf_blocks = s.lf_block_records
     for i in range(N_CTX):
         d = framegen.DeviceFrame(s)
         d.load_batch()
@@ -363,7 +365,10 @@ def run_gpu(args, s, wl):
             h2d += s.n_coefs * cs
         h2d += 16 * (len(s.itx_items) + n_mc + len(getattr(s, "obmc_items", ()))) + 32 * len(getattr(s, "comp_items", ())) \
             + 48 * len(getattr(s, "warp_items", ()))
-    h2d += n_sb * 1348 + (g.b4_stride * 32 * g.sb128h + 32) * 4 + 144 + n_sb * 108
+    if args.lf == "records":
+        h2d += 16 * len(s.lf_blocks) + n_sb * 4 + 144 + n_sb * 108
+    else:
+        h2d += n_sb * 1348 + (g.b4_stride * 32 * g.sb128h + 32) * 4 + 144 + n_sb * 108
     d2h = sum(out_bytes)
 
     line = None
@@ -398,6 +403,7 @@ def run_gpu(args, s, wl):
                 "config": {"workload": desc, "frames_per_step": FRAMES_PER_STEP, "width": w, "height": h, "bpc": bpc,
                            "l2": f"inputs larger than L2: {N_CTX} frame contexts cycled, > {ab['S'] * 4 // 1000000} MB working set each",
                            "frames_in_flight": N_CTX if multi else 1,
+                           "lf_metadata": "block records, masks built on the device" if args.lf == "records" else "masks and levels uploaded",
                            "parallelism": f"{world} independent streams (one per GPU)" if world > 1 else "1 video stream"},
                 "fps": value * 1e6 / (w * h),
                 "value_one_stream": value_serial,
@@ -452,6 +458,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="4k10", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--lf", default="masks", choices=["masks", "records"],
+                    help="loop-filter metadata: Av1Filter masks + levels uploaded, or per-block records uploaded and the masks built on the device")
     ap.add_argument("--streams", type=int, default=N_CTX, help="resident leg: 1 = all frames on one stream, >1 = one stream per frame context")
     ap.add_argument("--coefs", default="gather", choices=["gather", "zerocopy", "copy"],
                     help="e2e leg, how coefficients cross PCIe: a gather kernel pulls each block's non-zero columns into "

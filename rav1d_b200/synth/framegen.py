@@ -385,6 +385,15 @@ def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1, comp_frac=0.0, w
     for dy in (0, 2):
         np.bitwise_or.at(nsk, (sbb, ((by4 + dy) & 31) >> 1, (bx4 & 16) >> 4), (0xF << (bx4 & 15)).astype(np.uint16))
     s.masks = masks
+    # The same facts as per-block records, the arguments rav1d_create_lf_mask_inter would get for these blocks
+    # (SURVEY 8 row f2): assign to s.lf_blocks to have the masks and levels built on the device instead.
+    rec = np.zeros(nb, lib.LF_BLOCK_DT)
+    rec["bx"], rec["by"], rec["bs"] = bx * 4, by * 4, 12                     # BS_16x16
+    rec["flags"] = np.where(skip, lib.LFB_SKIP, 0) | lib.LFB_HAS_CHROMA
+    rec["ytx"], rec["uvtx"] = TX_16X16, np.where(ctx_split, TX_4X4, TX_8X8)
+    rec["tx_split"][:, 0] = ytx_split                                        # one split: four TX_8X8
+    rec["lvl"] = lv.reshape(4, nb).T
+    s.lf_block_records = rec
 
     # ---- loop restoration units
     lrm = np.zeros(g.sb128w * g.sb128h, lib.AV1_RESTORATION_DT)

@@ -196,3 +196,30 @@ def test_device_masks_match_the_reference_decoder(rb, key):
             assert np.array_equal(a, b), f"{key}: filtered plane {p} differs"
     finally:
         d.close()
+
+
+@pytest.mark.parametrize("w,h,bpc", [(200, 120, 8), (640, 360, 10)])
+def test_synthetic_frame_records_describe_its_masks(ref, w, h, bpc):
+    """The block records framegen.generate() emits, run through the reference's functions, give the masks and levels the
+    generator wrote by hand -- so a bench or test may hand either form to the frame path."""
+    from rav1d_b200.synth import framegen
+    s = framegen.generate(w, h, bpc, seed=w)
+    m, lv = oracle_lf(ref, s.lf_block_records, w, h, 1, 1)
+    assert_lf_equal(s.masks, s.levels, m, lv, w, h, 1, f"{w}x{h}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,bpc", [(200, 120, 8), (640, 360, 10), (264, 200, 12)])
+def test_frame_path_with_records_matches_the_reference_drivers(ref, rb, w, h, bpc):
+    """Recon + deblock + CDEF + LR with the masks built on the device against the reference's frame drivers."""
+    import framecheck
+    from rav1d_b200.synth import framegen
+    s = framegen.generate(w, h, bpc, seed=w + bpc)
+    a = framecheck.oracle_frame(ref, s, 15)
+    s.lf_blocks = s.lf_block_records
+    keep = s.masks
+    s.masks = keep.copy()
+    s.masks["filter_y"] = 0; s.masks["filter_uv"] = 0; s.masks["noskip_mask"] = 0
+    s.levels = np.zeros_like(s.levels)
+    b = framecheck.product_frame(s, 15)
+    framecheck.assert_planes_equal(a, b, f"{w}x{h}@{bpc} with lf records")
