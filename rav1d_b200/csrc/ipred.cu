@@ -316,6 +316,7 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
     using pixel = typename BD::pixel;
     __shared__ IpScratch<pixel> S;
     __shared__ int itile[65 * 32];          // the residual's transform tile (largest: 64 x 32 + padding)
+    __shared__ int res_s[64 * 64];          // the residual itself, computed while waiting for the neighbours
     __shared__ int16_t ac_s[32 * 32];       // chroma-from-luma: the sub-sampled, zero-mean luma of the block
     __shared__ int red_s[4];
     // Programmatic dependent launch: let the next level's grid be scheduled now; it (like this one) does its
@@ -357,6 +358,31 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
     const pixel *dst_top = dst - ps;      // only dereferenced when have_top
     pixel *tl = S.e + IP_EC;
     const int ti = itx_of ? itx_of[blockIdx.x] : -1;
+    // The residual depends on the coefficients only: both transform passes run BEFORE the wait, i.e. while the previous
+    // level is still reconstructing, and leave the term to add in shared memory.  After the wait the critical path is
+    // edge -> prediction -> add.
+    int res_w = 0, res_h = 0, res_plane = 0, res_x = 0, res_y = 0;
+    if (ti >= 0) {
+        const Rb200ItxItem t = itx[ti];
+        res_plane = t.plane; res_x = t.x; res_y = t.y;
+        switch (t.tx) {
+#define CASE(TX) case TX: itx_residual_block<BD, TX>(itile, res_s, tid, tid < ItxGeom<TX>::T, t, cf, bdmax); res_w = tx_w(TX); res_h = tx_h(TX); break;
+            CASE(0) CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9)
+            CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16) CASE(17) CASE(18)
+#undef CASE
+        default: break;
+        }
+    }
+    // dst = clip(dst + residual), rows of the block coalesced (call after a __syncthreads that follows the prediction)
+    auto add_residual = [&]() {
+        const int64_t rstride = plane_stride(cur, res_plane);
+        uint8_t *rbase = plane_ptr(cur, res_plane) + (int64_t)res_y * rstride;
+        const int lw = 31 - __clz(res_w);
+        for (int i = tid; i < res_w * res_h; i += blockDim.x) {
+            pixel *d = (pixel *)(rbase + (int64_t)(i >> lw) * rstride) + res_x + (i & (res_w - 1));
+            *d = (pixel)iclip((int)*d + res_s[i], 0, bdmax);
+        }
+    };
     asm volatile("griddepcontrol.wait;" ::: "memory");      // everything before this level is in the picture now
     if (it.mode >= 14) {
         // 14: palette block (pal_pred, src/ipred_tmpl.c:717-729): w4_end | h4_end << 16 is the offset, in 16-byte units, of
@@ -371,14 +397,7 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
         }
         if (ti < 0) return;
         __syncthreads();
-        const Rb200ItxItem t = itx[ti];
-        switch (t.tx) {
-#define CASE(TX) case TX: itx_add_block<BD, TX>(itile, tid, tid < ItxGeom<TX>::T, t, cur, cf, bdmax); break;
-            CASE(0) CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9)
-            CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16) CASE(17) CASE(18)
-#undef CASE
-        default: break;
-        }
+        add_residual();
         return;
     }
     // ---- left column and top row
@@ -498,14 +517,7 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
     // ---- the block's residual on top of its prediction, in the same launch (the prediction is visible to the CTA)
     if (ti < 0) return;
     __syncthreads();
-    const Rb200ItxItem t = itx[ti];
-    switch (t.tx) {
-#define CASE(TX) case TX: itx_add_block<BD, TX>(itile, tid, tid < ItxGeom<TX>::T, t, cur, cf, bdmax); break;
-        CASE(0) CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9)
-        CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16) CASE(17) CASE(18)
-#undef CASE
-    default: break;
-    }
+    add_residual();
 }
 
 int intra_items_launch(const Rb200Planes &cur, const Rb200IntraItem *d_items, const int32_t *d_itx_of, const Rb200ItxItem *d_itx,

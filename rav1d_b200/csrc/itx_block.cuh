@@ -140,4 +140,63 @@ __device__ __forceinline__ void itx_add_block(int *tl, int lane, bool live, cons
     }
 }
 
+// The same transform, but the term that itx_add_block adds to the destination is left in shared memory instead
+// (`res`, W x H ints, row-major): the fused intra kernel computes it while it waits for the block's neighbours and adds
+// it once the prediction is in place.  EVERY thread of the CTA must call this.
+template <typename BD, int TX>
+__device__ __forceinline__ void itx_residual_block(int *tl, int *res, int lane, bool live, const Rb200ItxItem &it,
+                                                   const typename BD::coef *__restrict__ cf, int bdmax) {
+    using G = ItxGeom<TX>;
+    constexpr int W = G::W, H = G::H, SW = G::SW, SH = G::SH;
+    constexpr int shift = tx_shift(TX);
+    constexpr bool rect2 = (W * 2 == H) || (H * 2 == W);
+    const int row_lo = BD::hbd ? (int)((unsigned)~bdmax << 7) : -32768;
+    const int col_lo = BD::hbd ? (int)((unsigned)~bdmax << 5) : -32768;
+    const int row_hi = ~row_lo, col_hi = ~col_lo;
+    const typename BD::coef *c = cf + it.cf_off;
+    const bool dconly = live && it.txtp == RB200_DCT_DCT && it.eob < 1;
+    const bool wht = it.txtp == RB200_WHT_WHT;
+    if (live && !dconly && lane < SH) {
+        int x[W];
+        const int nc = it.ncols ? it.ncols : SW;
+        if (wht) {
+#pragma unroll
+            for (int i = 0; i < SW; i++) x[i] = i < nc ? (int)c[lane + i * SH] >> 2 : 0;
+        } else {
+#pragma unroll
+            for (int i = 0; i < SW; i++) {
+                const int v = i < nc ? (int)c[lane + i * SH] : 0;
+                x[i] = rect2 ? (v * 181 + 128) >> 8 : v;
+            }
+        }
+        run_kind<W>(txtp_row_kind(it.txtp), x, row_lo, row_hi);
+        constexpr int rnd = (1 << shift) >> 1;
+        if (wht) {
+#pragma unroll
+            for (int i = 0; i < W; i++) tl[lane * G::PITCH + i] = x[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < W; i++) tl[lane * G::PITCH + i] = iclip((x[i] + rnd) >> shift, col_lo, col_hi);
+        }
+    }
+    __syncthreads();
+    if (!live || lane >= W) return;
+    if (dconly) {   // src/itx.rs:90-111
+        int dc = c[0];
+        if (rect2) dc = (dc * 181 + 128) >> 8;
+        dc = (dc * 181 + 128) >> 8;
+        dc = (dc + ((1 << shift) >> 1)) >> shift;
+        dc = (dc * 181 + 128 + 2048) >> 12;
+#pragma unroll
+        for (int i = 0; i < H; i++) res[i * W + lane] = dc;
+        return;
+    }
+    int v[H];
+#pragma unroll
+    for (int i = 0; i < SH; i++) v[i] = tl[i * G::PITCH + lane];
+    run_kind<H>(txtp_col_kind(it.txtp), v, col_lo, col_hi);
+#pragma unroll
+    for (int i = 0; i < H; i++) res[i * W + lane] = wht ? v[i] : (v[i] + 8) >> 4;
+}
+
 }  // namespace rb200
