@@ -400,55 +400,45 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
         add_residual();
         return;
     }
-    // ---- left column and top row
-    if (n_left) {
-        const int sz = th << 2;
-        if (have_left) {
-            const int px_have = imin(sz, (h - y) << 2);
-            for (int i = tid; i < sz; i += blockDim.x) tl[-(1 + i)] = dst[(int64_t)imin(i, px_have - 1) * ps - 1];
-        } else {
-            const pixel v = have_top ? dst_top[0] : (pixel)(((1 << bitdepth) >> 1) + 1);
-            for (int i = tid; i < sz; i += blockDim.x) tl[-(1 + i)] = v;
-        }
+    // ---- the edge: left column, top row and their bottom-left / top-right extensions.  Every segment is at most 64
+    // pixels, one per thread; all picture loads of a thread are issued back to back into registers (one global round
+    // trip for the whole edge), then stored; only the replication of a missing extension waits for them.
+    const int szl = th << 2, szt = tw << 2;
+    const int have_bl = (n_left && n_bl && have_left && y + th < h) ? left_has_bottom : 0;
+    const int have_tr = (n_top && n_tr && have_top && x + tw < w) ? top_has_right : 0;
+    {
+        const bool ld_l = n_left && have_left && tid < szl, ld_t = n_top && have_top && tid < szt;
+        const bool ld_bl = have_bl && tid < szl, ld_tr = have_tr && tid < szt;
+        pixel r_l = 0, r_t = 0, r_bl = 0, r_tr = 0, r_fl = 0, r_ft = 0;
+        if (ld_l) r_l = dst[(int64_t)imin(tid, imin(szl, (h - y) << 2) - 1) * ps - 1];
+        if (ld_t) r_t = dst_top[imin(tid, imin(szt, (w - x) << 2) - 1)];
+        if (ld_bl) r_bl = dst[(int64_t)(szl + imin(tid, imin(szl, (h - y - th) << 2) - 1)) * ps - 1];
+        if (ld_tr) r_tr = dst_top[szt + imin(tid, imin(szt, (w - x - tw) << 2) - 1)];
+        if (n_left && !have_left) r_fl = have_top ? dst_top[0] : (pixel)(((1 << bitdepth) >> 1) + 1);
+        if (n_top && !have_top) r_ft = have_left ? dst[-1] : (pixel)(((1 << bitdepth) >> 1) - 1);
+        if (n_left && tid < szl) tl[-(1 + tid)] = have_left ? r_l : r_fl;
+        if (n_top && tid < szt) tl[1 + tid] = have_top ? r_t : r_ft;
+        if (ld_bl) tl[-(szl + 1 + tid)] = r_bl;
+        if (ld_tr) tl[1 + szt + tid] = r_tr;
     }
-    if (n_top) {
-        const int sz = tw << 2;
-        if (have_top) {
-            const int px_have = imin(sz, (w - x) << 2);
-            for (int i = tid; i < sz; i += blockDim.x) tl[1 + i] = dst_top[imin(i, px_have - 1)];
-        } else {
-            const pixel v = have_left ? dst[-1] : (pixel)(((1 << bitdepth) >> 1) - 1);
-            for (int i = tid; i < sz; i += blockDim.x) tl[1 + i] = v;
-        }
+    int corner = 0;
+    if (n_tl && tid == 0) {
+        if (have_left) corner = have_top ? dst_top[-1] : dst[-1];
+        else corner = have_top ? dst_top[0] : (1 << bitdepth) >> 1;
     }
     __syncthreads();
-    // ---- bottom-left and top-right extensions
-    if (n_left && n_bl) {
+    if (n_left && n_bl && !have_bl) {
         const int sz = th << 2;
-        const int have_bl = (!have_left || y + th >= h) ? 0 : left_has_bottom;
-        if (have_bl) {
-            const int px_have = imin(sz, (h - y - th) << 2);
-            for (int i = tid; i < sz; i += blockDim.x) tl[-(sz + 1 + i)] = dst[(int64_t)(sz + imin(i, px_have - 1)) * ps - 1];
-        } else {
-            const pixel v = tl[-sz];
-            for (int i = tid; i < sz; i += blockDim.x) tl[-(sz + 1 + i)] = v;
-        }
+        const pixel v = tl[-sz];
+        for (int i = tid; i < sz; i += blockDim.x) tl[-(sz + 1 + i)] = v;
     }
-    if (n_top && n_tr) {
+    if (n_top && n_tr && !have_tr) {
         const int sz = tw << 2;
-        const int have_tr = (!have_top || x + tw >= w) ? 0 : top_has_right;
-        if (have_tr) {
-            const int px_have = imin(sz, (w - x - tw) << 2);
-            for (int i = tid; i < sz; i += blockDim.x) tl[1 + sz + i] = dst_top[sz + imin(i, px_have - 1)];
-        } else {
-            const pixel v = tl[sz];
-            for (int i = tid; i < sz; i += blockDim.x) tl[1 + sz + i] = v;
-        }
+        const pixel v = tl[sz];
+        for (int i = tid; i < sz; i += blockDim.x) tl[1 + sz + i] = v;
     }
     if (n_tl && tid == 0) {
-        int v;
-        if (have_left) v = have_top ? dst_top[-1] : dst[-1];
-        else v = have_top ? dst_top[0] : (1 << bitdepth) >> 1;
+        int v = corner;
         if (mode == IP_Z2 && tw + th >= 6 && eief) v = ((tl[-1] + tl[1]) * 5 + v * 6 + 8) >> 4;
         tl[0] = (pixel)v;
     }
@@ -510,6 +500,18 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
             pixel *d = (pixel *)(dst8 + (int64_t)py * stride) + px;
             *d = (pixel)(((int)*d * (64 - m) + (int)S.tile[py * bw + px] * m + 32) >> 6);
         }
+    } else if (ti >= 0 && res_plane == it.plane && res_x == x * 4 && res_y == y * 4 && res_w == tw * 4 && res_h == th * 4) {
+        // the usual case, a transform block with a residual: predict into shared memory (the transform tile is free by
+        // now) and write prediction + residual once, instead of writing the prediction and reading it back
+        static_assert(sizeof(itile) >= 64 * 64 * sizeof(pixel), "prediction tile");
+        pixel *pred = reinterpret_cast<pixel *>(itile);
+        ipred_block<BD>(S, mode, (uint8_t *)pred, (int64_t)res_w * sizeof(pixel), res_w, res_h,
+                        mode == IP_FILTER ? (it.angle & 7) : (angle | (is_sm << 9) | (eief << 10)), max_w, max_h, bdmax);
+        __syncthreads();
+        const int lw = 31 - __clz(res_w);
+        for (int i = tid; i < res_w * res_h; i += blockDim.x)
+            ((pixel *)(dst8 + (int64_t)(i >> lw) * stride))[i & (res_w - 1)] = (pixel)iclip((int)pred[i] + res_s[i], 0, bdmax);
+        return;
     } else {
         ipred_block<BD>(S, mode, dst8, stride, tw * 4, th * 4, mode == IP_FILTER ? (it.angle & 7) : (angle | (is_sm << 9) | (eief << 10)),
                         max_w, max_h, bdmax);
