@@ -91,6 +91,9 @@ int mc_warp_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_
 struct McRefDims { int w[8], h[8]; };   // luma size of each reference slot
 int mc_scaled_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, const McRefDims &dims, int ss_hor,
                            int ss_ver, const Rb200McScaledItem *d_items, int n, int bdmax, cudaStream_t st);
+int intra_levels_launch(const Rb200Planes &cur, const Rb200IntraItem *d_items, const int32_t *d_itx_of, const Rb200ItxItem *d_itx,
+                        const void *cf, const uint8_t *d_pal, const int32_t *d_level_off, int n_levels, int max_items_per_level,
+                        int frame_w4, int frame_h4, int ss_hor, int ss_ver, int bdmax, unsigned *d_sync, cudaStream_t st);
 int intra_items_launch(const Rb200Planes &cur, const Rb200IntraItem *d_items, const int32_t *d_itx_of, const Rb200ItxItem *d_itx,
                        const void *cf, const uint8_t *d_pal, int n, int frame_w4, int frame_h4, int ss_hor, int ss_ver, int bdmax,
                        cudaStream_t st);

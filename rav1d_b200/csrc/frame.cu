@@ -49,6 +49,9 @@ struct Rb200Frame {
     int32_t *h_intra_itx, *d_intra_itx;           // per intra item: index of its residual in the itx list, -1 = none
     uint8_t *h_pal, *d_pal; size_t max_pal, n_pal; // palette records of the palette blocks
     int32_t *intra_counts, *intra_itx_counts;     // [max_levels], [max_levels][RB200_N_RECT_TX_SIZES]
+    int32_t *h_level_off, *d_level_off;           // [max_levels + 1] item offsets of the levels (one-launch wavefront)
+    unsigned *d_intra_sync, *h_intra_sync;        // arrival counter + time-limit flag of that launch
+    int intra_widest; bool intra_check;
     // super-resolution (hdr.upscaled_width > hdr.width): plane sets at the upscaled width --
     // 0 = upscaled CDEF output, 1 = upscaled deblocked picture (what lr_line_buf holds on the CPU), 2 = LR output
     bool sr;
@@ -254,6 +257,10 @@ extern "C" int rb200_frame_destroy(Rb200Frame *f) {
     if (f->h_mc) cudaFreeHost(f->h_mc);
     if (f->d_mc) cudaFree(f->d_mc);
     if (f->d_counters) cudaFree(f->d_counters);
+    if (f->h_level_off) cudaFreeHost(f->h_level_off);
+    if (f->d_level_off) cudaFree(f->d_level_off);
+    if (f->h_intra_sync) cudaFreeHost(f->h_intra_sync);
+    if (f->d_intra_sync) cudaFree(f->d_intra_sync);
     if (f->h_lfb) cudaFreeHost(f->h_lfb);
     if (f->d_lfb) cudaFree(f->d_lfb);
     if (f->d_lf_cells) cudaFree(f->d_lf_cells);
@@ -616,6 +623,13 @@ extern "C" int rb200_frame_reserve_intra_items(Rb200Frame *f, int max_items, int
     }
     if (max_levels > f->max_levels) {
         free(f->intra_counts); free(f->intra_itx_counts);
+        RB_CUDA(cudaStreamSynchronize(f->stream));
+        if (f->h_level_off) cudaFreeHost(f->h_level_off);
+        if (f->d_level_off) cudaFree(f->d_level_off);
+        f->h_level_off = nullptr; f->d_level_off = nullptr;
+        int r = alloc_pair(&f->h_level_off, &f->d_level_off, (size_t)max_levels + 1);
+        if (!r && !f->d_intra_sync) r = alloc_pair(&f->h_intra_sync, &f->d_intra_sync, 2);
+        if (r) return r;
         f->intra_counts = (int32_t *)calloc((size_t)max_levels, sizeof(int32_t));
         f->intra_itx_counts = (int32_t *)calloc((size_t)max_levels * RB200_N_RECT_TX_SIZES, sizeof(int32_t));
         if (!f->intra_counts || !f->intra_itx_counts) return set_error(-12, "frame_reserve_intra_items: out of memory");
@@ -655,6 +669,12 @@ extern "C" int rb200_frame_set_intra_levels(Rb200Frame *f, int n_levels, const i
     if (n_levels) {
         memcpy(f->intra_counts, item_counts, (size_t)n_levels * sizeof(int32_t));
         memcpy(f->intra_itx_counts, itx_counts, (size_t)n_levels * RB200_N_RECT_TX_SIZES * sizeof(int32_t));
+    }
+    f->intra_widest = 0;
+    if (f->h_level_off) f->h_level_off[0] = 0;
+    for (int l = 0; l < n_levels; l++) {
+        f->h_level_off[l + 1] = f->h_level_off[l] + item_counts[l];
+        f->intra_widest = imax(f->intra_widest, item_counts[l]);
     }
     f->n_levels = n_levels;
     return 0;
@@ -790,6 +810,11 @@ extern "C" int rb200_frame_wait(Rb200Frame *f) {
     if (!f) return set_error(-22, "frame_wait: null frame");
     RB_CUDA(cudaStreamSynchronize(f->stream));
     RB_CUDA(cudaGetLastError());
+    if (f->intra_check) {       // the one-launch intra wavefront reports a wait that ran into its time limit
+        f->intra_check = false;
+        RB_CUDA(cudaMemcpy(f->h_intra_sync, f->d_intra_sync, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        if (f->h_intra_sync[1]) return set_error(-110, "frame_wait: the intra wavefront timed out waiting for a level (arrivals %u)", f->h_intra_sync[0]);
+    }
     return 0;
 }
 
@@ -877,6 +902,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
                 if (n_in) {
                     RB_CUDA(cudaMemcpyAsync(f->d_intra, f->h_intra, (size_t)n_in * sizeof(Rb200IntraItem), cudaMemcpyHostToDevice, st));
                     RB_CUDA(cudaMemcpyAsync(f->d_intra_itx, f->h_intra_itx, (size_t)n_in * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+                    RB_CUDA(cudaMemcpyAsync(f->d_level_off, f->h_level_off, (size_t)(f->n_levels + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
                     if (f->n_pal) RB_CUDA(cudaMemcpyAsync(f->d_pal, f->h_pal, f->n_pal, cudaMemcpyHostToDevice, st));
                 }
             }
@@ -958,13 +984,22 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         // picture, predicts it and adds its residual
         if ((stages & RB200_STAGE_INTRA) && f->n_levels) {
             const void *cf = upload == RB200_UPLOAD_ZERO_COPY_COEF ? f->h_coef : f->d_coef;
-            int ioff = 0;
-            for (int l = 0; l < f->n_levels; l++) {
-                if (!f->intra_counts[l]) continue;
-                if ((r = intra_items_launch(f->planes[0], f->d_intra + ioff, f->d_intra_itx + ioff, f->d_itx, cf, f->d_pal, f->intra_counts[l],
-                                            g.bw, g.bh, g.ss_hor, g.ss_ver, f->bdmax, st))) return r;
+            static const bool per_level = !(getenv("RB200_INTRA_ONE_LAUNCH") && atoi(getenv("RB200_INTRA_ONE_LAUNCH")));
+            if (!per_level) {
+                // the whole wavefront in one cooperative launch; levels are separated by an arrival counter in global memory
+                if ((r = intra_levels_launch(f->planes[0], f->d_intra, f->d_intra_itx, f->d_itx, cf, f->d_pal, f->d_level_off, f->n_levels,
+                                             f->intra_widest, g.bw, g.bh, g.ss_hor, g.ss_ver, f->bdmax, f->d_intra_sync, st))) return r;
                 f->launches++;
-                ioff += f->intra_counts[l];
+                f->intra_check = true;
+            } else {
+                int ioff = 0;
+                for (int l = 0; l < f->n_levels; l++) {
+                    if (!f->intra_counts[l]) continue;
+                    if ((r = intra_items_launch(f->planes[0], f->d_intra + ioff, f->d_intra_itx + ioff, f->d_itx, cf, f->d_pal, f->intra_counts[l],
+                                                g.bw, g.bh, g.ss_hor, g.ss_ver, f->bdmax, st))) return r;
+                    f->launches++;
+                    ioff += f->intra_counts[l];
+                }
             }
         }
     }

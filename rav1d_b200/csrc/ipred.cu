@@ -308,21 +308,32 @@ ipred_kernel(int mode, uint8_t *dst8, int64_t stride, const typename BD::pixel *
 // replicated, and which implementation mode the coded mode becomes; then the block is predicted in place.
 // The picture rows above a superblock row are still unfiltered when this runs (the in-loop filters come after
 // the whole reconstruction), so the reference's saved pre-filter edge (f.ipred_edge) is the picture itself.
-template <typename BD>
-__global__ void __launch_bounds__(128)
-intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, const int32_t *__restrict__ itx_of,
-                   const Rb200ItxItem *__restrict__ itx, const typename BD::coef *__restrict__ cf, const uint8_t *__restrict__ pal_buf,
-                   int frame_w4, int frame_h4, int ss_hor_c, int ss_ver_c, int bdmax) {
+template <typename P>
+struct IntraSmem {
+    IpScratch<P> S;
+    int itile[65 * 32];          // the residual's transform tile (largest: 64 x 32 + padding)
+    int res_s[64 * 64];          // the residual itself, computed while waiting for the neighbours
+    int16_t ac_s[32 * 32];       // chroma-from-luma: the sub-sampled, zero-mean luma of the block
+    int red_s[4];
+};
+// Picture reads of the persistent kernel bypass L1 (CG): another SM wrote those pixels during this very launch.
+template <bool CG, typename T>
+__device__ __forceinline__ T pic_ld(const T *p) { return CG ? __ldcg(p) : *p; }
+
+// One intra item, all threads of the CTA.  `wait()` is called once, after everything that does not depend on the picture
+// (the item's set-up and the residual's transform) and before the first picture read: it returns when every item of the
+// earlier levels is in the picture.
+template <typename BD, bool CG, typename WaitFn>
+__device__ __forceinline__ void intra_item(IntraSmem<typename BD::pixel> &M, const Rb200Planes &cur, const Rb200IntraItem it, const int ti,
+                                           const Rb200ItxItem *__restrict__ itx, const typename BD::coef *__restrict__ cf,
+                                           const uint8_t *__restrict__ pal_buf, int frame_w4, int frame_h4, int ss_hor_c, int ss_ver_c,
+                                           int bdmax, WaitFn wait) {
     using pixel = typename BD::pixel;
-    __shared__ IpScratch<pixel> S;
-    __shared__ int itile[65 * 32];          // the residual's transform tile (largest: 64 x 32 + padding)
-    __shared__ int res_s[64 * 64];          // the residual itself, computed while waiting for the neighbours
-    __shared__ int16_t ac_s[32 * 32];       // chroma-from-luma: the sub-sampled, zero-mean luma of the block
-    __shared__ int red_s[4];
-    // Programmatic dependent launch: let the next level's grid be scheduled now; it (like this one) does its
-    // picture-independent set-up and then waits below for the previous level to have completed.
-    asm volatile("griddepcontrol.launch_dependents;");
-    const Rb200IntraItem it = items[blockIdx.x];
+    IpScratch<pixel> &S = M.S;
+    int (&itile)[65 * 32] = M.itile;
+    int *res_s = M.res_s;
+    int16_t *ac_s = M.ac_s;
+    int *red_s = M.red_s;
     const int tid = threadIdx.x;
     const int ss_hor = it.plane ? ss_hor_c : 0, ss_ver = it.plane ? ss_ver_c : 0;
     const int64_t stride = plane_stride(cur, it.plane);
@@ -357,7 +368,6 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
     const bool n_tr = mode == IP_Z1, n_bl = mode == IP_Z3;
     const pixel *dst_top = dst - ps;      // only dereferenced when have_top
     pixel *tl = S.e + IP_EC;
-    const int ti = itx_of ? itx_of[blockIdx.x] : -1;
     // The residual depends on the coefficients only: both transform passes run BEFORE the wait, i.e. while the previous
     // level is still reconstructing, and leave the term to add in shared memory.  After the wait the critical path is
     // edge -> prediction -> add.
@@ -380,10 +390,10 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
         const int lw = 31 - __clz(res_w);
         for (int i = tid; i < res_w * res_h; i += blockDim.x) {
             pixel *d = (pixel *)(rbase + (int64_t)(i >> lw) * rstride) + res_x + (i & (res_w - 1));
-            *d = (pixel)iclip((int)*d + res_s[i], 0, bdmax);
+            *d = (pixel)iclip((int)pic_ld<CG>(d) + res_s[i], 0, bdmax);
         }
     };
-    asm volatile("griddepcontrol.wait;" ::: "memory");      // everything before this level is in the picture now
+    wait();                                                 // everything before this level is in the picture now
     if (it.mode >= 14) {
         // 14: palette block (pal_pred, src/ipred_tmpl.c:717-729): w4_end | h4_end << 16 is the offset, in 16-byte units, of
         // { 8 palette entries (16 bytes), w * h index bytes } in the frame's palette buffer.  15: no prediction, only the
@@ -410,12 +420,12 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
         const bool ld_l = n_left && have_left && tid < szl, ld_t = n_top && have_top && tid < szt;
         const bool ld_bl = have_bl && tid < szl, ld_tr = have_tr && tid < szt;
         pixel r_l = 0, r_t = 0, r_bl = 0, r_tr = 0, r_fl = 0, r_ft = 0;
-        if (ld_l) r_l = dst[(int64_t)imin(tid, imin(szl, (h - y) << 2) - 1) * ps - 1];
-        if (ld_t) r_t = dst_top[imin(tid, imin(szt, (w - x) << 2) - 1)];
-        if (ld_bl) r_bl = dst[(int64_t)(szl + imin(tid, imin(szl, (h - y - th) << 2) - 1)) * ps - 1];
-        if (ld_tr) r_tr = dst_top[szt + imin(tid, imin(szt, (w - x - tw) << 2) - 1)];
-        if (n_left && !have_left) r_fl = have_top ? dst_top[0] : (pixel)(((1 << bitdepth) >> 1) + 1);
-        if (n_top && !have_top) r_ft = have_left ? dst[-1] : (pixel)(((1 << bitdepth) >> 1) - 1);
+        if (ld_l) r_l = pic_ld<CG>(&dst[(int64_t)imin(tid, imin(szl, (h - y) << 2) - 1) * ps - 1]);
+        if (ld_t) r_t = pic_ld<CG>(&dst_top[imin(tid, imin(szt, (w - x) << 2) - 1)]);
+        if (ld_bl) r_bl = pic_ld<CG>(&dst[(int64_t)(szl + imin(tid, imin(szl, (h - y - th) << 2) - 1)) * ps - 1]);
+        if (ld_tr) r_tr = pic_ld<CG>(&dst_top[szt + imin(tid, imin(szt, (w - x - tw) << 2) - 1)]);
+        if (n_left && !have_left) r_fl = have_top ? pic_ld<CG>(&dst_top[0]) : (pixel)(((1 << bitdepth) >> 1) + 1);
+        if (n_top && !have_top) r_ft = have_left ? pic_ld<CG>(&dst[-1]) : (pixel)(((1 << bitdepth) >> 1) - 1);
         if (n_left && tid < szl) tl[-(1 + tid)] = have_left ? r_l : r_fl;
         if (n_top && tid < szt) tl[1 + tid] = have_top ? r_t : r_ft;
         if (ld_bl) tl[-(szl + 1 + tid)] = r_bl;
@@ -423,8 +433,8 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
     }
     int corner = 0;
     if (n_tl && tid == 0) {
-        if (have_left) corner = have_top ? dst_top[-1] : dst[-1];
-        else corner = have_top ? dst_top[0] : (1 << bitdepth) >> 1;
+        if (have_left) corner = have_top ? pic_ld<CG>(&dst_top[-1]) : pic_ld<CG>(&dst[-1]);
+        else corner = have_top ? pic_ld<CG>(&dst_top[0]) : (1 << bitdepth) >> 1;
     }
     __syncthreads();
     if (n_left && n_bl && !have_bl) {
@@ -455,12 +465,12 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
         for (int i = tid; i < cw * ch; i += blockDim.x) {
             const int cx = imin(i % cw, vw - 1), cy = imin(i / cw, vh - 1);
             const pixel *p = (const pixel *)(ypx + (int64_t)(cy << ss_ver) * lstride) + (cx << ss_hor);
-            int sum = p[0];
-            if (ss_hor) sum += p[1];
+            int sum = pic_ld<CG>(&p[0]);
+            if (ss_hor) sum += pic_ld<CG>(&p[1]);
             if (ss_ver) {
                 const pixel *q = (const pixel *)((const uint8_t *)p + lstride);
-                sum += q[0];
-                if (ss_hor) sum += q[1];
+                sum += pic_ld<CG>(&q[0]);
+                if (ss_hor) sum += pic_ld<CG>(&q[1]);
             }
             sum <<= 1 + !ss_ver + !ss_hor;
             ac_s[i] = (int16_t)sum;
@@ -498,7 +508,7 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
                 }
             }
             pixel *d = (pixel *)(dst8 + (int64_t)py * stride) + px;
-            *d = (pixel)(((int)*d * (64 - m) + (int)S.tile[py * bw + px] * m + 32) >> 6);
+            *d = (pixel)(((int)pic_ld<CG>(d) * (64 - m) + (int)S.tile[py * bw + px] * m + 32) >> 6);
         }
     } else if (ti >= 0 && res_plane == it.plane && res_x == x * 4 && res_y == y * 4 && res_w == tw * 4 && res_h == th * 4) {
         // the usual case, a transform block with a residual: predict into shared memory (the transform tile is free by
@@ -522,6 +532,70 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
     add_residual();
 }
 
+// (a) one launch per level, with programmatic dependent launch: the next level's grid is scheduled while this one runs,
+// does its picture-independent part and waits for this grid to complete.  Kept for RB200_INTRA_LEVEL_LAUNCHES=1.
+template <typename BD>
+__global__ void __launch_bounds__(128)
+intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, const int32_t *__restrict__ itx_of,
+                   const Rb200ItxItem *__restrict__ itx, const typename BD::coef *__restrict__ cf, const uint8_t *__restrict__ pal_buf,
+                   int frame_w4, int frame_h4, int ss_hor_c, int ss_ver_c, int bdmax) {
+    __shared__ IntraSmem<typename BD::pixel> M;
+    asm volatile("griddepcontrol.launch_dependents;");
+    intra_item<BD, false>(M, cur, items[blockIdx.x], itx_of ? itx_of[blockIdx.x] : -1, itx, cf, pal_buf, frame_w4, frame_h4, ss_hor_c,
+                          ss_ver_c, bdmax, [] { asm volatile("griddepcontrol.wait;" ::: "memory"); });
+}
+
+// (b) ALL levels in one cooperative launch: the grid (every CTA resident) walks the levels; CTA b takes items
+// b, b + gridDim, ... of a level.  Instead of a kernel boundary per level there is a counter in global memory: a CTA that
+// has written its items of level l adds one ("arrive"), and before the first picture read of a level-l item it waits until
+// the counter shows that every CTA has arrived for all levels below l.  Between arriving and waiting it already transforms
+// the residual of its next item.  Saves the launch gap per level and ~2,600 host launches per 4K key frame.
+// sync[0] = arrival counter, sync[1] = set if a wait ever ran into its time limit (a bug, not a state: reported by the host).
+template <typename BD>
+__global__ void __launch_bounds__(128)
+intra_levels_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, const int32_t *__restrict__ itx_of,
+                    const Rb200ItxItem *__restrict__ itx, const typename BD::coef *__restrict__ cf, const uint8_t *__restrict__ pal_buf,
+                    const int32_t *__restrict__ level_off, int n_levels, int frame_w4, int frame_h4, int ss_hor_c, int ss_ver_c,
+                    int bdmax, unsigned *sync) {
+    __shared__ IntraSmem<typename BD::pixel> M;
+    __shared__ int abort_s;
+    const int tid = threadIdx.x;
+    if (tid == 0) abort_s = 0;
+    __syncthreads();
+    for (int l = 0; l < n_levels; l++) {
+        const int beg = level_off[l], end = level_off[l + 1];
+        bool waited = false;
+        for (int i = beg + blockIdx.x; i < end; i += gridDim.x) {
+            intra_item<BD, true>(M, cur, items[i], itx_of ? itx_of[i] : -1, itx, cf, pal_buf, frame_w4, frame_h4, ss_hor_c, ss_ver_c, bdmax,
+                                 [&] {
+                if (waited || l == 0) return;
+                waited = true;
+                if (tid == 0) {
+                    const unsigned target = (unsigned)l * gridDim.x;
+                    const long long t0 = clock64();
+                    unsigned seen;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(sync) : "memory");
+                        if (seen < target && clock64() - t0 > 4000000000LL) { atomicExch(sync + 1, 1u); break; }
+                    } while (seen < target);
+                    unsigned bad;
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(bad) : "l"(sync + 1) : "memory");
+                    if (bad) abort_s = 1;
+                }
+                __syncthreads();
+            });
+            __syncthreads();            // the item's shared memory is reused by the next one
+            if (abort_s) return;
+        }
+        // arrive: this CTA's part of level l is in the picture
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(sync) : "memory");
+        }
+    }
+}
+
 int intra_items_launch(const Rb200Planes &cur, const Rb200IntraItem *d_items, const int32_t *d_itx_of, const Rb200ItxItem *d_itx,
                        const void *cf, const uint8_t *d_pal, int n, int frame_w4, int frame_h4, int ss_hor, int ss_ver, int bdmax,
                        cudaStream_t st) {
@@ -535,6 +609,39 @@ int intra_items_launch(const Rb200Planes &cur, const Rb200IntraItem *d_items, co
     cfg.attrs = attr; cfg.numAttrs = 1;
     if (bdmax > 255) RB_CUDA(cudaLaunchKernelEx(&cfg, intra_items_kernel<BD16>, cur, d_items, d_itx_of, d_itx, (const int32_t *)cf, d_pal, frame_w4, frame_h4, ss_hor, ss_ver, bdmax));
     else RB_CUDA(cudaLaunchKernelEx(&cfg, intra_items_kernel<BD8>, cur, d_items, d_itx_of, d_itx, (const int16_t *)cf, d_pal, frame_w4, frame_h4, ss_hor, ss_ver, bdmax));
+    RB_LAUNCH_CHECK();
+    return 0;
+}
+
+// d_level_off: device, n_levels + 1 item offsets; d_sync: device, 2 words, zeroed here on the stream.
+// max_items_per_level sizes the grid (no more CTAs than the widest level needs).
+int intra_levels_launch(const Rb200Planes &cur, const Rb200IntraItem *d_items, const int32_t *d_itx_of, const Rb200ItxItem *d_itx,
+                        const void *cf, const uint8_t *d_pal, const int32_t *d_level_off, int n_levels, int max_items_per_level,
+                        int frame_w4, int frame_h4, int ss_hor, int ss_ver, int bdmax, unsigned *d_sync, cudaStream_t st) {
+    if (n_levels <= 0) return 0;
+    static int per_sm[2] = { 0, 0 }, n_sm = 0;
+    const int hbd = bdmax > 255;
+    if (!per_sm[hbd]) {
+        int dev = 0, occ = 0;
+        RB_CUDA(cudaGetDevice(&dev));
+        RB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        if (hbd) RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, intra_levels_kernel<BD16>, 128, 0));
+        else RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, intra_levels_kernel<BD8>, 128, 0));
+        if (occ < 1) return set_error(-12, "intra_levels_launch: the kernel does not fit an SM");
+        per_sm[hbd] = occ < 4 ? occ : 4;
+    }
+    // Every CTA arrives once per level whether it had an item or not, so more CTAs than a level is wide only make the
+    // counter slower: two per SM unless RB200_INTRA_CTAS_PER_SM says otherwise, and never more than the widest level.
+    static const int want = getenv("RB200_INTRA_CTAS_PER_SM") ? atoi(getenv("RB200_INTRA_CTAS_PER_SM")) : 2;
+    int grid = imin(imax(want, 1), per_sm[hbd]) * n_sm;
+    if (max_items_per_level > 0 && max_items_per_level < grid) grid = max_items_per_level;
+    RB_CUDA(cudaMemsetAsync(d_sync, 0, 2 * sizeof(unsigned), st));
+    const int32_t *cf32 = (const int32_t *)cf; const int16_t *cf16 = (const int16_t *)cf;
+    Rb200Planes cur_v = cur;
+    void *args16[] = { &cur_v, &d_items, &d_itx_of, &d_itx, &cf32, &d_pal, &d_level_off, &n_levels, &frame_w4, &frame_h4, &ss_hor, &ss_ver, &bdmax, &d_sync };
+    void *args8[] = { &cur_v, &d_items, &d_itx_of, &d_itx, &cf16, &d_pal, &d_level_off, &n_levels, &frame_w4, &frame_h4, &ss_hor, &ss_ver, &bdmax, &d_sync };
+    if (hbd) RB_CUDA(cudaLaunchCooperativeKernel((const void *)intra_levels_kernel<BD16>, dim3(grid), dim3(128), args16, 0, st));
+    else RB_CUDA(cudaLaunchCooperativeKernel((const void *)intra_levels_kernel<BD8>, dim3(grid), dim3(128), args8, 0, st));
     RB_LAUNCH_CHECK();
     return 0;
 }
