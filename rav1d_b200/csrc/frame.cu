@@ -51,7 +51,7 @@ struct Rb200Frame {
     int32_t *intra_counts, *intra_itx_counts;     // [max_levels], [max_levels][RB200_N_RECT_TX_SIZES]
     int32_t *h_level_off, *d_level_off;           // [max_levels + 1] item offsets of the levels (one-launch wavefront)
     unsigned *d_intra_sync, *h_intra_sync;        // arrival counter + time-limit flag of that launch
-    int intra_widest; bool intra_check;
+    int intra_widest, n_levels_nonempty; bool intra_check;
     // super-resolution (hdr.upscaled_width > hdr.width): plane sets at the upscaled width --
     // 0 = upscaled CDEF output, 1 = upscaled deblocked picture (what lr_line_buf holds on the CPU), 2 = LR output
     bool sr;
@@ -628,7 +628,10 @@ extern "C" int rb200_frame_reserve_intra_items(Rb200Frame *f, int max_items, int
         if (f->d_level_off) cudaFree(f->d_level_off);
         f->h_level_off = nullptr; f->d_level_off = nullptr;
         int r = alloc_pair(&f->h_level_off, &f->d_level_off, (size_t)max_levels + 1);
-        if (!r && !f->d_intra_sync) r = alloc_pair(&f->h_intra_sync, &f->d_intra_sync, 2);
+        if (f->h_intra_sync) cudaFreeHost(f->h_intra_sync);
+        if (f->d_intra_sync) cudaFree(f->d_intra_sync);
+        f->h_intra_sync = nullptr; f->d_intra_sync = nullptr;
+        if (!r) r = alloc_pair(&f->h_intra_sync, &f->d_intra_sync, (size_t)max_levels + 1);
         if (r) return r;
         f->intra_counts = (int32_t *)calloc((size_t)max_levels, sizeof(int32_t));
         f->intra_itx_counts = (int32_t *)calloc((size_t)max_levels * RB200_N_RECT_TX_SIZES, sizeof(int32_t));
@@ -670,10 +673,13 @@ extern "C" int rb200_frame_set_intra_levels(Rb200Frame *f, int n_levels, const i
         memcpy(f->intra_counts, item_counts, (size_t)n_levels * sizeof(int32_t));
         memcpy(f->intra_itx_counts, itx_counts, (size_t)n_levels * RB200_N_RECT_TX_SIZES * sizeof(int32_t));
     }
-    f->intra_widest = 0;
+    // item offsets of the non-empty levels (the one-launch wavefront chains each level to the one before it)
+    f->intra_widest = 0; f->n_levels_nonempty = 0;
     if (f->h_level_off) f->h_level_off[0] = 0;
     for (int l = 0; l < n_levels; l++) {
-        f->h_level_off[l + 1] = f->h_level_off[l] + item_counts[l];
+        if (!item_counts[l]) continue;
+        const int k = f->n_levels_nonempty++;
+        f->h_level_off[k + 1] = f->h_level_off[k] + item_counts[l];
         f->intra_widest = imax(f->intra_widest, item_counts[l]);
     }
     f->n_levels = n_levels;
@@ -812,8 +818,8 @@ extern "C" int rb200_frame_wait(Rb200Frame *f) {
     RB_CUDA(cudaGetLastError());
     if (f->intra_check) {       // the one-launch intra wavefront reports a wait that ran into its time limit
         f->intra_check = false;
-        RB_CUDA(cudaMemcpy(f->h_intra_sync, f->d_intra_sync, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost));
-        if (f->h_intra_sync[1]) return set_error(-110, "frame_wait: the intra wavefront timed out waiting for a level (arrivals %u)", f->h_intra_sync[0]);
+        RB_CUDA(cudaMemcpy(f->h_intra_sync, f->d_intra_sync, sizeof(unsigned), cudaMemcpyDeviceToHost));
+        if (f->h_intra_sync[0]) return set_error(-110, "frame_wait: the intra wavefront timed out waiting for a level");
     }
     return 0;
 }
@@ -902,7 +908,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
                 if (n_in) {
                     RB_CUDA(cudaMemcpyAsync(f->d_intra, f->h_intra, (size_t)n_in * sizeof(Rb200IntraItem), cudaMemcpyHostToDevice, st));
                     RB_CUDA(cudaMemcpyAsync(f->d_intra_itx, f->h_intra_itx, (size_t)n_in * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-                    RB_CUDA(cudaMemcpyAsync(f->d_level_off, f->h_level_off, (size_t)(f->n_levels + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+                    RB_CUDA(cudaMemcpyAsync(f->d_level_off, f->h_level_off, (size_t)(f->n_levels_nonempty + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
                     if (f->n_pal) RB_CUDA(cudaMemcpyAsync(f->d_pal, f->h_pal, f->n_pal, cudaMemcpyHostToDevice, st));
                 }
             }
@@ -984,10 +990,10 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         // picture, predicts it and adds its residual
         if ((stages & RB200_STAGE_INTRA) && f->n_levels) {
             const void *cf = upload == RB200_UPLOAD_ZERO_COPY_COEF ? f->h_coef : f->d_coef;
-            static const bool per_level = !(getenv("RB200_INTRA_ONE_LAUNCH") && atoi(getenv("RB200_INTRA_ONE_LAUNCH")));
+            static const bool per_level = getenv("RB200_INTRA_LEVEL_LAUNCHES") && atoi(getenv("RB200_INTRA_LEVEL_LAUNCHES"));
             if (!per_level) {
                 // the whole wavefront in one cooperative launch; levels are separated by an arrival counter in global memory
-                if ((r = intra_levels_launch(f->planes[0], f->d_intra, f->d_intra_itx, f->d_itx, cf, f->d_pal, f->d_level_off, f->n_levels,
+                if ((r = intra_levels_launch(f->planes[0], f->d_intra, f->d_intra_itx, f->d_itx, cf, f->d_pal, f->d_level_off, f->n_levels_nonempty,
                                              f->intra_widest, g.bw, g.bh, g.ss_hor, g.ss_ver, f->bdmax, f->d_intra_sync, st))) return r;
                 f->launches++;
                 f->intra_check = true;

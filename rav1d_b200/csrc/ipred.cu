@@ -546,11 +546,13 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
 }
 
 // (b) ALL levels in one cooperative launch: the grid (every CTA resident) walks the levels; CTA b takes items
-// b, b + gridDim, ... of a level.  Instead of a kernel boundary per level there is a counter in global memory: a CTA that
-// has written its items of level l adds one ("arrive"), and before the first picture read of a level-l item it waits until
-// the counter shows that every CTA has arrived for all levels below l.  Between arriving and waiting it already transforms
-// the residual of its next item.  Saves the launch gap per level and ~2,600 host launches per 4K key frame.
-// sync[0] = arrival counter, sync[1] = set if a wait ever ran into its time limit (a bug, not a state: reported by the host).
+// b, b + gridDim, ... of a level.  Instead of a kernel boundary per level there is one counter per level in global memory:
+// the CTA that has written an item of level l adds one to done[l], and before the first picture read of a level-l item
+// a CTA waits until done[l - 1] equals the number of items of level l - 1.  That is enough: by induction every item of
+// level l - 1 was itself only started when level l - 2 was complete (levels are never empty -- the host drops empty
+// ones).  CTAs without an item in a level neither wait nor count.  Between its items a CTA already transforms the
+// residual of the next one.  Saves the launch gap per level and ~2,600 host launches per 4K key frame.
+// sync[0] = set if a wait ever ran into its time limit (a bug, not a state: reported by rb200_frame_wait), sync[1 + l] = done[l].
 template <typename BD>
 __global__ void __launch_bounds__(128)
 intra_levels_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, const int32_t *__restrict__ itx_of,
@@ -560,38 +562,38 @@ intra_levels_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, c
     __shared__ IntraSmem<typename BD::pixel> M;
     __shared__ int abort_s;
     const int tid = threadIdx.x;
+    unsigned *done = sync + 1;
     if (tid == 0) abort_s = 0;
     __syncthreads();
     for (int l = 0; l < n_levels; l++) {
         const int beg = level_off[l], end = level_off[l + 1];
         bool waited = false;
+        auto level_wait = [&] {
+            if (waited || l == 0) return;
+            waited = true;
+            if (tid == 0) {
+                const unsigned target = (unsigned)(beg - level_off[l - 1]);
+                const long long t0 = clock64();
+                unsigned seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(done + l - 1) : "memory");
+                    if (seen < target && clock64() - t0 > 4000000000LL) { atomicExch(sync, 1u); break; }
+                } while (seen < target);
+                unsigned bad;
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(bad) : "l"(sync) : "memory");
+                if (bad) abort_s = 1;
+            }
+            __syncthreads();
+        };
         for (int i = beg + blockIdx.x; i < end; i += gridDim.x) {
             intra_item<BD, true>(M, cur, items[i], itx_of ? itx_of[i] : -1, itx, cf, pal_buf, frame_w4, frame_h4, ss_hor_c, ss_ver_c, bdmax,
-                                 [&] {
-                if (waited || l == 0) return;
-                waited = true;
-                if (tid == 0) {
-                    const unsigned target = (unsigned)l * gridDim.x;
-                    const long long t0 = clock64();
-                    unsigned seen;
-                    do {
-                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(sync) : "memory");
-                        if (seen < target && clock64() - t0 > 4000000000LL) { atomicExch(sync + 1, 1u); break; }
-                    } while (seen < target);
-                    unsigned bad;
-                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(bad) : "l"(sync + 1) : "memory");
-                    if (bad) abort_s = 1;
-                }
-                __syncthreads();
-            });
-            __syncthreads();            // the item's shared memory is reused by the next one
+                                 level_wait);
+            __syncthreads();            // the item is in the picture (as far as this CTA is concerned) and its shared memory is free
             if (abort_s) return;
-        }
-        // arrive: this CTA's part of level l is in the picture
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(sync) : "memory");
+            if (tid == 0) {
+                __threadfence();
+                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(done + l) : "memory");
+            }
         }
     }
 }
@@ -613,7 +615,7 @@ int intra_items_launch(const Rb200Planes &cur, const Rb200IntraItem *d_items, co
     return 0;
 }
 
-// d_level_off: device, n_levels + 1 item offsets; d_sync: device, 2 words, zeroed here on the stream.
+// d_level_off: device, n_levels + 1 item offsets of NON-EMPTY levels; d_sync: device, n_levels + 1 words, zeroed here on the stream.
 // max_items_per_level sizes the grid (no more CTAs than the widest level needs).
 int intra_levels_launch(const Rb200Planes &cur, const Rb200IntraItem *d_items, const int32_t *d_itx_of, const Rb200ItxItem *d_itx,
                         const void *cf, const uint8_t *d_pal, const int32_t *d_level_off, int n_levels, int max_items_per_level,
@@ -630,12 +632,12 @@ int intra_levels_launch(const Rb200Planes &cur, const Rb200IntraItem *d_items, c
         if (occ < 1) return set_error(-12, "intra_levels_launch: the kernel does not fit an SM");
         per_sm[hbd] = occ < 4 ? occ : 4;
     }
-    // Every CTA arrives once per level whether it had an item or not, so more CTAs than a level is wide only make the
-    // counter slower: two per SM unless RB200_INTRA_CTAS_PER_SM says otherwise, and never more than the widest level.
-    static const int want = getenv("RB200_INTRA_CTAS_PER_SM") ? atoi(getenv("RB200_INTRA_CTAS_PER_SM")) : 2;
+    // As many CTAs as fit (three per SM at 168 registers) unless RB200_INTRA_CTAS_PER_SM says otherwise, and never more
+    // than the widest level has items.
+    static const int want = getenv("RB200_INTRA_CTAS_PER_SM") ? atoi(getenv("RB200_INTRA_CTAS_PER_SM")) : 3;
     int grid = imin(imax(want, 1), per_sm[hbd]) * n_sm;
     if (max_items_per_level > 0 && max_items_per_level < grid) grid = max_items_per_level;
-    RB_CUDA(cudaMemsetAsync(d_sync, 0, 2 * sizeof(unsigned), st));
+    RB_CUDA(cudaMemsetAsync(d_sync, 0, ((size_t)n_levels + 1) * sizeof(unsigned), st));
     const int32_t *cf32 = (const int32_t *)cf; const int16_t *cf16 = (const int16_t *)cf;
     Rb200Planes cur_v = cur;
     void *args16[] = { &cur_v, &d_items, &d_itx_of, &d_itx, &cf32, &d_pal, &d_level_off, &n_levels, &frame_w4, &frame_h4, &ss_hor, &ss_ver, &bdmax, &d_sync };

@@ -18,6 +18,8 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 wl = bench.WORKLOADS[name]
 s = framegen.generate(wl[0], wl[1], wl[2], seed=1, **bench.GEN_ARGS.get(name, {}))
 lib.check(lib.init(0))
+if os.environ.get("RB200_LF_RECORDS"):      # masks and levels built on the device (lf_cells_kernel + lf_words_kernel)
+    s.lf_blocks = s.lf_block_records
 d = framegen.DeviceFrame(s)
 d.load_batch()
 if wl[3] & 1:
