@@ -180,6 +180,32 @@ def test_intra_blocks_wavefront(rb, ref, w, h, bpc, inter_frac):
     framecheck.assert_planes_equal(a, b, f"intra {w}x{h}@{bpc}")
 
 
+@pytest.mark.gpu
+def test_intra_wavefront_per_level_launches(rb):
+    """The alternative schedule of the same wavefront (one launch per level with programmatic dependent launch,
+    RB200_INTRA_LEVEL_LAUNCHES=1; the default is one cooperative launch) stays bit-exact.  The switch is read once per
+    process, hence the child process."""
+    import os
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, 'tests'); import refharness, framecheck\n"
+            "from rav1d_b200 import lib; from rav1d_b200.synth import framegen\n"
+            "lib.check(lib.init(0)); ref = refharness.load()\n"
+            "for w, h, bpc, fr in ((96, 64, 8, 0.0), (192, 128, 10, 0.3)):\n"
+            "    s = framegen.generate_intra(w, h, bpc, seed=w + bpc, inter_frac=fr)\n"
+            "    a = framecheck.oracle_frame(ref, s, lib.STAGE_RECON)\n"
+            "    d = framegen.DeviceFrame(s); d.load_batch(); d.set_ref_from_host(s.ref)\n"
+            "    d.submit(lib.STAGE_RECON | lib.STAGE_INTRA, 1); d.wait()\n"
+            "    assert lib.frame_last_launches(d.h) > len(s.intra_counts) // 2, 'expected one launch per level'\n"
+            "    b = framecheck.visible(s, d.readback()); d.close()\n"
+            "    framecheck.assert_planes_equal(a, b, 'per-level intra')\n"
+            "print('per-level ok')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, RB200_INTRA_LEVEL_LAUNCHES="1"),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "per-level ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("layout", [0, 1, 2, 3])
 def test_intra_levels_host_helper(layout):
     """rb200_intra_assign_levels (host code) reproduces the generator's wavefront levels from the items in decode order,
