@@ -190,7 +190,7 @@ def run_reference(args, s, wl):
             "cpu_baseline": {"value": mpx, "unit": "Mpixel/s", "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": mpx, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------ GPU arm
@@ -430,7 +430,7 @@ def run_gpu(args, s, wl):
                                     "sample": f"{n} frames of the workload, {cores} threads, reference C DSP (no asm), {cpu_model()}"}
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -450,7 +450,23 @@ TRAFFIC = {
 WARP_INST_PER_FRAME = {"4k10": 203.0e6, "4k10c5": 293.9e6}
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The one JSON line, on the process's original stdout."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # stdout carries exactly one JSON line: everything else that writes to fd 1 (NCCL prints its version banner there
+    # from C) is sent to stderr, the line itself goes to a duplicate of the original descriptor.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
