@@ -44,7 +44,7 @@ extern "C" {
 #endif
 
 /* ------------------------------------------------------------------ core */
-#define RB200_ABI_VERSION 1
+#define RB200_ABI_VERSION 2
 int rb200_abi_version(void);
 /* Bind the calling thread to a CUDA device (default: current device). */
 int rb200_init(int device);
@@ -65,6 +65,8 @@ int rb200_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
 int rb200_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
 int rb200_memset(void *dst, int value, size_t bytes, void *stream);
 int rb200_stream_sync(void *stream);
+int rb200_stream_create(void **stream);   /* non-blocking stream; hand it to rb200_frame_set_stream to chain frames */
+int rb200_stream_destroy(void *stream);
 
 /* Up to three device planes of one picture (Y, U, V); stride in bytes. */
 typedef struct Rb200Planes {
@@ -478,6 +480,9 @@ typedef struct Rb200FrameGeometry {
 int rb200_frame_create(Rb200Frame **out, const Rb200FrameHeader *hdr, size_t max_coefs, int max_itx_items,
                        int max_mc_items);
 int rb200_frame_destroy(Rb200Frame *f);
+/* A decoder reuses a context for the next picture of the same geometry: everything in the header but width, height,
+ * bpc, layout, sb128 and upscaled_width may change (levels, CDEF strengths, restoration types and unit sizes). */
+int rb200_frame_set_params(Rb200Frame *f, const Rb200FrameHeader *hdr);
 int rb200_frame_geometry(const Rb200Frame *f, Rb200FrameGeometry *g);
 /* Pinned host staging the front end writes into (the batch the north star describes). */
 void *rb200_frame_coef_buffer(Rb200Frame *f);                 /* coef[max_coefs] (i16 / i32) */

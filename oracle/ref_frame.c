@@ -38,20 +38,7 @@
 
 #include "../include/rav1d_b200.h"
 
-typedef struct RefFrame {
-    Dav1dContext *c;
-    Dav1dFrameContext *f;
-    Dav1dSequenceHeader seq;
-    Dav1dFrameHeader hdr;
-    Dav1dTaskContext *tc;   /* n_tc entries */
-    int n_tc, hbd, bdmax;
-    uint8_t *plane_mem;
-    size_t plane_bytes;
-    uint8_t *lvl_mem;
-    uint8_t start_of_tile_row[1024];
-    uint8_t *grain_mem;     /* output picture of dav1d_apply_grain */
-    Dav1dPicture grain_out;
-} RefFrame;
+#include "ref_frame.h"
 
 void ref_init(void);
 void dav1d_filter_sbrow_8bpc(Dav1dFrameContext *f, int sby);
@@ -472,6 +459,9 @@ static void do_warp_item(RefFrame *r, int tid, int i, void *arg) {
     for (int pl = 0; pl < n_planes; pl++) {
         const int ss_ver = pl && layout == DAV1D_PIXEL_LAYOUT_I420, ss_hor = pl && layout != DAV1D_PIXEL_LAYOUT_I444;
         const int32_t *mat = it->matrix;
+        /* chroma is warped only when the chroma block is at least 8x8 (imin(cbw4, cbh4) > 1, src/recon_tmpl.c:1755); smaller
+         * chroma blocks of a warped block are ordinary Rb200McItems */
+        if (pl && ((it->w >> ss_hor) < 8 || (it->h >> ss_ver) < 8)) continue;
         const int width = (rf->cur.p.w + ss_hor) >> ss_hor, height = (rf->cur.p.h + ss_ver) >> ss_ver;
         uint8_t *dst8 = (uint8_t *)f->cur.data[pl] + f->cur.stride[!!pl] * (it->y >> ss_ver) + (ptrdiff_t)(it->x >> ss_hor) * px;
         for (int y = 0; y < it->h >> ss_ver; y += 8) {

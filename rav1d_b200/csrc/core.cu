@@ -141,6 +141,14 @@ extern "C" int rb200_memset(void *dst, int value, size_t bytes, void *stream) {
     RB_CUDA(cudaMemsetAsync(dst, value, bytes, (cudaStream_t)stream)); return 0;
 }
 extern "C" int rb200_stream_sync(void *stream) { RB_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); return 0; }
+extern "C" int rb200_stream_create(void **stream) {
+    if (!stream) return set_error(-22, "stream_create: null argument");
+    cudaStream_t s;
+    RB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = (void *)s;
+    return 0;
+}
+extern "C" int rb200_stream_destroy(void *stream) { RB_CUDA(cudaStreamDestroy((cudaStream_t)stream)); return 0; }
 
 // ---- CUDA IPC: map another process's device allocation (halo exchange between ranks, one process per GPU)
 static_assert(sizeof(cudaIpcMemHandle_t) == RB200_IPC_HANDLE_BYTES, "ipc handle size");

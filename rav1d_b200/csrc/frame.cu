@@ -280,6 +280,18 @@ extern "C" int rb200_frame_destroy(Rb200Frame *f) {
     return 0;
 }
 
+// Per-frame parameters of a context that is reused for the next picture of the same geometry (a decoder keeps a pool of
+// contexts; only the filter parameters change from frame to frame).
+extern "C" int rb200_frame_set_params(Rb200Frame *f, const Rb200FrameHeader *hdr) {
+    if (!f || !hdr) return set_error(-22, "frame_set_params: null argument");
+    const Rb200FrameHeader &o = f->hdr;
+    if (hdr->width != o.width || hdr->height != o.height || hdr->bpc != o.bpc || hdr->layout != o.layout ||
+        hdr->sb128 != o.sb128 || hdr->upscaled_width != o.upscaled_width)
+        return set_error(-22, "frame_set_params: the geometry of a frame context cannot change");
+    f->hdr = *hdr;
+    return 0;
+}
+
 extern "C" int rb200_frame_geometry(const Rb200Frame *f, Rb200FrameGeometry *g) {
     if (!f || !g) return set_error(-22, "frame_geometry: null argument");
     *g = f->g;

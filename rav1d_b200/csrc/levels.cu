@@ -33,7 +33,9 @@ extern "C" int rb200_intra_assign_levels(Rb200IntraItem *items, int n, int frame
     for (int i = 0; i < n; i++) {
         Rb200IntraItem &it = items[i];
         const int p = it.plane;
-        if (p > 2 || it.tw4 < 1 || it.th4 < 1 || it.x4 + it.tw4 > pw[p] || it.y4 + it.th4 > ph[p])
+        // a transform block may hang over the right / bottom picture edge (the reference reconstructs into the
+        // padding of the 128-aligned allocation); only its origin has to lie inside
+        if (p > 2 || it.tw4 < 1 || it.th4 < 1 || it.x4 >= pw[p] || it.y4 >= ph[p])
             return set_error(-22, "intra_assign_levels: item %d outside the picture", i);
         const int x = it.x4, y = it.y4, tw = it.tw4, th = it.th4;
         int dep = -1;
@@ -53,8 +55,8 @@ extern "C" int rb200_intra_assign_levels(Rb200IntraItem *items, int n, int frame
         if (level > 0xffff || level >= max_levels) return set_error(-34, "intra_assign_levels: more than %d levels", max_levels);
         it.level = (uint16_t)level;
         n_levels = std::max(n_levels, level + 1);
-        for (int yy = y; yy < y + th; yy++)
-            for (int xx = x; xx < x + tw; xx++) lvl[p][(size_t)yy * pw[p] + xx] = level;
+        for (int yy = y; yy < std::min(y + th, ph[p]); yy++)
+            for (int xx = x; xx < std::min(x + tw, pw[p]); xx++) lvl[p][(size_t)yy * pw[p] + xx] = level;
     }
     // stable counting sort by level
     std::fill(level_counts, level_counts + n_levels, 0);

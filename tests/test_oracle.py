@@ -118,7 +118,7 @@ def test_library_exports_every_declared_symbol():
     from rav1d_b200 import lib
     missing = [n for n in sorted(declared) if not hasattr(lib.cdll, n)]
     assert not missing, missing
-    assert lib.abi_version() == 1
+    assert lib.abi_version() == 2
 
 
 def test_record_layouts_match_the_reference(ref):
