@@ -133,7 +133,11 @@ int alloc_pair(T **h, T **d, size_t n) {
     RB_CUDA(cudaMallocHost((void **)h, bytes));
     memset(*h, 0, bytes);
     RB_CUDA(cudaMalloc((void **)d, bytes));
+    // cudaMemset on device memory is asynchronous with respect to the host and runs on the legacy default stream, which
+    // the frames' non-blocking streams do not wait for: without the synchronize a late memset can land on top of the
+    // first batch uploaded into this buffer (seen as garbage frames when several processes share the GPU).
     RB_CUDA(cudaMemset(*d, 0, bytes));
+    RB_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
     return 0;
 }
 

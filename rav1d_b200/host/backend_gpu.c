@@ -9,6 +9,7 @@
  * behind the frames it predicts from without host synchronisation; the host only waits when a picture is output
  * (rb200_frame_readback into the pinned planes the allocator handed to the decoder).
  */
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -27,6 +28,7 @@ typedef struct PoolEntry { Rb200Frame *fr; Rb200FrameHeader hdr; struct PoolEntr
 
 static void *g_stream;
 static PoolEntry *g_pool;
+static pthread_mutex_t g_pool_lock = PTHREAD_MUTEX_INITIALIZER;   /* pictures are released from any thread */
 static char g_err[600];
 
 static int fail(const char *what) {
@@ -61,21 +63,28 @@ static void gpu_pic_free(void *pic) {
     if (!p) return;
     if (p->fr) {    /* back to the pool; the next user waits for the stream before it touches the staging */
         PoolEntry *const e = malloc(sizeof(*e));
-        if (e) { e->fr = p->fr; e->hdr = p->hdr; e->next = g_pool; g_pool = e; }
-        else rb200_frame_destroy(p->fr);
+        if (e) {
+            e->fr = p->fr; e->hdr = p->hdr;
+            pthread_mutex_lock(&g_pool_lock);
+            e->next = g_pool; g_pool = e;
+            pthread_mutex_unlock(&g_pool_lock);
+        } else rb200_frame_destroy(p->fr);
     }
     free(p);
 }
 
 static Rb200Frame *acquire(const Rb200FrameHeader *const h) {
+    pthread_mutex_lock(&g_pool_lock);
     for (PoolEntry **pe = &g_pool; *pe; pe = &(*pe)->next) {
         if (!same_geometry(&(*pe)->hdr, h)) continue;
         PoolEntry *const e = *pe;
         Rb200Frame *const fr = e->fr;
         *pe = e->next;
+        pthread_mutex_unlock(&g_pool_lock);
         free(e);
         return fr;
     }
+    pthread_mutex_unlock(&g_pool_lock);
     /* worst case of a frame: one residual per 4x4 of every plane, one prediction per 4x4 of every plane */
     const int bw = ((h->width + 7) >> 3) << 1, bh = ((h->height + 7) >> 3) << 1;
     const size_t sb128 = (size_t)((bw + 31) >> 5) * ((bh + 31) >> 5);

@@ -58,7 +58,7 @@ static RbJob *g_jobs;
 static int g_n_jobs;
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 static pthread_cond_t g_cond = PTHREAD_COND_INITIALIZER;
-static int g_unsupported;
+static int g_unsupported, g_keep_going;
 static char g_why[128];
 static long g_frames, g_items[8];
 
@@ -120,8 +120,11 @@ EXPORT int dav1d_open(Dav1dContext **const c_out, const Dav1dSettings *const s) 
     static int (*real)(Dav1dContext **, const Dav1dSettings *);
     if (!real) real = real_sym("dav1d_open");
     if (g_c) { fprintf(stderr, "rav1d_b200 host: one decoder instance per process\n"); return DAV1D_ERR(EINVAL); }
-    g_be = rb200_host_backend();
-    if (g_be->init()) die("backend init failed");
+    if (!g_be) {
+        g_be = rb200_host_backend();
+        if (g_be->init()) die("backend init failed");
+    }
+    g_unsupported = 0; g_why[0] = 0;
     Dav1dSettings s2 = *s;
     /* the batch replaces pass 2 of the two-pass frame threading: at least two frame contexts */
     if (s2.n_threads < 2) s2.n_threads = 2;
@@ -148,12 +151,19 @@ EXPORT void dav1d_close(Dav1dContext **const c_out) {
     if (getenv("RB200_HOST_STATS"))
         fprintf(stderr, "rav1d_b200 host [%s]: %ld frames; items: mc %ld scaled %ld comp %ld warp %ld obmc %ld itx %ld intra %ld lf blocks %ld\n",
                 g_be->name, g_frames, g_items[0], g_items[1], g_items[2], g_items[3], g_items[4], g_items[5], g_items[6], g_items[7]);
-    if (g_unsupported) {
+    if (g_unsupported && !g_keep_going) {
         /* the run cannot claim parity: some block needed a record the batch formats do not have */
         fprintf(stderr, "rav1d_b200 host: UNSUPPORTED: %s\n", g_why);
         fflush(NULL);
         _exit(3);
     }
+}
+
+/* For a host that decodes several streams in one process (conformance_main.c): ask instead of exiting. */
+int rb200_host_unsupported(const char **const why) {
+    g_keep_going = 1;
+    if (why) *why = g_why;
+    return g_unsupported;
 }
 
 /* ------------------------------------------------------------------------------------------ frame set-up */
@@ -278,6 +288,40 @@ static int has_grain(const Dav1dFrameHeader *const h) {
            (fg->clip_to_restricted_range && fg->chroma_scaling_from_luma);
 }
 
+/* Debug aid (RB200_HOST_DUMP="plane,x,y"): every record of the frame that covers that pixel. */
+static void dump_records(const Dav1dFrameContext *const f, const RbHostBatch *const B, const RbHostFinal *const fin) {
+    int pl, x, y;
+    if (sscanf(getenv("RB200_HOST_DUMP"), "%d,%d,%d", &pl, &x, &y) != 3) return;
+    const int ss_hor = pl && f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444, ss_ver = pl && f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420;
+    fprintf(stderr, "== frame %ld (type %d, show %d, offset %d, %dx%d) plane %d pixel %d,%d\n", g_frames, f->frame_hdr->frame_type,
+            f->frame_hdr->show_frame, f->frame_hdr->frame_offset, f->cur.p.w, f->cur.p.h, pl, x, y);
+#define IN(x0, y0, w, h) (x >= (x0) && x < (x0) + (w) && y >= (y0) && y < (y0) + (h))
+    for (int i = 0; i < B->mc.n; i++) { const Rb200McItem *it = &B->mc.v[i];
+        if (it->plane == pl && IN(it->dst_x, it->dst_y, it->w, it->h))
+            fprintf(stderr, "  mc[%d] dst %d,%d src %d,%d %dx%d ref %d mx %d my %d f2d %d\n", i, it->dst_x, it->dst_y, it->src_x, it->src_y, it->w, it->h, it->ref, it->mx, it->my, it->filter2d); }
+    for (int i = 0; i < B->scaled.n; i++) { const Rb200McScaledItem *it = &B->scaled.v[i];
+        if (it->plane == pl && IN(it->dst_x, it->dst_y, it->w, it->h))
+            fprintf(stderr, "  scaled[%d] dst %d,%d %dx%d ref %d pos %d,%d step %d,%d f2d %d\n", i, it->dst_x, it->dst_y, it->w, it->h, it->ref, it->pos_x, it->pos_y, it->step_x, it->step_y, it->filter2d); }
+    for (int i = 0; i < B->comp.n; i++) { const Rb200CompItem *it = &B->comp.v[i];
+        if (IN(it->x >> ss_hor, it->y >> ss_ver, it->w >> ss_hor, it->h >> ss_ver))
+            fprintf(stderr, "  comp[%d] %d,%d %dx%d refs %d,%d mv (%d,%d) (%d,%d) f2d %d type %d w %d sign %d wedge %d\n", i, it->x, it->y, it->w, it->h, it->ref[0], it->ref[1],
+                    it->mv[0][0], it->mv[0][1], it->mv[1][0], it->mv[1][1], it->filter2d, it->comp_type, it->jnt_weight, it->mask_sign, it->wedge_idx); }
+    for (int i = 0; i < B->warp.n; i++) { const Rb200WarpItem *it = &B->warp.v[i];
+        if (IN(it->x >> ss_hor, it->y >> ss_ver, it->w >> ss_hor, it->h >> ss_ver))
+            fprintf(stderr, "  warp[%d] %d,%d %dx%d ref %d\n", i, it->x, it->y, it->w, it->h, it->ref); }
+    for (int k = 0; k < 2; k++) for (int i = 0; i < (k ? B->obmc_left.n : B->obmc_above.n); i++) { const Rb200McItem *it = k ? &B->obmc_left.v[i] : &B->obmc_above.v[i];
+        if (it->plane == pl && IN(it->dst_x, it->dst_y, it->w, it->h))
+            fprintf(stderr, "  obmc_%s[%d] dst %d,%d src %d,%d %dx%d ref %d mx %d my %d f2d %d\n", k ? "left" : "above", i, it->dst_x, it->dst_y, it->src_x, it->src_y, it->w, it->h, it->ref, it->mx, it->my, it->filter2d); }
+    static const uint8_t txw[19] = {4,8,16,32,64,4,8,8,16,16,32,32,64,4,16,8,32,16,64}, txh[19] = {4,8,16,32,64,8,4,16,8,32,16,64,32,16,4,32,8,64,16};
+    for (int i = 0; i < fin->n_itx; i++) { const Rb200ItxItem *it = &fin->itx[i];
+        if (it->plane == pl && IN(it->x, it->y, txw[it->tx], txh[it->tx]))
+            fprintf(stderr, "  itx[%d%s] %d,%d tx %d txtp %d eob %d cf_off %u\n", i, i >= fin->n_itx_inter ? " intra" : "", it->x, it->y, it->tx, it->txtp, it->eob, it->cf_off); }
+    for (int i = 0; i < fin->n_intra; i++) { const Rb200IntraItem *it = &fin->intra[i];
+        if (it->plane == pl && IN(it->x4 * 4, it->y4 * 4, it->tw4 * 4, it->th4 * 4))
+            fprintf(stderr, "  intra[%d] %d,%d %dx%d mode %d angle %d flags 0x%x level %d itx %d ends %d,%d\n", i, it->x4 * 4, it->y4 * 4, it->tw4 * 4, it->th4 * 4, it->mode, it->angle, it->flags, it->level, fin->intra_itx[i], it->w4_end, it->h4_end); }
+#undef IN
+}
+
 static void hand_over(Dav1dFrameContext *const f, RbJob *const j, RbPic *const rp) {
     const Dav1dContext *const c = f->c;
     const Dav1dFrameHeader *const h = f->frame_hdr;
@@ -341,6 +385,7 @@ static void hand_over(Dav1dFrameContext *const f, RbJob *const j, RbPic *const r
 
     RbHostFinal fin;
     if (rb_batch_finalize(B, &fin, f->bw, f->bh, ss_hor, ss_ver)) { fprintf(stderr, "rav1d_b200 host: %s\n", B->why); exit(4); }
+    if (getenv("RB200_HOST_DUMP")) dump_records(f, B, &fin);
     if (g_be->frame_stage(&d, B, &fin)) die("frame_stage failed");
     rb_final_free(&fin);
     if (g_be->frame_submit(rp->backend)) die("frame_submit failed");

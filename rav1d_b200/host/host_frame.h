@@ -17,4 +17,8 @@ void rb_host_block_end(const struct Dav1dFrameContext *f);
 void rb_host_push_palette(RbHostBatch *b, int x4, int y4, int w4_end, int h4_end, int pl, int bw4, int bh4,
                           const void *pal, int pal_bytes, const uint8_t *idx);
 
+/* Whether the last decoded stream needed a record the batch formats do not have (and what).  Calling it also turns off
+ * the default behaviour of leaving the process with status 3 in that case. */
+int rb200_host_unsupported(const char **why);
+
 #endif
