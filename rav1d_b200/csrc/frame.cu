@@ -202,9 +202,12 @@ extern "C" int rb200_frame_create(Rb200Frame **out, const Rb200FrameHeader *hdr,
     for (int i = 0; i < 3 && !r; i++) r = alloc_planes(f, i);
     for (int i = 0; i < 3 && !r && f->sr; i++) r = alloc_sr_planes(f, i);
     if (!r) {
-        RB_CUDA(cudaMallocHost(&f->h_coef, (max_coefs ? max_coefs : 1) * f->cs));
-        memset(f->h_coef, 0, (max_coefs ? max_coefs : 1) * f->cs);
-        RB_CUDA(cudaMalloc(&f->d_coef, (max_coefs ? max_coefs : 1) * f->cs));
+        e = cudaMallocHost(&f->h_coef, (max_coefs ? max_coefs : 1) * f->cs);
+        if (e == cudaSuccess) {
+            memset(f->h_coef, 0, (max_coefs ? max_coefs : 1) * f->cs);
+            e = cudaMalloc(&f->d_coef, (max_coefs ? max_coefs : 1) * f->cs);
+        }
+        if (e != cudaSuccess) r = cuda_fail(e, "coefficient staging", __FILE__, __LINE__);
     }
     if (!r) r = alloc_pair(&f->h_itx, &f->d_itx, (size_t)max_itx);
     if (!r) r = alloc_pair(&f->h_mc, &f->d_mc, (size_t)max_mc);
@@ -639,6 +642,7 @@ extern "C" int rb200_frame_reserve_intra_items(Rb200Frame *f, int max_items, int
     }
     if (max_levels > f->max_levels) {
         free(f->intra_counts); free(f->intra_itx_counts);
+        f->intra_counts = nullptr; f->intra_itx_counts = nullptr; f->max_levels = 0; f->n_levels = 0;
         RB_CUDA(cudaStreamSynchronize(f->stream));
         if (f->h_level_off) cudaFreeHost(f->h_level_off);
         if (f->d_level_off) cudaFree(f->d_level_off);

@@ -1,96 +1,98 @@
 // Deblocking loop filter for sm_100a.
 //
-// Replaces Rav1dLoopFilterDSPContext.loop_filter_sb[2][2] (src/loopfilter.rs:20-34;
-// core `loop_filter` src/loopfilter.rs:397 == src/loopfilter_tmpl.c:36-161, sb
-// drivers src/loopfilter_tmpl.c:163-240) and, at frame level, the per-sbrow drivers
-// rav1d_loopfilter_sbrow_cols / _rows (src/lf_apply.rs:597,763 ==
-// src/lf_apply_tmpl.c:327-466).
+// Replaces Rav1dLoopFilterDSPContext.loop_filter_sb[2][2] (src/loopfilter.rs:20-34; core `loop_filter`
+// src/loopfilter.rs:397, sb drivers :500-1079) and, at frame level, the per-sbrow drivers
+// rav1d_loopfilter_sbrow_cols / _rows (src/lf_apply.rs:597,763).
 //
-// Mapping: one thread filters one line (one row of a column edge, one column of
-// a row edge) of one 4-pixel edge unit.  Within a pass every edge is independent
-// of every other (read / write sets never overlap because the filter length is
-// bounded by the transform size on both sides), so a whole plane is
-// one launch per direction: all column edges first, then all row edges, which
-// is the order the reference's sbrow loop produces.  Threads of a warp are laid
-// along the edge-normal for column edges and along the edge for row edges so
-// that global accesses stay contiguous per row.
+// The edge filter is written from the AV1 specification (7.14.6), not from the reference's expanded sums:
+//   * the filter mask and the flatness masks are "largest difference <= limit" tests (one max chain each);
+//   * the narrow filter (7.14.6.3) is the spec's single formula with the high-edge-variance term selected;
+//   * the wide filters (7.14.6.4) are a sliding window -- out[i] = Round2(W[i] + centre taps, log2) with
+//     W[i] = sum_{j=-n..n} x[clip(i + j)], and W[i + 1] = W[i] + x[clip(i + n + 1)] - x[clip(i - n)] -- two adds per
+//     output instead of one add per tap (13 / 7 / 5 taps).
+// Mapping at frame level: within a pass every edge is independent of every other (the filter length is bounded by the
+// transform size on both sides), so a pass is one launch over all planes: all column edges, then all row
+// edges.  A CTA takes a run of candidate 4-pixel units, finds the ones that carry an edge (mask word bit + non-zero
+// level), COMPACTS them into a shared-memory list (ballot + prefix) and then filters list entries with full warps --
+// one thread per unit (4 lines), the lines' pixels moved as aligned 4-pixel words.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace rb200 {
 
-// Filter one line across an edge.  p points at q0; `sb` = element stride across the edge.
-// E, I, H already scaled by << (bpc - 8).   src/loopfilter_tmpl.c:48-160
-template <typename BD>
-__device__ __forceinline__ void lf_line(typename BD::pixel *p, const int64_t sb, int E, int I, int H, const int wd,
-                                        const int bdmin8, const int bdmax) {
-    using pixel = typename BD::pixel;
-    auto A = [](int v) { return v < 0 ? -v : v; };
-    const int F = 1 << bdmin8;
-    int p6, p5, p4, p3, p2, q2, q3, q4, q5, q6;
-    const int p1 = p[sb * -2], p0 = p[sb * -1], q0 = p[0], q1 = p[sb];
-    bool fm = A(p1 - p0) <= I && A(q1 - q0) <= I && A(p0 - q0) * 2 + (A(p1 - q1) >> 1) <= E;
-    if (wd > 4) {
-        p2 = p[sb * -3]; q2 = p[sb * 2];
-        fm = fm && A(p2 - p1) <= I && A(q2 - q1) <= I;
-        if (wd > 6) {
-            p3 = p[sb * -4]; q3 = p[sb * 3];
-            fm = fm && A(p3 - p2) <= I && A(q3 - q2) <= I;
-        }
-    }
-    if (!fm) return;
-    bool flat8out = false, flat8in = false;
-    if (wd >= 16) {
-        p6 = p[sb * -7]; p5 = p[sb * -6]; p4 = p[sb * -5];
-        q4 = p[sb * 4]; q5 = p[sb * 5]; q6 = p[sb * 6];
-        flat8out = A(p6 - p0) <= F && A(p5 - p0) <= F && A(p4 - p0) <= F && A(q4 - q0) <= F && A(q5 - q0) <= F &&
-                   A(q6 - q0) <= F;
-    }
-    if (wd >= 6) flat8in = A(p2 - p0) <= F && A(p1 - p0) <= F && A(q1 - q0) <= F && A(q2 - q0) <= F;
-    if (wd >= 8) flat8in = flat8in && A(p3 - p0) <= F && A(q3 - q0) <= F;
+__device__ __forceinline__ int lf_absdiff(int a, int b) { return __sad(a, b, 0); }
 
-    if (wd >= 16 && flat8out && flat8in) {
-        p[sb * -6] = (pixel)((p6 + p6 + p6 + p6 + p6 + p6 * 2 + p5 * 2 + p4 * 2 + p3 + p2 + p1 + p0 + q0 + 8) >> 4);
-        p[sb * -5] = (pixel)((p6 + p6 + p6 + p6 + p6 + p5 * 2 + p4 * 2 + p3 * 2 + p2 + p1 + p0 + q0 + q1 + 8) >> 4);
-        p[sb * -4] = (pixel)((p6 + p6 + p6 + p6 + p5 + p4 * 2 + p3 * 2 + p2 * 2 + p1 + p0 + q0 + q1 + q2 + 8) >> 4);
-        p[sb * -3] = (pixel)((p6 + p6 + p6 + p5 + p4 + p3 * 2 + p2 * 2 + p1 * 2 + p0 + q0 + q1 + q2 + q3 + 8) >> 4);
-        p[sb * -2] = (pixel)((p6 + p6 + p5 + p4 + p3 + p2 * 2 + p1 * 2 + p0 * 2 + q0 + q1 + q2 + q3 + q4 + 8) >> 4);
-        p[sb * -1] = (pixel)((p6 + p5 + p4 + p3 + p2 + p1 * 2 + p0 * 2 + q0 * 2 + q1 + q2 + q3 + q4 + q5 + 8) >> 4);
-        p[0]       = (pixel)((p5 + p4 + p3 + p2 + p1 + p0 * 2 + q0 * 2 + q1 * 2 + q2 + q3 + q4 + q5 + q6 + 8) >> 4);
-        p[sb * 1]  = (pixel)((p4 + p3 + p2 + p1 + p0 + q0 * 2 + q1 * 2 + q2 * 2 + q3 + q4 + q5 + q6 + q6 + 8) >> 4);
-        p[sb * 2]  = (pixel)((p3 + p2 + p1 + p0 + q0 + q1 * 2 + q2 * 2 + q3 * 2 + q4 + q5 + q6 + q6 + q6 + 8) >> 4);
-        p[sb * 3]  = (pixel)((p2 + p1 + p0 + q0 + q1 + q2 * 2 + q3 * 2 + q4 * 2 + q5 + q6 + q6 + q6 + q6 + 8) >> 4);
-        p[sb * 4]  = (pixel)((p1 + p0 + q0 + q1 + q2 + q3 * 2 + q4 * 2 + q5 * 2 + q6 + q6 + q6 + q6 + q6 + 8) >> 4);
-        p[sb * 5]  = (pixel)((p0 + q0 + q1 + q2 + q3 + q4 * 2 + q5 * 2 + q6 * 2 + q6 + q6 + q6 + q6 + q6 + 8) >> 4);
-    } else if (wd >= 8 && flat8in) {
-        p[sb * -3] = (pixel)((p3 + p3 + p3 + 2 * p2 + p1 + p0 + q0 + 4) >> 3);
-        p[sb * -2] = (pixel)((p3 + p3 + p2 + 2 * p1 + p0 + q0 + q1 + 4) >> 3);
-        p[sb * -1] = (pixel)((p3 + p2 + p1 + 2 * p0 + q0 + q1 + q2 + 4) >> 3);
-        p[0]       = (pixel)((p2 + p1 + p0 + 2 * q0 + q1 + q2 + q3 + 4) >> 3);
-        p[sb * 1]  = (pixel)((p1 + p0 + q0 + 2 * q1 + q2 + q3 + q3 + 4) >> 3);
-        p[sb * 2]  = (pixel)((p0 + q0 + q1 + 2 * q2 + q3 + q3 + q3 + 4) >> 3);
-    } else if (wd == 6 && flat8in) {
-        p[sb * -2] = (pixel)((p2 + 2 * p2 + 2 * p1 + 2 * p0 + q0 + 4) >> 3);
-        p[sb * -1] = (pixel)((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
-        p[0]       = (pixel)((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
-        p[sb * 1]  = (pixel)((p0 + 2 * q0 + 2 * q1 + 2 * q2 + q2 + 4) >> 3);
-    } else {
-        const bool hev = A(p1 - p0) > H || A(q1 - q0) > H;
-        const int lo = -128 * (1 << bdmin8), hi = 128 * (1 << bdmin8) - 1;
-        if (hev) {
-            int f = iclip(p1 - q1, lo, hi);
-            f = iclip(3 * (q0 - p0) + f, lo, hi);
-            const int f1 = imin(f + 4, hi) >> 3, f2 = imin(f + 3, hi) >> 3;
-            p[sb * -1] = (pixel)iclip(p0 + f2, 0, bdmax);
-            p[0] = (pixel)iclip(q0 - f1, 0, bdmax);
-        } else {
-            int f = iclip(3 * (q0 - p0), lo, hi);
-            const int f1 = imin(f + 4, hi) >> 3, f2 = imin(f + 3, hi) >> 3;
-            p[sb * -1] = (pixel)iclip(p0 + f2, 0, bdmax);
-            p[0] = (pixel)iclip(q0 - f1, 0, bdmax);
-            f = (f1 + 1) >> 1;
-            p[sb * -2] = (pixel)iclip(p1 + f, 0, bdmax);
-            p[sb * 1] = (pixel)iclip(q1 - f, 0, bdmax);
+// Wide filter of 2 * N outputs around the edge: x[8 + i], i = -N .. N - 1; samples are clipped to [-(N + 1), N].
+// N2 = 1: the taps at i - 1, i, i + 1 count twice (13-tap luma, 5-tap chroma); N2 = 0: only the centre tap (7-tap luma).
+template <int N, int N2, int LOG2>
+__device__ __forceinline__ void lf_smooth(int (&x)[16]) {
+    constexpr int LO = 8 - (N + 1), HI = 8 + N;
+    int out[2 * N];
+    int win = 0;
+#pragma unroll
+    for (int j = -N; j <= N; j++) { const int k = 8 - N + j; win += x[k < LO ? LO : (k > HI ? HI : k)]; }
+#pragma unroll
+    for (int i = -N; i < N; i++) {
+        const int c = 8 + i;
+        int centre = x[c];
+        if (N2) centre += x[c - 1 < LO ? LO : c - 1] + x[c + 1 > HI ? HI : c + 1];
+        out[i + N] = (win + centre + (1 << (LOG2 - 1))) >> LOG2;
+        const int in = c + N + 1, gone = c - N;
+        win += x[in > HI ? HI : in] - x[gone < LO ? LO : gone];
+    }
+#pragma unroll
+    for (int i = 0; i < 2 * N; i++) x[8 - N + i] = out[i];
+}
+
+// One line across an edge, in registers: x[0..15] = p7 .. p0 | q0 .. q7 (x[7] = p0, x[8] = q0); only the samples the
+// filter width needs have to be valid.  E, I, H are already scaled by << (bitdepth - 8).  Returns how many samples on
+// each side may have changed (0, 1, 2, 3 or 6).  WD: 4 (both planes), 6 (chroma), 8 / 16 (luma).
+template <int WD>
+__device__ __forceinline__ int lf_edge(int (&x)[16], const int E, const int I, const int H, const int bdmin8, const int bdmax) {
+    const int p0 = x[7], q0 = x[8], p1 = x[6], q1 = x[9];
+    // filter mask (7.14.6.2): no step between neighbouring samples larger than I, and the step across the edge within E
+    const int step01 = max(lf_absdiff(p1, p0), lf_absdiff(q1, q0));
+    int step = step01;
+    if (WD > 4) step = max(step, max(lf_absdiff(x[5], p1), lf_absdiff(x[10], q1)));
+    if (WD > 6) step = max(step, max(lf_absdiff(x[4], x[5]), lf_absdiff(x[11], x[10])));
+    if (step > I || lf_absdiff(p0, q0) * 2 + (lf_absdiff(p1, q1) >> 1) > E) return 0;
+    // flatness: every sample of a side within 1 << (bitdepth - 8) of the sample next to the edge
+    if (WD >= 6) {
+        const int F = 1 << bdmin8;
+        int dev = max(step01, max(lf_absdiff(x[5], p0), lf_absdiff(x[10], q0)));
+        if (WD >= 8) dev = max(dev, max(lf_absdiff(x[4], p0), lf_absdiff(x[11], q0)));
+        if (dev <= F) {
+            if (WD == 16) {
+                int far = max(max(lf_absdiff(x[3], p0), lf_absdiff(x[2], p0)), lf_absdiff(x[1], p0));
+                far = max(far, max(max(lf_absdiff(x[12], q0), lf_absdiff(x[13], q0)), lf_absdiff(x[14], q0)));
+                if (far <= F) { lf_smooth<6, 1, 4>(x); return 6; }
+            }
+            if (WD >= 8) { lf_smooth<3, 0, 3>(x); return 3; }
+            lf_smooth<2, 1, 3>(x);
+            return 2;
         }
+    }
+    // narrow filter (7.14.6.3)
+    const int lo = -(128 << bdmin8), hi = (128 << bdmin8) - 1;
+    const bool hev = step01 > H;
+    int f = hev ? iclip(p1 - q1, lo, hi) : 0;
+    f = iclip(f + 3 * (q0 - p0), lo, hi);
+    const int f1 = imin(f + 4, hi) >> 3, f2 = imin(f + 3, hi) >> 3;
+    x[8] = iclip(q0 - f1, 0, bdmax);
+    x[7] = iclip(p0 + f2, 0, bdmax);
+    if (hev) return 1;
+    const int f3 = (f1 + 1) >> 1;
+    x[9] = iclip(q1 - f3, 0, bdmax);
+    x[6] = iclip(p1 + f3, 0, bdmax);
+    return 2;
+}
+
+__device__ __forceinline__ int lf_edge_wd(int wd, int (&x)[16], int E, int I, int H, int bdmin8, int bdmax) {
+    switch (wd) {
+    case 16: return lf_edge<16>(x, E, I, H, bdmin8, bdmax);
+    case 8: return lf_edge<8>(x, E, I, H, bdmin8, bdmax);
+    case 6: return lf_edge<6>(x, E, I, H, bdmin8, bdmax);
+    default: return lf_edge<4>(x, E, I, H, bdmin8, bdmax);
     }
 }
 
@@ -106,7 +108,7 @@ struct LfGeom {
 // Filter width index of the edge unit (x4, y4) from the Av1Filter masks, or -1.
 // Luma:   filter_y[dir][a][idx][half] bit b;  chroma: filter_uv[dir][a][idx][half] bit b, where for
 // column edges a = x4 in sb128, bits run over y4; for row edges a = y4 in sb128, bits over x4
-// (src/lf_apply_tmpl.c:176-325: hmask/vmask assembly).
+// (the hmask / vmask assembly of src/lf_apply.rs).
 __device__ __forceinline__ int lf_mask_idx(const Rb200Av1Filter *__restrict__ masks, const LfGeom &g, int dir, int x4,
                                            int y4) {
     const int shx = 5 - g.ss_hor, shy = 5 - g.ss_ver;
@@ -127,80 +129,6 @@ __device__ __forceinline__ int lf_mask_idx(const Rb200Av1Filter *__restrict__ ma
     return -1;
 }
 
-// Register form of the edge filter for one line: P[i] = p_i, Q[i] = q_i (i = 0 next to the edge).
-// Returns how many samples on each side may have changed (0, 1, 2, 3 or 6).  Same arithmetic as
-// lf_line / src/loopfilter_tmpl.c:48-160.
-__device__ __forceinline__ int lf_line_regs(int *P, int *Q, int E, int I, int H, const int wd, const int bdmin8,
-                                            const int bdmax) {
-    auto A = [](int v) { return v < 0 ? -v : v; };
-    const int F = 1 << bdmin8;
-    const int p0 = P[0], p1 = P[1], q0 = Q[0], q1 = Q[1];
-    bool fm = A(p1 - p0) <= I && A(q1 - q0) <= I && A(p0 - q0) * 2 + (A(p1 - q1) >> 1) <= E;
-    if (wd > 4) {
-        fm = fm && A(P[2] - p1) <= I && A(Q[2] - q1) <= I;
-        if (wd > 6) fm = fm && A(P[3] - P[2]) <= I && A(Q[3] - Q[2]) <= I;
-    }
-    if (!fm) return 0;
-    bool flat8out = false, flat8in = false;
-    if (wd >= 16)
-        flat8out = A(P[6] - p0) <= F && A(P[5] - p0) <= F && A(P[4] - p0) <= F && A(Q[4] - q0) <= F && A(Q[5] - q0) <= F &&
-                   A(Q[6] - q0) <= F;
-    if (wd >= 6) flat8in = A(P[2] - p0) <= F && A(p1 - p0) <= F && A(q1 - q0) <= F && A(Q[2] - q0) <= F;
-    if (wd >= 8) flat8in = flat8in && A(P[3] - p0) <= F && A(Q[3] - q0) <= F;
-    if (wd >= 16 && flat8out && flat8in) {
-        const int p6 = P[6], p5 = P[5], p4 = P[4], p3 = P[3], p2 = P[2], q2 = Q[2], q3 = Q[3], q4 = Q[4], q5 = Q[5], q6 = Q[6];
-        P[5] = (p6 + p6 + p6 + p6 + p6 + p6 * 2 + p5 * 2 + p4 * 2 + p3 + p2 + p1 + p0 + q0 + 8) >> 4;
-        P[4] = (p6 + p6 + p6 + p6 + p6 + p5 * 2 + p4 * 2 + p3 * 2 + p2 + p1 + p0 + q0 + q1 + 8) >> 4;
-        P[3] = (p6 + p6 + p6 + p6 + p5 + p4 * 2 + p3 * 2 + p2 * 2 + p1 + p0 + q0 + q1 + q2 + 8) >> 4;
-        P[2] = (p6 + p6 + p6 + p5 + p4 + p3 * 2 + p2 * 2 + p1 * 2 + p0 + q0 + q1 + q2 + q3 + 8) >> 4;
-        P[1] = (p6 + p6 + p5 + p4 + p3 + p2 * 2 + p1 * 2 + p0 * 2 + q0 + q1 + q2 + q3 + q4 + 8) >> 4;
-        P[0] = (p6 + p5 + p4 + p3 + p2 + p1 * 2 + p0 * 2 + q0 * 2 + q1 + q2 + q3 + q4 + q5 + 8) >> 4;
-        Q[0] = (p5 + p4 + p3 + p2 + p1 + p0 * 2 + q0 * 2 + q1 * 2 + q2 + q3 + q4 + q5 + q6 + 8) >> 4;
-        Q[1] = (p4 + p3 + p2 + p1 + p0 + q0 * 2 + q1 * 2 + q2 * 2 + q3 + q4 + q5 + q6 + q6 + 8) >> 4;
-        Q[2] = (p3 + p2 + p1 + p0 + q0 + q1 * 2 + q2 * 2 + q3 * 2 + q4 + q5 + q6 + q6 + q6 + 8) >> 4;
-        Q[3] = (p2 + p1 + p0 + q0 + q1 + q2 * 2 + q3 * 2 + q4 * 2 + q5 + q6 + q6 + q6 + q6 + 8) >> 4;
-        Q[4] = (p1 + p0 + q0 + q1 + q2 + q3 * 2 + q4 * 2 + q5 * 2 + q6 + q6 + q6 + q6 + q6 + 8) >> 4;
-        Q[5] = (p0 + q0 + q1 + q2 + q3 + q4 * 2 + q5 * 2 + q6 * 2 + q6 + q6 + q6 + q6 + q6 + 8) >> 4;
-        return 6;
-    }
-    if (wd >= 8 && flat8in) {
-        const int p3 = P[3], p2 = P[2], q2 = Q[2], q3 = Q[3];
-        P[2] = (p3 + p3 + p3 + 2 * p2 + p1 + p0 + q0 + 4) >> 3;
-        P[1] = (p3 + p3 + p2 + 2 * p1 + p0 + q0 + q1 + 4) >> 3;
-        P[0] = (p3 + p2 + p1 + 2 * p0 + q0 + q1 + q2 + 4) >> 3;
-        Q[0] = (p2 + p1 + p0 + 2 * q0 + q1 + q2 + q3 + 4) >> 3;
-        Q[1] = (p1 + p0 + q0 + 2 * q1 + q2 + q3 + q3 + 4) >> 3;
-        Q[2] = (p0 + q0 + q1 + 2 * q2 + q3 + q3 + q3 + 4) >> 3;
-        return 3;
-    }
-    if (wd == 6 && flat8in) {
-        const int p2 = P[2], q2 = Q[2];
-        P[1] = (p2 + 2 * p2 + 2 * p1 + 2 * p0 + q0 + 4) >> 3;
-        P[0] = (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3;
-        Q[0] = (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3;
-        Q[1] = (p0 + 2 * q0 + 2 * q1 + 2 * q2 + q2 + 4) >> 3;
-        return 2;
-    }
-    const bool hev = A(p1 - p0) > H || A(q1 - q0) > H;
-    const int lo = -128 * (1 << bdmin8), hi = 128 * (1 << bdmin8) - 1;
-    if (hev) {
-        int f = iclip(p1 - q1, lo, hi);
-        f = iclip(3 * (q0 - p0) + f, lo, hi);
-        const int f1 = imin(f + 4, hi) >> 3, f2 = imin(f + 3, hi) >> 3;
-        P[0] = iclip(p0 + f2, 0, bdmax);
-        Q[0] = iclip(q0 - f1, 0, bdmax);
-        return 1;
-    }
-    int f = iclip(3 * (q0 - p0), lo, hi);
-    const int f1 = imin(f + 4, hi) >> 3, f2 = imin(f + 3, hi) >> 3;
-    P[0] = iclip(p0 + f2, 0, bdmax);
-    Q[0] = iclip(q0 - f1, 0, bdmax);
-    f = (f1 + 1) >> 1;
-    P[1] = iclip(p1 + f, 0, bdmax);
-    Q[1] = iclip(q1 - f, 0, bdmax);
-    return 2;
-}
-
 struct LfPlaneSet {
     uint8_t *plane[3];
     int64_t stride[3];
@@ -210,107 +138,144 @@ struct LfPlaneSet {
     int n_planes;
 };
 
-// One thread per 4-pixel edge unit, 4 lines each, all planes of a pass in one launch.
-// DIR 0: column edges -- per line the thread loads the 4/8/16 pixels straddling the edge with
-// aligned vector loads and writes back only what the filter may modify.
-// DIR 1: row edges -- the thread owns 4 adjacent columns; every row of the stencil is one
-// aligned 4-pixel load, coalesced across the warp.
+constexpr int LF_THREADS = 128, LF_CAND = 4;   // candidates examined per thread before the compacted list is filtered
+
+// DIR 0: column edges -- per line the thread loads the 4 / 8 / 16 pixels straddling the edge as aligned 4-pixel words and
+// writes back only the words the filter may have modified.
+// DIR 1: row edges -- the thread owns 4 adjacent columns; every stencil row is one aligned 4-pixel word.
 template <typename BD, int DIR>
-__global__ void __launch_bounds__(128, 8)
+__global__ void __launch_bounds__(LF_THREADS, 8)
 deblock_units_kernel(LfPlaneSet S, const Rb200Av1Filter *__restrict__ masks, const uint8_t (*__restrict__ lvl)[4],
                      const Rb200Av1FilterLUT *__restrict__ lut, int bdmax) {
     using pixel = typename BD::pixel;
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= S.unit_start[S.n_planes]) return;
-    const int pi = (S.n_planes > 1 && gid >= S.unit_start[1]) ? ((S.n_planes > 2 && gid >= S.unit_start[2]) ? 2 : 1) : 0;
-    const LfGeom g = pi == 0 ? S.g[0] : (pi == 1 ? S.g[1] : S.g[2]);
-    uint8_t *plane = pi == 0 ? S.plane[0] : (pi == 1 ? S.plane[1] : S.plane[2]);
-    const int64_t stride = pi == 0 ? S.stride[0] : (pi == 1 ? S.stride[1] : S.stride[2]);
-    const int u = gid - (pi == 0 ? 0 : (pi == 1 ? S.unit_start[1] : S.unit_start[2]));
-    const int yl = u / g.w4, x4 = u - yl * g.w4;
-    const int y4 = yl + (pi == 0 ? S.y4_first[0] : (pi == 1 ? S.y4_first[1] : S.y4_first[2]));
-    if (DIR == 0 ? x4 == 0 : y4 == 0) return;  // have_left / have_top
-    const int64_t ps = stride / (int64_t)sizeof(pixel);
-    pixel *base = (pixel *)plane + (int64_t)(y4 * 4) * ps + x4 * 4;   // q0 of line 0
-    // Row-edge pass: the 8 rows every filter width needs are requested before the mask / level lookups
-    // they would otherwise wait behind (the pass is latency-bound; units without an edge waste the loads,
-    // which L2 serves).
-    constexpr int WPR = BD::hbd ? 2 : 1;            // 32-bit words per 4-pixel row
-    unsigned rows[16][WPR];
-    if (DIR == 1) {
-#pragma unroll
-        for (int r = 4; r < 12; r++) {
-            const pixel *p = base + (int64_t)(r - 8) * ps;
-            if (BD::hbd) { const uint2 q = *(const uint2 *)p; rows[r][0] = q.x; rows[r][WPR - 1] = q.y; }
-            else rows[r][0] = *(const unsigned *)p;
-        }
-    }
-    const int idx = lf_mask_idx(masks, g, DIR, x4, y4);
-    if (idx < 0) return;
-    const uint8_t(*l)[4] = lvl + (int64_t)y4 * g.b4_stride + x4;
-    int L = l[0][g.lvl_idx];
-    if (!L) L = DIR == 0 ? l[-1][g.lvl_idx] : l[-(int64_t)g.b4_stride][g.lvl_idx];
-    if (!L) return;
-    const int bdmin8 = BD::hbd ? bpc_from_max(bdmax) - 8 : 0;
-    const int H = (L >> 4) << bdmin8, E = (int)lut->e[L] << bdmin8, I = (int)lut->i[L] << bdmin8;
-    const int wd = g.uv ? 4 + 2 * idx : 4 << idx;
-    const int ng = wd == 16 ? 2 : 1;           // 4-pixel groups loaded on each side of the edge
-    auto load4 = [](const pixel *p, int *v) {
-        if (BD::hbd) { const uint2 q = *(const uint2 *)p; v[0] = q.x & 0xffff; v[1] = q.x >> 16; v[2] = q.y & 0xffff; v[3] = q.y >> 16; }
-        else { const unsigned q = *(const unsigned *)p; v[0] = q & 0xff; v[1] = (q >> 8) & 0xff; v[2] = (q >> 16) & 0xff; v[3] = q >> 24; }
+    __shared__ uint32_t list[LF_THREADS * LF_CAND];   // gid << 10 | level << 2 | width index
+    __shared__ int warp_cnt[LF_THREADS / 32], n_list;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int total = S.unit_start[S.n_planes];
+    auto locate = [&](int gid, int &pi, int &x4, int &y4) {
+        pi = (S.n_planes > 1 && gid >= S.unit_start[1]) ? ((S.n_planes > 2 && gid >= S.unit_start[2]) ? 2 : 1) : 0;
+        const int w4 = pi == 0 ? S.g[0].w4 : (pi == 1 ? S.g[1].w4 : S.g[2].w4);
+        const int u = gid - (pi == 0 ? 0 : (pi == 1 ? S.unit_start[1] : S.unit_start[2]));
+        const int yl = u / w4;
+        x4 = u - yl * w4;
+        y4 = yl + (pi == 0 ? S.y4_first[0] : (pi == 1 ? S.y4_first[1] : S.y4_first[2]));
     };
-    if (DIR == 0) {
+    // ---- 1. which candidate units carry an edge: the mask bit and a non-zero level (own, else the neighbour's)
+    if (tid == 0) n_list = 0;
+    __syncthreads();
 #pragma unroll 1
-        for (int line = 0; line < 4; line++) {
-            pixel *p = base + (int64_t)line * ps;
-            int P[8], Q[8], t[4];
-            load4(p - 4, t); P[0] = t[3]; P[1] = t[2]; P[2] = t[1]; P[3] = t[0];
-            load4(p, Q);
-            if (ng == 2) { load4(p - 8, t); P[4] = t[3]; P[5] = t[2]; P[6] = t[1]; P[7] = t[0]; load4(p + 4, Q + 4); }
-            const int n = lf_line_regs(P, Q, E, I, H, wd, bdmin8, bdmax);
-#pragma unroll
-            for (int i = 0; i < 6; i++)
-                if (i < n) { p[-1 - i] = (pixel)P[i]; p[i] = (pixel)Q[i]; }
-        }
-    } else {
-        // rows y-4ng .. y+4ng-1, 4 columns each, kept PACKED (one or two registers per row) to leave room
-        // for more resident warps; column c is unpacked, filtered and re-packed
-        if (ng == 2) {
-#pragma unroll
-            for (int r = 0; r < 16; r++) {
-                if (r >= 4 && r < 12) continue;
-                const pixel *p = base + (int64_t)(r - 8) * ps;
-                if (BD::hbd) { const uint2 q = *(const uint2 *)p; rows[r][0] = q.x; rows[r][WPR - 1] = q.y; }
-                else rows[r][0] = *(const unsigned *)p;
+    for (int k = 0; k < LF_CAND; k++) {
+        const int gid = (blockIdx.x * LF_CAND + k) * LF_THREADS + tid;
+        uint32_t entry = 0;
+        bool on = false;
+        if (gid < total) {
+            int pi, x4, y4;
+            locate(gid, pi, x4, y4);
+            if (DIR == 0 ? x4 != 0 : y4 != 0) {                 // have_left / have_top
+                const LfGeom &g = pi == 0 ? S.g[0] : (pi == 1 ? S.g[1] : S.g[2]);
+                const int idx = lf_mask_idx(masks, g, DIR, x4, y4);
+                if (idx >= 0) {
+                    const uint8_t(*l)[4] = lvl + (int64_t)y4 * g.b4_stride + x4;
+                    int L = l[0][g.lvl_idx];
+                    if (!L) L = DIR == 0 ? l[-1][g.lvl_idx] : l[-(int64_t)g.b4_stride][g.lvl_idx];
+                    if (L) { on = true; entry = (uint32_t)(k * LF_THREADS + tid) << 10 | (uint32_t)L << 2 | (uint32_t)idx; }
+                }
             }
         }
-        auto get = [&](int r, int c) -> int {
-            if (BD::hbd) return (int)((rows[r][c >> 1] >> (16 * (c & 1))) & 0xffff);
-            return (int)((rows[r][0] >> (8 * c)) & 0xff);
-        };
-        auto put = [&](int r, int c, int v) {
-            if (BD::hbd) rows[r][c >> 1] = (rows[r][c >> 1] & ~(0xffffu << (16 * (c & 1)))) | ((unsigned)v << (16 * (c & 1)));
-            else rows[r][0] = (rows[r][0] & ~(0xffu << (8 * c))) | ((unsigned)v << (8 * c));
-        };
-        int nmax = 0;
+        const unsigned m = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) warp_cnt[warp] = __popc(m);
+        __syncthreads();
+        int base = n_list;
+        for (int w = 0; w < warp; w++) base += warp_cnt[w];
+        if (on) list[base + __popc(m & ((1u << lane) - 1))] = entry;
+        __syncthreads();
+        if (tid == 0) { int t = n_list; for (int w = 0; w < LF_THREADS / 32; w++) t += warp_cnt[w]; n_list = t; }
+        __syncthreads();
+    }
+    // ---- 2. filter the compacted list
+    const int n = n_list;
+    const int bdmin8 = BD::hbd ? bpc_from_max(bdmax) - 8 : 0;
+    constexpr int WPR = BD::hbd ? 2 : 1;            // 32-bit words per 4-pixel group
+    auto unpack4 = [](const unsigned *w, int *v) {
+        if (BD::hbd) { v[0] = w[0] & 0xffff; v[1] = w[0] >> 16; v[2] = w[WPR - 1] & 0xffff; v[3] = w[WPR - 1] >> 16; }
+        else { v[0] = w[0] & 0xff; v[1] = (w[0] >> 8) & 0xff; v[2] = (w[0] >> 16) & 0xff; v[3] = w[0] >> 24; }
+    };
+    auto pack4 = [](const int *v, unsigned *w) {
+        if (BD::hbd) { w[0] = (unsigned)v[0] | (unsigned)v[1] << 16; w[WPR - 1] = (unsigned)v[2] | (unsigned)v[3] << 16; }
+        else w[0] = (unsigned)v[0] | (unsigned)v[1] << 8 | (unsigned)v[2] << 16 | (unsigned)v[3] << 24;
+    };
+    auto ld4 = [](const pixel *p, unsigned *w) {
+        if (BD::hbd) { const uint2 q = *(const uint2 *)p; w[0] = q.x; w[WPR - 1] = q.y; } else w[0] = *(const unsigned *)p;
+    };
+    auto st4 = [](pixel *p, const unsigned *w) {
+        if (BD::hbd) *(uint2 *)p = make_uint2(w[0], w[WPR - 1]); else *(unsigned *)p = w[0];
+    };
+#pragma unroll 1
+    for (int e = tid; e < n; e += LF_THREADS) {
+        const uint32_t entry = list[e];
+        const int gid = blockIdx.x * LF_CAND * LF_THREADS + (int)(entry >> 10), L = (entry >> 2) & 0xff, idx = entry & 3;
+        int pi, x4, y4;
+        locate(gid, pi, x4, y4);
+        const int uv = pi == 0 ? S.g[0].uv : 1;
+        uint8_t *plane = pi == 0 ? S.plane[0] : (pi == 1 ? S.plane[1] : S.plane[2]);
+        const int64_t ps = (pi == 0 ? S.stride[0] : (pi == 1 ? S.stride[1] : S.stride[2])) / (int64_t)sizeof(pixel);
+        pixel *base = (pixel *)plane + (int64_t)(y4 * 4) * ps + x4 * 4;   // q0 of line 0
+        const int H = (L >> 4) << bdmin8, E = (int)lut->e[L] << bdmin8, I = (int)lut->i[L] << bdmin8;
+        const int wd = uv ? 4 + 2 * idx : 4 << idx;
+        const int ng = wd == 16 ? 2 : 1;           // 4-pixel groups on each side of the edge
+        if (DIR == 0) {
+#pragma unroll 1
+            for (int line = 0; line < 4; line++) {
+                pixel *p = base + (int64_t)line * ps;
+                unsigned w[4][WPR];
+                int x[16];
+                ld4(p - 4, w[1]); ld4(p, w[2]);
+                if (ng == 2) { ld4(p - 8, w[0]); ld4(p + 4, w[3]); unpack4(w[0], x); unpack4(w[3], x + 12); }
+                unpack4(w[1], x + 4); unpack4(w[2], x + 8);
+                const int m = lf_edge_wd(wd, x, E, I, H, bdmin8, bdmax);
+                if (!m) continue;
+                if (wd == 4) {
+                    // the neighbouring edges may be only 4 pixels away and own p3 / p2 and q2 / q3: write p1 p0 | q0 q1 only
+                    if (BD::hbd) { *(unsigned *)(p - 2) = (unsigned)x[6] | (unsigned)x[7] << 16; *(unsigned *)p = (unsigned)x[8] | (unsigned)x[9] << 16; }
+                    else { *(uint16_t *)(p - 2) = (uint16_t)(x[6] | x[7] << 8); *(uint16_t *)p = (uint16_t)(x[8] | x[9] << 8); }
+                    continue;
+                }
+                // wider filters: both transform blocks are at least 8 (16) pixels, so the 4-pixel words are this edge's alone
+                pack4(x + 4, w[1]); pack4(x + 8, w[2]); st4(p - 4, w[1]); st4(p, w[2]);
+                if (m > 4) { pack4(x, w[0]); pack4(x + 12, w[3]); st4(p - 8, w[0]); st4(p + 4, w[3]); }
+            }
+        } else {
+            // rows y - 4 ng .. y + 4 ng - 1 of the unit's 4 columns, one packed word group per row
+            unsigned rows[16][WPR];
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            int P[8], Q[8];
+            for (int r = 4; r < 12; r++) ld4(base + (int64_t)(r - 8) * ps, rows[r]);
+            if (ng == 2) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) { P[i] = get(7 - i, c); Q[i] = get(8 + i, c); }
-            const int n = lf_line_regs(P, Q, E, I, H, wd, bdmin8, bdmax);
-            nmax = imax(nmax, n);
+                for (int r = 0; r < 16; r++) if (r < 4 || r >= 12) ld4(base + (int64_t)(r - 8) * ps, rows[r]);
+            }
+            auto get = [&](int r, int c) -> int {
+                if (BD::hbd) return (int)((rows[r][c >> 1] >> (16 * (c & 1))) & 0xffff);
+                return (int)((rows[r][0] >> (8 * c)) & 0xff);
+            };
+            auto put = [&](int r, int c, int v) {
+                if (BD::hbd) rows[r][c >> 1] = (rows[r][c >> 1] & ~(0xffffu << (16 * (c & 1)))) | ((unsigned)v << (16 * (c & 1)));
+                else rows[r][0] = (rows[r][0] & ~(0xffu << (8 * c))) | ((unsigned)v << (8 * c));
+            };
+            int mmax = 0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                int x[16];
+#pragma unroll
+                for (int r = 0; r < 16; r++) x[r] = get(r, c);
+                const int m = lf_edge_wd(wd, x, E, I, H, bdmin8, bdmax);
+                mmax = imax(mmax, m);
+#pragma unroll
+                for (int i = 0; i < 6; i++)
+                    if (i < m) { put(7 - i, c, x[7 - i]); put(8 + i, c, x[8 + i]); }
+            }
 #pragma unroll
             for (int i = 0; i < 6; i++)
-                if (i < n) { put(7 - i, c, P[i]); put(8 + i, c, Q[i]); }
-        }
-#pragma unroll
-        for (int i = 0; i < 6; i++) {
-            if (i < nmax) {
-                pixel *pu = base + (int64_t)(-1 - i) * ps, *pd = base + (int64_t)i * ps;
-                if (BD::hbd) { *(uint2 *)pu = make_uint2(rows[7 - i][0], rows[7 - i][WPR - 1]); *(uint2 *)pd = make_uint2(rows[8 + i][0], rows[8 + i][WPR - 1]); }
-                else { *(unsigned *)pu = rows[7 - i][0]; *(unsigned *)pd = rows[8 + i][0]; }
-            }
+                if (i < mmax) { st4(base + (int64_t)(-1 - i) * ps, rows[7 - i]); st4(base + (int64_t)i * ps, rows[8 + i]); }
         }
     }
 }
@@ -334,9 +299,16 @@ __global__ void lpf_sb_kernel(uint8_t *dst, int64_t stride, int uv, int dir, uin
     const int bdmin8 = BD::hbd ? bpc_from_max(bdmax) - 8 : 0;
     const int H = (L >> 4) << bdmin8, E = (int)lut.e[L] << bdmin8, I = (int)lut.i[L] << bdmin8;
     const int64_t ps = stride / (int64_t)sizeof(pixel);
-    pixel *p = (pixel *)dst;
-    if (dir == 0) lf_line<BD>(p + (int64_t)(u * 4 + line) * ps, 1, E, I, H, wd, bdmin8, bdmax);
-    else lf_line<BD>(p + u * 4 + line, ps, E, I, H, wd, bdmin8, bdmax);
+    pixel *q0 = dir == 0 ? (pixel *)dst + (int64_t)(u * 4 + line) * ps : (pixel *)dst + u * 4 + line;
+    const int64_t sb = dir == 0 ? 1 : ps;           // element stride across the edge
+    const int reach = wd == 16 ? 7 : (wd >> 1);     // samples read on each side
+    int x[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = (i >= 8 - reach && i < 8 + reach) ? (int)q0[(int64_t)(i - 8) * sb] : 0;
+    const int m = lf_edge_wd(wd, x, E, I, H, bdmin8, bdmax);
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+        if (i < m) { q0[(int64_t)(-1 - i) * sb] = (pixel)x[7 - i]; q0[(int64_t)i * sb] = (pixel)x[8 + i]; }
 }
 
 // Whole-frame deblock: column edges of every plane (one launch), then row edges (one launch).
@@ -345,7 +317,9 @@ __global__ void lpf_sb_kernel(uint8_t *dst, int64_t stride, int uv, int dir, uin
 int deblock_frame_launch(const Rb200Planes &pl, int n_planes, int w4, int h4, int sb128w, int b4_stride, int ss_hor,
                          int ss_ver, bool do_uv, const Rb200Av1Filter *masks, const uint8_t (*lvl)[4],
                          const Rb200Av1FilterLUT *lut, int bdmax, cudaStream_t st, int *launches, int y4b, int y4e) {
+    static const int only_dir = getenv("RB200_LF_ONLY_DIR") ? atoi(getenv("RB200_LF_ONLY_DIR")) : -1;   // debugging aid
     for (int dir = 0; dir < 2; dir++) {
+        if (only_dir >= 0 && dir != only_dir) continue;
         LfPlaneSet S = {};
         int n = 0, total = 0;
         for (int p = 0; p < n_planes; p++) {
@@ -368,12 +342,15 @@ int deblock_frame_launch(const Rb200Planes &pl, int n_planes, int w4, int h4, in
         S.unit_start[n] = total;
         for (int k = n + 1; k < 4; k++) S.unit_start[k] = total;
         S.n_planes = n;
-        const int grid = (total + 127) / 128;
-#define L(BD, D) deblock_units_kernel<BD, D><<<grid, 128, 0, st>>>(S, masks, lvl, lut, bdmax)
+        const int grid = (total + LF_THREADS * LF_CAND - 1) / (LF_THREADS * LF_CAND);
+        if (!grid) continue;
+#define L(BD, D) deblock_units_kernel<BD, D><<<grid, LF_THREADS, 0, st>>>(S, masks, lvl, lut, bdmax)
         if (bdmax > 255) { if (dir) L(BD16, 1); else L(BD16, 0); } else { if (dir) L(BD8, 1); else L(BD8, 0); }
 #undef L
         RB_LAUNCH_CHECK();
         if (launches) ++*launches;
+        static const int sync_between = getenv("RB200_LF_SYNC_BETWEEN") ? atoi(getenv("RB200_LF_SYNC_BETWEEN")) : 0;   // debugging aid
+        if (sync_between) RB_CUDA(cudaStreamSynchronize(st));
     }
     return 0;
 }

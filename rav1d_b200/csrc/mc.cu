@@ -786,11 +786,29 @@ mc_comp_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int l
     cp_async_wait<0>();
 }
 
+// The packed sub-pel tap table (g_subpel_packed) is filled once per device; every launcher whose kernel goes through
+// mc_load_taps calls this first (the put batch and the compound batch -- a frame may hold only compound blocks).
+static int mc_ensure_packed_taps(cudaStream_t st) {
+    static std::mutex mu;
+    static bool packed[64] = {};
+    std::lock_guard<std::mutex> lock(mu);
+    int dev = 0;
+    RB_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !packed[dev]) {
+        mc_pack_table_kernel<<<1, 96, 0, st>>>();
+        RB_LAUNCH_CHECK();
+        RB_CUDA(cudaStreamSynchronize(st));   // once per device: visible to every stream that follows
+        packed[dev] = true;
+    }
+    return 0;
+}
+
 int mc_comp_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int layout,
                          const Rb200CompItem *d_items, int n, int bdmax, cudaStream_t st) {
     if (n <= 0) return 0;
     McRefSet rs = {};
     for (int i = 0; i < n_refs && i < 8; i++) rs.p[i] = refs[i];
+    { const int r = mc_ensure_packed_taps(st); if (r) return r; }
     const int grid = imin((n + MC_WARPS - 1) / MC_WARPS, 148 * 4);   // persistent warps walk the list
     if (bdmax > 255) mc_comp_batch_kernel<BD16><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, layout, d_items, n, bdmax);
     else mc_comp_batch_kernel<BD8><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, layout, d_items, n, bdmax);
@@ -1198,19 +1216,7 @@ int mc_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs,
     if (n <= 0) return 0;
     McRefSet rs = {};
     for (int i = 0; i < n_refs && i < 8; i++) rs.p[i] = refs[i];
-    {
-        static std::mutex mu;
-        static bool packed[64] = {};
-        std::lock_guard<std::mutex> lock(mu);
-        int dev = 0;
-        RB_CUDA(cudaGetDevice(&dev));
-        if (dev >= 0 && dev < 64 && !packed[dev]) {
-            mc_pack_table_kernel<<<1, 96, 0, st>>>();
-            RB_LAUNCH_CHECK();
-            RB_CUDA(cudaStreamSynchronize(st));   // once per device: visible to every stream that follows
-            packed[dev] = true;
-        }
-    }
+    { const int r = mc_ensure_packed_taps(st); if (r) return r; }
     // persistent warps: 148 SMs x 6 resident CTAs, capped by the item count
     // chunk size: as large as MC_CHUNK when there is enough work to give every resident warp a few chunks
     const int resident_warps = 148 * MC_BATCH_CTAS * MC_WARPS;

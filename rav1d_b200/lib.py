@@ -8,12 +8,17 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librav1d_b200.so")
 
-if not os.path.exists(LIB_PATH):
+# RB200_LIB_TYPES_ONLY=1: only the record types / numpy dtypes / constants of this module are wanted (bench.py's
+# --impl reference arm builds the synthetic frame with them and must not map the product library); every function
+# then raises when called.
+TYPES_ONLY = os.environ.get("RB200_LIB_TYPES_ONLY") == "1"
+
+if not TYPES_ONLY and not os.path.exists(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
         "(or `make -C rav1d_b200/csrc`). rav1d_b200 has no CPU fallback.")
 
-cdll = C.CDLL(LIB_PATH)
+cdll = None if TYPES_ONLY else C.CDLL(LIB_PATH)
 
 N_RECT_TX_SIZES = 19
 N_TX_TYPES_PLUS_LL = 17
@@ -46,6 +51,10 @@ class InvTxfmDSPContext(C.Structure):
 
 
 def _sig(name, restype, *argtypes):
+    if cdll is None:
+        def unavailable(*a, **k):
+            raise RuntimeError(f"{name}: rav1d_b200.lib was imported with RB200_LIB_TYPES_ONLY=1 (no library mapped)")
+        return unavailable
     f = getattr(cdll, name)
     f.restype = restype
     f.argtypes = list(argtypes)
