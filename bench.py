@@ -7,12 +7,17 @@ A *step* is one pass of the hot path over one batch of FRAMES_PER_STEP synthetic
 recon (8-tap MC + itx add) -> deblock -> CDEF -> Wiener/SGR loop restoration (4k10: BASELINE
 configs[2], the configuration the metric is quoted on).
 
-* `value`  : Mpixel/s (luma pixels of output frames / s) with the batch resident in HBM, timed
-             with CUDA events on the launching stream; frames cycle over N_CTX frame contexts
-             whose working sets (> 190 MB each at 4K) exceed the 126 MB L2.
-* `e2e`    : same metric through the C ABI with HOST buffers: per frame H2D of coefficients,
-             work items and filter metadata from pinned staging, the stage launches, D2H of the
-             output picture into pinned host planes; N_CTX frames in flight on their own streams.
+* `value`  : Mpixel/s (luma pixels of output frames / s) of ONE video stream with the batch resident in
+             HBM, timed with CUDA events on the launching streams: frames cycle over N_CTX frame
+             contexts (working sets > 190 MB each at 4K, beyond the 126 MB L2), and every frame
+             predicts from the OUTPUT of the frame before it (rb200_frame_depend: its kernels wait
+             for the previous frame's last kernel) -- the dependency chain of real inter frames.
+* `value_unchained`: the same contexts with a static reference and no dependency, i.e. N_CTX
+             independent streams sharing the GPU (what round 1 reported as `value`).
+* `e2e`    : `value`'s chained stream through the C ABI with HOST buffers: per frame H2D of
+             coefficients, work items and filter metadata from pinned staging, the stage launches, D2H
+             of the output picture into pinned host planes; N_CTX frames in flight on their own
+             streams (uploads and read-backs of neighbouring frames overlap the kernels).
 * `roofline`: the dominant kernel's algorithmic bytes / its CUDA-event duration (stage marks of
              rb200_frame_stage_times, recorded inside the timed region) against MEASURED_PEAKS.json.
 * `cpu_baseline`: the reference's own C DSP + frame drivers (oracle/_ref, all host threads) on a
@@ -48,7 +53,7 @@ WORKLOADS = {
                                    "recon + deblock + CDEF + Wiener/SGR LR + film grain"),
 }
 GEN_ARGS = {"4k10c5": dict(comp_frac=0.5, warp_frac=0.05, obmc_frac=0.1)}
-FRAMES_PER_STEP = 16
+FRAMES_PER_STEP = int(os.environ.get("RB200_BENCH_FRAMES_PER_STEP", "256"))   # x steps: a timed region of > 1 s
 N_CTX = int(os.environ.get("RB200_BENCH_CTX", "8"))
 # BASELINE.json's metric, verbatim; `value` is its Mpixel/s part (luma pixels of output frames per second), the
 # "% of HBM roofline" part is `frame_roofline_frac` (whole frame) and `roofline` (dominant kernel).
@@ -207,7 +212,6 @@ def run_gpu(args, s, wl):
         raise SystemExit("bench.py: no CUDA device; rav1d_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"     # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib.check(lib.init(local), "rb200_init")
 
@@ -252,89 +256,115 @@ def run_gpu(args, s, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- resident leg: CUDA events around K steps.
-    # --streams 1: every frame on one stream (kernels strictly serial).  --streams N_CTX (default): each
-    # frame context on its own stream, so stages of different frames overlap on the device the way
-    # the reference's frame threads (n_fc) overlap frames; the timed region is bracketed by one start
-    # event and one end event per stream, the slowest stream decides.
-    multi = args.streams > 1
+    # ---------------- resident legs: CUDA events around K steps.
+    # Each frame context runs on its own stream.  "chained": frame i predicts from the output of frame i - 1 (the
+    # context before it in the cycle) and its kernels wait for that frame's last kernel (rb200_frame_depend) -- one
+    # video stream, the way real inter frames depend on each other.  "unchained": a static reference and no
+    # dependency, i.e. N_CTX independent streams sharing the GPU.  The timed region is bracketed by one start event
+    # and one end event per stream; the slowest stream decides.
     main = torch.cuda.Stream()
+    one_stream = args.streams == 1           # debugging / ncu launch lists: every context on one CUDA stream
     for d in ctxs:
-        lib.check(lib.frame_set_stream(d.h, None if multi else C.c_void_p(main.cuda_stream)))
+        lib.check(lib.frame_set_stream(d.h, C.c_void_p(main.cuda_stream) if one_stream else None))
         submit(d, True)                      # batch becomes resident (not timed)
-    rstreams = [torch.cuda.ExternalStream(lib.frame_stream(d.h)) for d in ctxs] if multi else [main]
-    for _ in range(args.warmup):
-        for i in range(FRAMES_PER_STEP):
-            submit(ctxs[i % N_CTX], False)
+    rstreams = [main] if one_stream else [torch.cuda.ExternalStream(lib.frame_stream(d.h)) for d in ctxs]
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    static_ref = lib.Planes()
+    chain_refs = []
+    if stages & 1:
+        lib.check(lib.frame_stage_planes(ctxs[0].ref_handle, 0, C.byref(static_ref)))
+        for d in ctxs:
+            pl = lib.Planes()
+            lib.check(lib.frame_output_planes(d.h, C.byref(pl)))
+            chain_refs.append(pl)
+
+    def set_chain(on):
+        """Reference slot 0 of context i: the output planes of context i - 1 (chained) or the uploaded static picture."""
+        if not stages & 1:
+            return
+        for i, d in enumerate(ctxs):
+            lib.check(lib.frame_set_ref(d.h, 0, C.byref(chain_refs[i - 1] if on else static_ref)))
+
+    def frame(i, chained, upload=False):
+        d = ctxs[i % N_CTX]
+        if chained and stages & 1:
+            lib.check(lib.frame_depend(d.h, ctxs[(i - 1) % N_CTX].h))
+        submit(d, upload)
+        return d
+
+    def timed_resident(chained):
+        set_chain(chained)
+        for i in range(args.warmup * FRAMES_PER_STEP):
+            frame(i, chained)
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1s = [torch.cuda.Event(enable_timing=True) for _ in rstreams]
+        n_launch = 0
+        e0.record(rstreams[0])
+        for st in rstreams[1:]:
+            st.wait_event(e0)
+        for i in range(args.steps * FRAMES_PER_STEP):
+            n_launch += lib.frame_last_launches(frame(i, chained).h)
+        for st, ev in zip(rstreams, e1s):
+            ev.record(st)
+        barrier()
+        ms = max(e0.elapsed_time(ev) for ev in e1s)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), n_launch
+
+    sampler = ClockSampler(local) if rank == 0 else None      # started before the warm-up: sampled every 100 ms from here on
+    frames_total = world * args.steps * FRAMES_PER_STEP
+    ms_unchained, _ = timed_resident(False)
+    value_unchained = frames_total * w * h / (ms_unchained * 1e-3) / 1e6
+    if stages & 1:
+        ms_max, launches = timed_resident(True)
+    else:                                    # post-filters only: nothing predicts from anything, the frames are independent
+        ms_max, launches = timed_resident(False)
+    value = frames_total * w * h / (ms_max * 1e-3) / 1e6
+    clocks = sampler.stop() if sampler else None
+    # ---- per-stage kernel durations: with frames on several streams the stage marks of one frame can include other
+    # frames' kernels, so the stage table (and the roofline of the dominant kernel) comes from a pass of the same
+    # chained frames with every context on ONE stream (kernels strictly serial).
     stage_ms = np.zeros(7)
     stage_n = 0
     buf = (C.c_float * 7)()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1s = [torch.cuda.Event(enable_timing=True) for _ in rstreams]
-    launches = 0
-    e0.record(rstreams[0])
-    for st in rstreams[1:]:
-        st.wait_event(e0)
-    for _ in range(args.steps):
-        for i in range(FRAMES_PER_STEP):
-            submit(ctxs[i % N_CTX], False)
-            launches += lib.frame_last_launches(ctxs[i % N_CTX].h)
-        if not multi:
-            main.synchronize()               # read the stage marks of this step's last N_CTX frames
-            for d in ctxs:
-                lib.check(lib.frame_stage_times(d.h, buf))
-                stage_ms += np.array(buf[:])
-                stage_n += 1
-    for st, ev in zip(rstreams, e1s):
-        ev.record(st)
+    for d in ctxs:
+        lib.check(lib.frame_set_stream(d.h, C.c_void_p(main.cuda_stream)))
+    for i in range(FRAMES_PER_STEP):
+        frame(i, False)
     barrier()
-    clocks = sampler.stop() if sampler else None
-    ms = max(e0.elapsed_time(ev) for ev in e1s)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    frames_total = world * args.steps * FRAMES_PER_STEP
-    value = frames_total * w * h / (ms_max * 1e-3) / 1e6
-    # ---- per-stage kernel durations: with frames overlapping on several streams the stage marks of one
-    # frame include other frames' kernels, so the stage table (and the roofline of the dominant kernel)
-    # comes from a second pass of the same K steps with every frame on ONE stream (kernels serial).
-    value_serial = value
-    if multi:
-        for d in ctxs:
-            lib.check(lib.frame_set_stream(d.h, C.c_void_p(main.cuda_stream)))
+    s0e, s1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_steps = max(1, min(args.steps, 4))
+    s0e.record(main)
+    for _ in range(stage_steps):
         for i in range(FRAMES_PER_STEP):
-            submit(ctxs[i % N_CTX], False)
-        barrier()
-        s0e, s1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0e.record(main)
-        for _ in range(args.steps):
-            for i in range(FRAMES_PER_STEP):
-                submit(ctxs[i % N_CTX], False)
-            main.synchronize()
-            for d in ctxs:
-                lib.check(lib.frame_stage_times(d.h, buf))
-                stage_ms += np.array(buf[:])
-                stage_n += 1
-        s1e.record(main)
-        barrier()
-        value_serial = args.steps * FRAMES_PER_STEP * w * h / (s0e.elapsed_time(s1e) * 1e-3) / 1e6
+            frame(i, False)
+        main.synchronize()                   # read the stage marks of this step's last N_CTX frames
+        for d in ctxs:
+            lib.check(lib.frame_stage_times(d.h, buf))
+            stage_ms += np.array(buf[:])
+            stage_n += 1
+    s1e.record(main)
+    barrier()
+    value_serial = stage_steps * FRAMES_PER_STEP * w * h / (s0e.elapsed_time(s1e) * 1e-3) / 1e6
     stage_ms = stage_ms / max(stage_n, 1)
 
-    # ---------------- e2e leg: host buffers, N_CTX frames in flight on their own streams
+    # ---------------- e2e leg: host buffers, the chained stream with N_CTX frames in flight on their own streams
     for d in ctxs:
         lib.check(lib.frame_set_stream(d.h, None))
     streams = [torch.cuda.ExternalStream(lib.frame_stream(d.h)) for d in ctxs]
+    e2e_upload = {"gather": 3, "zerocopy": 2, "copy": 1}[args.coefs]
 
     def e2e_frame(i):
         d = ctxs[i % N_CTX]
         d.wait()                             # the context's previous frame (incl. its readback) is done;
-        submit(d, {"gather": 3, "zerocopy": 2, "copy": 1}[args.coefs])   # the front end would refill the pinned staging here
+        frame(i, True, e2e_upload)           # the front end would refill the pinned staging here
         lib.check(lib.frame_readback_async(d.h, host_out[i % N_CTX][0], host_out[i % N_CTX][1]))
 
-    for i in range(max(args.warmup * FRAMES_PER_STEP, 256)):   # >= 0.25 s of traffic: lets the host link and clocks settle
+    e2e_frames = args.steps * FRAMES_PER_STEP
+    for i in range(max(min(args.warmup * FRAMES_PER_STEP, e2e_frames), 256)):   # >= 0.25 s of traffic: lets the host link and clocks settle
         e2e_frame(i)
     barrier()
     s0 = torch.cuda.Event(enable_timing=True)
@@ -342,7 +372,7 @@ def run_gpu(args, s, wl):
     s0.record(streams[0])
     for st in streams[1:]:
         st.wait_event(s0)
-    for i in range(args.steps * FRAMES_PER_STEP):
+    for i in range(e2e_frames):
         e2e_frame(i)
     for st, ev in zip(streams, ends):
         ev.record(st)
@@ -375,6 +405,10 @@ def run_gpu(args, s, wl):
     if rank == 0:
         peak, peak_src = peaks()
         ab = algorithmic_bytes(w, h, bpc, GEN_ARGS.get(args.workload, {}).get('comp_frac', 0.0))
+        if stages & 1:      # the transforms fetch only the leading ncols columns of a block (Rb200ItxItem.ncols)
+            from rav1d_b200.lib import TX_DIMS
+            sh_ = np.array([min(TX_DIMS[t][1], 32) for t in range(19)])[s.itx_items["tx"]]
+            ab["itx"] = int((s.itx_items["ncols"].astype(np.int64) * sh_).sum()) * (4 if bpc > 8 else 2) + 2 * ab["S"]
         per_stage = {}
         for name, t_ms in zip(STAGE_NAMES, stage_ms):
             bit = {"mc": 1, "itx": 1, "deblock": 2, "cdef": 4, "lr": 8, "film_grain": 16}.get(name, 0)
@@ -402,13 +436,16 @@ def run_gpu(args, s, wl):
                 "dtype": "int32", "data": "synthetic",
                 "config": {"workload": desc, "frames_per_step": FRAMES_PER_STEP, "width": w, "height": h, "bpc": bpc,
                            "l2": f"inputs larger than L2: {N_CTX} frame contexts cycled, > {ab['S'] * 4 // 1000000} MB working set each",
-                           "frames_in_flight": N_CTX if multi else 1,
+                           "frames_in_flight": N_CTX,
+                           "dependency": "every frame predicts from the previous frame's output and waits for it on the device (rb200_frame_depend)"
+                                         if stages & 1 else "none (post-filters only)",
                            "lf_metadata": "block records, masks built on the device" if args.lf == "records" else "masks and levels uploaded",
-                           "parallelism": f"{world} independent streams (one per GPU)" if world > 1 else "1 video stream"},
+                           "parallelism": f"{world} independent video streams (one per GPU)" if world > 1 else "1 video stream"},
                 "fps": value * 1e6 / (w * h),
-                "value_one_stream": value_serial,
-                "stage_timing": "CUDA-event marks of a one-stream pass over the same steps (kernels serial)" if multi
-                                else "CUDA-event marks inside the timed region",
+                "value_unchained": value_unchained,
+                "value_unchained_note": f"{N_CTX} independent streams per GPU: same contexts, static reference, no frame-to-frame dependency",
+                "value_serial_kernels": value_serial,
+                "stage_timing": "CUDA-event marks of a one-CUDA-stream pass over the same frames (kernels strictly serial)",
                 "frame_roofline_frac": round(frame_bytes * (value * 1e6 / (w * h)) / world / (peak * 1e9), 4),
                 "stages": per_stage, "roofline": roofline, "issue": issue, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d * FRAMES_PER_STEP,
@@ -476,7 +513,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--lf", default="masks", choices=["masks", "records"],
                     help="loop-filter metadata: Av1Filter masks + levels uploaded, or per-block records uploaded and the masks built on the device")
-    ap.add_argument("--streams", type=int, default=N_CTX, help="resident leg: 1 = all frames on one stream, >1 = one stream per frame context")
+    ap.add_argument("--streams", type=int, default=N_CTX, help="resident legs: 1 = every frame context on one CUDA stream (launch lists), otherwise one stream per context")
     ap.add_argument("--coefs", default="gather", choices=["gather", "zerocopy", "copy"],
                     help="e2e leg, how coefficients cross PCIe: a gather kernel pulls each block's non-zero columns into "
                          "HBM (default); the transforms read pinned memory directly; or the whole buffer is H2D-copied")
@@ -484,8 +521,10 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", 0))
     wl = WORKLOADS[args.workload]
-    if args.impl == "reference" and rank != 0:
-        return
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        os.environ["RB200_LIB_TYPES_ONLY"] = "1"   # the generator needs the record types only: the product library is not mapped
     from rav1d_b200.synth import framegen
     s = framegen.generate(wl[0], wl[1], wl[2], seed=1 + (rank if args.impl == "b200" else 0), **GEN_ARGS.get(args.workload, {}))
     if wl[3] & 16:

@@ -627,6 +627,14 @@ int rb200_enable_peer_access(int peer_device);
 void *rb200_frame_stream(Rb200Frame *f);
 /* Run the frame's copies and launches on `stream` instead of the frame's own (NULL restores it). */
 int rb200_frame_set_stream(Rb200Frame *f, void *stream);
+/* Stream-ordered dependency between frame contexts that run on different streams: the kernels of `f`'s NEXT
+ * rb200_frame_submit wait on the device for the last kernel of `producer`'s most recent rb200_frame_submit (not for a
+ * read-back queued behind it); the submit's own batch uploads are not held back.  `producer` must stay alive until
+ * that submit.  This is what the reference's per-picture progress waits become
+ * (src/thread_task.rs:1255-1323, rav1d_thread_picture_wait): a frame that predicts from `producer`'s output names it
+ * here before its submit; no host synchronisation.  Up to 8 producers per submit; a no-op when both contexts share a
+ * stream. */
+int rb200_frame_depend(Rb200Frame *f, Rb200Frame *producer);
 /* Per-stage device times of the last submit (CUDA events on the frame's stream), the analogue
  * of the reference CLI's --frametimes (tools/dav1d.rs:127-150).  ms[] = H2D, MC, itx, deblock,
  * CDEF, LR, film grain; valid after rb200_frame_wait(). */

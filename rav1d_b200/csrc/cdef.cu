@@ -14,6 +14,7 @@
 // copied through.  Chroma planes reuse the tile buffer and the luma directions.
 #include "common.cuh"
 #include "tables.cuh"
+#include "tma.cuh"
 
 namespace rb200 {
 
@@ -297,126 +298,127 @@ __device__ __forceinline__ void cdef_stage2(int16_t *tile, const uint8_t *plane,
     }
 }
 
-// byte offset (from the tile base) of the aligned word holding pixels (s, s + 1) of a row-major element index s
-__device__ __forceinline__ int cdef_pair_addr(int s) { return (s & 1) ? 2 * (CDEF_COPY + s - 1) : 2 * s; }
-
-// Filter NP pixel pairs of one block row.  `s0`: element index of the first pixel (even).
-// Returns the filtered pixels in out[2 * NP].  Interior blocks only (no sentinel in reach).
-template <int NP>
-__device__ __forceinline__ void cdef_row_packed(const int16_t *tile, int s0, int pri, int sec, int dir, int damping,
-                                                int bdmin8, int *out) {
-    const char *base = (const char *)tile;
-    unsigned px2[NP], cst[NP], sum[NP], mn[NP], mx[NP];
-#pragma unroll
-    for (int j = 0; j < NP; j++) {
-        px2[j] = *(const unsigned *)(base + 2 * (s0 + 2 * j));
-        cst[j] = __vneg2(px2[j]);   // -px per half
-        sum[j] = 0; mn[j] = px2[j]; mx[j] = px2[j];
-    }
-    const unsigned B2 = CDEF_BIAS * 0x10001u;
-    int ktot = 0;
-    auto tap = [&](int off_el, int thr, int shift, int w, bool track) {
-        const unsigned m = (0xffffu >> shift) * 0x10001u;
-        const unsigned thr1 = (unsigned)(thr + 1) * 0x10001u;
-        const unsigned bmt = (unsigned)(CDEF_BIAS - thr) * 0x10001u;
-#pragma unroll
-        for (int sgn = 0; sgn < 2; sgn++) {
-            const int a0 = cdef_pair_addr(s0 + (sgn ? -off_el : off_el));
-#pragma unroll
-            for (int j = 0; j < NP; j++) {
-                const unsigned p2 = *(const unsigned *)(base + a0 + 4 * j);
-                const unsigned d = __vadd2(p2, cst[j]);                 // p - px
-                const unsigned a = __vmaxs2(d, __vneg2(d));             // |d|
-                const unsigned x = a >> shift;
-                const unsigned sft = x & m;                             // |d| >> shift, per half
-                const unsigned t = __viaddmax_s16x2(~sft, thr1, 0u);    // max(thr - s, 0)
-                const unsigned ntb = __viaddmin_s16x2(sft, bmt, B2);    // BIAS - t
-                const unsigned c = __viaddmax_s16x2(__vmins2(d, t), B2, ntb);  // BIAS + clamp(d, -t, t)
-                sum[j] += (unsigned)w * c;
-                if (track) { mn[j] = __vminu2(mn[j], p2); mx[j] = __vmaxs2(mx[j], p2); }
-            }
+// ---- the filter proper: pixel PAIRS in 32-bit registers, one lane per pair of a tile row
+//
+// A warp covers one tile row (luma: 32 pairs) or two (4:2:0 chroma: 16 pairs each) and walks down the rows of ONE
+// row of 8x8 blocks, so the per-block parameters are set up once per thread; consecutive lanes read consecutive
+// words of shared memory (no bank conflicts whatever the row pitch) and write consecutive words of the picture.
+//
+// constrain(d) = sign(d) * min(|d|, max(0, thr - (|d| >> shift)))  (src/cdef.rs:57-66) on two unsigned halves:
+//   dpos = max(p, px) - px,  dneg = px - min(p, px)     one of them is 0; plain 32-bit subtractions cannot borrow
+//   a    = dpos + dneg                                   = |d|
+//   mag  = relu(min(thr - (a >> shift), a))              one VIADDMNMX.S16x2.RELU
+//   the tap adds w * min(dpos, mag) to one sum and w * min(dneg, mag) to another; the sums (< 2^12) meet in the
+//   epilogue, which rounds, adds the centre pixel and clips to the tracked min / max, all still packed.
+// A tap that is "unavailable" (the reference's INT16_MIN sentinel, 0x8000 as an unsigned half) gives a >= 0x7001, so
+// mag = 0 and the tap drops out exactly as in the reference; it never wins the unsigned min or the signed max either.
+// Lanes whose block has no primary (secondary) strength run those taps with thr = 0, i.e. mag = 0.
+template <typename BD, bool PRI, bool SEC>
+__device__ __forceinline__ void cdef_rows(const char *cb, int row_step, int n_rows, const int (&aoff)[12], unsigned wp0,
+                                          unsigned wp1, unsigned pthr1, unsigned pmask, int pshift, unsigned sthr1,
+                                          unsigned smask, int sshift, bool clip, uint8_t *d, int64_t dstep, bool store) {
+    constexpr bool TRACK = PRI && SEC;
+    const unsigned clip_lo = clip ? 0u : 0xffffffffu, clip_hi = clip ? 0u : 0x7fff7fffu;
+#pragma unroll 1
+    for (int i = 0; i < n_rows; i++, cb += row_step, d += dstep) {
+        const unsigned px2 = *(const unsigned *)cb;
+        unsigned sum_p = 0, sum_n = 0, mn = px2, mx = px2;
+        auto tap = [&](int off, unsigned thr1, unsigned m, int shift, unsigned w) {
+            const unsigned p2 = *(const unsigned *)(cb + off);
+            const unsigned dpos = __vmaxu2(p2, px2) - px2, dneg = px2 - __vminu2(p2, px2);
+            const unsigned a = dpos + dneg;
+            const unsigned mag = __viaddmin_s16x2_relu(~((a >> shift) & m), thr1, a);
+            sum_p += w * __vminu2(dpos, mag);
+            sum_n += w * __vminu2(dneg, mag);
+            if (TRACK) { mn = __vminu2(mn, p2); mx = __vmaxs2(mx, p2); }
+        };
+        if (PRI) {
+            tap(aoff[0], pthr1, pmask, pshift, wp0); tap(aoff[1], pthr1, pmask, pshift, wp0);
+            tap(aoff[2], pthr1, pmask, pshift, wp1); tap(aoff[3], pthr1, pmask, pshift, wp1);
         }
-        ktot += 2 * w;
-    };
-    const bool both = pri && sec;
-    if (pri) {
-        const int pri_tap = 4 - ((pri >> bdmin8) & 1);
-        const int pri_shift = imax(0, damping - ulog2(pri));
-        int dy, dx;
-        tab::cdef_dir_off(dir, 0, dy, dx);
-        tap(dy * CDEF_TP + dx, pri, pri_shift, pri_tap, both);
-        tab::cdef_dir_off(dir, 1, dy, dx);
-        tap(dy * CDEF_TP + dx, pri, pri_shift, (pri_tap & 3) | 2, both);
-    }
-    if (sec) {
-        const int sec_shift = damping - ulog2(sec);
+        if (SEC) {
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
-            int dy, dx;
-            tab::cdef_dir_off((dir + 2) & 7, k, dy, dx);
-            tap(dy * CDEF_TP + dx, sec, sec_shift, 2 - k, both);
-            tab::cdef_dir_off((dir + 6) & 7, k, dy, dx);
-            tap(dy * CDEF_TP + dx, sec, sec_shift, 2 - k, both);
+            for (int k = 4; k < 8; k++) tap(aoff[k], sthr1, smask, sshift, 2u);
+#pragma unroll
+            for (int k = 8; k < 12; k++) tap(aoff[k], sthr1, smask, sshift, 1u);
         }
-    }
-    const int kb = ktot * (int)CDEF_BIAS;
-#pragma unroll
-    for (int j = 0; j < NP; j++) {
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int s = (int)((sum[j] >> (16 * h)) & 0xffff) - kb;
-            const int px = (int)((px2[j] >> (16 * h)) & 0xffff);
-            int v = px + ((s - (s < 0) + 8) >> 4);
-            if (both) v = iclip(v, (int)((mn[j] >> (16 * h)) & 0xffff), (int)((mx[j] >> (16 * h)) & 0xffff));
-            out[2 * j + h] = v;
+        // (sum - (sum < 0) + 8) >> 4 on both halves: sums biased by 4096 (a multiple of 16, > any |sum|)
+        const unsigned tb = sum_p + (0x10001000u - sum_n);
+        const unsigned neg = (~tb >> 12) & 0x00010001u;
+        const unsigned r = ((tb + 0x00080008u - neg) >> 4) & 0x0fff0fffu;   // 256 + rounded sum
+        unsigned vb = px2 + r;                                              // 256 + result, never negative
+        if (TRACK) vb = __vminu2(__vmaxu2(vb, (mn & ~clip_lo) + 0x01000100u), (mx | clip_hi) + 0x01000100u);
+        const unsigned v = vb - 0x01000100u;
+        if (store) {
+            if (BD::hbd) *(unsigned *)d = v;
+            else *(uint16_t *)d = (uint16_t)((v & 0xff) | ((v >> 8) & 0xff00));
         }
     }
 }
 
-// One plane of the area.  bw/bh: block size in this plane (8 or 4); tile staged already.
-template <typename BD, int BW>
-__device__ __forceinline__ void cdef_filter_plane(const int16_t *tile, const CdefBlk *blk, uint8_t *dbase, int64_t dstride,
-                                                  int px0, int py0, int tw, int th, int bh_log2, bool chroma, int damping,
-                                                  int bdmin8, int nbx, int nby, int gbx0, int gby0) {
+// One plane (luma) or two planes that share the block parameters (U and V) of the 64x64 area: `n_sub` staged tiles of
+// the same geometry.  tile pitch (pixels, even), copy_el: elements from copy A to the one-pixel-shifted copy B
+// (B[i] = A[i + 1]); the area's first pixel sits at row 2, column col0 (even) of a tile.
+template <typename BD>
+__device__ __forceinline__ void cdef_filter_tiles(const uint16_t *tile0, const uint16_t *tile1, uint8_t *dbase0, uint8_t *dbase1,
+                                                  int64_t dstride0, int64_t dstride1, int n_sub, int pitch, int copy_el, int col0,
+                                                  const CdefBlk *blk, int px0, int py0, int tw, int th, int ssh, int ssv, bool chroma,
+                                                  int damping, int bdmin8) {
     using pixel = typename BD::pixel;
-    constexpr int NP = BW / 2;
-    const int bh = 1 << bh_log2;
-    const int n_tasks = 64 << bh_log2;   // 64 blocks x rows
-    for (int t = threadIdx.x; t < n_tasks; t += blockDim.x) {
-        // a warp covers 8 blocks along x times 4 rows: conflict-free centre loads with the odd word pitch
-        const int lane = t & 31, grp = t >> 5;
-        const int bxl = lane & 7, rlow = lane >> 3;
-        const int rows_per_blk_grp = bh >> 2;                  // 4-row groups per block (1 or 2)
-        const int byl = grp / rows_per_blk_grp, r = rlow + 4 * (grp - byl * rows_per_blk_grp);
-        const int x = bxl * BW, y = byl * bh + r;
-        if (x >= tw || y >= th) continue;
-        const CdefBlk b = blk[byl * 8 + bxl];
-        const int s0 = (2 + y) * CDEF_TP + CDEF_X0 + x;
-        int out[BW];
-        const bool on = chroma ? b.do_uv : b.do_y;
-        const int pri = chroma ? b.uv_pri : b.y_pri, sec = chroma ? b.uv_sec : b.y_sec, dir = chroma ? b.uvdir : b.dir;
-        const int gbx = gbx0 + bxl, gby = gby0 + byl;
-        const bool border = gbx == 0 || gby == 0 || gbx == nbx - 1 || gby == nby - 1;
-        if (!on) {
+    const int lane = threadIdx.x & 31, byl = threadIdx.x >> 5;
+    const int bh = 8 >> ssv;
+    if (byl * bh >= th) return;                          // warp-uniform: block rows below the picture
+    const int ppr_log2 = 5 - ssh;                         // pairs per tile row: 32 or 16
+    const int pair = lane & ((1 << ppr_log2) - 1), rsub = lane >> ppr_log2, rows_per_it = 1 << ssh;
+    const int x = 2 * pair;
+    const CdefBlk b = blk[byl * 8 + (x >> (3 - ssh))];
+    const bool on = (chroma ? b.do_uv : b.do_y) && x < tw;
+    const int pri = on ? (chroma ? b.uv_pri : b.y_pri) : 0, sec = on ? (chroma ? b.uv_sec : b.y_sec) : 0;
+    const int dir = chroma ? b.uvdir : b.dir;
+    // byte offsets of the 12 taps from the centre pair: an odd column offset reads copy B
+    int aoff[12];
+    {
+        const int odd_adj = 2 * (copy_el - 1);
+        auto set = [&](int slot, int d, int k) {
+            int dy, dx;
+            tab::cdef_dir_off(d, k, dy, dx);
+            const int o = 2 * (dy * pitch + dx), adj = (dx & 1) ? odd_adj : 0;
+            aoff[slot] = o + adj; aoff[slot + 1] = adj - o;
+        };
+        set(0, dir, 0); set(2, dir, 1);
+        set(4, (dir + 2) & 7, 0); set(6, (dir + 6) & 7, 0);
+        set(8, (dir + 2) & 7, 1); set(10, (dir + 6) & 7, 1);
+    }
+    const unsigned pri_tap = 4 - ((pri >> bdmin8) & 1);
+    const unsigned wp0 = pri_tap, wp1 = (pri_tap & 3) | 2;
+    const int pshift = pri ? imax(0, damping - ulog2(pri)) : 0, sshift = sec ? damping - ulog2(sec) : 0;
+    const unsigned pthr1 = (unsigned)(pri + 1) * 0x10001u, sthr1 = (unsigned)(sec + 1) * 0x10001u;
+    const unsigned pmask = (0xffffu >> pshift) * 0x10001u, smask = (0xffffu >> sshift) * 0x10001u;
+    const bool clip = pri && sec;
+    const bool any_pri = __any_sync(0xffffffffu, pri != 0), any_sec = __any_sync(0xffffffffu, sec != 0);
+    const int y0r = byl * bh + rsub;                     // first row of this lane, then every rows_per_it-th
+    const int n_rows = bh >> ssh;
+    const bool store = x < tw;
 #pragma unroll
-            for (int i = 0; i < BW; i++) out[i] = tile[s0 + i];
-        } else if (border) {
-#pragma unroll
-            for (int i = 0; i < BW; i++) out[i] = cdef_filter_px(tile + s0 + i, CDEF_TP, pri, sec, dir, damping, bdmin8);
-        } else {
-            cdef_row_packed<NP>(tile, s0, pri, sec, dir, damping, bdmin8, out);
-        }
-        pixel *d = (pixel *)(dbase + (int64_t)(py0 + y) * dstride) + px0 + x;
-        if (BD::hbd) {
-            if (BW == 8) *(uint4 *)d = make_uint4(out[0] | (out[1] << 16), out[2] | (out[3] << 16), out[4] | (out[5] << 16), out[6] | (out[7] << 16));
-            else *(uint2 *)d = make_uint2(out[0] | (out[1] << 16), out[2] | (out[3] << 16));
-        } else {
-            if (BW == 8) *(uint2 *)d = make_uint2(out[0] | (out[1] << 8) | (out[2] << 16) | (out[3] << 24), out[4] | (out[5] << 8) | (out[6] << 16) | (out[7] << 24));
-            else *(unsigned *)d = out[0] | (out[1] << 8) | (out[2] << 16) | (out[3] << 24);
-        }
+    for (int sub = 0; sub < 2; sub++) {
+        if (sub >= n_sub) break;
+        const char *cb = (const char *)((sub ? tile1 : tile0) + (2 + y0r) * pitch + col0 + x);
+        const int row_step = 2 * pitch * rows_per_it;
+        const int64_t ds = sub ? dstride1 : dstride0;
+        uint8_t *d = (sub ? dbase1 : dbase0) + (int64_t)(py0 + y0r) * ds + (int64_t)(px0 + x) * sizeof(pixel);
+        const int64_t dstep = ds * rows_per_it;
+        if (any_pri && any_sec)
+            cdef_rows<BD, true, true>(cb, row_step, n_rows, aoff, wp0, wp1, pthr1, pmask, pshift, sthr1, smask, sshift, clip, d, dstep, store);
+        else if (any_pri)
+            cdef_rows<BD, true, false>(cb, row_step, n_rows, aoff, wp0, wp1, pthr1, pmask, pshift, sthr1, smask, sshift, false, d, dstep, store);
+        else if (any_sec)
+            cdef_rows<BD, false, true>(cb, row_step, n_rows, aoff, wp0, wp1, pthr1, pmask, pshift, sthr1, smask, sshift, false, d, dstep, store);
+        else
+            cdef_rows<BD, false, false>(cb, row_step, n_rows, aoff, wp0, wp1, pthr1, pmask, pshift, sthr1, smask, sshift, false, d, dstep, store);
     }
 }
 
+// 8-bit pictures: tiles widened to 16 bits by cdef_stage2, one plane at a time through one buffer.
 template <typename BD>
 __global__ void __launch_bounds__(256)
 cdef_filter_frame_kernel(Rb200Planes src, Rb200Planes dst, CdefFrameParams P, const CdefBlk *__restrict__ blocks, int nbx,
@@ -433,23 +435,95 @@ cdef_filter_frame_kernel(Rb200Planes src, Rb200Planes dst, CdefFrameParams P, co
         if (bx < nbx && by < nby) b = blocks[by * nbx + bx];
         blk[threadIdx.x] = b;
     }
-    cdef_stage2<BD>(tile, (const uint8_t *)src.data[0], src.stride[0], x0, y0, tw, th, fw, fh);
-    __syncthreads();
-    cdef_filter_plane<BD, 8>(tile, blk, (uint8_t *)dst.data[0], dst.stride[0], x0, y0, tw, th, 3, false, P.damping, P.bdmin8,
-                             nbx, nby, sbx * 8, sby * 8);
-    for (int p = 1; p < P.n_planes; p++) {
+    for (int p = 0; p < P.n_planes; p++) {
+        if (p) __syncthreads();
+        const int ssh = p ? P.ss_hor : 0, ssv = p ? P.ss_ver : 0;
+        cdef_stage2<BD>(tile, (const uint8_t *)plane_ptr(src, p), plane_stride(src, p), x0 >> ssh, y0 >> ssv, tw >> ssh, th >> ssv, fw >> ssh, fh >> ssv);
         __syncthreads();
-        const int cx0 = x0 >> P.ss_hor, cy0 = y0 >> P.ss_ver;
-        const int ctw = tw >> P.ss_hor, cth = th >> P.ss_ver, cfw = fw >> P.ss_hor, cfh = fh >> P.ss_ver;
-        cdef_stage2<BD>(tile, (const uint8_t *)src.data[p], src.stride[p], cx0, cy0, ctw, cth, cfw, cfh);
-        __syncthreads();
-        if (P.ss_hor)
-            cdef_filter_plane<BD, 4>(tile, blk, (uint8_t *)dst.data[p], dst.stride[p], cx0, cy0, ctw, cth, 3 - P.ss_ver, true,
-                                     P.damping - 1, P.bdmin8, nbx, nby, sbx * 8, sby * 8);
-        else
-            cdef_filter_plane<BD, 8>(tile, blk, (uint8_t *)dst.data[p], dst.stride[p], cx0, cy0, ctw, cth, 3, true,
-                                     P.damping - 1, P.bdmin8, nbx, nby, sbx * 8, sby * 8);
+        cdef_filter_tiles<BD>((const uint16_t *)tile, nullptr, (uint8_t *)plane_ptr(dst, p), nullptr, plane_stride(dst, p), 0, 1, CDEF_TP, CDEF_COPY, CDEF_X0, blk, x0 >> ssh, y0 >> ssv, tw >> ssh, th >> ssv, ssh, ssv,
+                              p != 0, P.damping - (p ? 1 : 0), P.bdmin8);
     }
+}
+
+// 16-bit pictures: the tiles are fetched by the copy engine.  Per plane one box of (tile + 16) x (tile + 4) pixels at
+// (x0 - 8, y0 - 2) -- the copy engine wants the first column of a box 16-byte aligned, hence 8 columns of halo where
+// the taps reach 2 -- lands in shared memory as dense rows (copy A); all three are requested by one thread at kernel
+// start.  What lies outside the picture arrives as zeros and is overwritten with the reference's "unavailable" sentinel
+// by the (few) CTAs on the picture border.  Copy B (one pixel to the left, so that odd column offsets are aligned words
+// too) is made from copy A in shared memory: one funnel shift per word.
+struct CdefTmaGeom {                     // (scalars, not arrays: a run-time index into a kernel parameter costs a local copy)
+    int pitch_y, rows_y, copy_y;         // luma tile geometry (pixels / elements)
+    int pitch_c, rows_c, copy_c;         // chroma
+    int off_y, off_u, off_v;             // byte offset of a plane's copy A in dynamic shared memory
+};
+constexpr int CDEF_TMA_X0 = 8;
+__device__ __forceinline__ void cdef_patch_outside(uint16_t *tile, int pitch, int rows, int x0, int y0, int fw, int fh) {
+    for (int i = threadIdx.x; i < rows * pitch; i += blockDim.x) {
+        const int r = i / pitch, c = i - r * pitch;
+        const int y = y0 - 2 + r, x = x0 - CDEF_TMA_X0 + c;
+        if (y < 0 || y >= fh || x < 0 || x >= fw) tile[i] = (uint16_t)CDEF_SENTINEL;
+    }
+}
+__device__ __forceinline__ void cdef_shifted_copy(uint16_t *tile, int n_el, int copy_el) {
+    const unsigned *a = (const unsigned *)tile;
+    unsigned *b = (unsigned *)(tile + copy_el);
+    const int nw = n_el >> 1;
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) b[i] = __funnelshift_r(a[i], i + 1 < nw ? a[i + 1] : 0u, 16);
+}
+template <typename BD>
+__global__ void __launch_bounds__(256, 3)
+cdef_filter_tma_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_u,
+                       const __grid_constant__ CUtensorMap map_v, Rb200Planes dst, CdefFrameParams P, CdefTmaGeom G,
+                       const CdefBlk *__restrict__ blocks, int nbx, int nby, int tile_row_first) {
+    extern __shared__ uint8_t cdef_dyn_smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ CdefBlk blk[64];
+    uint8_t *sm = cdef_dyn_smem + ((128u - (smem_addr(cdef_dyn_smem) & 127u)) & 127u);   // TMA destinations: 128-byte aligned
+    const int sbx = blockIdx.x, sby = tile_row_first + blockIdx.y;
+    const int x0 = sbx * 64, y0 = sby * 64;
+    const int fw = P.bw * 4, fh = P.bh * 4;
+    const int tw = imin(64, fw - x0), th = imin(64, fh - y0);
+    const bool chroma = P.n_planes > 1;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+        const unsigned bytes = 2u * (unsigned)(G.pitch_y * G.rows_y + (chroma ? 2 * G.pitch_c * G.rows_c : 0));
+        mbar_arrive_expect_tx(&bar, bytes);
+        tma_load_2d(sm + G.off_y, &map_y, x0 - CDEF_TMA_X0, y0 - 2, &bar);
+        if (chroma) {
+            const int cx = (x0 >> P.ss_hor) - CDEF_TMA_X0, cy = (y0 >> P.ss_ver) - 2;
+            tma_load_2d(sm + G.off_u, &map_u, cx, cy, &bar);
+            tma_load_2d(sm + G.off_v, &map_v, cx, cy, &bar);
+        }
+    }
+    if (threadIdx.x < 64) {
+        const int bx = sbx * 8 + (threadIdx.x & 7), by = sby * 8 + (threadIdx.x >> 3);
+        CdefBlk b = {};
+        if (bx < nbx && by < nby) b = blocks[by * nbx + bx];
+        blk[threadIdx.x] = b;
+    }
+    __syncthreads();     // barrier initialised, block records visible
+    mbar_wait(&bar, 0);
+    if (x0 == 0 || y0 == 0 || x0 + 64 >= fw || y0 + 64 >= fh) {      // the tile's halo leaves the picture
+        cdef_patch_outside((uint16_t *)(sm + G.off_y), G.pitch_y, G.rows_y, x0, y0, fw, fh);
+        if (chroma) {
+            cdef_patch_outside((uint16_t *)(sm + G.off_u), G.pitch_c, G.rows_c, x0 >> P.ss_hor, y0 >> P.ss_ver, fw >> P.ss_hor, fh >> P.ss_ver);
+            cdef_patch_outside((uint16_t *)(sm + G.off_v), G.pitch_c, G.rows_c, x0 >> P.ss_hor, y0 >> P.ss_ver, fw >> P.ss_hor, fh >> P.ss_ver);
+        }
+        __syncthreads();
+    }
+    cdef_shifted_copy((uint16_t *)(sm + G.off_y), G.pitch_y * G.rows_y, G.copy_y);
+    if (chroma) {
+        cdef_shifted_copy((uint16_t *)(sm + G.off_u), G.pitch_c * G.rows_c, G.copy_c);
+        cdef_shifted_copy((uint16_t *)(sm + G.off_v), G.pitch_c * G.rows_c, G.copy_c);
+    }
+    __syncthreads();
+    cdef_filter_tiles<BD>((const uint16_t *)(sm + G.off_y), nullptr, (uint8_t *)dst.data[0], nullptr, dst.stride[0], 0, 1, G.pitch_y, G.copy_y,
+                          CDEF_TMA_X0, blk, x0, y0, tw, th, 0, 0, false, P.damping, P.bdmin8);
+    if (chroma)
+        cdef_filter_tiles<BD>((const uint16_t *)(sm + G.off_u), (const uint16_t *)(sm + G.off_v), (uint8_t *)dst.data[1], (uint8_t *)dst.data[2],
+                              dst.stride[1], dst.stride[2], 2, G.pitch_c, G.copy_c, CDEF_TMA_X0, blk, x0 >> P.ss_hor, y0 >> P.ss_ver,
+                              tw >> P.ss_hor, th >> P.ss_ver, P.ss_hor, P.ss_ver, true, P.damping - 1, P.bdmin8);
 }
 
 // ---- per-call kernels
@@ -500,9 +574,24 @@ __global__ void cdef_fb_kernel(uint8_t *dst, int64_t stride, const uint8_t *left
     }
 }
 
-// t0 / t1: 64-row tile rows to produce (whole picture: 0, ceil(height / 64))
+// Tensor maps of the three source planes for cdef_filter_tma_kernel (16-bit pictures); the frame context encodes them
+// once, its planes never move.
+int cdef_encode_maps(CUtensorMap maps[3], const Rb200Planes &src, const CdefFrameParams &P) {
+    for (int p = 0; p < P.n_planes; p++) {
+        const int ssh = p ? P.ss_hor : 0, ssv = p ? P.ss_ver : 0;
+        const int r = tma_encode_plane(&maps[p], src.data[p], 2, (P.bw * 4) >> ssh, (P.bh * 4) >> ssv, src.stride[p], (64 >> ssh) + 16,
+                                       (64 >> ssv) + 4);
+        if (r) return r;
+    }
+    for (int p = P.n_planes; p < 3; p++) maps[p] = maps[0];
+    return 0;
+}
+
+// t0 / t1: 64-row tile rows to produce (whole picture: 0, ceil(height / 64)).  maps: cdef_encode_maps() of `src`
+// (16-bit pictures; null = stage with loads).
 int cdef_frame_launch(const Rb200Planes &src, const Rb200Planes &dst, const CdefFrameParams &P,
-                      const Rb200Av1Filter *masks, void *blk_scratch, int bdmax, cudaStream_t st, int t0, int t1) {
+                      const Rb200Av1Filter *masks, void *blk_scratch, int bdmax, cudaStream_t st, int t0, int t1,
+                      const CUtensorMap *maps) {
     const int nbx = P.bw >> 1, nby = P.bh >> 1;
     CdefBlk *blocks = (CdefBlk *)blk_scratch;
     const int by0 = t0 * 8, by1 = imin(t1 * 8, nby);
@@ -511,7 +600,25 @@ int cdef_frame_launch(const Rb200Planes &src, const Rb200Planes &dst, const Cdef
     dim3 grid((P.bw * 4 + 63) / 64, t1 - t0);
     if (bdmax > 255) {
         cdef_dir_frame_kernel<BD16><<<g1, b1, 0, st>>>(src, P, masks, blocks, nbx, nby, by0, by1);
-        cdef_filter_frame_kernel<BD16><<<grid, 256, 0, st>>>(src, dst, P, blocks, nbx, nby, t0);
+        if (maps) {
+            CdefTmaGeom G;
+            G.pitch_y = 64 + 16; G.rows_y = 64 + 4;
+            G.pitch_c = (64 >> P.ss_hor) + 16; G.rows_c = (64 >> P.ss_ver) + 4;
+            G.copy_y = (G.pitch_y * G.rows_y + 63) & ~63;      // copy B starts 128-byte aligned as well
+            G.copy_c = (G.pitch_c * G.rows_c + 63) & ~63;
+            G.off_y = 0; G.off_u = 4 * G.copy_y; G.off_v = G.off_u + 4 * G.copy_c;
+            const int smem = (P.n_planes > 1 ? G.off_v + 4 * G.copy_c : G.off_u) + 128;
+            static int smem_set[64] = {};     // per device: the opt-in above 48 KB (4:4:4) is a per-context function attribute
+            int dev = 0;
+            RB_CUDA(cudaGetDevice(&dev));
+            if (smem > 48 * 1024 && smem > smem_set[dev & 63]) {
+                RB_CUDA(cudaFuncSetAttribute(cdef_filter_tma_kernel<BD16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                smem_set[dev & 63] = smem;
+            }
+            cdef_filter_tma_kernel<BD16><<<grid, 256, smem, st>>>(maps[0], maps[1], maps[2], dst, P, G, blocks, nbx, nby, t0);
+        } else {
+            cdef_filter_frame_kernel<BD16><<<grid, 256, 0, st>>>(src, dst, P, blocks, nbx, nby, t0);
+        }
     } else {
         cdef_dir_frame_kernel<BD8><<<g1, b1, 0, st>>>(src, P, masks, blocks, nbx, nby, by0, by1);
         cdef_filter_frame_kernel<BD8><<<grid, 256, 0, st>>>(src, dst, P, blocks, nbx, nby, t0);

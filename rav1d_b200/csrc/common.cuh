@@ -7,6 +7,8 @@
 
 #include "../../include/rav1d_b200.h"
 
+struct CUtensorMap_st;   // <cuda.h>; tma.cuh
+
 namespace rb200 {
 
 // Bit-depth classes, mirroring the reference's BitDepth trait
@@ -111,7 +113,9 @@ int lf_build_launch(const Rb200LfBlock *d_blocks, int n, int w4, int h4, int sb1
                     cudaStream_t st);
 // blk_scratch: device, 8 bytes per 8x8 luma block ((bw / 2) * (bh / 2) records)
 int cdef_frame_launch(const Rb200Planes &src, const Rb200Planes &dst, const CdefFrameParams &P,
-                      const Rb200Av1Filter *masks, void *blk_scratch, int bdmax, cudaStream_t st, int t0, int t1);
+                      const Rb200Av1Filter *masks, void *blk_scratch, int bdmax, cudaStream_t st, int t0, int t1,
+                      const CUtensorMap_st *maps = nullptr);
+int cdef_encode_maps(CUtensorMap_st maps[3], const Rb200Planes &src, const CdefFrameParams &P);
 int lr_plane_launch(const uint8_t *cdef, const uint8_t *dbl, uint8_t *out, int64_t stride, const LrFrameParams &P,
                     const Rb200Av1Restoration *lrm, int bdmax, cudaStream_t st);
 

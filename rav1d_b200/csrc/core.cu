@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace rb200 {
 
@@ -95,6 +96,35 @@ int DevRect::download(Staging &st) {
 void DevRect::finish(void *host_row0) {
     uint8_t *d = (uint8_t *)host_row0;
     for (int y = 0; y < rows; y++) memcpy(d + (int64_t)y * hstride, hstage + (size_t)y * dpitch, row_bytes);
+}
+
+// ---- tensor maps (tma.cuh).  cuTensorMapEncodeTiled is a driver entry point; it is looked up through the runtime so
+// that the library needs no link-time libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int tma_encode_plane(CUtensorMap *out, const void *base, int elem_bytes, int width, int height, int64_t stride_bytes,
+                     int box_w, int box_h) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        RB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) return set_error(-38, "cuTensorMapEncodeTiled is not available from this driver");
+        fn = (EncodeTiledFn)p;
+    }
+    if (!out || !base || (elem_bytes != 1 && elem_bytes != 2) || width < 1 || height < 1 || box_w < 1 || box_h < 1 || box_w > 256 ||
+        box_h > 256 || ((box_w * elem_bytes) & 15) || (stride_bytes & 15) || ((uintptr_t)base & 15))
+        return set_error(-22, "tma_encode_plane: bad geometry (%d x %d, stride %lld, box %d x %d)", width, height, (long long)stride_bytes, box_w, box_h);
+    const cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)height};
+    const cuuint64_t strides[1] = {(cuuint64_t)stride_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h}, estr[2] = {1, 1};
+    const CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)base, dims, strides,
+                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(-22, "cuTensorMapEncodeTiled failed (%d) for %d x %d, stride %lld, box %d x %d", (int)r, width, height,
+                                            (long long)stride_bytes, box_w, box_h);
+    return 0;
 }
 
 }  // namespace rb200

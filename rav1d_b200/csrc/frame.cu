@@ -18,6 +18,7 @@
 // arrays in the reference's own formats (Av1Filter, level[4], Av1Restoration,
 // packed cf).
 #include "common.cuh"
+#include "tma.cuh"
 #include <new>
 #include <stdio.h>
 #include <stdlib.h>
@@ -70,6 +71,7 @@ struct Rb200Frame {
     cudaStream_t lf_stream;             // records upload + mask build run beside the reconstruction
     cudaEvent_t lf_fork, lf_join;
     void *d_cdef_blk;   // per-8x8 CDEF decisions (direction, strengths), device only
+    CUtensorMap tm_cdef[3]; bool tm_cdef_ok;   // tensor maps of plane set 0 for the CDEF tile loads (16-bit pictures)
     int *d_counters;    // work dispensers of the batch kernels (one int each)
     int band_s0, band_s1;   // loop-restoration stripes this context produces (0, 0 = whole picture)
     size_t n_masks, n_lvl;
@@ -85,6 +87,9 @@ struct Rb200Frame {
     uint8_t *plane_mem_fg; Rb200Planes planes_fg, display;
     // optional per-stage timing (the analogue of the reference CLI's --frametimes, tools/dav1d.rs:127-150)
     cudaStream_t own_stream;
+    cudaEvent_t done_event;     // recorded behind the last kernel of every submit (what rb200_frame_depend waits for)
+    cudaEvent_t dep_events[8];  // rb200_frame_depend: the producers' done events, waited for by the next submit
+    int n_deps;
     bool timing;
     cudaEvent_t ev[RB200_N_FRAME_MARKS];
     bool ev_valid[RB200_N_FRAME_MARKS];
@@ -199,6 +204,8 @@ extern "C" int rb200_frame_create(Rb200Frame **out, const Rb200FrameHeader *hdr,
     cudaError_t e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { r = cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); delete f; return r; }
     f->own_stream = f->stream;
+    e = cudaEventCreateWithFlags(&f->done_event, cudaEventDisableTiming);
+    if (e != cudaSuccess) r = cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__);
     for (int i = 0; i < 3 && !r; i++) r = alloc_planes(f, i);
     for (int i = 0; i < 3 && !r && f->sr; i++) r = alloc_sr_planes(f, i);
     if (!r) {
@@ -218,6 +225,12 @@ extern "C" int rb200_frame_create(Rb200Frame **out, const Rb200FrameHeader *hdr,
     if (!r) { e = cudaMalloc(&f->d_cdef_blk, (size_t)(g.bw >> 1) * (g.bh >> 1) * 8 + 64); if (e != cudaSuccess) r = cuda_fail(e, "cudaMalloc", __FILE__, __LINE__); }
     if (!r) { e = cudaMalloc((void **)&f->d_counters, 64); if (e != cudaSuccess) r = cuda_fail(e, "cudaMalloc", __FILE__, __LINE__); }
     if (!r) { e = cudaStreamSynchronize(f->stream); if (e != cudaSuccess) r = cuda_fail(e, "sync", __FILE__, __LINE__); }
+    if (!r && hdr->bpc > 8) {
+        CdefFrameParams P = {};
+        P.bw = g.bw; P.bh = g.bh; P.ss_hor = g.ss_hor; P.ss_ver = g.ss_ver; P.n_planes = g.n_planes;
+        r = cdef_encode_maps(f->tm_cdef, f->planes[0], P);
+        f->tm_cdef_ok = !r;
+    }
     if (r) { rb200_frame_destroy(f); return r; }
     f->out = f->planes[0];
     f->display = f->out;
@@ -282,6 +295,7 @@ extern "C" int rb200_frame_destroy(Rb200Frame *f) {
     if (f->h_lr) cudaFreeHost(f->h_lr);
     if (f->d_lr) cudaFree(f->d_lr);
     if (f->d_cdef_blk) cudaFree(f->d_cdef_blk);
+    if (f->done_event) cudaEventDestroy(f->done_event);
     if (f->own_stream) cudaStreamDestroy(f->own_stream);
     delete f;
     return 0;
@@ -539,6 +553,14 @@ extern "C" int rb200_frame_set_stream(Rb200Frame *f, void *stream) {
     if (!f) return set_error(-22, "frame_set_stream: null frame");
     RB_CUDA(cudaStreamSynchronize(f->stream));
     f->stream = stream ? (cudaStream_t)stream : f->own_stream;
+    return 0;
+}
+
+extern "C" int rb200_frame_depend(Rb200Frame *f, Rb200Frame *producer) {
+    if (!f || !producer) return set_error(-22, "frame_depend: null frame");
+    if (f == producer || f->stream == producer->stream) return 0;   // one stream: already ordered
+    if (f->n_deps >= 8) return set_error(-22, "frame_depend: more than 8 producers before a submit");
+    f->dep_events[f->n_deps++] = producer->done_event;
     return 0;
 }
 
@@ -952,6 +974,9 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
             RB_CUDA(cudaMemcpyAsync(f->d_lr, f->h_lr, f->n_masks * sizeof(Rb200Av1Restoration), cudaMemcpyHostToDevice, st));
     }
 
+    // producers named with rb200_frame_depend: the batch uploads above do not touch pictures and stay ahead of the wait
+    for (int i = 0; i < f->n_deps; i++) RB_CUDA(cudaStreamWaitEvent(st, f->dep_events[i], 0));
+    f->n_deps = 0;
     MARK(1);
     int r;
     if (build_lf) {
@@ -1046,7 +1071,8 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         P.n_planes = g.n_planes; P.bdmin8 = h.bpc - 8; P.damping = h.cdef_damping + P.bdmin8;
         for (int i = 0; i < 8; i++) { P.y_strength[i] = h.cdef_y_strength[i]; P.uv_strength[i] = h.cdef_uv_strength[i]; }
         P.layout_422 = h.layout == RB200_LAYOUT_I422;
-        if ((r = cdef_frame_launch(f->planes[0], f->planes[1], P, f->d_masks, f->d_cdef_blk, f->bdmax, st, band.t0, band.t1))) return r;
+        if ((r = cdef_frame_launch(f->planes[0], f->planes[1], P, f->d_masks, f->d_cdef_blk, f->bdmax, st, band.t0, band.t1,
+                                   f->tm_cdef_ok ? f->tm_cdef : nullptr))) return r;
         f->launches += 2;
         f->out = f->planes[1];
     }
@@ -1109,6 +1135,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
     }
     MARK(7);
 #undef MARK
+    RB_CUDA(cudaEventRecord(f->done_event, st));   // a read-back queued after this does not hold consumers up
     return 0;
 }
 static_assert(sizeof(Rb200WarpItem) == 48 && sizeof(Rb200CompItem) == 32 && sizeof(Rb200McItem) == 16 && sizeof(Rb200ItxItem) == 16 && sizeof(Rb200McScaledItem) == 32 && sizeof(Rb200IntraItem) == 16 && sizeof(Rb200LfBlock) == 16, "batch record sizes");

@@ -7,7 +7,10 @@ import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
-hdr = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+hdrs = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+which = int(sys.argv[3]) if len(sys.argv) > 3 else len(hdrs) - 1      # several launches in one export: the last one by default
+hdr = hdrs[which]
+rows = rows[:hdrs[which + 1]] if which + 1 < len(hdrs) else rows
 h = rows[hdr]
 data = [r for r in rows[hdr + 1:] if len(r) == len(h) and r[h.index("Instructions Executed")].isdigit()]
 S, I, W = h.index("Source"), h.index("Instructions Executed"), h.index("Warp Stall Sampling (All Samples)")
