@@ -84,8 +84,15 @@ struct LrFrameParams {
 int coef_gather_launch(const void *h_cf, void *d_cf, const Rb200ItxItem *d_items, int n, int bdmax, cudaStream_t st);
 int itx_launch(int tx, const Rb200Planes &planes, const void *cf, const Rb200ItxItem *items, int n, int bdmax,
                cudaStream_t st);
+// Tensor maps of up to 8 x 3 reference planes (mc.cu: McTmaMaps) and what each was encoded for; zero-initialise.
+struct alignas(64) McRefMapCache {
+    unsigned char maps[24 * 128];
+    const void *base[24]; int64_t stride[24]; int w[24], h[24];
+    unsigned mask;
+};
 int mc_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int ss_hor,
-                    int ss_ver, const Rb200McItem *d_items, int n, int bdmax, cudaStream_t st, int *counter = nullptr);
+                    int ss_ver, const Rb200McItem *d_items, int n, int bdmax, cudaStream_t st, int *counter = nullptr,
+                    McRefMapCache *map_cache = nullptr);
 int mc_comp_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int layout,
                          const Rb200CompItem *d_items, int n, int bdmax, cudaStream_t st);
 int mc_warp_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int layout,

@@ -71,7 +71,8 @@ struct Rb200Frame {
     cudaStream_t lf_stream;             // records upload + mask build run beside the reconstruction
     cudaEvent_t lf_fork, lf_join;
     void *d_cdef_blk;   // per-8x8 CDEF decisions (direction, strengths), device only
-    CUtensorMap tm_cdef[3]; bool tm_cdef_ok;   // tensor maps of plane set 0 for the CDEF tile loads (16-bit pictures)
+    CUtensorMap tm_cdef[3]; bool tm_cdef_ok;
+    rb200::McRefMapCache tm_refs;      // tensor maps of the reference planes for the prediction kernel's window fetches   // tensor maps of plane set 0 for the CDEF tile loads (16-bit pictures)
     int *d_counters;    // work dispensers of the batch kernels (one int each)
     int band_s0, band_s1;   // loop-restoration stripes this context produces (0, 0 = whole picture)
     size_t n_masks, n_lvl;
@@ -989,7 +990,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
     if (stages & RB200_STAGE_RECON) {
         if (n_mc) {
             if ((r = mc_batch_launch(f->planes[0], f->refs, f->n_refs, h.width, h.height, g.ss_hor, g.ss_ver, f->d_mc,
-                                     n_mc, f->bdmax, st, f->d_counters))) return r;
+                                     n_mc, f->bdmax, st, f->d_counters, &f->tm_refs))) return r;
             f->launches++;
         }
         if (f->n_comp) {

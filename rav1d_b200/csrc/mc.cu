@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "tables.cuh"
 #include "wedge.cuh"
+#include "tma.cuh"
 #include <mutex>
 #include <utility>
 
@@ -190,11 +191,13 @@ __device__ void mc_tile(McSmem &sm, const McRef ref, int sx, int sy, int w, int 
 // reference (free); windows that leave it horizontally are staged with the clamped per-pixel
 // gather (emu_edge, src/mc.rs:1032-1112) into the same layout.
 constexpr int MCF_WROWS = 24;   // window rows (16 + 7, rounded to pairs)
-constexpr int MCF_WPW = 13;     // words per window row (26 pixels >= 1 + 23 + 1), odd: rows spread over banks
+constexpr int MCF_WPW = 20;     // words per window row = the TMA box width of 40 pixels (7 of alignment + 23 + spare); row
+                                // pairs are 40 words apart, so the 4 row pairs x 8 column pairs a warp reads at once hit 32 banks
+constexpr int MCF_TMA_W = 2 * MCF_WPW, MCF_TMA_H = MCF_WROWS;   // box of the reference-plane tensor maps (16-bit pixels)
 constexpr int MCF_MPW = 17;     // words per row pair of the intermediate
 
 struct McFastSmem {
-    uint32_t win[2][MCF_WROWS * MCF_WPW];       // double buffered: the next item's window streams in during the arithmetic
+    __align__(128) uint32_t win[2][MCF_WROWS * MCF_WPW];   // double buffered: the next item's window streams in during the arithmetic (TMA destination: 128-byte aligned)
     uint32_t midv[(MCF_WROWS / 2) * MCF_MPW];   // [row pair][column] = (mid[2j][c], mid[2j + 1][c])
     __align__(16) uint16_t out[MC_TILE * MC_TILE];
 };
@@ -482,7 +485,7 @@ struct McRefSet {
 #define MC_BATCH_CTAS 6      // resident CTAs per SM the batch kernel is compiled for (register budget 80)
 #endif
 struct McJob {
-    int dst_x, dst_y, src_x, src_y, w, h, plane, mx, my, filter2d;
+    int dst_x, dst_y, src_x, src_y, w, h, plane, slot, mx, my, filter2d;
     McRef ref;
     McWin W;      // first tile
     bool fast;
@@ -495,6 +498,7 @@ __device__ __forceinline__ McJob mc_load_job(const Rb200McItem *__restrict__ ite
     j.src_x = (int)(short)(q.y & 0xffff); j.src_y = (int)q.y >> 16;
     j.w = q.z & 0xff; j.h = (q.z >> 8) & 0xff; j.plane = (q.z >> 16) & 0xff;
     const int slot = (q.z >> 24) & 7;
+    j.slot = slot;
     j.mx = q.w & 0xff; j.my = (q.w >> 8) & 0xff; j.filter2d = (q.w >> 16) & 0xff;
     const Rb200Planes &rp = refs.p[slot];
     j.ref.base = plane_ptr(rp, j.plane);
@@ -519,24 +523,50 @@ struct __align__(16) McJobS {
     int rw, rh, src_x, src_y;
     int w, h, phase /* mx | my << 8 | filter2d << 16 | fast << 24 */, xs;
     int ys, ncols, nrows2, xa;
-    int par, nw, flags /* fh | fv << 1 | inside << 2 */, pad;
+    int par, nw, flags /* fh | fv << 1 | inside << 2 */, map /* tensor map of the reference plane (slot * 3 + plane), -1: none */;
 };
+// Tensor maps of the reference planes, [slot * 3 + plane], boxes of MCF_TMA_W x MCF_TMA_H pixels (16-bit pictures).
+struct McTmaMaps { CUtensorMap m[24]; };
 static_assert(sizeof(McJobS) == 96, "six 128-bit words");
 
 template <typename BD>
 __global__ void __launch_bounds__(MC_WARPS * 32, MC_BATCH_CTAS)
 mc_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int ss_hor, int ss_ver,
-                const Rb200McItem *__restrict__ items, int n_items, int bdmax, int *__restrict__ chunk_counter, int chunk) {
+                const Rb200McItem *__restrict__ items, int n_items, int bdmax, int *__restrict__ chunk_counter, int chunk,
+                const __grid_constant__ McTmaMaps maps, unsigned tma_mask) {
     __shared__ struct { McFastSmem fast; McSmem slow; } smem[MC_WARPS];   // not a union: a prefetch may be in flight
+    __shared__ __align__(8) uint64_t tma_bar[MC_WARPS][2];                // one per window buffer of each warp
     __shared__ McJobS jobs[MC_WARPS][MC_CHUNK];
     __shared__ uint32_t raw8_s[BD::hbd ? 1 : MC_WARPS][2][BD::hbd ? 1 : MCF_WROWS * MCF_RAW8_WPR];   // 8-bit only
     uint32_t (*raw8)[BD::hbd ? 1 : MCF_WROWS * MCF_RAW8_WPR] = raw8_s[BD::hbd ? 0 : threadIdx.x >> 5];
-    auto stage_first = [&](int b, const McRef &ref, const McWin &W) {
+    auto stage_first_gather = [&](int b, const McRef &ref, const McWin &W) {
         if (!BD::hbd && mc_raw8_ok(ref, W)) mc_stage8_async(raw8[b], ref, W);
         else mc_stage<BD>(smem[threadIdx.x >> 5].fast.win[b], ref, W);
     };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     McFastSmem &sm = smem[warp].fast;
+    // Windows that lie inside the reference are fetched by the copy engine: lane 0 names the box (first column rounded
+    // down to a 16-byte boundary of the plane, MCF_TMA_W x MCF_TMA_H pixels) and the warp later waits on the buffer's
+    // mbarrier; no lane computes an address.  Windows that reach over the picture edge need replicated pixels, which
+    // the copy engine does not make (it fills with zeros): those keep the clamped gather of mc_stage.
+    unsigned tma_phase = 0;                                   // bit b: parity the next wait on buffer b's barrier uses
+    if (BD::hbd && tma_mask) {
+        if (lane == 0) { mbar_init(&tma_bar[warp][0], 1); mbar_init(&tma_bar[warp][1], 1); mbar_fence_init(); }
+        __syncwarp();
+    }
+    auto tma_window = [&](int map, const McWin &W, int rh) { return BD::hbd && map >= 0 && W.inside && W.ys >= 0 && W.ys + W.nrows2 <= rh; };
+    auto tma_issue = [&](int b, int map, const McWin &W) {
+        fence_proxy_async_smem();      // this lane's earlier writes to the buffer (a gathered window) are ordered before the engine's
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&tma_bar[warp][b], MCF_TMA_W * MCF_TMA_H * 2);
+            tma_load_2d(sm.win[b], &maps.m[map], W.xs & ~7, W.ys, &tma_bar[warp][b]);
+        }
+    };
+    auto tma_wait = [&](int b) {
+        mbar_wait(&tma_bar[warp][b], (tma_phase >> b) & 1u);
+        tma_phase ^= 1u << b;
+    };
     auto read_job = [&](int k) {
         McJobS J;
         const uint4 *p = (const uint4 *)&jobs[warp][k];
@@ -572,27 +602,32 @@ mc_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int ss_hor
             J.src_x = j.src_x; J.src_y = j.src_y; J.w = j.w; J.h = j.h;
             J.phase = j.mx | (j.my << 8) | (j.filter2d << 16) | ((int)j.fast << 24);
             J.xs = j.W.xs; J.ys = j.W.ys; J.ncols = j.W.ncols; J.nrows2 = j.W.nrows2; J.xa = j.W.xa; J.par = j.W.par; J.nw = j.W.nw;
-            J.flags = (int)j.W.fh | ((int)j.W.fv << 1) | ((int)j.W.inside << 2); J.pad = 0;
+            J.flags = (int)j.W.fh | ((int)j.W.fv << 1) | ((int)j.W.inside << 2);
+            J.map = ((tma_mask >> (j.slot * 3 + j.plane)) & 1u) ? j.slot * 3 + j.plane : -1;
             jobs[warp][lane] = J;
         }
         __syncwarp();
+        auto stage_first = [&](int b, const McJobS &J) {
+            if (!(J.phase >> 24)) return;
+            const McWin W = win_of(J);
+            if (tma_window(J.map, W, J.rh)) tma_issue(b, J.map, W);
+            else stage_first_gather(b, ref_of(J), W);
+        };
         int buf = 0;
-        {
-            const McJobS first = read_job(0);
-            if (first.phase >> 24) stage_first(0, ref_of(first), win_of(first));
-        }
+        stage_first(0, read_job(0));
         cp_async_commit();
         for (int k = 0; k < cnt; k++) {
-            if (k + 1 < cnt) {   // only one prepared job is held in registers at a time
-                const McJobS nxt = read_job(k + 1);
-                if (nxt.phase >> 24) stage_first(buf ^ 1, ref_of(nxt), win_of(nxt));
-            }
+            if (k + 1 < cnt) stage_first(buf ^ 1, read_job(k + 1));   // only one prepared job is held in registers at a time
             cp_async_commit();
-            cp_async_wait<1>();      // the current item's first window has landed
+            cp_async_wait<1>();      // the current item's first window has landed (gathered windows)
             __syncwarp();
             const McJobS cur = read_job(k);
             const int mx = cur.phase & 0xff, my = (cur.phase >> 8) & 0xff, filter2d = (cur.phase >> 16) & 0xff;
             const bool fast = cur.phase >> 24;
+            const bool first_by_tma = fast && tma_window(cur.map, win_of(cur), cur.rh);
+            if (first_by_tma) tma_wait(buf);                          // (windows fetched by the copy engine)
+            // a fetched window starts at the 16-byte boundary at or left of it: skip to the word of pixel xs & ~1
+            const uint32_t *win0 = sm.win[buf] + (first_by_tma ? (cur.xs & 6) >> 1 : 0);
             if (!BD::hbd && fast && mc_raw8_ok(ref_of(cur), win_of(cur))) {   // raw bytes have landed: widen them
                 mc_expand8(sm.win[buf], raw8[buf], win_of(cur));
                 __syncwarp();
@@ -601,11 +636,11 @@ mc_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int ss_hor
                 // the common case: the whole block is the prefetched tile
                 const McWin W = win_of(cur);
                 if (cur.w == 16 && cur.h == 16)
-                    mc_tile_fast<BD, 16, 16>(sm, sm.win[buf], W, 16, 16, 16, 16, mx, my, filter2d, cur.dst, cur.dstride, bdmax);
+                    mc_tile_fast<BD, 16, 16>(sm, win0, W, 16, 16, 16, 16, mx, my, filter2d, cur.dst, cur.dstride, bdmax);
                 else if (cur.w == 8 && cur.h == 8)
-                    mc_tile_fast<BD, 8, 8>(sm, sm.win[buf], W, 8, 8, 8, 8, mx, my, filter2d, cur.dst, cur.dstride, bdmax);
+                    mc_tile_fast<BD, 8, 8>(sm, win0, W, 8, 8, 8, 8, mx, my, filter2d, cur.dst, cur.dstride, bdmax);
                 else
-                    mc_tile_fast<BD, 0, 0>(sm, sm.win[buf], W, cur.w, cur.h, cur.w, cur.h, mx, my, filter2d, cur.dst, cur.dstride, bdmax);
+                    mc_tile_fast<BD, 0, 0>(sm, win0, W, cur.w, cur.h, cur.w, cur.h, mx, my, filter2d, cur.dst, cur.dstride, bdmax);
             } else {
                 const McRef ref = ref_of(cur);
                 for (int ty = 0; ty < cur.h; ty += MC_TILE) {
@@ -614,16 +649,24 @@ mc_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int ss_hor
                         const int tw = imin(MC_TILE, cur.w - tx), th = imin(MC_TILE, cur.h - ty);
                         if (fast) {
                             const McWin W = mc_window(ref, cur.src_x + tx, cur.src_y + ty, tw, th, mx, my, filter2d);
+                            const uint32_t *wt = win0;
                             if (tx | ty) {   // further tiles of a large block: staged in place, not prefetched
-                                mc_stage<BD>(sm.win[buf], ref, W);
-                                cp_async_commit();
-                                cp_async_wait<0>();
+                                if (tma_window(cur.map, W, cur.rh)) {
+                                    tma_issue(buf, cur.map, W);
+                                    tma_wait(buf);
+                                    wt = sm.win[buf] + ((W.xs & 6) >> 1);
+                                } else {
+                                    mc_stage<BD>(sm.win[buf], ref, W);
+                                    cp_async_commit();
+                                    cp_async_wait<0>();
+                                    wt = sm.win[buf];
+                                }
                                 __syncwarp();
                             }
                             if (tw == 16 && th == 16)
-                                mc_tile_fast<BD, 16, 16>(sm, sm.win[buf], W, tw, th, cur.w, cur.h, mx, my, filter2d, o, cur.dstride, bdmax);
+                                mc_tile_fast<BD, 16, 16>(sm, wt, W, tw, th, cur.w, cur.h, mx, my, filter2d, o, cur.dstride, bdmax);
                             else
-                                mc_tile_fast<BD, 0, 0>(sm, sm.win[buf], W, tw, th, cur.w, cur.h, mx, my, filter2d, o, cur.dstride, bdmax);
+                                mc_tile_fast<BD, 0, 0>(sm, wt, W, tw, th, cur.w, cur.h, mx, my, filter2d, o, cur.dstride, bdmax);
                         } else {
                             mc_tile<BD, false>(smem[warp].slow, ref, cur.src_x + tx, cur.src_y + ty, tw, th, cur.w, cur.h, mx, my,
                                                filter2d, o, cur.dstride, bdmax);
@@ -1211,11 +1254,39 @@ int resize_plane_launch(void *dst, int64_t dstride, const void *src, int64_t sst
     return 0;
 }
 
+// Tensor maps of the reference planes for the batch kernel (16-bit pictures).  `cache` remembers what each map was
+// encoded for, so a context whose references did not move re-encodes nothing.  A plane the copy engine cannot address
+// (base or stride not 16-byte aligned: only possible through rb200_mc_batch with foreign planes) gets no map.
+void mc_ref_maps_update(McRefMapCache &c, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int ss_hor, int ss_ver) {
+    static_assert(sizeof(c.maps) == sizeof(McTmaMaps), "McRefMapCache::maps holds a McTmaMaps");
+    McTmaMaps &M = *(McTmaMaps *)c.maps;
+    for (int sl = 0; sl < 8; sl++)
+        for (int p = 0; p < 3; p++) {
+            const int i = sl * 3 + p;
+            const void *base = sl < n_refs ? refs[sl].data[p] : nullptr;
+            const int64_t stride = sl < n_refs ? refs[sl].stride[p] : 0;
+            const int w = p ? (ref_w + ss_hor) >> ss_hor : ref_w, h = p ? (ref_h + ss_ver) >> ss_ver : ref_h;
+            if (c.base[i] == base && c.stride[i] == stride && c.w[i] == w && c.h[i] == h) continue;
+            c.base[i] = base; c.stride[i] = stride; c.w[i] = w; c.h[i] = h;
+            c.mask &= ~(1u << i);
+            if (!base || ((uintptr_t)base & 15) || (stride & 15) || stride <= 0) continue;
+            if (tma_encode_plane(&M.m[i], base, 2, w, h, stride, MCF_TMA_W, MCF_TMA_H) == 0) c.mask |= 1u << i;
+        }
+}
+
 int mc_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int ss_hor,
-                    int ss_ver, const Rb200McItem *d_items, int n, int bdmax, cudaStream_t st, int *counter) {
+                    int ss_ver, const Rb200McItem *d_items, int n, int bdmax, cudaStream_t st, int *counter, McRefMapCache *map_cache) {
     if (n <= 0) return 0;
     McRefSet rs = {};
     for (int i = 0; i < n_refs && i < 8; i++) rs.p[i] = refs[i];
+    McRefMapCache local;
+    if (bdmax > 255) {
+        if (!map_cache) { memset(&local, 0, sizeof(local)); map_cache = &local; }
+        mc_ref_maps_update(*map_cache, refs, n_refs, ref_w, ref_h, ss_hor, ss_ver);
+    }
+    static const McTmaMaps no_maps = {};
+    const McTmaMaps &maps = bdmax > 255 ? *(const McTmaMaps *)map_cache->maps : no_maps;
+    const unsigned tma_mask = bdmax > 255 ? map_cache->mask : 0u;
     { const int r = mc_ensure_packed_taps(st); if (r) return r; }
     // persistent warps: 148 SMs x 6 resident CTAs, capped by the item count
     // chunk size: as large as MC_CHUNK when there is enough work to give every resident warp a few chunks
@@ -1226,8 +1297,8 @@ int mc_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs,
     // counter: chunk dispenser of this launch (4 bytes of device memory owned by the caller, e.g. one per frame
     // context -- launches of different contexts overlap); nullptr = static round-robin
     if (counter) RB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
-    if (bdmax > 255) mc_batch_kernel<BD16><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, ss_hor, ss_ver, d_items, n, bdmax, counter, chunk);
-    else mc_batch_kernel<BD8><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, ss_hor, ss_ver, d_items, n, bdmax, counter, chunk);
+    if (bdmax > 255) mc_batch_kernel<BD16><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, ss_hor, ss_ver, d_items, n, bdmax, counter, chunk, maps, tma_mask);
+    else mc_batch_kernel<BD8><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, ss_hor, ss_ver, d_items, n, bdmax, counter, chunk, maps, tma_mask);
     RB_LAUNCH_CHECK();
     return 0;
 }
