@@ -265,6 +265,7 @@ def run_gpu(args, s, wl):
     main = torch.cuda.Stream()
     one_stream = args.streams == 1           # debugging / ncu launch lists: every context on one CUDA stream
     for d in ctxs:
+        lib.check(lib.frame_set_plane_streams(d.h, args.plane_streams))
         lib.check(lib.frame_set_stream(d.h, C.c_void_p(main.cuda_stream) if one_stream else None))
         submit(d, True)                      # batch becomes resident (not timed)
     rstreams = [main] if one_stream else [torch.cuda.ExternalStream(lib.frame_stream(d.h)) for d in ctxs]
@@ -332,6 +333,7 @@ def run_gpu(args, s, wl):
     buf = (C.c_float * 7)()
     for d in ctxs:
         lib.check(lib.frame_set_stream(d.h, C.c_void_p(main.cuda_stream)))
+        lib.check(lib.frame_set_plane_streams(d.h, 0))     # luma and chroma chains on the one stream as well
     for i in range(FRAMES_PER_STEP):
         frame(i, False)
     barrier()
@@ -354,6 +356,7 @@ def run_gpu(args, s, wl):
     # ---------------- e2e leg: host buffers, the chained stream with N_CTX frames in flight on their own streams
     for d in ctxs:
         lib.check(lib.frame_set_stream(d.h, None))
+        lib.check(lib.frame_set_plane_streams(d.h, args.plane_streams))
     streams = [torch.cuda.ExternalStream(lib.frame_stream(d.h)) for d in ctxs]
     e2e_upload = {"gather": 3, "zerocopy": 2, "copy": 1}[args.coefs]
 
@@ -437,6 +440,7 @@ def run_gpu(args, s, wl):
                 "config": {"workload": desc, "frames_per_step": FRAMES_PER_STEP, "width": w, "height": h, "bpc": bpc,
                            "l2": f"inputs larger than L2: {N_CTX} frame contexts cycled, > {ab['S'] * 4 // 1000000} MB working set each",
                            "frames_in_flight": N_CTX,
+                           "plane_streams": "luma and chroma post-filter chains of a frame on two CUDA streams" if args.plane_streams else "off",
                            "dependency": "every frame predicts from the previous frame's output and waits for it on the device (rb200_frame_depend)"
                                          if stages & 1 else "none (post-filters only)",
                            "lf_metadata": "block records, masks built on the device" if args.lf == "records" else "masks and levels uploaded",
@@ -514,6 +518,7 @@ def main():
     ap.add_argument("--lf", default="masks", choices=["masks", "records"],
                     help="loop-filter metadata: Av1Filter masks + levels uploaded, or per-block records uploaded and the masks built on the device")
     ap.add_argument("--streams", type=int, default=N_CTX, help="resident legs: 1 = every frame context on one CUDA stream (launch lists), otherwise one stream per context")
+    ap.add_argument("--plane-streams", type=int, default=1, help="1 (default): luma and chroma post-filter chains of a frame on two streams; 0: one stream")
     ap.add_argument("--coefs", default="gather", choices=["gather", "zerocopy", "copy"],
                     help="e2e leg, how coefficients cross PCIe: a gather kernel pulls each block's non-zero columns into "
                          "HBM (default); the transforms read pinned memory directly; or the whole buffer is H2D-copied")

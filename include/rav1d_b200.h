@@ -635,6 +635,10 @@ int rb200_frame_set_stream(Rb200Frame *f, void *stream);
  * here before its submit; no host synchronisation.  Up to 8 producers per submit; a no-op when both contexts share a
  * stream. */
 int rb200_frame_depend(Rb200Frame *f, Rb200Frame *producer);
+/* The post-filters of a frame run as a luma chain and a chroma chain on two streams (they only meet at the CDEF
+ * direction search), joined before the submit ends; on by default.  0 = every launch on the frame's one stream, which
+ * is what the per-stage times below need to mean anything. */
+int rb200_frame_set_plane_streams(Rb200Frame *f, int on);
 /* Per-stage device times of the last submit (CUDA events on the frame's stream), the analogue
  * of the reference CLI's --frametimes (tools/dav1d.rs:127-150).  ms[] = H2D, MC, itx, deblock,
  * CDEF, LR, film grain; valid after rb200_frame_wait(). */

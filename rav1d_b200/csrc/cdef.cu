@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "tables.cuh"
 #include "tma.cuh"
+#include "stages.cuh"
 
 namespace rb200 {
 
@@ -422,7 +423,7 @@ __device__ __forceinline__ void cdef_filter_tiles(const uint16_t *tile0, const u
 template <typename BD>
 __global__ void __launch_bounds__(256)
 cdef_filter_frame_kernel(Rb200Planes src, Rb200Planes dst, CdefFrameParams P, const CdefBlk *__restrict__ blocks, int nbx,
-                         int nby, int tile_row_first) {
+                         int nby, int tile_row_first, int plane_mask) {
     __shared__ __align__(16) int16_t tile[2 * CDEF_COPY + 8];
     __shared__ CdefBlk blk[64];
     const int sbx = blockIdx.x, sby = tile_row_first + blockIdx.y;
@@ -435,8 +436,11 @@ cdef_filter_frame_kernel(Rb200Planes src, Rb200Planes dst, CdefFrameParams P, co
         if (bx < nbx && by < nby) b = blocks[by * nbx + bx];
         blk[threadIdx.x] = b;
     }
+    bool first = true;
     for (int p = 0; p < P.n_planes; p++) {
-        if (p) __syncthreads();
+        if (!((plane_mask >> p) & 1)) continue;
+        if (!first) __syncthreads();
+        first = false;
         const int ssh = p ? P.ss_hor : 0, ssv = p ? P.ss_ver : 0;
         cdef_stage2<BD>(tile, (const uint8_t *)plane_ptr(src, p), plane_stride(src, p), x0 >> ssh, y0 >> ssv, tw >> ssh, th >> ssv, fw >> ssh, fh >> ssv);
         __syncthreads();
@@ -474,7 +478,7 @@ template <typename BD>
 __global__ void __launch_bounds__(256, 3)
 cdef_filter_tma_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_u,
                        const __grid_constant__ CUtensorMap map_v, Rb200Planes dst, CdefFrameParams P, CdefTmaGeom G,
-                       const CdefBlk *__restrict__ blocks, int nbx, int nby, int tile_row_first) {
+                       const CdefBlk *__restrict__ blocks, int nbx, int nby, int tile_row_first, int plane_mask) {
     extern __shared__ uint8_t cdef_dyn_smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ CdefBlk blk[64];
@@ -483,13 +487,13 @@ cdef_filter_tma_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_c
     const int x0 = sbx * 64, y0 = sby * 64;
     const int fw = P.bw * 4, fh = P.bh * 4;
     const int tw = imin(64, fw - x0), th = imin(64, fh - y0);
-    const bool chroma = P.n_planes > 1;
+    const bool luma = plane_mask & 1, chroma = P.n_planes > 1 && (plane_mask & 6);
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         mbar_fence_init();
-        const unsigned bytes = 2u * (unsigned)(G.pitch_y * G.rows_y + (chroma ? 2 * G.pitch_c * G.rows_c : 0));
+        const unsigned bytes = 2u * (unsigned)((luma ? G.pitch_y * G.rows_y : 0) + (chroma ? 2 * G.pitch_c * G.rows_c : 0));
         mbar_arrive_expect_tx(&bar, bytes);
-        tma_load_2d(sm + G.off_y, &map_y, x0 - CDEF_TMA_X0, y0 - 2, &bar);
+        if (luma) tma_load_2d(sm + G.off_y, &map_y, x0 - CDEF_TMA_X0, y0 - 2, &bar);
         if (chroma) {
             const int cx = (x0 >> P.ss_hor) - CDEF_TMA_X0, cy = (y0 >> P.ss_ver) - 2;
             tma_load_2d(sm + G.off_u, &map_u, cx, cy, &bar);
@@ -505,21 +509,22 @@ cdef_filter_tma_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_c
     __syncthreads();     // barrier initialised, block records visible
     mbar_wait(&bar, 0);
     if (x0 == 0 || y0 == 0 || x0 + 64 >= fw || y0 + 64 >= fh) {      // the tile's halo leaves the picture
-        cdef_patch_outside((uint16_t *)(sm + G.off_y), G.pitch_y, G.rows_y, x0, y0, fw, fh);
+        if (luma) cdef_patch_outside((uint16_t *)(sm + G.off_y), G.pitch_y, G.rows_y, x0, y0, fw, fh);
         if (chroma) {
             cdef_patch_outside((uint16_t *)(sm + G.off_u), G.pitch_c, G.rows_c, x0 >> P.ss_hor, y0 >> P.ss_ver, fw >> P.ss_hor, fh >> P.ss_ver);
             cdef_patch_outside((uint16_t *)(sm + G.off_v), G.pitch_c, G.rows_c, x0 >> P.ss_hor, y0 >> P.ss_ver, fw >> P.ss_hor, fh >> P.ss_ver);
         }
         __syncthreads();
     }
-    cdef_shifted_copy((uint16_t *)(sm + G.off_y), G.pitch_y * G.rows_y, G.copy_y);
+    if (luma) cdef_shifted_copy((uint16_t *)(sm + G.off_y), G.pitch_y * G.rows_y, G.copy_y);
     if (chroma) {
         cdef_shifted_copy((uint16_t *)(sm + G.off_u), G.pitch_c * G.rows_c, G.copy_c);
         cdef_shifted_copy((uint16_t *)(sm + G.off_v), G.pitch_c * G.rows_c, G.copy_c);
     }
     __syncthreads();
-    cdef_filter_tiles<BD>((const uint16_t *)(sm + G.off_y), nullptr, (uint8_t *)dst.data[0], nullptr, dst.stride[0], 0, 1, G.pitch_y, G.copy_y,
-                          CDEF_TMA_X0, blk, x0, y0, tw, th, 0, 0, false, P.damping, P.bdmin8);
+    if (luma)
+        cdef_filter_tiles<BD>((const uint16_t *)(sm + G.off_y), nullptr, (uint8_t *)dst.data[0], nullptr, dst.stride[0], 0, 1, G.pitch_y, G.copy_y,
+                              CDEF_TMA_X0, blk, x0, y0, tw, th, 0, 0, false, P.damping, P.bdmin8);
     if (chroma)
         cdef_filter_tiles<BD>((const uint16_t *)(sm + G.off_u), (const uint16_t *)(sm + G.off_v), (uint8_t *)dst.data[1], (uint8_t *)dst.data[2],
                               dst.stride[1], dst.stride[2], 2, G.pitch_c, G.copy_c, CDEF_TMA_X0, blk, x0 >> P.ss_hor, y0 >> P.ss_ver,
@@ -592,22 +597,33 @@ int cdef_encode_maps(CUtensorMap maps[3], const Rb200Planes &src, const CdefFram
 int cdef_frame_launch(const Rb200Planes &src, const Rb200Planes &dst, const CdefFrameParams &P,
                       const Rb200Av1Filter *masks, void *blk_scratch, int bdmax, cudaStream_t st, int t0, int t1,
                       const CUtensorMap *maps) {
+    return cdef_planes_launch(src, dst, P, masks, blk_scratch, bdmax, st, t0, t1, maps, 7, 3, nullptr);
+}
+
+int cdef_planes_launch(const Rb200Planes &src, const Rb200Planes &dst, const CdefFrameParams &P, const Rb200Av1Filter *masks,
+                       void *blk_scratch, int bdmax, cudaStream_t st, int t0, int t1, const CUtensorMap *maps, int plane_mask,
+                       int what, int *launches) {
     const int nbx = P.bw >> 1, nby = P.bh >> 1;
     CdefBlk *blocks = (CdefBlk *)blk_scratch;
     const int by0 = t0 * 8, by1 = imin(t1 * 8, nby);
     if (by1 <= by0) return 0;
     dim3 g1((nbx + 31) / 32, (by1 - by0 + 3) / 4), b1(32, 4);
     dim3 grid((P.bw * 4 + 63) / 64, t1 - t0);
-    if (bdmax > 255) {
-        cdef_dir_frame_kernel<BD16><<<g1, b1, 0, st>>>(src, P, masks, blocks, nbx, nby, by0, by1);
-        if (maps) {
+    if (what & 1) {
+        if (bdmax > 255) cdef_dir_frame_kernel<BD16><<<g1, b1, 0, st>>>(src, P, masks, blocks, nbx, nby, by0, by1);
+        else cdef_dir_frame_kernel<BD8><<<g1, b1, 0, st>>>(src, P, masks, blocks, nbx, nby, by0, by1);
+        if (launches) ++*launches;
+    }
+    if ((what & 2) && plane_mask) {
+        if (bdmax > 255 && maps) {
+            const bool luma = plane_mask & 1, chroma = P.n_planes > 1 && (plane_mask & 6);
             CdefTmaGeom G;
             G.pitch_y = 64 + 16; G.rows_y = 64 + 4;
             G.pitch_c = (64 >> P.ss_hor) + 16; G.rows_c = (64 >> P.ss_ver) + 4;
             G.copy_y = (G.pitch_y * G.rows_y + 63) & ~63;      // copy B starts 128-byte aligned as well
             G.copy_c = (G.pitch_c * G.rows_c + 63) & ~63;
-            G.off_y = 0; G.off_u = 4 * G.copy_y; G.off_v = G.off_u + 4 * G.copy_c;
-            const int smem = (P.n_planes > 1 ? G.off_v + 4 * G.copy_c : G.off_u) + 128;
+            G.off_y = 0; G.off_u = luma ? 4 * G.copy_y : 0; G.off_v = G.off_u + 4 * G.copy_c;
+            const int smem = (chroma ? G.off_v + 4 * G.copy_c : G.off_u) + 128;
             static int smem_set[64] = {};     // per device: the opt-in above 48 KB (4:4:4) is a per-context function attribute
             int dev = 0;
             RB_CUDA(cudaGetDevice(&dev));
@@ -615,13 +631,13 @@ int cdef_frame_launch(const Rb200Planes &src, const Rb200Planes &dst, const Cdef
                 RB_CUDA(cudaFuncSetAttribute(cdef_filter_tma_kernel<BD16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
                 smem_set[dev & 63] = smem;
             }
-            cdef_filter_tma_kernel<BD16><<<grid, 256, smem, st>>>(maps[0], maps[1], maps[2], dst, P, G, blocks, nbx, nby, t0);
+            cdef_filter_tma_kernel<BD16><<<grid, 256, smem, st>>>(maps[0], maps[1], maps[2], dst, P, G, blocks, nbx, nby, t0, plane_mask);
+        } else if (bdmax > 255) {
+            cdef_filter_frame_kernel<BD16><<<grid, 256, 0, st>>>(src, dst, P, blocks, nbx, nby, t0, plane_mask);
         } else {
-            cdef_filter_frame_kernel<BD16><<<grid, 256, 0, st>>>(src, dst, P, blocks, nbx, nby, t0);
+            cdef_filter_frame_kernel<BD8><<<grid, 256, 0, st>>>(src, dst, P, blocks, nbx, nby, t0, plane_mask);
         }
-    } else {
-        cdef_dir_frame_kernel<BD8><<<g1, b1, 0, st>>>(src, P, masks, blocks, nbx, nby, by0, by1);
-        cdef_filter_frame_kernel<BD8><<<grid, 256, 0, st>>>(src, dst, P, blocks, nbx, nby, t0);
+        if (launches) ++*launches;
     }
     RB_LAUNCH_CHECK();
     return 0;

@@ -19,6 +19,7 @@
 // packed cf).
 #include "common.cuh"
 #include "tma.cuh"
+#include "stages.cuh"
 #include <new>
 #include <stdio.h>
 #include <stdlib.h>
@@ -88,6 +89,10 @@ struct Rb200Frame {
     uint8_t *plane_mem_fg; Rb200Planes planes_fg, display;
     // optional per-stage timing (the analogue of the reference CLI's --frametimes, tools/dav1d.rs:127-150)
     cudaStream_t own_stream;
+    // luma | chroma post-filter chains on two streams (rb200_frame_set_plane_streams)
+    bool plane_split;
+    cudaStream_t uv_stream;
+    cudaEvent_t uv_fork, uv_dir, uv_join;
     cudaEvent_t done_event;     // recorded behind the last kernel of every submit (what rb200_frame_depend waits for)
     cudaEvent_t dep_events[8];  // rb200_frame_depend: the producers' done events, waited for by the next submit
     int n_deps;
@@ -205,6 +210,7 @@ extern "C" int rb200_frame_create(Rb200Frame **out, const Rb200FrameHeader *hdr,
     cudaError_t e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { r = cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); delete f; return r; }
     f->own_stream = f->stream;
+    f->plane_split = true;
     e = cudaEventCreateWithFlags(&f->done_event, cudaEventDisableTiming);
     if (e != cudaSuccess) r = cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__);
     for (int i = 0; i < 3 && !r; i++) r = alloc_planes(f, i);
@@ -297,6 +303,10 @@ extern "C" int rb200_frame_destroy(Rb200Frame *f) {
     if (f->d_lr) cudaFree(f->d_lr);
     if (f->d_cdef_blk) cudaFree(f->d_cdef_blk);
     if (f->done_event) cudaEventDestroy(f->done_event);
+    if (f->uv_fork) cudaEventDestroy(f->uv_fork);
+    if (f->uv_dir) cudaEventDestroy(f->uv_dir);
+    if (f->uv_join) cudaEventDestroy(f->uv_join);
+    if (f->uv_stream) cudaStreamDestroy(f->uv_stream);
     if (f->own_stream) cudaStreamDestroy(f->own_stream);
     delete f;
     return 0;
@@ -562,6 +572,12 @@ extern "C" int rb200_frame_depend(Rb200Frame *f, Rb200Frame *producer) {
     if (f == producer || f->stream == producer->stream) return 0;   // one stream: already ordered
     if (f->n_deps >= 8) return set_error(-22, "frame_depend: more than 8 producers before a submit");
     f->dep_events[f->n_deps++] = producer->done_event;
+    return 0;
+}
+
+extern "C" int rb200_frame_set_plane_streams(Rb200Frame *f, int on) {
+    if (!f) return set_error(-22, "frame_set_plane_streams: null frame");
+    f->plane_split = on != 0;
     return 0;
 }
 
@@ -1058,11 +1074,30 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
     f->out = f->planes[0];
     if (stages & RB200_STAGE_RECON) MARK(3); else { MARK(2); MARK(3); }
     if (build_lf) RB_CUDA(cudaStreamWaitEvent(st, f->lf_join, 0));
+    // The post-filters never mix planes (only the chroma CDEF wants the luma direction search), so the luma chain and
+    // the chroma chain of a frame run on two streams: each fills the issue slots the other leaves idle.
+    const bool do_sr = f->sr && (stages & RB200_STAGE_SUPER_RES);
+    const bool split = f->plane_split && g.n_planes > 1 && !do_sr && !(f->band_s1 > f->band_s0) && (do_lf || do_cdef || restore_planes);
+    cudaStream_t su = st;
+    if (split) {
+        if (!f->uv_stream) {
+            RB_CUDA(cudaStreamCreateWithFlags(&f->uv_stream, cudaStreamNonBlocking));
+            RB_CUDA(cudaEventCreateWithFlags(&f->uv_fork, cudaEventDisableTiming));
+            RB_CUDA(cudaEventCreateWithFlags(&f->uv_dir, cudaEventDisableTiming));
+            RB_CUDA(cudaEventCreateWithFlags(&f->uv_join, cudaEventDisableTiming));
+        }
+        su = f->uv_stream;
+        RB_CUDA(cudaEventRecord(f->uv_fork, st));
+        RB_CUDA(cudaStreamWaitEvent(su, f->uv_fork, 0));
+    }
     // ---- deblock (in place): all column edges, then all row edges (src/recon.rs:4047-4170)
     if (do_lf) {
-        if ((r = deblock_frame_launch(f->planes[0], g.n_planes, g.w4, g.h4, g.sb128w, g.b4_stride, g.ss_hor, g.ss_ver,
-                                      h.lf_level_u || h.lf_level_v, f->d_masks, f->d_lvl + 32, f->d_lut, f->bdmax, st,
-                                      &f->launches, band.y4b, band.y4e))) return r;
+        const int uv_mask = (h.lf_level_u || h.lf_level_v) && g.n_planes > 1 ? 6 : 0;
+        if ((r = deblock_planes_launch(f->planes[0], g.n_planes, g.w4, g.h4, g.sb128w, g.b4_stride, g.ss_hor, g.ss_ver, split ? 1 : 1 | uv_mask,
+                                       f->d_masks, f->d_lvl + 32, f->d_lut, f->bdmax, st, &f->launches, band.y4b, band.y4e))) return r;
+        if (split && uv_mask &&
+            (r = deblock_planes_launch(f->planes[0], g.n_planes, g.w4, g.h4, g.sb128w, g.b4_stride, g.ss_hor, g.ss_ver, uv_mask, f->d_masks,
+                                       f->d_lvl + 32, f->d_lut, f->bdmax, su, &f->launches, band.y4b, band.y4e))) return r;
     }
     MARK(4);
     // ---- CDEF: cur -> p2 (src/recon.rs:4172-4213)
@@ -1072,9 +1107,21 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         P.n_planes = g.n_planes; P.bdmin8 = h.bpc - 8; P.damping = h.cdef_damping + P.bdmin8;
         for (int i = 0; i < 8; i++) { P.y_strength[i] = h.cdef_y_strength[i]; P.uv_strength[i] = h.cdef_uv_strength[i]; }
         P.layout_422 = h.layout == RB200_LAYOUT_I422;
-        if ((r = cdef_frame_launch(f->planes[0], f->planes[1], P, f->d_masks, f->d_cdef_blk, f->bdmax, st, band.t0, band.t1,
-                                   f->tm_cdef_ok ? f->tm_cdef : nullptr))) return r;
-        f->launches += 2;
+        const CUtensorMap *maps = f->tm_cdef_ok ? f->tm_cdef : nullptr;
+        if (!split) {
+            if ((r = cdef_planes_launch(f->planes[0], f->planes[1], P, f->d_masks, f->d_cdef_blk, f->bdmax, st, band.t0, band.t1, maps, 7, 3,
+                                        &f->launches))) return r;
+        } else {
+            // per-block decisions (direction search on the deblocked luma), then the two filter launches
+            if ((r = cdef_planes_launch(f->planes[0], f->planes[1], P, f->d_masks, f->d_cdef_blk, f->bdmax, st, band.t0, band.t1, maps, 0, 1,
+                                        &f->launches))) return r;
+            RB_CUDA(cudaEventRecord(f->uv_dir, st));
+            RB_CUDA(cudaStreamWaitEvent(su, f->uv_dir, 0));
+            if ((r = cdef_planes_launch(f->planes[0], f->planes[1], P, f->d_masks, f->d_cdef_blk, f->bdmax, st, band.t0, band.t1, maps, 1, 2,
+                                        &f->launches))) return r;
+            if ((r = cdef_planes_launch(f->planes[0], f->planes[1], P, f->d_masks, f->d_cdef_blk, f->bdmax, su, band.t0, band.t1, maps, 6, 2,
+                                        &f->launches))) return r;
+        }
         f->out = f->planes[1];
     }
     MARK(5);
@@ -1082,7 +1129,6 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
     // stripes -- the deblocked picture are upscaled horizontally (rav1d_filter_sbrow_resize src/recon.rs:4215-4281,
     // backup_lpf with resize src/lf_apply.rs:24-141)
     f->out_w = h.width;
-    const bool do_sr = f->sr && (stages & RB200_STAGE_SUPER_RES);
     if (do_sr && ((stages & RB200_STAGE_FILM_GRAIN) || f->band_s1 > f->band_s0))
         return set_error(-38, "frame_submit: super-resolution together with film grain or a band restriction is not implemented");
     if (do_sr) {
@@ -1120,12 +1166,16 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
             const Rb200Planes &dbl = !do_sr ? f->planes[0] : (cdefp.data[p] == f->sr_planes[0].data[p] && !do_cdef ? f->sr_planes[0] : f->sr_planes[1]);
             const Rb200Planes &dst = do_sr ? f->sr_planes[2] : f->planes[2];
             if ((r = lr_plane_launch((const uint8_t *)cdefp.data[p], (const uint8_t *)dbl.data[p],
-                                     (uint8_t *)dst.data[p], dst.stride[p], P, f->d_lr, f->bdmax, st)))
+                                     (uint8_t *)dst.data[p], dst.stride[p], P, f->d_lr, f->bdmax, p ? su : st)))
                 return r;
             f->launches++;
             f->out.data[p] = dst.data[p];
             f->out.stride[p] = dst.stride[p];
         }
+    }
+    if (split) {
+        RB_CUDA(cudaEventRecord(f->uv_join, su));
+        RB_CUDA(cudaStreamWaitEvent(st, f->uv_join, 0));
     }
     MARK(6);
     f->display = f->out;

@@ -16,6 +16,7 @@
 // level), COMPACTS them into a shared-memory list (ballot + prefix) and then filters list entries with full warps --
 // one thread per unit (4 lines), the lines' pixels moved as aligned 4-pixel words.
 #include "common.cuh"
+#include "stages.cuh"
 #include <stdlib.h>
 
 namespace rb200 {
@@ -317,13 +318,20 @@ __global__ void lpf_sb_kernel(uint8_t *dst, int64_t stride, int uv, int dir, uin
 int deblock_frame_launch(const Rb200Planes &pl, int n_planes, int w4, int h4, int sb128w, int b4_stride, int ss_hor,
                          int ss_ver, bool do_uv, const Rb200Av1Filter *masks, const uint8_t (*lvl)[4],
                          const Rb200Av1FilterLUT *lut, int bdmax, cudaStream_t st, int *launches, int y4b, int y4e) {
+    return deblock_planes_launch(pl, n_planes, w4, h4, sb128w, b4_stride, ss_hor, ss_ver, do_uv ? 7 : 1, masks, lvl, lut, bdmax, st,
+                                 launches, y4b, y4e);
+}
+
+int deblock_planes_launch(const Rb200Planes &pl, int n_planes, int w4, int h4, int sb128w, int b4_stride, int ss_hor,
+                          int ss_ver, int plane_mask, const Rb200Av1Filter *masks, const uint8_t (*lvl)[4],
+                          const Rb200Av1FilterLUT *lut, int bdmax, cudaStream_t st, int *launches, int y4b, int y4e) {
     static const int only_dir = getenv("RB200_LF_ONLY_DIR") ? atoi(getenv("RB200_LF_ONLY_DIR")) : -1;   // debugging aid
     for (int dir = 0; dir < 2; dir++) {
         if (only_dir >= 0 && dir != only_dir) continue;
         LfPlaneSet S = {};
         int n = 0, total = 0;
         for (int p = 0; p < n_planes; p++) {
-            if (p && !do_uv) continue;
+            if (!((plane_mask >> p) & 1)) continue;
             LfGeom &g = S.g[n];
             g.uv = p ? 1 : 0;
             g.ss_hor = p ? ss_hor : 0; g.ss_ver = p ? ss_ver : 0;

@@ -1,0 +1,16 @@
+// Stage launchers that take a plane subset (bit p = plane p): the frame path runs the luma and the chroma post-filter
+// chains of a frame on two streams, so that one chain fills the issue slots the other leaves idle.
+#pragma once
+#include "common.cuh"
+
+namespace rb200 {
+
+int deblock_planes_launch(const Rb200Planes &pl, int n_planes, int w4, int h4, int sb128w, int b4_stride, int ss_hor,
+                          int ss_ver, int plane_mask, const Rb200Av1Filter *masks, const uint8_t (*lvl)[4],
+                          const Rb200Av1FilterLUT *lut, int bdmax, cudaStream_t st, int *launches, int y4b, int y4e);
+// what: bit 0 = the per-block decisions (direction search; needs the luma plane), bit 1 = filter the planes of plane_mask
+int cdef_planes_launch(const Rb200Planes &src, const Rb200Planes &dst, const CdefFrameParams &P, const Rb200Av1Filter *masks,
+                       void *blk_scratch, int bdmax, cudaStream_t st, int t0, int t1, const CUtensorMap_st *maps, int plane_mask,
+                       int what, int *launches);
+
+}  // namespace rb200

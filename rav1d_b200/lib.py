@@ -275,6 +275,7 @@ ipc_close_handle = _sig("rb200_ipc_close_handle", _i, _vp)
 enable_peer_access = _sig("rb200_enable_peer_access", _i, _i)
 frame_set_stream = _sig("rb200_frame_set_stream", _i, _vp, _vp)
 frame_depend = _sig("rb200_frame_depend", _i, _vp, _vp)
+frame_set_plane_streams = _sig("rb200_frame_set_plane_streams", _i, _vp, _i)
 frame_enable_timing = _sig("rb200_frame_enable_timing", _i, _vp, _i)
 frame_stage_times = _sig("rb200_frame_stage_times", _i, _vp, C.POINTER(C.c_float))
 frame_last_launches = _sig("rb200_frame_last_launches", _i, _vp)
