@@ -593,8 +593,22 @@ int rb200_frame_stage_planes(Rb200Frame *f, int which, Rb200Planes *out);
  * kernels read the coefficients directly from the pinned staging buffer, column-bounded by
  * Rb200ItxItem.ncols, so only the non-zero part of each block crosses PCIe;
  * RB200_UPLOAD_GATHER_COEF: the same bytes cross PCIe, but a gather kernel pulls each block's leading
- * columns into the device mirror with wide loads first and the transforms read device memory. */
-enum { RB200_UPLOAD_NONE = 0, RB200_UPLOAD_ALL = 1, RB200_UPLOAD_ZERO_COPY_COEF = 2, RB200_UPLOAD_GATHER_COEF = 3 };
+ * columns into the device mirror with wide loads first and the transforms read device memory;
+ * RB200_UPLOAD_GATHER_COEF16 (16-bit pictures): like RB200_UPLOAD_GATHER_COEF, but the coefficients cross PCIe as
+ * int16 from rb200_frame_coef16_buffer() -- half the bytes; the few that do not fit (AV1 allows 18 + bits at 10 / 12 bpc)
+ * travel as {index, value} records in rb200_frame_coef_escapes() and are patched in on the device. */
+enum { RB200_UPLOAD_NONE = 0, RB200_UPLOAD_ALL = 1, RB200_UPLOAD_ZERO_COPY_COEF = 2, RB200_UPLOAD_GATHER_COEF = 3,
+       RB200_UPLOAD_GATHER_COEF16 = 4 };
+/* int16 transport of the coefficients of a 16-bit picture.  The staging has the indexing of rb200_frame_coef_buffer()
+ * (element i of one is element i of the other).  A front end writes it directly -- decode_coefs stores `dq as i16` and
+ * pushes an escape when dq does not fit (src/recon.rs:1417: |dq| < 128 << bitdepth) -- or lets
+ * rb200_frame_pack_coef16 narrow the first n_coefs elements of the int32 staging (it sizes the escape list itself). */
+typedef struct Rb200CoefEscape { uint32_t index; int32_t value; } Rb200CoefEscape;
+int16_t *rb200_frame_coef16_buffer(Rb200Frame *f);           /* [max_coefs], pinned, allocated on first use; NULL: 8-bit picture */
+int rb200_frame_reserve_coef_escapes(Rb200Frame *f, int max_escapes);
+Rb200CoefEscape *rb200_frame_coef_escapes(Rb200Frame *f);
+int rb200_frame_set_coef_escape_count(Rb200Frame *f, int n);
+int rb200_frame_pack_coef16(Rb200Frame *f, size_t n_coefs);
 int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t itx_counts[RB200_N_RECT_TX_SIZES],
                        int n_mc_items, int stages, int upload);
 int rb200_frame_wait(Rb200Frame *f);

@@ -39,6 +39,8 @@ struct Rb200Frame {
     // batch staging: pinned host + device mirror
     size_t max_coefs; int max_itx, max_mc;
     void *h_coef, *d_coef;
+    int16_t *h_coef16;                              // int16 transport of a 16-bit picture's coefficients (allocated on first use)
+    Rb200CoefEscape *h_esc, *d_esc; int max_esc, n_esc;
     Rb200ItxItem *h_itx, *d_itx;
     Rb200McItem *h_mc, *d_mc;
     Rb200CompItem *h_comp, *d_comp; int max_comp, n_comp;
@@ -262,6 +264,9 @@ extern "C" int rb200_frame_destroy(Rb200Frame *f) {
     if (f->fg_join) cudaEventDestroy(f->fg_join);
     if (f->plane_mem_fg) cudaFree(f->plane_mem_fg);
     if (f->h_coef) cudaFreeHost(f->h_coef);
+    if (f->h_coef16) cudaFreeHost(f->h_coef16);
+    if (f->h_esc) cudaFreeHost(f->h_esc);
+    if (f->d_esc) cudaFree(f->d_esc);
     if (f->d_coef) cudaFree(f->d_coef);
     if (f->h_itx) cudaFreeHost(f->h_itx);
     if (f->d_itx) cudaFree(f->d_itx);
@@ -564,6 +569,56 @@ extern "C" int rb200_frame_set_stream(Rb200Frame *f, void *stream) {
     if (!f) return set_error(-22, "frame_set_stream: null frame");
     RB_CUDA(cudaStreamSynchronize(f->stream));
     f->stream = stream ? (cudaStream_t)stream : f->own_stream;
+    return 0;
+}
+
+extern "C" int16_t *rb200_frame_coef16_buffer(Rb200Frame *f) {
+    if (!f || f->cs != 4) return nullptr;
+    if (!f->h_coef16) {
+        if (cudaMallocHost((void **)&f->h_coef16, (f->max_coefs ? f->max_coefs : 1) * sizeof(int16_t)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        memset(f->h_coef16, 0, (f->max_coefs ? f->max_coefs : 1) * sizeof(int16_t));
+    }
+    return f->h_coef16;
+}
+extern "C" int rb200_frame_reserve_coef_escapes(Rb200Frame *f, int max_escapes) {
+    if (!f || max_escapes < 0) return set_error(-22, "frame_reserve_coef_escapes: bad argument");
+    if (max_escapes <= f->max_esc) return 0;
+    RB_CUDA(cudaStreamSynchronize(f->stream));
+    if (f->up_stream) RB_CUDA(cudaStreamSynchronize(f->up_stream));
+    Rb200CoefEscape *h = nullptr, *d = nullptr;
+    RB_CUDA(cudaMallocHost((void **)&h, (size_t)max_escapes * sizeof(Rb200CoefEscape)));
+    cudaError_t e = cudaMalloc((void **)&d, (size_t)max_escapes * sizeof(Rb200CoefEscape));
+    if (e != cudaSuccess) { cudaFreeHost(h); return cuda_fail(e, "cudaMalloc(escapes)", __FILE__, __LINE__); }
+    if (f->n_esc) memcpy(h, f->h_esc, (size_t)f->n_esc * sizeof(Rb200CoefEscape));
+    if (f->h_esc) cudaFreeHost(f->h_esc);
+    if (f->d_esc) cudaFree(f->d_esc);
+    f->h_esc = h; f->d_esc = d; f->max_esc = max_escapes;
+    return 0;
+}
+extern "C" Rb200CoefEscape *rb200_frame_coef_escapes(Rb200Frame *f) { return f ? f->h_esc : nullptr; }
+extern "C" int rb200_frame_set_coef_escape_count(Rb200Frame *f, int n) {
+    if (!f || n < 0 || n > f->max_esc) return set_error(-22, "frame_set_coef_escape_count: bad count");
+    f->n_esc = n;
+    return 0;
+}
+extern "C" int rb200_frame_pack_coef16(Rb200Frame *f, size_t n_coefs) {
+    if (!f || n_coefs > f->max_coefs) return set_error(-22, "frame_pack_coef16: bad argument");
+    if (f->cs != 4) return set_error(-22, "frame_pack_coef16: 8-bit pictures carry int16 coefficients already");
+    int16_t *o = rb200_frame_coef16_buffer(f);
+    if (!o) return set_error(-12, "frame_pack_coef16: out of pinned memory");
+    const int32_t *c = (const int32_t *)f->h_coef;
+    f->n_esc = 0;
+    for (size_t i = 0; i < n_coefs; i++) {
+        const int32_t v = c[i];
+        o[i] = (int16_t)v;
+        if (v != (int16_t)v) {
+            if (f->n_esc == f->max_esc) {
+                const int r = rb200_frame_reserve_coef_escapes(f, f->max_esc ? 2 * f->max_esc : 4096);
+                if (r) return r;
+            }
+            f->h_esc[f->n_esc].index = (uint32_t)i; f->h_esc[f->n_esc].value = v; f->n_esc++;
+        }
+    }
     return 0;
 }
 
@@ -936,7 +991,9 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         if (stages & RB200_STAGE_RECON) {
             if (n_coefs && upload == RB200_UPLOAD_ALL)
                 RB_CUDA(cudaMemcpyAsync(f->d_coef, f->h_coef, n_coefs * f->cs, cudaMemcpyHostToDevice, st));
-            const bool gather = upload == RB200_UPLOAD_GATHER_COEF && n_itx;
+            if (upload == RB200_UPLOAD_GATHER_COEF16 && (f->cs != 4 || !f->h_coef16))
+                return set_error(-22, "frame_submit: RB200_UPLOAD_GATHER_COEF16 needs a 16-bit picture whose rb200_frame_coef16_buffer() was filled");
+            const bool gather = (upload == RB200_UPLOAD_GATHER_COEF || upload == RB200_UPLOAD_GATHER_COEF16) && n_itx;
             if (gather) {
                 // The coefficient gather runs on a high-priority side stream: its CTAs are scheduled ahead of the
                 // stage kernels of other frames, so the PCIe link stays busy, and it overlaps this frame's
@@ -952,8 +1009,14 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
                 RB_CUDA(cudaStreamWaitEvent(f->up_stream, f->up_fork, 0));
                 RB_CUDA(cudaMemcpyAsync(f->d_itx, f->h_itx, (size_t)n_itx * sizeof(Rb200ItxItem), cudaMemcpyHostToDevice, f->up_stream));
                 int rg;
-                if ((rg = coef_gather_launch(f->h_coef, f->d_coef, f->d_itx, n_itx, f->bdmax, f->up_stream))) return rg;
-                f->launches++;
+                if (upload == RB200_UPLOAD_GATHER_COEF16) {
+                    if (f->n_esc)
+                        RB_CUDA(cudaMemcpyAsync(f->d_esc, f->h_esc, (size_t)f->n_esc * sizeof(Rb200CoefEscape), cudaMemcpyHostToDevice, f->up_stream));
+                    if ((rg = coef_gather16_launch(f->h_coef16, (int32_t *)f->d_coef, f->d_itx, n_itx, f->d_esc, f->n_esc, f->up_stream, &f->launches))) return rg;
+                } else {
+                    if ((rg = coef_gather_launch(f->h_coef, f->d_coef, f->d_itx, n_itx, f->bdmax, f->up_stream))) return rg;
+                    f->launches++;
+                }
                 RB_CUDA(cudaEventRecord(f->up_join, f->up_stream));
             } else if (n_itx) {
                 RB_CUDA(cudaMemcpyAsync(f->d_itx, f->h_itx, (size_t)n_itx * sizeof(Rb200ItxItem), cudaMemcpyHostToDevice, st));
@@ -1036,7 +1099,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
             f->launches++;
         }
         MARK(2);
-        if (upload == RB200_UPLOAD_GATHER_COEF && n_itx) RB_CUDA(cudaStreamWaitEvent(st, f->up_join, 0));
+        if ((upload == RB200_UPLOAD_GATHER_COEF || upload == RB200_UPLOAD_GATHER_COEF16) && n_itx) RB_CUDA(cudaStreamWaitEvent(st, f->up_join, 0));
         int off = 0;
         for (int t = 0; t < RB200_N_RECT_TX_SIZES; t++) {
             if (itx_counts[t]) {

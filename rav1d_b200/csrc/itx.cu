@@ -13,6 +13,8 @@
 // so the host buckets items by (size, type).  No tensor cores: this is an
 // integer butterfly network, not a contraction.
 #include "common.cuh"
+#include <stdlib.h>
+#include "stages.cuh"
 #include "itx1d.cuh"
 #include "itx_block.cuh"
 #include <string.h>
@@ -125,11 +127,84 @@ coef_gather_kernel(const coef *__restrict__ h_cf, coef *__restrict__ d_cf, const
     }
 }
 
+// Resident CTAs of the gather kernels: they sit on the device for as long as the link takes to deliver a frame's
+// coefficients, so they should hold as few thread slots as keep the link full (a warp has 2 KB of reads in flight;
+// the link's bandwidth-delay product is ~100 KB).
+static int gather_ctas() {
+    static const int n = getenv("RB200_GATHER_CTAS") ? atoi(getenv("RB200_GATHER_CTAS")) : 148;
+    return n > 0 ? n : 148;
+}
+
 int coef_gather_launch(const void *h_cf, void *d_cf, const Rb200ItxItem *d_items, int n, int bdmax, cudaStream_t st) {
     if (n <= 0) return 0;
-    const int grid = imin((n + 15) / 16, 148 * 4);
+    const int grid = imin((n + 15) / 16, gather_ctas());
     if (bdmax > 255) coef_gather_kernel<int32_t><<<grid, 256, 0, st>>>((const int32_t *)h_cf, (int32_t *)d_cf, d_items, n);
     else coef_gather_kernel<int16_t><<<grid, 256, 0, st>>>((const int16_t *)h_cf, (int16_t *)d_cf, d_items, n);
+    RB_LAUNCH_CHECK();
+    return 0;
+}
+
+// int16 transport: 8 coefficients per 16-byte load over PCIe, two 16-byte stores of int32 into HBM.  One warp per block,
+// two blocks' loads in flight before either is stored, like coef_gather_kernel.
+__global__ void __launch_bounds__(256)
+coef_gather16_kernel(const int16_t *__restrict__ h_cf, int32_t *__restrict__ d_cf, const Rb200ItxItem *__restrict__ items, int n) {
+    const int lane = threadIdx.x & 31;
+    const int n_warps = (int)((gridDim.x * (unsigned)blockDim.x) >> 5);
+    for (int idx = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5); idx < n; idx += 2 * n_warps) {
+        const int16_t *src[2]; int32_t *dst[2]; int count[2]; uint4 v[2][2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int i = idx + k * n_warps;
+            count[k] = 0;
+            if (i >= n) continue;
+            const Rb200ItxItem it = items[i];
+            const int w = tx_w(it.tx), h = tx_h(it.tx), sw = w < 32 ? w : 32, sh = h < 32 ? h : 32;
+            const int nc = it.ncols && it.ncols < sw ? it.ncols : sw;
+            count[k] = nc * sh;
+            src[k] = h_cf + it.cf_off; dst[k] = d_cf + it.cf_off;
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            if (!count[k] || ((uintptr_t)src[k] & 15)) continue;
+            const int n16 = count[k] >> 3;
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+                if (lane + 32 * u < n16) v[k][u] = __ldcs((const uint4 *)src[k] + lane + 32 * u);
+        }
+        auto widen = [](int32_t *d, const uint4 q) {
+            ((int4 *)d)[0] = make_int4((int)(short)(q.x & 0xffff), (int)q.x >> 16, (int)(short)(q.y & 0xffff), (int)q.y >> 16);
+            ((int4 *)d)[1] = make_int4((int)(short)(q.z & 0xffff), (int)q.z >> 16, (int)(short)(q.w & 0xffff), (int)q.w >> 16);
+        };
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            if (!count[k]) continue;
+            if ((uintptr_t)src[k] & 15) {      // (block offsets are multiples of 16 coefficients: not taken in practice)
+                for (int i = lane; i < count[k]; i += 32) dst[k][i] = src[k][i];
+                continue;
+            }
+            const int n16 = count[k] >> 3;
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+                if (lane + 32 * u < n16) widen(dst[k] + 8 * (lane + 32 * u), v[k][u]);
+            for (int i = lane + 64; i < n16; i += 32) widen(dst[k] + 8 * i, __ldcs((const uint4 *)src[k] + i));   // > 512-coefficient prefixes
+            for (int i = n16 * 8 + lane; i < count[k]; i += 32) dst[k][i] = src[k][i];
+        }
+    }
+}
+__global__ void coef_escape_kernel(int32_t *__restrict__ d_cf, const Rb200CoefEscape *__restrict__ esc, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) d_cf[esc[i].index] = esc[i].value;
+}
+
+int coef_gather16_launch(const int16_t *h_cf16, int32_t *d_cf, const Rb200ItxItem *d_items, int n, const Rb200CoefEscape *d_esc,
+                         int n_esc, cudaStream_t st, int *launches) {
+    if (n <= 0) return 0;
+    const int grid = imin((n + 15) / 16, gather_ctas());
+    coef_gather16_kernel<<<grid, 256, 0, st>>>(h_cf16, d_cf, d_items, n);
+    if (launches) ++*launches;
+    if (n_esc > 0) {
+        coef_escape_kernel<<<imin((n_esc + 255) / 256, 148), 256, 0, st>>>(d_cf, d_esc, n_esc);
+        if (launches) ++*launches;
+    }
     RB_LAUNCH_CHECK();
     return 0;
 }

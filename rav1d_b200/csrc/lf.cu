@@ -11,10 +11,9 @@
 //     W[i] = sum_{j=-n..n} x[clip(i + j)], and W[i + 1] = W[i] + x[clip(i + n + 1)] - x[clip(i - n)] -- two adds per
 //     output instead of one add per tap (13 / 7 / 5 taps).
 // Mapping at frame level: within a pass every edge is independent of every other (the filter length is bounded by the
-// transform size on both sides), so a pass is one launch over all planes: all column edges, then all row
-// edges.  A CTA takes a run of candidate 4-pixel units, finds the ones that carry an edge (mask word bit + non-zero
-// level), COMPACTS them into a shared-memory list (ballot + prefix) and then filters list entries with full warps --
-// one thread per unit (4 lines), the lines' pixels moved as aligned 4-pixel words.
+// transform size on both sides), so a pass is one launch over a plane set: all column edges, then all row
+// edges.  A CTA takes a 128x128 area, turns the set bits of its Av1Filter mask words into a compact shared-memory list
+// of edge units (pop counts + one prefix sum) and filters list entries with full warps (see deblock_units_kernel).
 #include "common.cuh"
 #include "stages.cuh"
 #include <stdlib.h>
@@ -97,104 +96,95 @@ __device__ __forceinline__ int lf_edge_wd(int wd, int (&x)[16], int E, int I, in
     }
 }
 
-struct LfGeom {
-    int w4, h4;         // plane size in 4-pixel units that are filtered (luma: f.w4/f.h4; chroma: rounded-up halves)
-    int sb128w;
-    int b4_stride;
+struct LfPlane {
+    uint8_t *base;
+    int64_t stride;
+    int w4, h4;         // plane size in 4-pixel units that are filtered (luma: f.w4 / f.h4; chroma: rounded-up halves)
     int ss_hor, ss_ver; // of this plane
     int lvl_idx;        // byte of level[][4]: luma col 0, luma row 1, u 2, v 3
     int uv;             // 0 luma, 1 chroma
+    int y4_begin, y4_end;   // unit rows processed in this launch (band restriction)
 };
-
-// Filter width index of the edge unit (x4, y4) from the Av1Filter masks, or -1.
-// Luma:   filter_y[dir][a][idx][half] bit b;  chroma: filter_uv[dir][a][idx][half] bit b, where for
-// column edges a = x4 in sb128, bits run over y4; for row edges a = y4 in sb128, bits over x4
-// (the hmask / vmask assembly of src/lf_apply.rs).
-__device__ __forceinline__ int lf_mask_idx(const Rb200Av1Filter *__restrict__ masks, const LfGeom &g, int dir, int x4,
-                                           int y4) {
-    const int shx = 5 - g.ss_hor, shy = 5 - g.ss_ver;
-    const Rb200Av1Filter &m = masks[(y4 >> shy) * g.sb128w + (x4 >> shx)];
-    const int xi = x4 & ((1 << shx) - 1), yi = y4 & ((1 << shy) - 1);
-    // `a` indexes the array, `b` is the bit position along the edge; halves hold 16 >> ss bits each
-    const int a = dir == 0 ? xi : yi, b = dir == 0 ? yi : xi;
-    const int hsh = dir == 0 ? 4 - g.ss_ver : 4 - g.ss_hor;
-    const int half = b >> hsh, bit = b & ((1 << hsh) - 1);
-    if (!g.uv) {
-        if ((m.filter_y[dir][a][2][half] >> bit) & 1) return 2;
-        if ((m.filter_y[dir][a][1][half] >> bit) & 1) return 1;
-        if ((m.filter_y[dir][a][0][half] >> bit) & 1) return 0;
-    } else {
-        if ((m.filter_uv[dir][a][1][half] >> bit) & 1) return 1;
-        if ((m.filter_uv[dir][a][0][half] >> bit) & 1) return 0;
-    }
-    return -1;
-}
-
 struct LfPlaneSet {
-    uint8_t *plane[3];
-    int64_t stride[3];
-    LfGeom g[3];
-    int unit_start[4];   // prefix sums of the unit counts of the planes in this launch
-    int y4_first[3];     // first 4-pixel unit row processed in each plane (band restriction)
+    LfPlane p[3];
     int n_planes;
+    int sb128w, b4_stride;
+    int sby_first;      // first 128-row superblock row of the launch
 };
 
-constexpr int LF_THREADS = 128, LF_CAND = 4;   // candidates examined per thread before the compacted list is filtered
+constexpr int LF_THREADS = 256;
+constexpr int LF_LIST = 3 * 32 * 32;   // edge units of one 128x128 area: luma + two chroma planes (4:4:4 at most)
 
-// DIR 0: column edges -- per line the thread loads the 4 / 8 / 16 pixels straddling the edge as aligned 4-pixel words and
-// writes back only the words the filter may have modified.
-// DIR 1: row edges -- the thread owns 4 adjacent columns; every stencil row is one aligned 4-pixel word.
+// Frame pass, one direction: a CTA takes one 128x128 luma area (and the co-located chroma).
+//  1. Edge list.  The Av1Filter words ARE the list of edges: filter_y[dir][a][idx][half] is a 16-bit word whose bits run
+//     along the edge direction.  A thread takes one (plane, a, half), ORs the words of the filter widths, masks what lies
+//     outside the picture / the band / on the picture border, and the CTA turns the set bits into a compact list of
+//     {x4, y4, width index, plane} (one block-wide prefix sum over the pop counts) -- no per-unit test, no division.
+//  2. Filtering.  Column edges (DIR 0): four lanes per list entry, one LINE each -- the line's 8 / 16 / 32 pixels
+//     straddling the edge as aligned 4-pixel words, only the words the filter may have modified written back.
+//     Row edges (DIR 1): one lane per entry; entries of a mask word are horizontally adjacent units, so every stencil
+//     row is one coalesced run of 4-pixel words.
 template <typename BD, int DIR>
-__global__ void __launch_bounds__(LF_THREADS, 8)
+__global__ void __launch_bounds__(LF_THREADS, DIR ? 3 : 4)
 deblock_units_kernel(LfPlaneSet S, const Rb200Av1Filter *__restrict__ masks, const uint8_t (*__restrict__ lvl)[4],
                      const Rb200Av1FilterLUT *__restrict__ lut, int bdmax) {
     using pixel = typename BD::pixel;
-    __shared__ uint32_t list[LF_THREADS * LF_CAND];   // gid << 10 | level << 2 | width index
-    __shared__ int warp_cnt[LF_THREADS / 32], n_list;
+    __shared__ uint32_t list[LF_LIST];            // x4 | y4 << 12 | idx << 24 | plane << 26
+    __shared__ int warp_tot[LF_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int total = S.unit_start[S.n_planes];
-    auto locate = [&](int gid, int &pi, int &x4, int &y4) {
-        pi = (S.n_planes > 1 && gid >= S.unit_start[1]) ? ((S.n_planes > 2 && gid >= S.unit_start[2]) ? 2 : 1) : 0;
-        const int w4 = pi == 0 ? S.g[0].w4 : (pi == 1 ? S.g[1].w4 : S.g[2].w4);
-        const int u = gid - (pi == 0 ? 0 : (pi == 1 ? S.unit_start[1] : S.unit_start[2]));
-        const int yl = u / w4;
-        x4 = u - yl * w4;
-        y4 = yl + (pi == 0 ? S.y4_first[0] : (pi == 1 ? S.y4_first[1] : S.y4_first[2]));
-    };
-    // ---- 1. which candidate units carry an edge: the mask bit and a non-zero level (own, else the neighbour's)
-    if (tid == 0) n_list = 0;
-    __syncthreads();
-#pragma unroll 1
-    for (int k = 0; k < LF_CAND; k++) {
-        const int gid = (blockIdx.x * LF_CAND + k) * LF_THREADS + tid;
-        uint32_t entry = 0;
-        bool on = false;
-        if (gid < total) {
-            int pi, x4, y4;
-            locate(gid, pi, x4, y4);
-            if (DIR == 0 ? x4 != 0 : y4 != 0) {                 // have_left / have_top
-                const LfGeom &g = pi == 0 ? S.g[0] : (pi == 1 ? S.g[1] : S.g[2]);
-                const int idx = lf_mask_idx(masks, g, DIR, x4, y4);
-                if (idx >= 0) {
-                    const uint8_t(*l)[4] = lvl + (int64_t)y4 * g.b4_stride + x4;
-                    int L = l[0][g.lvl_idx];
-                    if (!L) L = DIR == 0 ? l[-1][g.lvl_idx] : l[-(int64_t)g.b4_stride][g.lvl_idx];
-                    if (L) { on = true; entry = (uint32_t)(k * LF_THREADS + tid) << 10 | (uint32_t)L << 2 | (uint32_t)idx; }
-                }
-            }
+    const int sbx = blockIdx.x, sby = S.sby_first + blockIdx.y;
+    const Rb200Av1Filter &M = masks[sby * S.sb128w + sbx];
+    // ---- 1. edge list
+    // task t: plane pi, position a across the edges, half
+    int n_task[3], t0 = 0, my_pi = -1, my_t = 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        n_task[i] = 0;
+        if (i < S.n_planes) {
+            const LfPlane &P = S.p[i];
+            n_task[i] = 2 * (32 >> (DIR == 0 ? P.ss_hor : P.ss_ver));
+            if (my_pi < 0 && tid < t0 + n_task[i]) { my_pi = i; my_t = tid - t0; }
+            t0 += n_task[i];
         }
-        const unsigned m = __ballot_sync(0xffffffffu, on);
-        if (lane == 0) warp_cnt[warp] = __popc(m);
-        __syncthreads();
-        int base = n_list;
-        for (int w = 0; w < warp; w++) base += warp_cnt[w];
-        if (on) list[base + __popc(m & ((1u << lane) - 1))] = entry;
-        __syncthreads();
-        if (tid == 0) { int t = n_list; for (int w = 0; w < LF_THREADS / 32; w++) t += warp_cnt[w]; n_list = t; }
-        __syncthreads();
     }
-    // ---- 2. filter the compacted list
-    const int n = n_list;
+    unsigned bits = 0, w1 = 0, w2 = 0;
+    int ex4 = 0, ey4 = 0;               // unit of bit 0 of this thread's word; bits advance along y (DIR 0) or x (DIR 1)
+    if (my_pi >= 0) {
+        const LfPlane &P = my_pi == 0 ? S.p[0] : (my_pi == 1 ? S.p[1] : S.p[2]);
+        const int a = my_t >> 1, half = my_t & 1;
+        const int nb = 16 >> (DIR == 0 ? P.ss_ver : P.ss_hor);      // bits per half-word
+        unsigned w0;
+        if (!P.uv) { w0 = M.filter_y[DIR][a][0][half]; w1 = M.filter_y[DIR][a][1][half]; w2 = M.filter_y[DIR][a][2][half]; }
+        else { w0 = M.filter_uv[DIR][a][0][half]; w1 = M.filter_uv[DIR][a][1][half]; w2 = 0; }
+        bits = (w0 | w1 | w2) & ((1u << nb) - 1);
+        const int x4s = sbx << (5 - P.ss_hor), y4s = sby << (5 - P.ss_ver);      // first unit of the area in this plane
+        if (DIR == 0) { ex4 = x4s + a; ey4 = y4s + half * nb; }
+        else { ex4 = x4s + half * nb; ey4 = y4s + a; }
+        // what lies outside the picture or the rows of this launch, and the picture's own border, carries no edge
+        const int along0 = DIR == 0 ? ey4 : ex4, along_lo = DIR == 0 ? P.y4_begin : 0, along_hi = DIR == 0 ? P.y4_end : P.w4;
+        const int lo = imax(along_lo - along0, 0), hi = imin(along_hi - along0, nb);
+        bits = hi > lo ? bits & ((1u << hi) - (1u << lo)) : 0u;
+        const int across = DIR == 0 ? ex4 : ey4;
+        if (across == 0 || across >= (DIR == 0 ? P.w4 : P.h4) || (DIR == 1 && (across < P.y4_begin || across >= P.y4_end))) bits = 0;
+    }
+    // block-wide exclusive prefix sum of the pop counts
+    const int cnt = __popc(bits);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int off = incl - cnt, n = 0;
+#pragma unroll
+    for (int w = 0; w < LF_THREADS / 32; w++) { const int v = warp_tot[w]; if (w < warp) off += v; n += v; }
+    while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const unsigned idx = ((w2 >> b) & 1) ? 2u : ((w1 >> b) & 1);
+        list[off++] = (unsigned)(DIR == 0 ? ex4 : ex4 + b) | (unsigned)(DIR == 0 ? ey4 + b : ey4) << 12 | idx << 24 | (unsigned)my_pi << 26;
+    }
+    __syncthreads();
+    // ---- 2. filter the list
     const int bdmin8 = BD::hbd ? bpc_from_max(bdmax) - 8 : 0;
     constexpr int WPR = BD::hbd ? 2 : 1;            // 32-bit words per 4-pixel group
     auto unpack4 = [](const unsigned *w, int *v) {
@@ -211,40 +201,39 @@ deblock_units_kernel(LfPlaneSet S, const Rb200Av1Filter *__restrict__ masks, con
     auto st4 = [](pixel *p, const unsigned *w) {
         if (BD::hbd) *(uint2 *)p = make_uint2(w[0], w[WPR - 1]); else *(unsigned *)p = w[0];
     };
+    constexpr int LANES_PER_ENTRY = DIR == 0 ? 4 : 1;
 #pragma unroll 1
-    for (int e = tid; e < n; e += LF_THREADS) {
-        const uint32_t entry = list[e];
-        const int gid = blockIdx.x * LF_CAND * LF_THREADS + (int)(entry >> 10), L = (entry >> 2) & 0xff, idx = entry & 3;
-        int pi, x4, y4;
-        locate(gid, pi, x4, y4);
-        const int uv = pi == 0 ? S.g[0].uv : 1;
-        uint8_t *plane = pi == 0 ? S.plane[0] : (pi == 1 ? S.plane[1] : S.plane[2]);
-        const int64_t ps = (pi == 0 ? S.stride[0] : (pi == 1 ? S.stride[1] : S.stride[2])) / (int64_t)sizeof(pixel);
-        pixel *base = (pixel *)plane + (int64_t)(y4 * 4) * ps + x4 * 4;   // q0 of line 0
+    for (int e = tid; e < n * LANES_PER_ENTRY; e += LF_THREADS) {
+        const uint32_t entry = list[DIR == 0 ? e >> 2 : e];
+        const int x4 = entry & 0xfff, y4 = (entry >> 12) & 0xfff, idx = (entry >> 24) & 3, pi = entry >> 26;
+        const LfPlane &P = pi == 0 ? S.p[0] : (pi == 1 ? S.p[1] : S.p[2]);
+        const uint8_t(*l)[4] = lvl + (int64_t)y4 * S.b4_stride + x4;
+        int L = l[0][P.lvl_idx];
+        if (!L) L = DIR == 0 ? l[-1][P.lvl_idx] : l[-(int64_t)S.b4_stride][P.lvl_idx];
+        if (!L) continue;
+        const int64_t ps = P.stride / (int64_t)sizeof(pixel);
+        pixel *base = (pixel *)P.base + (int64_t)(y4 * 4) * ps + x4 * 4;   // q0 of line 0
         const int H = (L >> 4) << bdmin8, E = (int)lut->e[L] << bdmin8, I = (int)lut->i[L] << bdmin8;
-        const int wd = uv ? 4 + 2 * idx : 4 << idx;
+        const int wd = P.uv ? 4 + 2 * idx : 4 << idx;
         const int ng = wd == 16 ? 2 : 1;           // 4-pixel groups on each side of the edge
         if (DIR == 0) {
-#pragma unroll 1
-            for (int line = 0; line < 4; line++) {
-                pixel *p = base + (int64_t)line * ps;
-                unsigned w[4][WPR];
-                int x[16];
-                ld4(p - 4, w[1]); ld4(p, w[2]);
-                if (ng == 2) { ld4(p - 8, w[0]); ld4(p + 4, w[3]); unpack4(w[0], x); unpack4(w[3], x + 12); }
-                unpack4(w[1], x + 4); unpack4(w[2], x + 8);
-                const int m = lf_edge_wd(wd, x, E, I, H, bdmin8, bdmax);
-                if (!m) continue;
-                if (wd == 4) {
-                    // the neighbouring edges may be only 4 pixels away and own p3 / p2 and q2 / q3: write p1 p0 | q0 q1 only
-                    if (BD::hbd) { *(unsigned *)(p - 2) = (unsigned)x[6] | (unsigned)x[7] << 16; *(unsigned *)p = (unsigned)x[8] | (unsigned)x[9] << 16; }
-                    else { *(uint16_t *)(p - 2) = (uint16_t)(x[6] | x[7] << 8); *(uint16_t *)p = (uint16_t)(x[8] | x[9] << 8); }
-                    continue;
-                }
-                // wider filters: both transform blocks are at least 8 (16) pixels, so the 4-pixel words are this edge's alone
-                pack4(x + 4, w[1]); pack4(x + 8, w[2]); st4(p - 4, w[1]); st4(p, w[2]);
-                if (m > 4) { pack4(x, w[0]); pack4(x + 12, w[3]); st4(p - 8, w[0]); st4(p + 4, w[3]); }
+            pixel *p = base + (int64_t)(e & 3) * ps;
+            unsigned w[4][WPR];
+            int x[16];
+            ld4(p - 4, w[1]); ld4(p, w[2]);
+            if (ng == 2) { ld4(p - 8, w[0]); ld4(p + 4, w[3]); unpack4(w[0], x); unpack4(w[3], x + 12); }
+            unpack4(w[1], x + 4); unpack4(w[2], x + 8);
+            const int m = lf_edge_wd(wd, x, E, I, H, bdmin8, bdmax);
+            if (!m) continue;
+            if (wd == 4) {
+                // the neighbouring edges may be only 4 pixels away and own p3 / p2 and q2 / q3: write p1 p0 | q0 q1 only
+                if (BD::hbd) { *(unsigned *)(p - 2) = (unsigned)x[6] | (unsigned)x[7] << 16; *(unsigned *)p = (unsigned)x[8] | (unsigned)x[9] << 16; }
+                else { *(uint16_t *)(p - 2) = (uint16_t)(x[6] | x[7] << 8); *(uint16_t *)p = (uint16_t)(x[8] | x[9] << 8); }
+                continue;
             }
+            // wider filters: both transform blocks are at least 8 (16) pixels, so the 4-pixel words are this edge's alone
+            pack4(x + 4, w[1]); pack4(x + 8, w[2]); st4(p - 4, w[1]); st4(p, w[2]);
+            if (m > 4) { pack4(x, w[0]); pack4(x + 12, w[3]); st4(p - 8, w[0]); st4(p + 4, w[3]); }
         } else {
             // rows y - 4 ng .. y + 4 ng - 1 of the unit's 4 columns, one packed word group per row
             unsigned rows[16][WPR];
@@ -329,29 +318,27 @@ int deblock_planes_launch(const Rb200Planes &pl, int n_planes, int w4, int h4, i
     for (int dir = 0; dir < 2; dir++) {
         if (only_dir >= 0 && dir != only_dir) continue;
         LfPlaneSet S = {};
-        int n = 0, total = 0;
+        int n = 0, y_lo = 1 << 30, y_hi = 0;     // luma unit rows touched by this launch
         for (int p = 0; p < n_planes; p++) {
             if (!((plane_mask >> p) & 1)) continue;
-            LfGeom &g = S.g[n];
-            g.uv = p ? 1 : 0;
-            g.ss_hor = p ? ss_hor : 0; g.ss_ver = p ? ss_ver : 0;
-            g.w4 = (w4 + g.ss_hor) >> g.ss_hor; g.h4 = (h4 + g.ss_ver) >> g.ss_ver;
-            g.sb128w = sb128w; g.b4_stride = b4_stride;
-            g.lvl_idx = p ? 1 + p : dir;
-            S.plane[n] = (uint8_t *)pl.data[p]; S.stride[n] = pl.stride[p];
-            S.unit_start[n] = total;
-            // band in this plane's unit rows; chroma rows round outwards
+            LfPlane &P = S.p[n];
+            P.uv = p ? 1 : 0;
+            P.ss_hor = p ? ss_hor : 0; P.ss_ver = p ? ss_ver : 0;
+            P.w4 = (w4 + P.ss_hor) >> P.ss_hor; P.h4 = (h4 + P.ss_ver) >> P.ss_ver;
+            P.lvl_idx = p ? 1 + p : dir;
+            P.base = (uint8_t *)pl.data[p]; P.stride = pl.stride[p];
+            // band in this plane's unit rows (chroma rows round outwards); the column-edge pass covers two more unit
+            // rows on each side, which is everything the row edges of the band read
             int b = dir ? y4b : y4b - 2, e = dir ? y4e : y4e + 2;
-            b = imax(b >> g.ss_ver, 0); e = imin((e + g.ss_ver) >> g.ss_ver, g.h4);
-            S.y4_first[n] = b;
-            total += g.w4 * imax(e - b, 0);
+            b = imax(b >> P.ss_ver, 0); e = imin((e + P.ss_ver) >> P.ss_ver, P.h4);
+            P.y4_begin = b; P.y4_end = e;
+            if (e > b) { y_lo = imin(y_lo, b << P.ss_ver); y_hi = imax(y_hi, e << P.ss_ver); }
             n++;
         }
-        S.unit_start[n] = total;
-        for (int k = n + 1; k < 4; k++) S.unit_start[k] = total;
-        S.n_planes = n;
-        const int grid = (total + LF_THREADS * LF_CAND - 1) / (LF_THREADS * LF_CAND);
-        if (!grid) continue;
+        S.n_planes = n; S.sb128w = sb128w; S.b4_stride = b4_stride;
+        if (!n || y_hi <= y_lo) continue;
+        S.sby_first = y_lo >> 5;
+        const dim3 grid(sb128w, ((y_hi + 31) >> 5) - S.sby_first);
 #define L(BD, D) deblock_units_kernel<BD, D><<<grid, LF_THREADS, 0, st>>>(S, masks, lvl, lut, bdmax)
         if (bdmax > 255) { if (dir) L(BD16, 1); else L(BD16, 0); } else { if (dir) L(BD8, 1); else L(BD8, 0); }
 #undef L

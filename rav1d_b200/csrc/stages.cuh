@@ -13,4 +13,9 @@ int cdef_planes_launch(const Rb200Planes &src, const Rb200Planes &dst, const Cde
                        void *blk_scratch, int bdmax, cudaStream_t st, int t0, int t1, const CUtensorMap_st *maps, int plane_mask,
                        int what, int *launches);
 
+// int16 coefficient transport (RB200_UPLOAD_GATHER_COEF16): each block's leading columns pulled from the pinned int16
+// staging and widened into the int32 device array, then the escapes patched in
+int coef_gather16_launch(const int16_t *h_cf16, int32_t *d_cf, const Rb200ItxItem *d_items, int n, const Rb200CoefEscape *d_esc,
+                         int n_esc, cudaStream_t st, int *launches);
+
 }  // namespace rb200

@@ -275,6 +275,12 @@ ipc_close_handle = _sig("rb200_ipc_close_handle", _i, _vp)
 enable_peer_access = _sig("rb200_enable_peer_access", _i, _i)
 frame_set_stream = _sig("rb200_frame_set_stream", _i, _vp, _vp)
 frame_depend = _sig("rb200_frame_depend", _i, _vp, _vp)
+UPLOAD_GATHER_COEF16 = 4
+frame_coef16_buffer = _sig("rb200_frame_coef16_buffer", _vp, _vp)
+frame_pack_coef16 = _sig("rb200_frame_pack_coef16", _i, _vp, _sz)
+frame_reserve_coef_escapes = _sig("rb200_frame_reserve_coef_escapes", _i, _vp, _i)
+frame_coef_escapes = _sig("rb200_frame_coef_escapes", _vp, _vp)
+frame_set_coef_escape_count = _sig("rb200_frame_set_coef_escape_count", _i, _vp, _i)
 frame_set_plane_streams = _sig("rb200_frame_set_plane_streams", _i, _vp, _i)
 frame_enable_timing = _sig("rb200_frame_enable_timing", _i, _vp, _i)
 frame_stage_times = _sig("rb200_frame_stage_times", _i, _vp, C.POINTER(C.c_float))

@@ -57,6 +57,8 @@ def product_frame(s, stages, start_planes=None, upload=1):
                 d.set_ref_slot(2, s.ref3, size=s.scaled_ref_size)
         else:
             d.upload(0, start_planes)
+        if upload == lib.UPLOAD_GATHER_COEF16:      # what a front end does when it fills the staging: int16 + escapes
+            lib.check(lib.frame_pack_coef16(d.h, s.n_coefs), "frame_pack_coef16")
         d.submit(stages, upload)
         d.wait()
         return visible(s, d.readback())

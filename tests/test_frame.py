@@ -1,6 +1,8 @@
 """Frame-level parity: the product's stream-ordered stage launches (rb200_frame_*, C ABI)
 against the reference's own frame drivers (dav1d_filter_sbrow_* and the DSP tables, run by
 oracle/ref_frame.c) on the same synthetic frame batch -- stage by stage, then end to end."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -321,6 +323,39 @@ def test_zero_copy_coefficients(rb, ref, w, h, bpc):
     framecheck.assert_planes_equal(a, framecheck.product_frame(s, R | D, upload=2), "zero-copy, ncols unknown")
     framecheck.assert_planes_equal(a, framecheck.product_frame(s, R | D, upload=3), "gather, ncols unknown")
     framecheck.assert_planes_equal(a, framecheck.product_frame(s, R | D, upload=1), "copy, ncols unknown")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,bpc", [(640, 360, 10), (200, 120, 12)])
+def test_int16_coefficient_transport(rb, ref, w, h, bpc):
+    """RB200_UPLOAD_GATHER_COEF16: the coefficients of a 16-bit picture cross PCIe as int16; those that do not fit travel
+    as {index, value} escapes (forced here: real residuals of that size are rare) and are patched in on the device."""
+    s = framegen.generate(w, h, bpc, seed=23)
+    a = framecheck.oracle_frame(ref, s, R | D)
+    framecheck.assert_planes_equal(a, framecheck.product_frame(s, R | D, upload=rb.UPLOAD_GATHER_COEF16), "int16 transport")
+    # large coefficients: every 97th non-zero one pushed to the edge of the legal range (src/recon.rs:1417)
+    lim = 128 << bpc
+    nz = np.flatnonzero(s.coef)[::97]
+    s.coef = s.coef.copy()
+    s.coef[nz] = np.where(s.coef[nz] > 0, lim - 1 - (nz % 1000), -lim + (nz % 1000)).astype(s.coef.dtype)
+    assert (np.abs(s.coef.astype(np.int64)) > 32767).sum() > 50
+    a = framecheck.oracle_frame(ref, s, R | D)
+    framecheck.assert_planes_equal(a, framecheck.product_frame(s, R | D, upload=1), "large coefficients, copy")
+    framecheck.assert_planes_equal(a, framecheck.product_frame(s, R | D, upload=rb.UPLOAD_GATHER_COEF16), "large coefficients, int16 + escapes")
+
+
+@pytest.mark.gpu
+def test_int16_transport_is_refused_for_8bit(rb):
+    s = framegen.generate(64, 64, 8, seed=3)
+    d = framegen.DeviceFrame(s)
+    try:
+        d.load_batch(); d.set_ref_from_host(s.ref)
+        assert not rb.frame_coef16_buffer(d.h)
+        assert rb.frame_pack_coef16(d.h, s.n_coefs) != 0
+        counts = (C.c_int32 * 19)(*[int(c) for c in s.itx_counts])
+        assert rb.frame_submit(d.h, s.n_coefs, counts, len(s.mc_items), R, rb.UPLOAD_GATHER_COEF16) != 0
+    finally:
+        d.close()
 
 
 @pytest.mark.gpu
