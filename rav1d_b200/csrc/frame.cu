@@ -75,6 +75,7 @@ struct Rb200Frame {
     cudaEvent_t lf_fork, lf_join;
     void *d_cdef_blk;   // per-8x8 CDEF decisions (direction, strengths), device only
     CUtensorMap tm_cdef[3]; bool tm_cdef_ok;
+    CUtensorMap tm_lr_main[2][3], tm_lr_halo[3]; bool tm_lr_ok;   // loop-restoration windows: plane sets 0 / 1 (8-row boxes), set 0 (2-row boxes)
     rb200::McRefMapCache tm_refs;      // tensor maps of the reference planes for the prediction kernel's window fetches   // tensor maps of plane set 0 for the CDEF tile loads (16-bit pictures)
     int *d_counters;    // work dispensers of the batch kernels (one int each)
     int band_s0, band_s1;   // loop-restoration stripes this context produces (0, 0 = whole picture)
@@ -239,6 +240,14 @@ extern "C" int rb200_frame_create(Rb200Frame **out, const Rb200FrameHeader *hdr,
         P.bw = g.bw; P.bh = g.bh; P.ss_hor = g.ss_hor; P.ss_ver = g.ss_ver; P.n_planes = g.n_planes;
         r = cdef_encode_maps(f->tm_cdef, f->planes[0], P);
         f->tm_cdef_ok = !r;
+        for (int p = 0; p < g.n_planes && !r && !f->sr; p++) {
+            const int ssh = p ? g.ss_hor : 0, ssv = p ? g.ss_ver : 0;
+            const int pw = (hdr->width + ssh) >> ssh, ph = (hdr->height + ssv) >> ssv;
+            r = lr_encode_maps(&f->tm_lr_main[0][p], &f->tm_lr_halo[p], f->planes[0].data[p], f->planes[0].data[p], f->planes[0].stride[p], pw, ph);
+            CUtensorMap unused;
+            if (!r) r = lr_encode_maps(&f->tm_lr_main[1][p], &unused, f->planes[1].data[p], f->planes[0].data[p], f->planes[1].stride[p], pw, ph);
+        }
+        f->tm_lr_ok = !r && !f->sr;
     }
     if (r) { rb200_frame_destroy(f); return r; }
     f->out = f->planes[0];
@@ -1228,8 +1237,14 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
             // without CDEF the two are the same plane)
             const Rb200Planes &dbl = !do_sr ? f->planes[0] : (cdefp.data[p] == f->sr_planes[0].data[p] && !do_cdef ? f->sr_planes[0] : f->sr_planes[1]);
             const Rb200Planes &dst = do_sr ? f->sr_planes[2] : f->planes[2];
-            if ((r = lr_plane_launch((const uint8_t *)cdefp.data[p], (const uint8_t *)dbl.data[p],
-                                     (uint8_t *)dst.data[p], dst.stride[p], P, f->d_lr, f->bdmax, p ? su : st)))
+            const CUtensorMap *m_main = nullptr, *m_halo = nullptr;     // windows by TMA when the planes are the context's own
+            if (f->tm_lr_ok && !do_sr && dbl.data[p] == f->planes[0].data[p]) {
+                if (cdefp.data[p] == f->planes[1].data[p]) m_main = &f->tm_lr_main[1][p];
+                else if (cdefp.data[p] == f->planes[0].data[p]) m_main = &f->tm_lr_main[0][p];
+                if (m_main) m_halo = &f->tm_lr_halo[p];
+            }
+            if ((r = lr_plane_launch_tma((const uint8_t *)cdefp.data[p], (const uint8_t *)dbl.data[p], (uint8_t *)dst.data[p], dst.stride[p], P,
+                                         f->d_lr, f->bdmax, p ? su : st, m_main, m_halo)))
                 return r;
             f->launches++;
             f->out.data[p] = dst.data[p];

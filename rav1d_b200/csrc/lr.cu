@@ -16,6 +16,8 @@
 // and the deblocked plane is simply still alive.
 #include "common.cuh"
 #include "tables.cuh"
+#include "tma.cuh"
+#include "stages.cuh"
 
 namespace rb200 {
 
@@ -186,26 +188,44 @@ __device__ void lr_sgr_tile(LrSmem &sm, int tw, int th, int kind, unsigned s0, u
 
 
 // ---------------------------------------------------------------- frame level
-// Layout of the frame kernel's shared memory.  Window column e holds picture column
-// x0 - 3 + e, so that output column i reads its 7 Wiener taps at e = i .. i + 6 and groups of
-// four outputs start on 8-byte boundaries; A/B column c holds box column i = c - 1.
-constexpr int L2_WP = 40;                 // window pitch, pixels
+// Layout of the frame kernel's shared memory.  Window element e of a row holds picture column x0 - 8 + e (48 columns:
+// the box the copy engine delivers starts on a 16-byte boundary of the plane; the filters reach 3 columns out, i.e.
+// elements 5 .. 42 are used) and window row r holds picture row top - 3 + r.  Output column i therefore reads its 7 Wiener
+// taps at e = i + 5 .. i + 11; four outputs are served from the aligned 12 elements 4g + 4 .. 4g + 15.  A/B column c
+// holds box column i = c - 1.
+constexpr int L2_WP = 48;                 // window pitch, pixels
+constexpr int L2_X0 = 8;                  // element of picture column x0
 constexpr int L2_WROWS = LR_TH + 6;       // 70
 constexpr int L2_AP = 36;                 // A/B pitch, ints
 constexpr int L2_AROWS = LR_TH + 2;       // 66
 
 struct Lr2Smem {
-    __align__(16) uint16_t win[L2_WROWS * L2_WP];
+    // rows 3 .. of the window are TMA destinations (8-row boxes of 768 bytes): row 3 must sit on a 128-byte boundary,
+    // so the window starts 96 bytes into the aligned block (3 rows x 96 bytes + 96 = 384)
+    __align__(128) uint16_t pad_[48];
+    uint16_t win[L2_WROWS * L2_WP];
+    __align__(128) uint16_t above[2 * L2_WP + 32];   // deblocked rows top - 2, top - 1 (box of 2 rows; 256 bytes)
+    __align__(128) uint16_t below[2 * L2_WP + 32];   // deblocked rows bot, bot + 1
     union {
         __align__(16) uint16_t hor[L2_WROWS * LR_TW];
         struct { __align__(16) int32_t A[L2_AROWS * L2_AP]; __align__(16) int32_t B[L2_AROWS * L2_AP]; } s;
     } u;
 };
 
-__device__ __forceinline__ void lr2_unpack8(const uint16_t *p, int *v) {  // 8 pixels from an 8-byte aligned address
+// v[0 .. N-1] = elements 1 .. N of the 12 starting at the 8-byte aligned address p (N <= 10): the window's columns sit
+// one element past the alignment (L2_X0 - 3 = 5)
+template <int N>
+__device__ __forceinline__ void lr2_unpack_odd(const uint16_t *p, int *v) {
     const uint2 a = *(const uint2 *)p, b = *(const uint2 *)(p + 4);
-    v[0] = a.x & 0xffff; v[1] = a.x >> 16; v[2] = a.y & 0xffff; v[3] = a.y >> 16;
-    v[4] = b.x & 0xffff; v[5] = b.x >> 16; v[6] = b.y & 0xffff; v[7] = b.y >> 16;
+    v[0] = a.x >> 16; v[1] = a.y & 0xffff; v[2] = a.y >> 16;
+    v[3] = b.x & 0xffff; v[4] = b.x >> 16; v[5] = b.y & 0xffff;
+    if (N > 6) v[6] = b.y >> 16;
+    if (N > 7) {
+        const uint2 c = *(const uint2 *)(p + 8);
+        v[7] = c.x & 0xffff;
+        if (N > 8) v[8] = c.x >> 16;
+        if (N > 9) v[9] = c.y & 0xffff;
+    }
 }
 
 template <typename BD>
@@ -230,10 +250,8 @@ __device__ void lr2_wiener(Lr2Smem &sm, int tw, int th, const int16_t *fh, const
     for (int k = 0; k < 7; k++) F[k] = fh[k];
     for (int t = threadIdx.x; t < (th + 6) * 8; t += 256) {
         const int g = t & 7, r = t >> 3;
-        int px[10];
-        lr2_unpack8(sm.win + r * L2_WP + 4 * g, px);
-        const unsigned last = *(const unsigned *)(sm.win + r * L2_WP + 4 * g + 8);
-        px[8] = last & 0xffff; px[9] = last >> 16;
+        int px[10];      // picture columns x0 + 4g - 3 .. x0 + 4g + 6
+        lr2_unpack_odd<10>(sm.win + r * L2_WP + 4 * g + 4, px);
         unsigned outv[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -289,8 +307,8 @@ __device__ void lr2_sgr_ab(Lr2Smem &sm, int th, unsigned s, int bdmin8) {
         for (int c = 0; c < 8; c++) { cs[c] = 0; cq[c] = 0; }
 #pragma unroll
         for (int dy = -RAD; dy <= RAD; dy++) {
-            int px[8];
-            lr2_unpack8(sm.win + (j + 3 + dy) * L2_WP + 4 * k, px);
+            int px[8];   // picture columns x0 + 4k - 3 .. x0 + 4k + 4
+            lr2_unpack_odd<8>(sm.win + (j + 3 + dy) * L2_WP + 4 * k + 4, px);
 #pragma unroll
             for (int c = (N == 25 ? 0 : 1); c < (N == 25 ? 8 : 7); c++) { cs[c] += px[c]; cq[c] += px[c] * px[c]; }
         }
@@ -376,7 +394,7 @@ __device__ void lr2_sgr(Lr2Smem &sm, int tw, int th, int kind, unsigned s0, unsi
     for (int it = 0; it < 2; it++) {
         const int r = r_lo + 32 * it;
 #pragma unroll
-        for (int m = 0; m < 4; m++) { acc[it][m] = 0; src[it][m] = sm.win[(r + 3) * L2_WP + 3 + 4 * g + m]; }
+        for (int m = 0; m < 4; m++) { acc[it][m] = 0; src[it][m] = sm.win[(r + 3) * L2_WP + L2_X0 + 4 * g + m]; }
     }
     if (kind != 3) {
         lr2_sgr_ab<BD, 25>(sm, th, s0, bdmin8);
@@ -409,13 +427,19 @@ __device__ void lr2_sgr(Lr2Smem &sm, int tw, int th, int kind, unsigned s0, unsi
     }
 }
 
-// cdef: CDEF output (the picture being restored); dbl: deblocked pre-CDEF picture; out: restored picture
-template <typename BD>
+// cdef: CDEF output (the picture being restored); dbl: deblocked pre-CDEF picture; out: restored picture.
+// TMA (16-bit pictures): the window comes from the copy engine -- ceil(th / 8) boxes of 48 x 8 pixels of the CDEF output
+// into rows 3 .., one box of 48 x 2 deblocked rows above and one below into side buffers -- requested by one thread;
+// what the boxes cannot express (the stripe rule's repeated rows, replicated pixels at the picture's edges: the copy
+// engine fills with zeros) is patched by a few threads afterwards.
+template <typename BD, bool TMA>
 __global__ void __launch_bounds__(256, 6)
 lr_frame_kernel(const uint8_t *__restrict__ cdef, const uint8_t *__restrict__ dbl, uint8_t *__restrict__ outp,
-                int64_t stride, LrFrameParams P, const Rb200Av1Restoration *__restrict__ lrm, int bdmax) {
+                int64_t stride, LrFrameParams P, const Rb200Av1Restoration *__restrict__ lrm, int bdmax,
+                const __grid_constant__ CUtensorMap map_main, const __grid_constant__ CUtensorMap map_halo) {
     using pixel = typename BD::pixel;
     __shared__ Lr2Smem sm;
+    __shared__ __align__(8) uint64_t bar;
     const int x0 = blockIdx.x * LR_TW, s = P.stripe_first + blockIdx.y;
     const int sh = 64 >> P.ss_ver, off = 8 >> P.ss_ver;
     const int top = imax(0, s * sh - off), bot = imin(P.h, (s + 1) * sh - off);
@@ -453,9 +477,49 @@ lr_frame_kernel(const uint8_t *__restrict__ cdef, const uint8_t *__restrict__ db
         return;
     }
     // ---- stage the padded window (padding(), src/looprestoration_tmpl.c:41-137, with
-    //      lpf rows = deblocked rows saved by backup_lpf, src/lf_apply_tmpl.c:41-106).
-    //      A warp owns rows r = warp, warp + 8, ...; lanes own columns e and e + 32.
-    {
+    //      lpf rows = deblocked rows saved by backup_lpf, src/lf_apply_tmpl.c:41-106)
+    if (TMA) {
+        const bool have_above = top > 0, have_below = bot < P.h;
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            mbar_fence_init();
+            const int n_main = (th + 7) >> 3;
+            mbar_arrive_expect_tx(&bar, (unsigned)(n_main * 8 + (have_above ? 2 : 0) + (have_below ? 2 : 0)) * L2_WP * 2);
+            for (int k = 0; k < n_main; k++) tma_load_2d(sm.win + (3 + 8 * k) * L2_WP, &map_main, x0 - L2_X0, top + 8 * k, &bar);
+            if (have_above) tma_load_2d(sm.above, &map_halo, x0 - L2_X0, top - 2, &bar);
+            if (have_below) tma_load_2d(sm.below, &map_halo, x0 - L2_X0, bot, &bar);
+        }
+        __syncthreads();
+        mbar_wait(&bar, 0);
+        // rows above / below the stripe: deblocked rows top - 2, top - 2, top - 1 and bot, bot + 1, bot + 1 (the last one
+        // clamped to the picture); at the picture's top / bottom the first / last row of the stripe, three times
+        if (threadIdx.x < 6 * (L2_WP / 2)) {
+            const int r = threadIdx.x / (L2_WP / 2), k = threadIdx.x - r * (L2_WP / 2);      // 6 rows x 24 words
+            const unsigned *src;
+            int dst_row;
+            if (r < 3) {
+                dst_row = r;
+                src = have_above ? (const unsigned *)(sm.above + (r == 2 ? L2_WP : 0)) : (const unsigned *)(sm.win + 3 * L2_WP);
+            } else {
+                dst_row = th + r;
+                const bool second = r > 3 && bot + 1 < P.h;
+                src = have_below ? (const unsigned *)(sm.below + (second ? L2_WP : 0)) : (const unsigned *)(sm.win + (th + 2) * L2_WP);
+            }
+            const unsigned v = src[k];
+            ((unsigned *)(sm.win + dst_row * L2_WP))[k] = v;
+        }
+        if (x0 == 0 || x0 + LR_TW + 3 > P.w) {      // replicate the picture's first / last column into the 3 columns beyond it
+            __syncthreads();
+            const int e_last = P.w - 1 - x0 + L2_X0;            // element of the last picture column (>= L2_X0)
+            for (int i = threadIdx.x; i < (th + 6) * 8; i += 256) {
+                const int r = i >> 3, j = i & 7;
+                uint16_t *row = sm.win + r * L2_WP;
+                if (j < 3) { if (x0 == 0) row[L2_X0 - 1 - j] = row[L2_X0]; }
+                else if (j < 6 && x0 + LR_TW + 3 > P.w && e_last + (j - 2) < L2_WP) row[e_last + (j - 2)] = row[e_last];
+            }
+        }
+    } else {
+        // a warp owns rows r = warp, warp + 8, ...; lanes own columns e and e + 32
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         const int xa = iclip(x0 + lane - 3, 0, P.w - 1), xb = iclip(x0 + lane + 29, 0, P.w - 1);
         constexpr int NIT = (L2_WROWS + 7) / 8;
@@ -481,8 +545,8 @@ lr_frame_kernel(const uint8_t *__restrict__ cdef, const uint8_t *__restrict__ db
         for (int it = 0; it < NIT; it++) {
             const int r = warp + 8 * it;
             if (r < th + 6) {
-                sm.win[r * L2_WP + lane] = va[it];
-                if (lane < 8) sm.win[r * L2_WP + 32 + lane] = vb[it];
+                sm.win[r * L2_WP + L2_X0 - 3 + lane] = va[it];
+                if (lane < 8) sm.win[r * L2_WP + L2_X0 + 29 + lane] = vb[it];
             }
         }
     }
@@ -545,13 +609,30 @@ lr_call_kernel(const uint8_t *tmp, int pitch, uint8_t *dst, int64_t stride, int 
 // P.stripe_first / P.stripe_end: stripes to produce (whole plane: 0, number of stripes; end <= 0 means all)
 int lr_plane_launch(const uint8_t *cdef, const uint8_t *dbl, uint8_t *out, int64_t stride, const LrFrameParams &P,
                     const Rb200Av1Restoration *lrm, int bdmax, cudaStream_t st) {
+    return lr_plane_launch_tma(cdef, dbl, out, stride, P, lrm, bdmax, st, nullptr, nullptr);
+}
+
+// map_main: tensor map of the `cdef` plane (P.w x P.h pixels, boxes of 48 x 8); map_halo: of the `dbl` plane (boxes of
+// 48 x 2).  Both null: the window is gathered with loads (8-bit pictures, super-resolution planes).
+int lr_encode_maps(CUtensorMap *map_main, CUtensorMap *map_halo, const void *cdef, const void *dbl, int64_t stride, int w, int h) {
+    int r = tma_encode_plane(map_main, cdef, 2, w, h, stride, L2_WP, 8);
+    if (!r) r = tma_encode_plane(map_halo, dbl, 2, w, h, stride, L2_WP, 2);
+    return r;
+}
+
+int lr_plane_launch_tma(const uint8_t *cdef, const uint8_t *dbl, uint8_t *out, int64_t stride, const LrFrameParams &P,
+                        const Rb200Av1Restoration *lrm, int bdmax, cudaStream_t st, const CUtensorMap *map_main,
+                        const CUtensorMap *map_halo) {
     const int sh = 64 >> P.ss_ver, off = 8 >> P.ss_ver;
     const int n_stripes = (P.h + off + sh - 1) / sh;
     const int s1 = P.stripe_end > 0 ? imin(P.stripe_end, n_stripes) : n_stripes;
     if (s1 <= P.stripe_first) return 0;
     dim3 grid((P.w + LR_TW - 1) / LR_TW, s1 - P.stripe_first);
-    if (bdmax > 255) lr_frame_kernel<BD16><<<grid, 256, 0, st>>>(cdef, dbl, out, stride, P, lrm, bdmax);
-    else lr_frame_kernel<BD8><<<grid, 256, 0, st>>>(cdef, dbl, out, stride, P, lrm, bdmax);
+    static const CUtensorMap none = {};
+    if (bdmax > 255 && map_main && map_halo)
+        lr_frame_kernel<BD16, true><<<grid, 256, 0, st>>>(cdef, dbl, out, stride, P, lrm, bdmax, *map_main, *map_halo);
+    else if (bdmax > 255) lr_frame_kernel<BD16, false><<<grid, 256, 0, st>>>(cdef, dbl, out, stride, P, lrm, bdmax, none, none);
+    else lr_frame_kernel<BD8, false><<<grid, 256, 0, st>>>(cdef, dbl, out, stride, P, lrm, bdmax, none, none);
     RB_LAUNCH_CHECK();
     return 0;
 }

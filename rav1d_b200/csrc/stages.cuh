@@ -13,6 +13,11 @@ int cdef_planes_launch(const Rb200Planes &src, const Rb200Planes &dst, const Cde
                        void *blk_scratch, int bdmax, cudaStream_t st, int t0, int t1, const CUtensorMap_st *maps, int plane_mask,
                        int what, int *launches);
 
+// loop restoration with the window fetched by TMA (lr.cu)
+int lr_encode_maps(CUtensorMap_st *map_main, CUtensorMap_st *map_halo, const void *cdef, const void *dbl, int64_t stride, int w, int h);
+int lr_plane_launch_tma(const uint8_t *cdef, const uint8_t *dbl, uint8_t *out, int64_t stride, const LrFrameParams &P,
+                        const Rb200Av1Restoration *lrm, int bdmax, cudaStream_t st, const CUtensorMap_st *map_main,
+                        const CUtensorMap_st *map_halo);
 // int16 coefficient transport (RB200_UPLOAD_GATHER_COEF16): each block's leading columns pulled from the pinned int16
 // staging and widened into the int32 device array, then the escapes patched in
 int coef_gather16_launch(const int16_t *h_cf16, int32_t *d_cf, const Rb200ItxItem *d_items, int n, const Rb200CoefEscape *d_esc,

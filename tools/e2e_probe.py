@@ -33,6 +33,14 @@ counts = (C.c_int32 * 19)(*[int(c) for c in s.itx_counts])
 n_mc = len(s.mc_items)
 for d in ctxs:
     lib.check(lib.frame_submit(d.h, s.n_coefs, counts, n_mc, stages, 1)); d.wait()
+    lib.check(lib.frame_pack_coef16(d.h, s.n_coefs))
+CHAIN = os.environ.get("RB200_PROBE_CHAIN", "1") == "1"
+if CHAIN:      # frame i predicts from the output of frame i - 1, as in bench.py
+    outs_pl = []
+    for d in ctxs:
+        pl = lib.Planes(); lib.check(lib.frame_output_planes(d.h, C.byref(pl))); outs_pl.append(pl)
+    for i, d in enumerate(ctxs):
+        lib.check(lib.frame_set_ref(d.h, 0, C.byref(outs_pl[i - 1])))
 
 
 def run(upload, readback, frames=96):
@@ -43,6 +51,8 @@ def run(upload, readback, frames=96):
         d = ctxs[i % N]
         d.wait()
         a = time.perf_counter()
+        if CHAIN:
+            lib.check(lib.frame_depend(d.h, ctxs[(i - 1) % N].h))
         lib.check(lib.frame_submit(d.h, s.n_coefs, counts, n_mc, stages, upload))
         if readback:
             lib.check(lib.frame_readback_async(d.h, outs[i % N][0], outs[i % N][1]))
@@ -53,7 +63,7 @@ def run(upload, readback, frames=96):
     return dt / frames * 1e3, host / frames * 1e3
 
 
-for name, up, rb in [("gather+readback", 3, True), ("gather only", 3, False), ("zerocopy only", 2, False), ("copy only", 1, False),
+for name, up, rb in [("gather16+readback", 4, True), ("gather16 only", 4, False), ("gather+readback", 3, True), ("gather only", 3, False), ("zerocopy only", 2, False), ("copy only", 1, False),
                      ("readback only", 0, True), ("resident", 0, False)]:
     run(up, rb, 32)
     ms, hostms = run(up, rb)
