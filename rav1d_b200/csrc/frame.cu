@@ -95,7 +95,7 @@ struct Rb200Frame {
     // luma | chroma post-filter chains on two streams (rb200_frame_set_plane_streams)
     bool plane_split;
     cudaStream_t uv_stream;
-    cudaEvent_t uv_fork, uv_dir, uv_join;
+    cudaEvent_t uv_fork, uv_dir, uv_join, itx_fork, itx_join;
     cudaEvent_t done_event;     // recorded behind the last kernel of every submit (what rb200_frame_depend waits for)
     cudaEvent_t dep_events[8];  // rb200_frame_depend: the producers' done events, waited for by the next submit
     int n_deps;
@@ -320,6 +320,8 @@ extern "C" int rb200_frame_destroy(Rb200Frame *f) {
     if (f->uv_fork) cudaEventDestroy(f->uv_fork);
     if (f->uv_dir) cudaEventDestroy(f->uv_dir);
     if (f->uv_join) cudaEventDestroy(f->uv_join);
+    if (f->itx_fork) cudaEventDestroy(f->itx_fork);
+    if (f->itx_join) cudaEventDestroy(f->itx_join);
     if (f->uv_stream) cudaStreamDestroy(f->uv_stream);
     if (f->own_stream) cudaStreamDestroy(f->own_stream);
     delete f;
@@ -1109,16 +1111,39 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         }
         MARK(2);
         if ((upload == RB200_UPLOAD_GATHER_COEF || upload == RB200_UPLOAD_GATHER_COEF16) && n_itx) RB_CUDA(cudaStreamWaitEvent(st, f->up_join, 0));
-        int off = 0;
-        for (int t = 0; t < RB200_N_RECT_TX_SIZES; t++) {
-            if (itx_counts[t]) {
+        // The residual launches (one per transform size present) write disjoint pixels: they are dealt to two streams,
+        // the heavier buckets first, so that they overlap and fill each other's tails.
+        {
+            const void *cf = upload == RB200_UPLOAD_ZERO_COPY_COEF ? f->h_coef : f->d_coef;
+            static const int tx_area_log2[RB200_N_RECT_TX_SIZES] = {4, 6, 8, 10, 12, 5, 5, 7, 7, 9, 9, 11, 11, 6, 6, 8, 8, 10, 10};
+            int order[RB200_N_RECT_TX_SIZES], offs[RB200_N_RECT_TX_SIZES], n_b = 0, off = 0;
+            for (int t = 0; t < RB200_N_RECT_TX_SIZES; t++) { offs[t] = off; off += itx_counts[t]; if (itx_counts[t]) order[n_b++] = t; }
+            auto weight = [&](int t) { return (int64_t)itx_counts[t] << tx_area_log2[t]; };
+            for (int i = 1; i < n_b; i++)
+                for (int j = i; j > 0 && weight(order[j]) > weight(order[j - 1]); j--) { const int x = order[j]; order[j] = order[j - 1]; order[j - 1] = x; }
+            const bool two = f->plane_split && n_b > 1;
+            if (two) {
+                if (!f->uv_stream) RB_CUDA(cudaStreamCreateWithFlags(&f->uv_stream, cudaStreamNonBlocking));
+                if (!f->itx_fork) {
+                    RB_CUDA(cudaEventCreateWithFlags(&f->itx_fork, cudaEventDisableTiming));
+                    RB_CUDA(cudaEventCreateWithFlags(&f->itx_join, cudaEventDisableTiming));
+                }
+                RB_CUDA(cudaEventRecord(f->itx_fork, st));
+                RB_CUDA(cudaStreamWaitEvent(f->uv_stream, f->itx_fork, 0));
+            }
+            int64_t load[2] = {0, 0};
+            for (int i = 0; i < n_b; i++) {
+                const int t = order[i], which = two && load[1] < load[0] ? 1 : 0;
+                load[which] += weight(t);
                 // zero-copy: the kernel pulls exactly the coefficient columns it needs (Rb200ItxItem.ncols)
                 // over PCIe from the pinned staging instead of a full H2D copy first
-                const void *cf = upload == RB200_UPLOAD_ZERO_COPY_COEF ? f->h_coef : f->d_coef;
-                if ((r = itx_launch(t, f->planes[0], cf, f->d_itx + off, itx_counts[t], f->bdmax, st))) return r;
+                if ((r = itx_launch(t, f->planes[0], cf, f->d_itx + offs[t], itx_counts[t], f->bdmax, which ? f->uv_stream : st))) return r;
                 f->launches++;
             }
-            off += itx_counts[t];
+            if (two) {
+                RB_CUDA(cudaEventRecord(f->itx_join, f->uv_stream));
+                RB_CUDA(cudaStreamWaitEvent(st, f->itx_join, 0));
+            }
         }
         // ---- intra blocks: one launch per dependency level; a CTA prepares a block's edge from the reconstructed
         // picture, predicts it and adds its residual
@@ -1152,8 +1177,8 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
     const bool split = f->plane_split && g.n_planes > 1 && !do_sr && !(f->band_s1 > f->band_s0) && (do_lf || do_cdef || restore_planes);
     cudaStream_t su = st;
     if (split) {
-        if (!f->uv_stream) {
-            RB_CUDA(cudaStreamCreateWithFlags(&f->uv_stream, cudaStreamNonBlocking));
+        if (!f->uv_stream) RB_CUDA(cudaStreamCreateWithFlags(&f->uv_stream, cudaStreamNonBlocking));
+        if (!f->uv_fork) {
             RB_CUDA(cudaEventCreateWithFlags(&f->uv_fork, cudaEventDisableTiming));
             RB_CUDA(cudaEventCreateWithFlags(&f->uv_dir, cudaEventDisableTiming));
             RB_CUDA(cudaEventCreateWithFlags(&f->uv_join, cudaEventDisableTiming));
