@@ -475,99 +475,6 @@ __device__ void mc_tile_fast(McFastSmem &sm, const uint32_t *win, const McWin &W
     __syncwarp();
 }
 
-// The same arithmetic with the intermediate kept in REGISTERS: a lane owns one column pair and R output rows of the
-// tile, runs the horizontal pass for the R + 7 window rows its own outputs need and feeds the vertical pass from its
-// registers.  Lanes that share a column pair redo some rows of the horizontal pass (12 instead of 5.75 rows per lane at
-// 16x16), which is cheaper than the round trip of mc_tile_fast: no intermediate tile in shared memory, no warp
-// synchronisation between the passes, no address arithmetic for it, and the result goes from registers to the picture.
-// TW = 16: lanes = 8 column pairs x 4 row groups of 4; TW = 8: 4 column pairs x 8 rows.  put only (the compound
-// kernel's prep form stays on mc_tile_fast).  `win` as for mc_tile_fast; all MCF_WROWS rows of the buffer may be read
-// (rows beyond the window only ever meet zero taps or outputs that are not stored).
-template <typename BD, int TW>
-__device__ __forceinline__ void mc_tile_reg(const uint32_t *win, const McWin &W, int bw, int bh, int mx, int my, int filter2d,
-                                            uint8_t *out, int64_t out_pitch, int bdmax) {
-    constexpr int NCP = TW / 2, R = TW == 16 ? 4 : 1;
-    constexpr int NPAIR = (R + 8) / 2;            // vertical pairs of intermediate rows a lane holds per column
-    const int lane = threadIdx.x & 31;
-    const int cp = lane & (NCP - 1), row0 = R * (lane / NCP);
-    const int ib = McBits<BD>::ib(bdmax);
-    const bool fh = W.fh, fv = W.fv;
-    const int par = W.par;
-    const bool bilin = filter2d == RB200_FILTER_2D_BILINEAR;
-    const int base = bilin ? 4 : 6;
-    const int th_ = (0x111222000LL >> (4 * filter2d)) & 3, tv_ = (0x210210210LL >> (4 * filter2d)) & 3;
-    const uint32_t *wr = win + row0 * MCF_WPW + cp;
-    unsigned o[R];                                // R rows of this lane's pixel pair
-    if (fv) {
-        unsigned P[2][NPAIR];                     // [column of the pair][row pair] = (mid[2j], mid[2j + 1])
-        if (fh) {
-            const McTaps T = bilin ? mc_bilin_taps(mx) : mc_load_taps(bw > 4 ? th_ : 3 + (th_ & 1), mx - 1);
-            const int sh = base - ib, init = (1 << sh) >> 1;
-#pragma unroll
-            for (int j = 0; j < NPAIR; j++) {
-                int a[2][2];
-#pragma unroll
-                for (int rr = 0; rr < 2; rr++) {
-                    const uint32_t *wv = wr + (2 * j + rr) * MCF_WPW;
-                    const unsigned w0 = wv[0], w1 = wv[1], w2 = wv[2], w3 = wv[3], w4 = wv[4];
-                    if (par == 0) { a[rr][0] = mc_fir_even(T, w0, w1, w2, w3, init); a[rr][1] = mc_fir_odd(T, w0, w1, w2, w3, w4, init); }
-                    else { a[rr][0] = mc_fir_odd(T, w0, w1, w2, w3, w4, init); a[rr][1] = mc_fir_even(T, w1, w2, w3, w4, init); }
-                }
-                P[0][j] = __byte_perm((unsigned)(a[0][0] >> sh), (unsigned)(a[1][0] >> sh), 0x5410);
-                P[1][j] = __byte_perm((unsigned)(a[0][1] >> sh), (unsigned)(a[1][1] >> sh), 0x5410);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < NPAIR; j++) {
-                const uint32_t *r0 = wr + (2 * j) * MCF_WPW, *r1 = r0 + MCF_WPW;
-                const unsigned a0 = par == 0 ? r0[0] : __funnelshift_r(r0[0], r0[1], 16);
-                const unsigned a1 = par == 0 ? r1[0] : __funnelshift_r(r1[0], r1[1], 16);
-                P[0][j] = __byte_perm(a0, a1, 0x5410);
-                P[1][j] = __byte_perm(a0, a1, 0x7632);
-            }
-        }
-        const McTaps T = bilin ? mc_bilin_taps(my) : mc_load_taps(bh > 4 ? tv_ : 3 + (tv_ & 1), my - 1);
-        const int sh2 = fh ? base + ib : base, r2 = (1 << sh2) >> 1;
-#pragma unroll
-        for (int y = 0; y < R; y++) {
-            const int m = y >> 1;
-            int v[2];
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-                const int acc = (y & 1) ? mc_fir_odd(T, P[c][m], P[c][m + 1], P[c][m + 2], P[c][m + 3], P[c][m + 4 < NPAIR ? m + 4 : NPAIR - 1], r2)
-                                        : mc_fir_even(T, P[c][m], P[c][m + 1], P[c][m + 2], P[c][m + 3], r2);
-                v[c] = iclip(acc >> sh2, 0, bdmax);
-            }
-            o[y] = (unsigned)v[0] | ((unsigned)v[1] << 16);
-        }
-    } else if (fh) {
-        const McTaps T = bilin ? mc_bilin_taps(mx) : mc_load_taps(bw > 4 ? th_ : 3 + (th_ & 1), mx - 1);
-        const int r1 = (1 << (base - ib)) >> 1, init = (1 << (base - 1)) + r1;
-#pragma unroll
-        for (int y = 0; y < R; y++) {
-            const uint32_t *wv = wr + y * MCF_WPW;
-            const unsigned w0 = wv[0], w1 = wv[1], w2 = wv[2], w3 = wv[3], w4 = wv[4];
-            int a0, a1;
-            if (par == 0) { a0 = mc_fir_even(T, w0, w1, w2, w3, init); a1 = mc_fir_odd(T, w0, w1, w2, w3, w4, init); }
-            else { a0 = mc_fir_odd(T, w0, w1, w2, w3, w4, init); a1 = mc_fir_even(T, w1, w2, w3, w4, init); }
-            o[y] = (unsigned)iclip(a0 >> base, 0, bdmax) | ((unsigned)iclip(a1 >> base, 0, bdmax) << 16);
-        }
-    } else {
-#pragma unroll
-        for (int y = 0; y < R; y++) {
-            const uint32_t *wv = wr + y * MCF_WPW;
-            o[y] = par == 0 ? wv[0] : __funnelshift_r(wv[0], wv[1], 16);
-        }
-    }
-    uint8_t *d = out + (int64_t)row0 * out_pitch + cp * (BD::hbd ? 4 : 2);
-#pragma unroll
-    for (int y = 0; y < R; y++) {
-        if (BD::hbd) *(unsigned *)(d + (int64_t)y * out_pitch) = o[y];
-        else *(uint16_t *)(d + (int64_t)y * out_pitch) = (uint16_t)((o[y] & 0xff) | ((o[y] >> 8) & 0xff00));
-    }
-    __syncwarp();      // every lane is done with the window before the caller lets the next one land in it
-}
-
 struct McRefSet {
     Rb200Planes p[8];
 };
@@ -729,9 +636,9 @@ mc_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int ss_hor
                 // the common case: the whole block is the prefetched tile
                 const McWin W = win_of(cur);
                 if (cur.w == 16 && cur.h == 16)
-                    mc_tile_reg<BD, 16>(win0, W, 16, 16, mx, my, filter2d, cur.dst, cur.dstride, bdmax);
+                    mc_tile_fast<BD, 16, 16>(sm, win0, W, 16, 16, 16, 16, mx, my, filter2d, cur.dst, cur.dstride, bdmax);
                 else if (cur.w == 8 && cur.h == 8)
-                    mc_tile_reg<BD, 8>(win0, W, 8, 8, mx, my, filter2d, cur.dst, cur.dstride, bdmax);
+                    mc_tile_fast<BD, 8, 8>(sm, win0, W, 8, 8, 8, 8, mx, my, filter2d, cur.dst, cur.dstride, bdmax);
                 else
                     mc_tile_fast<BD, 0, 0>(sm, win0, W, cur.w, cur.h, cur.w, cur.h, mx, my, filter2d, cur.dst, cur.dstride, bdmax);
             } else {
@@ -757,7 +664,7 @@ mc_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int ss_hor
                                 __syncwarp();
                             }
                             if (tw == 16 && th == 16)
-                                mc_tile_reg<BD, 16>(wt, W, cur.w, cur.h, mx, my, filter2d, o, cur.dstride, bdmax);
+                                mc_tile_fast<BD, 16, 16>(sm, wt, W, tw, th, cur.w, cur.h, mx, my, filter2d, o, cur.dstride, bdmax);
                             else
                                 mc_tile_fast<BD, 0, 0>(sm, wt, W, tw, th, cur.w, cur.h, mx, my, filter2d, o, cur.dstride, bdmax);
                         } else {
