@@ -437,7 +437,7 @@ def run_gpu(args, s, wl):
         if args.workload in WARP_INST_PER_FRAME and clocks and clocks.get("sm_mhz"):
             peak_issue = 148 * 4 * clocks["sm_mhz"] * 1e6          # warp instructions / s
             wi = WARP_INST_PER_FRAME[args.workload]
-            issue = {"warp_inst_per_frame": wi, "peak_warp_inst_per_s": peak_issue, "source": "profiles/r01c_ncu_full_summary_*.csv",
+            issue = {"warp_inst_per_frame": wi, "peak_warp_inst_per_s": peak_issue, "source": "profiles/r02g_ncu_full_summary_4k10.csv" if args.workload == "4k10" else "profiles/r01c_ncu_full_summary_4k10c5.csv",
                      "frac": round(wi * (value * 1e6 / (w * h)) / world / peak_issue, 4)}
         # frame-level algorithmic bytes as BASELINE.md 4 counts them (MC + itx = one fused recon stage: 2S + C)
         frame_bytes = (ab["recon"] if stages & 1 else 0) + sum(ab[k] for k in ("deblock", "cdef", "lr", "film_grain") if k in per_stage)
@@ -467,6 +467,16 @@ def run_gpu(args, s, wl):
                 "gpu_launches": launches}
     for d in ctxs:
         d.close()
+    # BASELINE configs[3]: one 8K 10-bit picture's post-filters split by superblock rows over the N GPUs of this job, halo rows
+    # pulled peer to peer over NVLink, ordered by cross-GPU flags (no collective) -- reported beside the headline at N > 1
+    band = None
+    if world > 1 and args.workload == "4k10" and not args.no_band_split:
+        from rav1d_b200 import multigpu
+        torch.cuda.synchronize()
+        dist.barrier()
+        band = multigpu.run_band_split(7680, 4320, 10, steps=40, in_flight=2, check=False)
+        if line is not None:
+            line["band_split_8k10"] = band
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -487,16 +497,16 @@ def run_gpu(args, s, wl):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
 # capture of the dominant kernel (profiles/), keyed by (workload, stage); None until captured.
 TRAFFIC = {
-    # profiles/r01c_ncu_full_summary_4k10.csv: cdef_dir_frame_kernel 13.88 MB + cdef_filter_frame_kernel 26.05 + 2.43 MB
-    ("4k10", "cdef"): 42.36e6,
-    ("4k10", "mc"): 26.70e6,
-    ("4k10", "lr"): 27.22e6,
+    # profiles/r02g_ncu_full_summary_4k10.csv: cdef_dir_frame_kernel 13.88 MB + cdef_filter_tma_kernel 17.69 (luma) + 9.38 (chroma) MB
+    ("4k10", "cdef"): 40.95e6,
+    ("4k10", "mc"): 26.71e6,
+    ("4k10", "lr"): 27.32e6,       # 17.79 + 4.76 + 4.77 MB (three planes)
     # profiles/r01c_ncu_full_summary_4k10c5.csv: mc_batch 25.2 + mc_comp_batch 53.7 + warp 5.8 + obmc 8.4 + 13.9 MB
     ("4k10c5", "mc"): 107.0e6,
 }
 # Executed warp instructions per frame (smsp__inst_executed.sum over one frame's launches, same captures): the path is
 # integer-issue bound, so value x this / (SMs x 4 schedulers x clock) says how full the issue slots are.
-WARP_INST_PER_FRAME = {"4k10": 203.0e6, "4k10c5": 293.9e6}
+WARP_INST_PER_FRAME = {"4k10": 164.1e6, "4k10c5": 293.9e6}   # 4k10: r02g capture (209 M in round 1); 4k10c5: r01c
 
 
 _JSON_OUT = None
@@ -526,6 +536,7 @@ def main():
     ap.add_argument("--lf", default="masks", choices=["masks", "records"],
                     help="loop-filter metadata: Av1Filter masks + levels uploaded, or per-block records uploaded and the masks built on the device")
     ap.add_argument("--streams", type=int, default=N_CTX, help="resident legs: 1 = every frame context on one CUDA stream (launch lists), otherwise one stream per context")
+    ap.add_argument("--no-band-split", action="store_true", help="N > 1: skip the 8K band-split leg (BASELINE configs[3])")
     ap.add_argument("--plane-streams", type=int, default=1, help="1 (default): luma and chroma post-filter chains of a frame on two streams; 0: one stream")
     ap.add_argument("--coefs", default="gather16", choices=["gather16", "gather", "zerocopy", "copy"],
                     help="e2e leg, how coefficients cross PCIe: as int16 + escapes, a gather kernel pulling each block's non-zero "
@@ -543,6 +554,8 @@ def main():
     s = framegen.generate(wl[0], wl[1], wl[2], seed=1 + (rank if args.impl == "b200" else 0), **GEN_ARGS.get(args.workload, {}))
     if wl[3] & 16:
         s.film_grain = framegen.random_film_grain(np.random.default_rng(7), lag=3, overlap=1)
+    if args.impl == "b200" and args.plane_streams and wl[3] & 1:
+        framegen.sort_luma_first(s)          # what a front end does for free: two lists instead of one (rb200_frame_set_plane_counts)
     if args.impl == "reference":
         run_reference(args, s, wl)
     else:

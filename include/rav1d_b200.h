@@ -612,6 +612,12 @@ int rb200_frame_pack_coef16(Rb200Frame *f, size_t n_coefs);
 int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t itx_counts[RB200_N_RECT_TX_SIZES],
                        int n_mc_items, int stages, int upload);
 int rb200_frame_wait(Rb200Frame *f);
+/* Checks the staged batch the way rb200_frame_submit will read it -- reference slots that are set, blocks inside the
+ * picture allocation, coefficient offsets inside the buffer, transform sizes / types that exist, intra items' residual
+ * indices -- and names the first bad record in rb200_last_error().  The kernels trust the records (a bad one is an
+ * out-of-bounds access on the device, i.e. a sticky CUDA error); a front end calls this in debug builds or on
+ * untrusted bitstreams.  Arguments as for rb200_frame_submit; costs one pass over the host-side lists. */
+int rb200_frame_validate(Rb200Frame *f, size_t n_coefs, const int32_t itx_counts[RB200_N_RECT_TX_SIZES], int n_mc_items, int stages);
 /* D2H of the output picture into host planes (stride in bytes, may be negative). */
 int rb200_frame_readback(Rb200Frame *f, void *const data[3], const ptrdiff_t stride[2]);
 /* Same, queued on the frame's stream without waiting (use pinned host planes, then rb200_frame_wait). */
@@ -638,6 +644,13 @@ int rb200_ipc_get_handle(void *dptr, uint8_t handle[RB200_IPC_HANDLE_BYTES]);
 int rb200_ipc_open_handle(const uint8_t handle[RB200_IPC_HANDLE_BYTES], void **dptr);
 int rb200_ipc_close_handle(void *dptr);
 int rb200_enable_peer_access(int peer_device);
+/* Cross-GPU ordering without the host and without a collective (the band split's "my neighbours have pulled their halo
+ * rows out of my picture, I may deblock it in place"): `flag` is a uint32 in the WAITING GPU's memory (rb200_malloc +
+ * rb200_memset; shared like the planes with rb200_ipc_get_handle / _open_handle).  rb200_flag_signal writes `value`
+ * into it once everything queued on `stream` so far is done -- through the peer mapping when the stream belongs to
+ * another GPU; rb200_flag_wait holds `stream` until the flag has reached `value` (wrap-safe >=). */
+int rb200_flag_signal(void *stream, uint32_t *flag, uint32_t value);
+int rb200_flag_wait(void *stream, const uint32_t *flag, uint32_t value);
 void *rb200_frame_stream(Rb200Frame *f);
 /* Run the frame's copies and launches on `stream` instead of the frame's own (NULL restores it). */
 int rb200_frame_set_stream(Rb200Frame *f, void *stream);
@@ -653,6 +666,13 @@ int rb200_frame_depend(Rb200Frame *f, Rb200Frame *producer);
  * direction search), joined before the submit ends; on by default.  0 = every launch on the frame's one stream, which
  * is what the per-stage times below need to mean anything. */
 int rb200_frame_set_plane_streams(Rb200Frame *f, int on);
+/* Optional promise about the order of the staged lists: the put items [0, n_mc_luma) are plane 0 and the rest chroma, and
+ * every transform-size bucket t of the residual items holds its itx_luma_counts[t] plane-0 items first.  The
+ * reconstruction of a frame that has nothing but put predictions and residuals (no compound / warped / OBMC / scaled /
+ * intra items: those work on several planes at once) then runs as a luma chain and a chroma chain on the two streams as
+ * well, and the chains continue into the post-filters without meeting.  Holds for every following submit;
+ * n_mc_luma < 0 withdraws it. */
+int rb200_frame_set_plane_counts(Rb200Frame *f, int n_mc_luma, const int32_t itx_luma_counts[RB200_N_RECT_TX_SIZES]);
 /* Per-stage device times of the last submit (CUDA events on the frame's stream), the analogue
  * of the reference CLI's --frametimes (tools/dav1d.rs:127-150).  ms[] = H2D, MC, itx, deblock,
  * CDEF, LR, film grain; valid after rb200_frame_wait(). */

@@ -98,6 +98,19 @@ void DevRect::finish(void *host_row0) {
     for (int y = 0; y < rows; y++) memcpy(d + (int64_t)y * hstride, hstage + (size_t)y * dpitch, row_bytes);
 }
 
+// ---- cross-GPU flags: a stream of one GPU tells a stream of another that it is done with something (halo rows pulled),
+// without the host and without a collective.  The flag lives in the waiting GPU's memory; the signalling GPU writes it
+// through its peer mapping (NVLink).
+__global__ void flag_signal_kernel(volatile uint32_t *flag, uint32_t value) {
+    __threadfence_system();      // (the copies queued before this launch are complete: stream order)
+    *flag = value;
+    __threadfence_system();
+}
+__global__ void flag_wait_kernel(const volatile uint32_t *flag, uint32_t value) {
+    while ((int32_t)(*flag - value) < 0) __nanosleep(200);
+    __threadfence_system();
+}
+
 // ---- tensor maps (tma.cuh).  cuTensorMapEncodeTiled is a driver entry point; it is looked up through the runtime so
 // that the library needs no link-time libcuda.
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -195,6 +208,19 @@ extern "C" int rb200_ipc_open_handle(const uint8_t handle[RB200_IPC_HANDLE_BYTES
     return 0;
 }
 extern "C" int rb200_ipc_close_handle(void *dptr) { RB_CUDA(cudaIpcCloseMemHandle(dptr)); return 0; }
+extern "C" int rb200_flag_signal(void *stream, uint32_t *flag, uint32_t value) {
+    if (!flag) return set_error(-22, "flag_signal: null flag");
+    flag_signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag, value);
+    RB_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int rb200_flag_wait(void *stream, const uint32_t *flag, uint32_t value) {
+    if (!flag) return set_error(-22, "flag_wait: null flag");
+    flag_wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag, value);
+    RB_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int rb200_enable_peer_access(int peer_device) {
     int can = 0, dev = 0;
     RB_CUDA(cudaGetDevice(&dev));

@@ -94,6 +94,7 @@ struct Rb200Frame {
     cudaStream_t own_stream;
     // luma | chroma post-filter chains on two streams (rb200_frame_set_plane_streams)
     bool plane_split;
+    bool plane_counts; int n_mc_luma; int32_t itx_luma[RB200_N_RECT_TX_SIZES];   // rb200_frame_set_plane_counts
     cudaStream_t uv_stream;
     cudaEvent_t uv_fork, uv_dir, uv_join, itx_fork, itx_join;
     cudaEvent_t done_event;     // recorded behind the last kernel of every submit (what rb200_frame_depend waits for)
@@ -647,6 +648,19 @@ extern "C" int rb200_frame_set_plane_streams(Rb200Frame *f, int on) {
     return 0;
 }
 
+extern "C" int rb200_frame_set_plane_counts(Rb200Frame *f, int n_mc_luma, const int32_t itx_luma_counts[RB200_N_RECT_TX_SIZES]) {
+    if (!f) return set_error(-22, "frame_set_plane_counts: null frame");
+    f->plane_counts = n_mc_luma >= 0 && itx_luma_counts;
+    if (f->plane_counts) {
+        f->n_mc_luma = n_mc_luma;
+        for (int t = 0; t < RB200_N_RECT_TX_SIZES; t++) {
+            if (itx_luma_counts[t] < 0) { f->plane_counts = false; return set_error(-22, "frame_set_plane_counts: negative count"); }
+            f->itx_luma[t] = itx_luma_counts[t];
+        }
+    }
+    return 0;
+}
+
 extern "C" int rb200_frame_enable_timing(Rb200Frame *f, int on) {
     if (!f) return set_error(-22, "frame_enable_timing: null frame");
     if (on)
@@ -949,6 +963,65 @@ extern "C" int rb200_frame_wait(Rb200Frame *f) {
     return 0;
 }
 
+extern "C" int rb200_frame_validate(Rb200Frame *f, size_t n_coefs, const int32_t itx_counts[RB200_N_RECT_TX_SIZES], int n_mc, int stages) {
+    if (!f) return set_error(-22, "frame_validate: null frame");
+    if (!(stages & RB200_STAGE_RECON)) return 0;
+    if (!itx_counts) return set_error(-22, "frame_validate: itx_counts required");
+    const Rb200FrameGeometry &g = f->g;
+    static const uint8_t txw[RB200_N_RECT_TX_SIZES] = {4, 8, 16, 32, 64, 4, 8, 8, 16, 16, 32, 32, 64, 4, 16, 8, 32, 16, 64};
+    static const uint8_t txh[RB200_N_RECT_TX_SIZES] = {4, 8, 16, 32, 64, 8, 4, 16, 8, 32, 16, 64, 32, 16, 4, 32, 8, 64, 16};
+    auto plane_w = [&](int p) { return (int)(g.stride[p ? 1 : 0] / (int64_t)f->px); };
+    auto plane_h = [&](int p) { return g.plane_h[p ? 1 : 0]; };
+    if (n_coefs > f->max_coefs) return set_error(-22, "frame_validate: %zu coefficients, the frame holds %zu", n_coefs, f->max_coefs);
+    int n_itx = 0, idx = 0;
+    for (int t = 0; t < RB200_N_RECT_TX_SIZES; t++) {
+        if (itx_counts[t] < 0) return set_error(-22, "frame_validate: negative itx count");
+        n_itx += itx_counts[t];
+    }
+    int n_itx_all = n_itx;
+    if (stages & RB200_STAGE_INTRA)
+        for (int l = 0; l < f->n_levels; l++)
+            for (int t = 0; t < RB200_N_RECT_TX_SIZES; t++) n_itx_all += f->intra_itx_counts[l * RB200_N_RECT_TX_SIZES + t];
+    if (n_itx_all > f->max_itx) return set_error(-22, "frame_validate: %d residual items, the frame holds %d", n_itx_all, f->max_itx);
+    for (int t = 0; t < RB200_N_RECT_TX_SIZES; t++)
+        for (int k = 0; k < itx_counts[t]; k++, idx++) {
+            const Rb200ItxItem &it = f->h_itx[idx];
+            const int sw = txw[t] < 32 ? txw[t] : 32, sh = txh[t] < 32 ? txh[t] : 32;
+            if (it.tx != t) return set_error(-22, "frame_validate: itx item %d is in the bucket of size %d but says %d", idx, t, it.tx);
+            if (it.plane >= g.n_planes || !rb200_itx_valid(it.tx, it.txtp)) return set_error(-22, "frame_validate: itx item %d: plane %d / type %d", idx, it.plane, it.txtp);
+            if ((size_t)it.cf_off + (size_t)sw * sh > n_coefs) return set_error(-22, "frame_validate: itx item %d reads coefficients %u.. beyond %zu", idx, it.cf_off, n_coefs);
+            if (it.x + txw[t] > plane_w(it.plane) || it.y + txh[t] > plane_h(it.plane)) return set_error(-22, "frame_validate: itx item %d (%d, %d) leaves plane %d", idx, it.x, it.y, it.plane);
+            if (it.ncols > sw) return set_error(-22, "frame_validate: itx item %d: ncols %d of %d", idx, it.ncols, sw);
+        }
+    for (int i = n_itx; i < n_itx_all; i++) {
+        const Rb200ItxItem &it = f->h_itx[i];
+        if (it.tx >= RB200_N_RECT_TX_SIZES || it.plane >= g.n_planes || !rb200_itx_valid(it.tx, it.txtp)) return set_error(-22, "frame_validate: intra residual %d: size %d / plane %d / type %d", i, it.tx, it.plane, it.txtp);
+        const int sw = txw[it.tx] < 32 ? txw[it.tx] : 32, sh = txh[it.tx] < 32 ? txh[it.tx] : 32;
+        if ((size_t)it.cf_off + (size_t)sw * sh > n_coefs) return set_error(-22, "frame_validate: intra residual %d reads coefficients beyond %zu", i, n_coefs);
+        if (it.x + txw[it.tx] > plane_w(it.plane) || it.y + txh[it.tx] > plane_h(it.plane)) return set_error(-22, "frame_validate: intra residual %d leaves plane %d", i, it.plane);
+    }
+    if (n_mc < 0 || n_mc > f->max_mc) return set_error(-22, "frame_validate: %d prediction items, the frame holds %d", n_mc, f->max_mc);
+    auto check_mc = [&](const Rb200McItem &m, int i, const char *list) -> int {
+        if (m.plane >= g.n_planes || m.ref >= f->n_refs || !f->refs[m.ref].data[m.plane]) return set_error(-22, "frame_validate: %s item %d: plane %d, reference slot %d (%d set)", list, i, m.plane, m.ref, f->n_refs);
+        if (m.w < 2 || m.h < 2 || m.w > 128 || m.h > 128 || m.mx > 15 || m.my > 15 || m.filter2d > 9) return set_error(-22, "frame_validate: %s item %d: %d x %d, phase (%d, %d), filter %d", list, i, m.w, m.h, m.mx, m.my, m.filter2d);
+        if (m.dst_x < 0 || m.dst_y < 0 || m.dst_x + m.w > plane_w(m.plane) || m.dst_y + m.h > plane_h(m.plane)) return set_error(-22, "frame_validate: %s item %d (%d, %d) %d x %d leaves plane %d", list, i, m.dst_x, m.dst_y, m.w, m.h, m.plane);
+        return 0;
+    };
+    int r;
+    for (int i = 0; i < n_mc; i++) if ((r = check_mc(f->h_mc[i], i, "mc"))) return r;
+    for (int i = 0; i < f->n_obmc_above + f->n_obmc_left; i++) if ((r = check_mc(f->h_obmc[i], i, "obmc"))) return r;
+    if (stages & RB200_STAGE_INTRA) {
+        int n_in = 0;
+        for (int l = 0; l < f->n_levels; l++) n_in += f->intra_counts[l];
+        for (int i = 0; i < n_in; i++) {
+            const Rb200IntraItem &it = f->h_intra[i];
+            if (it.plane >= g.n_planes) return set_error(-22, "frame_validate: intra item %d: plane %d", i, it.plane);
+            if (f->h_intra_itx[i] >= n_itx_all || f->h_intra_itx[i] < -1) return set_error(-22, "frame_validate: intra item %d names residual %d of %d", i, f->h_intra_itx[i], n_itx_all);
+        }
+    }
+    return 0;
+}
+
 extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t itx_counts[RB200_N_RECT_TX_SIZES],
                                   int n_mc, int stages, int upload) {
     if (!f) return set_error(-22, "frame_submit: null frame");
@@ -985,6 +1058,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
     }
     const bool do_lf = (stages & RB200_STAGE_DEBLOCK) && (h.lf_level_y[0] || h.lf_level_y[1]);
     const bool do_cdef = (stages & RB200_STAGE_CDEF) != 0;
+    const bool do_sr = f->sr && (stages & RB200_STAGE_SUPER_RES);
     int restore_planes = 0;
     if (stages & RB200_STAGE_LR)
         for (int p = 0; p < g.n_planes; p++) if (h.lr_type[p] != RB200_RESTORATION_NONE) restore_planes |= 1 << p;
@@ -1076,8 +1150,49 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         f->launches += 2;
         RB_CUDA(cudaEventRecord(f->lf_join, f->lf_stream));
     }
-    // ---- reconstruction: prediction, then residual add
-    if (stages & RB200_STAGE_RECON) {
+    // ---- reconstruction: prediction, then residual add.
+    // With the lists sorted luma first (rb200_frame_set_plane_counts) and nothing but put predictions and residuals in the
+    // frame, the luma and the chroma reconstruction are two chains on two streams that run on into the post-filters.
+    bool recon_split = f->plane_split && f->plane_counts && g.n_planes > 1 && (stages & RB200_STAGE_RECON) && !f->n_comp && !f->n_warp &&
+                       !f->n_scaled && !f->n_obmc_above && !f->n_obmc_left && !((stages & RB200_STAGE_INTRA) && f->n_levels) && !do_sr &&
+                       !(f->band_s1 > f->band_s0) && f->n_mc_luma <= n_mc && (do_lf || do_cdef || restore_planes);
+    if (recon_split)
+        for (int t = 0; t < RB200_N_RECT_TX_SIZES; t++) if (f->itx_luma[t] > itx_counts[t]) recon_split = false;
+    if (recon_split) {
+        if (!f->uv_stream) RB_CUDA(cudaStreamCreateWithFlags(&f->uv_stream, cudaStreamNonBlocking));
+        if (!f->uv_fork) {
+            RB_CUDA(cudaEventCreateWithFlags(&f->uv_fork, cudaEventDisableTiming));
+            RB_CUDA(cudaEventCreateWithFlags(&f->uv_dir, cudaEventDisableTiming));
+            RB_CUDA(cudaEventCreateWithFlags(&f->uv_join, cudaEventDisableTiming));
+        }
+        cudaStream_t su = f->uv_stream;
+        RB_CUDA(cudaEventRecord(f->uv_fork, st));          // behind the batch uploads and the producers' events
+        RB_CUDA(cudaStreamWaitEvent(su, f->uv_fork, 0));
+        const int n_luma = f->n_mc_luma, n_chroma = n_mc - f->n_mc_luma;
+        if (n_luma) {
+            if ((r = mc_batch_launch(f->planes[0], f->refs, f->n_refs, h.width, h.height, g.ss_hor, g.ss_ver, f->d_mc, n_luma, f->bdmax, st,
+                                     f->d_counters, &f->tm_refs))) return r;
+            f->launches++;
+        }
+        if (n_chroma) {
+            if ((r = mc_batch_launch(f->planes[0], f->refs, f->n_refs, h.width, h.height, g.ss_hor, g.ss_ver, f->d_mc + n_luma, n_chroma, f->bdmax,
+                                     su, f->d_counters + 1, &f->tm_refs))) return r;
+            f->launches++;
+        }
+        if ((upload == RB200_UPLOAD_GATHER_COEF || upload == RB200_UPLOAD_GATHER_COEF16) && n_itx) {
+            RB_CUDA(cudaStreamWaitEvent(st, f->up_join, 0));
+            RB_CUDA(cudaStreamWaitEvent(su, f->up_join, 0));
+        }
+        const void *cf = upload == RB200_UPLOAD_ZERO_COPY_COEF ? f->h_coef : f->d_coef;
+        int off = 0;
+        for (int t = 0; t < RB200_N_RECT_TX_SIZES; t++) {
+            const int nl = f->itx_luma[t], nc = itx_counts[t] - nl;
+            if (nl) { if ((r = itx_launch(t, f->planes[0], cf, f->d_itx + off, nl, f->bdmax, st))) return r; f->launches++; }
+            if (nc) { if ((r = itx_launch(t, f->planes[0], cf, f->d_itx + off + nl, nc, f->bdmax, su))) return r; f->launches++; }
+            off += itx_counts[t];
+        }
+        if (build_lf) RB_CUDA(cudaStreamWaitEvent(su, f->lf_join, 0));
+    } else if (stages & RB200_STAGE_RECON) {
         if (n_mc) {
             if ((r = mc_batch_launch(f->planes[0], f->refs, f->n_refs, h.width, h.height, g.ss_hor, g.ss_ver, f->d_mc,
                                      n_mc, f->bdmax, st, f->d_counters, &f->tm_refs))) return r;
@@ -1173,8 +1288,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
     if (build_lf) RB_CUDA(cudaStreamWaitEvent(st, f->lf_join, 0));
     // The post-filters never mix planes (only the chroma CDEF wants the luma direction search), so the luma chain and
     // the chroma chain of a frame run on two streams: each fills the issue slots the other leaves idle.
-    const bool do_sr = f->sr && (stages & RB200_STAGE_SUPER_RES);
-    const bool split = f->plane_split && g.n_planes > 1 && !do_sr && !(f->band_s1 > f->band_s0) && (do_lf || do_cdef || restore_planes);
+    const bool split = recon_split || (f->plane_split && g.n_planes > 1 && !do_sr && !(f->band_s1 > f->band_s0) && (do_lf || do_cdef || restore_planes));
     cudaStream_t su = st;
     if (split) {
         if (!f->uv_stream) RB_CUDA(cudaStreamCreateWithFlags(&f->uv_stream, cudaStreamNonBlocking));
@@ -1184,8 +1298,10 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
             RB_CUDA(cudaEventCreateWithFlags(&f->uv_join, cudaEventDisableTiming));
         }
         su = f->uv_stream;
-        RB_CUDA(cudaEventRecord(f->uv_fork, st));
-        RB_CUDA(cudaStreamWaitEvent(su, f->uv_fork, 0));
+        if (!recon_split) {      // (a split reconstruction has forked the chroma chain already)
+            RB_CUDA(cudaEventRecord(f->uv_fork, st));
+            RB_CUDA(cudaStreamWaitEvent(su, f->uv_fork, 0));
+        }
     }
     // ---- deblock (in place): all column edges, then all row edges (src/recon.rs:4047-4170)
     if (do_lf) {

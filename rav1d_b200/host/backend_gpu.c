@@ -115,7 +115,16 @@ static int gpu_frame_stage(const RbHostFrameDesc *const d, const RbHostBatch *co
     /* reconstruction batch */
     if (d->n_coefs) memcpy(rb200_frame_coef_buffer(fr), d->coef, d->n_coefs * cs);
     if (fin->n_itx) memcpy(rb200_frame_itx_items(fr), fin->itx, (size_t)fin->n_itx * sizeof(Rb200ItxItem));
-    if (B->mc.n) memcpy(rb200_frame_mc_items(fr), B->mc.v, (size_t)B->mc.n * sizeof(Rb200McItem));
+    /* put predictions luma first, and the promise that goes with it: frames without compound / warped / OBMC / scaled /
+     * intra items are then reconstructed as a luma and a chroma chain */
+    {
+        Rb200McItem *const dst = rb200_frame_mc_items(fr);
+        int n = 0;
+        for (int i = 0; i < B->mc.n; i++) if (!B->mc.v[i].plane) dst[n++] = B->mc.v[i];
+        const int n_luma = n;
+        for (int i = 0; i < B->mc.n; i++) if (B->mc.v[i].plane) dst[n++] = B->mc.v[i];
+        CHECK(rb200_frame_set_plane_counts(fr, n_luma, fin->itx_luma_counts));
+    }
     CHECK(rb200_frame_reserve_comp_items(fr, B->comp.n));
     if (B->comp.n) memcpy(rb200_frame_comp_items(fr), B->comp.v, (size_t)B->comp.n * sizeof(Rb200CompItem));
     CHECK(rb200_frame_set_comp_count(fr, B->comp.n));
@@ -173,6 +182,9 @@ static int gpu_frame_submit(void *const cur) {
     GpuPic *const p = cur;
     if (!p || !p->staged) { snprintf(g_err, sizeof(g_err), "frame_submit: nothing staged"); return -1; }
     p->staged = 0;
+    static int validate = -1;      /* RB200_VALIDATE=1: check every record before the kernels trust it (untrusted bitstreams, debugging) */
+    if (validate < 0) validate = getenv("RB200_VALIDATE") && atoi(getenv("RB200_VALIDATE"));
+    if (validate) CHECK(rb200_frame_validate(p->fr, p->n_coefs, p->itx_counts, p->n_mc, p->stages));
     CHECK(rb200_frame_submit(p->fr, p->n_coefs, p->itx_counts, p->n_mc, p->stages, RB200_UPLOAD_ALL));
     return 0;
 }

@@ -50,11 +50,21 @@ int rb_batch_finalize(RbHostBatch *b, RbHostFinal *out, int frame_w4, int frame_
     out->intra_itx = malloc(sizeof(int32_t) * (size_t)(n_intra + 1));
     if (!out->itx || !out->intra || !out->intra_itx) return -12;
 
-    /* inter residuals: stable bucket sort by transform size (one launch per size) */
-    int start[RB200_N_RECT_TX_SIZES + 1] = { 0 };
-    for (int i = 0; i < n_inter; i++) out->itx_counts[b->itx.v[i].tx]++;
-    for (int t = 0; t < RB200_N_RECT_TX_SIZES; t++) start[t + 1] = start[t] + out->itx_counts[t];
-    for (int i = 0; i < n_inter; i++) out->itx[start[b->itx.v[i].tx]++] = b->itx.v[i];
+    /* inter residuals: stable bucket sort by transform size (one launch per size), luma first within a size
+     * (rb200_frame_set_plane_counts: the luma and the chroma reconstruction can then run as two chains) */
+    int start[RB200_N_RECT_TX_SIZES + 1] = { 0 }, cstart[RB200_N_RECT_TX_SIZES];
+    for (int i = 0; i < n_inter; i++) {
+        out->itx_counts[b->itx.v[i].tx]++;
+        if (!b->itx.v[i].plane) out->itx_luma_counts[b->itx.v[i].tx]++;
+    }
+    for (int t = 0; t < RB200_N_RECT_TX_SIZES; t++) {
+        start[t + 1] = start[t] + out->itx_counts[t];
+        cstart[t] = start[t] + out->itx_luma_counts[t];
+    }
+    for (int i = 0; i < n_inter; i++) {
+        const int t = b->itx.v[i].tx;
+        out->itx[b->itx.v[i].plane ? cstart[t]++ : start[t]++] = b->itx.v[i];
+    }
     out->n_itx_inter = n_inter;
     out->n_itx = n_inter;
     out->n_intra = n_intra;

@@ -62,6 +62,7 @@ void *rb_vec_grow(void *v, int *cap, int need, size_t elem);
 typedef struct RbHostFinal {
     Rb200ItxItem *itx; int n_itx_inter, n_itx;        /* [n_itx]: inter (bucketed), then the intra levels' residuals */
     int32_t itx_counts[RB200_N_RECT_TX_SIZES];        /* inter only */
+    int32_t itx_luma_counts[RB200_N_RECT_TX_SIZES];   /* of those, plane 0: every bucket holds its luma items first */
     Rb200IntraItem *intra; int32_t *intra_itx; int n_intra;   /* level order; intra_itx = index into itx or -1 */
     int n_levels; int32_t *level_counts, *level_itx_counts;   /* [n_levels], [n_levels][RB200_N_RECT_TX_SIZES] */
 } RbHostFinal;

@@ -275,6 +275,10 @@ ipc_close_handle = _sig("rb200_ipc_close_handle", _i, _vp)
 enable_peer_access = _sig("rb200_enable_peer_access", _i, _i)
 frame_set_stream = _sig("rb200_frame_set_stream", _i, _vp, _vp)
 frame_depend = _sig("rb200_frame_depend", _i, _vp, _vp)
+frame_set_plane_counts = _sig("rb200_frame_set_plane_counts", _i, _vp, _i, C.POINTER(C.c_int32))
+frame_validate = _sig("rb200_frame_validate", _i, _vp, _sz, C.POINTER(C.c_int32), _i, _i)
+flag_signal = _sig("rb200_flag_signal", _i, _vp, _vp, C.c_uint32)
+flag_wait = _sig("rb200_flag_wait", _i, _vp, _vp, C.c_uint32)
 UPLOAD_GATHER_COEF16 = 4
 frame_coef16_buffer = _sig("rb200_frame_coef16_buffer", _vp, _vp)
 frame_pack_coef16 = _sig("rb200_frame_pack_coef16", _i, _vp, _sz)

@@ -7,6 +7,12 @@ stripes, pulls the halo its earlier stages read (rb200_frame_band_rows) from the
 those rows -- a peer-to-peer copy over NVLink, no collective -- and then runs deblock, CDEF and
 loop restoration on its band only.  Ranks are one process per GPU; peers' plane memory is mapped
 with CUDA IPC handles that travel through torch.distributed (any backend: object all-gather).
+
+Ordering between GPUs (deblocking is in place, so a rank may not start it while a neighbour still reads
+its rows): a flag per (context, peer) in the waiting GPU's memory.  A rank that has pulled its halo out of
+peer p writes the frame's epoch into p's flag through the peer mapping (rb200_flag_signal, stream-ordered
+behind the copies); before its own filters it waits for the flags of the ranks that pull from it
+(rb200_flag_wait).  No host synchronisation, no collective; BandRing keeps several pictures in flight.
 """
 import ctypes as C
 
@@ -148,3 +154,159 @@ class BandContext:
         if self.h:
             lib.frame_destroy(self.h)
             self.h = None
+
+
+def pullers_of(height, ranges, rank, in_rows_of, padded_height=None):
+    """Ranks whose halo plan names `rank` (they read its rows, so it waits for them before filtering in place)."""
+    return [r for r in range(len(ranges)) if r != rank and ranges[r][1] > ranges[r][0] and
+            any(peer == rank for peer, _, _ in halo_plan(height, ranges, r, in_rows_of[r], padded_height))]
+
+
+class BandRing:
+    """K pictures in flight on one rank of a band split: K BandContexts with their flags, the IPC exchange and the
+    per-picture protocol pull -> signal -> wait -> filter.  `make_frame(k)` returns a DeviceFrame-like object (attributes
+    h, submit, wait) whose batch is loaded; `dist` is torch.distributed (initialised)."""
+
+    def __init__(self, hdr, world, rank, make_frame, in_flight=2):
+        import numpy as np
+        self.world, self.rank, self.k = world, rank, in_flight
+        self.ranges = split_stripes(hdr.height, world)
+        self.frames = [make_frame(i) for i in range(in_flight)]
+        self.bands = [BandContext(hdr, self.ranges, rank, frame_handle=f.h) for f in self.frames]
+        # in_rows of every rank (the plan is a pure function of the geometry, but band_rows() lives in the library)
+        mine = list(self.bands[0].in_rows)
+        self.in_rows_of = [tuple(x) for x in _all_gather(mine)]
+        self.epoch = [0] * in_flight
+        # flags: uint32[world] per context, in this GPU's memory
+        self.flags = []
+        for _ in range(in_flight):
+            p = C.c_void_p()
+            lib.check(lib.malloc(C.byref(p), 4 * max(world, 64)), "malloc(flags)")
+            lib.check(lib.memset(p, 0, 4 * max(world, 64), None))
+            self.flags.append(p.value)
+        lib.check(lib.stream_sync(None))
+        payload = []
+        for i in range(in_flight):
+            h = (C.c_uint8 * 64)()
+            lib.check(lib.ipc_get_handle(C.c_void_p(self.flags[i]), h), "ipc_get_handle(flags)")
+            payload.append((self.bands[i].ipc_handle(), bytes(h)))
+        everyone = _all_gather(payload)
+        self.peer_flags = [dict() for _ in range(in_flight)]
+        b0 = self.bands[0]
+        self.pull_from = sorted({peer for peer, _, _ in b0.plan()})
+        self.pulled_by = pullers_of(hdr.height, self.ranges, rank, self.in_rows_of, b0.geom.plane_h[0])
+        for i in range(in_flight):
+            self.bands[i].open_peers([everyone[r][i][0] for r in range(world)])
+            for peer in self.pull_from:
+                buf = (C.c_uint8 * 64).from_buffer_copy(everyone[peer][i][1])
+                q = C.c_void_p()
+                lib.check(lib.ipc_open_handle(buf, C.byref(q)), "ipc_open_handle(flags)")
+                self.peer_flags[i][peer] = q.value
+
+    def step(self, i, stages=14):
+        """One picture on context i: pull the halo, tell the owners, wait for the ranks that read this rank's rows, filter."""
+        band, f = self.bands[i], self.frames[i]
+        self.epoch[i] += 1
+        e = self.epoch[i]
+        st = C.c_void_p(lib.frame_stream(f.h))
+        band.pull_halo()
+        for peer in self.pull_from:
+            lib.check(lib.flag_signal(st, C.c_void_p(self.peer_flags[i][peer] + 4 * self.rank), e), "flag_signal")
+        for peer in self.pulled_by:
+            lib.check(lib.flag_wait(st, C.c_void_p(self.flags[i] + 4 * peer), e), "flag_wait")
+        if not band.empty:
+            f.submit(stages, upload=False)
+
+    def close(self):
+        for i in range(self.k):
+            for q in self.peer_flags[i].values():
+                lib.ipc_close_handle(C.c_void_p(q))
+            self.bands[i].close()
+            self.frames[i].h = None
+            lib.free(C.c_void_p(self.flags[i]))
+
+
+def _all_gather(obj):
+    import torch.distributed as dist
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, obj)
+    return out
+
+
+def run_band_split(w, h, bpc, steps=10, in_flight=2, check=True, seed=4):
+    """The post-filters (deblock + CDEF + LR) of one w x h picture split over the ranks of the current torch.distributed
+    job (one process per GPU, NCCL or gloo for the set-up only).  Returns, on every rank, a dict with the time per picture
+    (max over ranks, CUDA events), the halo bytes and -- with check -- whether every band equals the oracle's
+    whole-picture result bit for bit (rank 0 runs the oracle)."""
+    import os
+    import sys
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from .synth import framegen
+    rank, world = dist.get_rank(), dist.get_world_size()
+    s = framegen.generate(w, h, bpc, seed=seed)          # same seed on every rank: the same picture
+    start = framegen.recon_input_planes(s)
+
+    def make_frame(_):
+        d = framegen.DeviceFrame(s)
+        d.load_batch()
+        return d
+
+    ring = BandRing(s.hdr, world, rank, make_frame, in_flight)
+    for i in range(in_flight):
+        ring.bands[i].upload_owned(start)
+        ring.frames[i].submit(14, upload=True)          # metadata resident (also a warm-up of the band's kernels)
+        ring.frames[i].wait()
+        ring.bands[i].upload_owned(start)
+    torch.cuda.synchronize(); dist.barrier()             # every rank's own rows are resident
+    streams = [torch.cuda.ExternalStream(lib.frame_stream(f.h)) for f in ring.frames]
+    for n in range(2 * in_flight):
+        ring.step(n % in_flight)
+    torch.cuda.synchronize(); dist.barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = [torch.cuda.Event(enable_timing=True) for _ in streams]
+    e0.record(streams[0])
+    for st in streams[1:]:
+        st.wait_event(e0)
+    for n in range(steps):
+        ring.step(n % in_flight)
+    for st, ev in zip(streams, e1):
+        ev.record(st)
+    torch.cuda.synchronize(); dist.barrier()
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([max(e0.elapsed_time(ev) for ev in e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    ok = None
+    if check:
+        # the deblock stage is in place: restore the inputs, run one picture, compare this band
+        ring.bands[0].upload_owned(start)
+        torch.cuda.synchronize(); dist.barrier()
+        ring.step(0); ring.frames[0].wait()
+        out = [np.zeros_like(p) for p in s.ref]
+        ring.bands[0].readback_owned(out)
+        lst = [None]
+        if rank == 0:
+            root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+            sys.path.insert(0, os.path.join(root, "tests"))
+            import framecheck, refharness            # test infrastructure: the checker, not the product path
+            exp = framecheck.oracle_frame(refharness.load(), s, 14, n_tc=os.cpu_count() or 1, start_planes=start)
+            lst = [[e.copy() for e in exp]]
+        dist.broadcast_object_list(lst, src=0)
+        exp = lst[0]
+        lo, hi = ring.bands[0].out_rows
+        good = True
+        for p in range(3):
+            a, b = (lo, hi) if p == 0 else (lo >> 1, (hi + 1) >> 1)
+            good &= bool(np.array_equal(exp[p][a:b], out[p][a:b, :exp[p].shape[1]]))
+        g = torch.tensor([1 if good else 0], device=dev)
+        dist.all_reduce(g, op=dist.ReduceOp.MIN)
+        ok = bool(g.item())
+        torch.cuda.synchronize(); dist.barrier()
+    hb = torch.tensor([float(ring.bands[0].halo_bytes())], dtype=torch.float64, device=dev)
+    dist.all_reduce(hb, op=dist.ReduceOp.MAX)
+    ring.close()
+    return {"what": "post-filters (deblock + CDEF + LR) of one picture split by stripe rows over the GPUs, halo rows pulled peer to peer, "
+                    "flag-ordered (no collective)", "width": w, "height": h, "bpc": bpc, "n_gpus": world, "pictures_in_flight": in_flight,
+            "ms_per_frame": ms, "mpixel_per_s": w * h / ms / 1e3, "max_halo_bytes_per_rank": hb.item(), "bit_exact_vs_oracle": ok}

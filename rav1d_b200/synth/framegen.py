@@ -817,6 +817,29 @@ def _plane_args(planes):
     return data, strides
 
 
+def sort_luma_first(s):
+    """Reorders the put items and every transform-size bucket of the residual items luma first and records the counts
+    rb200_frame_set_plane_counts wants (s.n_mc_luma, s.itx_luma_counts), so that the reconstruction can run as a luma and
+    a chroma chain.  Frames with intra items are left alone (their items name residuals by index)."""
+    if len(getattr(s, "intra_items", ())):
+        return False
+    mc = s.mc_items
+    s.mc_items = mc[np.argsort(mc["plane"] != 0, kind="stable")]
+    s.n_mc_luma = int((mc["plane"] == 0).sum())
+    itx = s.itx_items.copy()
+    luma = np.zeros(19, np.int32)
+    off = 0
+    for t in range(19):
+        n = int(s.itx_counts[t])
+        b = itx[off:off + n]
+        itx[off:off + n] = b[np.argsort(b["plane"] != 0, kind="stable")]
+        luma[t] = int((b["plane"] == 0).sum())
+        off += n
+    s.itx_items = itx
+    s.itx_luma_counts = luma
+    return True
+
+
 class DeviceFrame:
     """Host-side driver of one rb200 frame object: fills the pinned staging from a SynthFrame."""
 
@@ -885,6 +908,8 @@ class DeviceFrame:
             lib.check(lib.frame_reserve_lf_blocks(self.h, len(lfb)), "reserve_lf_blocks")
             lib.np_view(lib.frame_lf_blocks(self.h), lib.LF_BLOCK_DT, len(lfb))[:] = lfb
             lib.check(lib.frame_set_lf_block_count(self.h, len(lfb)))
+        if hasattr(s, "itx_luma_counts"):          # lists sorted luma first (sort_luma_first)
+            lib.check(lib.frame_set_plane_counts(self.h, s.n_mc_luma, s.itx_luma_counts.ctypes.data_as(C.POINTER(C.c_int32))))
         comp = getattr(s, "comp_items", None)
         if comp is not None and len(comp):
             lib.check(lib.frame_reserve_comp_items(self.h, len(comp)), "reserve_comp_items")

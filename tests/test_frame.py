@@ -359,6 +359,51 @@ def test_int16_transport_is_refused_for_8bit(rb):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("w,h,bpc", [(424, 300, 10), (200, 120, 8), (264, 136, 12)])
+def test_luma_and_chroma_reconstruction_chains(rb, ref, w, h, bpc):
+    """rb200_frame_set_plane_counts: lists sorted luma first, reconstruction and post-filters as two chains on two streams;
+    several submits of the same context back to back (the chains join at the end of every submit)."""
+    s = framegen.generate(w, h, bpc, seed=31)
+    a = framecheck.oracle_frame(ref, s, 15)
+    assert framegen.sort_luma_first(s)
+    d = framegen.DeviceFrame(s)
+    try:
+        d.load_batch(); d.set_ref_from_host(s.ref)
+        for it in range(3):
+            d.submit(15, upload=it == 0)
+        d.wait()
+        framecheck.assert_planes_equal(a, framecheck.visible(s, d.readback()), "plane chains")
+        rb.check(rb.frame_set_plane_streams(d.h, 0))
+        d.submit(15, upload=False); d.wait()
+        framecheck.assert_planes_equal(a, framecheck.visible(s, d.readback()), "one stream, sorted lists")
+    finally:
+        d.close()
+
+
+@pytest.mark.gpu
+def test_validate_names_bad_records(rb):
+    """rb200_frame_validate: the staged batch as rb200_frame_submit will read it; a bad record is an error code, not a fault."""
+    s = framegen.generate(200, 120, 10, seed=9, obmc_frac=0.2)
+    d = framegen.DeviceFrame(s)
+    try:
+        d.load_batch(); d.set_ref_from_host(s.ref)
+        counts = (C.c_int32 * 19)(*[int(c) for c in s.itx_counts])
+        args = (d.h, s.n_coefs, counts, len(s.mc_items), R)
+        assert rb.frame_validate(*args) == 0, rb.last_error()
+        mc = rb.np_view(rb.frame_mc_items(d.h), rb.MC_ITEM_DT, len(s.mc_items))
+        itx = rb.np_view(rb.frame_itx_items(d.h), rb.ITX_ITEM_DT, len(s.itx_items))
+        for arr, field, bad, word in ((mc, "ref", 5, b"reference slot"), (mc, "dst_x", 4000, b"leaves plane"), (mc, "filter2d", 11, b"filter"),
+                                      (itx, "cf_off", s.n_coefs, b"coefficients"), (itx, "txtp", 17, b"type"), (itx, "x", 3000, b"leaves plane")):
+            keep = arr[field][3].copy()
+            arr[field][3] = bad
+            assert rb.frame_validate(*args) != 0 and word in rb.last_error(), (field, rb.last_error())
+            arr[field][3] = keep
+        assert rb.frame_validate(*args) == 0
+    finally:
+        d.close()
+
+
+@pytest.mark.gpu
 def test_resubmit_is_idempotent(rb, ref):
     """Submitting the same batch twice gives the same picture (recon overwrites, filters are
     out of place or restart from recon)."""

@@ -95,6 +95,8 @@ def test_banded_filters_match_whole_picture(rb, ref, w, h, bpc, n):
             for peer, _, _ in b.plan():
                 b.peer_bases[peer] = ctxs[peer][1].plane_block()[0]
             b.pull_halo()
+        for d, b in ctxs:                       # deblocking is in place: every pull is complete before any band filters
+            d.wait()                            # (between GPUs this is the flag protocol of multigpu.BandRing)
         for d, b in ctxs:
             if not b.empty:
                 d.submit(14)
@@ -109,3 +111,35 @@ def test_banded_filters_match_whole_picture(rb, ref, w, h, bpc, n):
             b.peer_bases = {}
             b.h = None
             d.close()
+
+
+def test_pullers_are_the_mirror_of_the_halo_plans():
+    """A rank waits for exactly the ranks whose halo plan names it (multigpu.pullers_of)."""
+    from rav1d_b200 import multigpu as mg
+    for height, n in ((4320, 8), (2160, 4), (1080, 3), (600, 8), (100, 4)):
+        ranges = mg.split_stripes(height, n)
+        # stand-in for rb200_frame_band_rows(): what a band reads = its own rows widened by the stages' reach
+        in_rows = []
+        for r in range(n):
+            lo, hi = mg.owned_rows(height, *ranges[r])
+            in_rows.append((max(lo - 84, 0), min(hi + 24, height)) if hi > lo else (0, 0))
+        plans = [mg.halo_plan(height, ranges, r, in_rows[r]) if ranges[r][1] > ranges[r][0] else [] for r in range(n)]
+        for r in range(n):
+            expect = sorted(q for q in range(n) if any(peer == r for peer, _, _ in plans[q]))
+            assert sorted(mg.pullers_of(height, ranges, r, in_rows)) == expect, (height, n, r)
+
+
+@pytest.mark.gpu
+def test_band_split_across_gpus():
+    """The flag-ordered band split on real peers: one process per GPU (torchrun), every band bit-exact against the oracle's
+    whole-picture result.  Needs two devices; the single-GPU test box skips it (tools/run_band_split.py is the same run)."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    n = min(n, 4)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+                        "--master-port", "29534", os.path.join(ROOT, "tools", "run_band_split.py"), "1280", "720", "10", "--steps", "4"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '"bit_exact_vs_oracle": true' in r.stdout, r.stdout[-1000:]
