@@ -358,12 +358,15 @@ def run_gpu(args, s, wl):
         lib.check(lib.frame_set_stream(d.h, None))
         lib.check(lib.frame_set_plane_streams(d.h, args.plane_streams))
     streams = [torch.cuda.ExternalStream(lib.frame_stream(d.h)) for d in ctxs]
-    if args.coefs == "gather16" and bpc == 8:
+    if args.coefs in ("gather16", "packed16") and bpc == 8:
         args.coefs = "gather"                # 8-bit pictures carry int16 coefficients anyway
-    e2e_upload = {"gather": 3, "zerocopy": 2, "copy": 1, "gather16": 4}[args.coefs]
+    e2e_upload = {"gather": 3, "zerocopy": 2, "copy": 1, "gather16": 4, "packed16": 5}[args.coefs]
     if args.coefs == "gather16":             # what the front end does when it fills the staging: int16 + escapes
         for d in ctxs:
             lib.check(lib.frame_pack_coef16(d.h, s.n_coefs), "frame_pack_coef16")
+    if args.coefs == "packed16":             # ... or one contiguous int16 stream of the blocks' leading columns
+        for d in ctxs:
+            lib.check(lib.frame_pack_coef_stream(d.h, s.n_coefs, counts, stages), "frame_pack_coef_stream")
 
     def e2e_frame(i):
         d = ctxs[i % N_CTX]
@@ -398,8 +401,12 @@ def run_gpu(args, s, wl):
         if args.coefs != "copy":   # only the leading ncols columns of every block cross PCIe
             from rav1d_b200.lib import TX_DIMS
             sh = np.array([min(TX_DIMS[t][1], 32) for t in range(19)])[s.itx_items["tx"]]
-            h2d += int((s.itx_items["ncols"].astype(np.int64) * sh).sum()) * (2 if args.coefs == "gather16" else cs)
-            if args.coefs == "gather16":
+            per_block = s.itx_items["ncols"].astype(np.int64) * sh
+            if args.coefs == "packed16":
+                h2d += int(((per_block + 7) & ~7).sum()) * 2 + 4 * len(s.itx_items)   # stream (blocks padded to 16 bytes) + offsets
+            else:
+                h2d += int(per_block.sum()) * (2 if args.coefs == "gather16" else cs)
+            if args.coefs in ("gather16", "packed16"):
                 h2d += 8 * int((np.abs(s.coef.astype(np.int64)) > 32767).sum())      # escapes (upper bound: whole buffer)
         else:
             h2d += s.n_coefs * cs
@@ -463,6 +470,7 @@ def run_gpu(args, s, wl):
                         "d2h_bytes_per_step": d2h * FRAMES_PER_STEP,
                         "coefficients": {"gather": "gather kernel over pinned host memory, column-bounded", "copy": "H2D copy",
                                          "gather16": "int16 transport + escape list: gather kernel over pinned host memory, column-bounded, widened on the device",
+                                         "packed16": "one contiguous int16 stream of the blocks' non-zero columns + escape list: DMA copy, spread into the int32 layout on the device",
                                          "zerocopy": "transforms read pinned host memory, column-bounded"}[args.coefs]},
                 "gpu_launches": launches}
     for d in ctxs:
@@ -538,9 +546,10 @@ def main():
     ap.add_argument("--streams", type=int, default=N_CTX, help="resident legs: 1 = every frame context on one CUDA stream (launch lists), otherwise one stream per context")
     ap.add_argument("--no-band-split", action="store_true", help="N > 1: skip the 8K band-split leg (BASELINE configs[3])")
     ap.add_argument("--plane-streams", type=int, default=1, help="1 (default): luma and chroma post-filter chains of a frame on two streams; 0: one stream")
-    ap.add_argument("--coefs", default="gather16", choices=["gather16", "gather", "zerocopy", "copy"],
-                    help="e2e leg, how coefficients cross PCIe: as int16 + escapes, a gather kernel pulling each block's non-zero "
-                         "columns into HBM and widening them (default for 16-bit pictures); the same gather on the int32 staging; the "
+    ap.add_argument("--coefs", default="packed16", choices=["packed16", "gather16", "gather", "zerocopy", "copy"],
+                    help="e2e leg, how coefficients cross PCIe: as one contiguous int16 stream of the blocks' non-zero columns + escapes, "
+                         "DMA-copied and spread out on the device (default for 16-bit pictures); as int16 + escapes in the block layout, a "
+                         "gather kernel pulling each block's non-zero columns into HBM and widening them; the same gather on the int32 staging; the "
                          "transforms read pinned memory directly; or the whole buffer is H2D-copied")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)

@@ -596,9 +596,13 @@ int rb200_frame_stage_planes(Rb200Frame *f, int which, Rb200Planes *out);
  * columns into the device mirror with wide loads first and the transforms read device memory;
  * RB200_UPLOAD_GATHER_COEF16 (16-bit pictures): like RB200_UPLOAD_GATHER_COEF, but the coefficients cross PCIe as
  * int16 from rb200_frame_coef16_buffer() -- half the bytes; the few that do not fit (AV1 allows 18 + bits at 10 / 12 bpc)
- * travel as {index, value} records in rb200_frame_coef_escapes() and are patched in on the device. */
+ * travel as {index, value} records in rb200_frame_coef_escapes() and are patched in on the device;
+ * RB200_UPLOAD_PACKED_COEF16 (16-bit pictures): the coefficients travel as ONE contiguous int16 stream -- each block's
+ * leading ncols columns back to back (rb200_frame_coef_stream(), block i at rb200_frame_coef_stream_offsets()[i],
+ * offsets multiples of 8) -- so a plain DMA copy moves exactly the bytes that matter at the link's full rate; a kernel
+ * then spreads the blocks into the int32 device array.  Escapes as for RB200_UPLOAD_GATHER_COEF16. */
 enum { RB200_UPLOAD_NONE = 0, RB200_UPLOAD_ALL = 1, RB200_UPLOAD_ZERO_COPY_COEF = 2, RB200_UPLOAD_GATHER_COEF = 3,
-       RB200_UPLOAD_GATHER_COEF16 = 4 };
+       RB200_UPLOAD_GATHER_COEF16 = 4, RB200_UPLOAD_PACKED_COEF16 = 5 };
 /* int16 transport of the coefficients of a 16-bit picture.  The staging has the indexing of rb200_frame_coef_buffer()
  * (element i of one is element i of the other).  A front end writes it directly -- decode_coefs stores `dq as i16` and
  * pushes an escape when dq does not fit (src/recon.rs:1417: |dq| < 128 << bitdepth) -- or lets
@@ -609,6 +613,14 @@ int rb200_frame_reserve_coef_escapes(Rb200Frame *f, int max_escapes);
 Rb200CoefEscape *rb200_frame_coef_escapes(Rb200Frame *f);
 int rb200_frame_set_coef_escape_count(Rb200Frame *f, int n);
 int rb200_frame_pack_coef16(Rb200Frame *f, size_t n_coefs);
+/* The packed stream of RB200_UPLOAD_PACKED_COEF16.  A front end appends to it directly (decode_coefs knows a block's
+ * last non-zero column when it is done with the block); rb200_frame_pack_coef_stream builds it -- stream, offsets,
+ * escapes, length -- from the int32 staging and the staged residual items (all of them: itx_counts plus the intra
+ * levels' residuals when stages has RB200_STAGE_INTRA). */
+int16_t *rb200_frame_coef_stream(Rb200Frame *f);             /* [max_coefs + 8 * max_itx_items], pinned, allocated on first use */
+uint32_t *rb200_frame_coef_stream_offsets(Rb200Frame *f);    /* [max_itx_items], parallel to rb200_frame_itx_items() */
+int rb200_frame_set_coef_stream_length(Rb200Frame *f, size_t n_elements);
+int rb200_frame_pack_coef_stream(Rb200Frame *f, size_t n_coefs, const int32_t itx_counts[RB200_N_RECT_TX_SIZES], int stages);
 int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t itx_counts[RB200_N_RECT_TX_SIZES],
                        int n_mc_items, int stages, int upload);
 int rb200_frame_wait(Rb200Frame *f);

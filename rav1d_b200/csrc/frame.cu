@@ -41,6 +41,7 @@ struct Rb200Frame {
     void *h_coef, *d_coef;
     int16_t *h_coef16;                              // int16 transport of a 16-bit picture's coefficients (allocated on first use)
     Rb200CoefEscape *h_esc, *d_esc; int max_esc, n_esc;
+    int16_t *h_pk, *d_pk; uint32_t *h_pkoff, *d_pkoff; size_t n_pk;   // packed int16 coefficient stream (RB200_UPLOAD_PACKED_COEF16)
     Rb200ItxItem *h_itx, *d_itx;
     Rb200McItem *h_mc, *d_mc;
     Rb200CompItem *h_comp, *d_comp; int max_comp, n_comp;
@@ -275,6 +276,10 @@ extern "C" int rb200_frame_destroy(Rb200Frame *f) {
     if (f->plane_mem_fg) cudaFree(f->plane_mem_fg);
     if (f->h_coef) cudaFreeHost(f->h_coef);
     if (f->h_coef16) cudaFreeHost(f->h_coef16);
+    if (f->h_pk) cudaFreeHost(f->h_pk);
+    if (f->d_pk) cudaFree(f->d_pk);
+    if (f->h_pkoff) cudaFreeHost(f->h_pkoff);
+    if (f->d_pkoff) cudaFree(f->d_pkoff);
     if (f->h_esc) cudaFreeHost(f->h_esc);
     if (f->d_esc) cudaFree(f->d_esc);
     if (f->d_coef) cudaFree(f->d_coef);
@@ -631,6 +636,60 @@ extern "C" int rb200_frame_pack_coef16(Rb200Frame *f, size_t n_coefs) {
             f->h_esc[f->n_esc].index = (uint32_t)i; f->h_esc[f->n_esc].value = v; f->n_esc++;
         }
     }
+    return 0;
+}
+
+static int ensure_coef_stream(Rb200Frame *f) {
+    if (f->h_pk) return 0;
+    const size_t n = f->max_coefs + 8 * (size_t)f->max_itx + 8;
+    RB_CUDA(cudaMallocHost((void **)&f->h_pk, n * sizeof(int16_t)));
+    RB_CUDA(cudaMalloc((void **)&f->d_pk, n * sizeof(int16_t)));
+    RB_CUDA(cudaMallocHost((void **)&f->h_pkoff, ((size_t)f->max_itx + 1) * sizeof(uint32_t)));
+    RB_CUDA(cudaMalloc((void **)&f->d_pkoff, ((size_t)f->max_itx + 1) * sizeof(uint32_t)));
+    return 0;
+}
+extern "C" int16_t *rb200_frame_coef_stream(Rb200Frame *f) { return f && f->cs == 4 && !ensure_coef_stream(f) ? f->h_pk : nullptr; }
+extern "C" uint32_t *rb200_frame_coef_stream_offsets(Rb200Frame *f) { return f && f->cs == 4 && !ensure_coef_stream(f) ? f->h_pkoff : nullptr; }
+extern "C" int rb200_frame_set_coef_stream_length(Rb200Frame *f, size_t n) {
+    if (!f || n > f->max_coefs + 8 * (size_t)f->max_itx) return set_error(-22, "frame_set_coef_stream_length: bad length");
+    f->n_pk = n;
+    return 0;
+}
+extern "C" int rb200_frame_pack_coef_stream(Rb200Frame *f, size_t n_coefs, const int32_t itx_counts[RB200_N_RECT_TX_SIZES], int stages) {
+    if (!f || !itx_counts || n_coefs > f->max_coefs) return set_error(-22, "frame_pack_coef_stream: bad argument");
+    if (f->cs != 4) return set_error(-22, "frame_pack_coef_stream: 8-bit pictures carry int16 coefficients already");
+    int r = ensure_coef_stream(f);
+    if (r) return r;
+    int n_itx = 0;
+    for (int t = 0; t < RB200_N_RECT_TX_SIZES; t++) n_itx += itx_counts[t];
+    if (stages & RB200_STAGE_INTRA)
+        for (int l = 0; l < f->n_levels; l++)
+            for (int t = 0; t < RB200_N_RECT_TX_SIZES; t++) n_itx += f->intra_itx_counts[l * RB200_N_RECT_TX_SIZES + t];
+    if (n_itx > f->max_itx) return set_error(-22, "frame_pack_coef_stream: more residual items than the frame holds");
+    static const uint8_t txw[RB200_N_RECT_TX_SIZES] = {4, 8, 16, 32, 64, 4, 8, 8, 16, 16, 32, 32, 64, 4, 16, 8, 32, 16, 64};
+    static const uint8_t txh[RB200_N_RECT_TX_SIZES] = {4, 8, 16, 32, 64, 8, 4, 16, 8, 32, 16, 64, 32, 16, 4, 32, 8, 64, 16};
+    const int32_t *c = (const int32_t *)f->h_coef;
+    size_t pos = 0;
+    f->n_esc = 0;
+    for (int i = 0; i < n_itx; i++) {
+        const Rb200ItxItem &it = f->h_itx[i];
+        if (it.tx >= RB200_N_RECT_TX_SIZES) return set_error(-22, "frame_pack_coef_stream: item %d has transform size %d", i, it.tx);
+        const int sw = txw[it.tx] < 32 ? txw[it.tx] : 32, sh = txh[it.tx] < 32 ? txh[it.tx] : 32;
+        const int nc = it.ncols && it.ncols < sw ? it.ncols : sw, count = nc * sh;
+        if ((size_t)it.cf_off + count > n_coefs) return set_error(-22, "frame_pack_coef_stream: item %d reads beyond the coefficients", i);
+        f->h_pkoff[i] = (uint32_t)pos;
+        for (int k = 0; k < count; k++) {
+            const int32_t v = c[it.cf_off + k];
+            f->h_pk[pos + k] = (int16_t)v;
+            if (v != (int16_t)v) {
+                if (f->n_esc == f->max_esc && (r = rb200_frame_reserve_coef_escapes(f, f->max_esc ? 2 * f->max_esc : 4096))) return r;
+                f->h_esc[f->n_esc].index = it.cf_off + (uint32_t)k; f->h_esc[f->n_esc].value = v; f->n_esc++;
+            }
+        }
+        for (int k = count; k & 7; k++) f->h_pk[pos + k] = 0;
+        pos += (size_t)(count + 7) & ~(size_t)7;
+    }
+    f->n_pk = pos;
     return 0;
 }
 
@@ -1078,7 +1137,9 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
                 RB_CUDA(cudaMemcpyAsync(f->d_coef, f->h_coef, n_coefs * f->cs, cudaMemcpyHostToDevice, st));
             if (upload == RB200_UPLOAD_GATHER_COEF16 && (f->cs != 4 || !f->h_coef16))
                 return set_error(-22, "frame_submit: RB200_UPLOAD_GATHER_COEF16 needs a 16-bit picture whose rb200_frame_coef16_buffer() was filled");
-            const bool gather = (upload == RB200_UPLOAD_GATHER_COEF || upload == RB200_UPLOAD_GATHER_COEF16) && n_itx;
+            if (upload == RB200_UPLOAD_PACKED_COEF16 && (f->cs != 4 || !f->h_pk))
+                return set_error(-22, "frame_submit: RB200_UPLOAD_PACKED_COEF16 needs a 16-bit picture whose rb200_frame_coef_stream() was filled");
+            const bool gather = (upload == RB200_UPLOAD_GATHER_COEF || upload == RB200_UPLOAD_GATHER_COEF16 || upload == RB200_UPLOAD_PACKED_COEF16) && n_itx;
             if (gather) {
                 // The coefficient gather runs on a high-priority side stream: its CTAs are scheduled ahead of the
                 // stage kernels of other frames, so the PCIe link stays busy, and it overlaps this frame's
@@ -1094,7 +1155,14 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
                 RB_CUDA(cudaStreamWaitEvent(f->up_stream, f->up_fork, 0));
                 RB_CUDA(cudaMemcpyAsync(f->d_itx, f->h_itx, (size_t)n_itx * sizeof(Rb200ItxItem), cudaMemcpyHostToDevice, f->up_stream));
                 int rg;
-                if (upload == RB200_UPLOAD_GATHER_COEF16) {
+                if (upload == RB200_UPLOAD_PACKED_COEF16) {
+                    // plain DMA of the stream and its offsets, then the blocks are spread out on the device
+                    if (f->n_pk) RB_CUDA(cudaMemcpyAsync(f->d_pk, f->h_pk, f->n_pk * sizeof(int16_t), cudaMemcpyHostToDevice, f->up_stream));
+                    RB_CUDA(cudaMemcpyAsync(f->d_pkoff, f->h_pkoff, (size_t)n_itx * sizeof(uint32_t), cudaMemcpyHostToDevice, f->up_stream));
+                    if (f->n_esc)
+                        RB_CUDA(cudaMemcpyAsync(f->d_esc, f->h_esc, (size_t)f->n_esc * sizeof(Rb200CoefEscape), cudaMemcpyHostToDevice, f->up_stream));
+                    if ((rg = coef_expand16_launch(f->d_pk, f->d_pkoff, (int32_t *)f->d_coef, f->d_itx, n_itx, f->d_esc, f->n_esc, f->up_stream, &f->launches))) return rg;
+                } else if (upload == RB200_UPLOAD_GATHER_COEF16) {
                     if (f->n_esc)
                         RB_CUDA(cudaMemcpyAsync(f->d_esc, f->h_esc, (size_t)f->n_esc * sizeof(Rb200CoefEscape), cudaMemcpyHostToDevice, f->up_stream));
                     if ((rg = coef_gather16_launch(f->h_coef16, (int32_t *)f->d_coef, f->d_itx, n_itx, f->d_esc, f->n_esc, f->up_stream, &f->launches))) return rg;
@@ -1179,7 +1247,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
                                      su, f->d_counters + 1, &f->tm_refs))) return r;
             f->launches++;
         }
-        if ((upload == RB200_UPLOAD_GATHER_COEF || upload == RB200_UPLOAD_GATHER_COEF16) && n_itx) {
+        if ((upload == RB200_UPLOAD_GATHER_COEF || upload == RB200_UPLOAD_GATHER_COEF16 || upload == RB200_UPLOAD_PACKED_COEF16) && n_itx) {
             RB_CUDA(cudaStreamWaitEvent(st, f->up_join, 0));
             RB_CUDA(cudaStreamWaitEvent(su, f->up_join, 0));
         }
@@ -1225,7 +1293,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
             f->launches++;
         }
         MARK(2);
-        if ((upload == RB200_UPLOAD_GATHER_COEF || upload == RB200_UPLOAD_GATHER_COEF16) && n_itx) RB_CUDA(cudaStreamWaitEvent(st, f->up_join, 0));
+        if ((upload == RB200_UPLOAD_GATHER_COEF || upload == RB200_UPLOAD_GATHER_COEF16 || upload == RB200_UPLOAD_PACKED_COEF16) && n_itx) RB_CUDA(cudaStreamWaitEvent(st, f->up_join, 0));
         // The residual launches (one per transform size present) write disjoint pixels: they are dealt to two streams,
         // the heavier buckets first, so that they overlap and fill each other's tails.
         {

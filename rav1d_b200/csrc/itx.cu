@@ -195,6 +195,41 @@ __global__ void coef_escape_kernel(int32_t *__restrict__ d_cf, const Rb200CoefEs
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) d_cf[esc[i].index] = esc[i].value;
 }
 
+// packed stream already in HBM: one warp per block, 16-byte loads, two 16-byte stores per load
+__global__ void __launch_bounds__(256)
+coef_expand16_kernel(const int16_t *__restrict__ stream, const uint32_t *__restrict__ offs, int32_t *__restrict__ d_cf,
+                     const Rb200ItxItem *__restrict__ items, int n) {
+    const int lane = threadIdx.x & 31;
+    const int n_warps = (int)((gridDim.x * (unsigned)blockDim.x) >> 5);
+    for (int i = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5); i < n; i += n_warps) {
+        const Rb200ItxItem it = items[i];
+        const int w = tx_w(it.tx), h = tx_h(it.tx), sw = w < 32 ? w : 32, sh = h < 32 ? h : 32;
+        const int nc = it.ncols && it.ncols < sw ? it.ncols : sw;
+        const int count = nc * sh;                      // a multiple of 4; the stream pads every block to a multiple of 8
+        const uint4 *src = (const uint4 *)(stream + offs[i]);
+        int32_t *dst = d_cf + it.cf_off;
+        for (int k = lane; 8 * k < count; k += 32) {
+            const uint4 q = __ldcs(src + k);
+            ((int4 *)dst)[2 * k] = make_int4((int)(short)(q.x & 0xffff), (int)q.x >> 16, (int)(short)(q.y & 0xffff), (int)q.y >> 16);
+            if (8 * k + 4 < count)
+                ((int4 *)dst)[2 * k + 1] = make_int4((int)(short)(q.z & 0xffff), (int)q.z >> 16, (int)(short)(q.w & 0xffff), (int)q.w >> 16);
+        }
+    }
+}
+
+int coef_expand16_launch(const int16_t *d_stream, const uint32_t *d_off, int32_t *d_cf, const Rb200ItxItem *d_items, int n,
+                         const Rb200CoefEscape *d_esc, int n_esc, cudaStream_t st, int *launches) {
+    if (n <= 0) return 0;
+    coef_expand16_kernel<<<imin((n + 7) / 8, 148 * 8), 256, 0, st>>>(d_stream, d_off, d_cf, d_items, n);
+    if (launches) ++*launches;
+    if (n_esc > 0) {
+        coef_escape_kernel<<<imin((n_esc + 255) / 256, 148), 256, 0, st>>>(d_cf, d_esc, n_esc);
+        if (launches) ++*launches;
+    }
+    RB_LAUNCH_CHECK();
+    return 0;
+}
+
 int coef_gather16_launch(const int16_t *h_cf16, int32_t *d_cf, const Rb200ItxItem *d_items, int n, const Rb200CoefEscape *d_esc,
                          int n_esc, cudaStream_t st, int *launches) {
     if (n <= 0) return 0;

@@ -23,4 +23,8 @@ int lr_plane_launch_tma(const uint8_t *cdef, const uint8_t *dbl, uint8_t *out, i
 int coef_gather16_launch(const int16_t *h_cf16, int32_t *d_cf, const Rb200ItxItem *d_items, int n, const Rb200CoefEscape *d_esc,
                          int n_esc, cudaStream_t st, int *launches);
 
+// packed int16 stream (RB200_UPLOAD_PACKED_COEF16): block i's leading columns at d_stream + d_off[i] -> int32 at its cf_off
+int coef_expand16_launch(const int16_t *d_stream, const uint32_t *d_off, int32_t *d_cf, const Rb200ItxItem *d_items, int n,
+                         const Rb200CoefEscape *d_esc, int n_esc, cudaStream_t st, int *launches);
+
 }  // namespace rb200

@@ -280,6 +280,11 @@ frame_validate = _sig("rb200_frame_validate", _i, _vp, _sz, C.POINTER(C.c_int32)
 flag_signal = _sig("rb200_flag_signal", _i, _vp, _vp, C.c_uint32)
 flag_wait = _sig("rb200_flag_wait", _i, _vp, _vp, C.c_uint32)
 UPLOAD_GATHER_COEF16 = 4
+UPLOAD_PACKED_COEF16 = 5
+frame_pack_coef_stream = _sig("rb200_frame_pack_coef_stream", _i, _vp, _sz, C.POINTER(C.c_int32), _i)
+frame_coef_stream = _sig("rb200_frame_coef_stream", _vp, _vp)
+frame_coef_stream_offsets = _sig("rb200_frame_coef_stream_offsets", _vp, _vp)
+frame_set_coef_stream_length = _sig("rb200_frame_set_coef_stream_length", _i, _vp, _sz)
 frame_coef16_buffer = _sig("rb200_frame_coef16_buffer", _vp, _vp)
 frame_pack_coef16 = _sig("rb200_frame_pack_coef16", _i, _vp, _sz)
 frame_reserve_coef_escapes = _sig("rb200_frame_reserve_coef_escapes", _i, _vp, _i)

@@ -59,6 +59,10 @@ def product_frame(s, stages, start_planes=None, upload=1):
             d.upload(0, start_planes)
         if upload == lib.UPLOAD_GATHER_COEF16:      # what a front end does when it fills the staging: int16 + escapes
             lib.check(lib.frame_pack_coef16(d.h, s.n_coefs), "frame_pack_coef16")
+        if upload == lib.UPLOAD_PACKED_COEF16:      # ... or one contiguous int16 stream of the blocks' leading columns
+            import ctypes as C
+            counts = (C.c_int32 * 19)(*[int(c) for c in s.itx_counts])
+            lib.check(lib.frame_pack_coef_stream(d.h, s.n_coefs, counts, stages), "frame_pack_coef_stream")
         d.submit(stages, upload)
         d.wait()
         return visible(s, d.readback())

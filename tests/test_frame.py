@@ -333,6 +333,7 @@ def test_int16_coefficient_transport(rb, ref, w, h, bpc):
     s = framegen.generate(w, h, bpc, seed=23)
     a = framecheck.oracle_frame(ref, s, R | D)
     framecheck.assert_planes_equal(a, framecheck.product_frame(s, R | D, upload=rb.UPLOAD_GATHER_COEF16), "int16 transport")
+    framecheck.assert_planes_equal(a, framecheck.product_frame(s, R | D, upload=rb.UPLOAD_PACKED_COEF16), "packed int16 stream")
     # large coefficients: every 97th non-zero one pushed to the edge of the legal range (src/recon.rs:1417)
     lim = 128 << bpc
     nz = np.flatnonzero(s.coef)[::97]
@@ -342,6 +343,9 @@ def test_int16_coefficient_transport(rb, ref, w, h, bpc):
     a = framecheck.oracle_frame(ref, s, R | D)
     framecheck.assert_planes_equal(a, framecheck.product_frame(s, R | D, upload=1), "large coefficients, copy")
     framecheck.assert_planes_equal(a, framecheck.product_frame(s, R | D, upload=rb.UPLOAD_GATHER_COEF16), "large coefficients, int16 + escapes")
+    framecheck.assert_planes_equal(a, framecheck.product_frame(s, R | D, upload=rb.UPLOAD_PACKED_COEF16), "large coefficients, packed stream + escapes")
+    s.itx_items = s.itx_items.copy(); s.itx_items["ncols"] = 0
+    framecheck.assert_planes_equal(a, framecheck.product_frame(s, R | D, upload=rb.UPLOAD_PACKED_COEF16), "packed stream, ncols unknown")
 
 
 @pytest.mark.gpu
