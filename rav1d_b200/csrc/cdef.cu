@@ -98,61 +98,51 @@ __device__ __forceinline__ int cdef_filter_px(const int16_t *t, int pitch, int p
     return px + ((sum - (sum < 0) + 8) >> 4);
 }
 
-// cdef_find_dir for one 8x8 block held in an int16 tile; fully unrolled so that the 90
-// partial sums live in registers.  src/cdef_tmpl.c:223-300
+// Direction search of one 8x8 block held in an int16 tile, as the AV1 specification states it (7.15.2, "CDEF direction
+// process"): every pixel is added to one line sum per direction -- line(d, i, j) below is the specification's index
+// into partial[d][] -- and a direction's cost is the sum of its squared line sums, each weighted by 840 / (number of pixels
+// on the line) (Div_Table).  Fully unrolled: the indices are compile-time constants and the 8 x 15 sums live in registers
+// (the entries a direction never touches fold away).  Replaces cdef_find_dir_rust, src/cdef.rs:921.
+__device__ __forceinline__ constexpr int cdef_line(int d, int i, int j) {
+    return d == 0 ? i + j : d == 1 ? i + j / 2 : d == 2 ? i : d == 3 ? 3 + i - j / 2 : d == 4 ? 7 + i - j : d == 5 ? 3 - i / 2 + j
+         : d == 6 ? j : i / 2 + j;
+}
 __device__ __forceinline__ int cdef_find_dir(const int16_t *t, int pitch, int bdmin8, unsigned *var) {
-    int hv0[8] = {0}, hv1[8] = {0}, dg0[15] = {0}, dg1[15] = {0}, al0[11] = {0}, al1[11] = {0}, al2[11] = {0},
-        al3[11] = {0};
+    int partial[8][15] = {};
 #pragma unroll
-    for (int y = 0; y < 8; y++) {
+    for (int i = 0; i < 8; i++) {
 #pragma unroll
-        for (int x = 0; x < 8; x++) {
-            const int px = ((int)t[y * pitch + x] >> bdmin8) - 128;
-            dg0[y + x] += px;
-            al0[y + (x >> 1)] += px;
-            hv0[y] += px;
-            al1[3 + y - (x >> 1)] += px;
-            dg1[7 + y - x] += px;
-            al2[3 - (y >> 1) + x] += px;
-            hv1[x] += px;
-            al3[(y >> 1) + x] += px;
+        for (int j = 0; j < 8; j++) {
+            const int x = ((int)t[i * pitch + j] >> bdmin8) - 128;
+#pragma unroll
+            for (int d = 0; d < 8; d++) partial[d][cdef_line(d, i, j)] += x;
         }
     }
-    unsigned cost[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // pixels on line k of a direction: diagonals (0, 4) 1..8..1 over 15 lines; the half-step directions (odd) 2, 4, 6, then
+    // 8 on the 5 middle lines of 11; rows and columns (2, 6) 8 on each of 8 lines.  weight = 840 / pixels.
+    unsigned cost[8];
 #pragma unroll
-    for (int n = 0; n < 8; n++) {
-        cost[2] += hv0[n] * hv0[n];
-        cost[6] += hv1[n] * hv1[n];
-    }
-    cost[2] *= 105; cost[6] *= 105;
-    constexpr int div_table[7] = {840, 420, 280, 210, 168, 140, 120};
-#pragma unroll
-    for (int n = 0; n < 7; n++) {
-        const int d = div_table[n];
-        cost[0] += (dg0[n] * dg0[n] + dg0[14 - n] * dg0[14 - n]) * d;
-        cost[4] += (dg1[n] * dg1[n] + dg1[14 - n] * dg1[14 - n]) * d;
-    }
-    cost[0] += dg0[7] * dg0[7] * 105;
-    cost[4] += dg1[7] * dg1[7] * 105;
-    auto alt_cost = [&](const int *a) -> unsigned {
+    for (int d = 0; d < 8; d++) {
         unsigned c = 0;
 #pragma unroll
-        for (int m = 0; m < 5; m++) c += a[3 + m] * a[3 + m];
-        c *= 105;
-#pragma unroll
-        for (int m = 0; m < 3; m++) c += (a[m] * a[m] + a[10 - m] * a[10 - m]) * div_table[2 * m + 1];
-        return c;
-    };
-    cost[1] = alt_cost(al0); cost[3] = alt_cost(al1); cost[5] = alt_cost(al2); cost[7] = alt_cost(al3);
+        for (int k = 0; k < 15; k++) {
+            int n;   // pixels on the line
+            if (d == 2 || d == 6) n = k < 8 ? 8 : 0;
+            else if (d & 1) n = k < 3 ? 2 * (k + 1) : (k < 8 ? 8 : (k < 11 ? 2 * (11 - k) : 0));
+            else n = k < 8 ? k + 1 : 15 - k;
+            if (n) c += (unsigned)(partial[d][k] * partial[d][k]) * (unsigned)(840 / n);
+        }
+        cost[d] = c;
+    }
     int best = 0;
     unsigned best_cost = cost[0];
 #pragma unroll
-    for (int n = 1; n < 8; n++)
-        if (cost[n] > best_cost) { best_cost = cost[n]; best = n; }
-    unsigned opp = 0;
+    for (int d = 1; d < 8; d++)
+        if (cost[d] > best_cost) { best_cost = cost[d]; best = d; }
+    unsigned across = 0;      // the cost of the direction at right angles to the best one
 #pragma unroll
-    for (int n = 0; n < 8; n++) if (n == (best ^ 4)) opp = cost[n];
-    *var = (best_cost - opp) >> 10;
+    for (int d = 0; d < 8; d++) if (d == (best ^ 4)) across = cost[d];
+    *var = (best_cost - across) >> 10;
     return best;
 }
 
