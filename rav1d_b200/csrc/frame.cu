@@ -990,7 +990,10 @@ extern "C" int rb200_frame_readback_async(Rb200Frame *f, void *const data[3], co
     for (int p = 0; p < f->g.n_planes; p++) {
         const int rows = plane_rows(f, p);
         const ptrdiff_t hs = stride[p ? 1 : 0];
-        if (hs >= 0) {
+        if (hs >= 0 && (size_t)hs == plane_row_bytes(f, p) && (int64_t)hs == f->display.stride[p]) {
+            // rows back to back on both sides: one linear copy
+            RB_CUDA(cudaMemcpyAsync(data[p], f->display.data[p], (size_t)hs * rows, cudaMemcpyDeviceToHost, f->stream));
+        } else if (hs >= 0) {
             RB_CUDA(cudaMemcpy2DAsync(data[p], (size_t)hs, f->display.data[p], (size_t)f->display.stride[p],
                                       plane_row_bytes(f, p), rows, cudaMemcpyDeviceToHost, f->stream));
         } else {

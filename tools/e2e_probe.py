@@ -34,6 +34,7 @@ n_mc = len(s.mc_items)
 for d in ctxs:
     lib.check(lib.frame_submit(d.h, s.n_coefs, counts, n_mc, stages, 1)); d.wait()
     lib.check(lib.frame_pack_coef16(d.h, s.n_coefs))
+    lib.check(lib.frame_pack_coef_stream(d.h, s.n_coefs, counts, stages))
 CHAIN = os.environ.get("RB200_PROBE_CHAIN", "1") == "1"
 if CHAIN:      # frame i predicts from the output of frame i - 1, as in bench.py
     outs_pl = []
@@ -63,7 +64,7 @@ def run(upload, readback, frames=96):
     return dt / frames * 1e3, host / frames * 1e3
 
 
-for name, up, rb in [("gather16+readback", 4, True), ("gather16 only", 4, False), ("gather+readback", 3, True), ("gather only", 3, False), ("zerocopy only", 2, False), ("copy only", 1, False),
+for name, up, rb in [("packed16+readback", 5, True), ("packed16 only", 5, False), ("gather16+readback", 4, True), ("gather16 only", 4, False), ("gather+readback", 3, True), ("gather only", 3, False), ("zerocopy only", 2, False), ("copy only", 1, False),
                      ("readback only", 0, True), ("resident", 0, False)]:
     run(up, rb, 32)
     ms, hostms = run(up, rb)
