@@ -373,19 +373,22 @@ extern "C" int rb200_frame_set_film_grain(Rb200Frame *f, const Rb200FilmGrainDat
         data->num_uv_points[1] < 0 || data->num_uv_points[1] > 10 || data->ar_coeff_lag < 0 || data->ar_coeff_lag > 3)
         return set_error(-22, "frame_set_film_grain: bad parameters");
     if (!f->fg_mem) {
-        const int rows = (f->hdr.height + 31) >> 5, cols = (f->hdr.width + 31) >> 5;
+        // grain goes onto the OUTPUT picture: at the upscaled width when the frame is coded with super-resolution
+        const int ow = f->sr ? f->sr_w : f->hdr.width, aw = (ow + 127) & ~127;
+        const int rows = (f->hdr.height + 31) >> 5, cols = (ow + 31) >> 5;
         RB_CUDA(cudaMalloc((void **)&f->fg_mem, FG_OFF_OFFSETS + (size_t)rows * (cols + 1) + 64));
         RB_CUDA(cudaStreamCreateWithFlags(&f->fg_stream, cudaStreamNonBlocking));
         RB_CUDA(cudaEventCreateWithFlags(&f->fg_fork, cudaEventDisableTiming));
         RB_CUDA(cudaEventCreateWithFlags(&f->fg_join, cudaEventDisableTiming));
-        const size_t ysz = (size_t)f->g.stride[0] * f->g.plane_h[0];
-        const size_t uvsz = f->g.n_planes > 1 ? (size_t)f->g.stride[1] * f->g.plane_h[1] : 0;
+        const int64_t sy = (int64_t)aw * (int64_t)f->px, suv = f->g.n_planes > 1 ? (int64_t)(aw >> f->g.ss_hor) * (int64_t)f->px : 0;
+        const size_t ysz = (size_t)sy * f->g.plane_h[0];
+        const size_t uvsz = (size_t)suv * f->g.plane_h[1];
         RB_CUDA(cudaMalloc((void **)&f->plane_mem_fg, ysz + 2 * uvsz + 256));
         Rb200Planes &p = f->planes_fg;
-        p.data[0] = f->plane_mem_fg; p.stride[0] = f->g.stride[0];
+        p.data[0] = f->plane_mem_fg; p.stride[0] = sy;
         p.data[1] = uvsz ? f->plane_mem_fg + ysz : nullptr;
         p.data[2] = uvsz ? f->plane_mem_fg + ysz + uvsz : nullptr;
-        p.stride[1] = p.stride[2] = uvsz ? f->g.stride[1] : 0;
+        p.stride[1] = p.stride[2] = suv;
     }
     f->fg = *data; f->fg_is_id = is_id; f->fg_set = true;
     return 0;
@@ -400,10 +403,10 @@ extern "C" int rb200_frame_display_planes(Rb200Frame *f, Rb200Planes *out) {
 // rav1d_prep_grain (src/fg_apply.rs:74-172): grain LUTs, scaling LUTs and block offsets.  None of it
 // depends on the picture, so it is launched on the frame's side stream at submit time and overlaps
 // the reconstruction and the in-loop filters; film_grain_apply joins it.
-static int film_grain_prepare(Rb200Frame *f, cudaStream_t st) {
+static int film_grain_prepare(Rb200Frame *f, cudaStream_t st, int out_w) {
     const Rb200FilmGrainData &d = f->fg;
     const Rb200FrameGeometry &g = f->g;
-    const int w = f->hdr.width, h = f->hdr.height, bpc = f->hdr.bpc;
+    const int w = out_w, h = f->hdr.height, bpc = f->hdr.bpc;
     uint8_t *lut[3], *sc[3];
     for (int i = 0; i < 3; i++) { lut[i] = f->fg_mem + FG_OFF_LUT + i * FG_LUT_BYTES; sc[i] = f->fg_mem + FG_OFF_SCALING + i * 4096; }
     uint8_t *d_off = f->fg_mem + FG_OFF_OFFSETS;
@@ -431,7 +434,7 @@ static int film_grain_prepare(Rb200Frame *f, cudaStream_t st) {
 static int film_grain_apply(Rb200Frame *f, cudaStream_t st) {
     const Rb200FilmGrainData &d = f->fg;
     const Rb200FrameGeometry &g = f->g;
-    const int w = f->hdr.width, h = f->hdr.height;
+    const int w = f->out_w, h = f->hdr.height;      // the output picture (upscaled width under super-resolution)
     uint8_t *lut[3], *sc[3];
     for (int i = 0; i < 3; i++) { lut[i] = f->fg_mem + FG_OFF_LUT + i * FG_LUT_BYTES; sc[i] = f->fg_mem + FG_OFF_SCALING + i * 4096; }
     uint8_t *d_off = f->fg_mem + FG_OFF_OFFSETS;
@@ -1115,7 +1118,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         RB_CUDA(cudaEventRecord(f->fg_fork, st));
         RB_CUDA(cudaStreamWaitEvent(f->fg_stream, f->fg_fork, 0));
         int r0;
-        if ((r0 = film_grain_prepare(f, f->fg_stream))) return r0;
+        if ((r0 = film_grain_prepare(f, f->fg_stream, f->sr && (stages & RB200_STAGE_SUPER_RES) ? f->sr_w : f->hdr.width))) return r0;
         RB_CUDA(cudaEventRecord(f->fg_join, f->fg_stream));
     }
     const bool do_lf = (stages & RB200_STAGE_DEBLOCK) && (h.lf_level_y[0] || h.lf_level_y[1]);
@@ -1413,8 +1416,8 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
     // stripes -- the deblocked picture are upscaled horizontally (rav1d_filter_sbrow_resize src/recon.rs:4215-4281,
     // backup_lpf with resize src/lf_apply.rs:24-141)
     f->out_w = h.width;
-    if (do_sr && ((stages & RB200_STAGE_FILM_GRAIN) || f->band_s1 > f->band_s0))
-        return set_error(-38, "frame_submit: super-resolution together with film grain or a band restriction is not implemented");
+    if (do_sr && f->band_s1 > f->band_s0)
+        return set_error(-38, "frame_submit: super-resolution together with a band restriction is not implemented");
     if (do_sr) {
         const Rb200Planes cdefp = f->out;
         for (int p = 0; p < g.n_planes; p++) {

@@ -149,6 +149,50 @@ def test_stream_super_resolution_bit_exact(rb, key):
                                  f"expected {a[tuple(bad[0])]} got {b[tuple(bad[0])]}; rows {np.unique(bad[:, 0])[:10]}")
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", [k for k, _ in GOLD_SR][:4])
+def test_super_resolution_then_film_grain(rb, ref, key):
+    """Film grain on a picture coded with super-resolution goes onto the UPSCALED output (rav1d_apply_grain runs on the
+    output picture, src/lib.rs:604): the stage chain deblock + CDEF + upscaling + LR + grain against the reference's grain
+    applied to the reference decoder's upscaled output."""
+    import ctypes as C
+    import refharness
+    from rav1d_b200.synth import framegen
+    s = dict(GOLD_SR)[key]
+    if s.layout == 0:
+        pytest.skip("monochrome")
+    out_w = getattr(s, "out_w", s.w)
+    rng = np.random.default_rng(out_w)
+    d = framegen.random_film_grain(rng, lag=2, overlap=1)
+    # the oracle: a frame object of the output size carries the upscaled picture through dav1d_apply_grain
+    carrier = framegen.generate(out_w, s.h, s.bpc, seed=1)
+    if carrier.hdr.layout != s.layout:
+        pytest.skip("the synthetic carrier frame is 4:2:0 only")
+    cur = refharness.RefFrame(ref, carrier, 1)
+    try:
+        post = streamdump.visible(s, s.post, out=True)
+        planes = cur.get_planes()
+        for p in range(3):
+            planes[p][:] = 0
+            planes[p][:post[p].shape[0], :post[p].shape[1]] = post[p]
+        cur.set_planes(planes)
+        exp = [a[:post[p].shape[0], :post[p].shape[1]] for p, a in enumerate(cur.apply_grain(d, 0))]
+    finally:
+        cur.close()
+    dev = framegen.DeviceFrame(s)
+    try:
+        dev.load_batch()
+        dev.upload(0, s.pre)
+        rb.check(rb.frame_set_film_grain(dev.h, C.byref(d), 0))
+        dev.submit(s.stages | rb.STAGE_FILM_GRAIN); dev.wait()
+        got = streamdump.visible(s, dev.readback(), out=True)
+    finally:
+        dev.close()
+    for p in range(3):
+        assert np.array_equal(exp[p], got[p]), (key, p, int((exp[p] != got[p]).sum()))
+    assert not np.array_equal(exp[0], post[0])
+
+
 # ---------------------------------------------------------------- film grain on real streams
 def _load_grain():
     if not os.path.exists(streamdump.GOLDEN_GRAIN):
