@@ -251,7 +251,10 @@ typedef struct Rb200CompItem {
     uint8_t jnt_weight;  /* w_avg weight, f.jnt_weights[ref0][ref1] (src/decode.rs:4354-4386) */
     uint8_t mask_sign;
     uint8_t wedge_idx;   /* RB200_COMP_WEDGE: 0..15, block sizes 8..32 (dav1d_wedge_masks, src/wedge.rs:377) */
-    uint8_t pad[11];
+    uint8_t warp_mask;   /* GLOBALMV_GLOBALMV blocks whose reference allows it (f.gmv_warp_allowed, src/recon.rs:3253-3268,3352-3369):
+                            bit i = the luma prediction from ref[i] is the reference's global-motion warp (rb200_frame_set_ref_gmv),
+                            bit 2 + i = the chroma predictions too (chroma block at least 8x8) */
+    uint8_t pad[10];
 } RB200_ALIGN16 Rb200CompItem;         /* 32 bytes */
 
 /* Warped (affine) prediction, one record per BLOCK (all planes): recon.rs `warp_affine`
@@ -521,6 +524,9 @@ typedef struct Rb200McScaledItem {
     uint8_t pad[7];
 } RB200_ALIGN16 Rb200McScaledItem;         /* 32 bytes */
 int rb200_frame_set_ref_size(Rb200Frame *f, int slot, int width, int height);   /* luma size of reference `slot` */
+/* Global-motion parameters of reference `slot` (frame_hdr.gmv[slot]: Rav1dWarpedMotionParams.matrix and alpha / beta /
+ * gamma / delta), used by compound blocks whose Rb200CompItem.warp_mask asks for the warped prediction. */
+int rb200_frame_set_ref_gmv(Rb200Frame *f, int slot, const int32_t matrix[6], const int16_t abcd[4]);
 int rb200_frame_reserve_scaled_items(Rb200Frame *f, int max_scaled_items);
 Rb200McScaledItem *rb200_frame_scaled_items(Rb200Frame *f);
 int rb200_frame_set_scaled_count(Rb200Frame *f, int n);

@@ -375,6 +375,42 @@ static void comp_prep(RefFrame *r, const RefFrame *rfr, int16_t *tmp, int pl, in
     else ((mct_fn8)f->dsp->mc.mct[filter2d])(tmp, ref, ref_stride, bw, bh, mx, my);
 }
 
+/* The prediction of a GLOBALMV_GLOBALMV compound block from a reference whose global motion may be warped: warp_affine
+ * with dst16 (src/recon_tmpl.c:1139-1198), i.e. warp8x8t per 8x8 of the block's plane, into tmp (row pitch bw). */
+static void comp_warp_prep(RefFrame *r, const RefFrame *rfr, int16_t *tmp, int pl, int bx_luma, int by_luma, int bw, int bh,
+                           const Dav1dWarpedMotionParams *wmp, uint8_t *emu) {
+    Dav1dFrameContext *f = r->f;
+    const Dav1dFrameContext *rf = rfr->f;
+    const int px = r->hbd ? 2 : 1;
+    const int ss_hor = pl && f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444, ss_ver = pl && f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420;
+    const int width = (rf->cur.p.w + ss_hor) >> ss_hor, height = (rf->cur.p.h + ss_ver) >> ss_ver;
+    const int32_t *mat = wmp->matrix;
+    for (int y = 0; y < bh; y += 8) {
+        const int src_y = by_luma + ((y + 4) << ss_ver);
+        const int64_t mat3_y = (int64_t)mat[3] * src_y + mat[0], mat5_y = (int64_t)mat[5] * src_y + mat[1];
+        for (int x = 0; x < bw; x += 8) {
+            const int src_x = bx_luma + ((x + 4) << ss_hor);
+            const int64_t mvx = ((int64_t)mat[2] * src_x + mat3_y) >> ss_hor, mvy = ((int64_t)mat[4] * src_x + mat5_y) >> ss_ver;
+            const int dx = (int)(mvx >> 16) - 4, dy = (int)(mvy >> 16) - 4;
+            const int mx = (((int)mvx & 0xffff) - wmp->u.abcd[0] * 4 - wmp->u.abcd[1] * 7) & ~0x3f;
+            const int my = (((int)mvy & 0xffff) - wmp->u.abcd[2] * 4 - wmp->u.abcd[3] * 4) & ~0x3f;
+            const uint8_t *ref_ptr;
+            ptrdiff_t ref_stride = rf->cur.stride[!!pl];
+            if (dx < 3 || dx + 8 + 4 > width || dy < 3 || dy + 8 + 4 > height) {
+                ((void (*)(intptr_t, intptr_t, intptr_t, intptr_t, intptr_t, intptr_t, void *, ptrdiff_t, const void *, ptrdiff_t))
+                     f->dsp->mc.emu_edge)(15, 15, width, height, dx - 3, dy - 3, emu, 32 * px, rf->cur.data[pl], ref_stride);
+                ref_ptr = emu + (32 * 3 + 3) * px;
+                ref_stride = 32 * px;
+            } else {
+                ref_ptr = (const uint8_t *)rf->cur.data[pl] + ref_stride * dy + (ptrdiff_t)dx * px;
+            }
+            int16_t *d = tmp + y * bw + x;
+            if (r->hbd) ((void (*)(int16_t *, ptrdiff_t, const void *, ptrdiff_t, const int16_t *, int, int, int))f->dsp->mc.warp8x8t)(d, bw, ref_ptr, ref_stride, wmp->u.abcd, mx, my, r->bdmax);
+            else ((void (*)(int16_t *, ptrdiff_t, const void *, ptrdiff_t, const int16_t *, int, int))f->dsp->mc.warp8x8t)(d, bw, ref_ptr, ref_stride, wmp->u.abcd, mx, my);
+        }
+    }
+}
+
 static int wedge_bs(int w, int h) {
     switch (w << 8 | h) {
     case 32 << 8 | 32: return BS_32x32; case 32 << 8 | 16: return BS_32x16; case 32 << 8 | 8: return BS_32x8;
@@ -401,8 +437,12 @@ static void do_comp_chunk(RefFrame *r, int tid, int chunk, void *arg) {
         for (int pl = 0; pl < n_planes; pl++) {
             const int ss_hor = pl && ss_hor_c, ss_ver = pl && ss_ver_c;
             const int bw = it->w >> ss_hor, bh = it->h >> ss_ver, x0 = it->x >> ss_hor, y0 = it->y >> ss_ver;
-            for (int k = 0; k < 2; k++)
-                comp_prep(r, a->refs[it->ref[k]], tmp[k], pl, x0, y0, bw, bh, it->mv[k][1], it->mv[k][0], it->filter2d, emu);
+            for (int k = 0; k < 2; k++) {
+                if ((it->warp_mask >> ((pl ? 2 : 0) + k)) & 1)      /* the reference's global-motion warp (frame_hdr.gmv) */
+                    comp_warp_prep(r, a->refs[it->ref[k]], tmp[k], pl, it->x, it->y, bw, bh, &f->frame_hdr->gmv[it->ref[k]], emu);
+                else
+                    comp_prep(r, a->refs[it->ref[k]], tmp[k], pl, x0, y0, bw, bh, it->mv[k][1], it->mv[k][0], it->filter2d, emu);
+            }
             uint8_t *dst = (uint8_t *)f->cur.data[pl] + f->cur.stride[!!pl] * y0 + (ptrdiff_t)x0 * px;
             const ptrdiff_t ds = f->cur.stride[!!pl];
             const int s = it->mask_sign;
@@ -431,6 +471,12 @@ static void do_comp_chunk(RefFrame *r, int tid, int chunk, void *arg) {
         }
     }
     free(seg_mask); free(tmp); free(emu);
+}
+
+/* frame_hdr.gmv[slot] of the harness frame (real decoder frames carry their own) */
+void ref_frame_set_gmv(RefFrame *r, int slot, const int32_t matrix[6], const int16_t abcd[4]) {
+    memcpy(r->hdr.gmv[slot].matrix, matrix, sizeof(r->hdr.gmv[slot].matrix));
+    memcpy(r->hdr.gmv[slot].u.abcd, abcd, sizeof(r->hdr.gmv[slot].u.abcd));
 }
 
 void ref_frame_recon_comp(RefFrame *r, RefFrame *const refs[], int n_refs, const Rb200CompItem *items, int n, int n_threads) {

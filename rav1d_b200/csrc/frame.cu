@@ -49,6 +49,7 @@ struct Rb200Frame {
     Rb200McItem *h_obmc, *d_obmc; int max_obmc, n_obmc_above, n_obmc_left;
     Rb200McScaledItem *h_scaled, *d_scaled; int max_scaled, n_scaled;
     rb200::McRefDims ref_dims;
+    rb200::McGmvSet ref_gmv;      // rb200_frame_set_ref_gmv
     // intra blocks, level by level (RB200_STAGE_INTRA)
     Rb200IntraItem *h_intra, *d_intra; int max_intra, max_levels, n_levels;
     int32_t *h_intra_itx, *d_intra_itx;           // per intra item: index of its residual in the itx list, -1 = none
@@ -800,6 +801,13 @@ extern "C" int rb200_frame_set_scaled_count(Rb200Frame *f, int n) {
     f->n_scaled = n;
     return 0;
 }
+extern "C" int rb200_frame_set_ref_gmv(Rb200Frame *f, int slot, const int32_t matrix[6], const int16_t abcd[4]) {
+    if (!f || slot < 0 || slot > 7 || !matrix || !abcd) return set_error(-22, "frame_set_ref_gmv: bad argument");
+    for (int k = 0; k < 6; k++) f->ref_gmv.g[slot].matrix[k] = matrix[k];
+    for (int k = 0; k < 4; k++) f->ref_gmv.g[slot].abcd[k] = abcd[k];
+    return 0;
+}
+
 extern "C" int rb200_frame_set_ref_size(Rb200Frame *f, int slot, int width, int height) {
     if (!f || slot < 0 || slot > 7 || width < 1 || height < 1) return set_error(-22, "frame_set_ref_size: bad argument");
     f->ref_dims.w[slot] = width; f->ref_dims.h[slot] = height;
@@ -1273,8 +1281,8 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
             f->launches++;
         }
         if (f->n_comp) {
-            if ((r = mc_comp_batch_launch(f->planes[0], f->refs, f->n_refs, h.width, h.height, h.layout, f->d_comp, f->n_comp,
-                                          f->bdmax, st))) return r;
+            if ((r = mc_comp_batch_launch_gmv(f->planes[0], f->refs, f->n_refs, h.width, h.height, h.layout, f->d_comp, f->n_comp,
+                                              f->bdmax, st, f->ref_gmv))) return r;
             f->launches++;
         }
         if (f->n_scaled) {

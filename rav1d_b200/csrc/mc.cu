@@ -19,6 +19,7 @@
 #include "tables.cuh"
 #include "wedge.cuh"
 #include "tma.cuh"
+#include "stages.cuh"
 #include <mutex>
 #include <utility>
 
@@ -703,7 +704,7 @@ struct McCompJob {
 template <typename BD>
 __global__ void __launch_bounds__(MC_WARPS * 32)
 mc_comp_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int layout,
-                     const Rb200CompItem *__restrict__ items, int n_items, int bdmax) {
+                     const Rb200CompItem *__restrict__ items, int n_items, int bdmax, McGmvSet gmv) {
     using pixel = typename BD::pixel;
     __shared__ McCompSmem smem[MC_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -716,9 +717,12 @@ mc_comp_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int l
     const int mask_sh = bitdepth + ib - 4, mask_rnd = 1 << (mask_sh - 5);
 
     // geometry of a job: reference plane, source position and phase (src/recon.rs:2047-2055,2100-2101)
-    struct Geo { McRef ref; int pw, ph, bw, bh, px0, py0, sx, sy, mx, my; bool fast; };
+    struct Geo { McRef ref; int pw, ph, bw, bh, px0, py0, sx, sy, mx, my; bool fast, warped; };
     auto geo = [&](const McCompJob &j) {
         Geo g;
+        // the prediction is the reference's global-motion warp (warp_affine with frame_hdr.gmv[ref], src/recon.rs:3253-3268;
+        // chroma only when the chroma block is at least 8x8, :3352-3369)
+        g.warped = (j.it.warp_mask >> ((j.pl ? 2 : 0) + j.i)) & 1;
         const int ss_hor = j.pl ? ss_hor_c : 0, ss_ver = j.pl ? ss_ver_c : 0;
         const Rb200Planes &rp = refs.p[(j.i ? j.it.ref[1] : j.it.ref[0]) & 7];
         g.ref.base = plane_ptr(rp, j.pl);
@@ -731,8 +735,55 @@ mc_comp_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int l
         const int mvy = j.i ? j.it.mv[1][0] : j.it.mv[0][0], mvx = j.i ? j.it.mv[1][1] : j.it.mv[0][1];
         g.mx = (mvx & (15 >> !ss_hor)) << !ss_hor; g.my = (mvy & (15 >> !ss_ver)) << !ss_ver;
         g.sx = g.px0 + (mvx >> (3 + ss_hor)); g.sy = g.py0 + (mvy >> (3 + ss_ver));
-        g.fast = !((g.pw | g.ph) & 1) && !(g.pw & (g.pw - 1));
+        g.fast = !((g.pw | g.ph) & 1) && !(g.pw & (g.pw - 1)) && !g.warped;
         return g;
+    };
+    // warp8x8t over the 8x8s of a tile into tmp (prep form), one warp: src/recon.rs:2311-2400, src/mc.rs:958-1030
+    auto warp_tile = [&](const McCompJob &j, const Geo &g, int16_t *tmp) {
+        const int ss_hor = j.pl ? ss_hor_c : 0, ss_ver = j.pl ? ss_ver_c : 0;
+        const int slot = (j.i ? j.it.ref[1] : j.it.ref[0]) & 7;
+            int32_t mat[6]; int ab[4];
+#pragma unroll
+        for (int s_ = 0; s_ < 8; s_++)
+            if (s_ == slot) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) mat[k] = gmv.g[s_].matrix[k];
+#pragma unroll
+                for (int k = 0; k < 4; k++) ab[k] = gmv.g[s_].abcd[k];
+            }
+        int16_t *mid = (int16_t *)sm.fast.midv;          // 15 x 8 intermediates (free: no mc_tile_fast is running)
+        for (int sy8 = 0; sy8 < g.ph; sy8 += 8)
+            for (int sx8 = 0; sx8 < g.pw; sx8 += 8) {
+                // position of this 8x8 inside the block's plane
+                const int bx = (j.tx >> ss_hor) + sx8, by = (j.ty >> ss_ver) + sy8;
+                const int src_y = j.it.y + ((by + 4) << ss_ver), src_x = j.it.x + ((bx + 4) << ss_hor);
+                const int64_t mvx = ((int64_t)mat[2] * src_x + (int64_t)mat[3] * src_y + mat[0]) >> ss_hor;
+                const int64_t mvy = ((int64_t)mat[4] * src_x + (int64_t)mat[5] * src_y + mat[1]) >> ss_ver;
+                const int dx = (int)(mvx >> 16) - 4, dy = (int)(mvy >> 16) - 4;
+                const int mx = (((int)mvx & 0xffff) - ab[0] * 4 - ab[1] * 7) & ~0x3f;
+                const int my = (((int)mvy & 0xffff) - ab[2] * 4 - ab[3] * 4) & ~0x3f;
+                for (int e = lane; e < 15 * 8; e += 32) {
+                    const int yy = e >> 3, xx = e & 7;
+                    const int tmx = mx + yy * ab[1] + xx * ab[0];
+                    const int8_t *f = tab::k_warp_filter + (64 + ((tmx + 512) >> 10)) * 8;
+                    int acc = (1 << (7 - ib)) >> 1;
+                    const pixel *row = (const pixel *)(g.ref.base + (int64_t)iclip(dy + yy - 3, 0, g.ref.h - 1) * g.ref.stride);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) acc += f[k] * (int)row[iclip(dx + xx + k - 3, 0, g.ref.w - 1)];
+                    mid[e] = (int16_t)(acc >> (7 - ib));
+                }
+                __syncwarp();
+                for (int e = lane; e < 64; e += 32) {
+                    const int yy = e >> 3, xx = e & 7;
+                    const int tmy = my + yy * ab[3] + xx * ab[2];
+                    const int8_t *f = tab::k_warp_filter + (64 + ((tmy + 512) >> 10)) * 8;
+                    int acc = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) acc += f[k] * (int)mid[(yy + k) * 8 + xx];
+                    tmp[(sy8 + yy) * MC_TILE + sx8 + xx] = (int16_t)(((acc + 64) >> 7) - pb);
+                }
+                __syncwarp();
+            }
     };
     auto advance = [&](McCompJob &j) {
         if (++j.i < 2) return;
@@ -777,6 +828,8 @@ mc_comp_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int l
                 mc_tile_fast<BD, 8, 8, true>(sm.fast, sm.fast.win[buf], W, g.pw, g.ph, g.bw, g.bh, g.mx, g.my, it.filter2d, nullptr, 0, bdmax, (uint16_t *)sm.tmp[cur.i]);
             else
                 mc_tile_fast<BD, 0, 0, true>(sm.fast, sm.fast.win[buf], W, g.pw, g.ph, g.bw, g.bh, g.mx, g.my, it.filter2d, nullptr, 0, bdmax, (uint16_t *)sm.tmp[cur.i]);
+        } else if (g.warped) {
+            warp_tile(cur, g, sm.tmp[cur.i]);
         } else {
             mc_tile<BD, true>(sm.slow, g.ref, g.sx, g.sy, g.pw, g.ph, g.bw, g.bh, g.mx, g.my, it.filter2d, sm.tmp[cur.i], MC_TILE, bdmax);
         }
@@ -848,13 +901,19 @@ static int mc_ensure_packed_taps(cudaStream_t st) {
 
 int mc_comp_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int layout,
                          const Rb200CompItem *d_items, int n, int bdmax, cudaStream_t st) {
+    static const McGmvSet none = {};
+    return mc_comp_batch_launch_gmv(dst, refs, n_refs, ref_w, ref_h, layout, d_items, n, bdmax, st, none);
+}
+
+int mc_comp_batch_launch_gmv(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int layout,
+                             const Rb200CompItem *d_items, int n, int bdmax, cudaStream_t st, const McGmvSet &gmv) {
     if (n <= 0) return 0;
     McRefSet rs = {};
     for (int i = 0; i < n_refs && i < 8; i++) rs.p[i] = refs[i];
     { const int r = mc_ensure_packed_taps(st); if (r) return r; }
     const int grid = imin((n + MC_WARPS - 1) / MC_WARPS, 148 * 4);   // persistent warps walk the list
-    if (bdmax > 255) mc_comp_batch_kernel<BD16><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, layout, d_items, n, bdmax);
-    else mc_comp_batch_kernel<BD8><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, layout, d_items, n, bdmax);
+    if (bdmax > 255) mc_comp_batch_kernel<BD16><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, layout, d_items, n, bdmax, gmv);
+    else mc_comp_batch_kernel<BD8><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, layout, d_items, n, bdmax, gmv);
     RB_LAUNCH_CHECK();
     return 0;
 }

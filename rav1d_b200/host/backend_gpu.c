@@ -157,6 +157,7 @@ static int gpu_frame_stage(const RbHostFrameDesc *const d, const RbHostBatch *co
         CHECK(rb200_frame_output_planes(r->fr, &planes));
         CHECK(rb200_frame_set_ref(fr, i, &planes));
         CHECK(rb200_frame_set_ref_size(fr, i, d->ref_w[i], d->ref_h[i]));
+        CHECK(rb200_frame_set_ref_gmv(fr, i, d->gmv_matrix[i], d->gmv_abcd[i]));
     }
     /* filter metadata: masks (cdef_idx; the rest is rebuilt on the device from the block records when there are any),
      * levels, limits, restoration units */

@@ -368,6 +368,10 @@ static void hand_over(Dav1dFrameContext *const f, RbJob *const j, RbPic *const r
         d.ref[i] = ((RbPic *)f->refp[i].p.allocator_data)->backend;
         d.ref_w[i] = f->refp[i].p.p.w; d.ref_h[i] = f->refp[i].p.p.h;
     }
+    for (int i = 0; i < 7; i++) {
+        memcpy(d.gmv_matrix[i], h->gmv[i].matrix, sizeof(d.gmv_matrix[i]));
+        memcpy(d.gmv_abcd[i], h->gmv[i].u.abcd, sizeof(d.gmv_abcd[i]));
+    }
     d.coef = f->frame_thread.cf; d.n_coefs = n_coefs;
     d.masks = (const Rb200Av1Filter *)f->lf.mask; d.n_masks = f->sb128w * f->sb128h;
     d.levels = (const uint8_t (*)[4])f->lf.level; d.n_levels = (size_t)f->b4_stride * 32 * f->sb128h;

@@ -77,6 +77,7 @@ typedef struct RbHostFrameDesc {
     void *cur;                            /* backend handle of the output picture */
     void *ref[7];                         /* backend handles of f.refp[0..6] (NULL = unused) */
     int ref_w[7], ref_h[7];
+    int32_t gmv_matrix[7][6]; int16_t gmv_abcd[7][4];   /* frame_hdr.gmv[i]: global-motion warp of reference i */
     const void *coef; size_t n_coefs;     /* f.frame_thread.cf and the number of coefficients used */
     const Rb200Av1Filter *masks; int n_masks;           /* f.lf.mask (cdef_idx; everything when there are no records) */
     const uint8_t (*levels)[4]; size_t n_levels;        /* f.lf.level */

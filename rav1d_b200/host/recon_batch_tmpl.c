@@ -571,8 +571,12 @@ int bytefn(dav1d_recon_b_inter)(Dav1dTaskContext *const t, const enum BlockSize 
         const int same_size[2] = {
             f->refp[b->ref[0]].p.p.w == f->cur.p.w && f->refp[b->ref[0]].p.p.h == f->cur.p.h,
             f->refp[b->ref[1]].p.p.w == f->cur.p.w && f->refp[b->ref[1]].p.p.h == f->cur.p.h };
-        if (b->inter_mode == GLOBALMV_GLOBALMV && (f->gmv_warp_allowed[b->ref[0]] || f->gmv_warp_allowed[b->ref[1]])) {
-            rb_batch_unsupported(B, "compound block with a warped global-motion prediction");
+        /* a prediction of a GLOBALMV_GLOBALMV block is the reference's global-motion warp where the reference allows it
+         * (src/recon.rs:3253-3268; chroma only when the chroma block is at least 8x8, :3352-3369) */
+        const int gmv_warp[2] = { b->inter_mode == GLOBALMV_GLOBALMV && f->gmv_warp_allowed[b->ref[0]],
+                                  b->inter_mode == GLOBALMV_GLOBALMV && f->gmv_warp_allowed[b->ref[1]] };
+        if ((gmv_warp[0] && !same_size[0]) || (gmv_warp[1] && !same_size[1])) {
+            rb_batch_unsupported(B, "warped block from a reference of another size");
         } else if (!same_size[0] || !same_size[1]) {
             rb_batch_unsupported(B, "compound block from a reference of another size");
         } else {
@@ -585,6 +589,10 @@ int bytefn(dav1d_recon_b_inter)(Dav1dTaskContext *const t, const enum BlockSize 
                 it->mv[i][0] = b->mv[i].y; it->mv[i][1] = b->mv[i].x;
             }
             it->filter2d = b->filter2d;
+            {
+                const int chroma_8x8 = imin(cbw4, cbh4) > 1;
+                it->warp_mask = (uint8_t)(gmv_warp[0] | gmv_warp[1] << 1 | (gmv_warp[0] && chroma_8x8) << 2 | (gmv_warp[1] && chroma_8x8) << 3);
+            }
             switch (b->comp_type) {
             case COMP_INTER_AVG: it->comp_type = RB200_COMP_AVG; break;
             case COMP_INTER_WEIGHTED_AVG:

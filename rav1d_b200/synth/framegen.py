@@ -100,7 +100,7 @@ def scale_mv(val, scale):
 
 
 def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1, comp_frac=0.0, warp_frac=0.0, obmc_frac=0.0,
-             scaled_frac=0.0, scaled_size=None):
+             scaled_frac=0.0, scaled_size=None, gmv_frac=0.0):
     """Returns a SynthFrame with numpy arrays; see module docstring."""
     rng = np.random.default_rng(seed)
     bdmax = (1 << bpc) - 1
@@ -171,6 +171,17 @@ def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1, comp_frac=0.0, w
     comp["jnt_weight"] = rng.choice(np.array([3, 5, 7, 9, 11, 13]), size=ci.size)   # dav1d quant_dist_lookup_table values
     comp["mask_sign"] = rng.integers(0, 2, size=ci.size)
     comp["wedge_idx"] = rng.integers(0, 16, size=ci.size)
+    if gmv_frac > 0:
+        # GLOBALMV_GLOBALMV blocks: one or both predictions are the reference's global-motion warp (luma, and chroma too:
+        # the 16x16 blocks have 8x8 chroma); per-reference parameters near the identity (frame_hdr.gmv)
+        comp["warp_mask"] = np.where(rng.random(ci.size) < gmv_frac, rng.integers(1, 4, size=ci.size) * 5, 0)
+        g = np.zeros((8, 6), np.int64)
+        g[:2, 0] = rng.integers(-(6 << 16), 6 << 16, size=2); g[:2, 1] = rng.integers(-(6 << 16), 6 << 16, size=2)
+        g[:2, 2] = (1 << 16) + rng.integers(-600, 600, size=2); g[:2, 3] = rng.integers(-600, 600, size=2)
+        g[:2, 4] = rng.integers(-600, 600, size=2); g[:2, 5] = (1 << 16) + rng.integers(-600, 600, size=2)
+        s.gmv_matrix = g.astype(np.int32)
+        s.gmv_abcd = np.zeros((8, 4), np.int16)
+        s.gmv_abcd[:2] = (rng.integers(0, 0x800, size=(2, 4)) - 0x400).astype(np.int16)
     s.comp_items = comp
     if comp_frac > 0:
         s.ref2 = [np.zeros((ah, aw), pdt), np.zeros((ah // 2, aw // 2), pdt), np.zeros((ah // 2, aw // 2), pdt)]
@@ -908,6 +919,10 @@ class DeviceFrame:
             lib.check(lib.frame_reserve_lf_blocks(self.h, len(lfb)), "reserve_lf_blocks")
             lib.np_view(lib.frame_lf_blocks(self.h), lib.LF_BLOCK_DT, len(lfb))[:] = lfb
             lib.check(lib.frame_set_lf_block_count(self.h, len(lfb)))
+        if hasattr(s, "gmv_matrix"):               # global-motion parameters of the references (compound warp predictions)
+            for slot in range(8):
+                lib.check(lib.frame_set_ref_gmv(self.h, slot, s.gmv_matrix[slot].ctypes.data_as(C.POINTER(C.c_int32)),
+                                                s.gmv_abcd[slot].ctypes.data_as(C.POINTER(C.c_int16))))
         if hasattr(s, "itx_luma_counts"):          # lists sorted luma first (sort_luma_first)
             lib.check(lib.frame_set_plane_counts(self.h, s.n_mc_luma, s.itx_luma_counts.ctypes.data_as(C.POINTER(C.c_int32))))
         comp = getattr(s, "comp_items", None)

@@ -73,6 +73,7 @@ def load():
         sig("ref_frame_recon_scaled", None, vp, vp, i, vp, i)
         sig("ref_frame_recon_intra", None, vp, vp, i, vp, vp, vp, vp)
         sig("ref_frame_apply_grain", None, vp, vp, i)
+        sig("ref_frame_set_gmv", None, vp, i, vp, vp)
         sig("ref_frame_grain_plane", vp, vp, i)
         sig("ref_fg_gen_y", None, vp, vp, i)
         sig("ref_fg_gen_uv", None, i, vp, vp, vp, ss, i)
@@ -145,6 +146,9 @@ class RefFrame:
         mc = np.ascontiguousarray(s.mc_items)
         itx = np.ascontiguousarray(s.itx_items)
         comp = np.ascontiguousarray(getattr(s, "comp_items", np.zeros(0, np.uint8)))
+        if hasattr(s, "gmv_matrix"):
+            for slot in range(7):
+                self.ref.ref_frame_set_gmv(self.h, slot, ptr(np.ascontiguousarray(s.gmv_matrix[slot])), ptr(np.ascontiguousarray(s.gmv_abcd[slot])))
         warp = np.ascontiguousarray(getattr(s, "warp_items", np.zeros(0, np.uint8)))
         if len(warp):
             self.ref.ref_frame_recon_warp(self.h, refs, len(frames), ptr(warp), len(warp), n_threads)

@@ -385,6 +385,17 @@ def test_luma_and_chroma_reconstruction_chains(rb, ref, w, h, bpc):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("w,h,bpc", [(424, 300, 10), (200, 136, 8), (264, 200, 12)])
+def test_compound_blocks_with_global_motion_warp(rb, ref, w, h, bpc):
+    """GLOBALMV_GLOBALMV compound blocks: one or both predictions are the reference's global-motion warp (warp8x8t with
+    frame_hdr.gmv, src/recon.rs:3253-3268,3352-3369), luma and chroma, under every compound type."""
+    s = framegen.generate(w, h, bpc, seed=41, comp_frac=0.6, gmv_frac=0.7)
+    assert (s.comp_items["warp_mask"] != 0).sum() > 10 and len({int(x) for x in s.comp_items["warp_mask"]}) >= 3
+    a = framecheck.oracle_frame(ref, s, R)
+    framecheck.assert_planes_equal(a, framecheck.product_frame(s, R), "compound with warped predictions")
+
+
+@pytest.mark.gpu
 def test_validate_names_bad_records(rb):
     """rb200_frame_validate: the staged batch as rb200_frame_submit will read it; a bad record is an error code, not a fault."""
     s = framegen.generate(200, 120, 10, seed=9, obmc_frac=0.2)
