@@ -175,11 +175,11 @@ def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1, comp_frac=0.0, w
         # GLOBALMV_GLOBALMV blocks: one or both predictions are the reference's global-motion warp (luma, and chroma too:
         # the 16x16 blocks have 8x8 chroma); per-reference parameters near the identity (frame_hdr.gmv)
         comp["warp_mask"] = np.where(rng.random(ci.size) < gmv_frac, rng.integers(1, 4, size=ci.size) * 5, 0)
-        g = np.zeros((8, 6), np.int64)
-        g[:2, 0] = rng.integers(-(6 << 16), 6 << 16, size=2); g[:2, 1] = rng.integers(-(6 << 16), 6 << 16, size=2)
-        g[:2, 2] = (1 << 16) + rng.integers(-600, 600, size=2); g[:2, 3] = rng.integers(-600, 600, size=2)
-        g[:2, 4] = rng.integers(-600, 600, size=2); g[:2, 5] = (1 << 16) + rng.integers(-600, 600, size=2)
-        s.gmv_matrix = g.astype(np.int32)
+        gm = np.zeros((8, 6), np.int64)
+        gm[:2, 0] = rng.integers(-(6 << 16), 6 << 16, size=2); gm[:2, 1] = rng.integers(-(6 << 16), 6 << 16, size=2)
+        gm[:2, 2] = (1 << 16) + rng.integers(-600, 600, size=2); gm[:2, 3] = rng.integers(-600, 600, size=2)
+        gm[:2, 4] = rng.integers(-600, 600, size=2); gm[:2, 5] = (1 << 16) + rng.integers(-600, 600, size=2)
+        s.gmv_matrix = gm.astype(np.int32)
         s.gmv_abcd = np.zeros((8, 4), np.int16)
         s.gmv_abcd[:2] = (rng.integers(0, 0x800, size=(2, 4)) - 0x400).astype(np.int16)
     s.comp_items = comp
