@@ -521,7 +521,9 @@ typedef struct Rb200McScaledItem {
     int32_t pos_x, pos_y;
     int32_t step_x, step_y;
     uint8_t filter2d;
-    uint8_t pad[7];
+    uint8_t flags;           /* RB200_MC_PUT, or RB200_MC_OBMC_ABOVE / _LEFT: an OBMC strip predicted from a reference of
+                                another size (w x h = the blend area, as for the Rb200McItem strips) */
+    uint8_t pad[6];
 } RB200_ALIGN16 Rb200McScaledItem;         /* 32 bytes */
 int rb200_frame_set_ref_size(Rb200Frame *f, int slot, int width, int height);   /* luma size of reference `slot` */
 /* Global-motion parameters of reference `slot` (frame_hdr.gmv[slot]: Rav1dWarpedMotionParams.matrix and alpha / beta /
@@ -530,6 +532,10 @@ int rb200_frame_set_ref_gmv(Rb200Frame *f, int slot, const int32_t matrix[6], co
 int rb200_frame_reserve_scaled_items(Rb200Frame *f, int max_scaled_items);
 Rb200McScaledItem *rb200_frame_scaled_items(Rb200Frame *f);
 int rb200_frame_set_scaled_count(Rb200Frame *f, int n);
+/* OBMC strips from references of another size: they follow the n put items of rb200_frame_set_scaled_count in the same
+ * list (reserve n + n_above + n_left), all ABOVE strips first, then all LEFT strips; they run with the ordinary strips
+ * of their kind (above before left). */
+int rb200_frame_set_scaled_obmc_counts(Rb200Frame *f, int n_above, int n_left);
 /* Frame level (stage RB200_STAGE_INTRA): the intra half of rav1d_recon_b_intra (src/recon.rs:2402-3160) as a
  * wavefront.  One record per intra-predicted TRANSFORM block; the host gives each its dependency level (a block
  * needs the reconstructed pixels left of, above, above-right and below-left of it, so level = 1 + the highest

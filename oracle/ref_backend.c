@@ -62,7 +62,9 @@ static int cpu_frame_stage(const RbHostFrameDesc *const d, const RbHostBatch *co
         ref_frame_recon_scaled(&cur, refs, 7, B->scaled.v, B->scaled.n);
         ref_frame_recon_warp(&cur, refs, 7, B->warp.v, B->warp.n, 1);
         ref_frame_recon_obmc(&cur, refs, 7, B->obmc_above.v, B->obmc_above.n);
+        ref_frame_recon_scaled(&cur, refs, 7, B->scaled_obmc_above.v, B->scaled_obmc_above.n);
         ref_frame_recon_obmc(&cur, refs, 7, B->obmc_left.v, B->obmc_left.n);
+        ref_frame_recon_scaled(&cur, refs, 7, B->scaled_obmc_left.v, B->scaled_obmc_left.n);
         ref_frame_recon(&cur, refs, 7, NULL, 0, fin->itx, fin->n_itx_inter, cf, 1);
         if (d->stages & RB200_STAGE_INTRA)
             ref_frame_recon_intra(&cur, fin->intra, fin->n_intra, fin->intra_itx, fin->itx, cf, B->pal.v);

@@ -603,14 +603,17 @@ void ref_frame_recon_scaled(RefFrame *r, RefFrame *const refs[], int n_refs, con
     Dav1dFrameContext *f = r->f;
     const int px = r->hbd ? 2 : 1;
     const int ss_ver_l = f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420, ss_hor_l = f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444;
-    uint8_t *emu = malloc(320 * (256 + 7) * 2);
+    uint8_t *emu = malloc(320 * (256 + 7) * 2), *lap = malloc(128 * 128 * 2);
     for (int i = 0; i < n; i++) {
         const Rb200McScaledItem *it = &items[i];
         const int pl = it->plane, ss_hor = pl && ss_hor_l, ss_ver = pl && ss_ver_l;
         const Dav1dFrameContext *rf = refs[it->ref]->f;
+        /* an OBMC strip: the neighbour's prediction (w x pred_h, src/recon_tmpl.c:1100-1130) into `lap`, then blend_h / blend_v */
+        const int strip = it->flags != RB200_MC_PUT, above = it->flags == RB200_MC_OBMC_ABOVE, v_mul = 4 >> ss_ver;
+        const int pw = it->w, ph = strip && above ? (((it->h / v_mul) * 3 + 3) >> 2) * v_mul : it->h;
         const int left = it->pos_x >> 10, top = it->pos_y >> 10;
-        const int right = ((it->pos_x + (it->w - 1) * it->step_x) >> 10) + 1;
-        const int bottom = ((it->pos_y + (it->h - 1) * it->step_y) >> 10) + 1;
+        const int right = ((it->pos_x + (pw - 1) * it->step_x) >> 10) + 1;
+        const int bottom = ((it->pos_y + (ph - 1) * it->step_y) >> 10) + 1;
         const int w = (rf->cur.p.w + ss_hor) >> ss_hor, h = (rf->cur.p.h + ss_ver) >> ss_ver;
         ptrdiff_t ref_stride = rf->cur.stride[!!pl];
         const uint8_t *ref;
@@ -624,12 +627,17 @@ void ref_frame_recon_scaled(RefFrame *r, RefFrame *const refs[], int n_refs, con
             ref = (const uint8_t *)rf->cur.data[pl] + ref_stride * top + (ptrdiff_t)left * px;
         }
         uint8_t *dst = (uint8_t *)f->cur.data[pl] + f->cur.stride[!!pl] * it->dst_y + (ptrdiff_t)it->dst_x * px;
-        if (r->hbd) ((mcs_fn16)f->dsp->mc.mc_scaled[it->filter2d])(dst, f->cur.stride[!!pl], ref, ref_stride, it->w, it->h,
+        uint8_t *out = strip ? lap : dst;
+        const ptrdiff_t out_stride = strip ? (ptrdiff_t)pw * px : f->cur.stride[!!pl];
+        if (r->hbd) ((mcs_fn16)f->dsp->mc.mc_scaled[it->filter2d])(out, out_stride, ref, ref_stride, pw, ph,
                                                                   it->pos_x & 0x3ff, it->pos_y & 0x3ff, it->step_x, it->step_y, r->bdmax);
-        else ((mcs_fn8)f->dsp->mc.mc_scaled[it->filter2d])(dst, f->cur.stride[!!pl], ref, ref_stride, it->w, it->h,
+        else ((mcs_fn8)f->dsp->mc.mc_scaled[it->filter2d])(out, out_stride, ref, ref_stride, pw, ph,
                                                            it->pos_x & 0x3ff, it->pos_y & 0x3ff, it->step_x, it->step_y);
+        if (strip)
+            ((void (*)(void *, ptrdiff_t, const void *, int, int))(above ? f->dsp->mc.blend_h : f->dsp->mc.blend_v))(
+                dst, f->cur.stride[!!pl], lap, it->w, it->h);
     }
-    free(emu);
+    free(lap); free(emu);
 }
 
 /* ------------------------------------------------------------ intra blocks */

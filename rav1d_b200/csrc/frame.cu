@@ -47,7 +47,7 @@ struct Rb200Frame {
     Rb200CompItem *h_comp, *d_comp; int max_comp, n_comp;
     Rb200WarpItem *h_warp, *d_warp; int max_warp, n_warp;
     Rb200McItem *h_obmc, *d_obmc; int max_obmc, n_obmc_above, n_obmc_left;
-    Rb200McScaledItem *h_scaled, *d_scaled; int max_scaled, n_scaled;
+    Rb200McScaledItem *h_scaled, *d_scaled; int max_scaled, n_scaled, n_scaled_above, n_scaled_left;   // put items, then OBMC strips
     rb200::McRefDims ref_dims;
     rb200::McGmvSet ref_gmv;      // rb200_frame_set_ref_gmv
     // intra blocks, level by level (RB200_STAGE_INTRA)
@@ -799,12 +799,20 @@ extern "C" Rb200McScaledItem *rb200_frame_scaled_items(Rb200Frame *f) { return f
 extern "C" int rb200_frame_set_scaled_count(Rb200Frame *f, int n) {
     if (!f || n < 0 || n > f->max_scaled) return set_error(-22, "frame_set_scaled_count: more items than reserved");
     f->n_scaled = n;
+    f->n_scaled_above = f->n_scaled_left = 0;
     return 0;
 }
 extern "C" int rb200_frame_set_ref_gmv(Rb200Frame *f, int slot, const int32_t matrix[6], const int16_t abcd[4]) {
     if (!f || slot < 0 || slot > 7 || !matrix || !abcd) return set_error(-22, "frame_set_ref_gmv: bad argument");
     for (int k = 0; k < 6; k++) f->ref_gmv.g[slot].matrix[k] = matrix[k];
     for (int k = 0; k < 4; k++) f->ref_gmv.g[slot].abcd[k] = abcd[k];
+    return 0;
+}
+
+extern "C" int rb200_frame_set_scaled_obmc_counts(Rb200Frame *f, int n_above, int n_left) {
+    if (!f || n_above < 0 || n_left < 0 || f->n_scaled + n_above + n_left > f->max_scaled)
+        return set_error(-22, "frame_set_scaled_obmc_counts: more items than reserved");
+    f->n_scaled_above = n_above; f->n_scaled_left = n_left;
     return 0;
 }
 
@@ -1113,7 +1121,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
                 for (int t = 0; t < RB200_N_RECT_TX_SIZES; t++) n_itx += f->intra_itx_counts[l * RB200_N_RECT_TX_SIZES + t];
         if (n_coefs > f->max_coefs || n_itx > f->max_itx || n_mc > f->max_mc || n_mc < 0)
             return set_error(-22, "frame_submit: batch larger than the frame was created for");
-        if ((n_mc || f->n_comp || f->n_warp || f->n_scaled || f->n_obmc_above || f->n_obmc_left) && f->n_refs < 1) return set_error(-22, "frame_submit: no reference picture set");
+        if ((n_mc || f->n_comp || f->n_warp || f->n_scaled || f->n_scaled_above || f->n_scaled_left || f->n_obmc_above || f->n_obmc_left) && f->n_refs < 1) return set_error(-22, "frame_submit: no reference picture set");
     }
     f->launches = 0;
     const BandRows band = band_rows(f);
@@ -1201,7 +1209,8 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
                     if (f->n_pal) RB_CUDA(cudaMemcpyAsync(f->d_pal, f->h_pal, f->n_pal, cudaMemcpyHostToDevice, st));
                 }
             }
-            if (f->n_scaled) RB_CUDA(cudaMemcpyAsync(f->d_scaled, f->h_scaled, (size_t)f->n_scaled * sizeof(Rb200McScaledItem), cudaMemcpyHostToDevice, st));
+            if (f->n_scaled + f->n_scaled_above + f->n_scaled_left)
+                RB_CUDA(cudaMemcpyAsync(f->d_scaled, f->h_scaled, (size_t)(f->n_scaled + f->n_scaled_above + f->n_scaled_left) * sizeof(Rb200McScaledItem), cudaMemcpyHostToDevice, st));
             if (f->n_obmc_above + f->n_obmc_left)
                 RB_CUDA(cudaMemcpyAsync(f->d_obmc, f->h_obmc, (size_t)(f->n_obmc_above + f->n_obmc_left) * sizeof(Rb200McItem), cudaMemcpyHostToDevice, st));
         }
@@ -1236,7 +1245,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
     // With the lists sorted luma first (rb200_frame_set_plane_counts) and nothing but put predictions and residuals in the
     // frame, the luma and the chroma reconstruction are two chains on two streams that run on into the post-filters.
     bool recon_split = f->plane_split && f->plane_counts && g.n_planes > 1 && (stages & RB200_STAGE_RECON) && !f->n_comp && !f->n_warp &&
-                       !f->n_scaled && !f->n_obmc_above && !f->n_obmc_left && !((stages & RB200_STAGE_INTRA) && f->n_levels) && !do_sr &&
+                       !f->n_scaled && !f->n_scaled_above && !f->n_scaled_left && !f->n_obmc_above && !f->n_obmc_left && !((stages & RB200_STAGE_INTRA) && f->n_levels) && !do_sr &&
                        !(f->band_s1 > f->band_s0) && f->n_mc_luma <= n_mc && (do_lf || do_cdef || restore_planes);
     if (recon_split)
         for (int t = 0; t < RB200_N_RECT_TX_SIZES; t++) if (f->itx_luma[t] > itx_counts[t]) recon_split = false;
@@ -1301,9 +1310,19 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
                                           f->n_obmc_above, f->bdmax, st))) return r;
             f->launches++;
         }
+        if (f->n_scaled_above) {      // ... strips from references of another size with the strips of their kind
+            if ((r = mc_scaled_batch_launch(f->planes[0], f->refs, f->n_refs, f->ref_dims, g.ss_hor, g.ss_ver, f->d_scaled + f->n_scaled,
+                                            f->n_scaled_above, f->bdmax, st))) return r;
+            f->launches++;
+        }
         if (f->n_obmc_left) {
             if ((r = mc_obmc_batch_launch(f->planes[0], f->refs, f->n_refs, h.width, h.height, g.ss_hor, g.ss_ver,
                                           f->d_obmc + f->n_obmc_above, f->n_obmc_left, f->bdmax, st))) return r;
+            f->launches++;
+        }
+        if (f->n_scaled_left) {
+            if ((r = mc_scaled_batch_launch(f->planes[0], f->refs, f->n_refs, f->ref_dims, g.ss_hor, g.ss_ver,
+                                            f->d_scaled + f->n_scaled + f->n_scaled_above, f->n_scaled_left, f->bdmax, st))) return r;
             f->launches++;
         }
         MARK(2);

@@ -1157,10 +1157,27 @@ mc_scaled_batch_kernel(Rb200Planes dst, McRefSet refs, McRefDims dims, int ss_ho
     const int64_t dstride = plane_stride(dst, it.plane);
     // src/recon_tmpl.c:1029-1062: the block starts at (pos >> 10), phase pos & 0x3ff
     const int ox = it.pos_x >> 10, oy = it.pos_y >> 10, mx = it.pos_x & 0x3ff, my = it.pos_y & 0x3ff;
-    for (int i = threadIdx.x; i < it.w * it.h; i += blockDim.x) {
-        const int y = i / it.w, x = i - y * it.w;
-        const int v = mc_scaled_px<BD, false>(ref, ox, oy, it.w, it.h, mx, my, it.step_x, it.step_y, it.filter2d, x, y, bdmax);
-        ((pixel *)(dbase + (int64_t)(it.dst_y + y) * dstride))[it.dst_x + x] = (pixel)v;
+    if (it.flags == RB200_MC_PUT) {
+        for (int i = threadIdx.x; i < it.w * it.h; i += blockDim.x) {
+            const int y = i / it.w, x = i - y * it.w;
+            const int v = mc_scaled_px<BD, false>(ref, ox, oy, it.w, it.h, mx, my, it.step_x, it.step_y, it.filter2d, x, y, bdmax);
+            ((pixel *)(dbase + (int64_t)(it.dst_y + y) * dstride))[it.dst_x + x] = (pixel)v;
+        }
+        return;
+    }
+    // OBMC strip (obmc(), src/recon.rs:2205-2309) from a reference of another size: w x h is the blend area; the
+    // neighbour's prediction is ((oh4 * 3 + 3) >> 2) units tall for an ABOVE strip (that size picks the 4-tap filters);
+    // blend_h / blend_v touch 3/4 of the rows / columns.  Every thread predicts and blends its own pixel.
+    const bool above = it.flags == RB200_MC_OBMC_ABOVE;
+    const int v_mul = 4 >> ss_ver;
+    const int pred_h = above ? (((it.h / v_mul) * 3 + 3) >> 2) * v_mul : it.h;
+    const int lim_r = above ? (it.h * 3) >> 2 : it.h, lim_c = above ? it.w : (it.w * 3) >> 2;
+    for (int i = threadIdx.x; i < lim_c * lim_r; i += blockDim.x) {
+        const int y = i / lim_c, x = i - y * lim_c;
+        const int v = mc_scaled_px<BD, false>(ref, ox, oy, it.w, pred_h, mx, my, it.step_x, it.step_y, it.filter2d, x, y, bdmax);
+        const int m = above ? tab::k_obmc_masks[it.h + y] : tab::k_obmc_masks[it.w + x];
+        pixel *d = (pixel *)(dbase + (int64_t)(it.dst_y + y) * dstride) + it.dst_x + x;
+        *d = (pixel)(((int)*d * (64 - m) + v * m + 32) >> 6);
     }
 }
 

@@ -131,9 +131,16 @@ static int gpu_frame_stage(const RbHostFrameDesc *const d, const RbHostBatch *co
     CHECK(rb200_frame_reserve_warp_items(fr, B->warp.n));
     if (B->warp.n) memcpy(rb200_frame_warp_items(fr), B->warp.v, (size_t)B->warp.n * sizeof(Rb200WarpItem));
     CHECK(rb200_frame_set_warp_count(fr, B->warp.n));
-    CHECK(rb200_frame_reserve_scaled_items(fr, B->scaled.n));
+    /* predictions from references of another size: the blocks' own, then the OBMC strips (above, left) */
+    CHECK(rb200_frame_reserve_scaled_items(fr, B->scaled.n + B->scaled_obmc_above.n + B->scaled_obmc_left.n));
     if (B->scaled.n) memcpy(rb200_frame_scaled_items(fr), B->scaled.v, (size_t)B->scaled.n * sizeof(Rb200McScaledItem));
+    if (B->scaled_obmc_above.n)
+        memcpy(rb200_frame_scaled_items(fr) + B->scaled.n, B->scaled_obmc_above.v, (size_t)B->scaled_obmc_above.n * sizeof(Rb200McScaledItem));
+    if (B->scaled_obmc_left.n)
+        memcpy(rb200_frame_scaled_items(fr) + B->scaled.n + B->scaled_obmc_above.n, B->scaled_obmc_left.v,
+               (size_t)B->scaled_obmc_left.n * sizeof(Rb200McScaledItem));
     CHECK(rb200_frame_set_scaled_count(fr, B->scaled.n));
+    CHECK(rb200_frame_set_scaled_obmc_counts(fr, B->scaled_obmc_above.n, B->scaled_obmc_left.n));
     const int n_obmc = B->obmc_above.n + B->obmc_left.n;
     CHECK(rb200_frame_reserve_obmc_items(fr, n_obmc));
     if (B->obmc_above.n) memcpy(rb200_frame_obmc_items(fr), B->obmc_above.v, (size_t)B->obmc_above.n * sizeof(Rb200McItem));

@@ -21,6 +21,7 @@ void *rb_vec_grow(void *v, int *cap, int need, size_t elem) {
 
 void rb_batch_reset(RbHostBatch *b) {
     b->mc.n = b->scaled.n = b->comp.n = b->warp.n = b->obmc_above.n = b->obmc_left.n = 0;
+    b->scaled_obmc_above.n = b->scaled_obmc_left.n = 0;
     b->itx.n = b->intra.n = b->intra_itx.n = b->iitx.n = b->pal.n = b->lfb.n = 0;
     b->unsupported = 0;
     b->why[0] = 0;
@@ -28,6 +29,7 @@ void rb_batch_reset(RbHostBatch *b) {
 
 void rb_batch_free(RbHostBatch *b) {
     free(b->mc.v); free(b->scaled.v); free(b->comp.v); free(b->warp.v); free(b->obmc_above.v); free(b->obmc_left.v);
+    free(b->scaled_obmc_above.v); free(b->scaled_obmc_left.v);
     free(b->itx.v); free(b->intra.v); free(b->intra_itx.v); free(b->iitx.v); free(b->pal.v); free(b->lfb.v);
     memset(b, 0, sizeof(*b));
 }

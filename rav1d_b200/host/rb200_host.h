@@ -38,6 +38,7 @@ extern "C" {
 typedef struct RbHostBatch {
     RB_VEC(Rb200McItem) mc;          /* single-reference predictions, same-size reference */
     RB_VEC(Rb200McScaledItem) scaled;/* ... reference of another size */
+    RB_VEC(Rb200McScaledItem) scaled_obmc_above, scaled_obmc_left;   /* OBMC strips from references of another size */
     RB_VEC(Rb200CompItem) comp;      /* compound blocks */
     RB_VEC(Rb200WarpItem) warp;      /* warped blocks */
     RB_VEC(Rb200McItem) obmc_above, obmc_left;

@@ -105,7 +105,6 @@ static void push_mc(RbHostBatch *const B, const Dav1dFrameContext *const f, cons
         it->flags = (uint8_t)(list == 0 ? RB200_MC_PUT : list == 1 ? RB200_MC_OBMC_ABOVE : RB200_MC_OBMC_LEFT);
     } else {
         /* reference of another size: the position arithmetic of the scaled branch stays on the host */
-        if (list) { rb_batch_unsupported(B, "OBMC strip from a scaled reference"); return; }
         const int orig_pos_y = (by * v_mul << 4) + mvy * (1 << !ss_ver);
         const int orig_pos_x = (bx * h_mul << 4) + mvx * (1 << !ss_hor);
 #define scale_mv(res, val, scale) do { \
@@ -116,10 +115,11 @@ static void push_mc(RbHostBatch *const B, const Dav1dFrameContext *const f, cons
         scale_mv(pos_x, orig_pos_x, f->svc[refidx][0].scale);
         scale_mv(pos_y, orig_pos_y, f->svc[refidx][1].scale);
 #undef scale_mv
-        Rb200McScaledItem *const it = RB_PUSH(B->scaled);
+        Rb200McScaledItem *const it = list == 0 ? RB_PUSH(B->scaled) : list == 1 ? RB_PUSH(B->scaled_obmc_above) : RB_PUSH(B->scaled_obmc_left);
         memset(it, 0, sizeof(*it));
         it->dst_x = (int16_t)dst_x; it->dst_y = (int16_t)dst_y;
-        it->w = (uint8_t)(bw4 * h_mul); it->h = (uint8_t)(bh4 * v_mul);
+        it->w = (uint8_t)(list ? blend_w : bw4 * h_mul); it->h = (uint8_t)(list ? blend_h : bh4 * v_mul);
+        it->flags = (uint8_t)(list == 0 ? RB200_MC_PUT : list == 1 ? RB200_MC_OBMC_ABOVE : RB200_MC_OBMC_LEFT);
         it->plane = (uint8_t)pl; it->ref = (uint8_t)refidx;
         it->pos_x = pos_x; it->pos_y = pos_y;
         it->step_x = f->svc[refidx][0].step; it->step_y = f->svc[refidx][1].step;

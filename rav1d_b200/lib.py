@@ -119,7 +119,7 @@ COMP_ITEM_DT = _np.dtype([("x", "<i2"), ("y", "<i2"), ("w", "u1"), ("h", "u1"), 
                           ("wedge_idx", "u1"), ("warp_mask", "u1"), ("pad", "u1", (10,))])
 SCALED_ITEM_DT = _np.dtype([("dst_x", "<i2"), ("dst_y", "<i2"), ("w", "u1"), ("h", "u1"), ("plane", "u1"), ("ref", "u1"),
                             ("pos_x", "<i4"), ("pos_y", "<i4"), ("step_x", "<i4"), ("step_y", "<i4"), ("filter2d", "u1"),
-                            ("pad", "u1", (7,))])
+                            ("flags", "u1"), ("pad", "u1", (6,))])
 assert SCALED_ITEM_DT.itemsize == 32
 INTRA_ITEM_DT = _np.dtype([("x4", "<u2"), ("y4", "<u2"), ("w4_end", "<u2"), ("h4_end", "<u2"), ("plane", "u1"), ("tw4", "u1"),
                            ("th4", "u1"), ("mode", "u1"), ("angle", "i1"), ("flags", "u1"), ("level", "<u2")])
@@ -275,6 +275,7 @@ ipc_close_handle = _sig("rb200_ipc_close_handle", _i, _vp)
 enable_peer_access = _sig("rb200_enable_peer_access", _i, _i)
 frame_set_stream = _sig("rb200_frame_set_stream", _i, _vp, _vp)
 frame_depend = _sig("rb200_frame_depend", _i, _vp, _vp)
+frame_set_scaled_obmc_counts = _sig("rb200_frame_set_scaled_obmc_counts", _i, _vp, _i, _i)
 frame_set_ref_gmv = _sig("rb200_frame_set_ref_gmv", _i, _vp, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int16))
 frame_set_plane_counts = _sig("rb200_frame_set_plane_counts", _i, _vp, _i, C.POINTER(C.c_int32))
 frame_validate = _sig("rb200_frame_validate", _i, _vp, _sz, C.POINTER(C.c_int32), _i, _i)

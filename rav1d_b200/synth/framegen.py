@@ -100,7 +100,7 @@ def scale_mv(val, scale):
 
 
 def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1, comp_frac=0.0, warp_frac=0.0, obmc_frac=0.0,
-             scaled_frac=0.0, scaled_size=None, gmv_frac=0.0):
+             scaled_frac=0.0, scaled_size=None, gmv_frac=0.0, scaled_obmc_frac=0.0):
     """Returns a SynthFrame with numpy arrays; see module docstring."""
     rng = np.random.default_rng(seed)
     bdmax = (1 << bpc) - 1
@@ -247,6 +247,29 @@ def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1, comp_frac=0.0, w
             o["step_x"] = st[0]; o["step_y"] = st[1]
             o["filter2d"] = f2d[si]
         s.scaled_items = out
+        s.n_scaled = (len(out), 0, 0)
+        if scaled_obmc_frac > 0:
+            # OBMC strips predicted from the scaled reference, on top of some of the scaled blocks: the blend area of an ABOVE
+            # strip is the block's upper half, of a LEFT strip its left half (obmc(), src/recon.rs:2205-2309); the strip's
+            # own vector (the neighbour's) differs from the block's
+            srng = np.random.default_rng(seed + 79)
+            strips = []
+            for kind, flag in ((0, lib.MC_OBMC_ABOVE), (1, lib.MC_OBMC_LEFT)):
+                pick = si[srng.random(si.size) < scaled_obmc_frac]
+                dvx, dvy = srng.integers(-40, 41, size=pick.size), srng.integers(-40, 41, size=pick.size)
+                for p in range(3):
+                    sh = 0 if p == 0 else 1
+                    o = np.zeros(pick.size, lib.SCALED_ITEM_DT)
+                    o["dst_x"] = bx[pick] * BLK >> sh; o["dst_y"] = by[pick] * BLK >> sh
+                    o["w"] = (BLK >> sh) >> (kind == 1); o["h"] = (BLK >> sh) >> (kind == 0); o["plane"] = p; o["ref"] = 2
+                    o["pos_x"] = scale_mv(((bx[pick] * BLK >> sh) << 4) + (mvx[pick] + dvx) * (2 >> sh), sc[0])
+                    o["pos_y"] = scale_mv(((by[pick] * BLK >> sh) << 4) + (mvy[pick] + dvy) * (2 >> sh), sc[1])
+                    o["step_x"] = st[0]; o["step_y"] = st[1]
+                    o["filter2d"] = f2d[pick]; o["flags"] = flag
+                    strips.append(o)
+            above, left = np.concatenate(strips[:3]), np.concatenate(strips[3:])
+            s.scaled_items = np.concatenate([out, above, left])
+            s.n_scaled = (len(out), len(above), len(left))
         raw, rah = (rw + 127) & ~127, (rh + 127) & ~127
         rrng = np.random.default_rng(seed + 78)
         s.ref3 = [np.zeros((rah, raw), pdt), np.zeros((rah // 2, raw // 2), pdt), np.zeros((rah // 2, raw // 2), pdt)]
@@ -908,7 +931,9 @@ class DeviceFrame:
         if scaled is not None and len(scaled):
             lib.check(lib.frame_reserve_scaled_items(self.h, len(scaled)), "reserve_scaled_items")
             lib.np_view(lib.frame_scaled_items(self.h), lib.SCALED_ITEM_DT, len(scaled))[:] = scaled
-            lib.check(lib.frame_set_scaled_count(self.h, len(scaled)))
+            n_put, n_above, n_left = getattr(s, "n_scaled", (len(scaled), 0, 0))
+            lib.check(lib.frame_set_scaled_count(self.h, n_put))
+            lib.check(lib.frame_set_scaled_obmc_counts(self.h, n_above, n_left))
         warp = getattr(s, "warp_items", None)
         if warp is not None and len(warp):
             lib.check(lib.frame_reserve_warp_items(self.h, len(warp)), "reserve_warp_items")

@@ -29,14 +29,16 @@ MANIFEST = json.load(open(os.path.join(FIX, "manifest.json")))["streams"]
 
 def _run_all(exe, ents, jobs):
     """Decode `ents` with the multi-stream runner `exe` (jobs processes, one CUDA context each); returns the lines that
-    are not "ok".  Streams with extra CLI arguments all ask for --filmgrain 1, which is the runner's (and the library's) default."""
+    are not "ok".  Streams with extra CLI arguments all ask for --filmgrain 1; without it the md5 muxer of the reference's CLI
+    decodes with film grain off (tools/dav1d_cli_parse.c:420-426), and so does the runner."""
     assert all(e["args"] in ([], ["--filmgrain", "1"]) for e in ents)
     import tempfile
     chunks = [ents[i::jobs] for i in range(jobs) if ents[i::jobs]]
 
     def one(chunk):
         with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
-            f.write("".join(f"{os.path.join(FIX, e['path'])} {e['md5']}\n" for e in chunk))
+            # film grain only where the manifest asks for it: under the md5 muxer the reference's CLI leaves it off otherwise
+            f.write("".join(f"{os.path.join(FIX, e['path'])} {e['md5']} {int('--filmgrain' in e['args'])}\n" for e in chunk))
         try:
             r = subprocess.run([os.path.join(BIN, exe), f.name], capture_output=True, text=True, timeout=1200)
         finally:

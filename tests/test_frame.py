@@ -104,6 +104,16 @@ def test_scaled_reference_blocks(rb, ref, w, h, bpc, rsize):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("w,h,bpc,rsize", [(320, 192, 8, (256, 160)), (256, 160, 10, (384, 200)), (208, 144, 12, (104, 72))])
+def test_obmc_strips_from_scaled_references(rb, ref, w, h, bpc, rsize):
+    """OBMC strips whose neighbour predicts from a reference of another size: mc_scaled for the strip (its prediction
+    height picks the filters), then blend_h / blend_v (src/recon.rs:2205-2309 with the scaled branch of mc())."""
+    s = framegen.generate(w, h, bpc, seed=w + 9, scaled_frac=0.5, scaled_size=rsize, scaled_obmc_frac=0.6)
+    assert s.n_scaled[1] > 10 and s.n_scaled[2] > 10
+    _check(ref, s, R)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("layout", [0, 1, 2, 3])
 @pytest.mark.parametrize("w,h,bpc", [(192, 128, 8), (256, 160, 10), (176, 144, 12)])
 def test_recon_all_layouts(rb, ref, layout, w, h, bpc):
