@@ -411,6 +411,41 @@ static void comp_warp_prep(RefFrame *r, const RefFrame *rfr, int16_t *tmp, int p
     }
 }
 
+/* The prediction of a compound block from a reference of another size: the scaled branch of mc() with dst16
+ * (src/recon_tmpl.c:1010-1073), scale factors as dav1d_submit_frame derives them from the two sizes. */
+typedef void (*mcts_fn8)(int16_t *, const void *, ptrdiff_t, int, int, int, int, int, int);
+typedef void (*mcts_fn16)(int16_t *, const void *, ptrdiff_t, int, int, int, int, int, int, int);
+static int comp_scale_mv(int v, int scale) {
+    const int64_t t = (int64_t)v * scale + (int64_t)(scale - 0x4000) * 8;
+    const int64_t a = ((t < 0 ? -t : t) + 128) >> 8;
+    return (int)(t < 0 ? -a : a) + 32;
+}
+static void comp_scaled_prep(RefFrame *r, const RefFrame *rfr, int16_t *tmp, int pl, int px0, int py0, int bw, int bh,
+                             int mvx, int mvy, int filter2d, uint8_t *emu) {
+    Dav1dFrameContext *f = r->f;
+    const Dav1dFrameContext *rf = rfr->f;
+    const int px = r->hbd ? 2 : 1;
+    const int ss_hor = pl && f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444, ss_ver = pl && f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420;
+    const int scale_x = ((rf->cur.p.w << 14) + (f->cur.p.w >> 1)) / f->cur.p.w, scale_y = ((rf->cur.p.h << 14) + (f->cur.p.h >> 1)) / f->cur.p.h;
+    const int step_x = (scale_x + 8) >> 4, step_y = (scale_y + 8) >> 4;
+    const int pos_x = comp_scale_mv((px0 << 4) + mvx * (1 << !ss_hor), scale_x), pos_y = comp_scale_mv((py0 << 4) + mvy * (1 << !ss_ver), scale_y);
+    const int left = pos_x >> 10, top = pos_y >> 10;
+    const int right = ((pos_x + (bw - 1) * step_x) >> 10) + 1, bottom = ((pos_y + (bh - 1) * step_y) >> 10) + 1;
+    const int w = (rf->cur.p.w + ss_hor) >> ss_hor, h = (rf->cur.p.h + ss_ver) >> ss_ver;
+    ptrdiff_t ref_stride = rf->cur.stride[!!pl];
+    const uint8_t *ref;
+    if (left < 3 || top < 3 || right + 4 > w || bottom + 4 > h) {
+        ((void (*)(intptr_t, intptr_t, intptr_t, intptr_t, intptr_t, intptr_t, void *, ptrdiff_t, const void *, ptrdiff_t))
+             f->dsp->mc.emu_edge)(right - left + 7, bottom - top + 7, w, h, left - 3, top - 3, emu, 320 * px, rf->cur.data[pl], ref_stride);
+        ref = emu + (320 * 3 + 3) * px;
+        ref_stride = 320 * px;
+    } else {
+        ref = (const uint8_t *)rf->cur.data[pl] + ref_stride * top + (ptrdiff_t)left * px;
+    }
+    if (r->hbd) ((mcts_fn16)f->dsp->mc.mct_scaled[filter2d])(tmp, ref, ref_stride, bw, bh, pos_x & 0x3ff, pos_y & 0x3ff, step_x, step_y, r->bdmax);
+    else ((mcts_fn8)f->dsp->mc.mct_scaled[filter2d])(tmp, ref, ref_stride, bw, bh, pos_x & 0x3ff, pos_y & 0x3ff, step_x, step_y);
+}
+
 static int wedge_bs(int w, int h) {
     switch (w << 8 | h) {
     case 32 << 8 | 32: return BS_32x32; case 32 << 8 | 16: return BS_32x16; case 32 << 8 | 8: return BS_32x8;
@@ -440,6 +475,8 @@ static void do_comp_chunk(RefFrame *r, int tid, int chunk, void *arg) {
             for (int k = 0; k < 2; k++) {
                 if ((it->warp_mask >> ((pl ? 2 : 0) + k)) & 1)      /* the reference's global-motion warp (frame_hdr.gmv) */
                     comp_warp_prep(r, a->refs[it->ref[k]], tmp[k], pl, it->x, it->y, bw, bh, &f->frame_hdr->gmv[it->ref[k]], emu);
+                else if (a->refs[it->ref[k]]->f->cur.p.w != f->cur.p.w || a->refs[it->ref[k]]->f->cur.p.h != f->cur.p.h)
+                    comp_scaled_prep(r, a->refs[it->ref[k]], tmp[k], pl, x0, y0, bw, bh, it->mv[k][1], it->mv[k][0], it->filter2d, emu);
                 else
                     comp_prep(r, a->refs[it->ref[k]], tmp[k], pl, x0, y0, bw, bh, it->mv[k][1], it->mv[k][0], it->filter2d, emu);
             }

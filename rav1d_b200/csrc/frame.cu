@@ -1291,7 +1291,7 @@ extern "C" int rb200_frame_submit(Rb200Frame *f, size_t n_coefs, const int32_t i
         }
         if (f->n_comp) {
             if ((r = mc_comp_batch_launch_gmv(f->planes[0], f->refs, f->n_refs, h.width, h.height, h.layout, f->d_comp, f->n_comp,
-                                              f->bdmax, st, f->ref_gmv))) return r;
+                                              f->bdmax, st, f->ref_gmv, &f->ref_dims))) return r;
             f->launches++;
         }
         if (f->n_scaled) {

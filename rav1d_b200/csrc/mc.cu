@@ -682,6 +682,10 @@ mc_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int ss_hor
     }
 }
 
+template <typename BD, bool PREP>
+__device__ __forceinline__ int mc_scaled_px(const McRef &ref, int ox, int oy, int w, int h, int mx, int my, int dx, int dy,
+                                            int filter2d, int x, int y, int bdmax);
+
 // ---------------------------------------------------------------- compound blocks (batch)
 // One warp per block.  Per 16x16 luma tile: both references are predicted in `prep` form into
 // shared memory, combined into the luma plane, and -- for the segmentation compound -- the full
@@ -704,7 +708,7 @@ struct McCompJob {
 template <typename BD>
 __global__ void __launch_bounds__(MC_WARPS * 32)
 mc_comp_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int layout,
-                     const Rb200CompItem *__restrict__ items, int n_items, int bdmax, McGmvSet gmv) {
+                     const Rb200CompItem *__restrict__ items, int n_items, int bdmax, McGmvSet gmv, McRefDims dims) {
     using pixel = typename BD::pixel;
     __shared__ McCompSmem smem[MC_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -717,7 +721,13 @@ mc_comp_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int l
     const int mask_sh = bitdepth + ib - 4, mask_rnd = 1 << (mask_sh - 5);
 
     // geometry of a job: reference plane, source position and phase (src/recon.rs:2047-2055,2100-2101)
-    struct Geo { McRef ref; int pw, ph, bw, bh, px0, py0, sx, sy, mx, my; bool fast, warped; };
+    struct Geo { McRef ref; int pw, ph, bw, bh, px0, py0, sx, sy, mx, my; bool fast, warped, scaled; int pos_x, pos_y, step_x, step_y; };
+    auto slot_dim = [&](int slot, bool height) {          // (no run-time index into the parameter struct)
+        int v = 0;
+#pragma unroll
+        for (int s_ = 0; s_ < 8; s_++) if (s_ == slot) v = height ? dims.h[s_] : dims.w[s_];
+        return v;
+    };
     auto geo = [&](const McCompJob &j) {
         Geo g;
         // the prediction is the reference's global-motion warp (warp_affine with frame_hdr.gmv[ref], src/recon.rs:3253-3268;
@@ -735,7 +745,26 @@ mc_comp_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int l
         const int mvy = j.i ? j.it.mv[1][0] : j.it.mv[0][0], mvx = j.i ? j.it.mv[1][1] : j.it.mv[0][1];
         g.mx = (mvx & (15 >> !ss_hor)) << !ss_hor; g.my = (mvy & (15 >> !ss_ver)) << !ss_ver;
         g.sx = g.px0 + (mvx >> (3 + ss_hor)); g.sy = g.py0 + (mvy >> (3 + ss_ver));
-        g.fast = !((g.pw | g.ph) & 1) && !(g.pw & (g.pw - 1)) && !g.warped;
+        // a reference of another size (src/recon.rs:2116-2199): position and step of the scaled prediction from the
+        // slot's size -- scale = ((ref << 14) + (cur >> 1)) / cur, step = (scale + 8) >> 4 (src/decode.rs, f.svc) -- and
+        // scale_mv() of the block's 1/16-pel position in this plane
+        const int slot = (j.i ? j.it.ref[1] : j.it.ref[0]) & 7;
+        const int rw = slot_dim(slot, false), rh = slot_dim(slot, true);
+        g.scaled = rw > 0 && rh > 0 && (rw != ref_w || rh != ref_h);
+        if (g.scaled) {
+            g.ref.w = j.pl ? (rw + ss_hor) >> ss_hor : rw;
+            g.ref.h = j.pl ? (rh + ss_ver) >> ss_ver : rh;
+            const int scale_x = ((rw << 14) + (ref_w >> 1)) / ref_w, scale_y = ((rh << 14) + (ref_h >> 1)) / ref_h;
+            g.step_x = (scale_x + 8) >> 4; g.step_y = (scale_y + 8) >> 4;
+            auto scale_mv = [](int v, int scale) {
+                const long long t = (long long)v * scale + (long long)(scale - 0x4000) * 8;
+                const long long a = ((t < 0 ? -t : t) + 128) >> 8;
+                return (int)(t < 0 ? -a : a) + 32;
+            };
+            g.pos_x = scale_mv(((j.it.x >> ss_hor) << 4) + mvx * (1 << !ss_hor), scale_x);
+            g.pos_y = scale_mv(((j.it.y >> ss_ver) << 4) + mvy * (1 << !ss_ver), scale_y);
+        }
+        g.fast = !((g.pw | g.ph) & 1) && !(g.pw & (g.pw - 1)) && !g.warped && !g.scaled;
         return g;
     };
     // warp8x8t over the 8x8s of a tile into tmp (prep form), one warp: src/recon.rs:2311-2400, src/mc.rs:958-1030
@@ -830,6 +859,15 @@ mc_comp_batch_kernel(Rb200Planes dst, McRefSet refs, int ref_w, int ref_h, int l
                 mc_tile_fast<BD, 0, 0, true>(sm.fast, sm.fast.win[buf], W, g.pw, g.ph, g.bw, g.bh, g.mx, g.my, it.filter2d, nullptr, 0, bdmax, (uint16_t *)sm.tmp[cur.i]);
         } else if (g.warped) {
             warp_tile(cur, g, sm.tmp[cur.i]);
+        } else if (g.scaled) {
+            // prep_8tap_scaled per pixel (rare path): the tile's pixels of the block-wide scaled prediction
+            const int ox = g.pos_x >> 10, oy = g.pos_y >> 10, smx = g.pos_x & 0x3ff, smy = g.pos_y & 0x3ff;
+            const int bx0 = g.px0 - (it.x >> (cur.pl ? ss_hor_c : 0)), by0 = g.py0 - (it.y >> (cur.pl ? ss_ver_c : 0));   // tile origin inside the block
+            for (int e = lane; e < g.pw * g.ph; e += 32) {
+                const int r = e / g.pw, c = e - r * g.pw;
+                sm.tmp[cur.i][r * MC_TILE + c] = (int16_t)mc_scaled_px<BD, true>(g.ref, ox, oy, g.bw, g.bh, smx, smy, g.step_x, g.step_y,
+                                                                                 it.filter2d, bx0 + c, by0 + r, bdmax);
+            }
         } else {
             mc_tile<BD, true>(sm.slow, g.ref, g.sx, g.sy, g.pw, g.ph, g.bw, g.bh, g.mx, g.my, it.filter2d, sm.tmp[cur.i], MC_TILE, bdmax);
         }
@@ -906,14 +944,16 @@ int mc_comp_batch_launch(const Rb200Planes &dst, const Rb200Planes *refs, int n_
 }
 
 int mc_comp_batch_launch_gmv(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int layout,
-                             const Rb200CompItem *d_items, int n, int bdmax, cudaStream_t st, const McGmvSet &gmv) {
+                             const Rb200CompItem *d_items, int n, int bdmax, cudaStream_t st, const McGmvSet &gmv, const McRefDims *dims_in) {
     if (n <= 0) return 0;
+    McRefDims dims = {};
+    if (dims_in) dims = *dims_in;
     McRefSet rs = {};
     for (int i = 0; i < n_refs && i < 8; i++) rs.p[i] = refs[i];
     { const int r = mc_ensure_packed_taps(st); if (r) return r; }
     const int grid = imin((n + MC_WARPS - 1) / MC_WARPS, 148 * 4);   // persistent warps walk the list
-    if (bdmax > 255) mc_comp_batch_kernel<BD16><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, layout, d_items, n, bdmax, gmv);
-    else mc_comp_batch_kernel<BD8><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, layout, d_items, n, bdmax, gmv);
+    if (bdmax > 255) mc_comp_batch_kernel<BD16><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, layout, d_items, n, bdmax, gmv, dims);
+    else mc_comp_batch_kernel<BD8><<<grid, MC_WARPS * 32, 0, st>>>(dst, rs, ref_w, ref_h, layout, d_items, n, bdmax, gmv, dims);
     RB_LAUNCH_CHECK();
     return 0;
 }

@@ -16,8 +16,10 @@ int cdef_planes_launch(const Rb200Planes &src, const Rb200Planes &dst, const Cde
 // compound blocks, with the references' global-motion parameters for predictions that are warps (Rb200CompItem.warp_mask)
 struct McGmv { int32_t matrix[6]; int16_t abcd[4]; };
 struct McGmvSet { McGmv g[8]; };
+// dims: luma size of every reference slot; a prediction from a slot whose size differs from ref_w x ref_h is a scaled one
 int mc_comp_batch_launch_gmv(const Rb200Planes &dst, const Rb200Planes *refs, int n_refs, int ref_w, int ref_h, int layout,
-                             const Rb200CompItem *d_items, int n, int bdmax, cudaStream_t st, const McGmvSet &gmv);
+                             const Rb200CompItem *d_items, int n, int bdmax, cudaStream_t st, const McGmvSet &gmv,
+                             const McRefDims *dims = nullptr);
 // loop restoration with the window fetched by TMA (lr.cu)
 int lr_encode_maps(CUtensorMap_st *map_main, CUtensorMap_st *map_halo, const void *cdef, const void *dbl, int64_t stride, int w, int h);
 int lr_plane_launch_tma(const uint8_t *cdef, const uint8_t *dbl, uint8_t *out, int64_t stride, const LrFrameParams &P,

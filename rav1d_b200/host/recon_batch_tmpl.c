@@ -577,9 +577,7 @@ int bytefn(dav1d_recon_b_inter)(Dav1dTaskContext *const t, const enum BlockSize 
                                   b->inter_mode == GLOBALMV_GLOBALMV && f->gmv_warp_allowed[b->ref[1]] };
         if ((gmv_warp[0] && !same_size[0]) || (gmv_warp[1] && !same_size[1])) {
             rb_batch_unsupported(B, "warped block from a reference of another size");
-        } else if (!same_size[0] || !same_size[1]) {
-            rb_batch_unsupported(B, "compound block from a reference of another size");
-        } else {
+        } else {      /* (predictions from references of another size: the kernel scales them, rb200_frame_set_ref_size) */
             Rb200CompItem *const it = RB_PUSH(B->comp);
             memset(it, 0, sizeof(*it));
             it->x = (int16_t)dx0; it->y = (int16_t)dy0;

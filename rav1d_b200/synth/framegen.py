@@ -100,7 +100,7 @@ def scale_mv(val, scale):
 
 
 def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1, comp_frac=0.0, warp_frac=0.0, obmc_frac=0.0,
-             scaled_frac=0.0, scaled_size=None, gmv_frac=0.0, scaled_obmc_frac=0.0):
+             scaled_frac=0.0, scaled_size=None, gmv_frac=0.0, scaled_obmc_frac=0.0, comp_scaled_frac=0.0):
     """Returns a SynthFrame with numpy arrays; see module docstring."""
     rng = np.random.default_rng(seed)
     bdmax = (1 << bpc) - 1
@@ -182,6 +182,13 @@ def generate(w, h, bpc, seed=1, res_amp_shift=4, skip_frac=0.1, comp_frac=0.0, w
         s.gmv_matrix = gm.astype(np.int32)
         s.gmv_abcd = np.zeros((8, 4), np.int16)
         s.gmv_abcd[:2] = (rng.integers(0, 0x800, size=(2, 4)) - 0x400).astype(np.int16)
+    if comp_scaled_frac > 0:
+        # compound blocks with one or both predictions from the reference of another size (slot 2; needs scaled_frac > 0)
+        crng = np.random.default_rng(seed + 80)
+        pick = crng.random(ci.size) < comp_scaled_frac
+        which = crng.integers(1, 4, size=ci.size)
+        comp["ref"][:, 0] = np.where(pick & ((which & 1) != 0), 2, comp["ref"][:, 0])
+        comp["ref"][:, 1] = np.where(pick & ((which & 2) != 0), 2, comp["ref"][:, 1])
     s.comp_items = comp
     if comp_frac > 0:
         s.ref2 = [np.zeros((ah, aw), pdt), np.zeros((ah // 2, aw // 2), pdt), np.zeros((ah // 2, aw // 2), pdt)]

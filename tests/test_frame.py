@@ -114,6 +114,16 @@ def test_obmc_strips_from_scaled_references(rb, ref, w, h, bpc, rsize):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("w,h,bpc,rsize", [(320, 192, 8, (256, 160)), (256, 160, 10, (384, 200)), (208, 144, 12, (104, 72))])
+def test_compound_blocks_from_scaled_references(rb, ref, w, h, bpc, rsize):
+    """Compound blocks with one or both predictions from a reference of another size (prep_8tap_scaled inside the compound
+    kernel, position and step from the two sizes), under every compound type."""
+    s = framegen.generate(w, h, bpc, seed=w + 13, comp_frac=0.5, scaled_frac=0.2, scaled_size=rsize, comp_scaled_frac=0.7)
+    assert (s.comp_items["ref"] == 2).any(axis=1).sum() > 10
+    _check(ref, s, R)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("layout", [0, 1, 2, 3])
 @pytest.mark.parametrize("w,h,bpc", [(192, 128, 8), (256, 160, 10), (176, 144, 12)])
 def test_recon_all_layouts(rb, ref, layout, w, h, bpc):
