@@ -550,7 +550,11 @@ int rb200_frame_set_scaled_obmc_counts(Rb200Frame *f, int n_above, int n_left);
  * inter prediction comes from the ordinary Rb200McItem lists, its residual must be attached to the intra item.
  * Palette blocks (pal_pred): mode 14, tw4 x th4 = the whole block, w4_end | h4_end << 16 = offset in 16-byte units of the
  * block's record { 8 palette entries padded to 16 bytes, w * h index bytes } in rb200_frame_palette_buffer(); the further
- * transform blocks of such a block are items of mode 15 (no prediction, only the residual). */
+ * transform blocks of such a block are items of mode 15 (no prediction, only the residual).
+ * Intra block copy (src/recon.rs:3196-3240 == src/recon_tmpl.c:1631-1645: mc() with the bilinear filter from the picture
+ * being reconstructed) is one item of mode 16 per plane: tw4 x th4 is the whole block, (int16) w4_end / h4_end the source
+ * position in plane pixels, angle = mx | my << 4 (the 1/16-pixel fractions mc() hands the filter), no residual of its
+ * own -- the block's transform blocks follow as items of mode 15.  Its level is one above everything in the source area. */
 typedef struct Rb200IntraItem {
     uint16_t x4, y4;          /* block position in `plane`, 4-pixel units (t.bx, t.by; >> ss for chroma) */
     uint16_t w4_end, h4_end;  /* tile end in the same units: the `w`, `h` arguments of rav1d_prepare_intra_edges (bits 0-12) */

@@ -714,6 +714,23 @@ void ref_frame_recon_intra(RefFrame *r, const Rb200IntraItem *items, int n, cons
                 const uint8_t *rec = pal_buf + ((size_t)it->w4_end | (size_t)it->h4_end << 16) * 16;
                 ((void (*)(void *, ptrdiff_t, const void *, const uint8_t *, int, int))f->dsp->ipred.pal_pred)(dst, stride, rec, rec + 16,
                                                                                                          it->tw4 * 4, it->th4 * 4);
+            } else if (it->mode == 16) {   /* intra block copy: mc() from the current picture, src/recon_tmpl.c:1631-1645,979-1009 */
+                static uint8_t emu[192 * (128 + 7) * 2];
+                const int dx = (int16_t)it->w4_end, dy = (int16_t)it->h4_end, mx = (uint8_t)it->angle & 15, my = (uint8_t)it->angle >> 4;
+                const int bw = it->tw4 * 4, bh = it->th4 * 4, w = f->bw * 4 >> ss_hor, h = f->bh * 4 >> ss_ver;
+                const uint8_t *ref;
+                ptrdiff_t ref_stride = stride;
+                if (dx < !!mx * 3 || dy < !!my * 3 || dx + bw + !!mx * 4 > w || dy + bh + !!my * 4 > h) {
+                    ((void (*)(intptr_t, intptr_t, intptr_t, intptr_t, intptr_t, intptr_t, void *, ptrdiff_t, const void *, ptrdiff_t))
+                         f->dsp->mc.emu_edge)(bw + !!mx * 7, bh + !!my * 7, w, h, dx - !!mx * 3, dy - !!my * 3, emu,
+                                              192 * px, f->cur.data[pl], stride);
+                    ref = emu + (192 * !!my * 3 + !!mx * 3) * px;
+                    ref_stride = 192 * px;
+                } else {
+                    ref = (const uint8_t *)f->cur.data[pl] + stride * dy + (ptrdiff_t)dx * px;
+                }
+                if (r->hbd) ((mc_fn16)f->dsp->mc.mc[FILTER_2D_BILINEAR])(dst, stride, ref, ref_stride, bw, bh, mx, my, r->bdmax);
+                else ((mc_fn8)f->dsp->mc.mc[FILTER_2D_BILINEAR])(dst, stride, ref, ref_stride, bw, bh, mx, my);
             }
         } else if (pl && it->mode == 13) {   /* chroma from luma, src/recon_tmpl.c:1376-1422 */
             int16_t ac[32 * 32];

@@ -405,6 +405,43 @@ __device__ __forceinline__ void intra_item(IntraSmem<typename BD::pixel> &M, con
             for (int i = tid; i < tw * th * 16; i += blockDim.x)
                 ((pixel *)(dst8 + (int64_t)(i / (tw * 4)) * stride))[i % (tw * 4)] = pal[idx[i] & 7];
         }
+        // 16: intra block copy (src/recon_tmpl.c:1631-1645): mc() with the bilinear filter from the picture being
+        // reconstructed.  (int16) w4_end / h4_end = the source position in plane pixels, angle = mx | my << 4 in 1/16
+        // pixels (non-zero only for sub-sampled chroma); source pixels clamp to the picture rounded up to 8 luma pixels
+        // (emu_edge with w = f.bw * 4 >> ss_hor, :988-989).  put_bilin_c (src/mc_tmpl.c:146-203) per pixel.
+        if (it.mode == 16) {
+            const int sx = (int16_t)it.w4_end, sy = (int16_t)it.h4_end;
+            const int mx = (uint8_t)it.angle & 15, my = ((uint8_t)it.angle >> 4) & 15;
+            const int pw = (frame_w4 * 4) >> ss_hor, ph = (frame_h4 * 4) >> ss_ver;
+            const uint8_t *sbase = plane_ptr(cur, it.plane);
+            const int ib = BD::hbd ? 14 - bitdepth : 4;
+            auto px = [&](int xx, int yy) -> int {
+                xx = iclip(xx, 0, pw - 1); yy = iclip(yy, 0, ph - 1);
+                return (int)pic_ld<CG>((const pixel *)(sbase + (int64_t)yy * stride) + xx);
+            };
+            const int bw = tw * 4, n = bw * th * 4;
+            for (int i = tid; i < n; i += blockDim.x) {
+                const int xx = sx + i % bw, yy = sy + i / bw;
+                int v;
+                if (mx) {
+                    const int a = px(xx, yy), b = px(xx + 1, yy);
+                    const int m0 = (16 * a + mx * (b - a) + ((1 << (4 - ib)) >> 1)) >> (4 - ib);
+                    if (my) {
+                        const int c = px(xx, yy + 1), d = px(xx + 1, yy + 1);
+                        const int m1 = (16 * c + mx * (d - c) + ((1 << (4 - ib)) >> 1)) >> (4 - ib);
+                        v = (16 * m0 + my * (m1 - m0) + ((1 << (4 + ib)) >> 1)) >> (4 + ib);
+                    } else {
+                        v = (m0 + ((1 << ib) >> 1)) >> ib;
+                    }
+                } else if (my) {
+                    const int a = px(xx, yy), c = px(xx, yy + 1);
+                    v = (16 * a + my * (c - a) + 8) >> 4;
+                } else {
+                    v = px(xx, yy);
+                }
+                ((pixel *)(dst8 + (int64_t)(i / bw) * stride))[i % bw] = (pixel)iclip(v, 0, bdmax);
+            }
+        }
         if (ti < 0) return;
         __syncthreads();
         add_residual();

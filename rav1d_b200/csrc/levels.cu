@@ -43,6 +43,10 @@ extern "C" int rb200_intra_assign_levels(Rb200IntraItem *items, int n, int frame
             dep = -1;                                                    // palette: no neighbours
         } else if (it.mode == 15) {
             dep = rect_max(p, x, x + tw, y, y + th);                     // residual on top of an earlier prediction
+        } else if (it.mode == 16) {                                      // intra block copy: the source area (+ 1 pixel
+            const int sx = (int16_t)it.w4_end, sy = (int16_t)it.h4_end;  // right / below for the bilinear filter)
+            const int xa = std::min(std::max(sx >> 2, 0), pw[p] - 1), ya = std::min(std::max(sy >> 2, 0), ph[p] - 1);
+            dep = rect_max(p, xa, std::max((sx + tw * 4 + 4) >> 2, xa + 1), ya, std::max((sy + th * 4 + 4) >> 2, ya + 1));
         } else {
             dep = std::max(rect_max(p, x - 1, x, y - 1, y + th), rect_max(p, x, x + tw, y - 1, y));
             const bool plain = !(it.flags & 64) && !(p && it.mode == 13);

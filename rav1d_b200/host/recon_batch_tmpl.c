@@ -38,7 +38,7 @@
 /* flags of Rb200IntraItem */
 enum { II_HAVE_LEFT = 1, II_HAVE_TOP = 2, II_TOP_HAS_RIGHT = 4, II_LEFT_HAS_BOTTOM = 8, II_SMOOTH = 16, II_EDGE_FILTER = 32,
        II_INTER_INTRA = 64 };
-enum { MODE_CFL = 13, MODE_PAL = 14, MODE_RESIDUAL = 15 };
+enum { MODE_CFL = 13, MODE_PAL = 14, MODE_RESIDUAL = 15, MODE_INTRABC = 16 };
 
 static inline int plane_ss_hor(const Dav1dFrameContext *const f, const int pl) {
     return pl && f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444;
@@ -72,6 +72,29 @@ static void push_intra_residual_only(RbHostBatch *const B, const Dav1dFrameConte
     it->plane = (uint8_t)pl; it->tw4 = td->w; it->th4 = td->h; it->mode = MODE_RESIDUAL;
     *RB_PUSH(B->intra_itx) = B->iitx.n;
     fill_itx(RB_PUSH(B->iitx), f, cf, pl, 4 * x4, 4 * y4, tx, txtp, eob);
+}
+
+/* Intra block copy of one plane: mc() (src/recon_tmpl.c:962-1014) with refp == the current picture, as an item of the
+ * intra wavefront.  x4 / y4: destination in plane 4-pixel units; bw4 / bh4, bx / by: mc()'s arguments. */
+static void push_intrabc(RbHostBatch *const B, const Dav1dFrameContext *const f, const int pl, const int x4, const int y4,
+                         const int bw4, const int bh4, const int bx, const int by, const mv mv)
+{
+    const int ss_ver = plane_ss_ver(f, pl), ss_hor = plane_ss_hor(f, pl);
+    const int h_mul = 4 >> ss_hor, v_mul = 4 >> ss_ver;
+    const int mx = mv.x & (15 >> !ss_hor), my = mv.y & (15 >> !ss_ver);
+    const int w = f->bw * 4 >> ss_hor, h = f->bh * 4 >> ss_ver;
+    /* emu_edge replicates the border: a window that lies wholly outside can be moved next to the picture */
+    const int dx = iclip(bx * h_mul + (mv.x >> (3 + ss_hor)), -(bw4 * h_mul + 16), w + 16);
+    const int dy = iclip(by * v_mul + (mv.y >> (3 + ss_ver)), -(bh4 * v_mul + 16), h + 16);
+    if (w + 16 > 32767 || h + 16 > 32767) { rb_batch_unsupported(B, "intra block copy in a picture beyond 32K"); return; }
+    Rb200IntraItem *const it = RB_PUSH(B->intra);
+    memset(it, 0, sizeof(*it));
+    it->x4 = (uint16_t)x4; it->y4 = (uint16_t)y4;
+    it->w4_end = (uint16_t)(int16_t)dx; it->h4_end = (uint16_t)(int16_t)dy;
+    it->plane = (uint8_t)pl; it->tw4 = (uint8_t)(bw4 * h_mul >> 2); it->th4 = (uint8_t)(bh4 * v_mul >> 2);
+    it->mode = MODE_INTRABC;
+    it->angle = (int8_t)(uint8_t)((mx << !ss_hor) | (my << !ss_ver) << 4);
+    *RB_PUSH(B->intra_itx) = -1;
 }
 
 /* ---- mc(): src/recon.rs:2025-2203 (C: src/recon_tmpl.c:962-1074).
@@ -485,8 +508,13 @@ int bytefn(dav1d_recon_b_inter)(Dav1dTaskContext *const t, const enum BlockSize 
 
     // prediction
     if (IS_KEY_OR_INTRA(f->frame_hdr)) {
-        /* intra block copy predicts from the frame being reconstructed: a dependency the frame-level stages cannot order */
-        rb_batch_unsupported(B, "intra block copy");
+        /* intra block copy (src/recon_tmpl.c:1631-1645) predicts from the picture being reconstructed: it joins the intra
+         * wavefront, one level above whatever wrote its source area, and its residual follows there too */
+        push_intrabc(B, f, 0, t->bx, t->by, bw4, bh4, t->bx, t->by, b->mv[0]);
+        if (has_chroma) for (int pl = 1; pl < 3; pl++)
+            push_intrabc(B, f, pl, t->bx >> ss_hor, t->by >> ss_ver, bw4 << (bw4 == ss_hor), bh4 << (bh4 == ss_ver),
+                         t->bx & ~ss_hor, t->by & ~ss_ver, b->mv[0]);
+        is_interintra = 1;
     } else if (b->comp_type == COMP_INTER_NONE) {
         const enum Filter2d filter_2d = b->filter2d;
         const int warped = (b->inter_mode == GLOBALMV && f->gmv_warp_allowed[b->ref[0]]) ||

@@ -583,7 +583,7 @@ def generate_recon_layout(w, h, bpc, layout, seed=1, comp_frac=0.3, warp_frac=0.
     return s
 
 
-def generate_intra(w, h, bpc, seed=1, inter_frac=0.0, layout=None, cfl_frac=0.25, ii_frac=0.3, pal_frac=0.1):
+def generate_intra(w, h, bpc, seed=1, inter_frac=0.0, layout=None, cfl_frac=0.25, ii_frac=0.3, pal_frac=0.1, ibc_frac=0.0):
     """A frame (4:2:0 unless `layout` says otherwise) whose 16x16 blocks are intra predicted (a fraction `inter_frac` of them translational inter blocks):
     per transform block a coded mode, angle delta, edge-availability flags consistent with the decode order (raster over
     blocks; inside a block luma transform blocks in raster order, then U, then V), the wavefront level the batch
@@ -655,6 +655,37 @@ def generate_intra(w, h, bpc, seed=1, inter_frac=0.0, layout=None, cfl_frac=0.25
                         itx_rows.append((p, x0, y0, rect) if rng.random() < 0.7 else None)
                     elif rng.random() < 0.7:
                         inter_itx.append((p, x0, y0, rect))
+                continue
+            if ibc_frac and (byi or bxi) and rng.random() < ibc_frac:
+                # intra block copy (src/recon.rs:3196-3240): per plane one item of mode 16 over the whole block, predicted from
+                # an area of the picture that is already decoded (rows of blocks above, or -- in the first row -- blocks to the
+                # left), a whole number of luma pixels away; the residual's transform blocks follow as items of mode 15
+                if byi: sxl, syl = int(rng.integers(-8, w - 4)), int(rng.integers(-8, (byi - 1) * BLK - 1))
+                else: sxl, syl = int(rng.integers(-8, (bxi - 1) * BLK - 1)), int(rng.integers(-6, -1))
+                mvx, mvy = 8 * (sxl - bxi * BLK), 8 * (syl - byi * BLK)
+                for p in range(n_planes):
+                    sx, sy = psx[p], psy[p]
+                    bwp, bhp = BLK >> sx, BLK >> sy
+                    x0, y0 = bxi * BLK >> sx, byi * BLK >> sy
+                    x4, y4, tw4, th4 = x0 // 4, y0 // 4, bwp // 4, bhp // 4
+                    dx, dy = x0 + (mvx >> (3 + sx)), y0 + (mvy >> (3 + sy))
+                    frac = ((mvx & (15 >> (1 - sx))) << (1 - sx)) | ((mvy & (15 >> (1 - sy))) << (1 - sy)) << 4
+                    W4, H4 = pw4[p], ph4[p]
+                    xa, ya = min(max(dx >> 2, 0), W4 - 1), min(max(dy >> 2, 0), H4 - 1)
+                    xb, yb = max((dx + bwp + 4) >> 2, xa + 1), max((dy + bhp + 4) >> 2, ya + 1)
+                    assert (dec[p][ya:min(yb, H4), xa:min(xb, W4)] < len(items)).all()
+                    level = int(lvl[p][ya:min(yb, H4), xa:min(xb, W4)].max()) + 1
+                    dec[p][y4:y4 + th4, x4:x4 + tw4] = len(items)
+                    lvl[p][y4:y4 + th4, x4:x4 + tw4] = level
+                    items.append((x4, y4, dx & 0xffff, dy & 0xffff, p, tw4, th4, 16, frac - 256 if frac > 127 else frac, 0, level))
+                    itx_rows.append(None)
+                    tsz = int(rng.choice([t for t in (4, 8, 16) if t <= min(bwp, bhp)]))
+                    for ty in range(0, th4, tsz // 4):
+                        for tx_ in range(0, tw4, tsz // 4):
+                            if rng.random() < 0.6:
+                                items.append((x4 + tx_, y4 + ty, 0, 0, p, tsz // 4, tsz // 4, 15, 0, 0, level + 1))
+                                itx_rows.append((p, (x4 + tx_) * 4, (y4 + ty) * 4, TXS[tsz]))
+                                lvl[p][y4 + ty:y4 + ty + tsz // 4, x4 + tx_:x4 + tx_ + tsz // 4] = level + 1
                 continue
             uv_cfl = rng.random() < cfl_frac                       # chroma from luma for this block (needs its luma first)
             pal_y, pal_uv = rng.random() < pal_frac, rng.random() < pal_frac

@@ -234,7 +234,7 @@ def test_intra_levels_host_helper(layout):
     and its level-sorted order is the one the frames are submitted in."""
     import ctypes as C
     from rav1d_b200 import lib
-    s = framegen.generate_intra(192, 160, 10, seed=90 + layout, inter_frac=0.3, layout=layout)
+    s = framegen.generate_intra(192, 160, 10, seed=90 + layout, inter_frac=0.3, layout=layout, ibc_frac=0.2 * (layout & 1))
     items = s.intra_items_decode.copy()
     want = items["level"].copy()
     items["level"] = 0xffff
@@ -264,6 +264,22 @@ def test_intra_blocks_other_layouts(rb, ref, layout):
     a = framecheck.oracle_frame(ref, s, R)
     b = framecheck.product_frame(s, R | rb.STAGE_INTRA)
     framecheck.assert_planes_equal(a, b, f"intra layout {layout}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,bpc,layout", [(192, 160, 8, 1), (160, 128, 10, 1), (192, 128, 12, 2), (160, 96, 10, 3), (96, 96, 8, 0)])
+def test_intra_block_copy(rb, ref, w, h, bpc, layout):
+    """Intra block copy (src/recon.rs:3196-3240: bilinear mc() from the picture being reconstructed, whole luma pixels, half
+    chroma pixels where chroma is sub-sampled, source windows that leave the picture) as items of the intra wavefront,
+    one level above whatever wrote the source area, with copies of copies and residuals on top."""
+    s = framegen.generate_intra(w, h, bpc, seed=w + bpc + layout, inter_frac=0.15, layout=layout, ibc_frac=0.35)
+    ibc = s.intra_items[s.intra_items["mode"] == 16]
+    assert len(ibc) > 10 and ibc["level"].max() > 3
+    if layout == 1:
+        assert set(int(a) & 0xff for a in ibc["angle"]) == {0, 8, 128, 136}
+    a = framecheck.oracle_frame(ref, s, R)
+    b = framecheck.product_frame(s, R | rb.STAGE_INTRA)
+    framecheck.assert_planes_equal(a, b, f"intra block copy {w}x{h}@{bpc} layout {layout}")
 
 
 @pytest.mark.gpu
