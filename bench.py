@@ -444,7 +444,7 @@ def run_gpu(args, s, wl):
         if args.workload in WARP_INST_PER_FRAME and clocks and clocks.get("sm_mhz"):
             peak_issue = 148 * 4 * clocks["sm_mhz"] * 1e6          # warp instructions / s
             wi = WARP_INST_PER_FRAME[args.workload]
-            issue = {"warp_inst_per_frame": wi, "peak_warp_inst_per_s": peak_issue, "source": "profiles/r02g_ncu_full_summary_4k10.csv" if args.workload == "4k10" else "profiles/r01c_ncu_full_summary_4k10c5.csv",
+            issue = {"warp_inst_per_frame": wi, "peak_warp_inst_per_s": peak_issue, "source": "profiles/r02i_ncu_full_summary_4k10.csv" if args.workload == "4k10" else "profiles/r02i_ncu_full_summary_4k10c5.csv",
                      "frac": round(wi * (value * 1e6 / (w * h)) / world / peak_issue, 4)}
         # frame-level algorithmic bytes as BASELINE.md 4 counts them (MC + itx = one fused recon stage: 2S + C)
         frame_bytes = (ab["recon"] if stages & 1 else 0) + sum(ab[k] for k in ("deblock", "cdef", "lr", "film_grain") if k in per_stage)
@@ -505,16 +505,16 @@ def run_gpu(args, s, wl):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
 # capture of the dominant kernel (profiles/), keyed by (workload, stage); None until captured.
 TRAFFIC = {
-    # profiles/r02g_ncu_full_summary_4k10.csv: cdef_dir_frame_kernel 13.88 MB + cdef_filter_tma_kernel 17.69 (luma) + 9.38 (chroma) MB
+    # profiles/r02i_ncu_full_summary_4k10.csv: cdef_dir_frame_kernel 13.9 MB + cdef_filter_tma_kernel 17.7 (luma) + 9.4 (chroma) MB
     ("4k10", "cdef"): 40.95e6,
     ("4k10", "mc"): 26.71e6,
     ("4k10", "lr"): 27.32e6,       # 17.79 + 4.76 + 4.77 MB (three planes)
-    # profiles/r01c_ncu_full_summary_4k10c5.csv: mc_batch 25.2 + mc_comp_batch 53.7 + warp 5.8 + obmc 8.4 + 13.9 MB
-    ("4k10c5", "mc"): 107.0e6,
+    # profiles/r02i_ncu_full_summary_4k10c5.csv: mc_batch 25.5 + mc_comp_batch 55.3 + warp 5.8 + obmc 8.4 + 13.9 MB
+    ("4k10c5", "mc"): 108.9e6,
 }
 # Executed warp instructions per frame (smsp__inst_executed.sum over one frame's launches, same captures): the path is
 # integer-issue bound, so value x this / (SMs x 4 schedulers x clock) says how full the issue slots are.
-WARP_INST_PER_FRAME = {"4k10": 164.1e6, "4k10c5": 293.9e6}   # 4k10: r02g capture (209 M in round 1); 4k10c5: r01c
+WARP_INST_PER_FRAME = {"4k10": 164.3e6, "4k10c5": 267.8e6}   # r02i captures (round 1: 209 M / 293.9 M)
 
 
 _JSON_OUT = None

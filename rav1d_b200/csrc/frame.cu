@@ -1097,6 +1097,11 @@ extern "C" int rb200_frame_validate(Rb200Frame *f, size_t n_coefs, const int32_t
         for (int i = 0; i < n_in; i++) {
             const Rb200IntraItem &it = f->h_intra[i];
             if (it.plane >= g.n_planes) return set_error(-22, "frame_validate: intra item %d: plane %d", i, it.plane);
+            if (it.mode > 16 || it.tw4 < 1 || it.tw4 > 16 || it.th4 < 1 || it.th4 > 16)
+                return set_error(-22, "frame_validate: intra item %d: mode %d, size %d x %d", i, it.mode, it.tw4, it.th4);
+            if (it.x4 * 4 >= plane_w(it.plane) || it.y4 * 4 >= plane_h(it.plane))      // the block may hang over, its origin may not
+                return set_error(-22, "frame_validate: intra item %d starts outside plane %d", i, it.plane);
+            if (it.level >= f->n_levels) return set_error(-22, "frame_validate: intra item %d: level %d of %d", i, it.level, f->n_levels);
             if (f->h_intra_itx[i] >= n_itx_all || f->h_intra_itx[i] < -1) return set_error(-22, "frame_validate: intra item %d names residual %d of %d", i, f->h_intra_itx[i], n_itx_all);
         }
     }

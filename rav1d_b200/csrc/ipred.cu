@@ -93,22 +93,26 @@ __device__ void ipred_block(IpScratch<typename BD::pixel> &S, int mode, uint8_t 
 
     switch (mode) {
     case IP_DC: case IP_TOP_DC: case IP_LEFT_DC: case IP_DC_128: {
+        // the edge sums by the first warp (every caller runs at least one full warp), the rest by its first lane
+        unsigned top_sum = 0, left_sum = 0;
+        if (tid < 32 && mode != IP_DC_128) {
+            if (mode != IP_LEFT_DC) for (int i = tid; i < w; i += 32) top_sum += tl[1 + i];
+            if (mode != IP_TOP_DC) for (int i = tid; i < h; i += 32) left_sum += tl[-(1 + i)];
+            for (int o = 16; o; o >>= 1) {
+                top_sum += __shfl_xor_sync(0xffffffffu, top_sum, o);
+                left_sum += __shfl_xor_sync(0xffffffffu, left_sum, o);
+            }
+        }
         if (tid == 0) {
             unsigned dc;
             if (mode == IP_DC_128) {
                 dc = BD::hbd ? (unsigned)(bdmax + 1) >> 1 : 128;
             } else if (mode == IP_TOP_DC) {
-                dc = w >> 1;
-                for (int i = 0; i < w; i++) dc += tl[1 + i];
-                dc >>= ulog2(w);
+                dc = ((w >> 1) + top_sum) >> ulog2(w);
             } else if (mode == IP_LEFT_DC) {
-                dc = h >> 1;
-                for (int i = 0; i < h; i++) dc += tl[-(1 + i)];
-                dc >>= ulog2(h);
+                dc = ((h >> 1) + left_sum) >> ulog2(h);
             } else {   // dc_gen, src/ipred_tmpl.c:150-166
-                dc = (w + h) >> 1;
-                for (int i = 0; i < w; i++) dc += tl[1 + i];
-                for (int i = 0; i < h; i++) dc += tl[-(1 + i)];
+                dc = ((w + h) >> 1) + top_sum + left_sum;
                 dc >>= __ffs(w + h) - 1;
                 if (w != h) {
                     const bool x4 = w > h * 2 || h > w * 2;
@@ -582,8 +586,8 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
                           ss_ver_c, bdmax, [] { asm volatile("griddepcontrol.wait;" ::: "memory"); });
 }
 
-// (b) ALL levels in one cooperative launch: the grid (every CTA resident) walks the levels; CTA b takes items
-// b, b + gridDim, ... of a level.  Instead of a kernel boundary per level there is one counter per level in global memory:
+// (b) ALL levels in one cooperative launch: the grid (every CTA resident) walks the levels; CTA b takes the items
+// i = b (mod gridDim) of the level-sorted list.  Instead of a kernel boundary per level there is one counter per level in global memory:
 // the CTA that has written an item of level l adds one to done[l], and before the first picture read of a level-l item
 // a CTA waits until done[l - 1] equals the number of items of level l - 1.  That is enough: by induction every item of
 // level l - 1 was itself only started when level l - 2 was complete (levels are never empty -- the host drops empty
@@ -622,15 +626,21 @@ intra_levels_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, c
             }
             __syncthreads();
         };
-        for (int i = beg + blockIdx.x; i < end; i += gridDim.x) {
+        // Item i of the level-sorted list belongs to CTA i % grid: consecutive levels then sit side by side on the ring of
+        // CTAs instead of all starting at CTA 0, so the CTAs of the next few levels have fetched their items and transformed
+        // their residuals by the time this level completes -- the per-level period is wait -> edge -> prediction -> release,
+        // not a whole item.
+        const int G = (int)gridDim.x;
+        int first = (int)blockIdx.x - beg % G;
+        if (first < 0) first += G;
+        for (int i = beg + first; i < end; i += G) {
             intra_item<BD, true>(M, cur, items[i], itx_of ? itx_of[i] : -1, itx, cf, pal_buf, frame_w4, frame_h4, ss_hor_c, ss_ver_c, bdmax,
                                  level_wait);
             __syncthreads();            // the item is in the picture (as far as this CTA is concerned) and its shared memory is free
             if (abort_s) return;
-            if (tid == 0) {
-                __threadfence();
-                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(done + l) : "memory");
-            }
+            // release at gpu scope, cumulative over the barrier above: every thread's stores of this item are visible to
+            // whoever acquires the counter -- no separate fence
+            if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(done + l) : "memory");
         }
     }
 }
@@ -669,9 +679,9 @@ int intra_levels_launch(const Rb200Planes &cur, const Rb200IntraItem *d_items, c
         if (occ < 1) return set_error(-12, "intra_levels_launch: the kernel does not fit an SM");
         per_sm[hbd] = occ < 4 ? occ : 4;
     }
-    // As many CTAs as fit (three per SM at 168 registers) unless RB200_INTRA_CTAS_PER_SM says otherwise, and never more
-    // than the widest level has items.
-    static const int want = getenv("RB200_INTRA_CTAS_PER_SM") ? atoi(getenv("RB200_INTRA_CTAS_PER_SM")) : 3;
+    // As many CTAs as fit (four per SM at 128 registers) unless RB200_INTRA_CTAS_PER_SM says otherwise, and never more
+    // than the widest level has items: the more CTAs on the ring, the more levels are prepared ahead.
+    static const int want = getenv("RB200_INTRA_CTAS_PER_SM") ? atoi(getenv("RB200_INTRA_CTAS_PER_SM")) : 4;
     int grid = imin(imax(want, 1), per_sm[hbd]) * n_sm;
     if (max_items_per_level > 0 && max_items_per_level < grid) grid = max_items_per_level;
     RB_CUDA(cudaMemsetAsync(d_sync, 0, ((size_t)n_levels + 1) * sizeof(unsigned), st));

@@ -455,6 +455,28 @@ def test_validate_names_bad_records(rb):
 
 
 @pytest.mark.gpu
+def test_validate_names_bad_intra_records(rb):
+    """rb200_frame_validate over the intra wavefront's records: mode, block size, origin and level."""
+    s = framegen.generate_intra(160, 128, 10, seed=3, inter_frac=0.2, ibc_frac=0.2)
+    d = framegen.DeviceFrame(s)
+    try:
+        d.load_batch(); d.set_ref_from_host(s.ref)
+        counts = (C.c_int32 * 19)(*[int(c) for c in s.itx_counts])
+        args = (d.h, s.n_coefs, counts, len(s.mc_items), R | rb.STAGE_INTRA)
+        assert rb.frame_validate(*args) == 0, rb.last_error()
+        items = rb.np_view(rb.frame_intra_items(d.h), rb.INTRA_ITEM_DT, len(s.intra_items))
+        for field, bad, word in (("mode", 17, b"mode"), ("tw4", 0, b"size"), ("th4", 17, b"size"), ("x4", 4000, b"outside plane"),
+                                 ("plane", 3, b"plane"), ("level", 0xffff, b"level")):
+            keep = items[field][5].copy()
+            items[field][5] = bad
+            assert rb.frame_validate(*args) != 0 and word in rb.last_error(), (field, rb.last_error())
+            items[field][5] = keep
+        assert rb.frame_validate(*args) == 0
+    finally:
+        d.close()
+
+
+@pytest.mark.gpu
 def test_resubmit_is_idempotent(rb, ref):
     """Submitting the same batch twice gives the same picture (recon overwrites, filters are
     out of place or restart from recon)."""
