@@ -10,6 +10,8 @@
 // dx * (y + 1) etc.  Filter-intra, the only predictor with a dependency inside the block, runs as a wavefront
 // over its 4x2 sub-blocks (a sub-block needs the ones to its left, above and above-left).
 #include "common.cuh"
+#include <cstdio>
+#include <vector>
 #include "tables.cuh"
 #include "itx_block.cuh"
 #include "wedge.cuh"
@@ -74,9 +76,20 @@ template <typename P>
 struct IpScratch {
     P e[IP_EDGE];             // the block's edge, topleft at e[IP_EC]
     P work[2 * IP_EC + 2];    // prepared edge of the directional modes
-    P tile[32 * 32];          // filter-intra block
+    P tile[33 * 33];          // filter-intra block with its top row / left column border; inter-intra prediction
     int dc;
+    // the predictors' tables, copied once per kernel (ip_load_tables): the level waits of the frame-level wavefront
+    // invalidate L1, and a table fetched from L2 after the wait would sit on the critical path of every level
+    uint8_t sm_w[128];
+    uint16_t dr[44];
+    int8_t flt[320];
 };
+template <typename P>
+__device__ __forceinline__ void ip_load_tables(IpScratch<P> &S) {      // followed by a __syncthreads of the caller
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) S.sm_w[i] = tab::k_sm_weights[i];
+    for (int i = threadIdx.x; i < 44; i += blockDim.x) S.dr[i] = tab::k_dr_intra_derivative[i];
+    for (int i = threadIdx.x; i < 320; i += blockDim.x) S.flt[i] = tab::k_filter_intra_taps[i];
+}
 
 // Predict one w x h block at dst8 from the edge in S.e (all threads of the CTA take part; S.e is complete and
 // visible on entry).  mode: IP_*; angle: the reference's packed argument.
@@ -89,7 +102,7 @@ __device__ void ipred_block(IpScratch<typename BD::pixel> &S, int mode, uint8_t 
     const int tid = threadIdx.x;
     const pixel *tl = S.e + IP_EC;
     auto put = [&](int x, int y, int v) { ((pixel *)(dst8 + (int64_t)y * stride))[x] = (pixel)v; };
-    const int n = w * h;
+    const int n = w * h, lw = 31 - __clz(w);       // block sizes are powers of two: no integer divisions on this path
 
     switch (mode) {
     case IP_DC: case IP_TOP_DC: case IP_LEFT_DC: case IP_DC_128: {
@@ -127,22 +140,22 @@ __device__ void ipred_block(IpScratch<typename BD::pixel> &S, int mode, uint8_t 
             for (int i = tid; i < n; i += blockDim.x) {
                 const int diff = cfl_alpha * cfl_ac[i];
                 const int m = (abs(diff) + 32) >> 6;
-                put(i % w, i / w, iclip(dc_s + (diff < 0 ? -m : m), 0, bdmax));
+                put((i & (w - 1)), (i >> lw), iclip(dc_s + (diff < 0 ? -m : m), 0, bdmax));
             }
         } else {
-            for (int i = tid; i < n; i += blockDim.x) put(i % w, i / w, dc_s);
+            for (int i = tid; i < n; i += blockDim.x) put((i & (w - 1)), (i >> lw), dc_s);
         }
         break;
     }
     case IP_VERT:
-        for (int i = tid; i < n; i += blockDim.x) put(i % w, i / w, tl[1 + i % w]);
+        for (int i = tid; i < n; i += blockDim.x) put((i & (w - 1)), (i >> lw), tl[1 + (i & (w - 1))]);
         break;
     case IP_HOR:
-        for (int i = tid; i < n; i += blockDim.x) put(i % w, i / w, tl[-(1 + i / w)]);
+        for (int i = tid; i < n; i += blockDim.x) put((i & (w - 1)), (i >> lw), tl[-(1 + (i >> lw))]);
         break;
     case IP_PAETH:
         for (int i = tid; i < n; i += blockDim.x) {
-            const int x = i % w, y = i / w;
+            const int x = (i & (w - 1)), y = (i >> lw);
             const int left = tl[-(y + 1)], top = tl[1 + x], topleft = tl[0];
             const int base = left + top - topleft;
             const int ld = abs(left - base), td = abs(top - base), tld = abs(topleft - base);
@@ -150,10 +163,10 @@ __device__ void ipred_block(IpScratch<typename BD::pixel> &S, int mode, uint8_t 
         }
         break;
     case IP_SMOOTH: case IP_SMOOTH_V: case IP_SMOOTH_H: {
-        const uint8_t *wh = tab::k_sm_weights + w, *wv = tab::k_sm_weights + h;
+        const uint8_t *wh = S.sm_w + w, *wv = S.sm_w + h;
         const int right = tl[w], bottom = tl[-h];
         for (int i = tid; i < n; i += blockDim.x) {
-            const int x = i % w, y = i / w;
+            const int x = (i & (w - 1)), y = (i >> lw);
             int v;
             if (mode == IP_SMOOTH)
                 v = (wv[y] * tl[1 + x] + (256 - wv[y]) * bottom + wh[x] * tl[-(1 + y)] + (256 - wh[x]) * right + 256) >> 9;
@@ -168,7 +181,7 @@ __device__ void ipred_block(IpScratch<typename BD::pixel> &S, int mode, uint8_t 
     case IP_Z1: {   // src/ipred_tmpl.c:408-460
         const int is_sm = (angle >> 9) & 1, eief = angle >> 10;
         angle &= 511;
-        int dx = tab::k_dr_intra_derivative[angle >> 1];
+        int dx = S.dr[angle >> 1];
         const int ups = eief ? ip_upsample(w + h, 90 - angle, is_sm) : 0;
         const pixel *top;
         int max_base_x;
@@ -187,7 +200,7 @@ __device__ void ipred_block(IpScratch<typename BD::pixel> &S, int mode, uint8_t 
         __syncthreads();
         const int inc = 1 + ups;
         for (int i = tid; i < n; i += blockDim.x) {
-            const int x = i % w, y = i / w;
+            const int x = (i & (w - 1)), y = (i >> lw);
             const int xpos = dx * (y + 1), frac = xpos & 0x3E, base = (xpos >> 6) + inc * x;
             put(x, y, base < max_base_x ? (top[base] * (64 - frac) + top[base + 1] * frac + 32) >> 6 : top[max_base_x]);
         }
@@ -196,7 +209,7 @@ __device__ void ipred_block(IpScratch<typename BD::pixel> &S, int mode, uint8_t 
     case IP_Z2: {   // src/ipred_tmpl.c:462-540
         const int is_sm = (angle >> 9) & 1, eief = angle >> 10;
         angle &= 511;
-        int dy = tab::k_dr_intra_derivative[(angle - 90) >> 1], dx = tab::k_dr_intra_derivative[(180 - angle) >> 1];
+        int dy = S.dr[(angle - 90) >> 1], dx = S.dr[(180 - angle) >> 1];
         const int ul = eief ? ip_upsample(w + h, 180 - angle, is_sm) : 0;
         const int ua = eief ? ip_upsample(w + h, angle - 90, is_sm) : 0;
         pixel *t2 = work + IP_EC;                 // the prepared corner: t2[0] = topleft
@@ -222,7 +235,7 @@ __device__ void ipred_block(IpScratch<typename BD::pixel> &S, int mode, uint8_t 
         const int incx = 1 + ua;
         const pixel *left = t2 - (1 + ul);
         for (int i = tid; i < n; i += blockDim.x) {
-            const int x = i % w, y = i / w;
+            const int x = (i & (w - 1)), y = (i >> lw);
             const int xpos = ((1 + ua) << 6) - dx * (y + 1);
             const int base_x = (xpos >> 6) + incx * x;
             int v;
@@ -241,7 +254,7 @@ __device__ void ipred_block(IpScratch<typename BD::pixel> &S, int mode, uint8_t 
     case IP_Z3: {   // src/ipred_tmpl.c:542-600
         const int is_sm = (angle >> 9) & 1, eief = angle >> 10;
         angle &= 511;
-        int dy = tab::k_dr_intra_derivative[(270 - angle) >> 1];
+        int dy = S.dr[(270 - angle) >> 1];
         const int ups = eief ? ip_upsample(w + h, angle - 180, is_sm) : 0;
         const pixel *left;
         int max_base_y;
@@ -260,15 +273,22 @@ __device__ void ipred_block(IpScratch<typename BD::pixel> &S, int mode, uint8_t 
         __syncthreads();
         const int inc = 1 + ups;
         for (int i = tid; i < n; i += blockDim.x) {
-            const int x = i % w, y = i / w;
+            const int x = (i & (w - 1)), y = (i >> lw);
             const int ypos = dy * (x + 1), frac = ypos & 0x3E, base = (ypos >> 6) + inc * y;
             put(x, y, base < max_base_y ? (left[-base] * (64 - frac) + left[-(base + 1)] * frac + 32) >> 6 : left[-max_base_y]);
         }
         break;
     }
     case IP_FILTER: {   // src/ipred_tmpl.c:618-655; up to 32x32
-        const int8_t *flt = tab::k_filter_intra_taps + (angle & 511) * 64;
+        const int8_t *flt = S.flt + (angle & 511) * 64 + (tid & 7);      // this thread's output of the 4x2 sub-block
+        const int f0 = flt[0], f1 = flt[8], f2 = flt[16], f3 = flt[24], f4 = flt[32], f5 = flt[40], f6 = flt[48];
         const int nbx = w >> 2, nby = h >> 1;
+        // the tile carries the edge as its row -1 / column -1, so the seven inputs of a sub-block are plain loads
+        constexpr int TS = 33;
+        pixel *tb = tile + TS + 1;                                     // (0, 0) of the block
+        for (int i = tid; i <= w; i += blockDim.x) tile[i] = tl[i];    // row -1: topleft, top
+        for (int i = tid; i < h; i += blockDim.x) tile[(i + 1) * TS] = tl[-(1 + i)];
+        __syncthreads();
         for (int t = 0; t < nbx + nby - 1; t++) {
             // sub-blocks on the anti-diagonal bx + by = t; 8 threads (outputs) per sub-block
             const int sb = tid >> 3, o = tid & 7;
@@ -276,20 +296,15 @@ __device__ void ipred_block(IpScratch<typename BD::pixel> &S, int mode, uint8_t 
                 const int bx = t - by;
                 if (bx < 0 || bx >= nbx) continue;
                 const int x0 = 4 * bx, y0 = 2 * by;
-                auto px = [&](int x, int y) -> int {   // reconstructed neighbourhood: the edge outside the block, the tile inside
-                    if (y < 0) return tl[1 + x];          // x = -1 gives topleft
-                    if (x < 0) return tl[-(1 + y)];
-                    return tile[y * 32 + x];
-                };
+                auto px = [&](int x, int y) -> int { return tb[y * TS + x]; };
                 const int p0 = px(x0 - 1, y0 - 1), p1 = px(x0, y0 - 1), p2 = px(x0 + 1, y0 - 1), p3 = px(x0 + 2, y0 - 1),
                           p4 = px(x0 + 3, y0 - 1), p5 = px(x0 - 1, y0), p6 = px(x0 - 1, y0 + 1);
-                const int acc = flt[o] * p0 + flt[8 + o] * p1 + flt[16 + o] * p2 + flt[24 + o] * p3 + flt[32 + o] * p4 +
-                                flt[40 + o] * p5 + flt[48 + o] * p6;
-                tile[(y0 + (o >> 2)) * 32 + x0 + (o & 3)] = (pixel)iclip((acc + 8) >> 4, 0, bdmax);
+                const int acc = f0 * p0 + f1 * p1 + f2 * p2 + f3 * p3 + f4 * p4 + f5 * p5 + f6 * p6;
+                tb[(y0 + (o >> 2)) * TS + x0 + (o & 3)] = (pixel)iclip((acc + 8) >> 4, 0, bdmax);
             }
             __syncthreads();
         }
-        for (int i = tid; i < n; i += blockDim.x) put(i % w, i / w, tile[(i / w) * 32 + i % w]);
+        for (int i = tid; i < n; i += blockDim.x) put((i & (w - 1)), (i >> lw), tb[((i >> lw)) * TS + (i & (w - 1))]);
         break;
     }
     default: break;
@@ -302,6 +317,7 @@ ipred_kernel(int mode, uint8_t *dst8, int64_t stride, const typename BD::pixel *
              int h, int angle, int max_w, int max_h, int bdmax) {
     __shared__ IpScratch<typename BD::pixel> S;
     for (int i = threadIdx.x; i < lo + hi + 1; i += blockDim.x) S.e[IP_EC - lo + i] = edge_in[i];
+    ip_load_tables(S);
     __syncthreads();
     ipred_block<BD>(S, mode, dst8, stride, w, h, angle, max_w, max_h, bdmax);
 }
@@ -323,6 +339,20 @@ struct IntraSmem {
 // Picture reads of the persistent kernel bypass L1 (CG): another SM wrote those pixels during this very launch.
 template <bool CG, typename T>
 __device__ __forceinline__ T pic_ld(const T *p) { return CG ? __ldcg(p) : *p; }
+
+// cfl_ac's sub-sampling sum of one output (src/ipred_tmpl.c:670-685): 1, 2 or 4 luma pixels
+template <bool CG, typename P>
+__device__ __forceinline__ int cfl_luma_sum(const uint8_t *ypx, int64_t lstride, int cx, int cy, int ss_hor, int ss_ver) {
+    const P *p = (const P *)(ypx + (int64_t)(cy << ss_ver) * lstride) + (cx << ss_hor);
+    int sum = pic_ld<CG>(&p[0]);
+    if (ss_hor) sum += pic_ld<CG>(&p[1]);
+    if (ss_ver) {
+        const P *q = (const P *)((const uint8_t *)p + lstride);
+        sum += pic_ld<CG>(&q[0]);
+        if (ss_hor) sum += pic_ld<CG>(&q[1]);
+    }
+    return sum;
+}
 
 // One intra item, all threads of the CTA.  `wait()` is called once, after everything that does not depend on the picture
 // (the item's set-up and the residual's transform) and before the first picture read: it returns when every item of the
@@ -406,8 +436,9 @@ __device__ __forceinline__ void intra_item(IntraSmem<typename BD::pixel> &M, con
             const uint8_t *rec = pal_buf + ((size_t)it.w4_end | (size_t)it.h4_end << 16) * 16;
             const pixel *pal = (const pixel *)rec;
             const uint8_t *idx = rec + 16;
+            const int lpw = 31 - __clz(tw * 4);
             for (int i = tid; i < tw * th * 16; i += blockDim.x)
-                ((pixel *)(dst8 + (int64_t)(i / (tw * 4)) * stride))[i % (tw * 4)] = pal[idx[i] & 7];
+                ((pixel *)(dst8 + (int64_t)((i >> lpw)) * stride))[(i & (tw * 4 - 1))] = pal[idx[i] & 7];
         }
         // 16: intra block copy (src/recon_tmpl.c:1631-1645): mc() with the bilinear filter from the picture being
         // reconstructed.  (int16) w4_end / h4_end = the source position in plane pixels, angle = mx | my << 4 in 1/16
@@ -423,9 +454,9 @@ __device__ __forceinline__ void intra_item(IntraSmem<typename BD::pixel> &M, con
                 xx = iclip(xx, 0, pw - 1); yy = iclip(yy, 0, ph - 1);
                 return (int)pic_ld<CG>((const pixel *)(sbase + (int64_t)yy * stride) + xx);
             };
-            const int bw = tw * 4, n = bw * th * 4;
+            const int bw = tw * 4, n = bw * th * 4, lbw = 31 - __clz(bw);
             for (int i = tid; i < n; i += blockDim.x) {
-                const int xx = sx + i % bw, yy = sy + i / bw;
+                const int xx = sx + (i & (bw - 1)), yy = sy + (i >> lbw);
                 int v;
                 if (mx) {
                     const int a = px(xx, yy), b = px(xx + 1, yy);
@@ -443,7 +474,7 @@ __device__ __forceinline__ void intra_item(IntraSmem<typename BD::pixel> &M, con
                 } else {
                     v = px(xx, yy);
                 }
-                ((pixel *)(dst8 + (int64_t)(i / bw) * stride))[i % bw] = (pixel)iclip(v, 0, bdmax);
+                ((pixel *)(dst8 + (int64_t)((i >> lbw)) * stride))[(i & (bw - 1))] = (pixel)iclip(v, 0, bdmax);
             }
         }
         if (ti < 0) return;
@@ -455,12 +486,25 @@ __device__ __forceinline__ void intra_item(IntraSmem<typename BD::pixel> &M, con
     // pixels, one per thread; all picture loads of a thread are issued back to back into registers (one global round
     // trip for the whole edge), then stored; only the replication of a missing extension waits for them.
     const int szl = th << 2, szt = tw << 2;
+    int cfl_first[2] = { 0, 0 };
     const int have_bl = (n_left && n_bl && have_left && y + th < h) ? left_has_bottom : 0;
     const int have_tr = (n_top && n_tr && have_top && x + tw < w) ? top_has_right : 0;
     {
         const bool ld_l = n_left && have_left && tid < szl, ld_t = n_top && have_top && tid < szt;
         const bool ld_bl = have_bl && tid < szl, ld_tr = have_tr && tid < szt;
         pixel r_l = 0, r_t = 0, r_bl = 0, r_tr = 0, r_fl = 0, r_ft = 0;
+        if (cfl) {
+            // chroma from luma: the block's own luma (this thread's first two outputs) in the same round trip as the edge
+            const int w_pad = it.w4_end >> 13, h_pad = it.h4_end >> 13;
+            const int cw = tw * 4, ch = th * 4, vw = cw - 4 * w_pad, vh = ch - 4 * h_pad, lcw = 31 - __clz(cw);
+            const int64_t lstride = plane_stride(cur, 0);
+            const uint8_t *ypx = plane_ptr(cur, 0) + (int64_t)((y << ss_ver) * 4) * lstride + (int64_t)((x << ss_hor) * 4) * sizeof(pixel);
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int i = tid + k * (int)blockDim.x;
+                if (i < cw * ch) cfl_first[k] = cfl_luma_sum<CG, pixel>(ypx, lstride, imin((i & (cw - 1)), vw - 1), imin((i >> lcw), vh - 1), ss_hor, ss_ver);
+            }
+        }
         if (ld_l) r_l = pic_ld<CG>(&dst[(int64_t)imin(tid, imin(szl, (h - y) << 2) - 1) * ps - 1]);
         if (ld_t) r_t = pic_ld<CG>(&dst_top[imin(tid, imin(szt, (w - x) << 2) - 1)]);
         if (ld_bl) r_bl = pic_ld<CG>(&dst[(int64_t)(szl + imin(tid, imin(szl, (h - y - th) << 2) - 1)) * ps - 1]);
@@ -499,20 +543,12 @@ __device__ __forceinline__ void intra_item(IntraSmem<typename BD::pixel> &M, con
         // cfl_ac (src/ipred_tmpl.c:657-703) on the block's reconstructed luma; the padding counts ride in the top bits
         // of w4_end / h4_end
         const int w_pad = it.w4_end >> 13, h_pad = it.h4_end >> 13;
-        const int cw = tw * 4, ch = th * 4, vw = cw - 4 * w_pad, vh = ch - 4 * h_pad;
+        const int cw = tw * 4, ch = th * 4, vw = cw - 4 * w_pad, vh = ch - 4 * h_pad, lcw = 31 - __clz(cw);
         const int64_t lstride = plane_stride(cur, 0);
         const uint8_t *ypx = plane_ptr(cur, 0) + (int64_t)((y << ss_ver) * 4) * lstride + (int64_t)((x << ss_hor) * 4) * sizeof(pixel);
         int part = 0;
-        for (int i = tid; i < cw * ch; i += blockDim.x) {
-            const int cx = imin(i % cw, vw - 1), cy = imin(i / cw, vh - 1);
-            const pixel *p = (const pixel *)(ypx + (int64_t)(cy << ss_ver) * lstride) + (cx << ss_hor);
-            int sum = pic_ld<CG>(&p[0]);
-            if (ss_hor) sum += pic_ld<CG>(&p[1]);
-            if (ss_ver) {
-                const pixel *q = (const pixel *)((const uint8_t *)p + lstride);
-                sum += pic_ld<CG>(&q[0]);
-                if (ss_hor) sum += pic_ld<CG>(&q[1]);
-            }
+        for (int i = tid, k = 0; i < cw * ch; i += blockDim.x, k++) {
+            int sum = k == 0 ? cfl_first[0] : (k == 1 ? cfl_first[1] : cfl_luma_sum<CG, pixel>(ypx, lstride, imin((i & (cw - 1)), vw - 1), imin((i >> lcw), vh - 1), ss_hor, ss_ver));
             sum <<= 1 + !ss_ver + !ss_hor;
             ac_s[i] = (int16_t)sum;
             part += sum;
@@ -524,18 +560,27 @@ __device__ __forceinline__ void intra_item(IntraSmem<typename BD::pixel> &M, con
         const int mean = (((1 << log2sz) >> 1) + red_s[0] + red_s[1] + red_s[2] + red_s[3]) >> log2sz;
         for (int i = tid; i < cw * ch; i += blockDim.x) ac_s[i] = (int16_t)(ac_s[i] - mean);
         __syncthreads();
+        if (ti >= 0 && res_plane == it.plane && res_x == x * 4 && res_y == y * 4 && res_w == cw && res_h == ch) {
+            // with a residual over the whole block: prediction into shared memory, one write (as for the plain modes below)
+            pixel *pred = reinterpret_cast<pixel *>(itile);
+            ipred_block<BD>(S, mode, (uint8_t *)pred, (int64_t)cw * sizeof(pixel), cw, ch, 0, max_w, max_h, bdmax, ac_s, it.angle);
+            __syncthreads();
+            for (int i = tid; i < cw * ch; i += blockDim.x)
+                ((pixel *)(dst8 + (int64_t)(i >> lcw) * stride))[i & (cw - 1)] = (pixel)iclip((int)pred[i] + res_s[i], 0, bdmax);
+            return;
+        }
         ipred_block<BD>(S, mode, dst8, stride, cw, ch, 0, max_w, max_h, bdmax, ac_s, it.angle);
     } else if (inter_intra) {
         // inter-intra (src/recon.rs:3475-3550, chroma :3742-3850): the intra prediction of the whole block goes into shared
         // memory and is blended over the inter prediction already in the picture, with the inter-intra mask of the
         // mode (it.angle < 0) or a wedge mask (it.angle = wedge index)
-        const int bw = tw * 4, bh = th * 4;
+        const int bw = tw * 4, bh = th * 4, lbw = 31 - __clz(bw);
         ipred_block<BD>(S, mode, (uint8_t *)S.tile, (int64_t)bw * sizeof(pixel), bw, bh, 0, 0, 0, bdmax);
         __syncthreads();
         const int ii_mode = it.mode == 9 ? 3 : it.mode;          // SMOOTH_PRED is II_SMOOTH_PRED
         const int lw = bw << ss_hor, lh = bh << ss_ver;            // the luma block the wedge is defined on
         for (int i = tid; i < bw * bh; i += blockDim.x) {
-            const int px = i % bw, py = i / bw;
+            const int px = (i & (bw - 1)), py = (i >> lbw);
             int m;
             if (it.angle < 0) {
                 m = ii_mask_at(bw, bh, ii_mode, px, py);
@@ -582,6 +627,8 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
                    int frame_w4, int frame_h4, int ss_hor_c, int ss_ver_c, int bdmax) {
     __shared__ IntraSmem<typename BD::pixel> M;
     asm volatile("griddepcontrol.launch_dependents;");
+    ip_load_tables(M.S);
+    __syncthreads();
     intra_item<BD, false>(M, cur, items[blockIdx.x], itx_of ? itx_of[blockIdx.x] : -1, itx, cf, pal_buf, frame_w4, frame_h4, ss_hor_c,
                           ss_ver_c, bdmax, [] { asm volatile("griddepcontrol.wait;" ::: "memory"); });
 }
@@ -594,21 +641,28 @@ intra_items_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, co
 // ones).  CTAs without an item in a level neither wait nor count.  Between its items a CTA already transforms the
 // residual of the next one.  Saves the launch gap per level and ~2,600 host launches per 4K key frame.
 // sync[0] = set if a wait ever ran into its time limit (a bug, not a state: reported by rb200_frame_wait), sync[1 + l] = done[l].
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 template <typename BD>
 __global__ void __launch_bounds__(128)
 intra_levels_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, const int32_t *__restrict__ itx_of,
                     const Rb200ItxItem *__restrict__ itx, const typename BD::coef *__restrict__ cf, const uint8_t *__restrict__ pal_buf,
                     const int32_t *__restrict__ level_off, int n_levels, int frame_w4, int frame_h4, int ss_hor_c, int ss_ver_c,
-                    int bdmax, unsigned *sync) {
+                    int bdmax, unsigned *sync, unsigned long long *trace) {
     __shared__ IntraSmem<typename BD::pixel> M;
     __shared__ int abort_s;
     const int tid = threadIdx.x;
     unsigned *done = sync + 1;
     if (tid == 0) abort_s = 0;
+    ip_load_tables(M.S);
     __syncthreads();
     for (int l = 0; l < n_levels; l++) {
         const int beg = level_off[l], end = level_off[l + 1];
         bool waited = false;
+        int cur_i = 0;
         auto level_wait = [&] {
             if (waited || l == 0) return;
             waited = true;
@@ -616,13 +670,16 @@ intra_levels_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, c
                 const unsigned target = (unsigned)(beg - level_off[l - 1]);
                 const long long t0 = clock64();
                 unsigned seen;
+                // a wait that runs into its time limit (a bug, not a state) ends this CTA; the CTAs that depend on it run
+                // into their own limit at about the same time, so the flag is not polled on the way
+                // relaxed polls and ONE acquire fence at the end: an acquire load is LDG + CCTL.IVALL, i.e. every turn of the
+                // loop would empty the L1 of an SM whose other CTAs are fetching their next items
                 do {
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(done + l - 1) : "memory");
-                    if (seen < target && clock64() - t0 > 4000000000LL) { atomicExch(sync, 1u); break; }
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(done + l - 1) : "memory");
+                    if (seen < target && clock64() - t0 > 4000000000LL) { atomicExch(sync, 1u); abort_s = 1; break; }
                 } while (seen < target);
-                unsigned bad;
-                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(bad) : "l"(sync) : "memory");
-                if (bad) abort_s = 1;
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                if (trace) trace[2 * cur_i] = global_ns();      // RB200_INTRA_TRACE: when this item saw its level released ...
             }
             __syncthreads();
         };
@@ -634,13 +691,17 @@ intra_levels_kernel(Rb200Planes cur, const Rb200IntraItem *__restrict__ items, c
         int first = (int)blockIdx.x - beg % G;
         if (first < 0) first += G;
         for (int i = beg + first; i < end; i += G) {
+            cur_i = i;
             intra_item<BD, true>(M, cur, items[i], itx_of ? itx_of[i] : -1, itx, cf, pal_buf, frame_w4, frame_h4, ss_hor_c, ss_ver_c, bdmax,
                                  level_wait);
             __syncthreads();            // the item is in the picture (as far as this CTA is concerned) and its shared memory is free
             if (abort_s) return;
             // release at gpu scope, cumulative over the barrier above: every thread's stores of this item are visible to
             // whoever acquires the counter -- no separate fence
-            if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(done + l) : "memory");
+            if (tid == 0) {
+                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(done + l) : "memory");
+                if (trace) trace[2 * i + 1] = global_ns();          // ... and when it had released its own
+            }
         }
     }
 }
@@ -685,13 +746,31 @@ int intra_levels_launch(const Rb200Planes &cur, const Rb200IntraItem *d_items, c
     int grid = imin(imax(want, 1), per_sm[hbd]) * n_sm;
     if (max_items_per_level > 0 && max_items_per_level < grid) grid = max_items_per_level;
     RB_CUDA(cudaMemsetAsync(d_sync, 0, ((size_t)n_levels + 1) * sizeof(unsigned), st));
+    // RB200_INTRA_TRACE=<file> (a debugging aid): two time stamps per item -- level seen released, own release done -- written
+    // to <file> after the launch (tools/intra_trace.py reads it)
+    static const char *trace_path = getenv("RB200_INTRA_TRACE");
+    unsigned long long *d_trace = nullptr;
+    int32_t n_items_total = 0;
+    if (trace_path) {
+        RB_CUDA(cudaStreamSynchronize(st));
+        RB_CUDA(cudaMemcpy(&n_items_total, d_level_off + n_levels, sizeof(int32_t), cudaMemcpyDeviceToHost));
+        RB_CUDA(cudaMalloc(&d_trace, (size_t)n_items_total * 16));
+        RB_CUDA(cudaMemsetAsync(d_trace, 0, (size_t)n_items_total * 16, st));
+    }
     const int32_t *cf32 = (const int32_t *)cf; const int16_t *cf16 = (const int16_t *)cf;
     Rb200Planes cur_v = cur;
-    void *args16[] = { &cur_v, &d_items, &d_itx_of, &d_itx, &cf32, &d_pal, &d_level_off, &n_levels, &frame_w4, &frame_h4, &ss_hor, &ss_ver, &bdmax, &d_sync };
-    void *args8[] = { &cur_v, &d_items, &d_itx_of, &d_itx, &cf16, &d_pal, &d_level_off, &n_levels, &frame_w4, &frame_h4, &ss_hor, &ss_ver, &bdmax, &d_sync };
+    void *args16[] = { &cur_v, &d_items, &d_itx_of, &d_itx, &cf32, &d_pal, &d_level_off, &n_levels, &frame_w4, &frame_h4, &ss_hor, &ss_ver, &bdmax, &d_sync, &d_trace };
+    void *args8[] = { &cur_v, &d_items, &d_itx_of, &d_itx, &cf16, &d_pal, &d_level_off, &n_levels, &frame_w4, &frame_h4, &ss_hor, &ss_ver, &bdmax, &d_sync, &d_trace };
     if (hbd) RB_CUDA(cudaLaunchCooperativeKernel((const void *)intra_levels_kernel<BD16>, dim3(grid), dim3(128), args16, 0, st));
     else RB_CUDA(cudaLaunchCooperativeKernel((const void *)intra_levels_kernel<BD8>, dim3(grid), dim3(128), args8, 0, st));
     RB_LAUNCH_CHECK();
+    if (d_trace) {
+        std::vector<unsigned long long> h((size_t)n_items_total * 2);
+        RB_CUDA(cudaStreamSynchronize(st));
+        RB_CUDA(cudaMemcpy(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost));
+        RB_CUDA(cudaFree(d_trace));
+        if (FILE *fp = fopen(trace_path, "wb")) { fwrite(h.data(), 8, h.size(), fp); fclose(fp); }
+    }
     return 0;
 }
 
