@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from concurrent.futures import ThreadPoolExecutor
 import sweep_conformance as sw
 
-MAX_BYTES = 40000
+MAX_BYTES = 100000
 OUT = os.path.join(sw.ROOT, "tests", "golden", "conformance")
 
 if __name__ == "__main__":
